@@ -1,0 +1,173 @@
+/*
+ * phylomap_b200 — C ABI of the B200-native stochastic-mapping MCMC core.
+ *
+ * This is the drop-in boundary for the hot path of vnminin/phylomap: the seven uniformization samplers that
+ * the reference exports to R through Rcpp (`.Call('phylomap_<fn>', ...)`, reference src/RcppExports.cpp).
+ * Every pm_maketreelist* entry below replaces exactly one `[[Rcpp::export]]` function of the reference
+ * src/phylomap.cpp; arguments keep the reference's meaning, order and 1-based conventions, flattened from
+ * R objects to plain pointers (INTEGRATION.md shows the Rcpp shim that does the flattening).
+ *
+ *   pm_SPARSEmaketreelistMCMC   <- SPARSEmaketreelistMCMC   src/phylomap.cpp:822  (src/RcppExports.cpp:11)
+ *   pm_maketreelistMCMC         <- maketreelistMCMC         src/phylomap.cpp:891  (src/RcppExports.cpp:34)
+ *   pm_maketreelistMCMC_bigtree <- maketreelistMCMC_bigtree src/phylomap.cpp:942  (src/RcppExports.cpp:57)
+ *   pm_maketreelistMCMCbf       <- maketreelistMCMCbf       src/phylomap.cpp:1258 (src/RcppExports.cpp:106)
+ *   pm_maketreelistMCMCks       <- maketreelistMCMCks       src/phylomap.cpp:1802 (src/RcppExports.cpp:132)
+ *   pm_maketreelistMCMCmt       <- maketreelistMCMCmt       src/phylomap.cpp:2267 (src/RcppExports.cpp:159)
+ *   pm_maketreelistMCMCksmt     <- maketreelistMCMCksmt     src/phylomap.cpp:2722 (src/RcppExports.cpp:185)
+ *   pm_tree_order               <- pruningwiseedgeorder / makenodelist / myreorder, R/sumstatMCMC.R:1-18 (O(E) here)
+ *
+ * There is no CPU fallback: every entry fails with PM_ERR_CUDA when no sm_100 device is usable.
+ *
+ * New with respect to the reference: a data-parallel SITE axis.  `states` may hold n_sites tip-state vectors
+ * (site-major).  All sites share the tree, the initial segmentation (`maps`) and Q; each site is an independent
+ * copy of the reference's chain; row i of the result holds the SUM over sites of the per-site statistics
+ * (this is what the conjugate rate updates consume); per-site columns (root state) report global site 0.
+ * n_sites == 1 reproduces the reference's call.
+ */
+#ifndef PHYLOMAP_B200_H
+#define PHYLOMAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_OK 0
+#define PM_ERR_ARG 1        /* malformed input (message in err) */
+#define PM_ERR_CUDA 2       /* CUDA runtime failure / no usable device */
+#define PM_ERR_SAMPLE 3     /* RcppArmadillo::sample would have thrown (NA / negative / all-zero weights) */
+#define PM_ERR_CAPACITY 4   /* a per-branch capacity was exceeded and could not be grown */
+#define PM_ERR_REPLAY 5     /* replay table exhausted */
+
+/* precision of the device arithmetic */
+#define PM_F64 0
+#define PM_F32 1
+/* arithmetic mode */
+#define PM_MODE_PRODUCTION 0     /* fast: fused multiply-add allowed, B^k tables, -log(u) exponentials */
+#define PM_MODE_DETERMINISTIC 1  /* reference order of operations, no FMA, R's exp_rand, sorted categorical draw */
+/* source of uniforms for the device-side draws */
+#define PM_RNG_PHILOX 0          /* Philox4x32-10 keyed by (seed, site, iteration, slot, k) */
+#define PM_RNG_TABLE 1           /* replay of a uniform stream exported from a sequential (R-order) run */
+
+/* One tree in the reference's tweaked ape/phytools layout (fields read at src/phylomap.cpp:896-910). */
+typedef struct pm_tree {
+  int32_t n_tips;            /* T = length(x$states); tips are nodes 1..T, internal nodes T+1..2T-1 */
+  int32_t n_edges;           /* E = nrow(x$edge) = 2T-2 (binary trees only, as the reference: :508-510) */
+  const int32_t* edge;       /* x$edge, column-major [2E]: E parents then E children, 1-based */
+  const int32_t* nen;        /* [E] pruning-wise edge order, 1-based edge rows, sibling pairs adjacent */
+  const int32_t* nodelist;   /* [T-2] internal nodes below the root, top-down, 1-based */
+  int32_t root;              /* 1-based root node */
+  const int64_t* maps_off;   /* [E+1] CSR offsets into maps_len / maps_state */
+  const double* maps_len;    /* x$maps: initial segment lengths of every branch */
+  const int32_t* maps_state; /* x$mapnames (1-based); validated only — every sweep redraws all segment states */
+  const int32_t* states;     /* x$states, 1-based, [n_sites][T] site-major; may be NULL if states_u8 is given */
+  const uint8_t* states_u8;  /* optional compact alternative to `states` (same values, same layout) */
+  int64_t n_sites;           /* S (1 = the reference) */
+} pm_tree;
+
+/* Called once per iteration by the rate-updating samplers (bf/ks/mt/ksmt) when the sites are sharded over
+ * several processes: must sum `count` doubles at DEVICE address `dev_buf` across all ranks, in stream order on
+ * the stream given in pm_options.cuda_stream (e.g. ncclAllReduce / torch.distributed.all_reduce).  Return 0. */
+typedef int (*pm_allreduce_fn)(void* ctx, double* dev_buf, int32_t count);
+
+typedef struct pm_options {
+  int32_t device;          /* CUDA device ordinal */
+  int32_t precision;       /* PM_F64 | PM_F32 */
+  int32_t mode;            /* PM_MODE_PRODUCTION | PM_MODE_DETERMINISTIC */
+  int32_t rng;             /* PM_RNG_PHILOX | PM_RNG_TABLE */
+  uint64_t seed;           /* Philox key; host-side rate-update draws use R's Mersenne-Twister set.seed((uint32)seed) */
+  int64_t site_offset;     /* global index of local site 0 (site sharding); keys use global site indices */
+  int32_t path_capacity;   /* merged-path segments kept per (branch, site); 0 = default (8) */
+  int32_t power_capacity;  /* initial number of tabulated powers of B; 0 = default (64); grows on demand */
+  const int64_t* tab_off;  /* PM_RNG_TABLE: CSR over slots ((tree*S+site)*N+iter)*(2T-1+2E) + slot */
+  const double* tab_u;     /*               the uniforms */
+  const double* host_tab;  /*               uniforms consumed by the host-side rate updates, in order */
+  int64_t host_tab_n;
+  pm_allreduce_fn allreduce; /* NULL = single process */
+  void* allreduce_ctx;
+  void* cuda_stream;       /* cudaStream_t to launch on; NULL = a private stream */
+  int32_t progress;        /* non-zero: print "%i \r" per iteration like the reference (:930) */
+  int32_t reserved;
+} pm_options;
+
+void pm_default_options(pm_options* o);
+
+/* Fixed-Q samplers.  out: caller-owned, column-major [N x (n + n(n-1))]:
+ * [R_0..R_{n-1}, N_{0->1}, N_{0->2}, ... (diagonal skipped) ..., N_{n-1->n-2}]  (man/sumstatMCMC.Rd:18). */
+int pm_maketreelistMCMC(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega,
+                        int32_t N, const pm_options* opt, double* out, char* err, size_t errlen);
+int pm_SPARSEmaketreelistMCMC(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega,
+                              int32_t N, const pm_options* opt, double* out, char* err, size_t errlen);
+int pm_maketreelistMCMC_bigtree(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega,
+                                int32_t N, const pm_options* opt, double* out, char* err, size_t errlen);
+
+/* Rate-updating samplers.  Q and B (column-major n x n) are updated IN PLACE like the reference does
+ * (B2 aliases B: src/phylomap.cpp:1284).  out column layouts:
+ *   bf   [N x 9]             t0 t1 n00 n01 n10 n11 l01 l10 root          (R/sumstatMCMCbf.R:33)
+ *   ks   [N x n+n^2+2+3k+1]  R(n) N(n x n row-major) l01 l10 rk(k) lk(k) gamma(k) root   (src/phylomap.cpp:1789-1795)
+ *   mt   [N x 9]             as bf, last column = 0-based index of the tree recorded    (R/sumstatMCMCmt.R:39)
+ *   ksmt                     as ks, last column = tree index                             (src/phylomap.cpp:2828)
+ * prior: bf/mt 4 values, ks 6, ksmt 8 (man/sumstatMCMCbf.Rd:16, man/sumstatMCMCks.Rd:16, man/sumstatMCMCksmt.Rd:16). */
+int pm_maketreelistMCMCbf(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega,
+                          int32_t N, const double* prior, int32_t nprior, const pm_options* opt, double* out,
+                          char* err, size_t errlen);
+int pm_maketreelistMCMCks(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega,
+                          int32_t N, const double* prior, int32_t nprior, const pm_options* opt, double* out,
+                          char* err, size_t errlen);
+int pm_maketreelistMCMCmt(const pm_tree* trees, int32_t ntrees, int32_t n, double* Q, const double* pid, double* B,
+                          double Omega, int32_t N, const double* prior, int32_t nprior, const pm_options* opt,
+                          double* out, char* err, size_t errlen);
+int pm_maketreelistMCMCksmt(const pm_tree* trees, int32_t ntrees, int32_t n, double* Q, const double* pid, double* B,
+                            double Omega, int32_t N, const double* prior, int32_t nprior, const pm_options* opt,
+                            double* out, char* err, size_t errlen);
+
+/* Number of result columns of a variant (PM_V_*) for n states. */
+#define PM_V_PLAIN 0
+#define PM_V_SPARSE 1
+#define PM_V_BIGTREE 2
+#define PM_V_BF 3
+#define PM_V_KS 4
+#define PM_V_MT 5
+#define PM_V_KSMT 6
+int32_t pm_ncols(int32_t variant, int32_t n);
+
+/* O(E) replacement of the R helpers pruningwiseedgeorder / makenodelist / myreorder (R/sumstatMCMC.R:1-18):
+ * a valid pruning-wise edge order (children before parents, sibling pairs adjacent), the top-down list of the
+ * internal nodes below the root, and the root.  edge: column-major [2E], 1-based. */
+int pm_tree_order(const int32_t* edge, int32_t n_edges, int32_t n_tips, int32_t* nen, int32_t* nodelist,
+                  int32_t* root, char* err, size_t errlen);
+
+/* ---- Resident-chain interface (what the one-call entries are built from; used by benchmarks and tests) ---- */
+typedef struct pm_chain pm_chain;
+
+int pm_chain_create(int32_t variant, const pm_tree* trees, int32_t ntrees, int32_t n, double* Q, const double* pid,
+                    double* B, double Omega, const double* prior, int32_t nprior, int32_t N_total,
+                    const pm_options* opt, pm_chain** out, char* err, size_t errlen);
+/* Run `count` further iterations; rows [first .. first+count) of `out` (column-major, leading dimension ld)
+ * are written.  first must equal the number of iterations already done. */
+int pm_chain_run(pm_chain* c, int32_t count, double* out, int64_t ld, char* err, size_t errlen);
+/* Launch `reps` pruning passes (kernel K1 only) on the current chain state; returns the mean milliseconds per pass
+ * measured with CUDA events on the chain's stream.  Does not modify the chain. */
+int pm_chain_time_prune(pm_chain* c, int32_t tree, int32_t reps, float* ms_per_pass, char* err, size_t errlen);
+/* Per-kernel CUDA-event times (ms) accumulated since creation: [prune, sample_nodes, resample_paths, reduce], and
+ * the number of kernel launches issued. */
+void pm_chain_kernel_times(pm_chain* c, double ms[4], int64_t* launches);
+void pm_chain_enable_timing(pm_chain* c, int32_t on);
+/* State after the last sweep, copied to host (for parity tests). */
+int pm_chain_get_node_states(pm_chain* c, int32_t tree, int32_t* out /* [S][2T-1] 0-based */);
+int pm_chain_get_piece_counts(pm_chain* c, int32_t tree, int32_t* out /* [S][E] */);
+int pm_chain_get_path(pm_chain* c, int32_t tree, int64_t site, int32_t e, double* len, int32_t* st, int32_t cap);
+int pm_chain_get_partials(pm_chain* c, int32_t tree, int64_t site, double* out /* [2T-1][n], tip rows zero */);
+int64_t pm_chain_device_bytes(pm_chain* c);
+void pm_chain_destroy(pm_chain* c);
+
+/* Library / device probe: returns the number of CUDA devices with compute capability 10.x, or a negative error. */
+int pm_device_count(void);
+const char* pm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,295 @@
+// Device-side building blocks of the B200 stochastic-mapping sampler: arithmetic policy, keyed uniform
+// streams (Philox4x32-10 / replay table), R-compatible exponential deviate, categorical draws and the
+// small-matrix helpers.  Everything here is header-only and templated on
+//   Real   : float | double            (precision of partials, path lengths, weights)
+//   NS     : 2 | 4 | 0                 (compile-time state count; 0 = run-time n <= PM_NMAX)
+//   EXACT  : deterministic mode        (reference order of operations, no FMA, R's exp_rand, sorted draw)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define PM_NMAX 32           // largest state count (generic path)
+#define PM_LOCAL_PATH_MAX 64 // largest merged-path capacity per (branch, site)
+#define PM_SMEM_POW 8        // powers of B kept in shared memory (fast mode, NS <= 4)
+
+// device-side error bits (sticky, OR-ed into ChainParams::err_flag)
+#define PM_DE_SAMPLE_NA 1u
+#define PM_DE_SAMPLE_NEG 2u
+#define PM_DE_SAMPLE_ZERO 4u
+#define PM_DE_PATH_CAP 8u
+#define PM_DE_M_OVERFLOW 16u
+#define PM_DE_REPLAY 32u
+#define PM_DE_INCONSISTENT 64u
+
+namespace pm {
+
+// ------------------------------------------------------------------------------------------------
+// Arithmetic policy.  EXACT pins every product and sum to a separately rounded IEEE operation so the result
+// is the one an x86-64 build of the reference (no FMA contraction) computes.
+// ------------------------------------------------------------------------------------------------
+template <typename Real, bool EXACT> struct Ar;
+template <> struct Ar<double, true> {
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+template <> struct Ar<float, true> {
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+template <typename Real> struct Ar<Real, false> {
+  static __device__ __forceinline__ Real mul(Real a, Real b) { return a * b; }
+  static __device__ __forceinline__ Real add(Real a, Real b) { return a + b; }
+  static __device__ __forceinline__ Real sub(Real a, Real b) { return a - b; }
+  static __device__ __forceinline__ Real div(Real a, Real b) { return a / b; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw; SC'11).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t o[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+enum SlotKind : uint32_t { K_NODE = 0, K_BRSTATE = 1, K_BREXP = 2 };
+__device__ __forceinline__ uint32_t make_slot(uint32_t kind, uint32_t idx) { return (kind << 28) | idx; }
+
+// Description of where uniforms come from (per launch).
+struct RngDesc {
+  uint32_t k0, k1;        // Philox key (per tree)
+  uint32_t site0;         // global index of local site 0
+  const int64_t* tab_off; // replay table (device), or nullptr
+  const double* tab_u;
+  int64_t tab_site_stride;  // N * slots_per_iter
+  int64_t tab_base;         // tree * S_global * N * slots_per_iter
+  int32_t slots_per_iter;   // 2T-1 + 2E
+  int32_t n_nodes;          // 2T-1
+};
+
+// 53-bit uniforms strictly inside (0,1), two per Philox block; optionally replayed from a table.
+struct StreamD {
+  uint32_t k0, k1, site, iter, slot, k;
+  uint32_t o[4];
+  const double* tab; int64_t tab_n; unsigned* err;
+  __device__ __forceinline__ void open(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t kind, uint32_t idx,
+                                      unsigned* err_flag) {
+    k0 = d.k0; k1 = d.k1; site = d.site0 + local_site; iter = it; slot = make_slot(kind, idx); k = 0; err = err_flag;
+    tab = nullptr; tab_n = 0;
+    if (d.tab_u) {
+      int64_t lin = d.tab_base + (int64_t)site * d.tab_site_stride + (int64_t)it * d.slots_per_iter +
+                    (kind == K_NODE ? (int64_t)idx : (int64_t)d.n_nodes + 2 * (int64_t)idx + (kind - 1));
+      int64_t a = d.tab_off[lin], b = d.tab_off[lin + 1];
+      tab = d.tab_u + a; tab_n = b - a;
+    }
+  }
+  __device__ __forceinline__ double next() {
+    double u;
+    if (tab) {
+      if ((int64_t)k >= tab_n) { atomicOr(err, PM_DE_REPLAY); u = 0.5; } else u = tab[k];
+    } else {
+      if ((k & 1u) == 0u) philox4x32_10(k >> 1, slot, iter, site, k0, k1, o);
+      uint32_t hi = (k & 1u) ? o[2] : o[0], lo = (k & 1u) ? o[3] : o[1];
+      unsigned long long bits = ((unsigned long long)hi << 21) | (unsigned long long)(lo >> 11);
+      u = ((double)bits + 0.5) * (1.0 / 9007199254740992.0);
+    }
+    k++;
+    return u;
+  }
+};
+
+// 24-bit uniforms strictly inside (0,1), four per Philox block (production, float).
+struct StreamF {
+  uint32_t k0, k1, site, iter, slot, k;
+  uint32_t o[4];
+  __device__ __forceinline__ void open(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t kind, uint32_t idx,
+                                      unsigned*) {
+    k0 = d.k0; k1 = d.k1; site = d.site0 + local_site; iter = it; slot = make_slot(kind, idx); k = 0;
+  }
+  __device__ __forceinline__ float next() {
+    if ((k & 3u) == 0u) philox4x32_10(k >> 2, slot, iter, site, k0, k1, o);
+    uint32_t x = o[k & 3u];
+    k++;
+    return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  }
+};
+
+template <typename Real, bool EXACT> struct StreamSel { typedef StreamD type; };
+template <> struct StreamSel<float, false> { typedef StreamF type; };
+
+// ------------------------------------------------------------------------------------------------
+// Standard exponential deviate.
+//  EXACT: R's exp_rand (sexp.c, Ahrens & Dieter 1972) on the keyed stream — variable uniform consumption.
+//  fast : -log(u), one uniform.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double exp_rand_R(StreamD& g) {
+  const double q[16] = {0.6931471805599453, 0.9333736875190459, 0.9888777961838675, 0.9984589039328340,
+                        0.9998292811061389, 0.9999833164100727, 0.9999985691438767, 0.9999998906925558,
+                        0.9999999924734159, 0.9999999995283275, 0.9999999999728814, 0.9999999999985598,
+                        0.9999999999999289, 0.9999999999999968, 0.9999999999999999, 1.0000000000000000};
+  double a = 0.;
+  double u = g.next();
+  while (u <= 0. || u >= 1.) u = g.next();
+  for (;;) {
+    u = __dadd_rn(u, u);
+    if (u > 1.) break;
+    a = __dadd_rn(a, q[0]);
+  }
+  u = __dsub_rn(u, 1.);
+  if (u <= q[0]) return __dadd_rn(a, u);
+  int i = 0;
+  double ustar = g.next(), umin = ustar;
+  do {
+    ustar = g.next();
+    if (umin > ustar) umin = ustar;
+    i++;
+  } while (u > q[i]);
+  return __dadd_rn(a, __dmul_rn(umin, q[0]));
+}
+
+template <typename Real, bool EXACT> struct ExpDev;
+template <> struct ExpDev<double, true> {
+  static __device__ __forceinline__ double draw(StreamD& g) { return exp_rand_R(g); }
+};
+template <> struct ExpDev<double, false> {
+  static __device__ __forceinline__ double draw(StreamD& g) { return -log(g.next()); }
+};
+template <> struct ExpDev<float, false> {
+  static __device__ __forceinline__ float draw(StreamF& g) { return -logf(g.next()); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Categorical draw.
+//  EXACT: RcppArmadillo::sample(sts, 1, TRUE, w): FixProb (validate, divide by the sum of the positive entries),
+//         descending insertion sort carrying indices (ties keep index order), cumsum, first j < n-1 with u <= c[j].
+//  fast : inverse CDF on the unsorted weights.
+// ------------------------------------------------------------------------------------------------
+template <typename Real, int NC, bool EXACT, typename U>
+__device__ __forceinline__ int categorical(const Real* w, int n, U u, unsigned* err) {
+  if (EXACT) {
+    Real sum = 0; int npos = 0; unsigned bad = 0;
+#pragma unroll
+    for (int i = 0; i < NC; i++) if (i < n) {
+      Real v = w[i];
+      if (!isfinite(v)) bad |= PM_DE_SAMPLE_NA;
+      else if (v < (Real)0) bad |= PM_DE_SAMPLE_NEG;
+      if (v > (Real)0) { npos++; sum = Ar<Real, true>::add(sum, v); }
+    }
+    if (npos == 0) bad |= PM_DE_SAMPLE_ZERO;
+    if (bad) { atomicOr(err, bad); return 0; }
+    Real p[NC]; int perm[NC];
+#pragma unroll
+    for (int i = 0; i < NC; i++) { p[i] = (i < n) ? Ar<Real, true>::div(w[i], sum) : (Real)-1; perm[i] = i; }
+    // insertion sort, descending, stable: fixed compare-exchange pattern (a non-swap leaves a sorted prefix alone)
+#pragma unroll
+    for (int i = 1; i < NC; i++) {
+#pragma unroll
+      for (int j = i; j >= 1; j--) {
+        if (i < n && p[j] > p[j - 1]) {
+          Real tp = p[j]; p[j] = p[j - 1]; p[j - 1] = tp;
+          int ti = perm[j]; perm[j] = perm[j - 1]; perm[j - 1] = ti;
+        }
+      }
+    }
+    Real c = 0;
+    int pick = -1, last = 0;
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+      if (j < n - 1) {
+        c = (j == 0) ? p[0] : Ar<Real, true>::add(c, p[j]);
+        if (pick < 0 && (double)u <= (double)c) pick = perm[j];
+      }
+      if (j == n - 1) last = perm[j];
+    }
+    return pick < 0 ? last : pick;
+  } else {
+    Real tot = 0;
+#pragma unroll
+    for (int i = 0; i < NC; i++) if (i < n) tot += w[i];
+    if (!(tot > (Real)0) || !isfinite(tot)) { atomicOr(err, tot > (Real)0 ? PM_DE_SAMPLE_NA : PM_DE_SAMPLE_ZERO); return 0; }
+    Real t = (Real)u * tot, c = 0;
+    int pick = -1, lastpos = 0;
+#pragma unroll
+    for (int i = 0; i < NC; i++) if (i < n) {
+      c += w[i];
+      if (w[i] > (Real)0) lastpos = i;
+      if (pick < 0 && t < c && w[i] > (Real)0) pick = i;
+    }
+    return pick < 0 ? lastpos : pick;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = M v  (M row-major n x n, left-to-right dot products) and y = M^T v.
+// ------------------------------------------------------------------------------------------------
+template <typename Real, int NC, bool EXACT>
+__device__ __forceinline__ void matvec(const Real* __restrict__ M, int n, Real* v) {
+  Real y[NC];
+#pragma unroll
+  for (int i = 0; i < NC; i++) if (i < n) {
+    Real acc = 0;
+#pragma unroll
+    for (int j = 0; j < NC; j++) if (j < n) acc = Ar<Real, EXACT>::add(acc, Ar<Real, EXACT>::mul(M[i * n + j], v[j]));
+    y[i] = acc;
+  }
+#pragma unroll
+  for (int i = 0; i < NC; i++) if (i < n) v[i] = y[i];
+}
+template <typename Real, int NC, bool EXACT>
+__device__ __forceinline__ void matvec_t(const Real* __restrict__ M, int n, Real* v) {
+  Real y[NC];
+#pragma unroll
+  for (int j = 0; j < NC; j++) if (j < n) {
+    Real acc = 0;
+#pragma unroll
+    for (int i = 0; i < NC; i++) if (i < n) acc = Ar<Real, EXACT>::add(acc, Ar<Real, EXACT>::mul(M[i * n + j], v[i]));
+    y[j] = acc;
+  }
+#pragma unroll
+  for (int j = 0; j < NC; j++) if (j < n) v[j] = y[j];
+}
+
+// Vector load/store of one partial-likelihood row (NS reals) — 16-byte accesses for NS in {2,4}.
+template <typename Real, int NS> struct VecIO {
+  static __device__ __forceinline__ void load(const Real* p, int n, Real* v) { for (int i = 0; i < n; i++) v[i] = p[i]; }
+  static __device__ __forceinline__ void store(Real* p, int n, const Real* v) { for (int i = 0; i < n; i++) p[i] = v[i]; }
+};
+template <> struct VecIO<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, int, float* v) {
+    float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  static __device__ __forceinline__ void store(float* p, int, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct VecIO<float, 2> {
+  static __device__ __forceinline__ void load(const float* p, int, float* v) {
+    float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
+  static __device__ __forceinline__ void store(float* p, int, const float* v) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+template <> struct VecIO<double, 4> {
+  static __device__ __forceinline__ void load(const double* p, int, double* v) {
+    double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; }
+  static __device__ __forceinline__ void store(double* p, int, const double* v) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]); reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]); }
+};
+template <> struct VecIO<double, 2> {
+  static __device__ __forceinline__ void load(const double* p, int, double* v) {
+    double2 a = *reinterpret_cast<const double2*>(p); v[0] = a.x; v[1] = a.y; }
+  static __device__ __forceinline__ void store(double* p, int, const double* v) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); }
+};
+
+}  // namespace pm

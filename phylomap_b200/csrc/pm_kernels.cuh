@@ -1,0 +1,415 @@
+// The four kernels of one MCMC sweep:
+//   K1 k_prune   Felsenstein pruning with P_e := B^(m_e - 1)        replaces makePLrcpp* (src/phylomap.cpp:490-529,
+//                                                                    1077-1088, 1938-1949) + mmmmvFORpl (:446-450)
+//   K2 k_nodes   root draw + top-down node (and hidden-tip) draws    replaces sampleinternalnodes* (:535-738, 1091-1164,
+//                                                                    1314-1403, 1952-2046) + updatenodestates (:460-475)
+//   K3 k_paths   per (site, branch): regenerate the virtual jumps of the previous sweep, redraw the segment states
+//                (resamplebranchstates :264-308), merge + count (shortener :44-73 / shortenerbf :997-1028), draw the
+//                new virtual jumps (:391-410), accumulate dwell times (:745-757), block-level reduction
+//   K4 k_reduce  deterministic reduction of the per-block partial sums into one row of sufficient statistics
+//
+// Data layout in HBM (site-minor everywhere, so a warp = 32 consecutive sites reads/writes contiguous bytes):
+//   tipcode    [T][S]      u8   observed tip state (0-based) or observed parity (hidden-rate models)
+//   node_state [2T-1][S]   u8   current state of every node
+//   meta       [E][S]      u32  m (pieces on the branch, bits 0-15) | real jumps nj (16-23) | first state (24-31)
+//   PL         [T-1][S][n] Real partial likelihoods of the internal nodes (one 16-byte vector per site for n=4 fp32)
+//   seg_len    [C][E][S]   Real merged real path: segment lengths   } only touched for branches that carry a real
+//   seg_st     [C][E][S]   u8   merged real path: segment states    } jump (production) — virtual jumps are never
+//                                                                      stored, they are regenerated from their key
+#pragma once
+#include <type_traits>
+#include "pm_device.cuh"
+
+namespace pm {
+
+template <typename Real>
+struct ChainParams {
+  int n, T, E, C;
+  long long S;
+  const Real* model;  // [B n*n | Bs n*n | pid n | scale_old n | scale_new n], matrices row-major
+  const Real* ppow;   // [jcap][n*n] P_j = Bs * P_{j-1}
+  int jcap;
+  const int* up_entries; const int* up_off; int n_up_levels;        // 5 ints per internal node: parent, a, ea, b, eb
+  const int* down_entries; const int* down_off; int n_down_levels;  // 3 ints per drawn node: v, parent, edge
+  const int* e_parent; const int* e_child; const Real* e_len;
+  const long long* maps_off; const double* maps_len;
+  int root;
+  const uint8_t* tipcode; uint8_t* node_state; uint32_t* meta; Real* PL; Real* seg_len; uint8_t* seg_st;
+  int normalize, full_counts, parity_tips;
+  double* dw_partial; unsigned long long* cnt; int* root_out;
+  unsigned* err_flag;
+  RngDesc rng;
+};
+
+template <typename Real, int NC>
+__device__ __forceinline__ void tip_partial(int code, int n, bool parity, Real* v) {
+#pragma unroll
+  for (int j = 0; j < NC; j++) if (j < n) v[j] = parity ? (Real)((j & 1) != code) : (Real)(j == code);
+}
+
+// v <- Bs^k v
+template <typename Real, int NC, bool EXACT>
+__device__ __forceinline__ void apply_power(const ChainParams<Real>& P, const Real* sBs, const Real* sPow, int npow_s, int n,
+                                            int k, Real* v) {
+  if (k <= 0) return;
+  if (!EXACT) {
+    if (k < npow_s) { matvec<Real, NC, false>(sPow + k * n * n, n, v); return; }
+    if (k < P.jcap) { matvec<Real, NC, false>(P.ppow + (size_t)k * n * n, n, v); return; }
+  }
+  for (int r = 0; r < k; r++) matvec<Real, NC, EXACT>(sBs, n, v);
+}
+
+template <typename Real>
+__device__ __forceinline__ void load_model_smem(const ChainParams<Real>& P, int n, Real* sB, Real* sBs, Real* sVec /*3n*/,
+                                                Real* sPow, int npow_s) {
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) { if (sB) sB[i] = P.model[i]; sBs[i] = P.model[n * n + i]; }
+  if (sVec) for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) sVec[i] = P.model[2 * n * n + i];
+  for (int i = threadIdx.x; i < npow_s * n * n; i += blockDim.x) sPow[i] = P.ppow[i];
+}
+
+template <int NS, bool EXACT> __host__ __device__ constexpr int smem_pow_count() { return (!EXACT && NS > 0 && NS <= 4) ? PM_SMEM_POW : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// K1: pruning.  Block = one tile of 32 sites x (blockDim/32) warps; warps stride over the nodes of a level,
+// levels are separated by __syncthreads (children written by sibling warps of the same block).
+// ------------------------------------------------------------------------------------------------
+template <typename Real, int NS, bool EXACT>
+__global__ void __launch_bounds__(256) k_prune(ChainParams<Real> P) {
+  constexpr int NC = NS > 0 ? NS : PM_NMAX;
+  const int n = NS > 0 ? NS : P.n;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Real* sBs = reinterpret_cast<Real*>(smem_raw);
+  Real* sPow = sBs + n * n;
+  const int npow_s = min(smem_pow_count<NS, EXACT>(), P.jcap);
+  load_model_smem<Real>(P, n, nullptr, sBs, nullptr, sPow, npow_s);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long S = P.S;
+  const long long site = (long long)blockIdx.x * 32 + lane;
+  const bool active = site < S;
+  const bool parity = P.parity_tips != 0;
+  for (int l = 0; l < P.n_up_levels; l++) {
+    const int beg = __ldg(P.up_off + l), end = __ldg(P.up_off + l + 1);
+    for (int idx = beg + warp; idx < end; idx += nw) {
+      const int* en = P.up_entries + 5 * idx;
+      const int pn = __ldg(en), a = __ldg(en + 1), ea = __ldg(en + 2), b = __ldg(en + 3), eb = __ldg(en + 4);
+      if (active) {
+        const int ka = (int)(P.meta[(long long)ea * S + site] & 0xffffu) - 1;
+        const int kb = (int)(P.meta[(long long)eb * S + site] & 0xffffu) - 1;
+        Real va[NC], vb[NC];
+        if (a < P.T) tip_partial<Real, NC>(P.tipcode[(long long)a * S + site], n, parity, va);
+        else VecIO<Real, NS>::load(P.PL + ((long long)(a - P.T) * S + site) * n, n, va);
+        if (b < P.T) tip_partial<Real, NC>(P.tipcode[(long long)b * S + site], n, parity, vb);
+        else VecIO<Real, NS>::load(P.PL + ((long long)(b - P.T) * S + site) * n, n, vb);
+        apply_power<Real, NC, EXACT>(P, sBs, sPow, npow_s, n, kb, vb);
+        apply_power<Real, NC, EXACT>(P, sBs, sPow, npow_s, n, ka, va);
+        Real out[NC];
+#pragma unroll
+        for (int j = 0; j < NC; j++) if (j < n) out[j] = Ar<Real, EXACT>::mul(vb[j], va[j]);
+        if (P.normalize) {
+          if (EXACT) {  // arma::accu order on a row view: two interleaved accumulators
+            Real a1 = 0, a2 = 0;
+#pragma unroll
+            for (int j = 0; j < NC; j++) if (j < n) { if (j & 1) a2 = Ar<Real, true>::add(a2, out[j]); else a1 = Ar<Real, true>::add(a1, out[j]); }
+            const Real s = Ar<Real, true>::add(a1, a2);
+#pragma unroll
+            for (int j = 0; j < NC; j++) if (j < n) out[j] = Ar<Real, true>::div(out[j], s);
+          } else {
+            Real s = 0;
+#pragma unroll
+            for (int j = 0; j < NC; j++) if (j < n) s += out[j];
+            const Real inv = (Real)1 / s;
+#pragma unroll
+            for (int j = 0; j < NC; j++) if (j < n) out[j] *= inv;
+          }
+        }
+        VecIO<Real, NS>::store(P.PL + ((long long)(pn - P.T) * S + site) * n, n, out);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: node states, top-down.
+// ------------------------------------------------------------------------------------------------
+template <typename Real, int NS, bool EXACT>
+__global__ void __launch_bounds__(256) k_nodes(ChainParams<Real> P, uint32_t iter) {
+  constexpr int NC = NS > 0 ? NS : PM_NMAX;
+  typedef typename StreamSel<Real, EXACT>::type Stream;
+  const int n = NS > 0 ? NS : P.n;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Real* sBs = reinterpret_cast<Real*>(smem_raw);
+  Real* sVec = sBs + n * n;  // pid, scale_old, scale_new
+  Real* sPow = sVec + 3 * n;
+  const int npow_s = min(smem_pow_count<NS, EXACT>(), P.jcap);
+  load_model_smem<Real>(P, n, nullptr, sBs, sVec, sPow, npow_s);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long S = P.S;
+  const long long site = (long long)blockIdx.x * 32 + lane;
+  const bool active = site < S;
+  const bool parity = P.parity_tips != 0;
+  if (warp == 0 && active) {  // root :618-627
+    Real w[NC], pl[NC];
+    VecIO<Real, NS>::load(P.PL + ((long long)(P.root - P.T) * S + site) * n, n, pl);
+#pragma unroll
+    for (int j = 0; j < NC; j++) if (j < n) w[j] = Ar<Real, EXACT>::mul(sVec[j], pl[j]);
+    Stream g; g.open(P.rng, (uint32_t)site, iter, K_NODE, (uint32_t)P.root, P.err_flag);
+    const int s = categorical<Real, NC, EXACT>(w, n, g.next(), P.err_flag);
+    P.node_state[(long long)P.root * S + site] = (uint8_t)s;
+    if (P.rng.site0 + (uint32_t)site == 0u) *P.root_out = s;
+  }
+  __syncthreads();
+  for (int l = 0; l < P.n_down_levels; l++) {
+    const int beg = __ldg(P.down_off + l), end = __ldg(P.down_off + l + 1);
+    for (int idx = beg + warp; idx < end; idx += nw) {
+      const int* en = P.down_entries + 3 * idx;
+      const int v = __ldg(en), pn = __ldg(en + 1), e = __ldg(en + 2);
+      if (active) {
+        const int ps = P.node_state[(long long)pn * S + site];
+        const int k = (int)(P.meta[(long long)e * S + site] & 0xffffu) - 1;
+        Real w[NC], pl[NC];
+        bool done = false;
+        if (!EXACT && k > 0) {  // row ps of B^k from the table
+          const Real* M = (k < npow_s) ? (sPow + k * n * n) : (k < P.jcap ? P.ppow + (size_t)k * n * n : nullptr);
+          if (M) {
+#pragma unroll
+            for (int j = 0; j < NC; j++) if (j < n) w[j] = M[ps * n + j];
+            done = true;
+          }
+        }
+        if (!done) {  // (B^T)^k e_ps as k mat-vecs, Tvmmp :431-436
+#pragma unroll
+          for (int j = 0; j < NC; j++) if (j < n) w[j] = (Real)(j == ps);
+          for (int r = 0; r < k; r++) matvec_t<Real, NC, EXACT>(sBs, n, w);
+        }
+        if (v < P.T) tip_partial<Real, NC>(P.tipcode[(long long)v * S + site], n, parity, pl);
+        else VecIO<Real, NS>::load(P.PL + ((long long)(v - P.T) * S + site) * n, n, pl);
+#pragma unroll
+        for (int j = 0; j < NC; j++) if (j < n) w[j] = Ar<Real, EXACT>::mul(w[j], pl[j]);
+        Stream g; g.open(P.rng, (uint32_t)site, iter, K_NODE, (uint32_t)v, P.err_flag);
+        const int s = categorical<Real, NC, EXACT>(w, n, g.next(), P.err_flag);
+        P.node_state[(long long)v * S + site] = (uint8_t)s;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: branch paths.  Thread = one site x a chunk of branches; block = 128 consecutive sites.
+// ------------------------------------------------------------------------------------------------
+template <typename Real, int NS, bool EXACT>
+__global__ void __launch_bounds__(128) k_paths(ChainParams<Real> P, uint32_t iter, int first, int chunk) {
+  constexpr int NC = NS > 0 ? NS : PM_NMAX;
+  typedef typename StreamSel<Real, EXACT>::type Stream;
+  typedef ExpDev<Real, EXACT> Exp;
+  typedef Ar<Real, EXACT> A;
+  typedef Ar<Real, true> AX;  // virtual-jump arithmetic is pinned (no FMA contraction) in every mode: the sweep that
+                              // regenerates these pieces must reproduce the sweep that counted them bit for bit
+  typedef typename std::conditional<EXACT, double, Real>::type Acc;
+  const int n = NS > 0 ? NS : P.n;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_dw = reinterpret_cast<double*>(smem_raw);                 // [4 warps][n] (NS>0) or [n] atomics (NS==0)
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_dw + 4 * n);       // [n*n]
+  Real* sB = reinterpret_cast<Real*>(s_cnt + n * n + ((n * n) & 1));  // dense B (forward row)
+  Real* sBs = sB + n * n;
+  Real* sVec = sBs + n * n;
+  Real* sPow = sVec + 3 * n;
+  const int npow_s = min(smem_pow_count<NS, EXACT>(), P.jcap);
+  load_model_smem<Real>(P, n, sB, sBs, sVec, sPow, npow_s);
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) s_cnt[i] = 0;
+  for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_dw[i] = 0.0;
+  __syncthreads();
+  const Real* s_scale_old = sVec + n;
+  const Real* s_scale_new = sVec + 2 * n;
+  const long long S = P.S;
+  const long long site = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = site < S;
+  const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
+  const int C = P.C, E = P.E;
+  const bool full = P.full_counts != 0;
+  Acc Racc[NS > 0 ? NS : 1];
+#pragma unroll
+  for (int j = 0; j < (NS > 0 ? NS : 1); j++) Racc[j] = 0;
+  unsigned errbits = 0;
+
+  if (active) for (int e = e0; e < e1; e++) {
+    const long long pe = (long long)e * S + site;
+    const uint32_t mt = P.meta[pe];
+    const int m = (int)(mt & 0xffffu), nj = (int)((mt >> 16) & 0xffu), s0 = (int)(mt >> 24);
+    const int ps = P.node_state[(long long)__ldg(P.e_parent + e) * S + site];
+    const int cs = P.node_state[(long long)__ldg(P.e_child + e) * S + site];
+    int nout = 0, newm = 0, sfirst = 0;
+    Stream gnew; gnew.open(P.rng, (uint32_t)site, iter, K_BREXP, (uint32_t)e, P.err_flag);
+
+    // emit one merged run: store it, add its dwell time, draw its new virtual jumps (count only)
+    auto emit = [&](Real L, int s, bool final_run) {
+      if (nout == 0) sfirst = s;
+      const bool skip = (!EXACT) && final_run && nout == 0;  // single-run path: length == t_e, state in meta
+      if (!skip) {
+        if (nout < C) {
+          const long long ps_ = ((long long)nout * E + e) * S + site;
+          P.seg_len[ps_] = L; P.seg_st[ps_] = (uint8_t)s;
+        } else errbits |= PM_DE_PATH_CAP;
+      }
+      if (NS > 0) {
+#pragma unroll
+        for (int j = 0; j < (NS > 0 ? NS : 1); j++) Racc[j] += (s == j) ? (Acc)L : (Acc)0;
+      } else atomicAdd(&s_dw[s], (double)L);
+      const Real sc = s_scale_new[s];
+      if (isfinite(sc) && sc > (Real)0) {
+        Real tot = 0;
+        for (;;) {
+          const Real g = AX::mul(sc, Exp::draw(gnew));
+          const Real t2 = AX::add(tot, g);
+          if (t2 < L) { tot = t2; newm++; if (newm > 70000) break; } else break;
+        }
+      }
+      newm++;
+      nout++;
+    };
+
+    if (!EXACT && !first && nj == 0 && (m == 1 || (m == 2 && ps == cs))) {
+      if (full && m == 2) atomicAdd(&s_cnt[ps * n + cs], 1u);
+      emit(__ldg(P.e_len + e), cs, true);
+    } else {
+      Real in_len[PM_LOCAL_PATH_MAX]; uint8_t in_st[PM_LOCAL_PATH_MAX];
+      int nin = 0;
+      if (!first) {
+        if (!EXACT && nj == 0) { nin = 1; in_len[0] = __ldg(P.e_len + e); in_st[0] = (uint8_t)s0; }
+        else {
+          nin = nj + 1;
+          for (int c = 0; c < nin; c++) {
+            const long long q = ((long long)c * E + e) * S + site;
+            in_len[c] = P.seg_len[q]; in_st[c] = P.seg_st[q];
+          }
+        }
+      }
+      Stream gold; gold.open(P.rng, (uint32_t)site, iter - 1u, K_BREXP, (uint32_t)e, P.err_flag);
+      Stream gst; gst.open(P.rng, (uint32_t)site, iter, K_BRSTATE, (uint32_t)e, P.err_flag);
+      int j = 0; Real tot = 0; long long cp = first ? P.maps_off[e] : 0;
+      auto next_piece = [&]() -> Real {
+        if (first) return (Real)P.maps_len[cp++];
+        if (j >= nin) { errbits |= PM_DE_INCONSISTENT; return (Real)0; }
+        const Real L = in_len[j];
+        const Real sc = s_scale_old[in_st[j]];
+        if (isfinite(sc) && sc > (Real)0) {
+          const Real g = AX::mul(sc, Exp::draw(gold));
+          const Real t2 = AX::add(tot, g);
+          if (t2 < L) { tot = t2; return g; }
+        }
+        const Real r = AX::sub(L, tot);
+        j++; tot = 0;
+        return r;
+      };
+      int cur_state = (m == 1) ? cs : ps;
+      Real cur_len = next_piece();
+      int prev = cur_state;
+      for (int p = 1; p < m; p++) {
+        int st;
+        if (p == m - 1) st = cs;
+        else {
+          const int jd = m - p - 1;  // beta_jd = Bs^jd e_cs
+          Real w[NC];
+          const Real* M = (jd < npow_s) ? (sPow + jd * n * n) : (jd < P.jcap ? P.ppow + (size_t)jd * n * n : nullptr);
+          if (M) {
+#pragma unroll
+            for (int c = 0; c < NC; c++) if (c < n) w[c] = M[c * n + cs];
+          } else {
+#pragma unroll
+            for (int c = 0; c < NC; c++) if (c < n) w[c] = (Real)(c == cs);
+            for (int r = 0; r < jd; r++) matvec<Real, NC, EXACT>(sBs, n, w);
+          }
+#pragma unroll
+          for (int c = 0; c < NC; c++) if (c < n) w[c] = A::mul(sB[prev * n + c], w[c]);
+          st = categorical<Real, NC, EXACT>(w, n, gst.next(), P.err_flag);
+        }
+        const Real len = next_piece();
+        if (full) atomicAdd(&s_cnt[prev * n + st], 1u);
+        if (st == cur_state) cur_len = A::add(cur_len, len);
+        else {
+          emit(cur_len, cur_state, false);
+          if (!full) atomicAdd(&s_cnt[cur_state * n + st], 1u);
+          cur_state = st; cur_len = len;
+        }
+        prev = st;
+      }
+      // production: a single-run path is not stored, the next sweep takes its length from the tree
+      if (!EXACT && nout == 0) cur_len = __ldg(P.e_len + e);
+      emit(cur_len, cur_state, true);
+    }
+    if (newm > 65535) { errbits |= PM_DE_M_OVERFLOW; newm = 65535; }
+    if (nout - 1 > 255) { errbits |= PM_DE_PATH_CAP; nout = 256; }
+    P.meta[pe] = (uint32_t)newm | ((uint32_t)(nout - 1) << 16) | ((uint32_t)sfirst << 24);
+  }
+  if (errbits) atomicOr(P.err_flag, errbits);
+
+  // block reduction: dwell times through a fixed-order shuffle tree + per-warp slots, counts through shared atomics
+  if (NS > 0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < (NS > 0 ? NS : 1); j++) {
+      double v = (double)Racc[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) s_dw[warp * n + j] = v;
+    }
+  }
+  __syncthreads();
+  const long long blk = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+  if ((int)threadIdx.x < n) {
+    double v;
+    if (NS > 0) { v = 0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += s_dw[w * n + threadIdx.x]; }
+    else v = s_dw[threadIdx.x];
+    P.dw_partial[blk * n + threadIdx.x] = v;
+  }
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) if (s_cnt[i]) atomicAdd(&P.cnt[i], (unsigned long long)s_cnt[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: one row of sufficient statistics [R(n) | N(n*n) | root].  One block, fixed summation order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ dw_partial, long long nblocks, int n,
+                                                unsigned long long* cnt, const int* root, double* row, int accumulate) {
+  __shared__ double sh[256];
+  for (int j = 0; j < n; j++) {
+    double acc = 0;
+    for (long long b = threadIdx.x; b < nblocks; b += 256) acc += dw_partial[b * n + j];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) row[j] = (accumulate ? row[j] : 0.0) + sh[0];
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n * n; i += 256) { row[n + i] = (accumulate ? row[n + i] : 0.0) + (double)cnt[i]; cnt[i] = 0ull; }
+  if (threadIdx.x == 0 && !accumulate) row[n + n * n] = (double)(*root);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Set-up kernels.
+// ------------------------------------------------------------------------------------------------
+// states [S][T] (int32 1-based, or u8) -> tipcode [T][S], node_state[tip] ; validates the range
+template <typename In>
+__global__ void k_init_tips(const In* __restrict__ states, long long S, int T, int n, int parity, uint8_t* tipcode,
+                            uint8_t* node_state, unsigned* err_flag) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * T) return;
+  const long long t = i / S, s = i % S;
+  const int v = (int)states[s * T + t];
+  uint8_t code;
+  if (parity) code = (uint8_t)(v & 1);
+  else { if (v < 1 || v > n) { atomicOr(err_flag, PM_DE_SAMPLE_NA); code = 0; } else code = (uint8_t)(v - 1); }
+  tipcode[t * S + s] = code;
+  node_state[t * S + s] = parity ? (uint8_t)(code ? 0 : 1) : code;
+}
+
+__global__ void k_init_meta(const long long* __restrict__ maps_off, long long S, int E, uint32_t* meta) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * E) return;
+  const long long e = i / S;
+  meta[i] = (uint32_t)(maps_off[e + 1] - maps_off[e]);
+}
+
+}  // namespace pm
