@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Headline benchmark: sampled branch-site histories / second (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[3] — sumstatMCMC_bigtree on a 10 000-tip Yule tree, 4-state
+hidden-rate model make2sQ(.1,.1,.2,.2,10), 1 000 000 sites site-sharded over 8 GPUs = 125 000 sites per GPU, weak
+scaling (every rank always holds 125 000 sites).  One step = one MCMC sweep (prune, node draws, path resampling,
+reduction) over all local sites = E x S_local branch-site histories.  Production arithmetic: FP32, Philox.
+
+`value`   : device-timed sweeps on the resident chain (CUDA events on the chain's stream), max over ranks.
+`e2e`     : the same sweeps through the drop-in entry pm_maketreelistMCMC_bigtree with HOST buffers: tip states
+            uploaded from pinned host memory, chain built, K sweeps, result matrix copied back — all inside the timer.
+`roofline`: pruning pass K1 (k_prune) timed alone with CUDA events; algorithmic bytes per site from SURVEY.md §8(d).
+`cpu_baseline` / `--impl reference`: the CPU oracle (line-for-line restatement of src/phylomap.cpp; the R package
+            itself cannot be built without R) on a bounded site sample, one process per host core.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TIPS = int(os.environ.get("PM_BENCH_TIPS", 10000))
+SITES_PER_GPU = int(os.environ.get("PM_BENCH_SITES", 125000))
+OMEGA = 2.4
+METRIC = "sampled branch-site histories/sec (4-state, 10k-tip tree)"
+UNIT = "histories/s"
+
+
+def workload_tree():
+    from phylomap_b200 import synth
+    Q = synth.make2sQ(0.1, 0.1, 0.2, 0.2, 10.0)
+    qmax = float(np.max(-np.diag(Q)))
+    tree = synth.yule_tree(TIPS, seed=4, mean_branch=0.1 / qmax)
+    return tree, Q, np.full(4, 0.25)
+
+
+def config(n_gpus, sites):
+    return {"workload": "sumstatMCMC_bigtree, %d-tip Yule tree (seed 4, mean branch 0.1/max|Qii|), 4-state make2sQ(.1,.1,.2,.2,10), "
+                        "Omega=2.4, %d sites per GPU x %d GPU(s), site-sharded" % (TIPS, sites, n_gpus),
+            "tips": TIPS, "branches": 2 * TIPS - 2, "states": 4, "sites_per_gpu": sites, "sites_total": sites * n_gpus,
+            "precision": "f32", "rng": "philox4x32-10",
+            "l2": "per-sweep working set (partials + jump counts, >30 GB at the default size) exceeds the 126 MB L2"}
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=3)
+
+    def summary(self):
+        sm = [int(r[0]) for r in self.rows if len(r) == 6 and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) == 6 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) == 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _oracle_worker(args):
+    """One process: the oracle on a slice of sites.  Returns (histories, seconds)."""
+    tree_d, Q, pid, N, seed = args
+    from oracle import bridge
+    run = bridge.OracleRun(bridge.BIGTREE, [tree_d], Q, pid, OMEGA, N, rng_mode=bridge.KEYED, seed=seed)
+    t0 = time.perf_counter()
+    run.run()
+    dt = time.perf_counter() - t0
+    return tree_d["edge"].shape[0] * tree_d["states"].shape[0] * N, dt
+
+
+def cpu_reference(tree, Q, pid, steps, sites_per_core=None, cores=None):
+    """The reference algorithm (oracle) on all host cores: sites are independent for fixed Q, so each core gets its
+    own slice — the most favourable way to run the single-threaded reference on this host."""
+    import multiprocessing as mp
+    from phylomap_b200 import synth
+    cores = cores or os.cpu_count() or 1
+    sites_per_core = sites_per_core or int(os.environ.get("PM_BENCH_CPU_SITES", 2))
+    st = synth.simulate_tip_states(tree, Q, pid, cores * sites_per_core, seed=99).numpy()
+    jobs = []
+    for c in range(cores):
+        z = tree.with_states(st[c * sites_per_core:(c + 1) * sites_per_core])
+        jobs.append((z.oracle_dict(), Q.copy(), pid, steps, 1000 + c))
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_oracle_worker, jobs)
+    wall = time.perf_counter() - t0
+    hist = sum(r[0] for r in res)
+    return {"value": hist / wall, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d sites x %d cores x %d sweeps of the same tree/model, one oracle process per core, wall %.1f s"
+                      % (sites_per_core, cores, steps, wall)}, wall
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    from oracle import bridge
+    bridge.build()
+    tree, Q, pid = workload_tree()
+    # warm-up: a tiny run so that page-in / fork costs stay out of the measurement
+    for _ in range(min(a.warmup, 1)):
+        cpu_reference(tree, Q, pid, 1, sites_per_core=1)
+    steps = max(1, min(a.steps, int(os.environ.get("PM_BENCH_CPU_STEPS", 3))))
+    cb, wall = cpu_reference(tree, Q, pid, steps)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(a.gpus, SITES_PER_GPU),
+            "cpu_baseline": cb, "gpu_launches": 0,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = CPU oracle restating src/phylomap.cpp (R/Rcpp/RcppArmadillo absent, the package cannot be built); "
+                    "each step is a bounded site sample of the workload"}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(a, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import phylomap_b200 as pb
+    from phylomap_b200 import capi, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the sampler has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    tree, Q, pid = workload_tree()
+    S = SITES_PER_GPU
+    E = tree.E
+    # synthetic tip data for this rank's site block, generated on the GPU, staged in pinned host memory
+    st_dev = synth.simulate_tip_states(tree, Q, pid, S, seed=101 + rank, device="cuda:%d" % local_rank,
+                                       batch_sites=min(S, 32768))
+    st_host = torch.empty((S, tree.T), dtype=torch.uint8, pin_memory=True)
+    st_host.copy_(st_dev)
+    del st_dev
+    torch.cuda.empty_cache()
+    z = tree.with_states(st_host.numpy())
+    order = [z.order()]
+    stream = torch.cuda.Stream()
+    opts = dict(precision="f32", mode="production", seed=2026, device=local_rank, site_offset=rank * S,
+                stream=stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    total = a.warmup + a.steps
+    chain = pb.Chain(capi.PM_V_BIGTREE, z, Q.copy(), pid, OMEGA, total + 2, order=order, **opts)
+    chain.run(a.warmup)
+    barrier()
+    chain.enable_timing(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            rows = chain.run(a.steps)
+            ev1.record(stream)
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    chain.enable_timing(False)
+    ktimes, launches = chain.kernel_times()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = E * S * world * a.steps / (ms_max * 1e-3)
+
+    # sanity: total dwell time per sweep == sites x tree length
+    tot = rows[:, :4].sum(1)
+    expect = S * tree.edge_length.sum()
+    if not np.allclose(tot, expect, rtol=1e-3):
+        raise SystemExit("bench sanity check failed: dwell %r vs %r" % (tot[:3], expect))
+
+    # roofline of the pruning pass
+    k1_ms = chain.time_prune(reps=5)
+    T = tree.T
+    bytes_site = (T - 1) * 16 + (T - 2) * 16 + T * 1 + E * 4
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = bytes_site * S / (k1_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_prune<float,4,false>", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650",
+            "ms_per_launch": k1_ms, "algorithmic_bytes_per_site": bytes_site,
+            "in_step_ms": {k: v / a.steps for k, v in ktimes.items()}}
+    dev_bytes = chain.device_bytes()
+    chain.close()
+    del chain
+    torch.cuda.empty_cache()
+
+    # end to end through the drop-in entry with host buffers
+    barrier()
+    out = np.zeros((a.steps, 16), order="F")
+    t0 = time.perf_counter()
+    res = pb.maketreelistMCMC_bigtree(z, Q.copy(), pid, np.asfortranarray(np.eye(4) + Q / OMEGA), OMEGA, *order[0], a.steps,
+                                      **{k: v for k, v in opts.items() if k != "stream"})
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    del out
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e = {"value": E * S * world * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(S * tree.T / a.steps),
+           "d2h_bytes_per_step": int(res.nbytes / a.steps), "seconds": e2e_s,
+           "what": "pm_maketreelistMCMC_bigtree(host tree + u8 tip states) incl. upload, chain build, %d sweeps, read-back" % a.steps}
+
+    cb = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        from oracle import bridge
+        bridge.build()
+        cb, _ = cpu_reference(tree, Q, pid, 2)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config(world, S), "clocks": clk.summary(), "e2e": e2e,
+                "gpu_launches": int(4 * a.steps), "roofline": roof, "cpu_baseline": cb, "device_bytes": dev_bytes}
+        print(json.dumps(line))
+
+
+def main():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours")
+    p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = p.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+    else:
+        run_ours(a, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -211,6 +211,7 @@ struct Flags {
 struct Chain {
   const TreeIn* tr; int64_t site; int tree_idx;
   std::vector<std::list<Seg>> br;
+  std::vector<std::vector<Seg>> merged;  // instrumentation: every branch right after shortener, before the new virtual jumps
   std::vector<double> PL;  // (2T-1) x n row-major
   std::vector<int> rm;     // node states 0-based, last sweep
   int n;
@@ -218,6 +219,7 @@ struct Chain {
   void init(const TreeIn* t, int64_t s, int tidx, int nstates, const Flags& f) {
     tr = t; site = s; tree_idx = tidx; n = nstates;
     br.assign(t->E, {});
+    merged.assign(t->E, {});
     for (int e = 0; e < t->E; e++)
       for (int64_t p = t->maps_off[e]; p < t->maps_off[e + 1]; p++) br[e].push_back({t->maps_len[p], t->maps_state[p] - 1});
     PL.assign((size_t)(2 * t->T - 1) * n, 0.0);
@@ -378,6 +380,7 @@ struct Chain {
       g.begin(K_BRSTATE, e, lin_slot(base, K_BRSTATE, e));
       resample_states(br[e], M, f, g);
       merge_and_count(br[e], stats, f.full_counts);
+      merged[e].assign(br[e].begin(), br[e].end());
       g.begin(K_BREXP, e, lin_slot(base, K_BREXP, e));
       insert_virtual(br[e], M, g);
     }
@@ -891,15 +894,11 @@ void orc_get_piece_counts(void* h, int tree, int32_t* out /* [S][E] */) {
   auto* r = (orc::Run*)h; int E = r->trees[tree].E;
   for (int64_t s = 0; s < r->trees[tree].S; s++) for (int e = 0; e < E; e++) out[s * E + e] = (int)r->chains[tree][s].br[e].size();
 }
-// merged real path of one (site, branch): runs of equal state with summed lengths (left to right)
+// merged real path of one (site, branch) as the last sweep's shortener left it (before the virtual-jump insertion)
 int orc_get_path(void* h, int tree, int64_t site, int e, double* len, int32_t* st, int cap) {
-  auto* r = (orc::Run*)h; auto& b = r->chains[tree][site].br[e];
-  int k = 0; bool have = false; double cur = 0; int cs = -1;
-  for (auto& s : b) {
-    if (have && s.st == cs) cur = cur + s.len;
-    else { if (have) { if (k < cap) { len[k] = cur; st[k] = cs; } k++; } cur = s.len; cs = s.st; have = true; }
-  }
-  if (have) { if (k < cap) { len[k] = cur; st[k] = cs; } k++; }
+  auto* r = (orc::Run*)h; auto& b = r->chains[tree][site].merged[e];
+  int k = 0;
+  for (auto& s : b) { if (k < cap) { len[k] = s.len; st[k] = s.st; } k++; }
   return k;
 }
 // raw pieces (incl. virtual jumps)

@@ -1,0 +1,11 @@
+"""phylomap_b200: B200-native stochastic-mapping MCMC core (the uniformization sampler of vnminin/phylomap).
+
+Only the hot path lives here: the CUDA kernels and C ABI (csrc/, include/phylomap_b200.h), the ctypes binding
+(capi), the host-side mirror of the reference's R functions (api), and synthetic-input generators (synth).
+"""
+from . import capi  # noqa: F401
+from .api import (Chain, SPARSEmaketreelistMCMC, SPARSEsumstatMCMC, makenodelist, maketreelistMCMC,  # noqa: F401
+                  maketreelistMCMC_bigtree, maketreelistMCMCbf, maketreelistMCMCks, maketreelistMCMCksmt,
+                  maketreelistMCMCmt, myreorder, pruningwiseedgeorder, sumstatMCMC, sumstatMCMC_bigtree,
+                  sumstatMCMCbf, sumstatMCMCks, sumstatMCMCksmt, sumstatMCMCmt)
+from .tree import PhyloTree  # noqa: F401

@@ -1,0 +1,310 @@
+"""Host-side mirror of the reference's R-facing API (same function names, argument order and return layout),
+calling the B200 library through its C ABI.
+
+    R/sumstatMCMC.R:21          sumstatMCMC(z, Q, pid, Omega, N)
+    R/SPARSEsumstatMCMC.R:21    SPARSEsumstatMCMC(z, Q, pid, Omega, N)
+    R/sumstatMCMC_bigtree.R:21  sumstatMCMC_bigtree(z, Q, pid, Omega, N)
+    R/sumstatMCMCbf.R:21        sumstatMCMCbf(z, Q, pid, Omega, N, prior)      -> named columns, ss[,1:9]
+    R/sumstatMCMCks.R:21        sumstatMCMCks(z, Q, pid, Omega, N, prior)
+    R/sumstatMCMCmt.R:21        sumstatMCMCmt(treelist, Q, pid, Omega, N, prior)
+    R/sumstatMCMCksmt.R:21      sumstatMCMCksmt(treelist, Q, pid, Omega, N, prior)
+    R/RcppExports.R:4-50        maketreelist*(x, Q, pid, B, Omega, nen, nodelist, root, N[, prior])
+
+Like the reference, the rate-updating samplers rewrite `Q` (and `B` in the maketreelist* forms) IN PLACE; pass
+Fortran-ordered float64 arrays to observe that (other arrays are copied and the caller's object is left alone,
+which is what R does for non-double input).  Extra keyword-only arguments (`n_gpu` sharding aside) select the
+device arithmetic; their defaults come from PHYLOMAP_B200_{PRECISION,MODE,SEED,DEVICE} so that the positional
+signatures stay those of the R functions.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+from .tree import PhyloTree
+
+BF_COLNAMES = ["time_0", "time_1", "n00", "n01", "n10", "n11", "l01", "l10", "root_state"]
+MT_COLNAMES = ["time_0", "time_1", "n00", "n01", "n10", "n11", "l01", "l10", "tree_number"]
+
+
+def _options(precision=None, mode=None, seed=None, device=None, rng=None, table=None, host_table=None,
+             site_offset=0, path_capacity=0, power_capacity=0, allreduce=None, stream=None, progress=False):
+    o = capi.default_options()
+    env = os.environ
+    precision = precision if precision is not None else env.get("PHYLOMAP_B200_PRECISION", "f64")
+    mode = mode if mode is not None else env.get("PHYLOMAP_B200_MODE", "production")
+    o.precision = {"f64": capi.PM_F64, "f32": capi.PM_F32}[str(precision).lower()]
+    o.mode = {"production": capi.PM_MODE_PRODUCTION, "deterministic": capi.PM_MODE_DETERMINISTIC}[str(mode).lower()]
+    o.seed = int(seed if seed is not None else env.get("PHYLOMAP_B200_SEED", "1"))
+    o.device = int(device if device is not None else env.get("PHYLOMAP_B200_DEVICE", "0"))
+    o.site_offset = int(site_offset)
+    o.path_capacity, o.power_capacity = int(path_capacity), int(power_capacity)
+    o.progress = int(bool(progress))
+    keep = []
+    if table is not None:
+        off = np.ascontiguousarray(table[0], dtype=np.int64)
+        u = np.ascontiguousarray(table[1], dtype=np.float64)
+        keep += [off, u]
+        o.rng, o.tab_off, o.tab_u = capi.PM_RNG_TABLE, capi.ptr(off), capi.ptr(u)
+        if host_table is not None:
+            ht = np.ascontiguousarray(host_table, dtype=np.float64)
+            keep.append(ht)
+            o.host_tab, o.host_tab_n = capi.ptr(ht), len(ht)
+    if allreduce is not None:
+        cb = capi.ALLREDUCE_FN(allreduce)
+        keep.append(cb)
+        o.allreduce = cb
+    if stream is not None:
+        o.cuda_stream = int(stream)
+    return o, keep
+
+
+def _inplace(a, n):
+    """float64 Fortran-ordered n x n view of `a` if it already is one (so in-place updates are visible), else a copy."""
+    if isinstance(a, np.ndarray) and a.dtype == np.float64 and a.shape == (n, n) and (a.flags.f_contiguous):
+        return a
+    return np.asfortranarray(np.array(a, dtype=np.float64))
+
+
+def _trees(x):
+    if isinstance(x, (list, tuple)):
+        return [PhyloTree.from_mapping(t) for t in x]
+    return [PhyloTree.from_mapping(x)]
+
+
+class Chain:
+    """Resident chain (pm_chain_*): what the one-call entries are built from; used by bench.py and the tests."""
+
+    def __init__(self, variant, x, Q, pid, Omega, N, prior=None, B=None, order=None, **opts):
+        L = capi.lib()
+        trees = _trees(x)
+        n = np.asarray(Q).shape[0]
+        self.n, self.N, self.variant = n, int(N), variant
+        self.Q = _inplace(Q, n)
+        self.B = _inplace(np.eye(n) + self.Q / Omega if B is None else B, n)
+        self.pid = np.ascontiguousarray(pid, dtype=np.float64)
+        self.prior = None if prior is None else np.ascontiguousarray(prior, dtype=np.float64)
+        self._keep = []
+        arr = (capi.PmTree * len(trees))()
+        for i, t in enumerate(trees):
+            o = order[i] if order is not None else (None, None, None)
+            arr[i], keep = t.flat(*o)
+            self._keep.append(keep)
+        self.trees = trees
+        self.opt, keep = _options(**opts)
+        self._keep.append(keep)
+        self.ncols = L.pm_ncols(variant, n)
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = L.pm_chain_create(variant, C.byref(arr), len(trees), n, capi.ptr(self.Q), capi.ptr(self.pid),
+                               capi.ptr(self.B), float(Omega), capi.ptr(self.prior),
+                               0 if self.prior is None else len(self.prior), self.N, C.byref(self.opt), C.byref(h),
+                               err, 512)
+        capi.check(rc, err)
+        self.h = h
+        self.done = 0
+
+    def run(self, count=None, out=None):
+        count = self.N - self.done if count is None else count
+        if out is None:
+            out = np.zeros((count, self.ncols), dtype=np.float64, order="F")
+        err = C.create_string_buffer(512)
+        rc = capi.lib().pm_chain_run(self.h, count, capi.ptr(out), out.shape[0], err, 512)
+        capi.check(rc, err)
+        self.done += count
+        return out
+
+    def time_prune(self, reps=10, tree=0):
+        ms = C.c_float(0)
+        err = C.create_string_buffer(512)
+        capi.check(capi.lib().pm_chain_time_prune(self.h, tree, reps, C.byref(ms), err, 512), err)
+        return float(ms.value)
+
+    def enable_timing(self, on=True):
+        capi.lib().pm_chain_enable_timing(self.h, int(on))
+
+    def kernel_times(self):
+        ms = (C.c_double * 4)()
+        n = C.c_int64(0)
+        capi.lib().pm_chain_kernel_times(self.h, ms, C.byref(n))
+        return {"prune": ms[0], "sample_nodes": ms[1], "resample_paths": ms[2], "reduce": ms[3]}, int(n.value)
+
+    def device_bytes(self):
+        return int(capi.lib().pm_chain_device_bytes(self.h))
+
+    def node_states(self, tree=0):
+        t = self.trees[tree]
+        out = np.zeros((t.n_sites(), 2 * t.T - 1), dtype=np.int32)
+        rc = capi.lib().pm_chain_get_node_states(self.h, tree, capi.ptr(out))
+        if rc:
+            raise capi.PhylomapError(rc, "get_node_states")
+        return out
+
+    def piece_counts(self, tree=0):
+        t = self.trees[tree]
+        out = np.zeros((t.n_sites(), t.E), dtype=np.int32)
+        rc = capi.lib().pm_chain_get_piece_counts(self.h, tree, capi.ptr(out))
+        if rc:
+            raise capi.PhylomapError(rc, "get_piece_counts")
+        return out
+
+    def path(self, site, e, tree=0, cap=256):
+        ln = np.zeros(cap)
+        st = np.zeros(cap, dtype=np.int32)
+        k = capi.lib().pm_chain_get_path(self.h, tree, site, e, capi.ptr(ln), capi.ptr(st), cap)
+        if k < 0:
+            raise capi.PhylomapError(-k, "get_path")
+        return ln[:k].copy(), st[:k].copy()
+
+    def partials(self, site=0, tree=0):
+        t = self.trees[tree]
+        out = np.zeros((2 * t.T - 1, self.n))
+        rc = capi.lib().pm_chain_get_partials(self.h, tree, site, capi.ptr(out))
+        if rc:
+            raise capi.PhylomapError(rc, "get_partials")
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            capi.lib().pm_chain_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_ENTRY = {capi.PM_V_PLAIN: "pm_maketreelistMCMC", capi.PM_V_SPARSE: "pm_SPARSEmaketreelistMCMC",
+          capi.PM_V_BIGTREE: "pm_maketreelistMCMC_bigtree", capi.PM_V_BF: "pm_maketreelistMCMCbf",
+          capi.PM_V_KS: "pm_maketreelistMCMCks", capi.PM_V_MT: "pm_maketreelistMCMCmt",
+          capi.PM_V_KSMT: "pm_maketreelistMCMCksmt"}
+
+
+def _call(variant, x, Q, pid, B, Omega, order, N, prior=None, **opts):
+    """One blocking call of the C-ABI entry that replaces the reference's `.Call('phylomap_<fn>', ...)`."""
+    L = capi.lib()
+    trees = _trees(x)
+    n = np.asarray(Q).shape[0]
+    Qf, Bf = _inplace(Q, n), _inplace(B, n)
+    pidc = np.ascontiguousarray(pid, dtype=np.float64)
+    arr = (capi.PmTree * len(trees))()
+    keep = []
+    for i, t in enumerate(trees):
+        arr[i], k = t.flat(*order[i])
+        keep.append(k)
+    opt, k2 = _options(**opts)
+    ncols = L.pm_ncols(variant, n)
+    out = np.zeros((int(N), ncols), dtype=np.float64, order="F")
+    err = C.create_string_buffer(512)
+    fn = getattr(L, _ENTRY[variant])
+    if variant in (capi.PM_V_PLAIN, capi.PM_V_SPARSE, capi.PM_V_BIGTREE):
+        rc = fn(C.byref(arr), n, capi.ptr(Qf), capi.ptr(pidc), capi.ptr(Bf), float(Omega), int(N), C.byref(opt),
+                capi.ptr(out), err, 512)
+    else:
+        pr = np.ascontiguousarray(prior, dtype=np.float64)
+        if variant in (capi.PM_V_BF, capi.PM_V_KS):
+            rc = fn(C.byref(arr), n, capi.ptr(Qf), capi.ptr(pidc), capi.ptr(Bf), float(Omega), int(N), capi.ptr(pr),
+                    len(pr), C.byref(opt), capi.ptr(out), err, 512)
+        else:
+            rc = fn(C.byref(arr), len(trees), n, capi.ptr(Qf), capi.ptr(pidc), capi.ptr(Bf), float(Omega), int(N),
+                    capi.ptr(pr), len(pr), C.byref(opt), capi.ptr(out), err, 512)
+    capi.check(rc, err)
+    return out
+
+
+# ---- R/RcppExports.R:4-50 -------------------------------------------------------------------------------------
+def maketreelistMCMC(x, Q, pid, B, Omega, nen, nodelist, root, N, **opts):
+    return _call(capi.PM_V_PLAIN, x, Q, pid, B, Omega, [(nen, nodelist, root)], N, **opts)
+
+
+def SPARSEmaketreelistMCMC(x, Q, pid, B, Omega, nen, nodelist, root, N, **opts):
+    return _call(capi.PM_V_SPARSE, x, Q, pid, B, Omega, [(nen, nodelist, root)], N, **opts)
+
+
+def maketreelistMCMC_bigtree(x, Q, pid, B, Omega, nen, nodelist, root, N, **opts):
+    return _call(capi.PM_V_BIGTREE, x, Q, pid, B, Omega, [(nen, nodelist, root)], N, **opts)
+
+
+def maketreelistMCMCbf(x, Q, pid, B, Omega, nen, nodelist, root, N, prior, **opts):
+    return _call(capi.PM_V_BF, x, Q, pid, B, Omega, [(nen, nodelist, root)], N, prior, **opts)
+
+
+def maketreelistMCMCks(x, Q, pid, B, Omega, nen, nodelist, root, N, prior, **opts):
+    return _call(capi.PM_V_KS, x, Q, pid, B, Omega, [(nen, nodelist, root)], N, prior, **opts)
+
+
+def maketreelistMCMCmt(x, Q, pid, B, Omega, nen, nodelist_m, roots, N, prior, **opts):
+    order = [(np.asarray(nen)[i], np.asarray(nodelist_m)[i], int(roots[i])) for i in range(len(x))]
+    return _call(capi.PM_V_MT, x, Q, pid, B, Omega, order, N, prior, **opts)
+
+
+def maketreelistMCMCksmt(x, Q, pid, B, Omega, nen, nodelist_m, roots, N, prior, **opts):
+    order = [(np.asarray(nen)[i], np.asarray(nodelist_m)[i], int(roots[i])) for i in range(len(x))]
+    return _call(capi.PM_V_KSMT, x, Q, pid, B, Omega, order, N, prior, **opts)
+
+
+# ---- R/sumstatMCMC.R:1-18 -------------------------------------------------------------------------------------
+def pruningwiseedgeorder(x):
+    return PhyloTree.from_mapping(x).order()[0]
+
+
+def makenodelist(x):
+    return PhyloTree.from_mapping(x).order()[1]
+
+
+def myreorder(x):
+    return PhyloTree.from_mapping(x).order()[2]
+
+
+# ---- the sumstat* wrappers ------------------------------------------------------------------------------------
+def _single(fn, z, Q, pid, Omega, N, prior=None, **opts):
+    z = PhyloTree.from_mapping(z)
+    nen, nodelist, root = z.order()
+    n = np.asarray(Q).shape[0]
+    B = np.asfortranarray(np.eye(n) + np.asarray(Q, dtype=np.float64) / Omega)
+    if prior is None:
+        return fn(z, Q, pid, B, Omega, nen, nodelist, root, N, **opts)
+    return fn(z, Q, pid, B, Omega, nen, nodelist, root, N, prior, **opts)
+
+
+def sumstatMCMC(z, Q, pid, Omega, N, **opts):
+    return _single(maketreelistMCMC, z, Q, pid, Omega, N, **opts)
+
+
+def SPARSEsumstatMCMC(z, Q, pid, Omega, N, **opts):
+    return _single(SPARSEmaketreelistMCMC, z, Q, pid, Omega, N, **opts)
+
+
+def sumstatMCMC_bigtree(z, Q, pid, Omega, N, **opts):
+    return _single(maketreelistMCMC_bigtree, z, Q, pid, Omega, N, **opts)
+
+
+def sumstatMCMCbf(z, Q, pid, Omega, N, prior, **opts):
+    ss = _single(maketreelistMCMCbf, z, Q, pid, Omega, N, prior, **opts)
+    return ss[:, 0:9]  # R/sumstatMCMCbf.R:33-34 names the columns BF_COLNAMES and returns ss[,1:9]
+
+
+def sumstatMCMCks(z, Q, pid, Omega, N, prior, **opts):
+    return _single(maketreelistMCMCks, z, Q, pid, Omega, N, prior, **opts)
+
+
+def _multi(fn, treelist, Q, pid, Omega, N, prior, **opts):
+    trees = _trees(treelist)
+    orders = [t.order() for t in trees]
+    nen_m = np.stack([o[0] for o in orders])
+    nodelist_m = np.stack([o[1] for o in orders])
+    roots = [o[2] for o in orders]
+    n = np.asarray(Q).shape[0]
+    B = np.asfortranarray(np.eye(n) + np.asarray(Q, dtype=np.float64) / Omega)
+    return fn(trees, Q, pid, B, Omega, nen_m, nodelist_m, roots, N, prior, **opts)
+
+
+def sumstatMCMCmt(treelist, Q, pid, Omega, N, prior, **opts):
+    return _multi(maketreelistMCMCmt, treelist, Q, pid, Omega, N, prior, **opts)
+
+
+def sumstatMCMCksmt(treelist, Q, pid, Omega, N, prior, **opts):
+    return _multi(maketreelistMCMCksmt, treelist, Q, pid, Omega, N, prior, **opts)

@@ -20,6 +20,7 @@
 #define PM_DE_M_OVERFLOW 16u
 #define PM_DE_REPLAY 32u
 #define PM_DE_INCONSISTENT 64u
+#define PM_DE_BAD_STATE 128u
 
 namespace pm {
 
@@ -181,7 +182,7 @@ __device__ __forceinline__ int categorical(const Real* w, int n, U u, unsigned* 
   if (EXACT) {
     Real sum = 0; int npos = 0; unsigned bad = 0;
 #pragma unroll
-    for (int i = 0; i < NC; i++) if (i < n) {
+    for (int i = 0; i < n; i++) {
       Real v = w[i];
       if (!isfinite(v)) bad |= PM_DE_SAMPLE_NA;
       else if (v < (Real)0) bad |= PM_DE_SAMPLE_NEG;
@@ -191,38 +192,36 @@ __device__ __forceinline__ int categorical(const Real* w, int n, U u, unsigned* 
     if (bad) { atomicOr(err, bad); return 0; }
     Real p[NC]; int perm[NC];
 #pragma unroll
-    for (int i = 0; i < NC; i++) { p[i] = (i < n) ? Ar<Real, true>::div(w[i], sum) : (Real)-1; perm[i] = i; }
+    for (int i = 0; i < n; i++) { p[i] = Ar<Real, true>::div(w[i], sum); perm[i] = i; }
     // insertion sort, descending, stable: fixed compare-exchange pattern (a non-swap leaves a sorted prefix alone)
 #pragma unroll
-    for (int i = 1; i < NC; i++) {
+    for (int i = 1; i < n; i++) {
 #pragma unroll
       for (int j = i; j >= 1; j--) {
-        if (i < n && p[j] > p[j - 1]) {
+        if (p[j] > p[j - 1]) {
           Real tp = p[j]; p[j] = p[j - 1]; p[j - 1] = tp;
           int ti = perm[j]; perm[j] = perm[j - 1]; perm[j - 1] = ti;
         }
       }
     }
     Real c = 0;
-    int pick = -1, last = 0;
+    int pick = -1;
+    const int last = perm[n - 1];
 #pragma unroll
-    for (int j = 0; j < NC; j++) {
-      if (j < n - 1) {
-        c = (j == 0) ? p[0] : Ar<Real, true>::add(c, p[j]);
-        if (pick < 0 && (double)u <= (double)c) pick = perm[j];
-      }
-      if (j == n - 1) last = perm[j];
+    for (int j = 0; j < n - 1; j++) {
+      c = (j == 0) ? p[0] : Ar<Real, true>::add(c, p[j]);
+      if (pick < 0 && (double)u <= (double)c) pick = perm[j];
     }
     return pick < 0 ? last : pick;
   } else {
     Real tot = 0;
 #pragma unroll
-    for (int i = 0; i < NC; i++) if (i < n) tot += w[i];
+    for (int i = 0; i < n; i++) tot += w[i];
     if (!(tot > (Real)0) || !isfinite(tot)) { atomicOr(err, tot > (Real)0 ? PM_DE_SAMPLE_NA : PM_DE_SAMPLE_ZERO); return 0; }
     Real t = (Real)u * tot, c = 0;
     int pick = -1, lastpos = 0;
 #pragma unroll
-    for (int i = 0; i < NC; i++) if (i < n) {
+    for (int i = 0; i < n; i++) {
       c += w[i];
       if (w[i] > (Real)0) lastpos = i;
       if (pick < 0 && t < c && w[i] > (Real)0) pick = i;
@@ -238,27 +237,27 @@ template <typename Real, int NC, bool EXACT>
 __device__ __forceinline__ void matvec(const Real* __restrict__ M, int n, Real* v) {
   Real y[NC];
 #pragma unroll
-  for (int i = 0; i < NC; i++) if (i < n) {
+  for (int i = 0; i < n; i++) {
     Real acc = 0;
 #pragma unroll
-    for (int j = 0; j < NC; j++) if (j < n) acc = Ar<Real, EXACT>::add(acc, Ar<Real, EXACT>::mul(M[i * n + j], v[j]));
+    for (int j = 0; j < n; j++) acc = Ar<Real, EXACT>::add(acc, Ar<Real, EXACT>::mul(M[i * n + j], v[j]));
     y[i] = acc;
   }
 #pragma unroll
-  for (int i = 0; i < NC; i++) if (i < n) v[i] = y[i];
+  for (int i = 0; i < n; i++) v[i] = y[i];
 }
 template <typename Real, int NC, bool EXACT>
 __device__ __forceinline__ void matvec_t(const Real* __restrict__ M, int n, Real* v) {
   Real y[NC];
 #pragma unroll
-  for (int j = 0; j < NC; j++) if (j < n) {
+  for (int j = 0; j < n; j++) {
     Real acc = 0;
 #pragma unroll
-    for (int i = 0; i < NC; i++) if (i < n) acc = Ar<Real, EXACT>::add(acc, Ar<Real, EXACT>::mul(M[i * n + j], v[i]));
+    for (int i = 0; i < n; i++) acc = Ar<Real, EXACT>::add(acc, Ar<Real, EXACT>::mul(M[i * n + j], v[i]));
     y[j] = acc;
   }
 #pragma unroll
-  for (int j = 0; j < NC; j++) if (j < n) v[j] = y[j];
+  for (int j = 0; j < n; j++) v[j] = y[j];
 }
 
 // Vector load/store of one partial-likelihood row (NS reals) — 16-byte accesses for NS in {2,4}.

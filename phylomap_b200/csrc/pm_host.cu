@@ -1,0 +1,845 @@
+// libphylomap_b200: host side of the B200 stochastic-mapping sampler and its C ABI (include/phylomap_b200.h).
+//
+// One pm_chain owns, per tree, the device-resident state of all local sites (layout in pm_kernels.cuh) and the
+// small replicated model (Q, B, powers of B).  An iteration is four launches per tree (prune, node draws, branch
+// paths, reduce); the fixed-Q samplers never synchronise inside pm_chain_run, the rate-updating samplers read
+// one row of n + n^2 + 1 doubles back per iteration, update Q on the host (pm_rates.hpp) and upload the model.
+//
+// Replaces (reference src/phylomap.cpp): maketreelistMCMC :891, SPARSEmaketreelistMCMC :822,
+// maketreelistMCMC_bigtree :942, maketreelistMCMCbf :1258, maketreelistMCMCks :1802, maketreelistMCMCmt :2267,
+// maketreelistMCMCksmt :2722.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/phylomap_b200.h"
+#include "pm_launch.cuh"
+#include "pm_setup_kernels.cuh"
+#include "pm_rates.hpp"
+#include "pm_tree.hpp"
+
+namespace {
+
+struct Fail {
+  int code;
+  std::string msg;
+};
+
+[[noreturn]] void fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Fail{code, buf};
+}
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) fail(PM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));        \
+  } while (0)
+
+void set_err(char* err, size_t n, const std::string& m) {
+  if (err && n) snprintf(err, n, "%s", m.c_str());
+}
+
+template <typename F>
+int guarded(char* err, size_t errlen, F&& f) {
+  try {
+    f();
+    if (err && errlen) err[0] = 0;
+    return PM_OK;
+  } catch (const Fail& x) {
+    set_err(err, errlen, x.msg);
+    return x.code;
+  } catch (const std::string& s) {
+    set_err(err, errlen, s);
+    return PM_ERR_ARG;
+  } catch (const std::exception& x) {
+    set_err(err, errlen, x.what());
+    return PM_ERR_ARG;
+  }
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  void alloc(size_t n) {
+    if (p) { cudaFree(p); p = nullptr; }
+    bytes = n;
+    if (n) CK(cudaMalloc(&p, n));
+  }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+template <typename T>
+void upload(DevBuf& b, const std::vector<T>& v, cudaStream_t st) {
+  b.alloc(std::max<size_t>(v.size(), 1) * sizeof(T));
+  if (!v.empty()) CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+
+struct Variant {
+  int id;
+  bool sparse, normalize, full_counts, redraw_tips, parity_tips, rates, multi, hidden;
+};
+Variant variant_of(int v) {
+  Variant r{};
+  r.id = v;
+  r.sparse = v == PM_V_SPARSE;
+  r.normalize = v == PM_V_BIGTREE || v == PM_V_BF || v == PM_V_KS;
+  r.full_counts = v == PM_V_BF || v == PM_V_KS || v == PM_V_MT || v == PM_V_KSMT;
+  r.redraw_tips = v == PM_V_KS || v == PM_V_MT || v == PM_V_KSMT;
+  r.parity_tips = v == PM_V_KS || v == PM_V_KSMT;
+  r.rates = r.full_counts;
+  r.multi = v == PM_V_MT || v == PM_V_KSMT;
+  r.hidden = v == PM_V_KS || v == PM_V_KSMT;
+  return r;
+}
+
+int ncols_of(int variant, int n) {
+  const int k = n / 2 - 1;
+  switch (variant) {
+    case PM_V_PLAIN: case PM_V_SPARSE: case PM_V_BIGTREE: return n + n * (n - 1);
+    case PM_V_BF: case PM_V_MT: return n + n * n + 3;
+    case PM_V_KS: case PM_V_KSMT: return n + n * n + 2 + 3 * k + 1;
+  }
+  return -1;
+}
+
+// smallest c with P(Poisson(lam) >= c) < eps
+int poisson_cap(double lam, double eps) {
+  double term = std::exp(-lam), cdf = term;
+  int c = 1;
+  while (1.0 - cdf > eps && c < 100000) { term *= lam / c; cdf += term; c++; }
+  return c;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------------------------
+struct pm_chain {
+  virtual ~pm_chain() {}
+  virtual void run(int count, double* out, int64_t ld) = 0;
+  virtual float time_prune(int tree, int reps) = 0;
+  virtual void node_states(int tree, int32_t* out) = 0;
+  virtual void piece_counts(int tree, int32_t* out) = 0;
+  virtual int path(int tree, int64_t site, int e, double* len, int32_t* st, int cap) = 0;
+  virtual void partials(int tree, int64_t site, double* out) = 0;
+  double kernel_ms[4] = {0, 0, 0, 0};
+  int64_t launches = 0;
+  int64_t dev_bytes = 0;
+  bool timing = false;
+};
+
+namespace {
+
+template <typename Real>
+struct TreeDev {
+  pm::host::Schedule sch;
+  long long S = 0;
+  DevBuf up_entries, up_off, down_entries, down_off, e_parent, e_child, e_len, maps_off, maps_len, cap_off;
+  DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial;
+  std::vector<int> cap_off_h;
+  pm::ChainParams<Real> P;
+  dim3 paths_grid;
+  int chunk = 0;
+  long long nblocks = 0;
+};
+
+template <typename Real>
+struct ChainT : pm_chain {
+  Variant V;
+  int n = 0, ntrees = 0, N_total = 0, iters_done = 0, W = 0, ncols = 0;
+  int NS = 0;  // compile-time state count used for dispatch (2, 4 or 0)
+  bool exact = false;
+  double* Q = nullptr;  // caller's
+  double* B = nullptr;  // caller's
+  std::vector<double> pid, prior;
+  double Omega = 0;
+  pm_options opt;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::vector<std::unique_ptr<TreeDev<Real>>> trees;
+  int jcap = 0;
+  DevBuf model, ppow, cnt, root_out, err_flag, rows, tab_off, tab_u;
+  Real* model_h = nullptr;   // pinned staging: model then ppow
+  double* rows_h = nullptr;  // pinned: ntrees * W
+  unsigned* err_h = nullptr;
+  std::vector<double> scale_prev;
+  pm::host::MersenneR mt{0};
+  std::unique_ptr<pm::host::ReplaySource> replay;
+  size_t smem_prune = 0, smem_nodes = 0, smem_paths = 0;
+  int rows_cap = 0;
+  struct Timed { cudaEvent_t a, b; int k; };
+  std::vector<Timed> timed;
+
+  ~ChainT() override {
+    cudaDeviceSynchronize();
+    for (auto& t : timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    if (model_h) cudaFreeHost(model_h);
+    if (rows_h) cudaFreeHost(rows_h);
+    if (err_h) cudaFreeHost(err_h);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+
+  pm::host::UniformSource& host_rng() { return replay ? static_cast<pm::host::UniformSource&>(*replay) : mt; }
+
+  size_t model_elems() const { return (size_t)2 * n * n + 3 * n; }
+
+  // ---- model upload: B, thresholded B, pid, scales, table of powers ----
+  void stage_model(bool first) {
+    std::vector<double> Bd((size_t)n * n), Bs((size_t)n * n);
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        const double v = B[i + (size_t)j * n];
+        Bd[(size_t)i * n + j] = v;
+        Bs[(size_t)i * n + j] = (V.sparse && !(v > 1e-7)) ? 0.0 : v;  // matTospmat keeps entries > 1e-7 (:811)
+      }
+    std::vector<double> scale_new(n);
+    for (int s = 0; s < n; s++) scale_new[s] = 1.0 / (Omega + Q[s + (size_t)s * n]);
+    if (first) scale_prev = scale_new;
+    Real* m = model_h;
+    for (size_t i = 0; i < (size_t)n * n; i++) { m[i] = (Real)Bd[i]; m[(size_t)n * n + i] = (Real)Bs[i]; }
+    Real* v = m + 2 * (size_t)n * n;
+    for (int s = 0; s < n; s++) { v[s] = (Real)pid[s]; v[n + s] = (Real)scale_prev[s]; v[2 * n + s] = (Real)scale_new[s]; }
+    scale_prev = scale_new;
+    // P_0 = I, P_j = Bs P_{j-1}: left-to-right dot products in double (column c of P_j is the reference's
+    // backward vector B^j e_c bit for bit, src/phylomap.cpp:283-287)
+    Real* pw = m + model_elems();
+    std::vector<double> cur((size_t)n * n, 0.0), nxt((size_t)n * n);
+    for (int i = 0; i < n; i++) cur[(size_t)i * n + i] = 1.0;
+    for (int j = 0; j < jcap; j++) {
+      for (size_t i = 0; i < (size_t)n * n; i++) pw[(size_t)j * n * n + i] = (Real)cur[i];
+      if (j + 1 < jcap) {
+        for (int r = 0; r < n; r++)
+          for (int c = 0; c < n; c++) {
+            double acc = 0;
+            for (int l = 0; l < n; l++) acc = acc + Bs[(size_t)r * n + l] * cur[(size_t)l * n + c];
+            nxt[(size_t)r * n + c] = acc;
+          }
+        cur.swap(nxt);
+      }
+    }
+    CK(cudaMemcpyAsync(model.p, m, model_elems() * sizeof(Real), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(ppow.p, pw, (size_t)jcap * n * n * sizeof(Real), cudaMemcpyHostToDevice, stream));
+  }
+
+  // ---- kernel dispatch ----
+  template <int NSc, bool EX>
+  void launch_sweep_t(TreeDev<Real>& t, uint32_t iter, double* row) {
+    const int gx = (int)((t.S + 31) / 32);
+    begin_timed(0);
+    pm::Sweep<Real, NSc, EX>::prune(t.P, gx, smem_prune, stream);
+    end_timed();
+    begin_timed(1);
+    pm::Sweep<Real, NSc, EX>::nodes(t.P, gx, smem_nodes, stream, iter);
+    end_timed();
+    begin_timed(2);
+    pm::Sweep<Real, NSc, EX>::paths(t.P, t.paths_grid, smem_paths, stream, iter, iter == 0 ? 1 : 0, t.chunk);
+    end_timed();
+    begin_timed(3);
+    pm::k_reduce<<<1, 256, 0, stream>>>(t.dw_partial.template as<double>(), t.nblocks, n, cnt.as<unsigned long long>(),
+                                        root_out.as<int>(), row, 0);
+    end_timed();
+    launches += 4;
+  }
+  template <int NSc, bool EX>
+  void launch_prune_t(TreeDev<Real>& t) {
+    const int gx = (int)((t.S + 31) / 32);
+    pm::Sweep<Real, NSc, EX>::prune(t.P, gx, smem_prune, stream);
+  }
+
+  template <bool EX>
+  void launch_sweep_e(TreeDev<Real>& t, uint32_t iter, double* row) {
+    if (NS == 2) launch_sweep_t<2, EX>(t, iter, row);
+    else if (NS == 4) launch_sweep_t<4, EX>(t, iter, row);
+    else launch_sweep_t<0, EX>(t, iter, row);
+  }
+  template <bool EX>
+  void launch_prune_e(TreeDev<Real>& t) {
+    if (NS == 2) launch_prune_t<2, EX>(t);
+    else if (NS == 4) launch_prune_t<4, EX>(t);
+    else launch_prune_t<0, EX>(t);
+  }
+  void launch_sweep(TreeDev<Real>& t, uint32_t iter, double* row);
+  void launch_prune(TreeDev<Real>& t);
+
+  void begin_timed(int k) {
+    if (!timing) return;
+    Timed t; t.k = k;
+    CK(cudaEventCreate(&t.a)); CK(cudaEventCreate(&t.b));
+    CK(cudaEventRecord(t.a, stream));
+    timed.push_back(t);
+  }
+  void end_timed() {
+    if (!timing) return;
+    CK(cudaEventRecord(timed.back().b, stream));
+  }
+  void collect_timed() {
+    for (auto& t : timed) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, t.a, t.b);
+      kernel_ms[t.k] += ms;
+      cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+    }
+    timed.clear();
+  }
+
+  void check_device_errors() {
+    CK(cudaMemcpyAsync(err_h, err_flag.p, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const unsigned f = *err_h;
+    if (!f) return;
+    if (f & PM_DE_BAD_STATE) fail(PM_ERR_ARG, "tip states must lie in 1..n");
+    if (f & PM_DE_SAMPLE_NA) fail(PM_ERR_SAMPLE, "NAs not allowed in probability");
+    if (f & PM_DE_SAMPLE_NEG) fail(PM_ERR_SAMPLE, "Negative probabilities not allowed");
+    if (f & PM_DE_SAMPLE_ZERO) fail(PM_ERR_SAMPLE, "Not enough positive probabilities");
+    if (f & PM_DE_REPLAY) fail(PM_ERR_REPLAY, "replay table exhausted");
+    if (f & PM_DE_PATH_CAP) fail(PM_ERR_CAPACITY, "a branch carries more real jumps than its path capacity; raise pm_options.path_capacity");
+    if (f & PM_DE_M_OVERFLOW) fail(PM_ERR_CAPACITY, "more than 65535 pieces on one branch");
+    fail(PM_ERR_CUDA, "inconsistent chain state (device flag %u)", f);
+  }
+
+  // ---- construction ----
+  void create(int variant, const pm_tree* tr, int ntr, int n_, double* Q_, const double* pid_, double* B_, double Om,
+              const double* prior_, int nprior, int Ntot, const pm_options* o) {
+    V = variant_of(variant);
+    n = n_; ntrees = ntr; N_total = Ntot; Q = Q_; B = B_; Omega = Om;
+    opt = *o;
+    if (n < 2 || n > PM_NMAX) fail(PM_ERR_ARG, "number of states must be in 2..%d", PM_NMAX);
+    if (!V.multi && ntr != 1) fail(PM_ERR_ARG, "this sampler takes exactly one tree");
+    if (ntr < 1) fail(PM_ERR_ARG, "no trees");
+    if (Ntot < 0) fail(PM_ERR_ARG, "N must be non-negative");
+    if (V.hidden && (n < 4 || (n & 1))) fail(PM_ERR_ARG, "hidden-rate samplers need an even number of states >= 4");
+    if ((variant == PM_V_BF || variant == PM_V_MT) && n != 2) fail(PM_ERR_ARG, "this sampler is 2-state only");
+    const int need_prior = variant == PM_V_BF || variant == PM_V_MT ? 4 : variant == PM_V_KS ? 6 : variant == PM_V_KSMT ? 8 : 0;
+    if (nprior < need_prior || (need_prior && !prior_)) fail(PM_ERR_ARG, "prior needs %d values", need_prior);
+    if (need_prior) prior.assign(prior_, prior_ + nprior);
+    pid.assign(pid_, pid_ + n);
+    exact = opt.mode == PM_MODE_DETERMINISTIC;
+    if (exact && opt.precision != PM_F64) fail(PM_ERR_ARG, "deterministic mode computes in FP64");
+    if (opt.rng == PM_RNG_TABLE && (!opt.tab_off || !opt.tab_u)) fail(PM_ERR_ARG, "replay table missing");
+    if (opt.rng == PM_RNG_TABLE && !exact) fail(PM_ERR_ARG, "the replay table feeds the deterministic mode only");
+    if (opt.rng == PM_RNG_TABLE && (opt.site_offset != 0 || opt.allreduce)) fail(PM_ERR_ARG, "replay runs are single-process");
+    NS = (n == 2) ? 2 : (n == 4) ? 4 : 0;
+    W = n + n * n + 1;
+    ncols = ncols_of(variant, n);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) fail(PM_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+    if (opt.device < 0 || opt.device >= ndev) fail(PM_ERR_CUDA, "device %d not present", opt.device);
+    CK(cudaSetDevice(opt.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, opt.device));
+    if (prop.major != 10) fail(PM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", opt.device, prop.major, prop.minor);
+    if (opt.cuda_stream) stream = (cudaStream_t)opt.cuda_stream;
+    else { CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
+
+    const int T0 = tr[0].n_tips, E0 = tr[0].n_edges;
+    double tmax = 0, qmax = 0;
+    for (int s = 0; s < n; s++) qmax = std::max(qmax, -Q[s + (size_t)s * n]);
+    if (!(Omega > 0)) fail(PM_ERR_ARG, "Omega must be positive");
+
+    for (int ti = 0; ti < ntr; ti++) {
+      const pm_tree& x = tr[ti];
+      if (x.n_tips != T0 || x.n_edges != E0) fail(PM_ERR_ARG, "all trees must have the same number of tips");
+      if (x.n_sites < 1 || x.n_sites != tr[0].n_sites) fail(PM_ERR_ARG, "n_sites must be >= 1 and equal across trees");
+      if (!x.edge || !x.nen || !x.nodelist || !x.maps_off || !x.maps_len) fail(PM_ERR_ARG, "tree %d: missing field", ti);
+      if (!x.states && !x.states_u8) fail(PM_ERR_ARG, "tree %d: states missing", ti);
+      std::unique_ptr<TreeDev<Real>> t(new TreeDev<Real>());
+      try {
+        pm::host::build_schedule(x.n_tips, x.n_edges, x.edge, x.nen, x.nodelist, x.root, V.redraw_tips, t->sch);
+      } catch (const std::string& s) { fail(PM_ERR_ARG, "tree %d: %s", ti, s.c_str()); }
+      t->S = x.n_sites;
+      const int E = x.n_edges, T = x.n_tips;
+      std::vector<long long> moff(E + 1);
+      std::vector<Real> elen(E);
+      for (int e = 0; e <= E; e++) moff[e] = x.maps_off[e];
+      if (moff[0] != 0) fail(PM_ERR_ARG, "tree %d: maps_off[0] must be 0", ti);
+      for (int e = 0; e < E; e++) {
+        const long long a = moff[e], b = moff[e + 1];
+        if (b <= a) fail(PM_ERR_ARG, "tree %d: branch %d has no segments", ti, e + 1);
+        if (b - a > 65535) fail(PM_ERR_ARG, "tree %d: branch %d has more than 65535 segments", ti, e + 1);
+        double tot = 0;
+        for (long long p = a; p < b; p++) {
+          if (!(x.maps_len[p] >= 0)) fail(PM_ERR_ARG, "tree %d: negative or NA segment length", ti);
+          if (x.maps_state && (x.maps_state[p] < 1 || x.maps_state[p] > n)) fail(PM_ERR_ARG, "tree %d: mapnames out of range", ti);
+          tot = tot + x.maps_len[p];
+        }
+        elen[e] = (Real)tot;
+        tmax = std::max(tmax, tot);
+      }
+      std::vector<double> mlen(x.maps_len, x.maps_len + moff[E]);
+      const long long S = t->S;
+      // launch geometry of the path kernel: a thread owns one site x one chunk of consecutive branches
+      const long long gx = (S + 127) / 128;
+      long long ny = (148LL * 16 * 6 + gx - 1) / gx;
+      ny = std::max(1LL, std::min<long long>(ny, (E + 15) / 16));
+      ny = std::min<long long>(ny, 65535);
+      t->chunk = (int)((E + ny - 1) / ny);
+      ny = (E + t->chunk - 1) / t->chunk;
+      t->paths_grid = dim3((unsigned)gx, (unsigned)ny, 1);
+      t->nblocks = gx * ny;
+      // record capacity of every chunk from the Poisson tail of its real-jump count (real jumps are dominated by
+      // a Poisson process of rate max|Q_ii| along the chunk's total length); a multi-run path stores jumps + 1 runs
+      t->cap_off_h.assign(ny + 1, 0);
+      for (long long c = 0; c < ny; c++) {
+        const int b0 = (int)c * t->chunk, b1 = std::min(E, b0 + t->chunk);
+        double len = 0;
+        for (int e = b0; e < b1; e++) len += (double)elen[e];
+        int cap;
+        if (opt.path_capacity > 0) cap = opt.path_capacity * (b1 - b0);
+        else {
+          const double rate = V.rates ? std::min(Omega, 4 * qmax) : qmax;
+          const int jumps = poisson_cap(1.5 * rate * len + 1.0, 1e-18);
+          cap = exact ? (b1 - b0) + jumps : 2 * jumps;
+        }
+        if (exact && cap < 2 * (b1 - b0)) cap = 2 * (b1 - b0);
+        cap = (cap + 3) & ~3;  // keep every slice 16-byte aligned
+        t->cap_off_h[c + 1] = t->cap_off_h[c] + cap;
+      }
+      const long long R = t->cap_off_h[ny];
+      upload(t->up_entries, t->sch.up_entries, stream);
+      upload(t->up_off, t->sch.up_off, stream);
+      upload(t->down_entries, t->sch.down_entries, stream);
+      upload(t->down_off, t->sch.down_off, stream);
+      upload(t->e_parent, t->sch.e_parent, stream);
+      upload(t->e_child, t->sch.e_child, stream);
+      upload(t->e_len, elen, stream);
+      upload(t->maps_off, moff, stream);
+      upload(t->maps_len, mlen, stream);
+      upload(t->cap_off, t->cap_off_h, stream);
+      t->tipcode.alloc((size_t)T * S);
+      t->node_state.alloc((size_t)(2 * T - 1) * S);
+      t->meta.alloc((size_t)E * S * sizeof(uint32_t));
+      t->PL.alloc((size_t)(T - 1) * S * n * sizeof(Real));
+      for (int b = 0; b < 2; b++) {
+        t->rec_len[b].alloc((size_t)R * S * sizeof(Real));
+        t->rec_st[b].alloc((size_t)R * S);
+      }
+      CK(cudaMemsetAsync(t->node_state.p, 0, t->node_state.bytes, stream));
+      t->dw_partial.alloc((size_t)t->nblocks * n * sizeof(double));
+      dev_bytes += t->tipcode.bytes + t->node_state.bytes + t->meta.bytes + t->PL.bytes + 2 * (t->rec_len[0].bytes + t->rec_st[0].bytes) +
+                   t->dw_partial.bytes;
+      trees.push_back(std::move(t));
+    }
+
+    // table of powers
+    jcap = opt.power_capacity > 0 ? opt.power_capacity : 64;
+    if (opt.power_capacity <= 0) {
+      const double lam = Omega * tmax;
+      const double want = lam + 10 * std::sqrt(lam) + 24;
+      jcap = (int)std::min(16384.0, std::max(64.0, want));
+    }
+    if (jcap < 2) jcap = 2;
+    model.alloc(model_elems() * sizeof(Real));
+    ppow.alloc((size_t)jcap * n * n * sizeof(Real));
+    CK(cudaMallocHost((void**)&model_h, (model_elems() + (size_t)jcap * n * n) * sizeof(Real)));
+    CK(cudaMallocHost((void**)&rows_h, (size_t)ntrees * W * sizeof(double)));
+    CK(cudaMallocHost((void**)&err_h, sizeof(unsigned)));
+    cnt.alloc((size_t)n * n * sizeof(unsigned long long));
+    root_out.alloc(sizeof(int));
+    err_flag.alloc(sizeof(unsigned));
+    CK(cudaMemsetAsync(cnt.p, 0, cnt.bytes, stream));
+    CK(cudaMemsetAsync(root_out.p, 0, root_out.bytes, stream));
+    CK(cudaMemsetAsync(err_flag.p, 0, err_flag.bytes, stream));
+
+    // replay table
+    const int T = T0, E = E0;
+    const int spi = (2 * T - 1) + 2 * E;
+    if (opt.rng == PM_RNG_TABLE) {
+      const long long nslots = (long long)ntrees * trees[0]->S * N_total * spi;
+      std::vector<long long> off(nslots + 1);
+      for (long long i = 0; i <= nslots; i++) off[i] = opt.tab_off[i];
+      std::vector<double> u(opt.tab_u, opt.tab_u + off[nslots]);
+      upload(tab_off, off, stream);
+      upload(tab_u, u, stream);
+      if (opt.host_tab) replay.reset(new pm::host::ReplaySource(opt.host_tab, opt.host_tab_n));
+    }
+    mt.reseed((uint32_t)opt.seed);
+
+    // shared-memory sizes
+    const int np_fast = exact ? 0 : ((NS == 2 || NS == 4) ? std::min(PM_SMEM_POW, jcap) : 0);
+    smem_prune = ((size_t)n * n + (size_t)np_fast * n * n) * sizeof(Real);
+    smem_nodes = ((size_t)n * n + 3 * n + (size_t)np_fast * n * n) * sizeof(Real);
+    smem_paths = (size_t)4 * n * sizeof(double) + ((size_t)n * n + ((n * n) & 1)) * sizeof(unsigned) +
+                 ((size_t)2 * n * n + 3 * n + (size_t)np_fast * n * n) * sizeof(Real);
+
+    for (int ti = 0; ti < ntr; ti++) {
+      TreeDev<Real>& t = *trees[ti];
+      const pm_tree& x = tr[ti];
+      pm::ChainParams<Real>& P = t.P;
+      P.n = n; P.T = T; P.E = E; P.S = t.S;
+      P.cap_off = t.cap_off.template as<int>();
+      P.model = model.as<Real>(); P.ppow = ppow.as<Real>(); P.jcap = jcap;
+      P.up_entries = t.up_entries.template as<int>(); P.up_off = t.up_off.template as<int>();
+      P.n_up_levels = (int)t.sch.up_off.size() - 1;
+      P.down_entries = t.down_entries.template as<int>(); P.down_off = t.down_off.template as<int>();
+      P.n_down_levels = (int)t.sch.down_off.size() - 1;
+      P.e_parent = t.e_parent.template as<int>(); P.e_child = t.e_child.template as<int>();
+      P.e_len = t.e_len.template as<Real>();
+      P.maps_off = t.maps_off.template as<long long>(); P.maps_len = t.maps_len.template as<double>();
+      P.root = t.sch.root;
+      P.tipcode = t.tipcode.template as<uint8_t>(); P.node_state = t.node_state.template as<uint8_t>();
+      P.meta = t.meta.template as<uint32_t>(); P.PL = t.PL.template as<Real>();
+      for (int b = 0; b < 2; b++) { P.rec_len[b] = t.rec_len[b].template as<Real>(); P.rec_st[b] = t.rec_st[b].template as<uint8_t>(); }
+      P.normalize = V.normalize; P.full_counts = V.full_counts; P.parity_tips = V.parity_tips;
+      P.dw_partial = t.dw_partial.template as<double>(); P.cnt = cnt.as<unsigned long long>();
+      P.root_out = root_out.as<int>(); P.err_flag = err_flag.as<unsigned>();
+      const uint64_t key = opt.seed + (uint64_t)ti * 0x9E3779B97F4A7C15ull;
+      P.rng.k0 = (uint32_t)key; P.rng.k1 = (uint32_t)(key >> 32);
+      P.rng.site0 = (uint32_t)opt.site_offset;
+      P.rng.tab_off = opt.rng == PM_RNG_TABLE ? (const int64_t*)tab_off.p : nullptr;
+      P.rng.tab_u = opt.rng == PM_RNG_TABLE ? tab_u.as<double>() : nullptr;
+      P.rng.tab_site_stride = (int64_t)N_total * spi;
+      P.rng.tab_base = (int64_t)ti * t.S * N_total * spi;
+      P.rng.slots_per_iter = spi; P.rng.n_nodes = 2 * T - 1;
+
+      // tip states -> [T][S], staged in blocks of site rows
+      const size_t esz = x.states_u8 ? 1 : 4;
+      long long rows_per = std::max<long long>(32, (256LL << 20) / ((long long)T * (long long)esz));
+      rows_per = std::min<long long>(rows_per, std::min<long long>(t.S, 32LL * 65535));
+      DevBuf stage;
+      stage.alloc((size_t)rows_per * T * esz);
+      for (long long s0 = 0; s0 < t.S; s0 += rows_per) {
+        const int ns = (int)std::min<long long>(rows_per, t.S - s0);
+        const void* src = x.states_u8 ? (const void*)(x.states_u8 + s0 * T) : (const void*)(x.states + s0 * T);
+        CK(cudaMemcpyAsync(stage.p, src, (size_t)ns * T * esz, cudaMemcpyHostToDevice, stream));
+        dim3 g((T + 31) / 32, (ns + 31) / 32), b(32, 8);
+        if (x.states_u8)
+          pm::k_init_tips<uint8_t><<<g, b, 0, stream>>>(stage.as<uint8_t>(), ns, s0, t.S, T, n, V.parity_tips, t.tipcode.template as<uint8_t>(), P.node_state, P.err_flag);
+        else
+          pm::k_init_tips<int32_t><<<g, b, 0, stream>>>(stage.as<int32_t>(), ns, s0, t.S, T, n, V.parity_tips, t.tipcode.template as<uint8_t>(), P.node_state, P.err_flag);
+        CK(cudaStreamSynchronize(stream));
+      }
+      const long long tot = t.S * E;
+      pm::k_init_meta<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(P.maps_off, t.S, E, P.meta);
+      CK(cudaGetLastError());
+    }
+    stage_model(true);
+    check_device_errors();
+  }
+
+  void ensure_rows(int count) {
+    const int need = std::max(count, 1) * ntrees;
+    if (need <= rows_cap) return;
+    rows.alloc((size_t)need * W * sizeof(double));
+    rows_cap = need;
+  }
+
+  void write_fixed_row(const double* r, double* out, int64_t ld, int i) {
+    for (int s = 0; s < n; s++) out[i + (int64_t)s * ld] = r[s];
+    for (int a = 0; a < n; a++)
+      for (int b = 0; b < n; b++) {
+        if (a == b) continue;
+        const int col = n + a * (n - 1) + b - (a < b ? 1 : 0);
+        out[i + (int64_t)col * ld] = r[n + a * n + b];
+      }
+  }
+
+  void run(int count, double* out, int64_t ld) override {
+    if (count < 0 || iters_done + count > N_total) fail(PM_ERR_ARG, "cannot run %d more iterations (%d of %d done)", count, iters_done, N_total);
+    if (count == 0) return;
+    if (ld < count) fail(PM_ERR_ARG, "leading dimension smaller than the number of rows");
+    CK(cudaSetDevice(opt.device));
+    if (!V.rates) {
+      ensure_rows(count);
+      TreeDev<Real>& t = *trees[0];
+      for (int i = 0; i < count; i++) {
+        launch_sweep(t, (uint32_t)(iters_done + i), rows.as<double>() + (size_t)i * W);
+        if (opt.progress) { printf("%i \r", iters_done + i); }
+      }
+      CK(cudaGetLastError());
+      if (opt.allreduce) {
+        if (opt.allreduce(opt.allreduce_ctx, rows.as<double>(), count * W) != 0) fail(PM_ERR_CUDA, "allreduce callback failed");
+      }
+      std::vector<double> h((size_t)count * W);
+      CK(cudaMemcpyAsync(h.data(), rows.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      check_device_errors();
+      collect_timed();
+      for (int i = 0; i < count; i++) write_fixed_row(&h[(size_t)i * W], out, ld, i);
+      iters_done += count;
+      return;
+    }
+
+    // rate-updating samplers: one host round trip per iteration
+    ensure_rows(1);
+    pm::host::RateModel rm{n, Q, B, Omega, prior.data()};
+    pm::host::UniformSource& g = host_rng();
+    const int k = n / 2 - 1;
+    std::vector<double> row(ncols);
+    std::vector<std::vector<double>> jodt(ntrees, std::vector<double>(ncols, 0.0));
+    for (int i = 0; i < count; i++) {
+      const int it = iters_done;
+      if (V.multi && it == 0) (void)g.next();  // the draw before the loop, :2332 / :2810
+      for (int j = 0; j < ntrees; j++) launch_sweep(*trees[j], (uint32_t)it, rows.as<double>() + (size_t)j * W);
+      CK(cudaGetLastError());
+      if (opt.allreduce) {
+        if (opt.allreduce(opt.allreduce_ctx, rows.as<double>(), ntrees * W) != 0) fail(PM_ERR_CUDA, "allreduce callback failed");
+      }
+      CK(cudaMemcpyAsync(rows_h, rows.p, (size_t)ntrees * W * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      check_device_errors();
+      for (int j = 0; j < ntrees; j++) {
+        std::fill(jodt[j].begin(), jodt[j].end(), 0.0);
+        const double* r = rows_h + (size_t)j * W;
+        for (int c = 0; c < n + n * n; c++) jodt[j][c] = r[c];
+        if (V.hidden) rm.record_hidden(jodt[j].data()); else rm.record_two_state(jodt[j].data());
+        jodt[j][ncols - 1] = r[n + n * n];  // root state of global site 0 (overwritten by the tree index for mt)
+      }
+      int pick = 0;
+      if (V.multi) {  // sampleOnce with equal weights, :2347-2348
+        const double u = g.next();
+        double cum = 0;
+        for (pick = 0; pick < ntrees; pick++) { cum += 1.0 / ntrees; if (u < cum) break; }
+        if (pick >= ntrees) pick = ntrees - 1;
+        jodt[pick][ncols - 1] = pick;
+      }
+      const double* st = jodt[pick].data();
+      for (int c = 0; c < ncols; c++) out[i + (int64_t)c * ld] = st[c];
+      if (V.hidden) rm.hidden_rates(st, g, V.multi); else rm.two_state(st, g, V.multi);
+      if (g.exhausted()) fail(PM_ERR_REPLAY, "host replay table exhausted");
+      iters_done++;
+      stage_model(false);
+      if (opt.progress) { printf("%i \r", it); }
+      (void)k;
+    }
+    CK(cudaStreamSynchronize(stream));
+    collect_timed();
+  }
+
+  float time_prune(int tree, int reps) override {
+    if (tree < 0 || tree >= ntrees || reps < 1) fail(PM_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(opt.device));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    launch_prune(*trees[tree]);  // warm
+    CK(cudaEventRecord(a, stream));
+    for (int r = 0; r < reps; r++) launch_prune(*trees[tree]);
+    CK(cudaEventRecord(b, stream));
+    CK(cudaEventSynchronize(b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    CK(cudaGetLastError());
+    launches += reps + 1;
+    return ms / reps;
+  }
+
+  // ---- state read-back (parity tests) ----
+  void node_states(int tree, int32_t* out) override {
+    TreeDev<Real>& t = *trees.at(tree);
+    const int NN = 2 * t.sch.T - 1;
+    std::vector<uint8_t> h((size_t)NN * t.S);
+    CK(cudaMemcpy(h.data(), t.node_state.p, h.size(), cudaMemcpyDeviceToHost));
+    for (long long s = 0; s < t.S; s++) for (int v = 0; v < NN; v++) out[s * NN + v] = h[(size_t)v * t.S + s];
+  }
+  void piece_counts(int tree, int32_t* out) override {
+    TreeDev<Real>& t = *trees.at(tree);
+    const int E = t.sch.E;
+    std::vector<uint32_t> h((size_t)E * t.S);
+    CK(cudaMemcpy(h.data(), t.meta.p, h.size() * 4, cudaMemcpyDeviceToHost));
+    for (long long s = 0; s < t.S; s++) for (int e = 0; e < E; e++) out[s * E + e] = (int)(h[(size_t)e * t.S + s] & 0xffffu);
+  }
+  int path(int tree, int64_t site, int e, double* len, int32_t* st, int cap) override {
+    TreeDev<Real>& t = *trees.at(tree);
+    if (site < 0 || site >= t.S || e < 0 || e >= t.sch.E) fail(PM_ERR_ARG, "bad site / branch");
+    uint32_t m = 0;
+    CK(cudaMemcpy(&m, t.meta.template as<uint32_t>() + (size_t)e * t.S + site, 4, cudaMemcpyDeviceToHost));
+    const int nj = (m >> 16) & 0xff, s0 = m >> 24;
+    if (iters_done == 0) fail(PM_ERR_ARG, "no sweep done yet");
+    if (!exact && nj == 0) {
+      Real L;
+      CK(cudaMemcpy(&L, t.e_len.template as<Real>() + e, sizeof(Real), cudaMemcpyDeviceToHost));
+      if (cap > 0) { len[0] = (double)L; st[0] = s0; }
+      return 1;
+    }
+    // locate the branch's records inside the (site, chunk) slice written by the last sweep
+    const int c = e / t.chunk, b0 = c * t.chunk;
+    const int cap_c = t.cap_off_h[c + 1] - t.cap_off_h[c];
+    long long pos = 0;
+    for (int e2 = b0; e2 < e; e2++) {
+      uint32_t m2 = 0;
+      CK(cudaMemcpy(&m2, t.meta.template as<uint32_t>() + (size_t)e2 * t.S + site, 4, cudaMemcpyDeviceToHost));
+      const int nj2 = (m2 >> 16) & 0xff;
+      pos += (exact || nj2 > 0) ? nj2 + 1 : 0;
+    }
+    const int buf = (iters_done - 1) & 1;
+    const size_t base = (size_t)t.cap_off_h[c] * t.S + (size_t)site * cap_c + pos;
+    for (int k = 0; k <= nj && k < cap; k++) {
+      Real L; uint8_t s;
+      CK(cudaMemcpy(&L, t.rec_len[buf].template as<Real>() + base + k, sizeof(Real), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(&s, t.rec_st[buf].template as<uint8_t>() + base + k, 1, cudaMemcpyDeviceToHost));
+      len[k] = (double)L; st[k] = s;
+    }
+    return nj + 1;
+  }
+  void partials(int tree, int64_t site, double* out) override {
+    TreeDev<Real>& t = *trees.at(tree);
+    const int T = t.sch.T;
+    if (site < 0 || site >= t.S) fail(PM_ERR_ARG, "bad site");
+    std::fill(out, out + (size_t)(2 * T - 1) * n, 0.0);
+    std::vector<Real> v(n);
+    for (int i = 0; i < T - 1; i++) {
+      CK(cudaMemcpy(v.data(), t.PL.template as<Real>() + ((size_t)i * t.S + site) * n, n * sizeof(Real), cudaMemcpyDeviceToHost));
+      for (int j = 0; j < n; j++) out[(size_t)(T + i) * n + j] = (double)v[j];
+    }
+  }
+};
+
+template <> void ChainT<double>::launch_sweep(TreeDev<double>& t, uint32_t iter, double* row) {
+  if (exact) launch_sweep_e<true>(t, iter, row); else launch_sweep_e<false>(t, iter, row);
+}
+template <> void ChainT<float>::launch_sweep(TreeDev<float>& t, uint32_t iter, double* row) { launch_sweep_e<false>(t, iter, row); }
+template <> void ChainT<double>::launch_prune(TreeDev<double>& t) {
+  if (exact) launch_prune_e<true>(t); else launch_prune_e<false>(t);
+}
+template <> void ChainT<float>::launch_prune(TreeDev<float>& t) { launch_prune_e<false>(t); }
+
+pm_chain* make_chain(int variant, const pm_tree* trees, int ntrees, int n, double* Q, const double* pid, double* B,
+                     double Omega, const double* prior, int nprior, int N_total, const pm_options* opt) {
+  pm_options def;
+  if (!opt) { pm_default_options(&def); opt = &def; }
+  if (!trees || !Q || !pid || !B) fail(PM_ERR_ARG, "null argument");
+  if (variant < PM_V_PLAIN || variant > PM_V_KSMT) fail(PM_ERR_ARG, "unknown variant");
+  if (opt->precision == PM_F32) {
+    std::unique_ptr<ChainT<float>> c(new ChainT<float>());
+    c->create(variant, trees, ntrees, n, Q, pid, B, Omega, prior, nprior, N_total, opt);
+    return c.release();
+  }
+  std::unique_ptr<ChainT<double>> c(new ChainT<double>());
+  c->create(variant, trees, ntrees, n, Q, pid, B, Omega, prior, nprior, N_total, opt);
+  return c.release();
+}
+
+int one_call(int variant, const pm_tree* trees, int ntrees, int n, double* Q, const double* pid, double* B, double Omega,
+             int N, const double* prior, int nprior, const pm_options* opt, double* out, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!out && N > 0) fail(PM_ERR_ARG, "null output");
+    std::unique_ptr<pm_chain> c(make_chain(variant, trees, ntrees, n, Q, pid, B, Omega, prior, nprior, N, opt));
+    c->run(N, out, N);
+  });
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+void pm_default_options(pm_options* o) {
+  memset(o, 0, sizeof *o);
+  o->precision = PM_F64;
+  o->mode = PM_MODE_PRODUCTION;
+  o->rng = PM_RNG_PHILOX;
+  o->seed = 1;
+}
+
+int32_t pm_ncols(int32_t variant, int32_t n) { return ncols_of(variant, n); }
+
+int pm_maketreelistMCMC(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega, int32_t N,
+                        const pm_options* opt, double* out, char* err, size_t errlen) {
+  return one_call(PM_V_PLAIN, x, 1, n, Q, pid, B, Omega, N, nullptr, 0, opt, out, err, errlen);
+}
+int pm_SPARSEmaketreelistMCMC(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega,
+                              int32_t N, const pm_options* opt, double* out, char* err, size_t errlen) {
+  return one_call(PM_V_SPARSE, x, 1, n, Q, pid, B, Omega, N, nullptr, 0, opt, out, err, errlen);
+}
+int pm_maketreelistMCMC_bigtree(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega,
+                                int32_t N, const pm_options* opt, double* out, char* err, size_t errlen) {
+  return one_call(PM_V_BIGTREE, x, 1, n, Q, pid, B, Omega, N, nullptr, 0, opt, out, err, errlen);
+}
+int pm_maketreelistMCMCbf(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega, int32_t N,
+                          const double* prior, int32_t nprior, const pm_options* opt, double* out, char* err,
+                          size_t errlen) {
+  return one_call(PM_V_BF, x, 1, n, Q, pid, B, Omega, N, prior, nprior, opt, out, err, errlen);
+}
+int pm_maketreelistMCMCks(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega, int32_t N,
+                          const double* prior, int32_t nprior, const pm_options* opt, double* out, char* err,
+                          size_t errlen) {
+  return one_call(PM_V_KS, x, 1, n, Q, pid, B, Omega, N, prior, nprior, opt, out, err, errlen);
+}
+int pm_maketreelistMCMCmt(const pm_tree* trees, int32_t ntrees, int32_t n, double* Q, const double* pid, double* B,
+                          double Omega, int32_t N, const double* prior, int32_t nprior, const pm_options* opt,
+                          double* out, char* err, size_t errlen) {
+  return one_call(PM_V_MT, trees, ntrees, n, Q, pid, B, Omega, N, prior, nprior, opt, out, err, errlen);
+}
+int pm_maketreelistMCMCksmt(const pm_tree* trees, int32_t ntrees, int32_t n, double* Q, const double* pid, double* B,
+                            double Omega, int32_t N, const double* prior, int32_t nprior, const pm_options* opt,
+                            double* out, char* err, size_t errlen) {
+  return one_call(PM_V_KSMT, trees, ntrees, n, Q, pid, B, Omega, N, prior, nprior, opt, out, err, errlen);
+}
+
+int pm_tree_order(const int32_t* edge, int32_t n_edges, int32_t n_tips, int32_t* nen, int32_t* nodelist, int32_t* root,
+                  char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!edge || !nen || !nodelist || !root) fail(PM_ERR_ARG, "null argument");
+    pm::host::tree_order(edge, n_edges, n_tips, nen, nodelist, root);
+  });
+}
+
+int pm_chain_create(int32_t variant, const pm_tree* trees, int32_t ntrees, int32_t n, double* Q, const double* pid,
+                    double* B, double Omega, const double* prior, int32_t nprior, int32_t N_total, const pm_options* opt,
+                    pm_chain** out, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!out) fail(PM_ERR_ARG, "null output");
+    *out = make_chain(variant, trees, ntrees, n, Q, pid, B, Omega, prior, nprior, N_total, opt);
+  });
+}
+int pm_chain_run(pm_chain* c, int32_t count, double* out, int64_t ld, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!c || (!out && count > 0)) fail(PM_ERR_ARG, "null argument");
+    c->run(count, out, ld);
+  });
+}
+int pm_chain_time_prune(pm_chain* c, int32_t tree, int32_t reps, float* ms_per_pass, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!c || !ms_per_pass) fail(PM_ERR_ARG, "null argument");
+    *ms_per_pass = c->time_prune(tree, reps);
+  });
+}
+void pm_chain_kernel_times(pm_chain* c, double ms[4], int64_t* launches) {
+  for (int i = 0; i < 4; i++) ms[i] = c->kernel_ms[i];
+  if (launches) *launches = c->launches;
+}
+void pm_chain_enable_timing(pm_chain* c, int32_t on) { c->timing = on != 0; }
+int pm_chain_get_node_states(pm_chain* c, int32_t tree, int32_t* out) {
+  return guarded(nullptr, 0, [&] { c->node_states(tree, out); });
+}
+int pm_chain_get_piece_counts(pm_chain* c, int32_t tree, int32_t* out) {
+  return guarded(nullptr, 0, [&] { c->piece_counts(tree, out); });
+}
+int pm_chain_get_path(pm_chain* c, int32_t tree, int64_t site, int32_t e, double* len, int32_t* st, int32_t cap) {
+  int r = -1;
+  const int rc = guarded(nullptr, 0, [&] { r = c->path(tree, site, e, len, st, cap); });
+  return rc == PM_OK ? r : -rc;
+}
+int pm_chain_get_partials(pm_chain* c, int32_t tree, int64_t site, double* out) {
+  return guarded(nullptr, 0, [&] { c->partials(tree, site, out); });
+}
+int64_t pm_chain_device_bytes(pm_chain* c) { return c->dev_bytes; }
+void pm_chain_destroy(pm_chain* c) { delete c; }
+
+int pm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return -PM_ERR_CUDA;
+  int ok = 0;
+  for (int d = 0; d < n; d++) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ok++;
+  }
+  return ok;
+}
+const char* pm_version(void) { return "phylomap_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -13,9 +13,12 @@
 //   node_state [2T-1][S]   u8   current state of every node
 //   meta       [E][S]      u32  m (pieces on the branch, bits 0-15) | real jumps nj (16-23) | first state (24-31)
 //   PL         [T-1][S][n] Real partial likelihoods of the internal nodes (one 16-byte vector per site for n=4 fp32)
-//   seg_len    [C][E][S]   Real merged real path: segment lengths   } only touched for branches that carry a real
-//   seg_st     [C][E][S]   u8   merged real path: segment states    } jump (production) — virtual jumps are never
-//                                                                      stored, they are regenerated from their key
+//   rec_len/st [chunk][S][cap_c]  merged real paths as (length Real, state u8) records, double-buffered.  A thread
+//                                 owns one (site, chunk of consecutive branches); it appends the runs of every
+//                                 branch that carries a real jump to its private slice and reads them back in the
+//                                 same order one sweep later.  cap_c comes from the Poisson tail of the chunk's
+//                                 real-jump count, so the slices are ~100x smaller than a per-branch worst case.
+//                                 Virtual jumps are never stored: they are regenerated from their Philox key.
 #pragma once
 #include <type_traits>
 #include "pm_device.cuh"
@@ -24,7 +27,8 @@ namespace pm {
 
 template <typename Real>
 struct ChainParams {
-  int n, T, E, C;
+  int n, T, E;
+  const int* cap_off;  // [n_chunks+1] prefix sums of the record capacities of the branch chunks (see k_paths)
   long long S;
   const Real* model;  // [B n*n | Bs n*n | pid n | scale_old n | scale_new n], matrices row-major
   const Real* ppow;   // [jcap][n*n] P_j = Bs * P_{j-1}
@@ -34,7 +38,8 @@ struct ChainParams {
   const int* e_parent; const int* e_child; const Real* e_len;
   const long long* maps_off; const double* maps_len;
   int root;
-  const uint8_t* tipcode; uint8_t* node_state; uint32_t* meta; Real* PL; Real* seg_len; uint8_t* seg_st;
+  const uint8_t* tipcode; uint8_t* node_state; uint32_t* meta; Real* PL;
+  Real* rec_len[2]; uint8_t* rec_st[2];  // double-buffered path records: written by sweep i into [i & 1], read by sweep i + 1
   int normalize, full_counts, parity_tips;
   double* dw_partial; unsigned long long* cnt; int* root_out;
   unsigned* err_flag;
@@ -44,7 +49,7 @@ struct ChainParams {
 template <typename Real, int NC>
 __device__ __forceinline__ void tip_partial(int code, int n, bool parity, Real* v) {
 #pragma unroll
-  for (int j = 0; j < NC; j++) if (j < n) v[j] = parity ? (Real)((j & 1) != code) : (Real)(j == code);
+  for (int j = 0; j < n; j++) v[j] = parity ? (Real)((j & 1) != code) : (Real)(j == code);
 }
 
 // v <- Bs^k v
@@ -105,22 +110,22 @@ __global__ void __launch_bounds__(256) k_prune(ChainParams<Real> P) {
         apply_power<Real, NC, EXACT>(P, sBs, sPow, npow_s, n, ka, va);
         Real out[NC];
 #pragma unroll
-        for (int j = 0; j < NC; j++) if (j < n) out[j] = Ar<Real, EXACT>::mul(vb[j], va[j]);
+        for (int j = 0; j < n; j++) out[j] = Ar<Real, EXACT>::mul(vb[j], va[j]);
         if (P.normalize) {
           if (EXACT) {  // arma::accu order on a row view: two interleaved accumulators
             Real a1 = 0, a2 = 0;
 #pragma unroll
-            for (int j = 0; j < NC; j++) if (j < n) { if (j & 1) a2 = Ar<Real, true>::add(a2, out[j]); else a1 = Ar<Real, true>::add(a1, out[j]); }
+            for (int j = 0; j < n; j++) { if (j & 1) a2 = Ar<Real, true>::add(a2, out[j]); else a1 = Ar<Real, true>::add(a1, out[j]); }
             const Real s = Ar<Real, true>::add(a1, a2);
 #pragma unroll
-            for (int j = 0; j < NC; j++) if (j < n) out[j] = Ar<Real, true>::div(out[j], s);
+            for (int j = 0; j < n; j++) out[j] = Ar<Real, true>::div(out[j], s);
           } else {
             Real s = 0;
 #pragma unroll
-            for (int j = 0; j < NC; j++) if (j < n) s += out[j];
+            for (int j = 0; j < n; j++) s += out[j];
             const Real inv = (Real)1 / s;
 #pragma unroll
-            for (int j = 0; j < NC; j++) if (j < n) out[j] *= inv;
+            for (int j = 0; j < n; j++) out[j] *= inv;
           }
         }
         VecIO<Real, NS>::store(P.PL + ((long long)(pn - P.T) * S + site) * n, n, out);
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(256) k_nodes(ChainParams<Real> P, uint32_t ite
     Real w[NC], pl[NC];
     VecIO<Real, NS>::load(P.PL + ((long long)(P.root - P.T) * S + site) * n, n, pl);
 #pragma unroll
-    for (int j = 0; j < NC; j++) if (j < n) w[j] = Ar<Real, EXACT>::mul(sVec[j], pl[j]);
+    for (int j = 0; j < n; j++) w[j] = Ar<Real, EXACT>::mul(sVec[j], pl[j]);
     Stream g; g.open(P.rng, (uint32_t)site, iter, K_NODE, (uint32_t)P.root, P.err_flag);
     const int s = categorical<Real, NC, EXACT>(w, n, g.next(), P.err_flag);
     P.node_state[(long long)P.root * S + site] = (uint8_t)s;
@@ -175,19 +180,19 @@ __global__ void __launch_bounds__(256) k_nodes(ChainParams<Real> P, uint32_t ite
           const Real* M = (k < npow_s) ? (sPow + k * n * n) : (k < P.jcap ? P.ppow + (size_t)k * n * n : nullptr);
           if (M) {
 #pragma unroll
-            for (int j = 0; j < NC; j++) if (j < n) w[j] = M[ps * n + j];
+            for (int j = 0; j < n; j++) w[j] = M[ps * n + j];
             done = true;
           }
         }
         if (!done) {  // (B^T)^k e_ps as k mat-vecs, Tvmmp :431-436
 #pragma unroll
-          for (int j = 0; j < NC; j++) if (j < n) w[j] = (Real)(j == ps);
+          for (int j = 0; j < n; j++) w[j] = (Real)(j == ps);
           for (int r = 0; r < k; r++) matvec_t<Real, NC, EXACT>(sBs, n, w);
         }
         if (v < P.T) tip_partial<Real, NC>(P.tipcode[(long long)v * S + site], n, parity, pl);
         else VecIO<Real, NS>::load(P.PL + ((long long)(v - P.T) * S + site) * n, n, pl);
 #pragma unroll
-        for (int j = 0; j < NC; j++) if (j < n) w[j] = Ar<Real, EXACT>::mul(w[j], pl[j]);
+        for (int j = 0; j < n; j++) w[j] = Ar<Real, EXACT>::mul(w[j], pl[j]);
         Stream g; g.open(P.rng, (uint32_t)site, iter, K_NODE, (uint32_t)v, P.err_flag);
         const int s = categorical<Real, NC, EXACT>(w, n, g.next(), P.err_flag);
         P.node_state[(long long)v * S + site] = (uint8_t)s;
@@ -228,7 +233,13 @@ __global__ void __launch_bounds__(128) k_paths(ChainParams<Real> P, uint32_t ite
   const long long site = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = site < S;
   const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
-  const int C = P.C, E = P.E;
+  const int cap0 = __ldg(P.cap_off + blockIdx.y), cap_c = __ldg(P.cap_off + blockIdx.y + 1) - cap0;
+  const long long abase = (long long)cap0 * S + (active ? site : 0) * (long long)cap_c;
+  const Real* __restrict__ rd_len = P.rec_len[(iter & 1u) ^ 1u] + abase;
+  const uint8_t* __restrict__ rd_st = P.rec_st[(iter & 1u) ^ 1u] + abase;
+  Real* __restrict__ wr_len = P.rec_len[iter & 1u] + abase;
+  uint8_t* __restrict__ wr_st = P.rec_st[iter & 1u] + abase;
+  int rd = 0, wr = 0;
   const bool full = P.full_counts != 0;
   Acc Racc[NS > 0 ? NS : 1];
 #pragma unroll
@@ -249,10 +260,8 @@ __global__ void __launch_bounds__(128) k_paths(ChainParams<Real> P, uint32_t ite
       if (nout == 0) sfirst = s;
       const bool skip = (!EXACT) && final_run && nout == 0;  // single-run path: length == t_e, state in meta
       if (!skip) {
-        if (nout < C) {
-          const long long ps_ = ((long long)nout * E + e) * S + site;
-          P.seg_len[ps_] = L; P.seg_st[ps_] = (uint8_t)s;
-        } else errbits |= PM_DE_PATH_CAP;
+        if (wr < cap_c && nout < PM_LOCAL_PATH_MAX) { wr_len[wr] = L; wr_st[wr] = (uint8_t)s; wr++; }
+        else errbits |= PM_DE_PATH_CAP;
       }
       if (NS > 0) {
 #pragma unroll
@@ -280,11 +289,9 @@ __global__ void __launch_bounds__(128) k_paths(ChainParams<Real> P, uint32_t ite
       if (!first) {
         if (!EXACT && nj == 0) { nin = 1; in_len[0] = __ldg(P.e_len + e); in_st[0] = (uint8_t)s0; }
         else {
-          nin = nj + 1;
-          for (int c = 0; c < nin; c++) {
-            const long long q = ((long long)c * E + e) * S + site;
-            in_len[c] = P.seg_len[q]; in_st[c] = P.seg_st[q];
-          }
+          nin = min(nj + 1, PM_LOCAL_PATH_MAX);
+          for (int c = 0; c < nin; c++) { const int q = min(rd + c, cap_c - 1); in_len[c] = rd_len[q]; in_st[c] = rd_st[q]; }
+          rd += nj + 1;
         }
       }
       Stream gold; gold.open(P.rng, (uint32_t)site, iter - 1u, K_BREXP, (uint32_t)e, P.err_flag);
@@ -316,14 +323,14 @@ __global__ void __launch_bounds__(128) k_paths(ChainParams<Real> P, uint32_t ite
           const Real* M = (jd < npow_s) ? (sPow + jd * n * n) : (jd < P.jcap ? P.ppow + (size_t)jd * n * n : nullptr);
           if (M) {
 #pragma unroll
-            for (int c = 0; c < NC; c++) if (c < n) w[c] = M[c * n + cs];
+            for (int c = 0; c < n; c++) w[c] = M[c * n + cs];
           } else {
 #pragma unroll
-            for (int c = 0; c < NC; c++) if (c < n) w[c] = (Real)(c == cs);
+            for (int c = 0; c < n; c++) w[c] = (Real)(c == cs);
             for (int r = 0; r < jd; r++) matvec<Real, NC, EXACT>(sBs, n, w);
           }
 #pragma unroll
-          for (int c = 0; c < NC; c++) if (c < n) w[c] = A::mul(sB[prev * n + c], w[c]);
+          for (int c = 0; c < n; c++) w[c] = A::mul(sB[prev * n + c], w[c]);
           st = categorical<Real, NC, EXACT>(w, n, gst.next(), P.err_flag);
         }
         const Real len = next_piece();
@@ -341,7 +348,7 @@ __global__ void __launch_bounds__(128) k_paths(ChainParams<Real> P, uint32_t ite
       emit(cur_len, cur_state, true);
     }
     if (newm > 65535) { errbits |= PM_DE_M_OVERFLOW; newm = 65535; }
-    if (nout - 1 > 255) { errbits |= PM_DE_PATH_CAP; nout = 256; }
+    if (nout > PM_LOCAL_PATH_MAX) nout = PM_LOCAL_PATH_MAX;  // flagged in emit
     P.meta[pe] = (uint32_t)newm | ((uint32_t)(nout - 1) << 16) | ((uint32_t)sfirst << 24);
   }
   if (errbits) atomicOr(P.err_flag, errbits);
@@ -366,50 +373,6 @@ __global__ void __launch_bounds__(128) k_paths(ChainParams<Real> P, uint32_t ite
     P.dw_partial[blk * n + threadIdx.x] = v;
   }
   for (int i = threadIdx.x; i < n * n; i += blockDim.x) if (s_cnt[i]) atomicAdd(&P.cnt[i], (unsigned long long)s_cnt[i]);
-}
-
-// ------------------------------------------------------------------------------------------------
-// K4: one row of sufficient statistics [R(n) | N(n*n) | root].  One block, fixed summation order.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ dw_partial, long long nblocks, int n,
-                                                unsigned long long* cnt, const int* root, double* row, int accumulate) {
-  __shared__ double sh[256];
-  for (int j = 0; j < n; j++) {
-    double acc = 0;
-    for (long long b = threadIdx.x; b < nblocks; b += 256) acc += dw_partial[b * n + j];
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
-    if (threadIdx.x == 0) row[j] = (accumulate ? row[j] : 0.0) + sh[0];
-    __syncthreads();
-  }
-  for (int i = threadIdx.x; i < n * n; i += 256) { row[n + i] = (accumulate ? row[n + i] : 0.0) + (double)cnt[i]; cnt[i] = 0ull; }
-  if (threadIdx.x == 0 && !accumulate) row[n + n * n] = (double)(*root);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Set-up kernels.
-// ------------------------------------------------------------------------------------------------
-// states [S][T] (int32 1-based, or u8) -> tipcode [T][S], node_state[tip] ; validates the range
-template <typename In>
-__global__ void k_init_tips(const In* __restrict__ states, long long S, int T, int n, int parity, uint8_t* tipcode,
-                            uint8_t* node_state, unsigned* err_flag) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S * T) return;
-  const long long t = i / S, s = i % S;
-  const int v = (int)states[s * T + t];
-  uint8_t code;
-  if (parity) code = (uint8_t)(v & 1);
-  else { if (v < 1 || v > n) { atomicOr(err_flag, PM_DE_SAMPLE_NA); code = 0; } else code = (uint8_t)(v - 1); }
-  tipcode[t * S + s] = code;
-  node_state[t * S + s] = parity ? (uint8_t)(code ? 0 : 1) : code;
-}
-
-__global__ void k_init_meta(const long long* __restrict__ maps_off, long long S, int E, uint32_t* meta) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S * E) return;
-  const long long e = i / S;
-  meta[i] = (uint32_t)(maps_off[e + 1] - maps_off[e]);
 }
 
 }  // namespace pm

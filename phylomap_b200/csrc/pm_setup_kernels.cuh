@@ -1,0 +1,67 @@
+// Set-up and reduction kernels (not templated on the arithmetic): included by pm_host.cu only.
+#pragma once
+#include "pm_device.cuh"
+
+namespace pm {
+
+// ------------------------------------------------------------------------------------------------
+// K4: one row of sufficient statistics [R(n) | N(n*n) | root].  One block, fixed summation order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ dw_partial, long long nblocks, int n,
+                                                unsigned long long* cnt, const int* root, double* row, int accumulate) {
+  __shared__ double sh[256];
+  for (int j = 0; j < n; j++) {
+    double acc = 0;
+    for (long long b = threadIdx.x; b < nblocks; b += 256) acc += dw_partial[b * n + j];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) row[j] = (accumulate ? row[j] : 0.0) + sh[0];
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n * n; i += 256) { row[n + i] = (accumulate ? row[n + i] : 0.0) + (double)cnt[i]; cnt[i] = 0ull; }
+  if (threadIdx.x == 0 && !accumulate) row[n + n * n] = (double)(*root);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Set-up kernels.
+// ------------------------------------------------------------------------------------------------
+// states [ns][T] (a staged block of site rows; int32 1-based, or u8) -> tipcode / node_state [T][S] at site s_base.
+// Tiled transpose through shared memory: reads coalesced along T, writes coalesced along S.  Validates the range.
+template <typename In>
+__global__ void __launch_bounds__(256) k_init_tips(const In* __restrict__ states, int ns, long long s_base, long long S,
+                                                   int T, int n, int parity, uint8_t* tipcode, uint8_t* node_state,
+                                                   unsigned* err_flag) {
+  __shared__ uint8_t tile[32][33];
+  const int t0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int s = s0 + r, t = t0 + threadIdx.x;
+    if (s < ns && t < T) {
+      const int v = (int)states[(long long)s * T + t];
+      uint8_t code;
+      if (parity) code = (uint8_t)(v & 1);
+      else if (v < 1 || v > n) { atomicOr(err_flag, PM_DE_BAD_STATE); code = 0; }
+      else code = (uint8_t)(v - 1);
+      tile[r][threadIdx.x] = code;
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int t = t0 + r, s = s0 + threadIdx.x;
+    if (s < ns && t < T) {
+      const uint8_t code = tile[threadIdx.x][r];
+      const long long o = (long long)t * S + s_base + s;
+      tipcode[o] = code;
+      node_state[o] = parity ? (uint8_t)(code ? 0 : 1) : code;
+    }
+  }
+}
+
+__global__ void k_init_meta(const long long* __restrict__ maps_off, long long S, int E, uint32_t* meta) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * E) return;
+  const long long e = i / S;
+  meta[i] = (uint32_t)(maps_off[e + 1] - maps_off[e]);
+}
+
+}  // namespace pm

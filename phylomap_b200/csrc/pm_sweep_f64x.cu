@@ -1,0 +1,4 @@
+// Sweep kernels, double deterministic arithmetic, 2 and 4 states.
+#include "pm_launch_impl.cuh"
+template struct pm::Sweep<double, 2, true>;
+template struct pm::Sweep<double, 4, true>;

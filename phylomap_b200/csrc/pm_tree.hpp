@@ -1,0 +1,156 @@
+// Host-side tree preparation: validation of the reference's tree inputs (x$edge, nen, nodelist, root — the
+// arguments of every maketreelist* entry, src/phylomap.cpp:891) and their conversion into the level schedules
+// the kernels walk.  Also the O(E) replacement of the R helpers pruningwiseedgeorder / makenodelist / myreorder
+// (R/sumstatMCMC.R:1-18), which are O(E^2) R loops in the reference.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace pm {
+namespace host {
+
+struct Schedule {
+  int T = 0, E = 0, root = 0;              // root 0-based
+  std::vector<int> e_parent, e_child;      // 0-based node ids per edge row
+  std::vector<int> parent_edge;            // per node: the edge row arriving at it (-1 for the root)
+  std::vector<int> up_entries, up_off;     // 5 ints per internal node (parent, a, ea, b, eb), grouped by height
+  std::vector<int> down_entries, down_off; // 3 ints per drawn node (v, parent, edge), grouped by depth
+};
+
+// Throws std::string on malformed input.
+inline void build_schedule(int T, int E, const int32_t* edge, const int32_t* nen, const int32_t* nodelist, int root1,
+                           bool draw_tips, Schedule& s) {
+  if (T < 2) throw std::string("tree needs at least 2 tips");
+  if (E != 2 * T - 2) throw std::string("only binary trees are supported: nrow(edge) must be 2*length(states)-2");
+  const int NN = 2 * T - 1;
+  if (root1 <= T || root1 > NN) throw std::string("root must be an internal node");
+  s.T = T; s.E = E; s.root = root1 - 1;
+  s.e_parent.resize(E); s.e_child.resize(E);
+  s.parent_edge.assign(NN, -1);
+  std::vector<int> nchild(NN, 0);
+  for (int e = 0; e < E; e++) {
+    const int p = edge[e], c = edge[E + e];
+    if (p <= T || p > NN) throw std::string("edge[,1] must hold internal nodes (T+1..2T-1)");
+    if (c < 1 || c > NN) throw std::string("edge[,2] out of range");
+    if (c == root1) throw std::string("the root cannot be a child");
+    if (s.parent_edge[c - 1] >= 0) throw std::string("a node has two parent edges");
+    s.e_parent[e] = p - 1; s.e_child[e] = c - 1;
+    s.parent_edge[c - 1] = e;
+    nchild[p - 1]++;
+  }
+  for (int v = T; v < NN; v++) if (nchild[v] != 2) throw std::string("every internal node needs exactly two children");
+
+  // pruning order -> heights
+  std::vector<int> height(NN, -1);
+  for (int v = 0; v < T; v++) height[v] = 0;
+  std::vector<char> used(E, 0);
+  const int Nn = T - 1;
+  std::vector<int> pair_parent(Nn), pair_h(Nn);
+  int maxh = 0;
+  for (int i = 0; i < Nn; i++) {
+    const int ea = nen[2 * i] - 1, eb = nen[2 * i + 1] - 1;
+    if (ea < 0 || ea >= E || eb < 0 || eb >= E || ea == eb) throw std::string("nen holds an invalid edge row");
+    if (used[ea] || used[eb]) throw std::string("nen is not a permutation of the edge rows");
+    used[ea] = used[eb] = 1;
+    if (s.e_parent[ea] != s.e_parent[eb]) throw std::string("nen must list sibling edges next to each other");
+    const int a = s.e_child[ea], b = s.e_child[eb], p = s.e_parent[ea];
+    if (height[a] < 0 || height[b] < 0) throw std::string("nen is not a pruning-wise order (a child is used before it is computed)");
+    height[p] = 1 + (height[a] > height[b] ? height[a] : height[b]);
+    pair_parent[i] = p; pair_h[i] = height[p];
+    if (height[p] > maxh) maxh = height[p];
+  }
+  s.up_off.assign(maxh + 1, 0);  // levels 1..maxh -> slots 0..maxh-1
+  for (int i = 0; i < Nn; i++) s.up_off[pair_h[i]]++;
+  {
+    int acc = 0;
+    for (int h = 1; h <= maxh; h++) { const int c = s.up_off[h]; s.up_off[h - 1] = acc; acc += c; }
+    s.up_off[maxh] = acc;
+  }
+  s.up_entries.resize((size_t)5 * Nn);
+  {
+    std::vector<int> cur(s.up_off.begin(), s.up_off.end() - 1);
+    for (int i = 0; i < Nn; i++) {
+      const int ea = nen[2 * i] - 1, eb = nen[2 * i + 1] - 1;
+      int* en = &s.up_entries[(size_t)5 * cur[pair_h[i] - 1]++];
+      en[0] = pair_parent[i]; en[1] = s.e_child[ea]; en[2] = ea; en[3] = s.e_child[eb]; en[4] = eb;
+    }
+  }
+
+  // top-down order -> depths
+  std::vector<int> depth(NN, -1);
+  depth[s.root] = 0;
+  int maxd = 0;
+  for (int i = 0; i < T - 2; i++) {
+    const int v = nodelist[i] - 1;
+    if (v < T || v >= NN || v == s.root) throw std::string("nodelist must hold the internal nodes below the root");
+    if (depth[v] >= 0) throw std::string("nodelist repeats a node");
+    const int p = s.e_parent[s.parent_edge[v]];
+    if (depth[p] < 0) throw std::string("nodelist is not top-down (a node comes before its parent)");
+    depth[v] = depth[p] + 1;
+    if (depth[v] > maxd) maxd = depth[v];
+  }
+  if (draw_tips) for (int v = 0; v < T; v++) {
+    depth[v] = depth[s.e_parent[s.parent_edge[v]]] + 1;
+    if (depth[v] > maxd) maxd = depth[v];
+  }
+  std::vector<int> cnt(maxd + 1, 0);
+  int ndraw = 0;
+  for (int v = 0; v < NN; v++) if (depth[v] > 0) { cnt[depth[v]]++; ndraw++; }
+  s.down_off.assign(maxd + 1, 0);
+  {
+    int acc = 0;
+    for (int d = 1; d <= maxd; d++) { s.down_off[d - 1] = acc; acc += cnt[d]; }
+    s.down_off[maxd] = acc;
+  }
+  s.down_entries.resize((size_t)3 * ndraw);
+  {
+    std::vector<int> cur(s.down_off.begin(), s.down_off.end() - 1);
+    for (int v = 0; v < NN; v++) if (depth[v] > 0) {
+      int* en = &s.down_entries[(size_t)3 * cur[depth[v] - 1]++];
+      en[0] = v; en[1] = s.e_parent[s.parent_edge[v]]; en[2] = s.parent_edge[v];
+    }
+  }
+}
+
+// A valid pruning-wise edge order (children before parents, the two edges of a node adjacent), the internal nodes
+// below the root top-down (reverse pruning order, like makenodelist), and the root.  O(E), iterative.
+inline void tree_order(const int32_t* edge, int E, int T, int32_t* nen, int32_t* nodelist, int32_t* root1) {
+  if (T < 2 || E != 2 * T - 2) throw std::string("only binary trees are supported");
+  const int NN = 2 * T - 1;
+  std::vector<int> kid(2 * (size_t)NN, -1), has_parent(NN, 0);
+  for (int e = 0; e < E; e++) {
+    const int p = edge[e] - 1, c = edge[E + e] - 1;
+    if (p < T || p >= NN || c < 0 || c >= NN) throw std::string("edge entry out of range");
+    if (kid[2 * p] < 0) kid[2 * p] = e; else if (kid[2 * p + 1] < 0) kid[2 * p + 1] = e;
+    else throw std::string("a node has more than two children");
+    if (has_parent[c]) throw std::string("a node has two parent edges");
+    has_parent[c] = 1;
+  }
+  int root = -1;
+  for (int v = T; v < NN; v++) {
+    if (kid[2 * v + 1] < 0) throw std::string("every internal node needs exactly two children");
+    if (!has_parent[v]) { if (root >= 0) throw std::string("more than one root"); root = v; }
+  }
+  if (root < 0) throw std::string("no root");
+  // iterative post-order
+  std::vector<int> stack, order;  // order: internal nodes, children before parents
+  std::vector<char> expanded(NN, 0);
+  stack.push_back(root);
+  while (!stack.empty()) {
+    const int v = stack.back();
+    if (v < T) { stack.pop_back(); continue; }
+    if (!expanded[v]) {
+      expanded[v] = 1;
+      stack.push_back(edge[E + kid[2 * v + 1]] - 1);
+      stack.push_back(edge[E + kid[2 * v]] - 1);
+    } else { stack.pop_back(); order.push_back(v); }
+  }
+  if ((int)order.size() != T - 1) throw std::string("edge matrix is not a tree");
+  for (int i = 0; i < T - 1; i++) { nen[2 * i] = kid[2 * order[i]] + 1; nen[2 * i + 1] = kid[2 * order[i] + 1] + 1; }
+  for (int i = 1; i <= T - 2; i++) nodelist[i - 1] = order[T - 2 - i] + 1;
+  *root1 = root + 1;
+}
+
+}  // namespace host
+}  // namespace pm

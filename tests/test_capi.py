@@ -1,0 +1,89 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/phylomap_b200.h declares, the
+host-only entries work, and the compute entries refuse to run without a B200 (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+import phylomap_b200 as pb
+from phylomap_b200 import capi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported():
+    hdr = open(os.path.join(ROOT, "include", "phylomap_b200.h")).read()
+    declared = set(re.findall(r"\b(pm_[A-Za-z0-9_]+)\s*\(", hdr)) - {"pm_allreduce_fn"}
+    assert declared, "no declarations found"
+    L = capi.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), "%s declared in the header but not exported" % name
+    assert declared == set(capi.EXPORTS)
+
+
+def test_ncols_layouts():
+    L = capi.lib()
+    assert L.pm_ncols(capi.PM_V_PLAIN, 2) == 4          # man/sumstatMCMC.Rd:18
+    assert L.pm_ncols(capi.PM_V_BIGTREE, 4) == 16
+    assert L.pm_ncols(capi.PM_V_BF, 2) == 9             # R/sumstatMCMCbf.R:33
+    assert L.pm_ncols(capi.PM_V_MT, 2) == 9
+    assert L.pm_ncols(capi.PM_V_KS, 4) == 4 + 16 + 2 + 3 + 1
+    assert L.pm_ncols(capi.PM_V_KSMT, 6) == 6 + 36 + 2 + 6 + 1
+
+
+@pytest.mark.parametrize("T,seed", [(2, 1), (3, 2), (17, 3), (200, 4), (3000, 5)])
+def test_tree_order_is_a_valid_pruningwise_order(T, seed):
+    t = synth.yule_tree(T, seed)
+    nen, nodelist, root = t.order()
+    E = t.E
+    assert sorted(nen) == list(range(1, E + 1))
+    parent, child = t.edge[:, 0], t.edge[:, 1]
+    assert root == T + 1 and root not in child
+    done = set(range(1, T + 1))
+    for i in range(T - 1):
+        a, b = nen[2 * i] - 1, nen[2 * i + 1] - 1
+        assert parent[a] == parent[b]                      # sibling pairs adjacent (src/phylomap.cpp:508-510)
+        assert child[a] in done and child[b] in done       # children before parents
+        done.add(parent[a])
+    assert parent[nen[-1] - 1] == root                     # myreorder: last edge's parent is the root
+    assert len(nodelist) == T - 2 and len(set(nodelist)) == T - 2
+    seen = {root}
+    pe = {child[e]: parent[e] for e in range(E)}
+    for v in nodelist:                                     # makenodelist: top-down
+        assert pe[v] in seen
+        seen.add(v)
+    # makenodelist reads the parents of the pruning-wise edge pairs backwards (R/sumstatMCMC.R:11-17)
+    assert [parent[nen[E - 2 * i - 1] - 1] for i in range(1, T - 1)] == list(nodelist)
+
+
+def test_tree_order_rejects_non_binary():
+    edge = np.asfortranarray(np.array([[4, 1], [4, 2], [4, 3]], dtype=np.int32))
+    err = C.create_string_buffer(256)
+    nen = np.zeros(3, dtype=np.int32)
+    nl = np.zeros(1, dtype=np.int32)
+    root = C.c_int32()
+    rc = capi.lib().pm_tree_order(capi.ptr(edge), 3, 3, capi.ptr(nen), capi.ptr(nl), C.byref(root), err, 256)
+    assert rc == capi.PM_ERR_ARG and b"binary" in err.value
+
+
+def test_no_cpu_fallback():
+    """Without a usable sm_100 device every sampler entry fails with PM_ERR_CUDA."""
+    if capi.lib().pm_device_count() > 0:
+        pytest.skip("a B200 is present")
+    z = cases.tree2(T=8)
+    with pytest.raises(capi.PhylomapError) as e:
+        pb.sumstatMCMC(z, cases.Q2, cases.PID2, 0.2, 2)
+    assert e.value.code == capi.PM_ERR_CUDA
+
+
+def test_product_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "phylomap_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle/" not in src.replace("oracle/bridge.py takes (tests only)", "") or f == "tree.py"
+                assert "import oracle" not in src and "from oracle" not in src

@@ -1,0 +1,214 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Deterministic mode (FP64, reference order of operations, keyed or replayed uniforms): node states, piece counts,
+merged paths and integer transition counts must be IDENTICAL; dwell-time sums within 1e-9 relative (the sums
+are accumulated in a different order; the bar in BASELINE.json is 1e-6).
+"""
+import numpy as np
+import pytest
+
+import cases
+import phylomap_b200 as pb
+from phylomap_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+DET = dict(mode="deterministic", precision="f64")
+
+
+def _oracle(oracle, variant, trees, Q, pid, Omega, N, prior=None, seed=7, **kw):
+    o = oracle.OracleRun(variant, [t.oracle_dict() for t in trees], Q, pid, Omega, N, prior=prior,
+                         rng_mode=kw.pop("rng_mode", oracle.KEYED), seed=seed, **kw)
+    return o, o.run()
+
+
+def _compare_rows(got, ref, n, int_cols, tol=1e-9):
+    assert got.shape == ref.shape
+    for c in range(ref.shape[1]):
+        if c in int_cols:
+            assert np.array_equal(got[:, c], ref[:, c]), "integer column %d differs" % c
+        else:
+            np.testing.assert_allclose(got[:, c], ref[:, c], rtol=tol, atol=1e-12, err_msg="column %d" % c)
+
+
+def _compare_state(chain, orc, tree, S, E, n_paths=40, tree_idx=0):
+    assert np.array_equal(chain.node_states(tree_idx), orc.node_states(tree_idx))
+    assert np.array_equal(chain.piece_counts(tree_idx), orc.piece_counts(tree_idx))
+    rng = np.random.default_rng(0)
+    for _ in range(n_paths):
+        s, e = int(rng.integers(S)), int(rng.integers(E))
+        gl, gs = chain.path(s, e, tree_idx)
+        ol, os_ = orc.path(s, e, tree_idx)
+        assert np.array_equal(gs, os_)
+        np.testing.assert_array_equal(gl, ol)  # same additions in the same order: bit-exact
+
+
+@pytest.mark.parametrize("variant,name", [(capi.PM_V_PLAIN, "PLAIN"), (capi.PM_V_SPARSE, "SPARSE"),
+                                          (capi.PM_V_BIGTREE, "BIGTREE")])
+@pytest.mark.parametrize("S", [1, 37])
+def test_fixed_q_two_state(oracle, variant, name, S):
+    z = cases.tree2(T=24, S=S, seed=3)
+    N, Om = 25, 0.2
+    orc, ref = _oracle(oracle, getattr(oracle, name), [z], cases.Q2, cases.PID2, Om, N)
+    ch = pb.Chain(variant, z, cases.Q2.copy(), cases.PID2, Om, N, seed=7, **DET)
+    got = ch.run()
+    _compare_rows(got, ref, 2, int_cols={2, 3})
+    _compare_state(ch, orc, z, S, z.E)
+
+
+@pytest.mark.parametrize("variant,name", [(capi.PM_V_PLAIN, "PLAIN"), (capi.PM_V_BIGTREE, "BIGTREE")])
+def test_fixed_q_four_state(oracle, variant, name):
+    Q = cases.q4()
+    z = cases.tree_n(Q, T=40, S=19, seed=5, mean_branch=0.8)
+    N, Om = 20, 2.4
+    pid = np.full(4, 0.25)
+    orc, ref = _oracle(oracle, getattr(oracle, name), [z], Q, pid, Om, N)
+    ch = pb.Chain(variant, z, Q.copy(), pid, Om, N, seed=7, **DET)
+    got = ch.run()
+    _compare_rows(got, ref, 4, int_cols=set(range(4, 16)))
+    _compare_state(ch, orc, z, 19, z.E)
+
+
+def test_sparse_threshold_active(oracle):
+    """SPARSE with B entries <= 1e-7 dropped (matTospmat, src/phylomap.cpp:811)."""
+    Q = np.array([[-0.1, 0.1, 0.0], [1e-9, -0.1 - 1e-9, 0.1], [0.05, 0.05, -0.1]])
+    z = cases.tree_n(cases.jc(3), T=16, S=5, seed=2, mean_branch=3.0)
+    N, Om = 15, 0.4
+    pid = np.full(3, 1 / 3)
+    orc, ref = _oracle(oracle, oracle.SPARSE, [z], Q, pid, Om, N)
+    ch = pb.Chain(capi.PM_V_SPARSE, z, Q.copy(), pid, Om, N, seed=7, **DET)
+    _compare_rows(ch.run(), ref, 3, int_cols=set(range(3, 9)))
+    _compare_state(ch, orc, z, 5, z.E)
+
+
+@pytest.mark.parametrize("n", [3, 6, 20])
+def test_generic_state_count(oracle, n):
+    """Run-time state count (the tutorial's 20-state tridiagonal-like chain, phylomap_tutorial.Rnw:119-135)."""
+    Q = cases.jc(n, 0.02)
+    z = cases.tree_n(Q, T=12, S=3, seed=n, mean_branch=4.0)
+    N, Om = 6, 2 * 0.02 * (n - 1)
+    pid = np.full(n, 1.0 / n)
+    orc, ref = _oracle(oracle, oracle.PLAIN, [z], Q, pid, Om, N)
+    ch = pb.Chain(capi.PM_V_PLAIN, z, Q.copy(), pid, Om, N, seed=7, **DET)
+    _compare_rows(ch.run(), ref, n, int_cols=set(range(n, n * n)))
+    _compare_state(ch, orc, z, 3, z.E, n_paths=20)
+
+
+def test_bf(oracle):
+    z = cases.tree2(T=30, S=4, seed=9)
+    N, Om = 40, 0.5
+    Qo, Qg = cases.Q2.copy(), np.asfortranarray(cases.Q2.copy())
+    orc, ref = _oracle(oracle, oracle.BF, [z], Qo, cases.PID2, Om, N, prior=cases.PRIOR_BF)
+    ch = pb.Chain(capi.PM_V_BF, z, Qg, cases.PID2, Om, N, prior=cases.PRIOR_BF, seed=7, **DET)
+    got = ch.run()
+    _compare_rows(got, ref, 2, int_cols={2, 3, 4, 5, 8}, tol=1e-8)
+    np.testing.assert_allclose(Qg, orc.Q, rtol=1e-8)      # Q updated in place like the reference
+    np.testing.assert_allclose(ch.B, orc.B, rtol=1e-8)
+    _compare_state(ch, orc, z, 4, z.E)
+
+
+def test_ks(oracle):
+    Q = cases.q4()
+    z = cases.tree_hidden(Q, T=30, S=3, seed=4, mean_branch=0.5)
+    N, Om = 30, 4.0
+    pid = np.full(4, 0.25)
+    orc, ref = _oracle(oracle, oracle.KS, [z], Q.copy(), pid, Om, N, prior=cases.PRIOR_KS)
+    Qg = np.asfortranarray(Q.copy())
+    ch = pb.Chain(capi.PM_V_KS, z, Qg, pid, Om, N, prior=cases.PRIOR_KS, seed=7, **DET)
+    got = ch.run()
+    n = 4
+    _compare_rows(got, ref, n, int_cols=set(range(n, n + n * n)) | {ref.shape[1] - 1}, tol=1e-7)
+    np.testing.assert_allclose(Qg, orc.Q, rtol=1e-7, atol=1e-12)
+    _compare_state(ch, orc, z, 3, z.E)
+
+
+def test_ks_six_state(oracle):
+    Q = cases.q6()
+    z = cases.tree_hidden(Q, T=16, S=2, seed=6, mean_branch=0.5)
+    N, Om = 12, 8.0
+    pid = np.full(6, 1 / 6)
+    orc, ref = _oracle(oracle, oracle.KS, [z], Q.copy(), pid, Om, N, prior=cases.PRIOR_KS)
+    ch = pb.Chain(capi.PM_V_KS, z, np.asfortranarray(Q.copy()), pid, Om, N, prior=cases.PRIOR_KS, seed=7, **DET)
+    n = 6
+    _compare_rows(ch.run(), ref, n, int_cols=set(range(n, n + n * n)) | {ref.shape[1] - 1}, tol=1e-7)
+
+
+def _tree_set(maker, k, **kw):
+    base = maker(seed=11, **kw)
+    out = [base]
+    rng = np.random.default_rng(5)
+    for _ in range(k - 1):
+        el = base.edge_length * rng.uniform(0.7, 1.3, size=base.E)
+        t = pb.PhyloTree(base.edge, el).with_states(base.states)
+        out.append(t)
+    return out
+
+
+def test_mt(oracle):
+    trees = _tree_set(lambda seed, **kw: cases.tree2(T=18, S=3, seed=seed), 3)
+    N, Om = 25, 0.5
+    orc, ref = _oracle(oracle, oracle.MT, trees, cases.Q2.copy(), cases.PID2, Om, N, prior=cases.PRIOR_BF)
+    ch = pb.Chain(capi.PM_V_MT, trees, np.asfortranarray(cases.Q2.copy()), cases.PID2, Om, N, prior=cases.PRIOR_BF,
+                  seed=7, **DET)
+    _compare_rows(ch.run(), ref, 2, int_cols={2, 3, 4, 5, 8}, tol=1e-8)
+    for ti in range(3):
+        _compare_state(ch, orc, trees[ti], 3, trees[ti].E, n_paths=10, tree_idx=ti)
+
+
+def test_ksmt(oracle):
+    Q = cases.q4()
+    trees = _tree_set(lambda seed, **kw: cases.tree_hidden(Q, T=14, S=2, seed=seed, mean_branch=0.5), 2)
+    N, Om = 15, 4.0
+    pid = np.full(4, 0.25)
+    orc, ref = _oracle(oracle, oracle.KSMT, trees, Q.copy(), pid, Om, N, prior=cases.PRIOR_KSMT)
+    ch = pb.Chain(capi.PM_V_KSMT, trees, np.asfortranarray(Q.copy()), pid, Om, N, prior=cases.PRIOR_KSMT, seed=7, **DET)
+    n = 4
+    _compare_rows(ch.run(), ref, n, int_cols=set(range(n, n + n * n)) | {ref.shape[1] - 1}, tol=1e-7)
+
+
+@pytest.mark.parametrize("variant,name,prior", [(capi.PM_V_PLAIN, "PLAIN", None), (capi.PM_V_BF, "BF", cases.PRIOR_BF)])
+def test_replay_of_sequential_r_stream(oracle, variant, name, prior):
+    """Tier 1 of BASELINE.json: the kernels consume a uniform stream exported from a sequential (R-order,
+    Mersenne-Twister) run of the reference algorithm and reproduce its histories and counts."""
+    z = cases.tree2(T=16, S=2, seed=13)
+    N, Om = 12, 0.4
+    orc = oracle.OracleRun(getattr(oracle, name), [z.oracle_dict()], cases.Q2.copy(), cases.PID2, Om, N, prior=prior,
+                           rng_mode=oracle.SEQUENTIAL, seed=101, want_log=True)
+    ref = orc.run()
+    table, host = orc.export_log()
+    ch = pb.Chain(variant, z, np.asfortranarray(cases.Q2.copy()), cases.PID2, Om, N, prior=prior, seed=101,
+                  table=table, host_table=host, **DET)
+    got = ch.run()
+    _compare_rows(got, ref, 2, int_cols={2, 3} if prior is None else {2, 3, 4, 5, 8}, tol=1e-8)
+    _compare_state(ch, orc, z, 2, z.E, n_paths=20)
+
+
+def test_one_call_entries_match_chain(oracle):
+    """The seven drop-in entries (pm_maketreelist*) are the chain interface run in one go."""
+    z = cases.tree2(T=20, S=3, seed=21)
+    N, Om = 10, 0.2
+    _, ref = _oracle(oracle, oracle.PLAIN, [z], cases.Q2, cases.PID2, Om, N)
+    got = pb.sumstatMCMC(z, cases.Q2, cases.PID2, Om, N, seed=7, **DET)
+    _compare_rows(got, ref, 2, int_cols={2, 3})
+    _, ref = _oracle(oracle, oracle.BF, [z], cases.Q2.copy(), cases.PID2, 0.5, N, prior=cases.PRIOR_BF)
+    got = pb.sumstatMCMCbf(z, cases.Q2.copy(), cases.PID2, 0.5, N, cases.PRIOR_BF, seed=7, **DET)
+    _compare_rows(got, ref, 2, int_cols={2, 3, 4, 5, 8}, tol=1e-8)
+
+
+def test_chunked_run_equals_single_run():
+    z = cases.tree2(T=20, S=5, seed=2)
+    a = pb.Chain(capi.PM_V_PLAIN, z, cases.Q2.copy(), cases.PID2, 0.2, 12, seed=3, **DET).run()
+    c = pb.Chain(capi.PM_V_PLAIN, z, cases.Q2.copy(), cases.PID2, 0.2, 12, seed=3, **DET)
+    b = np.vstack([c.run(5), c.run(4), c.run(3)])
+    assert np.array_equal(a, b)
+
+
+def test_errors_like_the_reference():
+    z = cases.tree2(T=10, S=1, seed=2)
+    with pytest.raises(capi.PhylomapError) as e:  # zero root prior -> RcppArmadillo::sample throws
+        pb.sumstatMCMC(z, cases.Q2, np.array([0.0, 0.0]), 0.2, 2, **DET)
+    assert e.value.code == capi.PM_ERR_SAMPLE
+    bad = pb.PhyloTree(z.edge, z.edge_length, np.array([1, 2, 3] + [1] * 7), z.maps, z.mapnames)
+    with pytest.raises(capi.PhylomapError) as e:
+        pb.sumstatMCMC(bad, cases.Q2, cases.PID2, 0.2, 2, **DET)
+    assert e.value.code == capi.PM_ERR_ARG
