@@ -104,11 +104,11 @@ def cpu_reference(tree, Q, pid, steps, sites_per_core=None, cores=None):
     import multiprocessing as mp
     from phylomap_b200 import synth
     cores = cores or os.cpu_count() or 1
-    sites_per_core = sites_per_core or int(os.environ.get("PM_BENCH_CPU_SITES", 2))
+    sites_per_core = sites_per_core or int(os.environ.get("PM_BENCH_CPU_SITES", 8))
     st = synth.simulate_tip_states(tree, Q, pid, cores * sites_per_core, seed=99).numpy()
     jobs = []
     for c in range(cores):
-        z = tree.with_states(st[c * sites_per_core:(c + 1) * sites_per_core])
+        z = tree.with_states(st[c * sites_per_core:(c + 1) * sites_per_core], segments=2)
         jobs.append((z.oracle_dict(), Q.copy(), pid, steps, 1000 + c))
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
@@ -129,7 +129,7 @@ def run_reference(a, rank, world):
     # warm-up: a tiny run so that page-in / fork costs stay out of the measurement
     for _ in range(min(a.warmup, 1)):
         cpu_reference(tree, Q, pid, 1, sites_per_core=1)
-    steps = max(1, min(a.steps, int(os.environ.get("PM_BENCH_CPU_STEPS", 3))))
+    steps = max(1, min(a.steps, int(os.environ.get("PM_BENCH_CPU_STEPS", 6))))
     cb, wall = cpu_reference(tree, Q, pid, steps)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
@@ -164,7 +164,7 @@ def run_ours(a, rank, local_rank, world):
     st_host.copy_(st_dev)
     del st_dev
     torch.cuda.empty_cache()
-    z = tree.with_states(st_host.numpy())
+    z = tree.with_states(st_host.numpy(), segments=2)
     order = [z.order()]
     stream = torch.cuda.Stream()
     opts = dict(precision="f32", mode="production", seed=2026, device=local_rank, site_offset=rank * S,
@@ -244,7 +244,7 @@ def run_ours(a, rank, local_rank, world):
     if rank == 0 and world == 1 and not a.no_cpu:
         from oracle import bridge
         bridge.build()
-        cb, _ = cpu_reference(tree, Q, pid, 2)
+        cb, _ = cpu_reference(tree, Q, pid, 4)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -28,7 +28,8 @@ class _Config(C.Structure):
                 ("Omega", C.c_double), ("prior", C.c_void_p), ("nprior", C.c_int32),
                 ("rng_mode", C.c_int32), ("seed", C.c_uint64), ("want_log", C.c_int32),
                 ("tab_off", C.c_void_p), ("tab_u", C.c_void_p), ("host_tab", C.c_void_p),
-                ("host_tab_n", C.c_int64), ("lefts", C.c_void_p), ("rights", C.c_void_p), ("d", C.c_void_p)]
+                ("host_tab_n", C.c_int64), ("lefts", C.c_void_p), ("rights", C.c_void_p), ("d", C.c_void_p),
+                ("site_offset", C.c_int64)]
 
 
 def build(force=False):
@@ -85,7 +86,7 @@ class OracleRun:
     column-major buffers (self.Q / self.B) which the bf/ks/mt variants mutate like the reference does."""
 
     def __init__(self, variant, trees, Q, pid, Omega, N, prior=None, rng_mode=KEYED, seed=1, want_log=False,
-                 table=None, host_table=None, B=None, eig=None):
+                 table=None, host_table=None, B=None, eig=None, site_offset=0):
         L = lib()
         self._keep = []
         n = Q.shape[0]
@@ -118,6 +119,7 @@ class OracleRun:
         cfg.variant, cfg.n, cfg.N, cfg.ntrees, cfg.Omega = variant, n, N, len(trees), float(Omega)
         cfg.prior, cfg.nprior = _p(pr), 0 if pr is None else len(pr)
         cfg.rng_mode, cfg.seed, cfg.want_log = rng_mode, seed, int(want_log)
+        cfg.site_offset = int(site_offset)
         if table is not None:
             off = np.ascontiguousarray(table[0], dtype=np.int64)
             u = np.ascontiguousarray(table[1], dtype=np.float64)

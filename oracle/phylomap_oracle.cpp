@@ -399,6 +399,7 @@ struct Run {
   int N = 0;
   int rng_mode = SEQUENTIAL;
   uint64_t seed = 0;
+  int64_t site_offset = 0;  // keyed mode: global index of local site 0 (site-sharded runs)
   RMersenne mt{0};
   std::vector<std::vector<Chain>> chains;  // [tree][site]
   // logs (sequential mode)
@@ -454,12 +455,12 @@ struct Run {
     int root0 = 0;
     for (int64_t s = 0; s < trees[tree].S; s++) {
       SweepRng g;
-      g.mode = rng_mode; g.mt = &mt; g.seed = tree_seed(tree); g.site = (uint32_t)s; g.iter = (uint32_t)it;
+      g.mode = rng_mode; g.mt = &mt; g.seed = tree_seed(tree); g.site = (uint32_t)(site_offset + s); g.iter = (uint32_t)it;
       g.tab_off = tab_off; g.tab_u = tab_u;
       g.log = (want_log && rng_mode == SEQUENTIAL) ? &slot_log : nullptr;
       int r = chains[tree][s].sweep(M, F, g, base_of(tree, s, it), stats);
       if (g.table_underrun) throw std::runtime_error("replay table exhausted");
-      if (s == 0) root0 = r;
+      if (site_offset + s == 0) root0 = r;
     }
     return root0;
   }
@@ -852,6 +853,7 @@ struct orc_config {
   int32_t rng_mode; uint64_t seed; int32_t want_log;
   const int64_t* tab_off; const double* tab_u; const double* host_tab; int64_t host_tab_n;
   const double* lefts; const double* rights; const double* d;
+  int64_t site_offset;
 };
 
 void* orc_create(const orc_tree* trees, const orc_config* cfg, double* Q, const double* pid, double* B, char* err, int errlen) {
@@ -868,6 +870,7 @@ void* orc_create(const orc_tree* trees, const orc_config* cfg, double* Q, const 
     r->M.n = cfg->n; r->M.Q = Q; r->M.B = B; r->M.Omega = cfg->Omega;
     r->M.pid.assign(pid, pid + cfg->n);
     if (cfg->prior) r->prior.assign(cfg->prior, cfg->prior + cfg->nprior);
+    r->site_offset = cfg->site_offset;
     r->rng_mode = cfg->rng_mode; r->seed = cfg->seed; r->want_log = cfg->want_log != 0;
     r->tab_off = cfg->tab_off; r->tab_u = cfg->tab_u; r->host_tab = cfg->host_tab; r->host_tab_n = cfg->host_tab_n;
     r->lefts = cfg->lefts; r->rights = cfg->rights; r->dmat = cfg->d;

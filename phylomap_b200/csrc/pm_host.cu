@@ -118,12 +118,16 @@ int ncols_of(int variant, int n) {
   return -1;
 }
 
-// smallest c with P(Poisson(lam) >= c) < eps
+// smallest c > lam with P(Poisson(lam) >= c) < eps, from the geometric bound on the tail beyond the mode:
+// P(X >= c) <= pmf(c) / (1 - lam / (c + 1))
 int poisson_cap(double lam, double eps) {
-  double term = std::exp(-lam), cdf = term;
-  int c = 1;
-  while (1.0 - cdf > eps && c < 100000) { term *= lam / c; cdf += term; c++; }
-  return c;
+  if (!(lam > 0)) return 1;
+  const double loglam = std::log(lam), logeps = std::log(eps);
+  for (int c = (int)std::ceil(lam) + 1; c < 1000000; c++) {
+    const double logpmf = -lam + c * loglam - std::lgamma(c + 1.0);
+    if (logpmf - std::log1p(-lam / (c + 1.0)) < logeps) return c;
+  }
+  return 1000000;
 }
 
 }  // namespace
@@ -392,23 +396,30 @@ struct ChainT : pm_chain {
       ny = (E + t->chunk - 1) / t->chunk;
       t->paths_grid = dim3((unsigned)gx, (unsigned)ny, 1);
       t->nblocks = gx * ny;
-      // record capacity of every chunk from the Poisson tail of its real-jump count (real jumps are dominated by
-      // a Poisson process of rate max|Q_ii| along the chunk's total length); a multi-run path stores jumps + 1 runs
+      // record capacity of every chunk.  Real jumps sit on uniformization points, and in equilibrium the points of a
+      // chunk are Poisson(Omega x total length), so the Poisson tail bounds them; a path with j real jumps stores
+      // j + 1 runs (<= 2j).  The first sweep instead finds its points in the caller's maps (m_e - 1 per branch), so
+      // the initial segmentation is a second lower bound.
       t->cap_off_h.assign(ny + 1, 0);
       for (long long c = 0; c < ny; c++) {
         const int b0 = (int)c * t->chunk, b1 = std::min(E, b0 + t->chunk);
         double len = 0;
-        for (int e = b0; e < b1; e++) len += (double)elen[e];
-        int cap;
-        if (opt.path_capacity > 0) cap = opt.path_capacity * (b1 - b0);
-        else {
-          const double rate = V.rates ? std::min(Omega, 4 * qmax) : qmax;
-          const int jumps = poisson_cap(1.5 * rate * len + 1.0, 1e-18);
-          cap = exact ? (b1 - b0) + jumps : 2 * jumps;
+        long long init_records = 0;
+        for (int e = b0; e < b1; e++) {
+          len += (double)elen[e];
+          const long long m0 = moff[e + 1] - moff[e];
+          if (exact || m0 >= 2) init_records += m0;
         }
-        if (exact && cap < 2 * (b1 - b0)) cap = 2 * (b1 - b0);
+        long long cap;
+        if (opt.path_capacity > 0) cap = (long long)opt.path_capacity * (b1 - b0);
+        else {
+          const int jumps = poisson_cap(1.5 * Omega * len + 1.0, 1e-18);
+          cap = exact ? (long long)(b1 - b0) + jumps : 2LL * jumps;
+          cap = std::max(cap, init_records);
+        }
+        if (cap > (1 << 28)) fail(PM_ERR_CAPACITY, "path capacity of a branch chunk too large");
         cap = (cap + 3) & ~3;  // keep every slice 16-byte aligned
-        t->cap_off_h[c + 1] = t->cap_off_h[c] + cap;
+        t->cap_off_h[c + 1] = t->cap_off_h[c] + (int)cap;
       }
       const long long R = t->cap_off_h[ny];
       upload(t->up_entries, t->sch.up_entries, stream);

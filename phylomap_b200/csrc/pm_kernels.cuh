@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(128) k_paths(ChainParams<Real> P, uint32_t ite
           rd += nj + 1;
         }
       }
-      Stream gold; gold.open(P.rng, (uint32_t)site, iter - 1u, K_BREXP, (uint32_t)e, P.err_flag);
+      Stream gold;  // the stream that drew the virtual jumps of the previous sweep (none before the first one)
+      gold.open(P.rng, (uint32_t)site, first ? iter : iter - 1u, K_BREXP, (uint32_t)e, P.err_flag);
       Stream gst; gst.open(P.rng, (uint32_t)site, iter, K_BRSTATE, (uint32_t)e, P.err_flag);
       int j = 0; Real tot = 0; long long cp = first ? P.maps_off[e] : 0;
       auto next_piece = [&]() -> Real {

@@ -213,15 +213,15 @@ def simulate_tip_states(tree, Q, pid, n_sites, seed=101, device="cpu", batch_sit
     return out
 
 
-def simulate_2_state_tree(seed, atree, Q, pid2, n_sites=1, device="cpu"):
+def simulate_2_state_tree(seed, atree, Q, pid2, n_sites=1, device="cpu", segments=None):
     """R/simulate_2_state_tree.R:8-32 for any tree / any number of sites: simulate tips, halve the tip branches."""
     st = simulate_tip_states(atree, np.asarray(Q, dtype=np.float64), pid2, n_sites, seed, device).cpu().numpy()
-    return atree.with_states(st[0].astype(np.int32) if n_sites == 1 else st)
+    return atree.with_states(st[0].astype(np.int32) if n_sites == 1 else st, segments=segments)
 
 
-def simulate_4_state_tree(seed, atree, Q, pid4, n_sites=1, device="cpu"):
+def simulate_4_state_tree(seed, atree, Q, pid4, n_sites=1, device="cpu", segments=None):
     """R/simulate_4_state_tree.R:7-34: simulate under the hidden-rate Q, observe the trait (odd states -> 1,
     even states -> 2 in the reference's 1-based numbering)."""
     st = simulate_tip_states(atree, np.asarray(Q, dtype=np.float64), pid4, n_sites, seed, device).cpu().numpy()
     obs = (((st.astype(np.int32) % 2) - 1) * -1) + 1
-    return atree.with_states(obs[0] if n_sites == 1 else obs.astype(np.uint8))
+    return atree.with_states(obs[0] if n_sites == 1 else obs.astype(np.uint8), segments=segments)

@@ -38,14 +38,19 @@ class PhyloTree:
         return cls(z["edge"], z.get("edge.length", [float(np.sum(m)) for m in z["maps"]]), z.get("states"),
                    z.get("maps"), z.get("mapnames"))
 
-    def with_states(self, states, halve_tip_branches=True):
+    def with_states(self, states, halve_tip_branches=True, segments=None):
         """Attach tip data the way simulate_2_state_tree does (R/simulate_2_state_tree.R:16-30): every tip branch
         becomes two halves named (1, tip state); with an [S, T] matrix the shared initial segmentation uses
-        site 0's tip states (the segment states are redrawn by the first sweep anyway)."""
+        site 0's tip states (the segment states are redrawn by the first sweep anyway).
+        segments=k instead cuts EVERY branch into k equal pieces (R/Squamate_tree_setup.R:54-82 uses 100): the first
+        sweep needs B^(m-1) to connect the node states, which a one-segment branch cannot do for a sparse Q."""
         st = np.asarray(states)
         first = st if st.ndim == 1 else st[0]
         maps, names = list(self.maps), list(self.mapnames)
-        if halve_tip_branches:
+        if segments is not None:
+            maps = [np.full(segments, t / segments) for t in self.edge_length]
+            names = [np.ones(segments, dtype=np.int32) for _ in range(self.E)]
+        elif halve_tip_branches:
             for e in range(self.E):
                 c = self.edge[e, 1]
                 if c <= self.T:

@@ -30,14 +30,14 @@ def tree2(T=20, S=1, seed=1, mean_branch=5.0):
     return synth.simulate_2_state_tree(101 + seed, t, Q2, PID2, n_sites=S)
 
 
-def tree_n(Q, T=20, S=1, seed=1, mean_branch=1.0):
+def tree_n(Q, T=20, S=1, seed=1, mean_branch=1.0, segments=None):
     t = synth.yule_tree(T, seed, mean_branch=mean_branch)
     n = Q.shape[0]
     st = synth.simulate_tip_states(t, Q, np.full(n, 1.0 / n), S, 300 + seed).numpy()
-    return t.with_states(st[0].astype(np.int32) if S == 1 else st)
+    return t.with_states(st[0].astype(np.int32) if S == 1 else st, segments=segments)
 
 
-def tree_hidden(Q, T=20, S=1, seed=1, mean_branch=1.0):
+def tree_hidden(Q, T=20, S=1, seed=1, mean_branch=1.0, segments=3):
     t = synth.yule_tree(T, seed, mean_branch=mean_branch)
     n = Q.shape[0]
-    return synth.simulate_4_state_tree(500 + seed, t, Q, np.full(n, 1.0 / n), n_sites=S)
+    return synth.simulate_4_state_tree(500 + seed, t, Q, np.full(n, 1.0 / n), n_sites=S, segments=segments)

@@ -31,7 +31,7 @@ def _compare_rows(got, ref, n, int_cols, tol=1e-9):
             np.testing.assert_allclose(got[:, c], ref[:, c], rtol=tol, atol=1e-12, err_msg="column %d" % c)
 
 
-def _compare_state(chain, orc, tree, S, E, n_paths=40, tree_idx=0):
+def _compare_state(chain, orc, tree, S, E, n_paths=40, tree_idx=0, exact_lengths=True):
     assert np.array_equal(chain.node_states(tree_idx), orc.node_states(tree_idx))
     assert np.array_equal(chain.piece_counts(tree_idx), orc.piece_counts(tree_idx))
     rng = np.random.default_rng(0)
@@ -40,7 +40,12 @@ def _compare_state(chain, orc, tree, S, E, n_paths=40, tree_idx=0):
         gl, gs = chain.path(s, e, tree_idx)
         ol, os_ = orc.path(s, e, tree_idx)
         assert np.array_equal(gs, os_)
-        np.testing.assert_array_equal(gl, ol)  # same additions in the same order: bit-exact
+        if exact_lengths:
+            np.testing.assert_array_equal(gl, ol)  # same additions in the same order: bit-exact
+        else:
+            # rate-updating samplers: the proposals see dwell-time SUMS, which the GPU accumulates in another order
+            # (1e-13 relative), so rates and hence piece lengths agree to rounding, not bit for bit
+            np.testing.assert_allclose(gl, ol, rtol=1e-9)
 
 
 @pytest.mark.parametrize("variant,name", [(capi.PM_V_PLAIN, "PLAIN"), (capi.PM_V_SPARSE, "SPARSE"),
@@ -59,7 +64,7 @@ def test_fixed_q_two_state(oracle, variant, name, S):
 @pytest.mark.parametrize("variant,name", [(capi.PM_V_PLAIN, "PLAIN"), (capi.PM_V_BIGTREE, "BIGTREE")])
 def test_fixed_q_four_state(oracle, variant, name):
     Q = cases.q4()
-    z = cases.tree_n(Q, T=40, S=19, seed=5, mean_branch=0.8)
+    z = cases.tree_n(Q, T=40, S=19, seed=5, mean_branch=0.8, segments=4)
     N, Om = 20, 2.4
     pid = np.full(4, 0.25)
     orc, ref = _oracle(oracle, getattr(oracle, name), [z], Q, pid, Om, N)
@@ -72,7 +77,7 @@ def test_fixed_q_four_state(oracle, variant, name):
 def test_sparse_threshold_active(oracle):
     """SPARSE with B entries <= 1e-7 dropped (matTospmat, src/phylomap.cpp:811)."""
     Q = np.array([[-0.1, 0.1, 0.0], [1e-9, -0.1 - 1e-9, 0.1], [0.05, 0.05, -0.1]])
-    z = cases.tree_n(cases.jc(3), T=16, S=5, seed=2, mean_branch=3.0)
+    z = cases.tree_n(cases.jc(3), T=16, S=5, seed=2, mean_branch=3.0, segments=4)
     N, Om = 15, 0.4
     pid = np.full(3, 1 / 3)
     orc, ref = _oracle(oracle, oracle.SPARSE, [z], Q, pid, Om, N)
@@ -104,7 +109,7 @@ def test_bf(oracle):
     _compare_rows(got, ref, 2, int_cols={2, 3, 4, 5, 8}, tol=1e-8)
     np.testing.assert_allclose(Qg, orc.Q, rtol=1e-8)      # Q updated in place like the reference
     np.testing.assert_allclose(ch.B, orc.B, rtol=1e-8)
-    _compare_state(ch, orc, z, 4, z.E)
+    _compare_state(ch, orc, z, 4, z.E, exact_lengths=False)
 
 
 def test_ks(oracle):
@@ -119,7 +124,7 @@ def test_ks(oracle):
     n = 4
     _compare_rows(got, ref, n, int_cols=set(range(n, n + n * n)) | {ref.shape[1] - 1}, tol=1e-7)
     np.testing.assert_allclose(Qg, orc.Q, rtol=1e-7, atol=1e-12)
-    _compare_state(ch, orc, z, 3, z.E)
+    _compare_state(ch, orc, z, 3, z.E, exact_lengths=False)
 
 
 def test_ks_six_state(oracle):
@@ -152,7 +157,7 @@ def test_mt(oracle):
                   seed=7, **DET)
     _compare_rows(ch.run(), ref, 2, int_cols={2, 3, 4, 5, 8}, tol=1e-8)
     for ti in range(3):
-        _compare_state(ch, orc, trees[ti], 3, trees[ti].E, n_paths=10, tree_idx=ti)
+        _compare_state(ch, orc, trees[ti], 3, trees[ti].E, n_paths=10, tree_idx=ti, exact_lengths=False)
 
 
 def test_ksmt(oracle):
@@ -180,7 +185,7 @@ def test_replay_of_sequential_r_stream(oracle, variant, name, prior):
                   table=table, host_table=host, **DET)
     got = ch.run()
     _compare_rows(got, ref, 2, int_cols={2, 3} if prior is None else {2, 3, 4, 5, 8}, tol=1e-8)
-    _compare_state(ch, orc, z, 2, z.E, n_paths=20)
+    _compare_state(ch, orc, z, 2, z.E, n_paths=20, exact_lengths=prior is None)
 
 
 def test_one_call_entries_match_chain(oracle):
@@ -212,3 +217,33 @@ def test_errors_like_the_reference():
     with pytest.raises(capi.PhylomapError) as e:
         pb.sumstatMCMC(bad, cases.Q2, cases.PID2, 0.2, 2, **DET)
     assert e.value.code == capi.PM_ERR_ARG
+
+
+def test_golden_vectors():
+    """The committed fixtures (tests/golden/*.json: inputs + expected rows) through the CUDA library."""
+    import json
+    import os
+    import sys
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold)
+    import make_golden
+    var = {"PLAIN": capi.PM_V_PLAIN, "SPARSE": capi.PM_V_SPARSE, "BIGTREE": capi.PM_V_BIGTREE, "BF": capi.PM_V_BF,
+           "KS": capi.PM_V_KS, "MT": capi.PM_V_MT, "KSMT": capi.PM_V_KSMT}
+    names = [f for f in sorted(os.listdir(gold)) if f.endswith(".json")]
+    assert len(names) >= 7
+    for name in names:
+        g = json.load(open(os.path.join(gold, name)))
+        case = g["case"]
+        z = make_golden.tree_from_case(case)
+        trees = [z]
+        for sc in case.get("extra_tree_scales", []):
+            trees.append(pb.PhyloTree(z.edge, z.edge_length * np.array(sc), z.states,
+                                      [m * s for m, s in zip(z.maps, sc)], z.mapnames))
+        Q = np.asfortranarray(np.array(case["Q"]))
+        n = Q.shape[0]
+        ch = pb.Chain(var[case["variant"]], trees if len(trees) > 1 else z, Q, np.array(case["pid"]), case["Omega"],
+                      case["N"], prior=case.get("prior"), seed=case["seed"], **DET)
+        got, ref = ch.run(), np.array(g["rows"])
+        fixed = case["variant"] in ("PLAIN", "SPARSE", "BIGTREE")
+        ints = set(range(n, ref.shape[1])) if fixed else set(range(n, n + n * n)) | {ref.shape[1] - 1}
+        _compare_rows(got, ref, n, ints, tol=1e-7)

@@ -1,0 +1,108 @@
+"""GPU tests of the production arithmetic (FP32 / FP64 fast path, Philox streams): tier 2 of BASELINE.json.
+
+Posterior distributions of N_ij and R_i must agree with the oracle's chains (two-sample KS, p > 0.01), expected
+counts with the matrix-exponential sampler sumstatEXP within 1 %, and — at the full tree size of the benchmark —
+the size-independent invariants of a sweep must hold.
+"""
+import numpy as np
+import pytest
+from scipy import stats
+
+import cases
+import phylomap_b200 as pb
+from phylomap_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_ks_against_oracle_chain(oracle, precision):
+    """One site, long chains, thinned: the GPU chain (production mode) and the oracle chain (R-order Mersenne-Twister
+    stream) sample the same posterior of (N01, N10, R0)."""
+    z = cases.tree2(T=20, S=1, seed=3, mean_branch=6.0)
+    N, thin, burn = 12000, 12, 600
+    ref = oracle.OracleRun(oracle.PLAIN, [z.oracle_dict()], cases.Q2, cases.PID2, 0.2, N, rng_mode=oracle.SEQUENTIAL,
+                           seed=123).run()[burn::thin]
+    got = pb.sumstatMCMC(z, cases.Q2, cases.PID2, 0.2, N, seed=99, precision=precision)[burn::thin]
+    np.testing.assert_allclose(got[:, :2].sum(1), z.edge_length.sum(), rtol=1e-5)
+    for col, name in [(2, "N01"), (3, "N10"), (0, "R0")]:
+        p = stats.ks_2samp(got[:, col], ref[:, col]).pvalue
+        assert p > 0.01, "%s: KS p = %.4f" % (name, p)
+
+
+def test_ks_rate_traces_bf(oracle):
+    """Rate-updating sampler: posterior of (lambda01, lambda10) from the GPU chain vs the oracle chain."""
+    z = cases.tree2(T=40, S=1, seed=8, mean_branch=4.0)
+    N, thin, burn = 8000, 10, 500
+    ref = oracle.OracleRun(oracle.BF, [z.oracle_dict()], cases.Q2.copy(), cases.PID2, 1.0, N, prior=cases.PRIOR_BF,
+                           rng_mode=oracle.SEQUENTIAL, seed=5).run()[burn::thin]
+    got = pb.sumstatMCMCbf(z, cases.Q2.copy(), cases.PID2, 1.0, N, cases.PRIOR_BF, seed=77, precision="f32")[burn::thin]
+    for col, name in [(6, "l01"), (7, "l10"), (3, "n01")]:
+        p = stats.ks_2samp(got[:, col], ref[:, col]).pvalue
+        assert p > 0.01, "%s: KS p = %.4f" % (name, p)
+
+
+def test_expected_counts_match_sumstatEXP(oracle):
+    """configs[1] of BASELINE.json in miniature: 4-state nucleotide-like model, many sites; mean transition counts
+    and dwell times per site from the GPU MCMC within 1 % of the direct sampler (plus its Monte-Carlo error)."""
+    Q, pid = cases.jc(4, 0.1), np.full(4, 0.25)
+    S = 1500
+    z = cases.tree_n(Q, T=100, S=S, seed=2, mean_branch=1.5)
+    Om = 2 * 0.3
+    N = 60
+    got = pb.sumstatMCMC(z, Q, pid, Om, N, seed=4, precision="f32")[20:] / S
+    w, V = np.linalg.eig(Q)
+    eig = (V.real, np.linalg.inv(V).real, np.diag(w.real))
+    ex = oracle.OracleRun(oracle.EXP, [z.oracle_dict()], Q, pid, Om, 6, rng_mode=oracle.SEQUENTIAL, seed=22, eig=eig).run() / S
+    tot_g, tot_e = got[:, 4:].sum(1), ex[:, 4:].sum(1)
+    se = np.sqrt(tot_g.var() / 4 + tot_e.var() / len(ex))
+    assert abs(tot_g.mean() - tot_e.mean()) < 0.01 * tot_e.mean() + 4 * se
+    np.testing.assert_allclose(got[:, :4].mean(0), ex[:, :4].mean(0), rtol=0.02)
+    np.testing.assert_allclose(got[:, 4:].mean(0), ex[:, 4:].mean(0), rtol=0.06)   # 12 individual N_ij, noisier
+
+
+def test_f32_and_f64_production_agree_statistically():
+    Q, pid = cases.q4(), np.full(4, 0.25)
+    z = cases.tree_n(Q, T=200, S=512, seed=9, mean_branch=0.3, segments=2)
+    a = pb.sumstatMCMC_bigtree(z, Q, pid, 2.4, 40, seed=1, precision="f32")[15:]
+    b = pb.sumstatMCMC_bigtree(z, Q, pid, 2.4, 40, seed=2, precision="f64")[15:]
+    np.testing.assert_allclose(a[:, :4].mean(0), b[:, :4].mean(0), rtol=0.02)
+    np.testing.assert_allclose(a[:, 4:].sum(1).mean(), b[:, 4:].sum(1).mean(), rtol=0.02)
+
+
+def test_full_tree_size_invariants():
+    """The benchmark's tree (10 000 tips, 4 states, sumstatMCMC_bigtree) at a reduced site count: properties that do
+    not need the oracle.  (i) total dwell time = sites x tree length; (ii) counts are non-negative integers;
+    (iii) same seed -> identical rows; (iv) two site shards keyed by global site index sum to the unsharded run."""
+    Q, pid = cases.q4(), np.full(4, 0.25)
+    tree = synth.yule_tree(10000, seed=4, mean_branch=0.1 / 1.2)
+    S = 4096
+    st = synth.simulate_tip_states(tree, Q, pid, S, seed=7, device="cuda").cpu().numpy()
+    z = tree.with_states(st, segments=2)
+    kw = dict(precision="f32", seed=11)
+    N = 4
+    a = pb.sumstatMCMC_bigtree(z, Q, pid, 2.4, N, **kw)
+    np.testing.assert_allclose(a[:, :4].sum(1), S * tree.edge_length.sum(), rtol=2e-4)
+    assert np.all(a[:, 4:] >= 0) and np.array_equal(a[:, 4:], np.round(a[:, 4:]))
+    assert a[:, 4:].sum() > 0
+    b = pb.sumstatMCMC_bigtree(z, Q, pid, 2.4, N, **kw)
+    assert np.array_equal(a, b)
+    h = S // 2
+    lo = pb.sumstatMCMC_bigtree(tree.with_states(st[:h], segments=2), Q, pid, 2.4, N, site_offset=0, **kw)
+    hi = pb.sumstatMCMC_bigtree(tree.with_states(st[h:], segments=2), Q, pid, 2.4, N, site_offset=h, **kw)
+    assert np.array_equal(lo[:, 4:] + hi[:, 4:], a[:, 4:])
+    np.testing.assert_allclose(lo[:, :4] + hi[:, :4], a[:, :4], rtol=1e-5)
+
+
+def test_squamate_sized_sparse_run():
+    """configs[2] shape: 3 951 tips, 2-state SPARSE sampler with the vignette's Q (Squamate_DIC_model_selection.Rnw:83),
+    many synthetic sites.  (The Squamate newick itself lives under /root/reference, which does not exist on the GPU
+    box; a Yule tree of the same size and total length stands in.)"""
+    Q = np.array([[-0.001, 0.001], [0.006, -0.006]])
+    tree = synth.yule_tree(3951, seed=3)
+    tree = pb.PhyloTree(tree.edge, tree.edge_length * (87740.48 / tree.edge_length.sum()))
+    S = 2048
+    z = synth.simulate_2_state_tree(5, tree, Q, cases.PID2, n_sites=S, device="cuda")
+    out = pb.SPARSEsumstatMCMC(z, Q, cases.PID2, 0.012, 6, precision="f32", seed=3)
+    np.testing.assert_allclose(out[:, :2].sum(1), S * tree.edge_length.sum(), rtol=2e-4)
+    assert np.all(out[:, 2:] >= 0)
