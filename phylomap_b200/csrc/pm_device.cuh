@@ -11,6 +11,12 @@
 #define PM_NMAX 32           // largest state count (generic path)
 #define PM_LOCAL_PATH_MAX 64 // largest merged-path capacity per (branch, site)
 #define PM_SMEM_POW 8        // powers of B kept in shared memory (fast mode, NS <= 4)
+// Production arithmetic: smallest value a stored (sum-normalised) partial may take.  Components whose relative weight
+// is below it can never be drawn in practice, but keeping them positive stops the product of two sibling partials
+// from underflowing to all-zero in FP32 (sibling clades that are each certain of different states, which happens
+// during burn-in from the reference's one-segment initial maps).  Structural zeros still surface through the exact
+// zeros of B^k in the draws.
+#define PM_PARTIAL_FLOOR 1e-18
 
 // device-side error bits (sticky, OR-ed into ChainParams::err_flag)
 #define PM_DE_SAMPLE_NA 1u
@@ -65,7 +71,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
-enum SlotKind : uint32_t { K_NODE = 0, K_BRSTATE = 1, K_BREXP = 2 };
+enum SlotKind : uint32_t { K_NODE = 0, K_BRSTATE = 1, K_BREXP = 2, K_NODEGRP = 3, K_BREXP2 = 4 };
 __device__ __forceinline__ uint32_t make_slot(uint32_t kind, uint32_t idx) { return (kind << 28) | idx; }
 
 // Description of where uniforms come from (per launch).
@@ -83,7 +89,7 @@ struct RngDesc {
 // 53-bit uniforms strictly inside (0,1), two per Philox block; optionally replayed from a table.
 struct StreamD {
   uint32_t k0, k1, site, iter, slot, k;
-  uint32_t o[4];
+  uint32_t o0, o1, o2, o3;
   const double* tab; int64_t tab_n; unsigned* err;
   __device__ __forceinline__ void open(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t kind, uint32_t idx,
                                       unsigned* err_flag) {
@@ -101,8 +107,12 @@ struct StreamD {
     if (tab) {
       if ((int64_t)k >= tab_n) { atomicOr(err, PM_DE_REPLAY); u = 0.5; } else u = tab[k];
     } else {
-      if ((k & 1u) == 0u) philox4x32_10(k >> 1, slot, iter, site, k0, k1, o);
-      uint32_t hi = (k & 1u) ? o[2] : o[0], lo = (k & 1u) ? o[3] : o[1];
+      if ((k & 1u) == 0u) {
+        uint32_t o[4];
+        philox4x32_10(k >> 1, slot, iter, site, k0, k1, o);
+        o0 = o[0]; o1 = o[1]; o2 = o[2]; o3 = o[3];
+      }
+      uint32_t hi = (k & 1u) ? o2 : o0, lo = (k & 1u) ? o3 : o1;
       unsigned long long bits = ((unsigned long long)hi << 21) | (unsigned long long)(lo >> 11);
       u = ((double)bits + 0.5) * (1.0 / 9007199254740992.0);
     }
@@ -111,17 +121,23 @@ struct StreamD {
   }
 };
 
-// 24-bit uniforms strictly inside (0,1), four per Philox block (production, float).
+// 24-bit uniforms strictly inside (0,1), four per Philox block (production, float).  The block is kept in four
+// scalar registers (a dynamically indexed array would live in local memory).
 struct StreamF {
   uint32_t k0, k1, site, iter, slot, k;
-  uint32_t o[4];
+  uint32_t o0, o1, o2, o3;
   __device__ __forceinline__ void open(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t kind, uint32_t idx,
                                       unsigned*) {
     k0 = d.k0; k1 = d.k1; site = d.site0 + local_site; iter = it; slot = make_slot(kind, idx); k = 0;
   }
   __device__ __forceinline__ float next() {
-    if ((k & 3u) == 0u) philox4x32_10(k >> 2, slot, iter, site, k0, k1, o);
-    uint32_t x = o[k & 3u];
+    const uint32_t j = k & 3u;
+    if (j == 0u) {
+      uint32_t o[4];
+      philox4x32_10(k >> 2, slot, iter, site, k0, k1, o);
+      o0 = o[0]; o1 = o[1]; o2 = o[2]; o3 = o[3];
+    }
+    const uint32_t x = j == 0u ? o0 : j == 1u ? o1 : j == 2u ? o2 : o3;
     k++;
     return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);
   }
@@ -169,6 +185,44 @@ template <> struct ExpDev<double, false> {
 };
 template <> struct ExpDev<float, false> {
   static __device__ __forceinline__ float draw(StreamF& g) { return -logf(g.next()); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Production stream of the exponential gaps of one (site, branch, sweep).  FP32: the first two uniforms come from a
+// Philox block shared by the two branches 2j, 2j+1 (words 0,1 / 2,3 of the block keyed by K_BREXP2, j), so the
+// common case — zero or one new virtual jump — costs half a Philox block per branch; further uniforms come from the
+// branch's own K_BREXP stream.  FP64: the branch's own stream from the start.
+// ------------------------------------------------------------------------------------------------
+template <typename Real> struct BranchGaps;
+template <> struct BranchGaps<float> {
+  uint32_t w0, w1, k;
+  StreamF rest;
+  static __device__ __forceinline__ void pair_block(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t e, uint32_t o[4]) {
+    philox4x32_10(e >> 1, make_slot(K_BREXP2, 0u), it, d.site0 + local_site, d.k0, d.k1, o);
+  }
+  __device__ __forceinline__ void open_with(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t e, const uint32_t o[4]) {
+    w0 = (e & 1u) ? o[2] : o[0]; w1 = (e & 1u) ? o[3] : o[1]; k = 0;
+    rest.open(d, local_site, it, K_BREXP, e, nullptr);
+  }
+  __device__ __forceinline__ void open(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t e, unsigned*) {
+    uint32_t o[4];
+    pair_block(d, local_site, it, e, o);
+    open_with(d, local_site, it, e, o);
+  }
+  static __device__ __forceinline__ float cvt(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+  __device__ __forceinline__ float gap() {
+    float u;
+    if (k == 0u) u = cvt(w0); else if (k == 1u) u = cvt(w1); else u = rest.next();
+    k++;
+    return -logf(u);
+  }
+};
+template <> struct BranchGaps<double> {
+  StreamD s;
+  __device__ __forceinline__ void open(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t e, unsigned* err) {
+    s.open(d, local_site, it, K_BREXP, e, err);
+  }
+  __device__ __forceinline__ double gap() { return -log(s.next()); }
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -506,7 +506,10 @@ struct ChainT : pm_chain {
       P.tipcode = t.tipcode.template as<uint8_t>(); P.node_state = t.node_state.template as<uint8_t>();
       P.meta = t.meta.template as<uint32_t>(); P.PL = t.PL.template as<Real>();
       for (int b = 0; b < 2; b++) { P.rec_len[b] = t.rec_len[b].template as<Real>(); P.rec_st[b] = t.rec_st[b].template as<uint8_t>(); }
-      P.normalize = V.normalize; P.full_counts = V.full_counts; P.parity_tips = V.parity_tips;
+      // per-node rescaling (makePLrcpp_bigtree :525) only rescales the weights of each draw: the production
+      // arithmetic always applies it (FP32 partials underflow after ~40 tips otherwise); the deterministic mode
+      // follows the variant, underflow included
+      P.normalize = V.normalize || !exact; P.full_counts = V.full_counts; P.parity_tips = V.parity_tips;
       P.dw_partial = t.dw_partial.template as<double>(); P.cnt = cnt.as<unsigned long long>();
       P.root_out = root_out.as<int>(); P.err_flag = err_flag.as<unsigned>();
       const uint64_t key = opt.seed + (uint64_t)ti * 0x9E3779B97F4A7C15ull;

@@ -125,11 +125,98 @@ __global__ void __launch_bounds__(256) k_prune(ChainParams<Real> P) {
             for (int j = 0; j < n; j++) s += out[j];
             const Real inv = (Real)1 / s;
 #pragma unroll
-            for (int j = 0; j < n; j++) out[j] *= inv;
+            for (int j = 0; j < n; j++) out[j] = fmax(out[j] * inv, (Real)PM_PARTIAL_FLOOR);
           }
         }
         VecIO<Real, NS>::store(P.PL + ((long long)(pn - P.T) * S + site) * n, n, out);
       }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1, production arithmetic, 2 or 4 states.  Same tiling as k_prune; what changes is the instruction stream:
+// every lane multiplies by its own tabulated power P_k = B^k straight from shared memory (k = 0 is the identity,
+// so lanes with different jump counts do not diverge), vector loads for the matrix rows, and two nodes of a
+// level in flight per warp so that more child partials are outstanding per thread.
+// ------------------------------------------------------------------------------------------------
+template <typename Real, int NS>
+__device__ __forceinline__ void pow_times(const ChainParams<Real>& P, const Real* sPow, int npow_s, int k, Real* v) {
+  if (k < npow_s) {
+    const Real* M = sPow + k * NS * NS;
+    Real y[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      Real acc = 0;
+#pragma unroll
+      for (int j = 0; j < NS; j++) acc += M[i * NS + j] * v[j];
+      y[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < NS; i++) v[i] = y[i];
+  } else if (k < P.jcap) {
+    matvec<Real, NS, false>(P.ppow + (size_t)k * NS * NS, NS, v);
+  } else {
+    for (int r = 0; r < k; r++) matvec<Real, NS, false>(sPow + NS * NS, NS, v);  // P_1 = B
+  }
+}
+
+template <typename Real, int NS>
+__global__ void __launch_bounds__(256) k_prune_fast(ChainParams<Real> P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Real* sBs = reinterpret_cast<Real*>(smem_raw);
+  Real* sPow = sBs + NS * NS;
+  const int npow_s = min(PM_SMEM_POW, P.jcap);
+  load_model_smem<Real>(P, NS, nullptr, sBs, nullptr, sPow, npow_s);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long S = P.S;
+  const long long site_raw = (long long)blockIdx.x * 32 + lane;
+  const bool active = site_raw < S;
+  const long long site = active ? site_raw : S - 1;
+  const bool parity = P.parity_tips != 0;
+  const bool normalize = P.normalize != 0;
+  const int T = P.T;
+  const uint32_t* __restrict__ meta = P.meta + site;
+  const uint8_t* __restrict__ tip = P.tipcode + site;
+  Real* __restrict__ PLs = P.PL + site * NS;
+  const long long rowPL = S * NS;
+
+  auto load_child = [&](int c, Real* v) {
+    if (c < T) tip_partial<Real, NS>(tip[(long long)c * S], NS, parity, v);
+    else VecIO<Real, NS>::load(PLs + (long long)(c - T) * rowPL, NS, v);
+  };
+  auto finish = [&](int pn, int ka, int kb, Real* va, Real* vb) {
+    pow_times<Real, NS>(P, sPow, npow_s, kb, vb);
+    pow_times<Real, NS>(P, sPow, npow_s, ka, va);
+    Real out[NS];
+    Real s = 0;
+#pragma unroll
+    for (int j = 0; j < NS; j++) { out[j] = vb[j] * va[j]; s += out[j]; }
+    if (normalize) {
+      const Real inv = (Real)1 / s;
+#pragma unroll
+      for (int j = 0; j < NS; j++) out[j] = fmax(out[j] * inv, (Real)PM_PARTIAL_FLOOR);
+    }
+    if (active) VecIO<Real, NS>::store(PLs + (long long)(pn - T) * rowPL, NS, out);
+  };
+
+  for (int l = 0; l < P.n_up_levels; l++) {
+    const int beg = __ldg(P.up_off + l), end = __ldg(P.up_off + l + 1);
+    for (int idx = beg + warp; idx < end; idx += 2 * nw) {
+      const bool two = idx + nw < end;  // warp-uniform
+      const int* en0 = P.up_entries + 5 * idx;
+      const int* en1 = P.up_entries + 5 * (two ? idx + nw : idx);
+      const int pn0 = __ldg(en0), a0 = __ldg(en0 + 1), ea0 = __ldg(en0 + 2), b0 = __ldg(en0 + 3), eb0 = __ldg(en0 + 4);
+      const int pn1 = __ldg(en1), a1 = __ldg(en1 + 1), ea1 = __ldg(en1 + 2), b1 = __ldg(en1 + 3), eb1 = __ldg(en1 + 4);
+      const uint32_t ma0 = meta[(long long)ea0 * S], mb0 = meta[(long long)eb0 * S];
+      const uint32_t ma1 = meta[(long long)ea1 * S], mb1 = meta[(long long)eb1 * S];
+      Real va0[NS], vb0[NS], va1[NS], vb1[NS];
+      load_child(a0, va0); load_child(b0, vb0);
+      load_child(a1, va1); load_child(b1, vb1);
+      finish(pn0, (int)(ma0 & 0xffffu) - 1, (int)(mb0 & 0xffffu) - 1, va0, vb0);
+      if (two) finish(pn1, (int)(ma1 & 0xffffu) - 1, (int)(mb1 & 0xffffu) - 1, va1, vb1);
     }
     __syncthreads();
   }
@@ -196,6 +283,95 @@ __global__ void __launch_bounds__(256) k_nodes(ChainParams<Real> P, uint32_t ite
         Stream g; g.open(P.rng, (uint32_t)site, iter, K_NODE, (uint32_t)v, P.err_flag);
         const int s = categorical<Real, NC, EXACT>(w, n, g.next(), P.err_flag);
         P.node_state[(long long)v * S + site] = (uint8_t)s;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2, production arithmetic, 2 or 4 states.  One Philox block feeds FOUR consecutive entries of the top-down
+// list (the block is keyed by list position / 4, the word by position % 4), which cuts the dominant cost of the
+// draw — ten Philox rounds per node — by four.  A warp owns a group of four positions.
+// ------------------------------------------------------------------------------------------------
+template <typename Real> __device__ __forceinline__ Real u01_from_word(uint32_t x);
+template <> __device__ __forceinline__ float u01_from_word<float>(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+template <> __device__ __forceinline__ double u01_from_word<double>(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
+
+template <typename Real, int NS>
+__global__ void __launch_bounds__(256) k_nodes_fast(ChainParams<Real> P, uint32_t iter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Real* sBs = reinterpret_cast<Real*>(smem_raw);
+  Real* sVec = sBs + NS * NS;  // pid, scale_old, scale_new
+  Real* sPow = sVec + 3 * NS;
+  const int npow_s = min(PM_SMEM_POW, P.jcap);
+  load_model_smem<Real>(P, NS, nullptr, sBs, sVec, sPow, npow_s);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long S = P.S;
+  const long long site_raw = (long long)blockIdx.x * 32 + lane;
+  const bool active = site_raw < S;
+  const long long site = active ? site_raw : S - 1;
+  const bool parity = P.parity_tips != 0;
+  const int T = P.T;
+  const uint32_t gsite = P.rng.site0 + (uint32_t)site;
+  if (warp == 0) {  // root :618-627
+    Real w[NS], pl[NS];
+    VecIO<Real, NS>::load(P.PL + ((long long)(P.root - T) * S + site) * NS, NS, pl);
+#pragma unroll
+    for (int j = 0; j < NS; j++) w[j] = sVec[j] * pl[j];
+    uint32_t o[4];
+    philox4x32_10(0xffffffffu, make_slot(K_NODEGRP, 0u), iter, gsite, P.rng.k0, P.rng.k1, o);
+    const int s = categorical<Real, NS, false>(w, NS, u01_from_word<Real>(o[0]), P.err_flag);
+    if (active) {
+      P.node_state[(long long)P.root * S + site] = (uint8_t)s;
+      if (gsite == 0u) *P.root_out = s;
+    }
+  }
+  __syncthreads();
+  for (int l = 0; l < P.n_down_levels; l++) {
+    const int beg = __ldg(P.down_off + l), end = __ldg(P.down_off + l + 1);
+    for (int grp = (beg >> 2) + warp; grp <= ((end - 1) >> 2); grp += nw) {
+      uint32_t o[4];
+      philox4x32_10((uint32_t)grp, make_slot(K_NODEGRP, 0u), iter, gsite, P.rng.k0, P.rng.k1, o);
+      const int p0 = max(beg, grp << 2), p1 = min(end, (grp << 2) + 4);
+      // issue the loads of the whole group first
+      int vs[4], ks[4], pss[4];
+      Real pls[4][NS];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int pos = min(p0 + q, p1 - 1);
+        const int* en = P.down_entries + 3 * pos;
+        const int v = __ldg(en), pn = __ldg(en + 1), e = __ldg(en + 2);
+        vs[q] = v;
+        pss[q] = P.node_state[(long long)pn * S + site];
+        ks[q] = (int)(P.meta[(long long)e * S + site] & 0xffffu) - 1;
+        if (v < T) tip_partial<Real, NS>(P.tipcode[(long long)v * S + site], NS, parity, pls[q]);
+        else VecIO<Real, NS>::load(P.PL + ((long long)(v - T) * S + site) * NS, NS, pls[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int pos = p0 + q;
+        if (pos < p1) {  // warp-uniform
+          const int k = ks[q], ps = pss[q];
+          Real w[NS];
+          if (k < npow_s) {
+#pragma unroll
+            for (int j = 0; j < NS; j++) w[j] = sPow[k * NS * NS + ps * NS + j];
+          } else if (k < P.jcap) {
+#pragma unroll
+            for (int j = 0; j < NS; j++) w[j] = P.ppow[(size_t)k * NS * NS + ps * NS + j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < NS; j++) w[j] = (Real)(j == ps);
+            for (int r = 0; r < k; r++) matvec_t<Real, NS, false>(sBs, NS, w);
+          }
+#pragma unroll
+          for (int j = 0; j < NS; j++) w[j] *= pls[q][j];
+          const uint32_t word = (pos & 3) == 0 ? o[0] : (pos & 3) == 1 ? o[1] : (pos & 3) == 2 ? o[2] : o[3];
+          const int s = categorical<Real, NS, false>(w, NS, u01_from_word<Real>(word), P.err_flag);
+          if (active) P.node_state[(long long)vs[q] * S + site] = (uint8_t)s;
+        }
       }
     }
     __syncthreads();
@@ -360,6 +536,251 @@ __global__ void __launch_bounds__(128) k_paths(ChainParams<Real> P, uint32_t ite
 #pragma unroll
     for (int j = 0; j < (NS > 0 ? NS : 1); j++) {
       double v = (double)Racc[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) s_dw[warp * n + j] = v;
+    }
+  }
+  __syncthreads();
+  const long long blk = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+  if ((int)threadIdx.x < n) {
+    double v;
+    if (NS > 0) { v = 0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += s_dw[w * n + threadIdx.x]; }
+    else v = s_dw[threadIdx.x];
+    P.dw_partial[blk * n + threadIdx.x] = v;
+  }
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) if (s_cnt[i]) atomicAdd(&P.cnt[i], (unsigned long long)s_cnt[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3, production arithmetic.  Same algorithm as k_paths<.., false>, reorganised around warp divergence: with
+// Omega * t ~ 0.2 most branches need no resampling at all (no jump point, or one virtual jump between equal
+// end states), yet in a warp of 32 sites almost always SOME lane does.  Lanes therefore handle the common case
+// inline and push the other branches on a small per-thread FIFO in shared memory; the warp runs the general
+// path only when at least PM_SERVE_LANES lanes have work queued (or a FIFO is full), each lane popping its own
+// branch.  Records are appended in pop order = branch order, so the next sweep reads them back in the same order.
+// ------------------------------------------------------------------------------------------------
+#define PM_QDEPTH 8
+#define PM_SERVE_LANES 20
+
+template <typename Real, int NS>
+__global__ void __launch_bounds__(128) k_paths_fast(ChainParams<Real> P, uint32_t iter, int first, int chunk) {
+  constexpr int NC = NS > 0 ? NS : PM_NMAX;
+  constexpr int NR = NS > 0 ? NS : 1;
+  typedef typename StreamSel<Real, false>::type Stream;
+  typedef BranchGaps<Real> Gaps;
+  typedef Ar<Real, true> AX;  // piece arithmetic is pinned: the regenerating sweep must reproduce it bit for bit
+  const int n = NS > 0 ? NS : P.n;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_dw = reinterpret_cast<double*>(smem_raw);                 // [4 warps][n] (NS>0) or [n] atomics (NS==0)
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_dw + 4 * n);       // [n*n]
+  Real* sB = reinterpret_cast<Real*>(s_cnt + n * n + ((n * n) & 1));  // dense B (forward row)
+  Real* sBs = sB + n * n;
+  Real* sVec = sBs + n * n;
+  Real* sPow = sVec + 3 * n;
+  const int npow_s = min(smem_pow_count<NS, false>(), P.jcap);
+  __shared__ unsigned short s_q[PM_QDEPTH][128];
+  load_model_smem<Real>(P, n, sB, sBs, sVec, sPow, npow_s);
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) s_cnt[i] = 0;
+  for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_dw[i] = 0.0;
+  __syncthreads();
+  const Real* s_scale_old = sVec + n;
+  const Real* s_scale_new = sVec + 2 * n;
+  const long long S = P.S;
+  const long long site_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = site_raw < S;
+  const long long site = active ? site_raw : S - 1;  // idle lanes shadow a valid site for loads, never store
+  const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
+  const int cap0 = __ldg(P.cap_off + blockIdx.y), cap_c = __ldg(P.cap_off + blockIdx.y + 1) - cap0;
+  const long long abase = (long long)cap0 * S + site * (long long)cap_c;
+  const Real* __restrict__ rd_len = P.rec_len[(iter & 1u) ^ 1u] + abase;
+  const uint8_t* __restrict__ rd_st = P.rec_st[(iter & 1u) ^ 1u] + abase;
+  Real* __restrict__ wr_len = P.rec_len[iter & 1u] + abase;
+  uint8_t* __restrict__ wr_st = P.rec_st[iter & 1u] + abase;
+  int rd = 0, wr = 0;
+  const bool full = P.full_counts != 0;
+  Real Racc[NR];
+  double Rsum[NR];
+#pragma unroll
+  for (int j = 0; j < NR; j++) { Racc[j] = 0; Rsum[j] = 0; }
+  unsigned errbits = 0;
+  int qhead = 0, qn = 0;
+
+  auto add_dwell = [&](int s, Real L) {
+    if (NS > 0) {
+#pragma unroll
+      for (int j = 0; j < NR; j++) Racc[j] += (s == j) ? L : (Real)0;
+    } else atomicAdd(&s_dw[s], (double)L);
+  };
+
+  // prefetch of the per-branch inputs
+  uint32_t mt_n = 0; int ps_n = 0, cs_n = 0;
+  auto fetch = [&](int e) {
+    mt_n = P.meta[(long long)e * S + site];
+    ps_n = P.node_state[(long long)__ldg(P.e_parent + e) * S + site];
+    cs_n = P.node_state[(long long)__ldg(P.e_child + e) * S + site];
+  };
+  if (e0 < e1) fetch(e0);
+  // FP32: Philox block shared by the branch pair (2j, 2j+1) of the current sweep, refreshed when the pair changes
+  uint32_t pair_o[4]; int pair_id = -1;
+  auto open_new = [&](Gaps& g, int e) {
+    if constexpr (std::is_same<Real, float>::value) {
+      if ((e >> 1) != pair_id) { Gaps::pair_block(P.rng, (uint32_t)site, iter, (uint32_t)e, pair_o); pair_id = e >> 1; }
+      g.open_with(P.rng, (uint32_t)site, iter, (uint32_t)e, pair_o);
+    } else g.open(P.rng, (uint32_t)site, iter, (uint32_t)e, P.err_flag);
+  };
+
+  int e = e0;
+  for (;;) {
+    const bool have = e < e1;  // uniform across the block
+    if (have) {
+      const uint32_t mt = mt_n; const int ps = ps_n, cs = cs_n;
+      if (e + 1 < e1) fetch(e + 1);
+      const int m = (int)(mt & 0xffffu), nj = (int)((mt >> 16) & 0xffu);
+      const bool easy = !first && nj == 0 && (m == 1 || (m == 2 && ps == cs));
+      if (active) {
+        bool queued = !easy;
+        if (easy) {
+          // one run of the whole branch in state cs.  Decide the number of new virtual jumps from at most two gaps;
+          // the rare third gap sends the branch to the general path (nothing has been committed yet).
+          const Real L = __ldg(P.e_len + e);
+          const Real sc = s_scale_new[cs];
+          int newm = 1;
+          if (isfinite(sc) && sc > (Real)0) {
+            Gaps gnew; open_new(gnew, e);
+            const Real g0 = AX::mul(sc, gnew.gap());
+            if (g0 < L) {
+              const Real t2 = AX::add(g0, AX::mul(sc, gnew.gap()));
+              if (t2 < L) queued = true; else newm = 2;
+            }
+          }
+          if (!queued) {
+            if (full && m == 2) atomicAdd(&s_cnt[ps * n + cs], 1u);  // the virtual self-jump (bf/ks/mt)
+            add_dwell(cs, L);
+            P.meta[(long long)e * S + site] = (uint32_t)newm | ((uint32_t)cs << 24);
+          }
+        }
+        if (queued) {
+          s_q[(qhead + qn) & (PM_QDEPTH - 1)][threadIdx.x] = (unsigned short)(e - e0);
+          qn++;
+        }
+      }
+      if (NS > 0 && ((e - e0) & 63) == 63) {
+#pragma unroll
+        for (int j = 0; j < NR; j++) { Rsum[j] += (double)Racc[j]; Racc[j] = 0; }
+      }
+      e++;
+    }
+    const unsigned pend = __ballot_sync(0xffffffffu, qn > 0);
+    if (!have && pend == 0u) break;  // `have` is block-uniform, pend warp-uniform
+    const unsigned fullq = __ballot_sync(0xffffffffu, qn == PM_QDEPTH);
+    const bool serve = !have || fullq != 0u || __popc(pend) >= PM_SERVE_LANES;
+    if (serve && qn > 0) {
+      // ---- general path for one queued branch ----
+      const int eb = e0 + (int)s_q[qhead][threadIdx.x];
+      qhead = (qhead + 1) & (PM_QDEPTH - 1); qn--;
+      const long long pe = (long long)eb * S + site;
+      const uint32_t mt = P.meta[pe];
+      const int m = (int)(mt & 0xffffu), nj = (int)((mt >> 16) & 0xffu), s0 = (int)(mt >> 24);
+      const int ps = P.node_state[(long long)__ldg(P.e_parent + eb) * S + site];
+      const int cs = P.node_state[(long long)__ldg(P.e_child + eb) * S + site];
+      const Real Le = __ldg(P.e_len + eb);
+      Gaps gnew; gnew.open(P.rng, (uint32_t)site, iter, (uint32_t)eb, P.err_flag);
+      Gaps gold; gold.open(P.rng, (uint32_t)site, first ? iter : iter - 1u, (uint32_t)eb, P.err_flag);
+      Stream gst; gst.open(P.rng, (uint32_t)site, iter, K_BRSTATE, (uint32_t)eb, P.err_flag);
+      int nout = 0, newm = 0, sfirst = 0;
+      const int wr0 = wr;
+
+      auto emit = [&](Real L, int s, bool store) {
+        if (nout == 0) sfirst = s;
+        if (store) {
+          if (wr < cap_c && nout < PM_LOCAL_PATH_MAX) { wr_len[wr] = L; wr_st[wr] = (uint8_t)s; wr++; }
+          else errbits |= PM_DE_PATH_CAP;
+        }
+        add_dwell(s, L);
+        const Real sc = s_scale_new[s];
+        if (isfinite(sc) && sc > (Real)0) {
+          Real tot = 0;
+          for (;;) {
+            const Real g = AX::mul(sc, gnew.gap());
+            const Real t2 = AX::add(tot, g);
+            if (t2 < L) { tot = t2; newm++; if (newm > 70000) break; } else break;
+          }
+        }
+        newm++;
+        nout++;
+      };
+
+      // old path: runs (oldL, oldS), read on demand; their virtual jumps are regenerated from last sweep's key
+      int jrun = 0; const int nrun = nj + 1;
+      Real oldL = Le; int oldS = s0;
+      if (!first && nj > 0) {
+        const int q = min(rd, cap_c - 1);
+        oldL = rd_len[q]; oldS = rd_st[q];
+      }
+      Real tot = 0; long long cp = first ? P.maps_off[eb] : 0;
+      auto next_piece = [&]() -> Real {
+        if (first) return (Real)P.maps_len[cp++];
+        if (jrun >= nrun) { errbits |= PM_DE_INCONSISTENT; return (Real)0; }
+        const Real sc = s_scale_old[oldS];
+        if (isfinite(sc) && sc > (Real)0) {
+          const Real g = AX::mul(sc, gold.gap());
+          const Real t2 = AX::add(tot, g);
+          if (t2 < oldL) { tot = t2; return g; }
+        }
+        const Real r = AX::sub(oldL, tot);
+        jrun++; tot = 0;
+        if (jrun < nrun) { const int q = min(rd + jrun, cap_c - 1); oldL = rd_len[q]; oldS = rd_st[q]; }
+        return r;
+      };
+
+      int cur_state = (m == 1) ? cs : ps;
+      Real cur_len = next_piece();
+      int prev = cur_state;
+      for (int p = 1; p < m; p++) {
+        int st;
+        if (p == m - 1) st = cs;
+        else {
+          const int jd = m - p - 1;  // beta_jd = Bs^jd e_cs
+          Real w[NC];
+          const Real* M = (jd < npow_s) ? (sPow + jd * n * n) : (jd < P.jcap ? P.ppow + (size_t)jd * n * n : nullptr);
+          if (M) {
+#pragma unroll
+            for (int c = 0; c < n; c++) w[c] = M[c * n + cs];
+          } else {
+#pragma unroll
+            for (int c = 0; c < n; c++) w[c] = (Real)(c == cs);
+            for (int r = 0; r < jd; r++) matvec<Real, NC, false>(sBs, n, w);
+          }
+#pragma unroll
+          for (int c = 0; c < n; c++) w[c] = sB[prev * n + c] * w[c];
+          st = categorical<Real, NC, false>(w, n, gst.next(), P.err_flag);
+        }
+        const Real len = next_piece();
+        if (full) atomicAdd(&s_cnt[prev * n + st], 1u);
+        if (st == cur_state) cur_len = cur_len + len;
+        else {
+          emit(cur_len, cur_state, true);
+          if (!full) atomicAdd(&s_cnt[cur_state * n + st], 1u);
+          cur_state = st; cur_len = len;
+        }
+        prev = st;
+      }
+      if (!first && nj > 0) rd += nj + 1;
+      // a single-run path is not stored: the next sweep takes its length from the tree
+      if (nout == 0) emit(Le, cur_state, false); else emit(cur_len, cur_state, true);
+      if (newm > 65535) { errbits |= PM_DE_M_OVERFLOW; newm = 65535; }
+      if (nout > PM_LOCAL_PATH_MAX) { nout = PM_LOCAL_PATH_MAX; wr = wr0 + nout; }
+      P.meta[pe] = (uint32_t)newm | ((uint32_t)(nout - 1) << 16) | ((uint32_t)sfirst << 24);
+    }
+  }
+  if (errbits) atomicOr(P.err_flag, errbits);
+
+  if (NS > 0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+      double v = Rsum[j] + (double)Racc[j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
       if (lane == 0) s_dw[warp * n + j] = v;

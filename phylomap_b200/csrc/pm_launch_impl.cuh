@@ -5,16 +5,19 @@ namespace pm {
 
 template <typename Real, int NS, bool EXACT>
 void Sweep<Real, NS, EXACT>::prune(const ChainParams<Real>& P, int grid, size_t smem, cudaStream_t st) {
-  k_prune<Real, NS, EXACT><<<grid, 256, smem, st>>>(P);
+  if constexpr (!EXACT && (NS == 2 || NS == 4)) k_prune_fast<Real, NS><<<grid, 256, smem, st>>>(P);
+  else k_prune<Real, NS, EXACT><<<grid, 256, smem, st>>>(P);
 }
 template <typename Real, int NS, bool EXACT>
 void Sweep<Real, NS, EXACT>::nodes(const ChainParams<Real>& P, int grid, size_t smem, cudaStream_t st, uint32_t iter) {
-  k_nodes<Real, NS, EXACT><<<grid, 256, smem, st>>>(P, iter);
+  if constexpr (!EXACT && (NS == 2 || NS == 4)) k_nodes_fast<Real, NS><<<grid, 256, smem, st>>>(P, iter);
+  else k_nodes<Real, NS, EXACT><<<grid, 256, smem, st>>>(P, iter);
 }
 template <typename Real, int NS, bool EXACT>
 void Sweep<Real, NS, EXACT>::paths(const ChainParams<Real>& P, dim3 grid, size_t smem, cudaStream_t st, uint32_t iter,
                                    int first, int chunk) {
-  k_paths<Real, NS, EXACT><<<grid, 128, smem, st>>>(P, iter, first, chunk);
+  if constexpr (EXACT) k_paths<Real, NS, true><<<grid, 128, smem, st>>>(P, iter, first, chunk);
+  else k_paths_fast<Real, NS><<<grid, 128, smem, st>>>(P, iter, first, chunk);
 }
 
 }  // namespace pm

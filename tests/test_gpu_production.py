@@ -33,7 +33,7 @@ def test_ks_against_oracle_chain(oracle, precision):
 def test_ks_rate_traces_bf(oracle):
     """Rate-updating sampler: posterior of (lambda01, lambda10) from the GPU chain vs the oracle chain."""
     z = cases.tree2(T=40, S=1, seed=8, mean_branch=4.0)
-    N, thin, burn = 8000, 10, 500
+    N, thin, burn = 24000, 40, 1000
     ref = oracle.OracleRun(oracle.BF, [z.oracle_dict()], cases.Q2.copy(), cases.PID2, 1.0, N, prior=cases.PRIOR_BF,
                            rng_mode=oracle.SEQUENTIAL, seed=5).run()[burn::thin]
     got = pb.sumstatMCMCbf(z, cases.Q2.copy(), cases.PID2, 1.0, N, cases.PRIOR_BF, seed=77, precision="f32")[burn::thin]
