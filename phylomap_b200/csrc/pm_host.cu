@@ -154,7 +154,8 @@ struct TreeDev {
   pm::host::Schedule sch;
   long long S = 0;
   DevBuf up_entries, up_off, down_entries, down_off, e_parent, e_child, e_len, maps_off, maps_len, cap_off;
-  DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial;
+  DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, slow_mask;
+  int mask_words = 0;
   std::vector<int> cap_off_h;
   pm::ChainParams<Real> P;
   dim3 paths_grid;
@@ -254,10 +255,10 @@ struct ChainT : pm_chain {
     pm::Sweep<Real, NSc, EX>::paths(t.P, t.paths_grid, smem_paths, stream, iter, iter == 0 ? 1 : 0, t.chunk);
     end_timed();
     begin_timed(3);
-    pm::k_reduce<<<1, 256, 0, stream>>>(t.dw_partial.template as<double>(), t.nblocks, n, cnt.as<unsigned long long>(),
+    pm::k_reduce<<<1, 256, 0, stream>>>(t.dw_partial.template as<double>(), 2 * t.nblocks, n, cnt.as<unsigned long long>(),
                                         root_out.as<int>(), row, 0);
     end_timed();
-    launches += 4;
+    launches += (exact || iter == 0) ? 4 : 5;
   }
   template <int NSc, bool EX>
   void launch_prune_t(TreeDev<Real>& t) {
@@ -441,9 +442,13 @@ struct ChainT : pm_chain {
         t->rec_st[b].alloc((size_t)R * S);
       }
       CK(cudaMemsetAsync(t->node_state.p, 0, t->node_state.bytes, stream));
-      t->dw_partial.alloc((size_t)t->nblocks * n * sizeof(double));
+      // two rows of partial dwell sums per block: [0, nblocks) easy / deterministic kernel, [nblocks, 2 nblocks) hard kernel
+      t->dw_partial.alloc((size_t)2 * t->nblocks * n * sizeof(double));
+      CK(cudaMemsetAsync(t->dw_partial.p, 0, t->dw_partial.bytes, stream));
+      t->mask_words = (t->chunk + 31) / 32;
+      if (!exact) t->slow_mask.alloc((size_t)ny * t->mask_words * S * sizeof(uint32_t));
       dev_bytes += t->tipcode.bytes + t->node_state.bytes + t->meta.bytes + t->PL.bytes + 2 * (t->rec_len[0].bytes + t->rec_st[0].bytes) +
-                   t->dw_partial.bytes;
+                   t->dw_partial.bytes + t->slow_mask.bytes;
       trees.push_back(std::move(t));
     }
 
@@ -494,6 +499,7 @@ struct ChainT : pm_chain {
       pm::ChainParams<Real>& P = t.P;
       P.n = n; P.T = T; P.E = E; P.S = t.S;
       P.cap_off = t.cap_off.template as<int>();
+      P.slow_mask = t.slow_mask.template as<uint32_t>(); P.mask_words = t.mask_words;
       P.model = model.as<Real>(); P.ppow = ppow.as<Real>(); P.jcap = jcap;
       P.up_entries = t.up_entries.template as<int>(); P.up_off = t.up_off.template as<int>();
       P.n_up_levels = (int)t.sch.up_off.size() - 1;

@@ -39,6 +39,7 @@ struct ChainParams {
   const long long* maps_off; const double* maps_len;
   int root;
   const uint8_t* tipcode; uint8_t* node_state; uint32_t* meta; Real* PL;
+  uint32_t* slow_mask; int mask_words;  // production: per (chunk, word, site) bit mask of the branches left to k_paths_hard
   Real* rec_len[2]; uint8_t* rec_st[2];  // double-buffered path records: written by sweep i into [i & 1], read by sweep i + 1
   int normalize, full_counts, parity_tips;
   double* dw_partial; unsigned long long* cnt; int* root_out;
@@ -553,18 +554,112 @@ __global__ void __launch_bounds__(128) k_paths(ChainParams<Real> P, uint32_t ite
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3, production arithmetic.  Same algorithm as k_paths<.., false>, reorganised around warp divergence: with
-// Omega * t ~ 0.2 most branches need no resampling at all (no jump point, or one virtual jump between equal
-// end states), yet in a warp of 32 sites almost always SOME lane does.  Lanes therefore handle the common case
-// inline and push the other branches on a small per-thread FIFO in shared memory; the warp runs the general
-// path only when at least PM_SERVE_LANES lanes have work queued (or a FIFO is full), each lane popping its own
-// branch.  Records are appended in pop order = branch order, so the next sweep reads them back in the same order.
+// K3, production arithmetic: two kernels.  With Omega * t ~ 0.2 most (site, branch) pairs need no resampling at
+// all — no jump point, or one virtual jump between equal end states — yet in a warp of 32 sites almost always SOME
+// lane does, so a single kernel runs the general path at a quarter of its lanes.
+//   k_paths_easy  streams over the branches of its chunk (coalesced, few registers, memory-bound): commits the easy
+//                 branches (dwell time, virtual self-jump count, number of new virtual jumps from at most two
+//                 exponential gaps) and sets a bit for every other branch in a per-(site, chunk) mask.
+//   k_paths_hard  thread = (site, chunk) again; every lane walks the set bits of ITS mask, so all lanes of a warp
+//                 are in the general path together.  Records are appended in branch order, which is the order the
+//                 next sweep reads them back in.
 // ------------------------------------------------------------------------------------------------
-#define PM_QDEPTH 8
-#define PM_SERVE_LANES 20
+template <typename Real, int NS>
+__global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_t iter, int chunk) {
+  constexpr int NR = NS > 0 ? NS : 1;
+  typedef BranchGaps<Real> Gaps;
+  typedef Ar<Real, true> AX;
+  const int n = NS > 0 ? NS : P.n;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_dw = reinterpret_cast<double*>(smem_raw);                // [4 warps][n] (NS>0) or [n] atomics (NS==0)
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_dw + 4 * n);      // [n] virtual self-jumps per state
+  Real* s_scale_new = reinterpret_cast<Real*>(s_cnt + n + (n & 1));  // [n]
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { s_cnt[i] = 0; s_scale_new[i] = P.model[2 * n * n + 2 * n + i]; }
+  for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_dw[i] = 0.0;
+  __syncthreads();
+  const long long S = P.S;
+  const long long site_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = site_raw < S;
+  const long long site = active ? site_raw : S - 1;
+  const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
+  const bool full = P.full_counts != 0;
+  uint32_t* __restrict__ mask = P.slow_mask + (long long)blockIdx.y * P.mask_words * S + site;
+  Real Racc[NR]; double Rsum[NR];
+#pragma unroll
+  for (int j = 0; j < NR; j++) { Racc[j] = 0; Rsum[j] = 0; }
+  uint32_t mt_n = 0; int ps_n = 0, cs_n = 0;
+  auto fetch = [&](int e) {
+    mt_n = P.meta[(long long)e * S + site];
+    ps_n = P.node_state[(long long)__ldg(P.e_parent + e) * S + site];
+    cs_n = P.node_state[(long long)__ldg(P.e_child + e) * S + site];
+  };
+  if (e0 < e1) fetch(e0);
+  uint32_t pair_o[4]; int pair_id = -1;
+  uint32_t bits = 0;
+  for (int e = e0; e < e1; e++) {
+    const uint32_t mt = mt_n; const int ps = ps_n, cs = cs_n;
+    if (e + 1 < e1) fetch(e + 1);
+    const int m = (int)(mt & 0xffffu), nj = (int)((mt >> 16) & 0xffu);
+    bool hard = !(nj == 0 && (m == 1 || (m == 2 && ps == cs)));
+    if (!hard) {
+      const Real L = __ldg(P.e_len + e);
+      const Real sc = s_scale_new[cs];
+      int newm = 1;
+      if (isfinite(sc) && sc > (Real)0) {
+        Gaps gnew;
+        if constexpr (std::is_same<Real, float>::value) {
+          if ((e >> 1) != pair_id) { Gaps::pair_block(P.rng, (uint32_t)site, iter, (uint32_t)e, pair_o); pair_id = e >> 1; }
+          gnew.open_with(P.rng, (uint32_t)site, iter, (uint32_t)e, pair_o);
+        } else gnew.open(P.rng, (uint32_t)site, iter, (uint32_t)e, P.err_flag);
+        const Real g0 = AX::mul(sc, gnew.gap());
+        if (g0 < L) {
+          const Real t2 = AX::add(g0, AX::mul(sc, gnew.gap()));
+          if (t2 < L) hard = true; else newm = 2;  // a third gap is rare: leave the branch to the general path
+        }
+      }
+      if (!hard && active) {
+        if (full && m == 2) atomicAdd(&s_cnt[cs], 1u);
+        if (NS > 0) {
+#pragma unroll
+          for (int j = 0; j < NR; j++) Racc[j] += (cs == j) ? L : (Real)0;
+        } else atomicAdd(&s_dw[cs], (double)L);
+        P.meta[(long long)e * S + site] = (uint32_t)newm | ((uint32_t)cs << 24);
+      }
+    }
+    const int b = (e - e0) & 31;
+    bits |= (hard ? 1u : 0u) << b;
+    if (b == 31 || e == e1 - 1) {
+      if (active) mask[(long long)((e - e0) >> 5) * S] = bits;
+      bits = 0;
+      if (NS > 0) {
+#pragma unroll
+        for (int j = 0; j < NR; j++) { Rsum[j] += (double)Racc[j]; Racc[j] = 0; }
+      }
+    }
+  }
+  if (NS > 0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+      double v = Rsum[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) s_dw[warp * n + j] = v;
+    }
+  }
+  __syncthreads();
+  const long long blk = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+  if ((int)threadIdx.x < n) {
+    double v;
+    if (NS > 0) { v = 0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += s_dw[w * n + threadIdx.x]; }
+    else v = s_dw[threadIdx.x];
+    P.dw_partial[blk * n + threadIdx.x] = v;
+    if (s_cnt[threadIdx.x]) atomicAdd(&P.cnt[threadIdx.x * n + threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+  }
+}
 
 template <typename Real, int NS>
-__global__ void __launch_bounds__(128) k_paths_fast(ChainParams<Real> P, uint32_t iter, int first, int chunk) {
+__global__ void __launch_bounds__(128) k_paths_hard(ChainParams<Real> P, uint32_t iter, int first, int chunk) {
   constexpr int NC = NS > 0 ? NS : PM_NMAX;
   constexpr int NR = NS > 0 ? NS : 1;
   typedef typename StreamSel<Real, false>::type Stream;
@@ -579,7 +674,6 @@ __global__ void __launch_bounds__(128) k_paths_fast(ChainParams<Real> P, uint32_
   Real* sVec = sBs + n * n;
   Real* sPow = sVec + 3 * n;
   const int npow_s = min(smem_pow_count<NS, false>(), P.jcap);
-  __shared__ unsigned short s_q[PM_QDEPTH][128];
   load_model_smem<Real>(P, n, sB, sBs, sVec, sPow, npow_s);
   for (int i = threadIdx.x; i < n * n; i += blockDim.x) s_cnt[i] = 0;
   for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_dw[i] = 0.0;
@@ -589,8 +683,10 @@ __global__ void __launch_bounds__(128) k_paths_fast(ChainParams<Real> P, uint32_
   const long long S = P.S;
   const long long site_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = site_raw < S;
-  const long long site = active ? site_raw : S - 1;  // idle lanes shadow a valid site for loads, never store
+  const long long site = active ? site_raw : S - 1;
   const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
+  const int nwords = (e1 - e0 + 31) >> 5;
+  const uint32_t* __restrict__ mask = P.slow_mask + (long long)blockIdx.y * P.mask_words * S + site;
   const int cap0 = __ldg(P.cap_off + blockIdx.y), cap_c = __ldg(P.cap_off + blockIdx.y + 1) - cap0;
   const long long abase = (long long)cap0 * S + site * (long long)cap_c;
   const Real* __restrict__ rd_len = P.rec_len[(iter & 1u) ^ 1u] + abase;
@@ -599,180 +695,123 @@ __global__ void __launch_bounds__(128) k_paths_fast(ChainParams<Real> P, uint32_
   uint8_t* __restrict__ wr_st = P.rec_st[iter & 1u] + abase;
   int rd = 0, wr = 0;
   const bool full = P.full_counts != 0;
-  Real Racc[NR];
   double Rsum[NR];
 #pragma unroll
-  for (int j = 0; j < NR; j++) { Racc[j] = 0; Rsum[j] = 0; }
+  for (int j = 0; j < NR; j++) Rsum[j] = 0;
   unsigned errbits = 0;
-  int qhead = 0, qn = 0;
 
   auto add_dwell = [&](int s, Real L) {
     if (NS > 0) {
 #pragma unroll
-      for (int j = 0; j < NR; j++) Racc[j] += (s == j) ? L : (Real)0;
+      for (int j = 0; j < NR; j++) Rsum[j] += (s == j) ? (double)L : 0.0;
     } else atomicAdd(&s_dw[s], (double)L);
   };
 
-  // prefetch of the per-branch inputs
-  uint32_t mt_n = 0; int ps_n = 0, cs_n = 0;
-  auto fetch = [&](int e) {
-    mt_n = P.meta[(long long)e * S + site];
-    ps_n = P.node_state[(long long)__ldg(P.e_parent + e) * S + site];
-    cs_n = P.node_state[(long long)__ldg(P.e_child + e) * S + site];
-  };
-  if (e0 < e1) fetch(e0);
-  // FP32: Philox block shared by the branch pair (2j, 2j+1) of the current sweep, refreshed when the pair changes
-  uint32_t pair_o[4]; int pair_id = -1;
-  auto open_new = [&](Gaps& g, int e) {
-    if constexpr (std::is_same<Real, float>::value) {
-      if ((e >> 1) != pair_id) { Gaps::pair_block(P.rng, (uint32_t)site, iter, (uint32_t)e, pair_o); pair_id = e >> 1; }
-      g.open_with(P.rng, (uint32_t)site, iter, (uint32_t)e, pair_o);
-    } else g.open(P.rng, (uint32_t)site, iter, (uint32_t)e, P.err_flag);
-  };
-
-  int e = e0;
-  for (;;) {
-    const bool have = e < e1;  // uniform across the block
-    if (have) {
-      const uint32_t mt = mt_n; const int ps = ps_n, cs = cs_n;
-      if (e + 1 < e1) fetch(e + 1);
-      const int m = (int)(mt & 0xffffu), nj = (int)((mt >> 16) & 0xffu);
-      const bool easy = !first && nj == 0 && (m == 1 || (m == 2 && ps == cs));
-      if (active) {
-        bool queued = !easy;
-        if (easy) {
-          // one run of the whole branch in state cs.  Decide the number of new virtual jumps from at most two gaps;
-          // the rare third gap sends the branch to the general path (nothing has been committed yet).
-          const Real L = __ldg(P.e_len + e);
-          const Real sc = s_scale_new[cs];
-          int newm = 1;
-          if (isfinite(sc) && sc > (Real)0) {
-            Gaps gnew; open_new(gnew, e);
-            const Real g0 = AX::mul(sc, gnew.gap());
-            if (g0 < L) {
-              const Real t2 = AX::add(g0, AX::mul(sc, gnew.gap()));
-              if (t2 < L) queued = true; else newm = 2;
-            }
-          }
-          if (!queued) {
-            if (full && m == 2) atomicAdd(&s_cnt[ps * n + cs], 1u);  // the virtual self-jump (bf/ks/mt)
-            add_dwell(cs, L);
-            P.meta[(long long)e * S + site] = (uint32_t)newm | ((uint32_t)cs << 24);
-          }
-        }
-        if (queued) {
-          s_q[(qhead + qn) & (PM_QDEPTH - 1)][threadIdx.x] = (unsigned short)(e - e0);
-          qn++;
-        }
-      }
-      if (NS > 0 && ((e - e0) & 63) == 63) {
-#pragma unroll
-        for (int j = 0; j < NR; j++) { Rsum[j] += (double)Racc[j]; Racc[j] = 0; }
-      }
-      e++;
+  int w = 0; uint32_t bits = 0;
+  const uint32_t lastmask = ((e1 - e0) & 31) ? ((1u << ((e1 - e0) & 31)) - 1u) : 0xffffffffu;
+  if (active) for (;;) {
+    while (bits == 0u && w < nwords) {
+      bits = first ? 0xffffffffu : mask[(long long)w * S];
+      if (w == nwords - 1) bits &= lastmask;
+      w++;
     }
-    const unsigned pend = __ballot_sync(0xffffffffu, qn > 0);
-    if (!have && pend == 0u) break;  // `have` is block-uniform, pend warp-uniform
-    const unsigned fullq = __ballot_sync(0xffffffffu, qn == PM_QDEPTH);
-    const bool serve = !have || fullq != 0u || __popc(pend) >= PM_SERVE_LANES;
-    if (serve && qn > 0) {
-      // ---- general path for one queued branch ----
-      const int eb = e0 + (int)s_q[qhead][threadIdx.x];
-      qhead = (qhead + 1) & (PM_QDEPTH - 1); qn--;
-      const long long pe = (long long)eb * S + site;
-      const uint32_t mt = P.meta[pe];
-      const int m = (int)(mt & 0xffffu), nj = (int)((mt >> 16) & 0xffu), s0 = (int)(mt >> 24);
-      const int ps = P.node_state[(long long)__ldg(P.e_parent + eb) * S + site];
-      const int cs = P.node_state[(long long)__ldg(P.e_child + eb) * S + site];
-      const Real Le = __ldg(P.e_len + eb);
-      Gaps gnew; gnew.open(P.rng, (uint32_t)site, iter, (uint32_t)eb, P.err_flag);
-      Gaps gold; gold.open(P.rng, (uint32_t)site, first ? iter : iter - 1u, (uint32_t)eb, P.err_flag);
-      Stream gst; gst.open(P.rng, (uint32_t)site, iter, K_BRSTATE, (uint32_t)eb, P.err_flag);
-      int nout = 0, newm = 0, sfirst = 0;
-      const int wr0 = wr;
+    if (bits == 0u) break;
+    const int eb = e0 + ((w - 1) << 5) + (__ffs((int)bits) - 1);
+    bits &= bits - 1u;
 
-      auto emit = [&](Real L, int s, bool store) {
-        if (nout == 0) sfirst = s;
-        if (store) {
-          if (wr < cap_c && nout < PM_LOCAL_PATH_MAX) { wr_len[wr] = L; wr_st[wr] = (uint8_t)s; wr++; }
-          else errbits |= PM_DE_PATH_CAP;
-        }
-        add_dwell(s, L);
-        const Real sc = s_scale_new[s];
-        if (isfinite(sc) && sc > (Real)0) {
-          Real tot = 0;
-          for (;;) {
-            const Real g = AX::mul(sc, gnew.gap());
-            const Real t2 = AX::add(tot, g);
-            if (t2 < L) { tot = t2; newm++; if (newm > 70000) break; } else break;
-          }
-        }
-        newm++;
-        nout++;
-      };
+    const long long pe = (long long)eb * S + site;
+    const uint32_t mt = P.meta[pe];
+    const int m = (int)(mt & 0xffffu), nj = (int)((mt >> 16) & 0xffu), s0 = (int)(mt >> 24);
+    const int ps = P.node_state[(long long)__ldg(P.e_parent + eb) * S + site];
+    const int cs = P.node_state[(long long)__ldg(P.e_child + eb) * S + site];
+    const Real Le = __ldg(P.e_len + eb);
+    Gaps gnew; gnew.open(P.rng, (uint32_t)site, iter, (uint32_t)eb, P.err_flag);
+    Gaps gold; gold.open(P.rng, (uint32_t)site, first ? iter : iter - 1u, (uint32_t)eb, P.err_flag);
+    Stream gst; gst.open(P.rng, (uint32_t)site, iter, K_BRSTATE, (uint32_t)eb, P.err_flag);
+    int nout = 0, newm = 0, sfirst = 0;
+    const int wr0 = wr;
 
-      // old path: runs (oldL, oldS), read on demand; their virtual jumps are regenerated from last sweep's key
-      int jrun = 0; const int nrun = nj + 1;
-      Real oldL = Le; int oldS = s0;
-      if (!first && nj > 0) {
-        const int q = min(rd, cap_c - 1);
-        oldL = rd_len[q]; oldS = rd_st[q];
+    auto emit = [&](Real L, int s, bool store) {
+      if (nout == 0) sfirst = s;
+      if (store) {
+        if (wr < cap_c && nout < PM_LOCAL_PATH_MAX) { wr_len[wr] = L; wr_st[wr] = (uint8_t)s; wr++; }
+        else errbits |= PM_DE_PATH_CAP;
       }
-      Real tot = 0; long long cp = first ? P.maps_off[eb] : 0;
-      auto next_piece = [&]() -> Real {
-        if (first) return (Real)P.maps_len[cp++];
-        if (jrun >= nrun) { errbits |= PM_DE_INCONSISTENT; return (Real)0; }
-        const Real sc = s_scale_old[oldS];
-        if (isfinite(sc) && sc > (Real)0) {
-          const Real g = AX::mul(sc, gold.gap());
+      add_dwell(s, L);
+      const Real sc = s_scale_new[s];
+      if (isfinite(sc) && sc > (Real)0) {
+        Real tot = 0;
+        for (;;) {
+          const Real g = AX::mul(sc, gnew.gap());
           const Real t2 = AX::add(tot, g);
-          if (t2 < oldL) { tot = t2; return g; }
+          if (t2 < L) { tot = t2; newm++; if (newm > 70000) break; } else break;
         }
-        const Real r = AX::sub(oldL, tot);
-        jrun++; tot = 0;
-        if (jrun < nrun) { const int q = min(rd + jrun, cap_c - 1); oldL = rd_len[q]; oldS = rd_st[q]; }
-        return r;
-      };
-
-      int cur_state = (m == 1) ? cs : ps;
-      Real cur_len = next_piece();
-      int prev = cur_state;
-      for (int p = 1; p < m; p++) {
-        int st;
-        if (p == m - 1) st = cs;
-        else {
-          const int jd = m - p - 1;  // beta_jd = Bs^jd e_cs
-          Real w[NC];
-          const Real* M = (jd < npow_s) ? (sPow + jd * n * n) : (jd < P.jcap ? P.ppow + (size_t)jd * n * n : nullptr);
-          if (M) {
-#pragma unroll
-            for (int c = 0; c < n; c++) w[c] = M[c * n + cs];
-          } else {
-#pragma unroll
-            for (int c = 0; c < n; c++) w[c] = (Real)(c == cs);
-            for (int r = 0; r < jd; r++) matvec<Real, NC, false>(sBs, n, w);
-          }
-#pragma unroll
-          for (int c = 0; c < n; c++) w[c] = sB[prev * n + c] * w[c];
-          st = categorical<Real, NC, false>(w, n, gst.next(), P.err_flag);
-        }
-        const Real len = next_piece();
-        if (full) atomicAdd(&s_cnt[prev * n + st], 1u);
-        if (st == cur_state) cur_len = cur_len + len;
-        else {
-          emit(cur_len, cur_state, true);
-          if (!full) atomicAdd(&s_cnt[cur_state * n + st], 1u);
-          cur_state = st; cur_len = len;
-        }
-        prev = st;
       }
-      if (!first && nj > 0) rd += nj + 1;
-      // a single-run path is not stored: the next sweep takes its length from the tree
-      if (nout == 0) emit(Le, cur_state, false); else emit(cur_len, cur_state, true);
-      if (newm > 65535) { errbits |= PM_DE_M_OVERFLOW; newm = 65535; }
-      if (nout > PM_LOCAL_PATH_MAX) { nout = PM_LOCAL_PATH_MAX; wr = wr0 + nout; }
-      P.meta[pe] = (uint32_t)newm | ((uint32_t)(nout - 1) << 16) | ((uint32_t)sfirst << 24);
+      newm++;
+      nout++;
+    };
+
+    // old path: runs (oldL, oldS), read on demand; their virtual jumps are regenerated from last sweep's key
+    int jrun = 0; const int nrun = nj + 1;
+    Real oldL = Le; int oldS = s0;
+    if (!first && nj > 0) {
+      const int q = min(rd, cap_c - 1);
+      oldL = rd_len[q]; oldS = rd_st[q];
     }
+    Real tot = 0; long long cp = first ? P.maps_off[eb] : 0;
+    auto next_piece = [&]() -> Real {
+      if (first) return (Real)P.maps_len[cp++];
+      if (jrun >= nrun) { errbits |= PM_DE_INCONSISTENT; return (Real)0; }
+      const Real sc = s_scale_old[oldS];
+      if (isfinite(sc) && sc > (Real)0) {
+        const Real g = AX::mul(sc, gold.gap());
+        const Real t2 = AX::add(tot, g);
+        if (t2 < oldL) { tot = t2; return g; }
+      }
+      const Real r = AX::sub(oldL, tot);
+      jrun++; tot = 0;
+      if (jrun < nrun) { const int q = min(rd + jrun, cap_c - 1); oldL = rd_len[q]; oldS = rd_st[q]; }
+      return r;
+    };
+
+    int cur_state = (m == 1) ? cs : ps;
+    Real cur_len = next_piece();
+    int prev = cur_state;
+    for (int p = 1; p < m; p++) {
+      int st;
+      if (p == m - 1) st = cs;
+      else {
+        const int jd = m - p - 1;  // beta_jd = Bs^jd e_cs
+        Real wv[NC];
+        const Real* M = (jd < npow_s) ? (sPow + jd * n * n) : (jd < P.jcap ? P.ppow + (size_t)jd * n * n : nullptr);
+        if (M) {
+#pragma unroll
+          for (int c = 0; c < n; c++) wv[c] = M[c * n + cs];
+        } else {
+#pragma unroll
+          for (int c = 0; c < n; c++) wv[c] = (Real)(c == cs);
+          for (int r = 0; r < jd; r++) matvec<Real, NC, false>(sBs, n, wv);
+        }
+#pragma unroll
+        for (int c = 0; c < n; c++) wv[c] = sB[prev * n + c] * wv[c];
+        st = categorical<Real, NC, false>(wv, n, gst.next(), P.err_flag);
+      }
+      const Real len = next_piece();
+      if (full) atomicAdd(&s_cnt[prev * n + st], 1u);
+      if (st == cur_state) cur_len = cur_len + len;
+      else {
+        emit(cur_len, cur_state, true);
+        if (!full) atomicAdd(&s_cnt[cur_state * n + st], 1u);
+        cur_state = st; cur_len = len;
+      }
+      prev = st;
+    }
+    if (!first && nj > 0) rd += nj + 1;
+    // a single-run path is not stored: the next sweep takes its length from the tree
+    if (nout == 0) emit(Le, cur_state, false); else emit(cur_len, cur_state, true);
+    if (newm > 65535) { errbits |= PM_DE_M_OVERFLOW; newm = 65535; }
+    if (nout > PM_LOCAL_PATH_MAX) { nout = PM_LOCAL_PATH_MAX; wr = wr0 + nout; }
+    P.meta[pe] = (uint32_t)newm | ((uint32_t)(nout - 1) << 16) | ((uint32_t)sfirst << 24);
   }
   if (errbits) atomicOr(P.err_flag, errbits);
 
@@ -780,17 +819,17 @@ __global__ void __launch_bounds__(128) k_paths_fast(ChainParams<Real> P, uint32_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < NR; j++) {
-      double v = Rsum[j] + (double)Racc[j];
+      double v = Rsum[j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
       if (lane == 0) s_dw[warp * n + j] = v;
     }
   }
   __syncthreads();
-  const long long blk = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+  const long long blk = (long long)gridDim.y * gridDim.x + (long long)blockIdx.y * gridDim.x + blockIdx.x;
   if ((int)threadIdx.x < n) {
     double v;
-    if (NS > 0) { v = 0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += s_dw[w * n + threadIdx.x]; }
+    if (NS > 0) { v = 0; for (int ww = 0; ww < (int)(blockDim.x >> 5); ww++) v += s_dw[ww * n + threadIdx.x]; }
     else v = s_dw[threadIdx.x];
     P.dw_partial[blk * n + threadIdx.x] = v;
   }

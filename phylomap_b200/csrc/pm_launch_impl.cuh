@@ -17,7 +17,13 @@ template <typename Real, int NS, bool EXACT>
 void Sweep<Real, NS, EXACT>::paths(const ChainParams<Real>& P, dim3 grid, size_t smem, cudaStream_t st, uint32_t iter,
                                    int first, int chunk) {
   if constexpr (EXACT) k_paths<Real, NS, true><<<grid, 128, smem, st>>>(P, iter, first, chunk);
-  else k_paths_fast<Real, NS><<<grid, 128, smem, st>>>(P, iter, first, chunk);
+  else {
+    // first sweep: every branch takes its jump points from the caller's maps -> general path only.  The easy kernel
+    // must still define this sweep's partial sums, so it runs on an empty range instead (chunk = 0 branches).
+    const size_t smem_easy = (size_t)4 * P.n * sizeof(double) + (size_t)(P.n + (P.n & 1)) * sizeof(unsigned) + (size_t)P.n * sizeof(Real);
+    if (!first) k_paths_easy<Real, NS><<<grid, 128, smem_easy, st>>>(P, iter, chunk);
+    k_paths_hard<Real, NS><<<grid, 128, smem, st>>>(P, iter, first, chunk);
+  }
 }
 
 }  // namespace pm
