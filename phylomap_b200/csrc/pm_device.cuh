@@ -71,7 +71,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
-enum SlotKind : uint32_t { K_NODE = 0, K_BRSTATE = 1, K_BREXP = 2, K_NODEGRP = 3, K_BREXP2 = 4 };
+enum SlotKind : uint32_t { K_NODE = 0, K_BRSTATE = 1, K_BREXP = 2, K_NODEGRP = 3, K_BRPAIR = 4, K_BRCNT = 5, K_BRPOS = 6, K_BRGAP = 7 };
 __device__ __forceinline__ uint32_t make_slot(uint32_t kind, uint32_t idx) { return (kind << 28) | idx; }
 
 // Description of where uniforms come from (per launch).
@@ -188,42 +188,92 @@ template <> struct ExpDev<float, false> {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Production stream of the exponential gaps of one (site, branch, sweep).  FP32: the first two uniforms come from a
-// Philox block shared by the two branches 2j, 2j+1 (words 0,1 / 2,3 of the block keyed by K_BREXP2, j), so the
-// common case — zero or one new virtual jump — costs half a Philox block per branch; further uniforms come from the
-// branch's own K_BREXP stream.  FP64: the branch's own stream from the start.
+// Production model of the virtual jumps (statistically the reference's Poisson process of rate Omega + Q_ss on every
+// run of the path, src/phylomap.cpp:391-410, drawn differently).  For a run of length L in state s,
+// lambda = (Omega + Q_ss) L:
+//   lambda <= PM_LAMBDA_INV : the NUMBER of jumps is drawn by inversion of the Poisson cdf from ONE uniform; their
+//                             positions are the order statistics of that many uniforms, generated in increasing order
+//                             (x <- x + (1 - x)(1 - u^(1/remaining))) and only when a later sweep needs them;
+//   lambda >  PM_LAMBDA_INV : exponential gaps until the run is exhausted, like the reference.
+// Everything is a pure function of (seed, site, sweep, branch, run, index) through Philox4x32-10, so the sweep that
+// consumes the jumps regenerates exactly what the sweep that counted them drew; nothing but the count is stored.
+// Word map of one (site, sweep, branch e):
+//   pair block  (K_BRPAIR, e >> 1): words 2(e&1), 2(e&1)+1 = A, B.  A: count uniform of run 0.  B: count uniform of
+//               run 1 if the path has >= 2 runs, else the uniform of the FIRST position on run 0.
+//   (K_BRCNT, e): count uniforms of runs 2, 3, ...      (K_BRPOS, e; run r): the other position uniforms of run r
+//   (K_BRGAP, e; run r): exponential gaps of run r      (K_BRSTATE, e): the state draws
+// All arithmetic that decides a count or a position is pinned to single IEEE operations so that every kernel that
+// evaluates it gets the same bits.
 // ------------------------------------------------------------------------------------------------
-template <typename Real> struct BranchGaps;
-template <> struct BranchGaps<float> {
-  uint32_t w0, w1, k;
-  StreamF rest;
-  static __device__ __forceinline__ void pair_block(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t e, uint32_t o[4]) {
-    philox4x32_10(e >> 1, make_slot(K_BREXP2, 0u), it, d.site0 + local_site, d.k0, d.k1, o);
-  }
-  __device__ __forceinline__ void open_with(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t e, const uint32_t o[4]) {
-    w0 = (e & 1u) ? o[2] : o[0]; w1 = (e & 1u) ? o[3] : o[1]; k = 0;
-    rest.open(d, local_site, it, K_BREXP, e, nullptr);
-  }
-  __device__ __forceinline__ void open(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t e, unsigned*) {
-    uint32_t o[4];
-    pair_block(d, local_site, it, e, o);
-    open_with(d, local_site, it, e, o);
-  }
-  static __device__ __forceinline__ float cvt(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
-  __device__ __forceinline__ float gap() {
-    float u;
-    if (k == 0u) u = cvt(w0); else if (k == 1u) u = cvt(w1); else u = rest.next();
+#define PM_LAMBDA_INV 16
+
+template <typename Real> struct Pin;
+template <> struct Pin<float> {
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float u01(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+  static __device__ __forceinline__ float expm(float x) { return expf(-x); }
+  static __device__ __forceinline__ float root(float u, int k) { return exp2f(__fdiv_rn(log2f(u), (float)k)); }
+  static __device__ __forceinline__ float neglog(float u) { return -logf(u); }
+};
+template <> struct Pin<double> {
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ double u01(uint32_t w) { return ((double)w + 0.5) * (1.0 / 4294967296.0); }
+  static __device__ __forceinline__ double expm(double x) { return exp(-x); }
+  static __device__ __forceinline__ double root(double u, int k) { return exp2(__ddiv_rn(log2(u), (double)k)); }
+  static __device__ __forceinline__ double neglog(double u) { return -log(u); }
+};
+
+// number of Poisson(lam) events by inversion of the cdf
+template <typename Real>
+__device__ __forceinline__ int poisson_inv(Real lam, uint32_t word) {
+  const Real u = Pin<Real>::u01(word);
+  Real p = Pin<Real>::expm(lam), c = p;
+  int k = 0;
+  while (u > c) {
     k++;
-    return -logf(u);
+    p = Pin<Real>::mul(p, Pin<Real>::div(lam, (Real)k));
+    c = Pin<Real>::add(c, p);
+    if (p < (Real)1e-12 && (Real)k > lam) break;  // cdf saturated below u (resolution of u): stop in the tail
+  }
+  return k;
+}
+
+// position of the next of `remaining` jumps that are uniform on (x, L)
+template <typename Real>
+__device__ __forceinline__ Real next_order_stat(Real x, Real L, int remaining, uint32_t word) {
+  const Real u = Pin<Real>::u01(word);
+  const Real frac = Pin<Real>::sub((Real)1, remaining == 1 ? u : Pin<Real>::root(u, remaining));
+  return Pin<Real>::add(x, Pin<Real>::mul(Pin<Real>::sub(L, x), frac));
+}
+
+// lazily evaluated sequence of Philox words: (kind, idx) stream, sub-stream `hi` (run index), word j
+struct WordStream {
+  uint32_t k0, k1, site, iter, slot, hi, j;
+  uint32_t o0, o1, o2, o3;
+  __device__ __forceinline__ void open(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t kind, uint32_t idx, uint32_t run) {
+    k0 = d.k0; k1 = d.k1; site = d.site0 + local_site; iter = it; slot = make_slot(kind, idx); hi = run << 20; j = 0;
+  }
+  __device__ __forceinline__ uint32_t next() {
+    const uint32_t q = j & 3u;
+    if (q == 0u) {
+      uint32_t o[4];
+      philox4x32_10(hi | (j >> 2), slot, iter, site, k0, k1, o);
+      o0 = o[0]; o1 = o[1]; o2 = o[2]; o3 = o[3];
+    }
+    j++;
+    return q == 0u ? o0 : q == 1u ? o1 : q == 2u ? o2 : o3;
   }
 };
-template <> struct BranchGaps<double> {
-  StreamD s;
-  __device__ __forceinline__ void open(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t e, unsigned* err) {
-    s.open(d, local_site, it, K_BREXP, e, err);
-  }
-  __device__ __forceinline__ double gap() { return -log(s.next()); }
-};
+
+__device__ __forceinline__ void pair_block(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t e, uint32_t o[4]) {
+  philox4x32_10(e >> 1, make_slot(K_BRPAIR, 0u), it, d.site0 + local_site, d.k0, d.k1, o);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Categorical draw.

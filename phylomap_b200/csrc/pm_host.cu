@@ -130,6 +130,32 @@ int poisson_cap(double lam, double eps) {
   return 1000000;
 }
 
+// c such that P( sum_e X_e >= c ) < eps for independent X_e = (N_e + 1) 1[N_e >= 2], N_e ~ Poisson(lam_e):
+// min over theta of (log(1/eps) + sum_e log E exp(theta X_e)) / theta
+long long chernoff_records_cap(const std::vector<double>& lams, double eps) {
+  double best = 1e300;
+  for (double theta : {0.25, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0}) {
+    double acc = std::log(1.0 / eps);
+    bool ok = true;
+    for (double lam : lams) {
+      // E exp(theta X) = P(N < 2) + sum_{j >= 2} exp(theta (j + 1)) P(N = j)
+      double pj = std::exp(-lam), mgf = pj;  // j = 0
+      pj *= lam; mgf += pj;                  // j = 1
+      for (int j = 2; j < 400; j++) {
+        pj *= lam / j;
+        const double term = std::exp(theta * (j + 1)) * pj;
+        mgf += term;
+        if (j > lam * std::exp(theta) + 5 && term < 1e-30 * mgf) break;
+      }
+      if (!std::isfinite(mgf)) { ok = false; break; }
+      acc += std::log(mgf);
+    }
+    if (ok) best = std::min(best, acc / theta);
+  }
+  if (!(best < 1e15)) return 1LL << 40;
+  return (long long)std::ceil(best);
+}
+
 }  // namespace
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -153,8 +179,8 @@ template <typename Real>
 struct TreeDev {
   pm::host::Schedule sch;
   long long S = 0;
-  DevBuf up_entries, up_off, down_entries, down_off, e_parent, e_child, e_len, maps_off, maps_len, cap_off;
-  DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, slow_mask;
+  DevBuf up_entries, up_off, down_entries, down_off, e_parent, e_child, e_len, maps_off, maps_len, cap_off, dfs_prog;
+  DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, slow_mask, pos1;
   int mask_words = 0;
   std::vector<int> cap_off_h;
   pm::ChainParams<Real> P;
@@ -182,7 +208,7 @@ struct ChainT : pm_chain {
   Real* model_h = nullptr;   // pinned staging: model then ppow
   double* rows_h = nullptr;  // pinned: ntrees * W
   unsigned* err_h = nullptr;
-  std::vector<double> scale_prev;
+  std::vector<double> scale_prev, rate_prev;
   pm::host::MersenneR mt{0};
   std::unique_ptr<pm::host::ReplaySource> replay;
   size_t smem_prune = 0, smem_nodes = 0, smem_paths = 0;
@@ -201,7 +227,7 @@ struct ChainT : pm_chain {
 
   pm::host::UniformSource& host_rng() { return replay ? static_cast<pm::host::UniformSource&>(*replay) : mt; }
 
-  size_t model_elems() const { return (size_t)2 * n * n + 3 * n; }
+  size_t model_elems() const { return (size_t)2 * n * n + 5 * n; }
 
   // ---- model upload: B, thresholded B, pid, scales, table of powers ----
   void stage_model(bool first) {
@@ -214,12 +240,17 @@ struct ChainT : pm_chain {
       }
     std::vector<double> scale_new(n);
     for (int s = 0; s < n; s++) scale_new[s] = 1.0 / (Omega + Q[s + (size_t)s * n]);
-    if (first) scale_prev = scale_new;
+    std::vector<double> rate_new(n);
+    for (int s = 0; s < n; s++) rate_new[s] = Omega + Q[s + (size_t)s * n];
+    if (first) { scale_prev = scale_new; rate_prev = rate_new; }
     Real* m = model_h;
     for (size_t i = 0; i < (size_t)n * n; i++) { m[i] = (Real)Bd[i]; m[(size_t)n * n + i] = (Real)Bs[i]; }
     Real* v = m + 2 * (size_t)n * n;
-    for (int s = 0; s < n; s++) { v[s] = (Real)pid[s]; v[n + s] = (Real)scale_prev[s]; v[2 * n + s] = (Real)scale_new[s]; }
-    scale_prev = scale_new;
+    for (int s = 0; s < n; s++) {
+      v[s] = (Real)pid[s]; v[n + s] = (Real)scale_prev[s]; v[2 * n + s] = (Real)scale_new[s];
+      v[3 * n + s] = (Real)rate_prev[s]; v[4 * n + s] = (Real)rate_new[s];
+    }
+    scale_prev = scale_new; rate_prev = rate_new;
     // P_0 = I, P_j = Bs P_{j-1}: left-to-right dot products in double (column c of P_j is the reference's
     // backward vector B^j e_c bit for bit, src/phylomap.cpp:283-287)
     Real* pw = m + model_elems();
@@ -242,11 +273,19 @@ struct ChainT : pm_chain {
   }
 
   // ---- kernel dispatch ----
+  // K1 geometry: the depth-first kernel (production, 2 / 4 states) runs 4 independent warps of 32 sites per block
+  bool dfs_prune() const { return !exact && (NS == 2 || NS == 4); }
+  int prune_grid(const TreeDev<Real>& t) const { return dfs_prune() ? (int)((t.S + 127) / 128) : (int)((t.S + 31) / 32); }
+  size_t prune_smem(const TreeDev<Real>& t) const {
+    if (!dfs_prune()) return smem_prune;
+    return ((size_t)PM_SMEM_POW * n * n + (size_t)4 * t.sch.dfs_depth * 32 * n) * sizeof(Real);
+  }
+
   template <int NSc, bool EX>
   void launch_sweep_t(TreeDev<Real>& t, uint32_t iter, double* row) {
     const int gx = (int)((t.S + 31) / 32);
     begin_timed(0);
-    pm::Sweep<Real, NSc, EX>::prune(t.P, gx, smem_prune, stream);
+    pm::Sweep<Real, NSc, EX>::prune(t.P, prune_grid(t), prune_smem(t), stream);
     end_timed();
     begin_timed(1);
     pm::Sweep<Real, NSc, EX>::nodes(t.P, gx, smem_nodes, stream, iter);
@@ -262,8 +301,7 @@ struct ChainT : pm_chain {
   }
   template <int NSc, bool EX>
   void launch_prune_t(TreeDev<Real>& t) {
-    const int gx = (int)((t.S + 31) / 32);
-    pm::Sweep<Real, NSc, EX>::prune(t.P, gx, smem_prune, stream);
+    pm::Sweep<Real, NSc, EX>::prune(t.P, prune_grid(t), prune_smem(t), stream);
   }
 
   template <bool EX>
@@ -413,10 +451,20 @@ struct ChainT : pm_chain {
         }
         long long cap;
         if (opt.path_capacity > 0) cap = (long long)opt.path_capacity * (b1 - b0);
-        else {
+        else if (exact) {
           const int jumps = poisson_cap(1.5 * Omega * len + 1.0, 1e-18);
-          cap = exact ? (long long)(b1 - b0) + jumps : 2LL * jumps;
-          cap = std::max(cap, init_records);
+          cap = std::max<long long>((long long)(b1 - b0) + jumps, init_records);
+        } else {
+          // production: only paths with >= 2 real jumps keep records (j + 1 of them); Chernoff bound on their sum
+          // over the chunk with every branch's jump count dominated by Poisson(1.5 Omega t)
+          std::vector<double> lams;
+          long long init3 = 0;
+          for (int e = b0; e < b1; e++) {
+            lams.push_back(1.5 * Omega * (double)elen[e]);
+            const long long m0 = moff[e + 1] - moff[e];
+            if (m0 >= 3) init3 += m0;
+          }
+          cap = std::max<long long>(chernoff_records_cap(lams, 1e-18), init3) + 4;
         }
         if (cap > (1 << 28)) fail(PM_ERR_CAPACITY, "path capacity of a branch chunk too large");
         cap = (cap + 3) & ~3;  // keep every slice 16-byte aligned
@@ -433,6 +481,8 @@ struct ChainT : pm_chain {
       upload(t->maps_off, moff, stream);
       upload(t->maps_len, mlen, stream);
       upload(t->cap_off, t->cap_off_h, stream);
+      pm::host::build_dfs_program(t->sch);
+      upload(t->dfs_prog, t->sch.dfs_prog, stream);
       t->tipcode.alloc((size_t)T * S);
       t->node_state.alloc((size_t)(2 * T - 1) * S);
       t->meta.alloc((size_t)E * S * sizeof(uint32_t));
@@ -446,9 +496,12 @@ struct ChainT : pm_chain {
       t->dw_partial.alloc((size_t)2 * t->nblocks * n * sizeof(double));
       CK(cudaMemsetAsync(t->dw_partial.p, 0, t->dw_partial.bytes, stream));
       t->mask_words = (t->chunk + 31) / 32;
-      if (!exact) t->slow_mask.alloc((size_t)ny * t->mask_words * S * sizeof(uint32_t));
+      if (!exact) {
+        t->slow_mask.alloc((size_t)ny * t->mask_words * S * sizeof(uint32_t));
+        t->pos1.alloc((size_t)E * S * sizeof(Real));
+      }
       dev_bytes += t->tipcode.bytes + t->node_state.bytes + t->meta.bytes + t->PL.bytes + 2 * (t->rec_len[0].bytes + t->rec_st[0].bytes) +
-                   t->dw_partial.bytes + t->slow_mask.bytes;
+                   t->dw_partial.bytes + t->slow_mask.bytes + t->pos1.bytes;
       trees.push_back(std::move(t));
     }
 
@@ -491,7 +544,7 @@ struct ChainT : pm_chain {
     smem_prune = ((size_t)n * n + (size_t)np_fast * n * n) * sizeof(Real);
     smem_nodes = ((size_t)n * n + 3 * n + (size_t)np_fast * n * n) * sizeof(Real);
     smem_paths = (size_t)4 * n * sizeof(double) + ((size_t)n * n + ((n * n) & 1)) * sizeof(unsigned) +
-                 ((size_t)2 * n * n + 3 * n + (size_t)np_fast * n * n) * sizeof(Real);
+                 ((size_t)2 * n * n + 5 * n + (size_t)np_fast * n * n) * sizeof(Real);
 
     for (int ti = 0; ti < ntr; ti++) {
       TreeDev<Real>& t = *trees[ti];
@@ -500,6 +553,8 @@ struct ChainT : pm_chain {
       P.n = n; P.T = T; P.E = E; P.S = t.S;
       P.cap_off = t.cap_off.template as<int>();
       P.slow_mask = t.slow_mask.template as<uint32_t>(); P.mask_words = t.mask_words;
+      P.pos1 = t.pos1.template as<Real>();
+      P.dfs_prog = t.dfs_prog.template as<int>(); P.dfs_nops = T - 1; P.dfs_depth = t.sch.dfs_depth;
       P.model = model.as<Real>(); P.ppow = ppow.as<Real>(); P.jcap = jcap;
       P.up_entries = t.up_entries.template as<int>(); P.up_off = t.up_off.template as<int>();
       P.n_up_levels = (int)t.sch.up_off.size() - 1;
@@ -677,32 +732,53 @@ struct ChainT : pm_chain {
     if (site < 0 || site >= t.S || e < 0 || e >= t.sch.E) fail(PM_ERR_ARG, "bad site / branch");
     uint32_t m = 0;
     CK(cudaMemcpy(&m, t.meta.template as<uint32_t>() + (size_t)e * t.S + site, 4, cudaMemcpyDeviceToHost));
-    const int nj = (m >> 16) & 0xff, s0 = m >> 24;
     if (iters_done == 0) fail(PM_ERR_ARG, "no sweep done yet");
-    if (!exact && nj == 0) {
-      Real L;
-      CK(cudaMemcpy(&L, t.e_len.template as<Real>() + e, sizeof(Real), cudaMemcpyDeviceToHost));
-      if (cap > 0) { len[0] = (double)L; st[0] = s0; }
-      return 1;
-    }
-    // locate the branch's records inside the (site, chunk) slice written by the last sweep
     const int c = e / t.chunk, b0 = c * t.chunk;
     const int cap_c = t.cap_off_h[c + 1] - t.cap_off_h[c];
+    const int buf = (iters_done - 1) & 1;
+    auto records = [&](long long pos, int count) {
+      const size_t base = (size_t)t.cap_off_h[c] * t.S + (size_t)site * cap_c + pos;
+      for (int k = 0; k < count && k < cap; k++) {
+        Real L; uint8_t s;
+        CK(cudaMemcpy(&L, t.rec_len[buf].template as<Real>() + base + k, sizeof(Real), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&s, t.rec_st[buf].template as<uint8_t>() + base + k, 1, cudaMemcpyDeviceToHost));
+        len[k] = (double)L; st[k] = s;
+      }
+    };
+    if (exact) {  // meta = m | nj << 16 | s0 << 24; every path keeps nj + 1 records
+      const int nj = (m >> 16) & 0xff;
+      long long pos = 0;
+      for (int e2 = b0; e2 < e; e2++) {
+        uint32_t m2 = 0;
+        CK(cudaMemcpy(&m2, t.meta.template as<uint32_t>() + (size_t)e2 * t.S + site, 4, cudaMemcpyDeviceToHost));
+        pos += ((m2 >> 16) & 0xff) + 1;
+      }
+      records(pos, nj + 1);
+      return nj + 1;
+    }
+    // production: meta = m | nj << 16 (6 bits) | s0 << 22 | s1 << 27; pos1 for nj == 1; records for nj >= 2
+    const int nj = (m >> 16) & 0x3f, s0 = (m >> 22) & 0x1f, s1 = (m >> 27) & 0x1f;
+    Real Le;
+    CK(cudaMemcpy(&Le, t.e_len.template as<Real>() + e, sizeof(Real), cudaMemcpyDeviceToHost));
+    if (nj == 0) {
+      if (cap > 0) { len[0] = (double)Le; st[0] = s0; }
+      return 1;
+    }
+    if (nj == 1) {
+      Real p1;
+      CK(cudaMemcpy(&p1, t.pos1.template as<Real>() + (size_t)e * t.S + site, sizeof(Real), cudaMemcpyDeviceToHost));
+      if (cap > 0) { len[0] = (double)p1; st[0] = s0; }
+      if (cap > 1) { len[1] = (double)(Le - p1); st[1] = s1; }
+      return 2;
+    }
     long long pos = 0;
     for (int e2 = b0; e2 < e; e2++) {
       uint32_t m2 = 0;
       CK(cudaMemcpy(&m2, t.meta.template as<uint32_t>() + (size_t)e2 * t.S + site, 4, cudaMemcpyDeviceToHost));
-      const int nj2 = (m2 >> 16) & 0xff;
-      pos += (exact || nj2 > 0) ? nj2 + 1 : 0;
+      const int nj2 = (m2 >> 16) & 0x3f;
+      if (nj2 >= 2) pos += nj2 + 1;
     }
-    const int buf = (iters_done - 1) & 1;
-    const size_t base = (size_t)t.cap_off_h[c] * t.S + (size_t)site * cap_c + pos;
-    for (int k = 0; k <= nj && k < cap; k++) {
-      Real L; uint8_t s;
-      CK(cudaMemcpy(&L, t.rec_len[buf].template as<Real>() + base + k, sizeof(Real), cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(&s, t.rec_st[buf].template as<uint8_t>() + base + k, 1, cudaMemcpyDeviceToHost));
-      len[k] = (double)L; st[k] = s;
-    }
+    records(pos, nj + 1);
     return nj + 1;
   }
   void partials(int tree, int64_t site, double* out) override {

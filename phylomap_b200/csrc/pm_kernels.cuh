@@ -30,7 +30,7 @@ struct ChainParams {
   int n, T, E;
   const int* cap_off;  // [n_chunks+1] prefix sums of the record capacities of the branch chunks (see k_paths)
   long long S;
-  const Real* model;  // [B n*n | Bs n*n | pid n | scale_old n | scale_new n], matrices row-major
+  const Real* model;  // [B n*n | Bs n*n | pid n | scale_old n | scale_new n | rate_old n | rate_new n], matrices row-major
   const Real* ppow;   // [jcap][n*n] P_j = Bs * P_{j-1}
   int jcap;
   const int* up_entries; const int* up_off; int n_up_levels;        // 5 ints per internal node: parent, a, ea, b, eb
@@ -40,6 +40,8 @@ struct ChainParams {
   int root;
   const uint8_t* tipcode; uint8_t* node_state; uint32_t* meta; Real* PL;
   uint32_t* slow_mask; int mask_words;  // production: per (chunk, word, site) bit mask of the branches left to k_paths_hard
+  const int* dfs_prog; int dfs_nops, dfs_depth;  // production K1: post-order program (pm_tree.hpp)
+  Real* pos1;  // production [E][S]: length of the first piece when m == 2 or the path has exactly one real jump
   Real* rec_len[2]; uint8_t* rec_st[2];  // double-buffered path records: written by sweep i into [i & 1], read by sweep i + 1
   int normalize, full_counts, parity_tips;
   double* dw_partial; unsigned long long* cnt; int* root_out;
@@ -220,6 +222,95 @@ __global__ void __launch_bounds__(256) k_prune_fast(ChainParams<Real> P) {
       if (two) finish(pn1, (int)(ma1 & 0xffffu) - 1, (int)(mb1 & 0xffffu) - 1, va1, vb1);
     }
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1, production arithmetic, 2 or 4 states, depth-first.  A warp owns 32 sites and evaluates the whole tree for them
+// in post-order (host-built program, pm_tree.hpp): the partial of the node just computed stays in registers for its
+// parent, the partial of a first-visited child waits on a <= log2(T)+1 deep stack in shared memory while its
+// sibling's subtree is evaluated.  Child partials are therefore never re-read from HBM — per site the kernel reads
+// the jump counts and tip states and writes every internal partial once (K2 needs them) — and there is no barrier.
+// The loads that do not depend on the recursion (jump counts, tip states) are prefetched PM_DFS_PF nodes ahead.
+// ------------------------------------------------------------------------------------------------
+#define PM_DFS_PF 8
+
+template <typename Real, int NS>
+__global__ void __launch_bounds__(128) k_prune_dfs(ChainParams<Real> P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Real* sPow = reinterpret_cast<Real*>(smem_raw);
+  const int npow_s = min(PM_SMEM_POW, P.jcap);
+  Real* sStack = sPow + PM_SMEM_POW * NS * NS;
+  for (int i = threadIdx.x; i < npow_s * NS * NS; i += blockDim.x) sPow[i] = P.ppow[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long S = P.S;
+  const long long site_raw = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 32 + lane;
+  if (site_raw - lane >= S) return;  // whole warp beyond the last site
+  const bool active = site_raw < S;
+  const long long site = active ? site_raw : S - 1;
+  const bool parity = P.parity_tips != 0;
+  const bool normalize = P.normalize != 0;
+  const int nops = P.dfs_nops;
+  const uint32_t* __restrict__ meta = P.meta + site;
+  const uint8_t* __restrict__ tip = P.tipcode + site;
+  Real* __restrict__ PLs = P.PL + site * NS;
+  const long long rowPL = S * NS;
+  const int4* __restrict__ prog = reinterpret_cast<const int4*>(P.dfs_prog);
+  Real* stack = sStack + ((size_t)warp * P.dfs_depth * 32 + lane) * NS;  // slot stride 32 * NS
+  int sp = 0;
+
+  uint32_t rma[PM_DFS_PF], rmb[PM_DFS_PF]; int rta[PM_DFS_PF], rtb[PM_DFS_PF];
+  auto issue = [&](int k, uint32_t& ma, uint32_t& mb, int& ta, int& tb) {
+    const int4 o0 = __ldg(prog + 2 * k), o1 = __ldg(prog + 2 * k + 1);  // (row, a, ea, b) (eb, flags, -, -)
+    ma = meta[(long long)o0.z * S];
+    mb = meta[(long long)o1.x * S];
+    ta = (o1.y & 1) ? (int)tip[(long long)o0.y * S] : 0;
+    tb = (o1.y & 8) ? (int)tip[(long long)o0.w * S] : 0;
+  };
+#pragma unroll
+  for (int j = 0; j < PM_DFS_PF; j++) if (j < nops) issue(j, rma[j], rmb[j], rta[j], rtb[j]);
+
+  Real acc[NS];
+#pragma unroll
+  for (int j = 0; j < NS; j++) acc[j] = 0;
+  for (int k0 = 0; k0 < nops; k0 += PM_DFS_PF) {
+#pragma unroll
+    for (int j = 0; j < PM_DFS_PF; j++) {
+      const int k = k0 + j;
+      if (k < nops) {
+        const uint32_t ma = rma[j], mb = rmb[j]; const int ta = rta[j], tb = rtb[j];
+        if (k + PM_DFS_PF < nops) issue(k + PM_DFS_PF, rma[j], rmb[j], rta[j], rtb[j]);
+        const int4 o0 = __ldg(prog + 2 * k), o1 = __ldg(prog + 2 * k + 1);
+        const int flags = o1.y;
+        Real va[NS], vb[NS];
+        if (flags & 8) tip_partial<Real, NS>(tb, NS, parity, vb);
+        else {
+#pragma unroll
+          for (int q = 0; q < NS; q++) vb[q] = acc[q];
+        }
+        if (flags & 1) tip_partial<Real, NS>(ta, NS, parity, va);
+        else if (flags & 2) {
+#pragma unroll
+          for (int q = 0; q < NS; q++) va[q] = acc[q];
+        } else {
+          sp--;
+          VecIO<Real, NS>::load(stack + (size_t)sp * 32 * NS, NS, va);
+        }
+        pow_times<Real, NS>(P, sPow, npow_s, (int)(mb & 0xffffu) - 1, vb);
+        pow_times<Real, NS>(P, sPow, npow_s, (int)(ma & 0xffffu) - 1, va);
+        Real s = 0;
+#pragma unroll
+        for (int q = 0; q < NS; q++) { acc[q] = vb[q] * va[q]; s += acc[q]; }
+        if (normalize) {
+          const Real inv = (Real)1 / s;
+#pragma unroll
+          for (int q = 0; q < NS; q++) acc[q] = fmax(acc[q] * inv, (Real)PM_PARTIAL_FLOOR);
+        }
+        if (active) VecIO<Real, NS>::store(PLs + (long long)o0.x * rowPL, NS, acc);
+        if (flags & 32) { VecIO<Real, NS>::store(stack + (size_t)sp * 32 * NS, NS, acc); sp++; }
+      }
+    }
   }
 }
 
@@ -554,27 +645,37 @@ __global__ void __launch_bounds__(128) k_paths(ChainParams<Real> P, uint32_t ite
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3, production arithmetic: two kernels.  With Omega * t ~ 0.2 most (site, branch) pairs need no resampling at
-// all — no jump point, or one virtual jump between equal end states — yet in a warp of 32 sites almost always SOME
-// lane does, so a single kernel runs the general path at a quarter of its lanes.
-//   k_paths_easy  streams over the branches of its chunk (coalesced, few registers, memory-bound): commits the easy
-//                 branches (dwell time, virtual self-jump count, number of new virtual jumps from at most two
-//                 exponential gaps) and sets a bit for every other branch in a per-(site, chunk) mask.
-//   k_paths_hard  thread = (site, chunk) again; every lane walks the set bits of ITS mask, so all lanes of a warp
-//                 are in the general path together.  Records are appended in branch order, which is the order the
-//                 next sweep reads them back in.
+// K3, production arithmetic: two kernels (virtual-jump model: see pm_device.cuh).
+//
+// State a sweep leaves per (branch, site):  meta = m (bits 0-15) | real jumps nj (16-21) | state of run 0 (22-26) |
+// state of run 1 (27-31);  pos1 = length of the first piece when m == 2 or nj == 1 (the position of the only jump point,
+// respectively of the only real jump);  paths with nj >= 2 (a fraction of a percent) keep all their runs as records.
+//
+//   k_paths_easy  every branch whose previous path has at most one jump point (m <= 2: ~98 % here).  No
+//                 regeneration and no record is needed: the pieces are (pos1, t - pos1), the new states are the two
+//                 node states, the new virtual-jump counts take one uniform per run from a Philox block shared by two
+//                 branches.  Coalesced streaming over the chunk, straight-line code; everything else gets a bit in the
+//                 per-(site, chunk) mask.
+//   k_paths_hard  thread = (site, chunk) again, every lane walks the set bits of ITS mask: regenerates the virtual jumps
+//                 of the previous sweep run by run, redraws the interior states (resamplebranchstates :264-308),
+//                 merges and counts (shortener :44-73 / shortenerbf :997-1028), draws the new counts.
 // ------------------------------------------------------------------------------------------------
+#define PM_META(m, nj, s0, s1) ((uint32_t)(m) | ((uint32_t)(nj) << 16) | ((uint32_t)(s0) << 22) | ((uint32_t)(s1) << 27))
+
+template <typename Real>
+__device__ __forceinline__ bool rate_ok(Real r) { return isfinite(r) && r > (Real)0; }
+
 template <typename Real, int NS>
 __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_t iter, int chunk) {
   constexpr int NR = NS > 0 ? NS : 1;
-  typedef BranchGaps<Real> Gaps;
-  typedef Ar<Real, true> AX;
+  typedef Pin<Real> PN;
   const int n = NS > 0 ? NS : P.n;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_dw = reinterpret_cast<double*>(smem_raw);                // [4 warps][n] (NS>0) or [n] atomics (NS==0)
-  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_dw + 4 * n);      // [n] virtual self-jumps per state
-  Real* s_scale_new = reinterpret_cast<Real*>(s_cnt + n + (n & 1));  // [n]
-  for (int i = threadIdx.x; i < n; i += blockDim.x) { s_cnt[i] = 0; s_scale_new[i] = P.model[2 * n * n + 2 * n + i]; }
+  double* s_dw = reinterpret_cast<double*>(smem_raw);              // [4 warps][n] (NS>0) or [n] atomics (NS==0)
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_dw + 4 * n);    // [n*n]
+  Real* s_rate = reinterpret_cast<Real*>(s_cnt + n * n + ((n * n) & 1));  // [n] Omega + Q_ss of this sweep
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) s_cnt[i] = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_rate[i] = P.model[2 * n * n + 4 * n + i];
   for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_dw[i] = 0.0;
   __syncthreads();
   const long long S = P.S;
@@ -584,46 +685,60 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
   const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
   const bool full = P.full_counts != 0;
   uint32_t* __restrict__ mask = P.slow_mask + (long long)blockIdx.y * P.mask_words * S + site;
+  uint32_t* __restrict__ meta = P.meta + site;
+  Real* __restrict__ pos1 = P.pos1 + site;
+  const uint8_t* __restrict__ nstate = P.node_state + site;
   Real Racc[NR]; double Rsum[NR];
 #pragma unroll
   for (int j = 0; j < NR; j++) { Racc[j] = 0; Rsum[j] = 0; }
-  uint32_t mt_n = 0; int ps_n = 0, cs_n = 0;
+  auto add_dwell = [&](int s, Real L) {
+    if (NS > 0) {
+#pragma unroll
+      for (int j = 0; j < NR; j++) Racc[j] += (s == j) ? L : (Real)0;
+    } else atomicAdd(&s_dw[s], (double)L);
+  };
+  // software prefetch of the next branch
+  uint32_t mt_n = 0; int ps_n = 0, cs_n = 0; Real p1_n = 0;
   auto fetch = [&](int e) {
-    mt_n = P.meta[(long long)e * S + site];
-    ps_n = P.node_state[(long long)__ldg(P.e_parent + e) * S + site];
-    cs_n = P.node_state[(long long)__ldg(P.e_child + e) * S + site];
+    mt_n = meta[(long long)e * S];
+    ps_n = nstate[(long long)__ldg(P.e_parent + e) * S];
+    cs_n = nstate[(long long)__ldg(P.e_child + e) * S];
+    p1_n = pos1[(long long)e * S];
   };
   if (e0 < e1) fetch(e0);
-  uint32_t pair_o[4]; int pair_id = -1;
+  uint32_t po[4] = {0, 0, 0, 0};
   uint32_t bits = 0;
   for (int e = e0; e < e1; e++) {
-    const uint32_t mt = mt_n; const int ps = ps_n, cs = cs_n;
+    const uint32_t mt = mt_n; const int ps = ps_n, cs = cs_n; const Real p1 = p1_n;
     if (e + 1 < e1) fetch(e + 1);
-    const int m = (int)(mt & 0xffffu), nj = (int)((mt >> 16) & 0xffu);
-    bool hard = !(nj == 0 && (m == 1 || (m == 2 && ps == cs)));
+    if (((e & 1) == 0) || e == e0) pair_block(P.rng, (uint32_t)site, iter, (uint32_t)e, po);
+    const uint32_t wA = (e & 1) ? po[2] : po[0], wB = (e & 1) ? po[3] : po[1];
+    const int m = (int)(mt & 0xffffu);
+    const Real Le = __ldg(P.e_len + e);
+    bool hard = m > 2;
     if (!hard) {
-      const Real L = __ldg(P.e_len + e);
-      const Real sc = s_scale_new[cs];
-      int newm = 1;
-      if (isfinite(sc) && sc > (Real)0) {
-        Gaps gnew;
-        if constexpr (std::is_same<Real, float>::value) {
-          if ((e >> 1) != pair_id) { Gaps::pair_block(P.rng, (uint32_t)site, iter, (uint32_t)e, pair_o); pair_id = e >> 1; }
-          gnew.open_with(P.rng, (uint32_t)site, iter, (uint32_t)e, pair_o);
-        } else gnew.open(P.rng, (uint32_t)site, iter, (uint32_t)e, P.err_flag);
-        const Real g0 = AX::mul(sc, gnew.gap());
-        if (g0 < L) {
-          const Real t2 = AX::add(g0, AX::mul(sc, gnew.gap()));
-          if (t2 < L) hard = true; else newm = 2;  // a third gap is rare: leave the branch to the general path
+      // pieces: (Le) or (p1, Le - p1); states ps | cs (a one-piece branch carries the child state, :460-475)
+      const bool two = (m == 2) && (ps != cs);
+      const Real L0 = two ? p1 : Le;
+      const Real L1 = PN::sub(Le, p1);
+      const int s0 = two ? ps : cs;
+      const Real r0 = s_rate[s0], r1 = s_rate[cs];
+      const Real lam0 = rate_ok(r0) ? PN::mul(r0, L0) : (Real)0;
+      const Real lam1 = (two && rate_ok(r1)) ? PN::mul(r1, L1) : (Real)0;
+      if (lam0 > (Real)PM_LAMBDA_INV || lam1 > (Real)PM_LAMBDA_INV) hard = true;
+      else {
+        const int k0 = lam0 > (Real)0 ? poisson_inv<Real>(lam0, wA) : 0;
+        const int k1 = lam1 > (Real)0 ? poisson_inv<Real>(lam1, wB) : 0;
+        if (active) {
+          if (m == 2 && (full || two)) atomicAdd(&s_cnt[ps * n + cs], 1u);
+          add_dwell(s0, L0);
+          if (two) add_dwell(cs, L1);
+          const int newm = (two ? 2 : 1) + k0 + k1;
+          // a path that ends up with a single jump point keeps that point in pos1: the real jump stays where it was;
+          // a lone new virtual jump gets its position now
+          if (!two && k0 == 1) pos1[(long long)e * S] = next_order_stat<Real>((Real)0, Le, 1, wB);
+          meta[(long long)e * S] = PM_META(newm, two ? 1 : 0, s0, cs);
         }
-      }
-      if (!hard && active) {
-        if (full && m == 2) atomicAdd(&s_cnt[cs], 1u);
-        if (NS > 0) {
-#pragma unroll
-          for (int j = 0; j < NR; j++) Racc[j] += (cs == j) ? L : (Real)0;
-        } else atomicAdd(&s_dw[cs], (double)L);
-        P.meta[(long long)e * S + site] = (uint32_t)newm | ((uint32_t)cs << 24);
       }
     }
     const int b = (e - e0) & 31;
@@ -654,32 +769,72 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
     if (NS > 0) { v = 0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += s_dw[w * n + threadIdx.x]; }
     else v = s_dw[threadIdx.x];
     P.dw_partial[blk * n + threadIdx.x] = v;
-    if (s_cnt[threadIdx.x]) atomicAdd(&P.cnt[threadIdx.x * n + threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
   }
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) if (s_cnt[i]) atomicAdd(&P.cnt[i], (unsigned long long)s_cnt[i]);
 }
+
+// The pieces of one run of the previous path, in order (regenerated, never stored).
+template <typename Real>
+struct RunPieces {
+  Real L, x, rate;
+  int left;       // count mode: jumps not yet emitted
+  bool gaps;      // lambda > PM_LAMBDA_INV
+  bool firstB;    // the first position uniform is the pair block's B word (single-run path)
+  uint32_t wB;
+  WordStream ws;  // positions (count mode) or gaps
+  __device__ __forceinline__ void begin(const RngDesc& d, uint32_t site, uint32_t it, uint32_t e, int run, Real len, Real r,
+                                       uint32_t cnt_word, bool single_run, uint32_t wordB) {
+    L = len; x = 0; rate = r; left = 0; gaps = false; firstB = single_run; wB = wordB;
+    if (!rate_ok(r)) return;
+    const Real lam = Pin<Real>::mul(r, len);
+    if (lam > (Real)PM_LAMBDA_INV) { gaps = true; ws.open(d, site, it, K_BRGAP, e, (uint32_t)run); }
+    else { left = poisson_inv<Real>(lam, cnt_word); ws.open(d, site, it, K_BRPOS, e, (uint32_t)run); }
+  }
+  // returns the next piece; `last` tells whether it closes the run
+  __device__ __forceinline__ Real next(bool& last) {
+    typedef Pin<Real> PN;
+    if (gaps) {
+      const Real g = PN::div(PN::neglog(PN::u01(ws.next())), rate);
+      const Real t2 = PN::add(x, g);
+      if (t2 < L) { x = t2; last = false; return g; }
+      last = true;
+      return PN::sub(L, x);
+    }
+    if (left > 0) {
+      uint32_t w;
+      if (firstB) { w = wB; firstB = false; } else w = ws.next();
+      const Real t2 = next_order_stat<Real>(x, L, left, w);
+      const Real piece = PN::sub(t2, x);
+      x = t2; left--; last = false;
+      return piece;
+    }
+    last = true;
+    return PN::sub(L, x);
+  }
+};
 
 template <typename Real, int NS>
 __global__ void __launch_bounds__(128) k_paths_hard(ChainParams<Real> P, uint32_t iter, int first, int chunk) {
   constexpr int NC = NS > 0 ? NS : PM_NMAX;
   constexpr int NR = NS > 0 ? NS : 1;
   typedef typename StreamSel<Real, false>::type Stream;
-  typedef BranchGaps<Real> Gaps;
-  typedef Ar<Real, true> AX;  // piece arithmetic is pinned: the regenerating sweep must reproduce it bit for bit
+  typedef Pin<Real> PN;
   const int n = NS > 0 ? NS : P.n;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_dw = reinterpret_cast<double*>(smem_raw);                 // [4 warps][n] (NS>0) or [n] atomics (NS==0)
   unsigned* s_cnt = reinterpret_cast<unsigned*>(s_dw + 4 * n);       // [n*n]
   Real* sB = reinterpret_cast<Real*>(s_cnt + n * n + ((n * n) & 1));  // dense B (forward row)
   Real* sBs = sB + n * n;
-  Real* sVec = sBs + n * n;
-  Real* sPow = sVec + 3 * n;
+  Real* sVec = sBs + n * n;  // pid | scale_old | scale_new | rate_old | rate_new
+  Real* sPow = sVec + 5 * n;
   const int npow_s = min(smem_pow_count<NS, false>(), P.jcap);
-  load_model_smem<Real>(P, n, sB, sBs, sVec, sPow, npow_s);
-  for (int i = threadIdx.x; i < n * n; i += blockDim.x) s_cnt[i] = 0;
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) { sB[i] = P.model[i]; sBs[i] = P.model[n * n + i]; s_cnt[i] = 0; }
+  for (int i = threadIdx.x; i < 5 * n; i += blockDim.x) sVec[i] = P.model[2 * n * n + i];
+  for (int i = threadIdx.x; i < npow_s * n * n; i += blockDim.x) sPow[i] = P.ppow[i];
   for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_dw[i] = 0.0;
   __syncthreads();
-  const Real* s_scale_old = sVec + n;
-  const Real* s_scale_new = sVec + 2 * n;
+  const Real* s_rate_old = sVec + 3 * n;
+  const Real* s_rate_new = sVec + 4 * n;
   const long long S = P.S;
   const long long site_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = site_raw < S;
@@ -699,7 +854,6 @@ __global__ void __launch_bounds__(128) k_paths_hard(ChainParams<Real> P, uint32_
 #pragma unroll
   for (int j = 0; j < NR; j++) Rsum[j] = 0;
   unsigned errbits = 0;
-
   auto add_dwell = [&](int s, Real L) {
     if (NS > 0) {
 #pragma unroll
@@ -721,57 +875,84 @@ __global__ void __launch_bounds__(128) k_paths_hard(ChainParams<Real> P, uint32_
 
     const long long pe = (long long)eb * S + site;
     const uint32_t mt = P.meta[pe];
-    const int m = (int)(mt & 0xffffu), nj = (int)((mt >> 16) & 0xffu), s0 = (int)(mt >> 24);
+    const int m = (int)(mt & 0xffffu);
+    const int nj = first ? 0 : (int)((mt >> 16) & 0x3fu);
     const int ps = P.node_state[(long long)__ldg(P.e_parent + eb) * S + site];
     const int cs = P.node_state[(long long)__ldg(P.e_child + eb) * S + site];
     const Real Le = __ldg(P.e_len + eb);
-    Gaps gnew; gnew.open(P.rng, (uint32_t)site, iter, (uint32_t)eb, P.err_flag);
-    Gaps gold; gold.open(P.rng, (uint32_t)site, first ? iter : iter - 1u, (uint32_t)eb, P.err_flag);
+    uint32_t po_old[4], po_new[4];
+    pair_block(P.rng, (uint32_t)site, iter, (uint32_t)eb, po_new);
+    if (!first) pair_block(P.rng, (uint32_t)site, iter - 1u, (uint32_t)eb, po_old);
+    const uint32_t oA = (eb & 1) ? po_old[2] : po_old[0], oB = (eb & 1) ? po_old[3] : po_old[1];
+    const uint32_t nA = (eb & 1) ? po_new[2] : po_new[0], nB = (eb & 1) ? po_new[3] : po_new[1];
+    WordStream cnt_old; cnt_old.open(P.rng, (uint32_t)site, first ? iter : iter - 1u, K_BRCNT, (uint32_t)eb, 0u);
+    WordStream cnt_new; cnt_new.open(P.rng, (uint32_t)site, iter, K_BRCNT, (uint32_t)eb, 0u);
     Stream gst; gst.open(P.rng, (uint32_t)site, iter, K_BRSTATE, (uint32_t)eb, P.err_flag);
-    int nout = 0, newm = 0, sfirst = 0;
-    const int wr0 = wr;
 
-    auto emit = [&](Real L, int s, bool store) {
-      if (nout == 0) sfirst = s;
-      if (store) {
-        if (wr < cap_c && nout < PM_LOCAL_PATH_MAX) { wr_len[wr] = L; wr_st[wr] = (uint8_t)s; wr++; }
-        else errbits |= PM_DE_PATH_CAP;
-      }
-      add_dwell(s, L);
-      const Real sc = s_scale_new[s];
-      if (isfinite(sc) && sc > (Real)0) {
-        Real tot = 0;
-        for (;;) {
-          const Real g = AX::mul(sc, gnew.gap());
-          const Real t2 = AX::add(tot, g);
-          if (t2 < L) { tot = t2; newm++; if (newm > 70000) break; } else break;
-        }
-      }
-      newm++;
-      nout++;
+    // ---- the previous path, run by run ----
+    const int nrun = nj + 1;
+    int jrun = 0;
+    RunPieces<Real> rp;
+    long long cp = first ? P.maps_off[eb] : 0;
+    const Real p1 = (!first && (nj == 1)) ? P.pos1[pe] : (Real)0;
+    auto open_run = [&](int r) {
+      Real len; int st;
+      if (nj == 0) { len = Le; st = (int)((mt >> 22) & 0x1fu); }
+      else if (nj == 1) { len = r == 0 ? p1 : PN::sub(Le, p1); st = (int)((mt >> (r == 0 ? 22 : 27)) & 0x1fu); }
+      else { const int q = min(rd + r, cap_c - 1); len = rd_len[q]; st = rd_st[q]; }
+      const uint32_t cw = r == 0 ? oA : r == 1 ? oB : cnt_old.next();
+      rp.begin(P.rng, (uint32_t)site, iter - 1u, (uint32_t)eb, r, len, s_rate_old[st], cw, nj == 0, oB);
     };
-
-    // old path: runs (oldL, oldS), read on demand; their virtual jumps are regenerated from last sweep's key
-    int jrun = 0; const int nrun = nj + 1;
-    Real oldL = Le; int oldS = s0;
-    if (!first && nj > 0) {
-      const int q = min(rd, cap_c - 1);
-      oldL = rd_len[q]; oldS = rd_st[q];
-    }
-    Real tot = 0; long long cp = first ? P.maps_off[eb] : 0;
+    if (!first) open_run(0);
     auto next_piece = [&]() -> Real {
       if (first) return (Real)P.maps_len[cp++];
       if (jrun >= nrun) { errbits |= PM_DE_INCONSISTENT; return (Real)0; }
-      const Real sc = s_scale_old[oldS];
-      if (isfinite(sc) && sc > (Real)0) {
-        const Real g = AX::mul(sc, gold.gap());
-        const Real t2 = AX::add(tot, g);
-        if (t2 < oldL) { tot = t2; return g; }
+      bool last;
+      const Real piece = rp.next(last);
+      if (last) { jrun++; if (jrun < nrun) open_run(jrun); }
+      return piece;
+    };
+
+    // ---- the new path ----
+    // Runs are emitted in order; the first two are held in registers until a third one shows up (a path with at most
+    // one real jump lives in meta + pos1, only longer ones go to the record slice).
+    int nout = 0, newm = 0, S0 = 0, S1 = 0, k0 = 0;
+    Real L0 = 0, L1 = 0, gap0 = 0;
+    bool gaps0 = false;
+    auto put = [&](Real L, int s) {
+      if (wr < cap_c) { wr_len[wr] = L; wr_st[wr] = (uint8_t)s; wr++; } else errbits |= PM_DE_PATH_CAP;
+    };
+    auto emit = [&](Real L, int s) {
+      const int r = nout;
+      if (r == 0) { L0 = L; S0 = s; }
+      else if (r == 1) { L1 = L; S1 = s; }
+      else {
+        if (r == 2) { put(L0, S0); put(L1, S1); }
+        put(L, s);
       }
-      const Real r = AX::sub(oldL, tot);
-      jrun++; tot = 0;
-      if (jrun < nrun) { const int q = min(rd + jrun, cap_c - 1); oldL = rd_len[q]; oldS = rd_st[q]; }
-      return r;
+      add_dwell(s, L);
+      const Real rate = s_rate_new[s];
+      int k = 0;
+      if (rate_ok(rate)) {
+        const Real lam = PN::mul(rate, L);
+        if (lam > (Real)PM_LAMBDA_INV) {
+          WordStream g; g.open(P.rng, (uint32_t)site, iter, K_BRGAP, (uint32_t)eb, (uint32_t)r);
+          Real x = 0;
+          for (;;) {
+            const Real gp = PN::div(PN::neglog(PN::u01(g.next())), rate);
+            const Real t2 = PN::add(x, gp);
+            if (!(t2 < L) || k > 70000) break;
+            x = t2; k++;
+            if (r == 0 && k == 1) gap0 = gp;
+          }
+          if (r == 0) gaps0 = true;
+        } else {
+          k = poisson_inv<Real>(lam, r == 0 ? nA : r == 1 ? nB : cnt_new.next());
+        }
+      }
+      if (r == 0) k0 = k;
+      newm += k + 1;
+      nout++;
     };
 
     int cur_state = (m == 1) ? cs : ps;
@@ -800,18 +981,23 @@ __global__ void __launch_bounds__(128) k_paths_hard(ChainParams<Real> P, uint32_
       if (full) atomicAdd(&s_cnt[prev * n + st], 1u);
       if (st == cur_state) cur_len = cur_len + len;
       else {
-        emit(cur_len, cur_state, true);
+        emit(cur_len, cur_state);
         if (!full) atomicAdd(&s_cnt[cur_state * n + st], 1u);
         cur_state = st; cur_len = len;
       }
       prev = st;
     }
-    if (!first && nj > 0) rd += nj + 1;
-    // a single-run path is not stored: the next sweep takes its length from the tree
-    if (nout == 0) emit(Le, cur_state, false); else emit(cur_len, cur_state, true);
+    if (!first && (jrun != nrun)) errbits |= PM_DE_INCONSISTENT;  // the regenerated pieces must add up to m
+    if (!first && nj >= 2) rd += nj + 1;
+    // a single-run path spans the whole branch: take its length from the tree, not from the sum of its pieces
+    // ... and the second run of a two-run path is what is left after the first (the form the next sweep rebuilds it in)
+    emit(nout == 0 ? Le : nout == 1 ? PN::sub(Le, L0) : cur_len, cur_state);
     if (newm > 65535) { errbits |= PM_DE_M_OVERFLOW; newm = 65535; }
-    if (nout > PM_LOCAL_PATH_MAX) { nout = PM_LOCAL_PATH_MAX; wr = wr0 + nout; }
-    P.meta[pe] = (uint32_t)newm | ((uint32_t)(nout - 1) << 16) | ((uint32_t)sfirst << 24);
+    if (nout > 63) { errbits |= PM_DE_PATH_CAP; nout = 63; }
+    if (nout == 1) {
+      if (k0 == 1) P.pos1[pe] = gaps0 ? gap0 : next_order_stat<Real>((Real)0, Le, 1, nB);
+    } else if (nout == 2) P.pos1[pe] = L0;
+    P.meta[pe] = PM_META(newm, nout - 1, S0, S1);
   }
   if (errbits) atomicOr(P.err_flag, errbits);
 

@@ -5,7 +5,7 @@ namespace pm {
 
 template <typename Real, int NS, bool EXACT>
 void Sweep<Real, NS, EXACT>::prune(const ChainParams<Real>& P, int grid, size_t smem, cudaStream_t st) {
-  if constexpr (!EXACT && (NS == 2 || NS == 4)) k_prune_fast<Real, NS><<<grid, 256, smem, st>>>(P);
+  if constexpr (!EXACT && (NS == 2 || NS == 4)) k_prune_dfs<Real, NS><<<grid, 128, smem, st>>>(P);
   else k_prune<Real, NS, EXACT><<<grid, 256, smem, st>>>(P);
 }
 template <typename Real, int NS, bool EXACT>
@@ -20,7 +20,7 @@ void Sweep<Real, NS, EXACT>::paths(const ChainParams<Real>& P, dim3 grid, size_t
   else {
     // first sweep: every branch takes its jump points from the caller's maps -> general path only.  The easy kernel
     // must still define this sweep's partial sums, so it runs on an empty range instead (chunk = 0 branches).
-    const size_t smem_easy = (size_t)4 * P.n * sizeof(double) + (size_t)(P.n + (P.n & 1)) * sizeof(unsigned) + (size_t)P.n * sizeof(Real);
+    const size_t smem_easy = (size_t)4 * P.n * sizeof(double) + (size_t)(P.n * P.n + ((P.n * P.n) & 1)) * sizeof(unsigned) + (size_t)P.n * sizeof(Real);
     if (!first) k_paths_easy<Real, NS><<<grid, 128, smem_easy, st>>>(P, iter, chunk);
     k_paths_hard<Real, NS><<<grid, 128, smem, st>>>(P, iter, first, chunk);
   }
