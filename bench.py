@@ -169,6 +169,9 @@ def run_ours(a, rank, local_rank, world):
     stream = torch.cuda.Stream()
     opts = dict(precision="f32", mode="production", seed=2026, device=local_rank, site_offset=rank * S,
                 stream=stream.cuda_stream)
+    if world > 1:  # the one collective of the path: sum of the statistics rows (here once per pm_chain_run, fixed Q)
+        from phylomap_b200 import dist as pdist
+        opts["allreduce"] = pdist.allreduce_callback(stream.cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -200,7 +203,7 @@ def run_ours(a, rank, local_rank, world):
 
     # sanity: total dwell time per sweep == sites x tree length
     tot = rows[:, :4].sum(1)
-    expect = S * tree.edge_length.sum()
+    expect = S * world * tree.edge_length.sum()
     if not np.allclose(tot, expect, rtol=1e-3):
         raise SystemExit("bench sanity check failed: dwell %r vs %r" % (tot[:3], expect))
 
@@ -228,8 +231,9 @@ def run_ours(a, rank, local_rank, world):
     barrier()
     out = np.zeros((a.steps, 16), order="F")
     t0 = time.perf_counter()
+    e2e_opts = dict(opts)  # same stream: the all-reduce callback must be ordered after the sweeps
     res = pb.maketreelistMCMC_bigtree(z, Q.copy(), pid, np.asfortranarray(np.eye(4) + Q / OMEGA), OMEGA, *order[0], a.steps,
-                                      **{k: v for k, v in opts.items() if k != "stream"})
+                                      **e2e_opts)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     del out

@@ -214,7 +214,7 @@ template <> struct Pin<float> {
   static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
   static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
   static __device__ __forceinline__ float u01(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }
-  static __device__ __forceinline__ float expm(float x) { return expf(-x); }
+  static __device__ __forceinline__ float expm(float x) { return __expf(-x); }  // ex2.approx: same bits everywhere
   static __device__ __forceinline__ float root(float u, int k) { return exp2f(__fdiv_rn(log2f(u), (float)k)); }
   static __device__ __forceinline__ float neglog(float u) { return -logf(u); }
 };
@@ -229,15 +229,24 @@ template <> struct Pin<double> {
   static __device__ __forceinline__ double neglog(double u) { return -log(u); }
 };
 
-// number of Poisson(lam) events by inversion of the cdf
+// number of Poisson(lam) events by inversion of the cdf.  p_k = p_{k-1} * lam * (1/k) with the reciprocal from a
+// table (one rounding per multiply, the same in every kernel), so the loop body is two multiplies and an add.
+__constant__ float pm_recip[65] = {
+    0.f, 1.f, 1.f / 2, 1.f / 3, 1.f / 4, 1.f / 5, 1.f / 6, 1.f / 7, 1.f / 8, 1.f / 9, 1.f / 10, 1.f / 11, 1.f / 12, 1.f / 13,
+    1.f / 14, 1.f / 15, 1.f / 16, 1.f / 17, 1.f / 18, 1.f / 19, 1.f / 20, 1.f / 21, 1.f / 22, 1.f / 23, 1.f / 24, 1.f / 25,
+    1.f / 26, 1.f / 27, 1.f / 28, 1.f / 29, 1.f / 30, 1.f / 31, 1.f / 32, 1.f / 33, 1.f / 34, 1.f / 35, 1.f / 36, 1.f / 37,
+    1.f / 38, 1.f / 39, 1.f / 40, 1.f / 41, 1.f / 42, 1.f / 43, 1.f / 44, 1.f / 45, 1.f / 46, 1.f / 47, 1.f / 48, 1.f / 49,
+    1.f / 50, 1.f / 51, 1.f / 52, 1.f / 53, 1.f / 54, 1.f / 55, 1.f / 56, 1.f / 57, 1.f / 58, 1.f / 59, 1.f / 60, 1.f / 61,
+    1.f / 62, 1.f / 63, 1.f / 64};
+
 template <typename Real>
 __device__ __forceinline__ int poisson_inv(Real lam, uint32_t word) {
   const Real u = Pin<Real>::u01(word);
   Real p = Pin<Real>::expm(lam), c = p;
   int k = 0;
-  while (u > c) {
+  while (u > c && k < 64) {
     k++;
-    p = Pin<Real>::mul(p, Pin<Real>::div(lam, (Real)k));
+    p = Pin<Real>::mul(Pin<Real>::mul(p, lam), (Real)pm_recip[k]);
     c = Pin<Real>::add(c, p);
     if (p < (Real)1e-12 && (Real)k > lam) break;  // cdf saturated below u (resolution of u): stop in the tail
   }

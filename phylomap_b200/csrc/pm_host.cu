@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -179,7 +180,7 @@ template <typename Real>
 struct TreeDev {
   pm::host::Schedule sch;
   long long S = 0;
-  DevBuf up_entries, up_off, down_entries, down_off, e_parent, e_child, e_len, maps_off, maps_len, cap_off, dfs_prog;
+  DevBuf up_entries8, up_entries, up_off, down_entries, down_off, e_parent, e_child, e_len, maps_off, maps_len, cap_off;
   DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, slow_mask, pos1;
   int mask_words = 0;
   std::vector<int> cap_off_h;
@@ -213,6 +214,7 @@ struct ChainT : pm_chain {
   std::unique_ptr<pm::host::ReplaySource> replay;
   size_t smem_prune = 0, smem_nodes = 0, smem_paths = 0;
   int rows_cap = 0;
+  int k1_variant = 21;  // production pruning kernel variant (pm_launch_impl.cuh; PHYLOMAP_B200_K1_UNROLL overrides, for tuning)
   struct Timed { cudaEvent_t a, b; int k; };
   std::vector<Timed> timed;
 
@@ -273,19 +275,14 @@ struct ChainT : pm_chain {
   }
 
   // ---- kernel dispatch ----
-  // K1 geometry: the depth-first kernel (production, 2 / 4 states) runs 4 independent warps of 32 sites per block
-  bool dfs_prune() const { return !exact && (NS == 2 || NS == 4); }
-  int prune_grid(const TreeDev<Real>& t) const { return dfs_prune() ? (int)((t.S + 127) / 128) : (int)((t.S + 31) / 32); }
-  size_t prune_smem(const TreeDev<Real>& t) const {
-    if (!dfs_prune()) return smem_prune;
-    return ((size_t)PM_SMEM_POW * n * n + (size_t)4 * t.sch.dfs_depth * 32 * n) * sizeof(Real);
-  }
+  int prune_grid(const TreeDev<Real>& t) const { return (int)((t.S + 31) / 32); }
+  size_t prune_smem(const TreeDev<Real>&) const { return smem_prune; }
 
   template <int NSc, bool EX>
   void launch_sweep_t(TreeDev<Real>& t, uint32_t iter, double* row) {
     const int gx = (int)((t.S + 31) / 32);
     begin_timed(0);
-    pm::Sweep<Real, NSc, EX>::prune(t.P, prune_grid(t), prune_smem(t), stream);
+    pm::Sweep<Real, NSc, EX>::prune(t.P, prune_grid(t), prune_smem(t), stream, k1_variant);
     end_timed();
     begin_timed(1);
     pm::Sweep<Real, NSc, EX>::nodes(t.P, gx, smem_nodes, stream, iter);
@@ -301,7 +298,7 @@ struct ChainT : pm_chain {
   }
   template <int NSc, bool EX>
   void launch_prune_t(TreeDev<Real>& t) {
-    pm::Sweep<Real, NSc, EX>::prune(t.P, prune_grid(t), prune_smem(t), stream);
+    pm::Sweep<Real, NSc, EX>::prune(t.P, prune_grid(t), prune_smem(t), stream, k1_variant);
   }
 
   template <bool EX>
@@ -431,6 +428,7 @@ struct ChainT : pm_chain {
       long long ny = (148LL * 16 * 6 + gx - 1) / gx;
       ny = std::max(1LL, std::min<long long>(ny, (E + 15) / 16));
       ny = std::min<long long>(ny, 65535);
+      ny = std::max<long long>(ny, (E + 2047) / 2048);  // the easy path kernel stages a chunk's topology in shared memory
       t->chunk = (int)((E + ny - 1) / ny);
       ny = (E + t->chunk - 1) / t->chunk;
       t->paths_grid = dim3((unsigned)gx, (unsigned)ny, 1);
@@ -472,6 +470,11 @@ struct ChainT : pm_chain {
       }
       const long long R = t->cap_off_h[ny];
       upload(t->up_entries, t->sch.up_entries, stream);
+      {
+        std::vector<int> e8((size_t)8 * (T - 1), 0);
+        for (int i = 0; i < T - 1; i++) for (int j = 0; j < 5; j++) e8[(size_t)8 * i + j] = t->sch.up_entries[(size_t)5 * i + j];
+        upload(t->up_entries8, e8, stream);
+      }
       upload(t->up_off, t->sch.up_off, stream);
       upload(t->down_entries, t->sch.down_entries, stream);
       upload(t->down_off, t->sch.down_off, stream);
@@ -481,8 +484,6 @@ struct ChainT : pm_chain {
       upload(t->maps_off, moff, stream);
       upload(t->maps_len, mlen, stream);
       upload(t->cap_off, t->cap_off_h, stream);
-      pm::host::build_dfs_program(t->sch);
-      upload(t->dfs_prog, t->sch.dfs_prog, stream);
       t->tipcode.alloc((size_t)T * S);
       t->node_state.alloc((size_t)(2 * T - 1) * S);
       t->meta.alloc((size_t)E * S * sizeof(uint32_t));
@@ -538,6 +539,7 @@ struct ChainT : pm_chain {
       if (opt.host_tab) replay.reset(new pm::host::ReplaySource(opt.host_tab, opt.host_tab_n));
     }
     mt.reseed((uint32_t)opt.seed);
+    if (const char* v = getenv("PHYLOMAP_B200_K1_UNROLL")) k1_variant = atoi(v);
 
     // shared-memory sizes
     const int np_fast = exact ? 0 : ((NS == 2 || NS == 4) ? std::min(PM_SMEM_POW, jcap) : 0);
@@ -554,9 +556,9 @@ struct ChainT : pm_chain {
       P.cap_off = t.cap_off.template as<int>();
       P.slow_mask = t.slow_mask.template as<uint32_t>(); P.mask_words = t.mask_words;
       P.pos1 = t.pos1.template as<Real>();
-      P.dfs_prog = t.dfs_prog.template as<int>(); P.dfs_nops = T - 1; P.dfs_depth = t.sch.dfs_depth;
       P.model = model.as<Real>(); P.ppow = ppow.as<Real>(); P.jcap = jcap;
       P.up_entries = t.up_entries.template as<int>(); P.up_off = t.up_off.template as<int>();
+      P.up_entries8 = t.up_entries8.template as<int>();
       P.n_up_levels = (int)t.sch.up_off.size() - 1;
       P.down_entries = t.down_entries.template as<int>(); P.down_off = t.down_off.template as<int>();
       P.n_down_levels = (int)t.sch.down_off.size() - 1;

@@ -34,13 +34,13 @@ struct ChainParams {
   const Real* ppow;   // [jcap][n*n] P_j = Bs * P_{j-1}
   int jcap;
   const int* up_entries; const int* up_off; int n_up_levels;        // 5 ints per internal node: parent, a, ea, b, eb
+  const int* up_entries8;  // the same entries padded to 8 ints (two 16-byte loads)
   const int* down_entries; const int* down_off; int n_down_levels;  // 3 ints per drawn node: v, parent, edge
   const int* e_parent; const int* e_child; const Real* e_len;
   const long long* maps_off; const double* maps_len;
   int root;
   const uint8_t* tipcode; uint8_t* node_state; uint32_t* meta; Real* PL;
   uint32_t* slow_mask; int mask_words;  // production: per (chunk, word, site) bit mask of the branches left to k_paths_hard
-  const int* dfs_prog; int dfs_nops, dfs_depth;  // production K1: post-order program (pm_tree.hpp)
   Real* pos1;  // production [E][S]: length of the first piece when m == 2 or the path has exactly one real jump
   Real* rec_len[2]; uint8_t* rec_st[2];  // double-buffered path records: written by sweep i into [i & 1], read by sweep i + 1
   int normalize, full_counts, parity_tips;
@@ -165,7 +165,7 @@ __device__ __forceinline__ void pow_times(const ChainParams<Real>& P, const Real
   }
 }
 
-template <typename Real, int NS>
+template <typename Real, int NS, int U>
 __global__ void __launch_bounds__(256) k_prune_fast(ChainParams<Real> P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Real* sBs = reinterpret_cast<Real*>(smem_raw);
@@ -186,131 +186,219 @@ __global__ void __launch_bounds__(256) k_prune_fast(ChainParams<Real> P) {
   Real* __restrict__ PLs = P.PL + site * NS;
   const long long rowPL = S * NS;
 
-  auto load_child = [&](int c, Real* v) {
-    if (c < T) tip_partial<Real, NS>(tip[(long long)c * S], NS, parity, v);
-    else VecIO<Real, NS>::load(PLs + (long long)(c - T) * rowPL, NS, v);
-  };
-  auto finish = [&](int pn, int ka, int kb, Real* va, Real* vb) {
-    pow_times<Real, NS>(P, sPow, npow_s, kb, vb);
-    pow_times<Real, NS>(P, sPow, npow_s, ka, va);
-    Real out[NS];
-    Real s = 0;
-#pragma unroll
-    for (int j = 0; j < NS; j++) { out[j] = vb[j] * va[j]; s += out[j]; }
-    if (normalize) {
-      const Real inv = (Real)1 / s;
-#pragma unroll
-      for (int j = 0; j < NS; j++) out[j] = fmax(out[j] * inv, (Real)PM_PARTIAL_FLOOR);
-    }
-    if (active) VecIO<Real, NS>::store(PLs + (long long)(pn - T) * rowPL, NS, out);
-  };
-
   for (int l = 0; l < P.n_up_levels; l++) {
     const int beg = __ldg(P.up_off + l), end = __ldg(P.up_off + l + 1);
-    for (int idx = beg + warp; idx < end; idx += 2 * nw) {
-      const bool two = idx + nw < end;  // warp-uniform
-      const int* en0 = P.up_entries + 5 * idx;
-      const int* en1 = P.up_entries + 5 * (two ? idx + nw : idx);
-      const int pn0 = __ldg(en0), a0 = __ldg(en0 + 1), ea0 = __ldg(en0 + 2), b0 = __ldg(en0 + 3), eb0 = __ldg(en0 + 4);
-      const int pn1 = __ldg(en1), a1 = __ldg(en1 + 1), ea1 = __ldg(en1 + 2), b1 = __ldg(en1 + 3), eb1 = __ldg(en1 + 4);
-      const uint32_t ma0 = meta[(long long)ea0 * S], mb0 = meta[(long long)eb0 * S];
-      const uint32_t ma1 = meta[(long long)ea1 * S], mb1 = meta[(long long)eb1 * S];
-      Real va0[NS], vb0[NS], va1[NS], vb1[NS];
-      load_child(a0, va0); load_child(b0, vb0);
-      load_child(a1, va1); load_child(b1, vb1);
-      finish(pn0, (int)(ma0 & 0xffffu) - 1, (int)(mb0 & 0xffffu) - 1, va0, vb0);
-      if (two) finish(pn1, (int)(ma1 & 0xffffu) - 1, (int)(mb1 & 0xffffu) - 1, va1, vb1);
+    for (int idx = beg + warp; idx < end; idx += U * nw) {
+      // U nodes of the level in flight per warp: issue every load first, then do the arithmetic
+      int pn[U]; uint32_t ma[U], mb[U]; Real va[U][NS], vb[U][NS];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int id = min(idx + u * nw, end - 1);
+        const int* en = P.up_entries + 5 * id;
+        pn[u] = __ldg(en);
+        const int a = __ldg(en + 1), ea = __ldg(en + 2), b = __ldg(en + 3), eb = __ldg(en + 4);
+        ma[u] = meta[(long long)ea * S];
+        mb[u] = meta[(long long)eb * S];
+        if (a < T) tip_partial<Real, NS>(tip[(long long)a * S], NS, parity, va[u]);
+        else VecIO<Real, NS>::load(PLs + (long long)(a - T) * rowPL, NS, va[u]);
+        if (b < T) tip_partial<Real, NS>(tip[(long long)b * S], NS, parity, vb[u]);
+        else VecIO<Real, NS>::load(PLs + (long long)(b - T) * rowPL, NS, vb[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (idx + u * nw < end) {  // warp-uniform
+          pow_times<Real, NS>(P, sPow, npow_s, (int)(mb[u] & 0xffffu) - 1, vb[u]);
+          pow_times<Real, NS>(P, sPow, npow_s, (int)(ma[u] & 0xffffu) - 1, va[u]);
+          Real out[NS];
+          Real s = 0;
+#pragma unroll
+          for (int j = 0; j < NS; j++) { out[j] = vb[u][j] * va[u][j]; s += out[j]; }
+          if (normalize) {
+            const Real inv = (Real)1 / s;
+#pragma unroll
+            for (int j = 0; j < NS; j++) out[j] = fmax(out[j] * inv, (Real)PM_PARTIAL_FLOOR);
+          }
+          if (active) VecIO<Real, NS>::store(PLs + (long long)(pn[u] - T) * rowPL, NS, out);
+        }
+      }
     }
     __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1, production arithmetic, 2 or 4 states, depth-first.  A warp owns 32 sites and evaluates the whole tree for them
-// in post-order (host-built program, pm_tree.hpp): the partial of the node just computed stays in registers for its
-// parent, the partial of a first-visited child waits on a <= log2(T)+1 deep stack in shared memory while its
-// sibling's subtree is evaluated.  Child partials are therefore never re-read from HBM — per site the kernel reads
-// the jump counts and tip states and writes every internal partial once (K2 needs them) — and there is no barrier.
-// The loads that do not depend on the recursion (jump counts, tip states) are prefetched PM_DFS_PF nodes ahead.
+// K1, production arithmetic, warp-per-tile variant.  Each warp owns 32 sites and walks ALL nodes in level order on
+// its own: a node only ever reads partials the same warp wrote earlier, so no barrier is needed, and the U nodes
+// of a round (always inside one level, hence independent) give each lane 2U partial loads + 2U jump-count loads in
+// flight.  The 4 warps of a block (and the other blocks of the SM) walk the same node list at about the same pace, so
+// a node's row is touched as one multi-KB contiguous burst, and the schedule entries stay in L1.
 // ------------------------------------------------------------------------------------------------
-#define PM_DFS_PF 8
-
-template <typename Real, int NS>
-__global__ void __launch_bounds__(128) k_prune_dfs(ChainParams<Real> P) {
+template <typename Real, int NS, int U>
+__global__ void __launch_bounds__(128, 7) k_prune_tile(ChainParams<Real> P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Real* sPow = reinterpret_cast<Real*>(smem_raw);
+  Real* sBs = reinterpret_cast<Real*>(smem_raw);
+  Real* sPow = sBs + NS * NS;
   const int npow_s = min(PM_SMEM_POW, P.jcap);
-  Real* sStack = sPow + PM_SMEM_POW * NS * NS;
-  for (int i = threadIdx.x; i < npow_s * NS * NS; i += blockDim.x) sPow[i] = P.ppow[i];
+  load_model_smem<Real>(P, NS, nullptr, sBs, nullptr, sPow, npow_s);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long S = P.S;
-  const long long site_raw = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 32 + lane;
-  if (site_raw - lane >= S) return;  // whole warp beyond the last site
+  const long long tile0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+  if (tile0 >= S) return;
+  const bool active = tile0 + lane < S;
+  const long long site = active ? tile0 + lane : S - 1;
+  const bool parity = P.parity_tips != 0;
+  const bool normalize = P.normalize != 0;
+  const int T = P.T;
+  const uint32_t* __restrict__ meta = P.meta + site;
+  const uint8_t* __restrict__ tip = P.tipcode + site;
+  Real* PLs = P.PL + site * NS;
+  const long long rowPL = S * NS;
+
+  for (int l = 0; l < P.n_up_levels; l++) {
+    const int beg = __ldg(P.up_off + l), end = __ldg(P.up_off + l + 1);
+    for (int idx = beg; idx < end; idx += U) {
+      int pn[U]; uint32_t ma[U], mb[U]; Real va[U][NS], vb[U][NS];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (idx + u < end) {  // warp-uniform
+          const int* en = P.up_entries + 5 * (idx + u);
+          pn[u] = __ldg(en);
+          const int a = __ldg(en + 1), ea = __ldg(en + 2), b = __ldg(en + 3), eb = __ldg(en + 4);
+          ma[u] = meta[(long long)ea * S];
+          mb[u] = meta[(long long)eb * S];
+          if (a < T) tip_partial<Real, NS>(tip[(long long)a * S], NS, parity, va[u]);
+          else VecIO<Real, NS>::load(PLs + (long long)(a - T) * rowPL, NS, va[u]);
+          if (b < T) tip_partial<Real, NS>(tip[(long long)b * S], NS, parity, vb[u]);
+          else VecIO<Real, NS>::load(PLs + (long long)(b - T) * rowPL, NS, vb[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (idx + u < end) {
+          pow_times<Real, NS>(P, sPow, npow_s, (int)(mb[u] & 0xffffu) - 1, vb[u]);
+          pow_times<Real, NS>(P, sPow, npow_s, (int)(ma[u] & 0xffffu) - 1, va[u]);
+          Real out[NS];
+          Real s = 0;
+#pragma unroll
+          for (int j = 0; j < NS; j++) { out[j] = vb[u][j] * va[u][j]; s += out[j]; }
+          if (normalize) {
+            const Real inv = (Real)1 / s;
+#pragma unroll
+            for (int j = 0; j < NS; j++) out[j] = fmax(out[j] * inv, (Real)PM_PARTIAL_FLOOR);
+          }
+          if (active) VecIO<Real, NS>::store(PLs + (long long)(pn[u] - T) * rowPL, NS, out);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1, production arithmetic, software-pipelined.  k_prune_fast spends about as long issuing the arithmetic of a
+// round as it waits for the round's loads, one after the other, so neither the issue slots nor HBM are busy more
+// than ~45 % of the time (ncu, profiles/).  Here the loads of the NEXT round of the level are issued before the
+// arithmetic of the current one (two register buffers, ping-pong), and the arithmetic is shorter: a tip child
+// contributes a COLUMN of P_k, read as one vector from a transposed copy of the table, instead of a mat-vec with a
+// one-hot vector; schedule entries are two vector loads; the normalisation uses the hardware reciprocal.
+// ------------------------------------------------------------------------------------------------
+template <typename Real> __device__ __forceinline__ Real fast_rcp(Real x) { return (Real)1 / x; }
+template <> __device__ __forceinline__ float fast_rcp<float>(float x) { return __frcp_rn(x); }
+
+template <typename Real, int NS>
+struct PruneNode {  // one node of a round: what was loaded for it
+  int pn; uint32_t ma, mb;
+  int ca, cb;        // tip codes (or -1 for an internal child)
+  Real va[NS], vb[NS];
+};
+
+template <typename Real, int NS, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_prune_pipe(ChainParams<Real> P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Real* sPow = reinterpret_cast<Real*>(smem_raw);            // [PM_SMEM_POW][NS*NS]  P_k, row-major
+  Real* sPowT = sPow + PM_SMEM_POW * NS * NS;                // [PM_SMEM_POW][NS*NS]  P_k transposed
+  const int npow_s = min(PM_SMEM_POW, P.jcap);
+  for (int i = threadIdx.x; i < npow_s * NS * NS; i += blockDim.x) {
+    const Real v = P.ppow[i];
+    sPow[i] = v;
+    const int k = i / (NS * NS), r = (i / NS) % NS, c = i % NS;
+    sPowT[k * NS * NS + c * NS + r] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long S = P.S;
+  const long long site_raw = (long long)blockIdx.x * 32 + lane;
   const bool active = site_raw < S;
   const long long site = active ? site_raw : S - 1;
   const bool parity = P.parity_tips != 0;
   const bool normalize = P.normalize != 0;
-  const int nops = P.dfs_nops;
+  const int T = P.T;
   const uint32_t* __restrict__ meta = P.meta + site;
   const uint8_t* __restrict__ tip = P.tipcode + site;
-  Real* __restrict__ PLs = P.PL + site * NS;
+  Real* PLs = P.PL + site * NS;
   const long long rowPL = S * NS;
-  const int4* __restrict__ prog = reinterpret_cast<const int4*>(P.dfs_prog);
-  Real* stack = sStack + ((size_t)warp * P.dfs_depth * 32 + lane) * NS;  // slot stride 32 * NS
-  int sp = 0;
+  const int4* __restrict__ ent = reinterpret_cast<const int4*>(P.up_entries8);  // (pn, a, ea, b) (eb, -, -, -)
 
-  uint32_t rma[PM_DFS_PF], rmb[PM_DFS_PF]; int rta[PM_DFS_PF], rtb[PM_DFS_PF];
-  auto issue = [&](int k, uint32_t& ma, uint32_t& mb, int& ta, int& tb) {
-    const int4 o0 = __ldg(prog + 2 * k), o1 = __ldg(prog + 2 * k + 1);  // (row, a, ea, b) (eb, flags, -, -)
-    ma = meta[(long long)o0.z * S];
-    mb = meta[(long long)o1.x * S];
-    ta = (o1.y & 1) ? (int)tip[(long long)o0.y * S] : 0;
-    tb = (o1.y & 8) ? (int)tip[(long long)o0.w * S] : 0;
+  auto load = [&](PruneNode<Real, NS>* nd, int idx, int end) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int id = min(idx + u * nw, end - 1);
+      const int4 e0 = __ldg(ent + 2 * id), e1 = __ldg(ent + 2 * id + 1);
+      nd[u].pn = e0.x;
+      nd[u].ma = meta[(long long)e0.z * S];
+      nd[u].mb = meta[(long long)e1.x * S];
+      nd[u].ca = -1; nd[u].cb = -1;
+      if (e0.y < T) nd[u].ca = tip[(long long)e0.y * S];
+      else VecIO<Real, NS>::load(PLs + (long long)(e0.y - T) * rowPL, NS, nd[u].va);
+      if (e0.w < T) nd[u].cb = tip[(long long)e0.w * S];
+      else VecIO<Real, NS>::load(PLs + (long long)(e0.w - T) * rowPL, NS, nd[u].vb);
+    }
   };
+  // child contribution: P_k v for an internal child, column `code` of P_k for a tip
+  auto contribution = [&](int k, int code, Real* v) {
+    if (code >= 0 && !parity && k < npow_s) {
+      VecIO<Real, NS>::load(sPowT + k * NS * NS + code * NS, NS, v);
+    } else {
+      if (code >= 0) tip_partial<Real, NS>(code, NS, parity, v);
+      pow_times<Real, NS>(P, sPow, npow_s, k, v);
+    }
+  };
+  auto compute = [&](PruneNode<Real, NS>* nd, int idx, int end) {
 #pragma unroll
-  for (int j = 0; j < PM_DFS_PF; j++) if (j < nops) issue(j, rma[j], rmb[j], rta[j], rtb[j]);
-
-  Real acc[NS];
-#pragma unroll
-  for (int j = 0; j < NS; j++) acc[j] = 0;
-  for (int k0 = 0; k0 < nops; k0 += PM_DFS_PF) {
-#pragma unroll
-    for (int j = 0; j < PM_DFS_PF; j++) {
-      const int k = k0 + j;
-      if (k < nops) {
-        const uint32_t ma = rma[j], mb = rmb[j]; const int ta = rta[j], tb = rtb[j];
-        if (k + PM_DFS_PF < nops) issue(k + PM_DFS_PF, rma[j], rmb[j], rta[j], rtb[j]);
-        const int4 o0 = __ldg(prog + 2 * k), o1 = __ldg(prog + 2 * k + 1);
-        const int flags = o1.y;
-        Real va[NS], vb[NS];
-        if (flags & 8) tip_partial<Real, NS>(tb, NS, parity, vb);
-        else {
-#pragma unroll
-          for (int q = 0; q < NS; q++) vb[q] = acc[q];
-        }
-        if (flags & 1) tip_partial<Real, NS>(ta, NS, parity, va);
-        else if (flags & 2) {
-#pragma unroll
-          for (int q = 0; q < NS; q++) va[q] = acc[q];
-        } else {
-          sp--;
-          VecIO<Real, NS>::load(stack + (size_t)sp * 32 * NS, NS, va);
-        }
-        pow_times<Real, NS>(P, sPow, npow_s, (int)(mb & 0xffffu) - 1, vb);
-        pow_times<Real, NS>(P, sPow, npow_s, (int)(ma & 0xffffu) - 1, va);
+    for (int u = 0; u < U; u++) {
+      if (idx + u * nw < end) {  // warp-uniform
+        contribution((int)(nd[u].mb & 0xffffu) - 1, nd[u].cb, nd[u].vb);
+        contribution((int)(nd[u].ma & 0xffffu) - 1, nd[u].ca, nd[u].va);
+        Real out[NS];
         Real s = 0;
 #pragma unroll
-        for (int q = 0; q < NS; q++) { acc[q] = vb[q] * va[q]; s += acc[q]; }
+        for (int j = 0; j < NS; j++) { out[j] = nd[u].vb[j] * nd[u].va[j]; s += out[j]; }
         if (normalize) {
-          const Real inv = (Real)1 / s;
+          const Real inv = fast_rcp<Real>(s);
 #pragma unroll
-          for (int q = 0; q < NS; q++) acc[q] = fmax(acc[q] * inv, (Real)PM_PARTIAL_FLOOR);
+          for (int j = 0; j < NS; j++) out[j] = fmax(out[j] * inv, (Real)PM_PARTIAL_FLOOR);
         }
-        if (active) VecIO<Real, NS>::store(PLs + (long long)o0.x * rowPL, NS, acc);
-        if (flags & 32) { VecIO<Real, NS>::store(stack + (size_t)sp * 32 * NS, NS, acc); sp++; }
+        if (active) VecIO<Real, NS>::store(PLs + (long long)(nd[u].pn - T) * rowPL, NS, out);
       }
     }
+  };
+
+  PruneNode<Real, NS> A[U], B[U];
+  for (int l = 0; l < P.n_up_levels; l++) {
+    const int beg = __ldg(P.up_off + l), end = __ldg(P.up_off + l + 1);
+    const int step = U * nw;
+    int idx = beg + warp;
+    if (idx < end) load(A, idx, end);
+    while (idx < end) {
+      if (idx + step < end) load(B, idx + step, end);
+      compute(A, idx, end);
+      idx += step;
+      if (idx >= end) break;
+      if (idx + step < end) load(A, idx + step, end);
+      compute(B, idx, end);
+      idx += step;
+    }
+    __syncthreads();
   }
 }
 
@@ -674,19 +762,26 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
   double* s_dw = reinterpret_cast<double*>(smem_raw);              // [4 warps][n] (NS>0) or [n] atomics (NS==0)
   unsigned* s_cnt = reinterpret_cast<unsigned*>(s_dw + 4 * n);    // [n*n]
   Real* s_rate = reinterpret_cast<Real*>(s_cnt + n * n + ((n * n) & 1));  // [n] Omega + Q_ss of this sweep
+  // topology of the chunk (the same for every thread of the block): parent / child node and branch length
+  int* s_par = reinterpret_cast<int*>(s_rate + n + (n & 1));
+  int* s_chi = s_par + chunk;
+  Real* s_len = reinterpret_cast<Real*>(s_chi + chunk);
+  const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
   for (int i = threadIdx.x; i < n * n; i += blockDim.x) s_cnt[i] = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s_rate[i] = P.model[2 * n * n + 4 * n + i];
   for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_dw[i] = 0.0;
+  for (int i = threadIdx.x; i < e1 - e0; i += blockDim.x) {
+    s_par[i] = P.e_parent[e0 + i]; s_chi[i] = P.e_child[e0 + i]; s_len[i] = P.e_len[e0 + i];
+  }
   __syncthreads();
   const long long S = P.S;
   const long long site_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = site_raw < S;
   const long long site = active ? site_raw : S - 1;
-  const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
   const bool full = P.full_counts != 0;
   uint32_t* __restrict__ mask = P.slow_mask + (long long)blockIdx.y * P.mask_words * S + site;
-  uint32_t* __restrict__ meta = P.meta + site;
-  Real* __restrict__ pos1 = P.pos1 + site;
+  uint32_t* __restrict__ meta_p = P.meta + (long long)e0 * S + site;   // walks one row (S entries) per branch
+  Real* __restrict__ pos1_p = P.pos1 + (long long)e0 * S + site;
   const uint8_t* __restrict__ nstate = P.node_state + site;
   Real Racc[NR]; double Rsum[NR];
 #pragma unroll
@@ -697,34 +792,39 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
       for (int j = 0; j < NR; j++) Racc[j] += (s == j) ? L : (Real)0;
     } else atomicAdd(&s_dw[s], (double)L);
   };
-  // software prefetch of the next branch
-  uint32_t mt_n = 0; int ps_n = 0, cs_n = 0; Real p1_n = 0;
-  auto fetch = [&](int e) {
-    mt_n = meta[(long long)e * S];
-    ps_n = nstate[(long long)__ldg(P.e_parent + e) * S];
-    cs_n = nstate[(long long)__ldg(P.e_child + e) * S];
-    p1_n = pos1[(long long)e * S];
+  // two-deep software pipeline: jump count and node states of branch i + 2, then pos1 of branch i + 1 if it has a
+  // jump point
+  const int nb = e1 - e0;
+  uint32_t mtA = 0, mtB = 0; int psA = 0, csA = 0, psB = 0, csB = 0; Real p1A = 0;
+  auto fetch = [&](int i, uint32_t& mt, int& ps, int& cs) {
+    mt = meta_p[(long long)i * S];
+    ps = nstate[(long long)s_par[i] * S];
+    cs = nstate[(long long)s_chi[i] * S];
   };
-  if (e0 < e1) fetch(e0);
+  if (nb > 0) { fetch(0, mtA, psA, csA); if ((mtA & 0xffffu) == 2u) p1A = pos1_p[0]; }
+  if (nb > 1) fetch(1, mtB, psB, csB);
   uint32_t po[4] = {0, 0, 0, 0};
   uint32_t bits = 0;
-  for (int e = e0; e < e1; e++) {
-    const uint32_t mt = mt_n; const int ps = ps_n, cs = cs_n; const Real p1 = p1_n;
-    if (e + 1 < e1) fetch(e + 1);
-    if (((e & 1) == 0) || e == e0) pair_block(P.rng, (uint32_t)site, iter, (uint32_t)e, po);
+  for (int i = 0; i < nb; i++) {
+    const int e = e0 + i;
+    const uint32_t mt = mtA; const int ps = psA, cs = csA; const Real p1 = p1A;
+    mtA = mtB; psA = psB; csA = csB;
+    if (i + 1 < nb && (mtA & 0xffffu) == 2u) p1A = pos1_p[(long long)(i + 1) * S];
+    if (i + 2 < nb) fetch(i + 2, mtB, psB, csB);
+    if (((e & 1) == 0) || i == 0) pair_block(P.rng, (uint32_t)site, iter, (uint32_t)e, po);
     const uint32_t wA = (e & 1) ? po[2] : po[0], wB = (e & 1) ? po[3] : po[1];
     const int m = (int)(mt & 0xffffu);
-    const Real Le = __ldg(P.e_len + e);
+    const Real Le = s_len[i];
     bool hard = m > 2;
     if (!hard) {
       // pieces: (Le) or (p1, Le - p1); states ps | cs (a one-piece branch carries the child state, :460-475)
       const bool two = (m == 2) && (ps != cs);
       const Real L0 = two ? p1 : Le;
-      const Real L1 = PN::sub(Le, p1);
       const int s0 = two ? ps : cs;
-      const Real r0 = s_rate[s0], r1 = s_rate[cs];
+      const Real r0 = s_rate[s0];
       const Real lam0 = rate_ok(r0) ? PN::mul(r0, L0) : (Real)0;
-      const Real lam1 = (two && rate_ok(r1)) ? PN::mul(r1, L1) : (Real)0;
+      Real L1 = 0, lam1 = 0;
+      if (two) { L1 = PN::sub(Le, p1); const Real r1 = s_rate[cs]; lam1 = rate_ok(r1) ? PN::mul(r1, L1) : (Real)0; }
       if (lam0 > (Real)PM_LAMBDA_INV || lam1 > (Real)PM_LAMBDA_INV) hard = true;
       else {
         const int k0 = lam0 > (Real)0 ? poisson_inv<Real>(lam0, wA) : 0;
@@ -736,15 +836,15 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
           const int newm = (two ? 2 : 1) + k0 + k1;
           // a path that ends up with a single jump point keeps that point in pos1: the real jump stays where it was;
           // a lone new virtual jump gets its position now
-          if (!two && k0 == 1) pos1[(long long)e * S] = next_order_stat<Real>((Real)0, Le, 1, wB);
-          meta[(long long)e * S] = PM_META(newm, two ? 1 : 0, s0, cs);
+          if (!two && k0 == 1) pos1_p[(long long)i * S] = next_order_stat<Real>((Real)0, Le, 1, wB);
+          meta_p[(long long)i * S] = PM_META(newm, two ? 1 : 0, s0, cs);
         }
       }
     }
-    const int b = (e - e0) & 31;
+    const int b = i & 31;
     bits |= (hard ? 1u : 0u) << b;
-    if (b == 31 || e == e1 - 1) {
-      if (active) mask[(long long)((e - e0) >> 5) * S] = bits;
+    if (b == 31 || i == nb - 1) {
+      if (active) mask[(long long)(i >> 5) * S] = bits;
       bits = 0;
       if (NS > 0) {
 #pragma unroll

@@ -17,59 +17,7 @@ struct Schedule {
   std::vector<int> parent_edge;            // per node: the edge row arriving at it (-1 for the root)
   std::vector<int> up_entries, up_off;     // 5 ints per internal node (parent, a, ea, b, eb), grouped by height
   std::vector<int> down_entries, down_off; // 3 ints per drawn node (v, parent, edge), grouped by depth
-  // depth-first pruning program (production K1): 8 ints per internal node in post-order with the child that needs the
-  // deeper stack first: (PL row, a, edge a, b, edge b, flags, 0, 0).  a = first-visited child, b = second.
-  std::vector<int> dfs_prog;
-  int dfs_depth = 0;                       // stack slots a warp needs (<= log2(T) + 1)
 };
-enum { DFS_A_TIP = 1, DFS_A_ACC = 2, DFS_A_STACK = 4, DFS_B_TIP = 8, DFS_B_ACC = 16, DFS_PUSH = 32 };
-
-// Post-order evaluation plan: the result of a node stays in registers ("acc") when its parent is evaluated next, and
-// goes to a small stack only when the sibling subtree has to be evaluated in between.  Visiting the child with the
-// larger stack need first bounds the depth by log2(T) + 1 for any topology.
-inline void build_dfs_program(Schedule& s) {
-  const int T = s.T, NN = 2 * T - 1, Nn = T - 1;
-  std::vector<int> kid(4 * (size_t)NN, -1);  // per internal node: a, ea, b, eb
-  std::vector<int> order;                    // internal nodes, children before parents (level order)
-  for (int i = 0; i < Nn; i++) {
-    const int* en = &s.up_entries[(size_t)5 * i];
-    int* k = &kid[(size_t)4 * en[0]];
-    k[0] = en[1]; k[1] = en[2]; k[2] = en[3]; k[3] = en[4];
-    order.push_back(en[0]);
-  }
-  std::vector<int> need(NN, 0);
-  for (int v : order) {
-    int* k = &kid[(size_t)4 * v];
-    const bool ia = k[0] >= T, ib = k[2] >= T;
-    // make k[0] the first-visited child: internal before tip, deeper need before shallower
-    if ((!ia && ib) || (ia && ib && need[k[2]] > need[k[0]])) { std::swap(k[0], k[2]); std::swap(k[1], k[3]); }
-    const bool fa = k[0] >= T, fb = k[2] >= T;
-    if (fa && fb) need[v] = std::max(need[k[0]], 1 + need[k[2]]);
-    else if (fa) need[v] = need[k[0]];
-    else need[v] = 0;
-  }
-  s.dfs_depth = std::max(1, need[s.root]);
-  s.dfs_prog.clear();
-  s.dfs_prog.reserve((size_t)8 * Nn);
-  // iterative post-order; a node's PUSH flag is set when it is a first-visited child with an internal sibling
-  struct Frame { int v; int stage; bool push; };
-  std::vector<Frame> st;
-  st.push_back({s.root, 0, false});
-  while (!st.empty()) {
-    Frame& f = st.back();
-    const int* k = &kid[(size_t)4 * f.v];
-    const bool fa = k[0] >= T, fb = k[2] >= T;
-    if (f.stage == 0) { f.stage = 1; if (fa) { st.push_back({k[0], 0, fb}); continue; } }
-    if (f.stage == 1) { f.stage = 2; if (fb) { st.push_back({k[2], 0, false}); continue; } }
-    int flags = 0;
-    if (!fa) flags |= DFS_A_TIP; else flags |= fb ? DFS_A_STACK : DFS_A_ACC;
-    if (!fb) flags |= DFS_B_TIP; else flags |= DFS_B_ACC;
-    if (f.push) flags |= DFS_PUSH;
-    const int rec[8] = {f.v - T, k[0], k[1], k[2], k[3], flags, 0, 0};
-    s.dfs_prog.insert(s.dfs_prog.end(), rec, rec + 8);
-    st.pop_back();
-  }
-}
 
 // Throws std::string on malformed input.
 inline void build_schedule(int T, int E, const int32_t* edge, const int32_t* nen, const int32_t* nodelist, int root1,
