@@ -396,6 +396,7 @@ struct ChainT : pm_chain {
       const pm_tree& x = tr[ti];
       if (x.n_tips != T0 || x.n_edges != E0) fail(PM_ERR_ARG, "all trees must have the same number of tips");
       if (x.n_sites < 1 || x.n_sites != tr[0].n_sites) fail(PM_ERR_ARG, "n_sites must be >= 1 and equal across trees");
+      if (x.n_sites >= (1LL << 31)) fail(PM_ERR_ARG, "at most 2^31 - 1 sites per process");
       if (!x.edge || !x.nen || !x.nodelist || !x.maps_off || !x.maps_len) fail(PM_ERR_ARG, "tree %d: missing field", ti);
       if (!x.states && !x.states_u8) fail(PM_ERR_ARG, "tree %d: states missing", ti);
       std::unique_ptr<TreeDev<Real>> t(new TreeDev<Real>());

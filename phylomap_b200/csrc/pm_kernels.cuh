@@ -768,13 +768,17 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
   Real* s_len = reinterpret_cast<Real*>(s_chi + chunk);
   const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
   for (int i = threadIdx.x; i < n * n; i += blockDim.x) s_cnt[i] = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s_rate[i] = P.model[2 * n * n + 4 * n + i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {  // a state without a valid rate draws no virtual jumps
+    const Real r = P.model[2 * n * n + 4 * n + i];
+    s_rate[i] = rate_ok(r) ? r : (Real)0;
+  }
   for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_dw[i] = 0.0;
   for (int i = threadIdx.x; i < e1 - e0; i += blockDim.x) {
     s_par[i] = P.e_parent[e0 + i]; s_chi[i] = P.e_child[e0 + i]; s_len[i] = P.e_len[e0 + i];
   }
   __syncthreads();
   const long long S = P.S;
+  const uint32_t Su = (uint32_t)S;  // S < 2^31 (checked by the host): 32 x 32 -> 64-bit offsets are one instruction
   const long long site_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = site_raw < S;
   const long long site = active ? site_raw : S - 1;
@@ -796,10 +800,11 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
   // jump point
   const int nb = e1 - e0;
   uint32_t mtA = 0, mtB = 0; int psA = 0, csA = 0, psB = 0, csB = 0; Real p1A = 0;
+  const uint32_t* meta_f = meta_p;  // fetch cursor (two rows ahead of the store cursor)
   auto fetch = [&](int i, uint32_t& mt, int& ps, int& cs) {
-    mt = meta_p[(long long)i * S];
-    ps = nstate[(long long)s_par[i] * S];
-    cs = nstate[(long long)s_chi[i] * S];
+    mt = *meta_f; meta_f += Su;
+    ps = nstate[(uint64_t)(uint32_t)s_par[i] * Su];
+    cs = nstate[(uint64_t)(uint32_t)s_chi[i] * Su];
   };
   if (nb > 0) { fetch(0, mtA, psA, csA); if ((mtA & 0xffffu) == 2u) p1A = pos1_p[0]; }
   if (nb > 1) fetch(1, mtB, psB, csB);
@@ -809,42 +814,37 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
     const int e = e0 + i;
     const uint32_t mt = mtA; const int ps = psA, cs = csA; const Real p1 = p1A;
     mtA = mtB; psA = psB; csA = csB;
-    if (i + 1 < nb && (mtA & 0xffffu) == 2u) p1A = pos1_p[(long long)(i + 1) * S];
+    if (i + 1 < nb && (mtA & 0xffffu) == 2u) p1A = pos1_p[Su];
     if (i + 2 < nb) fetch(i + 2, mtB, psB, csB);
     if (((e & 1) == 0) || i == 0) pair_block(P.rng, (uint32_t)site, iter, (uint32_t)e, po);
     const uint32_t wA = (e & 1) ? po[2] : po[0], wB = (e & 1) ? po[3] : po[1];
     const int m = (int)(mt & 0xffffu);
     const Real Le = s_len[i];
-    bool hard = m > 2;
-    if (!hard) {
-      // pieces: (Le) or (p1, Le - p1); states ps | cs (a one-piece branch carries the child state, :460-475)
-      const bool two = (m == 2) && (ps != cs);
-      const Real L0 = two ? p1 : Le;
-      const int s0 = two ? ps : cs;
-      const Real r0 = s_rate[s0];
-      const Real lam0 = rate_ok(r0) ? PN::mul(r0, L0) : (Real)0;
-      Real L1 = 0, lam1 = 0;
-      if (two) { L1 = PN::sub(Le, p1); const Real r1 = s_rate[cs]; lam1 = rate_ok(r1) ? PN::mul(r1, L1) : (Real)0; }
-      if (lam0 > (Real)PM_LAMBDA_INV || lam1 > (Real)PM_LAMBDA_INV) hard = true;
-      else {
-        const int k0 = lam0 > (Real)0 ? poisson_inv<Real>(lam0, wA) : 0;
-        const int k1 = lam1 > (Real)0 ? poisson_inv<Real>(lam1, wB) : 0;
-        if (active) {
-          if (m == 2 && (full || two)) atomicAdd(&s_cnt[ps * n + cs], 1u);
-          add_dwell(s0, L0);
-          if (two) add_dwell(cs, L1);
-          const int newm = (two ? 2 : 1) + k0 + k1;
-          // a path that ends up with a single jump point keeps that point in pos1: the real jump stays where it was;
-          // a lone new virtual jump gets its position now
-          if (!two && k0 == 1) pos1_p[(long long)i * S] = next_order_stat<Real>((Real)0, Le, 1, wB);
-          meta_p[(long long)i * S] = PM_META(newm, two ? 1 : 0, s0, cs);
-        }
-      }
+    // pieces: (Le) or (p1, Le - p1); states ps | cs (a one-piece branch carries the child state, :460-475)
+    const bool two = (m == 2) && (ps != cs);
+    const Real L0 = two ? p1 : Le;
+    const int s0 = two ? ps : cs;
+    const Real lam0 = PN::mul(s_rate[s0], L0);                       // rates are clamped to >= 0 when staged
+    const Real L1 = PN::sub(Le, p1);
+    const Real lam1 = two ? PN::mul(s_rate[cs], L1) : (Real)0;
+    const bool hard = (m > 2) || lam0 > (Real)PM_LAMBDA_INV || lam1 > (Real)PM_LAMBDA_INV;
+    const int k0 = poisson_inv<Real>(lam0, wA);
+    const int k1 = two ? poisson_inv<Real>(lam1, wB) : 0;
+    if (!hard && active) {
+      if (m == 2 && (full || two)) atomicAdd(&s_cnt[ps * n + cs], 1u);
+      add_dwell(s0, L0);
+      if (two) add_dwell(cs, L1);
+      const int newm = (two ? 2 : 1) + k0 + k1;
+      // a path that ends up with a single jump point keeps that point in pos1: the real jump stays where it was;
+      // a lone new virtual jump gets its position now
+      if (!two && k0 == 1) *pos1_p = next_order_stat<Real>((Real)0, Le, 1, wB);
+      *meta_p = PM_META(newm, two ? 1 : 0, s0, cs);
     }
+    meta_p += Su; pos1_p += Su;
     const int b = i & 31;
     bits |= (hard ? 1u : 0u) << b;
     if (b == 31 || i == nb - 1) {
-      if (active) mask[(long long)(i >> 5) * S] = bits;
+      if (active) mask[(uint64_t)(uint32_t)(i >> 5) * Su] = bits;
       bits = 0;
       if (NS > 0) {
 #pragma unroll
