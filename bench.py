@@ -104,7 +104,7 @@ def cpu_reference(tree, Q, pid, steps, sites_per_core=None, cores=None):
     import multiprocessing as mp
     from phylomap_b200 import synth
     cores = cores or os.cpu_count() or 1
-    sites_per_core = sites_per_core or int(os.environ.get("PM_BENCH_CPU_SITES", 8))
+    sites_per_core = sites_per_core or int(os.environ.get("PM_BENCH_CPU_SITES", 12))
     st = synth.simulate_tip_states(tree, Q, pid, cores * sites_per_core, seed=99).numpy()
     jobs = []
     for c in range(cores):
@@ -217,9 +217,18 @@ def run_ours(a, rank, local_rank, world):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch, from the committed ncu capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        k1 = tj["k_prune_pipe<float,4,1,4>"]
+        if S == 125000 and TIPS == 10000:
+            traffic = k1["dram_bytes_read"] + k1["dram_bytes_write"]
+    except Exception:
+        pass
     ach = bytes_site * S / (k1_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_prune<float,4,false>", "achieved": ach, "peak": peak, "unit": "GB/s",
-            "frac": ach / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650",
+    roof = {"bound": "hbm", "kernel": "k_prune_pipe<float,4,1,4>", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu capture of this workload)" if traffic else None,
+            "algorithmic_bytes_per_launch": bytes_site * S, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650",
             "ms_per_launch": k1_ms, "algorithmic_bytes_per_site": bytes_site,
             "in_step_ms": {k: v / a.steps for k, v in ktimes.items()}}
     dev_bytes = chain.device_bytes()
@@ -249,7 +258,7 @@ def run_ours(a, rank, local_rank, world):
     if rank == 0 and world == 1 and not a.no_cpu:
         from oracle import bridge
         bridge.build()
-        cb, _ = cpu_reference(tree, Q, pid, 4)
+        cb, _ = cpu_reference(tree, Q, pid, 6)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -214,6 +214,7 @@ struct ChainT : pm_chain {
   std::unique_ptr<pm::host::ReplaySource> replay;
   size_t smem_prune = 0, smem_nodes = 0, smem_paths = 0;
   int rows_cap = 0;
+  int k3_variant = 4;   // minimum resident blocks the general path kernel is compiled for (PHYLOMAP_B200_K3H, for tuning)
   int k1_variant = 21;  // production pruning kernel variant (pm_launch_impl.cuh; PHYLOMAP_B200_K1_UNROLL overrides, for tuning)
   struct Timed { cudaEvent_t a, b; int k; };
   std::vector<Timed> timed;
@@ -288,7 +289,7 @@ struct ChainT : pm_chain {
     pm::Sweep<Real, NSc, EX>::nodes(t.P, gx, smem_nodes, stream, iter);
     end_timed();
     begin_timed(2);
-    pm::Sweep<Real, NSc, EX>::paths(t.P, t.paths_grid, smem_paths, stream, iter, iter == 0 ? 1 : 0, t.chunk);
+    pm::Sweep<Real, NSc, EX>::paths(t.P, t.paths_grid, smem_paths, stream, iter, iter == 0 ? 1 : 0, t.chunk, k3_variant);
     end_timed();
     begin_timed(3);
     pm::k_reduce<<<1, 256, 0, stream>>>(t.dw_partial.template as<double>(), 2 * t.nblocks, n, cnt.as<unsigned long long>(),
@@ -541,6 +542,7 @@ struct ChainT : pm_chain {
     }
     mt.reseed((uint32_t)opt.seed);
     if (const char* v = getenv("PHYLOMAP_B200_K1_UNROLL")) k1_variant = atoi(v);
+    if (const char* v = getenv("PHYLOMAP_B200_K3H")) k3_variant = atoi(v);
 
     // shared-memory sizes
     const int np_fast = exact ? 0 : ((NS == 2 || NS == 4) ? std::min(PM_SMEM_POW, jcap) : 0);

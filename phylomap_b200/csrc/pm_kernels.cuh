@@ -913,8 +913,8 @@ struct RunPieces {
   }
 };
 
-template <typename Real, int NS>
-__global__ void __launch_bounds__(128) k_paths_hard(ChainParams<Real> P, uint32_t iter, int first, int chunk) {
+template <typename Real, int NS, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, uint32_t iter, int first, int chunk) {
   constexpr int NC = NS > 0 ? NS : PM_NMAX;
   constexpr int NR = NS > 0 ? NS : 1;
   typedef typename StreamSel<Real, false>::type Stream;

@@ -9,7 +9,8 @@ template <typename Real, int NS, bool EXACT>
 struct Sweep {
   static void prune(const ChainParams<Real>& P, int grid, size_t smem, cudaStream_t st, int variant);
   static void nodes(const ChainParams<Real>& P, int grid, size_t smem, cudaStream_t st, uint32_t iter);
-  static void paths(const ChainParams<Real>& P, dim3 grid, size_t smem, cudaStream_t st, uint32_t iter, int first, int chunk);
+  static void paths(const ChainParams<Real>& P, dim3 grid, size_t smem, cudaStream_t st, uint32_t iter, int first, int chunk,
+                    int variant);
 };
 
 }  // namespace pm

@@ -28,7 +28,7 @@ void Sweep<Real, NS, EXACT>::nodes(const ChainParams<Real>& P, int grid, size_t 
 }
 template <typename Real, int NS, bool EXACT>
 void Sweep<Real, NS, EXACT>::paths(const ChainParams<Real>& P, dim3 grid, size_t smem, cudaStream_t st, uint32_t iter,
-                                   int first, int chunk) {
+                                   int first, int chunk, int variant) {
   if constexpr (EXACT) k_paths<Real, NS, true><<<grid, 128, smem, st>>>(P, iter, first, chunk);
   else {
     // first sweep: every branch takes its jump points from the caller's maps -> general path only.  The easy kernel
@@ -36,7 +36,10 @@ void Sweep<Real, NS, EXACT>::paths(const ChainParams<Real>& P, dim3 grid, size_t
     const size_t smem_easy = (size_t)4 * P.n * sizeof(double) + (size_t)(P.n * P.n + ((P.n * P.n) & 1)) * sizeof(unsigned) +
                              (size_t)(P.n + (P.n & 1)) * sizeof(Real) + (size_t)chunk * (2 * sizeof(int) + sizeof(Real));
     if (!first) k_paths_easy<Real, NS><<<grid, 128, smem_easy, st>>>(P, iter, chunk);
-    k_paths_hard<Real, NS><<<grid, 128, smem, st>>>(P, iter, first, chunk);
+    if (variant == 4) k_paths_hard<Real, NS, 4><<<grid, 128, smem, st>>>(P, iter, first, chunk);
+    else if (variant == 5) k_paths_hard<Real, NS, 5><<<grid, 128, smem, st>>>(P, iter, first, chunk);
+    else if (variant == 6) k_paths_hard<Real, NS, 6><<<grid, 128, smem, st>>>(P, iter, first, chunk);
+    else k_paths_hard<Real, NS, 3><<<grid, 128, smem, st>>>(P, iter, first, chunk);
   }
 }
 
