@@ -138,12 +138,9 @@ __global__ void __launch_bounds__(256) k_prune(ChainParams<Real> P) {
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K1, production arithmetic, 2 or 4 states.  Same tiling as k_prune; what changes is the instruction stream:
-// every lane multiplies by its own tabulated power P_k = B^k straight from shared memory (k = 0 is the identity,
-// so lanes with different jump counts do not diverge), vector loads for the matrix rows, and two nodes of a
-// level in flight per warp so that more child partials are outstanding per thread.
-// ------------------------------------------------------------------------------------------------
+// v <- P_k v with the tabulated power P_k = B^k (production arithmetic, 2 or 4 states): from shared memory for the
+// first PM_SMEM_POW powers (k = 0 is the identity, so lanes with different jump counts do not diverge), from the global
+// table up to jcap, repeated mat-vecs beyond.
 template <typename Real, int NS>
 __device__ __forceinline__ void pow_times(const ChainParams<Real>& P, const Real* sPow, int npow_s, int k, Real* v) {
   if (k < npow_s) {
@@ -165,139 +162,10 @@ __device__ __forceinline__ void pow_times(const ChainParams<Real>& P, const Real
   }
 }
 
-template <typename Real, int NS, int U>
-__global__ void __launch_bounds__(256) k_prune_fast(ChainParams<Real> P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Real* sBs = reinterpret_cast<Real*>(smem_raw);
-  Real* sPow = sBs + NS * NS;
-  const int npow_s = min(PM_SMEM_POW, P.jcap);
-  load_model_smem<Real>(P, NS, nullptr, sBs, nullptr, sPow, npow_s);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const long long S = P.S;
-  const long long site_raw = (long long)blockIdx.x * 32 + lane;
-  const bool active = site_raw < S;
-  const long long site = active ? site_raw : S - 1;
-  const bool parity = P.parity_tips != 0;
-  const bool normalize = P.normalize != 0;
-  const int T = P.T;
-  const uint32_t* __restrict__ meta = P.meta + site;
-  const uint8_t* __restrict__ tip = P.tipcode + site;
-  Real* __restrict__ PLs = P.PL + site * NS;
-  const long long rowPL = S * NS;
-
-  for (int l = 0; l < P.n_up_levels; l++) {
-    const int beg = __ldg(P.up_off + l), end = __ldg(P.up_off + l + 1);
-    for (int idx = beg + warp; idx < end; idx += U * nw) {
-      // U nodes of the level in flight per warp: issue every load first, then do the arithmetic
-      int pn[U]; uint32_t ma[U], mb[U]; Real va[U][NS], vb[U][NS];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        const int id = min(idx + u * nw, end - 1);
-        const int* en = P.up_entries + 5 * id;
-        pn[u] = __ldg(en);
-        const int a = __ldg(en + 1), ea = __ldg(en + 2), b = __ldg(en + 3), eb = __ldg(en + 4);
-        ma[u] = meta[(long long)ea * S];
-        mb[u] = meta[(long long)eb * S];
-        if (a < T) tip_partial<Real, NS>(tip[(long long)a * S], NS, parity, va[u]);
-        else VecIO<Real, NS>::load(PLs + (long long)(a - T) * rowPL, NS, va[u]);
-        if (b < T) tip_partial<Real, NS>(tip[(long long)b * S], NS, parity, vb[u]);
-        else VecIO<Real, NS>::load(PLs + (long long)(b - T) * rowPL, NS, vb[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (idx + u * nw < end) {  // warp-uniform
-          pow_times<Real, NS>(P, sPow, npow_s, (int)(mb[u] & 0xffffu) - 1, vb[u]);
-          pow_times<Real, NS>(P, sPow, npow_s, (int)(ma[u] & 0xffffu) - 1, va[u]);
-          Real out[NS];
-          Real s = 0;
-#pragma unroll
-          for (int j = 0; j < NS; j++) { out[j] = vb[u][j] * va[u][j]; s += out[j]; }
-          if (normalize) {
-            const Real inv = (Real)1 / s;
-#pragma unroll
-            for (int j = 0; j < NS; j++) out[j] = fmax(out[j] * inv, (Real)PM_PARTIAL_FLOOR);
-          }
-          if (active) VecIO<Real, NS>::store(PLs + (long long)(pn[u] - T) * rowPL, NS, out);
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// K1, production arithmetic, warp-per-tile variant.  Each warp owns 32 sites and walks ALL nodes in level order on
-// its own: a node only ever reads partials the same warp wrote earlier, so no barrier is needed, and the U nodes
-// of a round (always inside one level, hence independent) give each lane 2U partial loads + 2U jump-count loads in
-// flight.  The 4 warps of a block (and the other blocks of the SM) walk the same node list at about the same pace, so
-// a node's row is touched as one multi-KB contiguous burst, and the schedule entries stay in L1.
-// ------------------------------------------------------------------------------------------------
-template <typename Real, int NS, int U>
-__global__ void __launch_bounds__(128, 7) k_prune_tile(ChainParams<Real> P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Real* sBs = reinterpret_cast<Real*>(smem_raw);
-  Real* sPow = sBs + NS * NS;
-  const int npow_s = min(PM_SMEM_POW, P.jcap);
-  load_model_smem<Real>(P, NS, nullptr, sBs, nullptr, sPow, npow_s);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long S = P.S;
-  const long long tile0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 32;
-  if (tile0 >= S) return;
-  const bool active = tile0 + lane < S;
-  const long long site = active ? tile0 + lane : S - 1;
-  const bool parity = P.parity_tips != 0;
-  const bool normalize = P.normalize != 0;
-  const int T = P.T;
-  const uint32_t* __restrict__ meta = P.meta + site;
-  const uint8_t* __restrict__ tip = P.tipcode + site;
-  Real* PLs = P.PL + site * NS;
-  const long long rowPL = S * NS;
-
-  for (int l = 0; l < P.n_up_levels; l++) {
-    const int beg = __ldg(P.up_off + l), end = __ldg(P.up_off + l + 1);
-    for (int idx = beg; idx < end; idx += U) {
-      int pn[U]; uint32_t ma[U], mb[U]; Real va[U][NS], vb[U][NS];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (idx + u < end) {  // warp-uniform
-          const int* en = P.up_entries + 5 * (idx + u);
-          pn[u] = __ldg(en);
-          const int a = __ldg(en + 1), ea = __ldg(en + 2), b = __ldg(en + 3), eb = __ldg(en + 4);
-          ma[u] = meta[(long long)ea * S];
-          mb[u] = meta[(long long)eb * S];
-          if (a < T) tip_partial<Real, NS>(tip[(long long)a * S], NS, parity, va[u]);
-          else VecIO<Real, NS>::load(PLs + (long long)(a - T) * rowPL, NS, va[u]);
-          if (b < T) tip_partial<Real, NS>(tip[(long long)b * S], NS, parity, vb[u]);
-          else VecIO<Real, NS>::load(PLs + (long long)(b - T) * rowPL, NS, vb[u]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (idx + u < end) {
-          pow_times<Real, NS>(P, sPow, npow_s, (int)(mb[u] & 0xffffu) - 1, vb[u]);
-          pow_times<Real, NS>(P, sPow, npow_s, (int)(ma[u] & 0xffffu) - 1, va[u]);
-          Real out[NS];
-          Real s = 0;
-#pragma unroll
-          for (int j = 0; j < NS; j++) { out[j] = vb[u][j] * va[u][j]; s += out[j]; }
-          if (normalize) {
-            const Real inv = (Real)1 / s;
-#pragma unroll
-            for (int j = 0; j < NS; j++) out[j] = fmax(out[j] * inv, (Real)PM_PARTIAL_FLOOR);
-          }
-          if (active) VecIO<Real, NS>::store(PLs + (long long)(pn[u] - T) * rowPL, NS, out);
-        }
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1, production arithmetic, software-pipelined.  k_prune_fast spends about as long issuing the arithmetic of a
-// round as it waits for the round's loads, one after the other, so neither the issue slots nor HBM are busy more
-// than ~45 % of the time (ncu, profiles/).  Here the loads of the NEXT round of the level are issued before the
+// K1, production arithmetic, software-pipelined.  Same tiling as k_prune.  A plain load-then-compute loop spends
+// about as long issuing the arithmetic of a round as it waits for the round's loads, one after the other, so neither
+// the issue slots nor HBM are busy more than ~45 % of the time (ncu, profiles/).  Here the loads of the NEXT round of the level are issued before the
 // arithmetic of the current one (two register buffers, ping-pong), and the arithmetic is shorter: a tip child
 // contributes a COLUMN of P_k, read as one vector from a transposed copy of the table, instead of a mat-vec with a
 // one-hot vector; schedule entries are two vector loads; the normalisation uses the hardware reciprocal.

@@ -6,18 +6,9 @@ namespace pm {
 template <typename Real, int NS, bool EXACT>
 void Sweep<Real, NS, EXACT>::prune(const ChainParams<Real>& P, int grid, size_t smem, cudaStream_t st, int variant) {
   if constexpr (!EXACT && (NS == 2 || NS == 4)) {
-    const int gtile = (int)((P.S + 127) / 128);
     const size_t spipe = 2 * PM_SMEM_POW * NS * NS * sizeof(Real);
-    if (variant == 20) k_prune_pipe<Real, NS, 2, 3><<<grid, 256, spipe, st>>>(P);
-    else if (variant == 21) k_prune_pipe<Real, NS, 1, 4><<<grid, 256, spipe, st>>>(P);
-    else if (variant == 22) k_prune_pipe<Real, NS, 2, 2><<<grid, 256, spipe, st>>>(P);
-    else if (variant == 23) k_prune_pipe<Real, NS, 1, 5><<<grid, 256, spipe, st>>>(P);
-    else if (variant == 24) k_prune_pipe<Real, NS, 3, 2><<<grid, 256, spipe, st>>>(P);
-    else if (variant == 14) k_prune_tile<Real, NS, 4><<<gtile, 128, smem, st>>>(P);
-    else if (variant == 12) k_prune_tile<Real, NS, 2><<<gtile, 128, smem, st>>>(P);
-    else if (variant == 2) k_prune_fast<Real, NS, 2><<<grid, 256, smem, st>>>(P);
-    else if (variant == 8) k_prune_fast<Real, NS, 8><<<grid, 256, smem, st>>>(P);
-    else k_prune_fast<Real, NS, 4><<<grid, 256, smem, st>>>(P);
+    if (variant == 20) k_prune_pipe<Real, NS, 2, 3><<<grid, 256, spipe, st>>>(P);  // two nodes per round
+    else k_prune_pipe<Real, NS, 1, 4><<<grid, 256, spipe, st>>>(P);
   }
   else k_prune<Real, NS, EXACT><<<grid, 256, smem, st>>>(P);
 }
@@ -36,10 +27,8 @@ void Sweep<Real, NS, EXACT>::paths(const ChainParams<Real>& P, dim3 grid, size_t
     const size_t smem_easy = (size_t)4 * P.n * sizeof(double) + (size_t)(P.n * P.n + ((P.n * P.n) & 1)) * sizeof(unsigned) +
                              (size_t)(P.n + (P.n & 1)) * sizeof(Real) + (size_t)chunk * (2 * sizeof(int) + sizeof(Real));
     if (!first) k_paths_easy<Real, NS><<<grid, 128, smem_easy, st>>>(P, iter, chunk);
-    if (variant == 4) k_paths_hard<Real, NS, 4><<<grid, 128, smem, st>>>(P, iter, first, chunk);
-    else if (variant == 5) k_paths_hard<Real, NS, 5><<<grid, 128, smem, st>>>(P, iter, first, chunk);
-    else if (variant == 6) k_paths_hard<Real, NS, 6><<<grid, 128, smem, st>>>(P, iter, first, chunk);
-    else k_paths_hard<Real, NS, 3><<<grid, 128, smem, st>>>(P, iter, first, chunk);
+    if (variant == 3) k_paths_hard<Real, NS, 3><<<grid, 128, smem, st>>>(P, iter, first, chunk);
+    else k_paths_hard<Real, NS, 4><<<grid, 128, smem, st>>>(P, iter, first, chunk);
   }
 }
 

@@ -1,4 +1,5 @@
-"""Times the production pruning kernel alone (pm_chain_time_prune) for the unroll variants at the benchmark size."""
+"""Times the production pruning kernel alone (pm_chain_time_prune) for its variants (PHYLOMAP_B200_K1_UNROLL:
+21 = one node per round [default], 20 = two) at the benchmark size, and checks that they give identical rows."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -11,7 +12,7 @@ st = synth.simulate_tip_states(tree, Q, pid, S, seed=101, device="cuda", batch_s
 z = tree.with_states(st, segments=2)
 T, E = tree.T, tree.E
 bytes_site = (T - 1) * 16 + (T - 2) * 16 + T + 4 * E
-for v in sys.argv[1:] or ["2", "4", "8"]:
+for v in sys.argv[1:] or ["21", "20"]:
     os.environ["PHYLOMAP_B200_K1_UNROLL"] = v
     ch = pb.Chain(capi.PM_V_BIGTREE, z, Q.copy(), pid, 2.4, 20, precision="f32", seed=1)
     rows = ch.run(6)
