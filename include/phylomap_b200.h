@@ -163,6 +163,11 @@ int pm_chain_get_partials(pm_chain* c, int32_t tree, int64_t site, double* out /
 int64_t pm_chain_device_bytes(pm_chain* c);
 void pm_chain_destroy(pm_chain* c);
 
+/* Host-side random numbers used by the rate updates (R's Mersenne-Twister after set.seed(seed), unif_rand, exp_rand,
+ * norm_rand, rgamma(a, scale=b)): n deviates of kind 0 unif, 1 exp, 2 norm, 3 gamma.  No device needed; lets the CPU tests
+ * pin this restatement of R's nmath (Rf_rgamma at src/phylomap.cpp:1202, runif at :1210, ...) against known R outputs. */
+void pm_rng_probe(uint32_t seed, int32_t kind, int32_t n, double a, double b, double* out);
+
 /* Library / device probe: returns the number of CUDA devices with compute capability 10.x, or a negative error. */
 int pm_device_count(void);
 const char* pm_version(void);

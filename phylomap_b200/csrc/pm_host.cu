@@ -931,6 +931,18 @@ int pm_chain_get_partials(pm_chain* c, int32_t tree, int64_t site, double* out) 
 int64_t pm_chain_device_bytes(pm_chain* c) { return c->dev_bytes; }
 void pm_chain_destroy(pm_chain* c) { delete c; }
 
+void pm_rng_probe(uint32_t seed, int32_t kind, int32_t n, double a, double b, double* out) {
+  pm::host::MersenneR g(seed);
+  for (int i = 0; i < n; i++) {
+    switch (kind) {
+      case 0: out[i] = g.next(); break;
+      case 1: out[i] = pm::host::r_exp_rand(g); break;
+      case 2: out[i] = pm::host::r_norm_rand(g); break;
+      default: out[i] = pm::host::r_rgamma(g, a, b); break;
+    }
+  }
+}
+
 int pm_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return -PM_ERR_CUDA;

@@ -87,3 +87,22 @@ def test_product_does_not_touch_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle/" not in src.replace("oracle/bridge.py takes (tests only)", "") or f == "tree.py"
                 assert "import oracle" not in src and "from oracle" not in src
+
+
+def _probe(seed, kind, n, a=0.0, b=0.0):
+    out = np.zeros(n)
+    capi.lib().pm_rng_probe(seed, kind, n, a, b, capi.ptr(out))
+    return out
+
+
+def test_host_rng_matches_known_r_outputs_and_the_oracle(oracle):
+    """The product's own restatement of R's RNG (pm_rrng.hpp, used by the rate updates) against published R outputs
+    and, draw for draw, against the oracle's independent restatement."""
+    np.testing.assert_allclose(_probe(1, 0, 3), [0.2655087, 0.3721239, 0.5728534], atol=5e-8)      # set.seed(1); runif(3)
+    np.testing.assert_allclose(_probe(123, 0, 3), [0.2875775, 0.7883051, 0.4089769], atol=5e-8)
+    np.testing.assert_allclose(_probe(1, 1, 3), [0.7551818, 1.1816428, 0.1457067], atol=5e-8)      # rexp(3)
+    np.testing.assert_allclose(_probe(1, 2, 3), [-0.6264538, 0.1836433, -0.8356286], atol=5e-8)    # rnorm(3)
+    for kind, name in [(0, "unif"), (1, "exp"), (2, "norm")]:
+        assert np.array_equal(_probe(77, kind, 2000), oracle.rng_probe(77, name, 2000))
+    for shape, scale in [(0.3, 2.0), (1.0, 1.0), (2.5, 0.5), (7.0, 0.1), (20.0, 0.05)]:
+        assert np.array_equal(_probe(9, 3, 3000, shape, scale), oracle.rng_probe(9, "gamma", 3000, shape, scale))
