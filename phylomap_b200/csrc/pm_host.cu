@@ -776,13 +776,9 @@ struct ChainT : pm_chain {
       if (cap > 1) { len[1] = (double)(Le - p1); st[1] = s1; }
       return 2;
     }
-    long long pos = 0;
-    for (int e2 = b0; e2 < e; e2++) {
-      uint32_t m2 = 0;
-      CK(cudaMemcpy(&m2, t.meta.template as<uint32_t>() + (size_t)e2 * t.S + site, 4, cudaMemcpyDeviceToHost));
-      const int nj2 = (m2 >> 16) & 0x3f;
-      if (nj2 >= 2) pos += nj2 + 1;
-    }
+    Real off;  // paths with two or more real jumps: pos1 holds the offset of their records in the site's slice
+    CK(cudaMemcpy(&off, t.pos1.template as<Real>() + (size_t)e * t.S + site, sizeof(Real), cudaMemcpyDeviceToHost));
+    const long long pos = (long long)off;
     records(pos, nj + 1);
     return nj + 1;
   }

@@ -803,20 +803,24 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
   __syncthreads();
   const Real* s_rate_old = sVec + 3 * n;
   const Real* s_rate_new = sVec + 4 * n;
+  // block-wide work queue: the set bits of the 128 masks of this block, compacted, so that every round hands each
+  // thread one (site, branch) item whatever the distribution of the bits over the sites
+  __shared__ uint32_t s_queue[128 * 32 + 128];  // item = branch-in-chunk << 8 | site-in-block
+  __shared__ int s_wr[128];                     // records appended so far to the slice of each site
+  __shared__ int s_scan[4];
   const long long S = P.S;
-  const long long site_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = site_raw < S;
-  const long long site = active ? site_raw : S - 1;
+  const long long site0 = (long long)blockIdx.x * blockDim.x;
+  const int nsites = (int)min((long long)blockDim.x, S - site0);
   const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
   const int nwords = (e1 - e0 + 31) >> 5;
-  const uint32_t* __restrict__ mask = P.slow_mask + (long long)blockIdx.y * P.mask_words * S + site;
+  const uint32_t* __restrict__ mask = P.slow_mask + (long long)blockIdx.y * P.mask_words * S + site0 + min((int)threadIdx.x, nsites - 1);
   const int cap0 = __ldg(P.cap_off + blockIdx.y), cap_c = __ldg(P.cap_off + blockIdx.y + 1) - cap0;
-  const long long abase = (long long)cap0 * S + site * (long long)cap_c;
-  const Real* __restrict__ rd_len = P.rec_len[(iter & 1u) ^ 1u] + abase;
-  const uint8_t* __restrict__ rd_st = P.rec_st[(iter & 1u) ^ 1u] + abase;
-  Real* __restrict__ wr_len = P.rec_len[iter & 1u] + abase;
-  uint8_t* __restrict__ wr_st = P.rec_st[iter & 1u] + abase;
-  int rd = 0, wr = 0;
+  const long long abase0 = (long long)cap0 * S + site0 * (long long)cap_c;  // + site-in-block * cap_c + offset
+  const Real* __restrict__ rd_len = P.rec_len[(iter & 1u) ^ 1u] + abase0;
+  const uint8_t* __restrict__ rd_st = P.rec_st[(iter & 1u) ^ 1u] + abase0;
+  Real* __restrict__ wr_len = P.rec_len[iter & 1u] + abase0;
+  uint8_t* __restrict__ wr_st = P.rec_st[iter & 1u] + abase0;
+  s_wr[threadIdx.x] = 0;
   const bool full = P.full_counts != 0;
   double Rsum[NR];
 #pragma unroll
@@ -828,18 +832,48 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       for (int j = 0; j < NR; j++) Rsum[j] += (s == j) ? (double)L : 0.0;
     } else atomicAdd(&s_dw[s], (double)L);
   };
-
-  int w = 0; uint32_t bits = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lastmask = ((e1 - e0) & 31) ? ((1u << ((e1 - e0) & 31)) - 1u) : 0xffffffffu;
-  if (active) for (;;) {
-    while (bits == 0u && w < nwords) {
-      bits = first ? 0xffffffffu : mask[(long long)w * S];
-      if (w == nwords - 1) bits &= lastmask;
-      w++;
+  int qn = 0;  // items waiting in s_queue[0 .. qn)  (block-uniform)
+  __syncthreads();
+
+  for (int w = 0; w <= nwords; w++) {
+    if (w < nwords) {
+      // append this word's items: exclusive scan of the popcounts over the block
+      uint32_t bits = 0;
+      if ((int)threadIdx.x < nsites) {
+        bits = first ? 0xffffffffu : mask[(long long)w * S];
+        if (w == nwords - 1) bits &= lastmask;
+      }
+      const int c = __popc(bits);
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+      if (lane == 31) s_scan[warp] = inc;
+      __syncthreads();
+      int base = qn;
+      for (int ww = 0; ww < warp; ww++) base += s_scan[ww];
+      const int total = s_scan[0] + s_scan[1] + s_scan[2] + s_scan[3];
+      int pos = base + inc - c;
+      while (bits) {
+        const int b = __ffs((int)bits) - 1;
+        bits &= bits - 1u;
+        s_queue[pos++] = ((uint32_t)((w << 5) + b) << 8) | threadIdx.x;
+      }
+      qn += total;
+      __syncthreads();
     }
-    if (bits == 0u) break;
-    const int eb = e0 + ((w - 1) << 5) + (__ffs((int)bits) - 1);
-    bits &= bits - 1u;
+    // full rounds of 128 items (and, after the last word, the remainder)
+    while (qn >= (int)blockDim.x || (w == nwords && qn > 0)) {
+      const int take = min(qn, (int)blockDim.x);
+      const bool have = (int)threadIdx.x < take;
+      const uint32_t item = have ? s_queue[qn - take + threadIdx.x] : 0u;
+      qn -= take;
+      if (have) {
+    const int tsite = (int)(item & 0xffu);
+    const long long site = site0 + tsite;
+    const int eb = e0 + (int)(item >> 8);
+    const long long sbase = (long long)tsite * cap_c;  // this site's slice inside the block's arena window
 
     const long long pe = (long long)eb * S + site;
     const uint32_t mt = P.meta[pe];
@@ -862,12 +896,13 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     int jrun = 0;
     RunPieces<Real> rp;
     long long cp = first ? P.maps_off[eb] : 0;
-    const Real p1 = (!first && (nj == 1)) ? P.pos1[pe] : (Real)0;
+    const Real p1 = (!first && (nj >= 1)) ? P.pos1[pe] : (Real)0;  // nj == 1: length of run 0; nj >= 2: record offset
+    const int rd0 = (nj >= 2) ? (int)p1 : 0;
     auto open_run = [&](int r) {
       Real len; int st;
       if (nj == 0) { len = Le; st = (int)((mt >> 22) & 0x1fu); }
       else if (nj == 1) { len = r == 0 ? p1 : PN::sub(Le, p1); st = (int)((mt >> (r == 0 ? 22 : 27)) & 0x1fu); }
-      else { const int q = min(rd + r, cap_c - 1); len = rd_len[q]; st = rd_st[q]; }
+      else { const int q = min(rd0 + r, cap_c - 1); len = rd_len[sbase + q]; st = rd_st[sbase + q]; }
       const uint32_t cw = r == 0 ? oA : r == 1 ? oB : cnt_old.next();
       rp.begin(P.rng, (uint32_t)site, iter - 1u, (uint32_t)eb, r, len, s_rate_old[st], cw, nj == 0, oB);
     };
@@ -887,17 +922,12 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     int nout = 0, newm = 0, S0 = 0, S1 = 0, k0 = 0;
     Real L0 = 0, L1 = 0, gap0 = 0;
     bool gaps0 = false;
-    auto put = [&](Real L, int s) {
-      if (wr < cap_c) { wr_len[wr] = L; wr_st[wr] = (uint8_t)s; wr++; } else errbits |= PM_DE_PATH_CAP;
-    };
+    Real bufL[PM_LOCAL_PATH_MAX]; uint8_t bufS[PM_LOCAL_PATH_MAX];  // runs 2.. of a long path (local memory, rarely touched)
     auto emit = [&](Real L, int s) {
       const int r = nout;
       if (r == 0) { L0 = L; S0 = s; }
       else if (r == 1) { L1 = L; S1 = s; }
-      else {
-        if (r == 2) { put(L0, S0); put(L1, S1); }
-        put(L, s);
-      }
+      else if (r < PM_LOCAL_PATH_MAX) { bufL[r] = L; bufS[r] = (uint8_t)s; }
       add_dwell(s, L);
       const Real rate = s_rate_new[s];
       int k = 0;
@@ -956,7 +986,6 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       prev = st;
     }
     if (!first && (jrun != nrun)) errbits |= PM_DE_INCONSISTENT;  // the regenerated pieces must add up to m
-    if (!first && nj >= 2) rd += nj + 1;
     // a single-run path spans the whole branch: take its length from the tree, not from the sum of its pieces
     // ... and the second run of a two-run path is what is left after the first (the form the next sweep rebuilds it in)
     emit(nout == 0 ? Le : nout == 1 ? PN::sub(Le, L0) : cur_len, cur_state);
@@ -965,12 +994,24 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     if (nout == 1) {
       if (k0 == 1) P.pos1[pe] = gaps0 ? gap0 : next_order_stat<Real>((Real)0, Le, 1, nB);
     } else if (nout == 2) P.pos1[pe] = L0;
+    else {
+      // three or more runs: a contiguous block of records in the site's slice; its offset goes where a shorter path
+      // keeps the length of its first run
+      const int base = atomicAdd(&s_wr[tsite], nout);
+      if (base + nout <= cap_c) {
+        wr_len[sbase + base] = L0; wr_st[sbase + base] = (uint8_t)S0;
+        wr_len[sbase + base + 1] = L1; wr_st[sbase + base + 1] = (uint8_t)S1;
+        for (int r = 2; r < nout; r++) { wr_len[sbase + base + r] = bufL[r]; wr_st[sbase + base + r] = bufS[r]; }
+      } else errbits |= PM_DE_PATH_CAP;
+      P.pos1[pe] = (Real)base;
+    }
     P.meta[pe] = PM_META(newm, nout - 1, S0, S1);
-  }
+      }  // have
+    }    // rounds
+  }      // words
   if (errbits) atomicOr(P.err_flag, errbits);
 
   if (NS > 0) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < NR; j++) {
       double v = Rsum[j];
