@@ -168,6 +168,10 @@ void pm_chain_destroy(pm_chain* c);
  * pin this restatement of R's nmath (Rf_rgamma at src/phylomap.cpp:1202, runif at :1210, ...) against known R outputs. */
 void pm_rng_probe(uint32_t seed, int32_t kind, int32_t n, double a, double b, double* out);
 
+/* Device memory of destroyed chains is cached per process for the next call of the same shape (cudaMalloc / cudaFree of
+ * tens of GB would dominate a short call); this returns it to the driver.  PHYLOMAP_B200_CACHE=0 disables the cache. */
+void pm_release_cached_memory(void);
+
 /* Library / device probe: returns the number of CUDA devices with compute capability 10.x, or a negative error. */
 int pm_device_count(void);
 const char* pm_version(void);

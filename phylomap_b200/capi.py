@@ -42,7 +42,7 @@ EXPORTS = ["pm_default_options", "pm_maketreelistMCMC", "pm_SPARSEmaketreelistMC
            "pm_ncols", "pm_tree_order", "pm_chain_create", "pm_chain_run", "pm_chain_time_prune",
            "pm_chain_kernel_times", "pm_chain_enable_timing", "pm_chain_get_node_states", "pm_chain_get_piece_counts",
            "pm_chain_get_path", "pm_chain_get_partials", "pm_chain_device_bytes", "pm_chain_destroy",
-           "pm_rng_probe", "pm_device_count", "pm_version"]
+           "pm_rng_probe", "pm_release_cached_memory", "pm_device_count", "pm_version"]
 
 _LIB = None
 
@@ -93,6 +93,7 @@ def lib():
     L.pm_chain_destroy.restype = None
     L.pm_rng_probe.argtypes = [C.c_uint32, i32, i32, dbl, dbl, vp]
     L.pm_rng_probe.restype = None
+    L.pm_release_cached_memory.restype = None
     L.pm_device_count.restype = C.c_int
     L.pm_version.restype = C.c_char_p
     _LIB = L

@@ -16,7 +16,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -70,17 +72,57 @@ int guarded(char* err, size_t errlen, F&& f) {
   }
 }
 
+// Device allocations go through a small per-process cache: cudaMalloc / cudaFree of tens of GB cost 0.1-0.4 s per call,
+// which would dominate a short drop-in call (R users call the samplers repeatedly on the same tree).  Freed blocks are
+// kept by (device, size) and handed back to the next chain that asks for exactly that size; pm_release_cached_memory()
+// returns them to the driver, PHYLOMAP_B200_CACHE=0 disables the cache.
+struct DevicePool {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void*> free_blocks;
+  bool enabled;
+  DevicePool() { const char* v = getenv("PHYLOMAP_B200_CACHE"); enabled = !(v && v[0] == '0'); }
+  void* take(int dev, size_t n) {
+    if (enabled) {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = free_blocks.find({dev, n});
+      if (it != free_blocks.end()) { void* p = it->second; free_blocks.erase(it); return p; }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess && enabled) {  // make room and retry once
+      cudaGetLastError();
+      release();
+      e = cudaMalloc(&p, n);
+    }
+    if (e != cudaSuccess) fail(PM_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+    return p;
+  }
+  void give(int dev, size_t n, void* p) {
+    if (!p) return;
+    if (enabled) { std::lock_guard<std::mutex> g(mu); free_blocks.insert({{dev, n}, p}); }
+    else cudaFree(p);
+  }
+  void release() {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& kv : free_blocks) cudaFree(kv.second);
+    free_blocks.clear();
+  }
+};
+DevicePool& pool() { static DevicePool p; return p; }
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  int dev = 0;
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  ~DevBuf() { if (p) cudaFree(p); }
+  ~DevBuf() { pool().give(dev, bytes, p); }
   void alloc(size_t n) {
-    if (p) { cudaFree(p); p = nullptr; }
-    bytes = n;
-    if (n) CK(cudaMalloc(&p, n));
+    pool().give(dev, bytes, p);
+    p = nullptr; bytes = n;
+    cudaGetDevice(&dev);
+    if (n) p = pool().take(dev, n);
   }
   template <typename T> T* as() const { return static_cast<T*>(p); }
 };
@@ -938,6 +980,8 @@ void pm_rng_probe(uint32_t seed, int32_t kind, int32_t n, double a, double b, do
     }
   }
 }
+
+void pm_release_cached_memory(void) { pool().release(); }
 
 int pm_device_count(void) {
   int n = 0;

@@ -247,3 +247,23 @@ def test_golden_vectors():
         fixed = case["variant"] in ("PLAIN", "SPARSE", "BIGTREE")
         ints = set(range(n, ref.shape[1])) if fixed else set(range(n, n + n * n)) | {ref.shape[1] - 1}
         _compare_rows(got, ref, n, ints, tol=1e-7)
+
+
+def test_smallest_tree_and_zero_iterations(oracle):
+    """A cherry (2 tips, empty nodelist) and N = 0."""
+    tree = pb.PhyloTree(np.array([[3, 1], [3, 2]]), np.array([1.0, 2.0])).with_states(np.array([1, 2]))
+    _, ref = _oracle(oracle, oracle.PLAIN, [tree], cases.Q2, cases.PID2, 0.2, 30)
+    got = pb.sumstatMCMC(tree, cases.Q2, cases.PID2, 0.2, 30, seed=7, **DET)
+    _compare_rows(got, ref, 2, int_cols={2, 3})
+    assert pb.sumstatMCMC(tree, cases.Q2, cases.PID2, 0.2, 0, seed=7, **DET).shape == (0, 4)
+
+
+def test_long_branches_many_pieces(oracle):
+    """Omega * t ~ 30 per branch: hundreds of pieces per branch, powers of B beyond the shared-memory table."""
+    z = cases.tree2(T=10, S=3, seed=4, mean_branch=150.0)
+    N, Om = 6, 0.2
+    orc, ref = _oracle(oracle, oracle.PLAIN, [z], cases.Q2, cases.PID2, Om, N)
+    ch = pb.Chain(capi.PM_V_PLAIN, z, cases.Q2.copy(), cases.PID2, Om, N, seed=7, **DET)
+    _compare_rows(ch.run(), ref, 2, int_cols={2, 3})
+    _compare_state(ch, orc, z, 3, z.E, n_paths=15)
+    assert orc.piece_counts().max() > 40

@@ -106,3 +106,32 @@ def test_squamate_sized_sparse_run():
     out = pb.SPARSEsumstatMCMC(z, Q, cases.PID2, 0.012, 6, precision="f32", seed=3)
     np.testing.assert_allclose(out[:, :2].sum(1), S * tree.edge_length.sum(), rtol=2e-4)
     assert np.all(out[:, 2:] >= 0)
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_long_branches_gap_mode(oracle, precision):
+    """Runs with (Omega + Q_ss) L > 16 draw their virtual jumps from exponential gaps (pm_device.cuh); with
+    Omega * t ~ 30 almost every branch does, every branch goes through the general path kernel, and the power table
+    is longer than its shared-memory part.  Posterior of the jump counts against the oracle chain."""
+    z = cases.tree2(T=12, S=1, seed=6, mean_branch=150.0)
+    N, thin, burn = 6000, 10, 300
+    ref = oracle.OracleRun(oracle.PLAIN, [z.oracle_dict()], cases.Q2, cases.PID2, 0.2, N, rng_mode=oracle.SEQUENTIAL,
+                           seed=11).run()[burn::thin]
+    got = pb.sumstatMCMC(z, cases.Q2, cases.PID2, 0.2, N, seed=5, precision=precision)[burn::thin]
+    np.testing.assert_allclose(got[:, :2].sum(1), z.edge_length.sum(), rtol=1e-5)
+    for col, name in [(2, "N01"), (3, "N10"), (0, "R0")]:
+        p = stats.ks_2samp(got[:, col], ref[:, col]).pvalue
+        assert p > 0.01, "%s: KS p = %.4f" % (name, p)
+
+
+def test_ragged_site_counts_and_chunk_edges():
+    """Site counts that are not multiples of the 32-site tiles / 128-site blocks, on a tree whose branch count is not a
+    multiple of the chunk size: the invariants must hold for every S."""
+    Q, pid = cases.q4(), np.full(4, 0.25)
+    tree = synth.yule_tree(333, seed=8, mean_branch=0.2)
+    for S in (1, 31, 33, 127, 129, 1000):
+        st = synth.simulate_tip_states(tree, Q, pid, S, seed=S).numpy()
+        z = tree.with_states(st if S > 1 else st[0].astype(np.int32), segments=2)
+        out = pb.sumstatMCMC_bigtree(z, Q, pid, 2.4, 5, seed=3, precision="f32")
+        np.testing.assert_allclose(out[:, :4].sum(1), S * tree.edge_length.sum(), rtol=2e-4)
+        assert np.array_equal(out[:, 4:], np.round(out[:, 4:])) and np.all(out[:, 4:] >= 0)
