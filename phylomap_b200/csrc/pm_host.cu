@@ -420,6 +420,31 @@ struct ChainT : pm_chain {
     W = n + n * n + 1;
     ncols = ncols_of(variant, n);
 
+    // host-only validation of the trees first: malformed input is reported as PM_ERR_ARG even where no device exists
+    if (!(Om > 0)) fail(PM_ERR_ARG, "Omega must be positive");
+    std::vector<pm::host::Schedule> schedules(ntr);
+    for (int ti = 0; ti < ntr; ti++) {
+      const pm_tree& x = tr[ti];
+      if (x.n_tips != tr[0].n_tips || x.n_edges != tr[0].n_edges) fail(PM_ERR_ARG, "all trees must have the same number of tips");
+      if (x.n_sites < 1 || x.n_sites != tr[0].n_sites) fail(PM_ERR_ARG, "n_sites must be >= 1 and equal across trees");
+      if (x.n_sites >= (1LL << 31)) fail(PM_ERR_ARG, "at most 2^31 - 1 sites per process");
+      if (!x.edge || !x.nen || !x.nodelist || !x.maps_off || !x.maps_len) fail(PM_ERR_ARG, "tree %d: missing field", ti);
+      if (!x.states && !x.states_u8) fail(PM_ERR_ARG, "tree %d: states missing", ti);
+      try {
+        pm::host::build_schedule(x.n_tips, x.n_edges, x.edge, x.nen, x.nodelist, x.root, V.redraw_tips, schedules[ti]);
+      } catch (const std::string& msg) { fail(PM_ERR_ARG, "tree %d: %s", ti, msg.c_str()); }
+      if (x.maps_off[0] != 0) fail(PM_ERR_ARG, "tree %d: maps_off[0] must be 0", ti);
+      for (int e = 0; e < x.n_edges; e++) {
+        const long long a = x.maps_off[e], b = x.maps_off[e + 1];
+        if (b <= a) fail(PM_ERR_ARG, "tree %d: branch %d has no segments", ti, e + 1);
+        if (b - a > 65535) fail(PM_ERR_ARG, "tree %d: branch %d has more than 65535 segments", ti, e + 1);
+        for (long long p = a; p < b; p++) {
+          if (!(x.maps_len[p] >= 0)) fail(PM_ERR_ARG, "tree %d: negative or NA segment length", ti);
+          if (x.maps_state && (x.maps_state[p] < 1 || x.maps_state[p] > n)) fail(PM_ERR_ARG, "tree %d: mapnames out of range", ti);
+        }
+      }
+    }
+
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) fail(PM_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
     if (opt.device < 0 || opt.device >= ndev) fail(PM_ERR_CUDA, "device %d not present", opt.device);
@@ -433,35 +458,19 @@ struct ChainT : pm_chain {
     const int T0 = tr[0].n_tips, E0 = tr[0].n_edges;
     double tmax = 0, qmax = 0;
     for (int s = 0; s < n; s++) qmax = std::max(qmax, -Q[s + (size_t)s * n]);
-    if (!(Omega > 0)) fail(PM_ERR_ARG, "Omega must be positive");
 
     for (int ti = 0; ti < ntr; ti++) {
       const pm_tree& x = tr[ti];
-      if (x.n_tips != T0 || x.n_edges != E0) fail(PM_ERR_ARG, "all trees must have the same number of tips");
-      if (x.n_sites < 1 || x.n_sites != tr[0].n_sites) fail(PM_ERR_ARG, "n_sites must be >= 1 and equal across trees");
-      if (x.n_sites >= (1LL << 31)) fail(PM_ERR_ARG, "at most 2^31 - 1 sites per process");
-      if (!x.edge || !x.nen || !x.nodelist || !x.maps_off || !x.maps_len) fail(PM_ERR_ARG, "tree %d: missing field", ti);
-      if (!x.states && !x.states_u8) fail(PM_ERR_ARG, "tree %d: states missing", ti);
       std::unique_ptr<TreeDev<Real>> t(new TreeDev<Real>());
-      try {
-        pm::host::build_schedule(x.n_tips, x.n_edges, x.edge, x.nen, x.nodelist, x.root, V.redraw_tips, t->sch);
-      } catch (const std::string& s) { fail(PM_ERR_ARG, "tree %d: %s", ti, s.c_str()); }
+      t->sch = std::move(schedules[ti]);
       t->S = x.n_sites;
       const int E = x.n_edges, T = x.n_tips;
       std::vector<long long> moff(E + 1);
       std::vector<Real> elen(E);
       for (int e = 0; e <= E; e++) moff[e] = x.maps_off[e];
-      if (moff[0] != 0) fail(PM_ERR_ARG, "tree %d: maps_off[0] must be 0", ti);
       for (int e = 0; e < E; e++) {
-        const long long a = moff[e], b = moff[e + 1];
-        if (b <= a) fail(PM_ERR_ARG, "tree %d: branch %d has no segments", ti, e + 1);
-        if (b - a > 65535) fail(PM_ERR_ARG, "tree %d: branch %d has more than 65535 segments", ti, e + 1);
         double tot = 0;
-        for (long long p = a; p < b; p++) {
-          if (!(x.maps_len[p] >= 0)) fail(PM_ERR_ARG, "tree %d: negative or NA segment length", ti);
-          if (x.maps_state && (x.maps_state[p] < 1 || x.maps_state[p] > n)) fail(PM_ERR_ARG, "tree %d: mapnames out of range", ti);
-          tot = tot + x.maps_len[p];
-        }
+        for (long long p = moff[e]; p < moff[e + 1]; p++) tot = tot + x.maps_len[p];
         elen[e] = (Real)tot;
         tmax = std::max(tmax, tot);
       }

@@ -106,3 +106,39 @@ def test_host_rng_matches_known_r_outputs_and_the_oracle(oracle):
         assert np.array_equal(_probe(77, kind, 2000), oracle.rng_probe(77, name, 2000))
     for shape, scale in [(0.3, 2.0), (1.0, 1.0), (2.5, 0.5), (7.0, 0.1), (20.0, 0.05)]:
         assert np.array_equal(_probe(9, 3, 3000, shape, scale), oracle.rng_probe(9, "gamma", 3000, shape, scale))
+
+
+def _expect_arg_error(fn, fragment):
+    with pytest.raises(capi.PhylomapError) as e:
+        fn()
+    assert e.value.code == capi.PM_ERR_ARG, e.value
+    assert fragment in e.value.msg, e.value.msg
+
+
+def test_malformed_inputs_are_reported_before_any_device_work():
+    """Host-side validation of the reference's tree inputs (x$edge, nen, nodelist, root, maps): PM_ERR_ARG with a
+    message, also on a machine without a GPU."""
+    z = cases.tree2(T=8)
+    nen, nodelist, root = z.order()
+    B = np.asfortranarray(np.eye(2) + cases.Q2 / 0.2)
+    call = lambda **kw: pb.maketreelistMCMC(kw.get("z", z), cases.Q2, cases.PID2, B, kw.get("Om", 0.2), kw.get("nen", nen),
+                                            kw.get("nodelist", nodelist), kw.get("root", root), 3)
+    _expect_arg_error(lambda: call(nen=nen[::-1].copy()), "pruning-wise")            # parents before children
+    bad = nen.copy(); bad[1] = bad[0]
+    _expect_arg_error(lambda: call(nen=bad), "nen")
+    swapped = nen.copy(); swapped[[1, 2]] = swapped[[2, 1]]
+    _expect_arg_error(lambda: call(nen=swapped), "sibling")
+    _expect_arg_error(lambda: call(nodelist=nodelist[::-1].copy()), "top-down")
+    _expect_arg_error(lambda: call(root=1), "root")
+    _expect_arg_error(lambda: call(Om=0.0), "Omega")
+    neg = pb.PhyloTree(z.edge, z.edge_length, z.states, [m.copy() for m in z.maps], z.mapnames)
+    neg.maps[0][0] = -1.0
+    _expect_arg_error(lambda: call(z=neg), "segment length")
+    edge = z.edge.copy(); edge[0, 0] = 1                                                # a tip as a parent
+    _expect_arg_error(lambda: call(z=pb.PhyloTree(edge, z.edge_length, z.states, z.maps, z.mapnames)), "edge")
+    with pytest.raises(capi.PhylomapError) as e:                                         # bf is 2-state only
+        pb.sumstatMCMCbf(cases.tree_n(cases.jc(3), T=6), cases.jc(3), np.full(3, 1 / 3), 1.0, 2, cases.PRIOR_BF)
+    assert e.value.code == capi.PM_ERR_ARG
+    with pytest.raises(capi.PhylomapError) as e:                                         # prior too short
+        pb.sumstatMCMCks(cases.tree_hidden(cases.q4(), T=6), cases.q4(), np.full(4, .25), 4.0, 2, [1.0, 2.0])
+    assert e.value.code == capi.PM_ERR_ARG
