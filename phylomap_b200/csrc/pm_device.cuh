@@ -213,7 +213,8 @@ template <> struct Pin<float> {
   static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
   static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
   static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
-  static __device__ __forceinline__ float u01(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+  // (w >> 9 + 1/2) 2^-23: exact in FP32 (24 significant bits), strictly inside (0, 1), one fused multiply-add
+  static __device__ __forceinline__ float u01(uint32_t w) { return __fmaf_rn((float)(w >> 9), 1.0f / 8388608.0f, 1.0f / 16777216.0f); }
   static __device__ __forceinline__ float expm(float x) { return __expf(-x); }  // ex2.approx: same bits everywhere
   static __device__ __forceinline__ float root(float u, int k) { return exp2f(__fdiv_rn(log2f(u), (float)k)); }
   static __device__ __forceinline__ float neglog(float u) { return -logf(u); }
