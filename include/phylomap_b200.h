@@ -14,6 +14,8 @@
  *   pm_maketreelistMCMCks       <- maketreelistMCMCks       src/phylomap.cpp:1802 (src/RcppExports.cpp:132)
  *   pm_maketreelistMCMCmt       <- maketreelistMCMCmt       src/phylomap.cpp:2267 (src/RcppExports.cpp:159)
  *   pm_maketreelistMCMCksmt     <- maketreelistMCMCksmt     src/phylomap.cpp:2722 (src/RcppExports.cpp:185)
+ *   pm_maketreelistMCMC2sDICt   <- maketreelistMCMC2sDICt   src/phylomap.cpp:3183 (src/RcppExports.cpp:211)
+ *   pm_maketreelistMCMCksDICt   <- maketreelistMCMCksDICt   src/phylomap.cpp:3300 (src/RcppExports.cpp:237)
  *   pm_tree_order               <- pruningwiseedgeorder / makenodelist / myreorder, R/sumstatMCMC.R:1-18 (O(E) here)
  *
  * There is no CPU fallback: every entry fails with PM_ERR_CUDA when no sm_100 device is usable.
@@ -65,6 +67,7 @@ typedef struct pm_tree {
   const int32_t* states;     /* x$states, 1-based, [n_sites][T] site-major; may be NULL if states_u8 is given */
   const uint8_t* states_u8;  /* optional compact alternative to `states` (same values, same layout) */
   int64_t n_sites;           /* S (1 = the reference) */
+  const double* edge_length; /* x$edge.length [E]: read by the DIC samplers only (src/phylomap.cpp:3225); NULL = sum of maps */
 } pm_tree;
 
 /* Called once per iteration by the rate-updating samplers (bf/ks/mt/ksmt) when the sites are sharded over
@@ -123,6 +126,17 @@ int pm_maketreelistMCMCksmt(const pm_tree* trees, int32_t ntrees, int32_t n, dou
                             double Omega, int32_t N, const double* prior, int32_t nprior, const pm_options* opt,
                             double* out, char* err, size_t errlen);
 
+/* DIC chains: the bf / ks samplers with one more column, log p(y | Q) of the current rates by matrix exponentiation
+ * (summed over sites), computed after every sweep and before the rate update (src/phylomap.cpp:3242-3250, :3383-3390):
+ *   2sDICt [N x 10]                  t0 t1 n00 n01 n10 n11 l01 l10 root loglik
+ *   ksDICt [N x n+n^2+2+3k+2]        as ks, then loglik */
+int pm_maketreelistMCMC2sDICt(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega, int32_t N,
+                              const double* prior, int32_t nprior, const pm_options* opt, double* out, char* err,
+                              size_t errlen);
+int pm_maketreelistMCMCksDICt(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega, int32_t N,
+                              const double* prior, int32_t nprior, const pm_options* opt, double* out, char* err,
+                              size_t errlen);
+
 /* Number of result columns of a variant (PM_V_*) for n states. */
 #define PM_V_PLAIN 0
 #define PM_V_SPARSE 1
@@ -131,6 +145,8 @@ int pm_maketreelistMCMCksmt(const pm_tree* trees, int32_t ntrees, int32_t n, dou
 #define PM_V_KS 4
 #define PM_V_MT 5
 #define PM_V_KSMT 6
+#define PM_V_DIC2S 7
+#define PM_V_DICKS 8
 int32_t pm_ncols(int32_t variant, int32_t n);
 
 /* O(E) replacement of the R helpers pruningwiseedgeorder / makenodelist / myreorder (R/sumstatMCMC.R:1-18):

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-PLAIN, SPARSE, BIGTREE, BF, KS, MT, KSMT, EXP = range(8)
+PLAIN, SPARSE, BIGTREE, BF, KS, MT, KSMT, EXP, DIC2S, DICKS = range(10)
 SEQUENTIAL, KEYED, TABLE = range(3)
 
 

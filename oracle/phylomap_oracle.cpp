@@ -27,6 +27,9 @@
 //   updateks*, recordQks, ...ks ..... :1435-1872  -> Run::update_ks_*, Run::run_ks
 //   mt / ksmt ....................... :2169-2362, :2371-2844 -> Run::run_mt
 //   EXP comparator .................. :81-208, :2877-3051 -> Run::run_exp
+//   DIC chains (2sDICt / ksDICt) .... :3064-3403  -> Run::loglik (PPmakePLD / PPmakePLksD), run_bf / run_ks with dic
+//                                                   (arma::expmat is a Pade scheme in Armadillo; restated here as scaling and
+//                                                   squaring of a Taylor series, accurate to ~1e-15)
 //
 // The "site" axis (tree->S > 1) does not exist in the reference: every site is an independent copy of the
 // reference's chain state sharing Q; row i of the output holds the SUM over sites of the per-site statistics
@@ -46,7 +49,7 @@
 
 namespace orc {
 
-enum Variant { PLAIN = 0, SPARSE = 1, BIGTREE = 2, BF = 3, KS = 4, MT = 5, KSMT = 6, EXPV = 7 };
+enum Variant { PLAIN = 0, SPARSE = 1, BIGTREE = 2, BF = 3, KS = 4, MT = 5, KSMT = 6, EXPV = 7, DIC2S = 8, DICKS = 9 };
 enum RngMode { SEQUENTIAL = 0, KEYED = 1, TABLE = 2 };
 enum SlotKind { K_NODE = 0, K_BRSTATE = 1, K_BREXP = 2 };
 
@@ -425,6 +428,8 @@ struct Run {
     switch (variant) {
       case PLAIN: case SPARSE: case BIGTREE: case EXPV: return n + n * (n - 1);
       case BF: case MT: return n + n * n + 3;
+      case DIC2S: return n + n * n + 4;
+      case DICKS: return n + n * n + 2 + 3 * k + 2;
       default: return n + n * n + 2 + 3 * k + 1;
     }
   }
@@ -433,10 +438,11 @@ struct Run {
     int n = M.n;
     F = Flags();
     F.sparse = (variant == SPARSE);
-    F.normalize = (variant == BIGTREE || variant == BF || variant == KS);
-    F.full_counts = (variant == BF || variant == KS || variant == MT || variant == KSMT);
-    F.redraw_tips = (variant == KS || variant == MT || variant == KSMT);
-    F.parity_tips = (variant == KS || variant == KSMT);
+    const bool bf = (variant == BF || variant == DIC2S), ks = (variant == KS || variant == DICKS);
+    F.normalize = (variant == BIGTREE || bf || ks);
+    F.full_counts = (bf || ks || variant == MT || variant == KSMT);
+    F.redraw_tips = (ks || variant == MT || variant == KSMT);
+    F.parity_tips = (ks || variant == KSMT);
     if (F.sparse) {
       M.Bs.assign((size_t)n * n, 0.0);
       for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) if (M.b(i, j) > 1e-7) M.Bs[i + j * n] = M.b(i, j);
@@ -515,14 +521,90 @@ struct Run {
     }
   }
 
+  // ---- DIC: log p(y | Q) by matrix exponentiation, :3135-3178 (PPmakePLD), :3268-3297 (PPmakePLksD), :3242-3250 ----
+  // exp(A) for a small dense matrix (row-major n x n): scaling and squaring of a degree-20 Taylor series
+  static void expm(const std::vector<double>& A, int n, std::vector<double>& E) {
+    double nrm = 0;
+    for (int i = 0; i < n; i++) { double r = 0; for (int j = 0; j < n; j++) r += std::fabs(A[i * n + j]); nrm = std::max(nrm, r); }
+    int sq = 0;
+    while (nrm > 0.5) { nrm *= 0.5; sq++; }
+    const double sc = std::ldexp(1.0, -sq);
+    std::vector<double> X(n * n), T(n * n, 0.0), N2(n * n);
+    for (int i = 0; i < n * n; i++) X[i] = A[i] * sc;
+    E.assign(n * n, 0.0);
+    for (int i = 0; i < n; i++) { E[i * n + i] = 1.0; T[i * n + i] = 1.0; }
+    for (int k = 1; k <= 20; k++) {
+      for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) {
+        double acc = 0; for (int l = 0; l < n; l++) acc += T[i * n + l] * X[l * n + j];
+        N2[i * n + j] = acc / k;
+      }
+      T = N2;
+      for (int i = 0; i < n * n; i++) E[i] += T[i];
+    }
+    for (int r = 0; r < sq; r++) {
+      for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) {
+        double acc = 0; for (int l = 0; l < n; l++) acc += E[i * n + l] * E[l * n + j];
+        N2[i * n + j] = acc;
+      }
+      E = N2;
+    }
+  }
+  // sum over sites of log( sum_j pid_j PL[root][j] ) + S, with P(t_e) = expm(Q t_e)
+  double loglik(int tree) {
+    const TreeIn& t = trees[tree];
+    int n = M.n;
+    std::vector<double> Qr(n * n), TP((size_t)t.E * n * n), A(n * n), E;
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) Qr[i * n + j] = M.q(i, j);
+    for (int e = 0; e < t.E; e++) {
+      for (int i = 0; i < n * n; i++) A[i] = Qr[i] * t.edge_length[e];
+      expm(A, n, E);
+      std::copy(E.begin(), E.end(), TP.begin() + (size_t)e * n * n);
+    }
+    double total = 0;
+    std::vector<double> PL((size_t)(2 * t.T - 1) * n), x(n), y(n);
+    for (int64_t s = 0; s < t.S; s++) {
+      const int* st = t.states + s * t.T;
+      std::fill(PL.begin(), PL.end(), 0.0);
+      for (int i = 0; i < t.T; i++) {
+        if (!F.parity_tips) PL[(size_t)i * n + (st[i] - 1)] = 1;
+        else {
+          int par = st[i] - 2 * (st[i] / 2);
+          if (par == 0) for (int j = 1; j < n; j += 2) PL[(size_t)i * n + j] = 1;
+          if (par == 1) for (int j = 0; j < n; j += 2) PL[(size_t)i * n + j] = 1;
+        }
+      }
+      double S = 0;
+      for (int i = 0; i < t.T - 1; i++) {
+        int ea = t.nen[2 * i] - 1, eb = t.nen[2 * i + 1] - 1;
+        const double* Pa = &TP[(size_t)ea * n * n]; const double* Pb = &TP[(size_t)eb * n * n];
+        const double* ca = &PL[(size_t)(t.child(ea) - 1) * n]; const double* cb = &PL[(size_t)(t.child(eb) - 1) * n];
+        double sum = 0;
+        double* row = &PL[(size_t)(t.parent(ea) - 1) * n];
+        for (int r = 0; r < n; r++) {
+          double xa = 0, xb = 0;
+          for (int c = 0; c < n; c++) { xa += Pa[r * n + c] * ca[c]; xb += Pb[r * n + c] * cb[c]; }
+          x[r] = xa * xb;
+          sum += x[r];
+        }
+        S += std::log(sum);
+        for (int r = 0; r < n; r++) row[r] = x[r] / sum;
+      }
+      double X = 0;
+      for (int j = 0; j < n; j++) X += PL[(size_t)(t.root - 1) * n + j] * M.pid[j];
+      total += std::log(X) + S;
+    }
+    return total;
+  }
+
   void run_bf(double* out) {
-    int nc = ncols();  // 9
+    int nc = ncols();  // 9 (10 with the log-likelihood column of 2sDICt)
     HostRng H(*this);
     std::vector<double> row(nc);
     for (int i = 0; i < N; i++) {
       std::fill(row.begin(), row.end(), 0.0);
       row[6] = M.q(0, 1); row[7] = M.q(1, 0);
       row[8] = sweep_tree(0, i, row.data());
+      if (variant == DIC2S) row[9] = loglik(0);
       update_2s(row.data(), *H.src, false, false);
       update_2s(row.data(), *H.src, true, false);
       for (int c = 0; c < nc; c++) out[i + (size_t)c * N] = row[c];
@@ -684,6 +766,7 @@ struct Run {
       std::fill(row.begin(), row.end(), 0.0);
       record_ks(row.data());
       row[n + n * n + 2 + 3 * k] = sweep_tree(0, i, row.data());
+      if (variant == DICKS) row[n + n * n + 2 + 3 * k + 1] = loglik(0);
       ks_updates(row.data(), *H.src, false);
       for (int c = 0; c < nc; c++) out[i + (size_t)c * N] = row[c];
       iters_done = i + 1;
@@ -822,8 +905,8 @@ struct Run {
   void run(double* out) {
     switch (variant) {
       case PLAIN: case SPARSE: case BIGTREE: run_fixed(out); break;
-      case BF: run_bf(out); break;
-      case KS: run_ks(out); break;
+      case BF: case DIC2S: run_bf(out); break;
+      case KS: case DICKS: run_ks(out); break;
       case MT: case KSMT: run_mt(out); break;
       case EXPV: run_exp(out); break;
       default: throw std::runtime_error("unknown variant");

@@ -5,7 +5,8 @@ Only the hot path lives here: the CUDA kernels and C ABI (csrc/, include/phyloma
 """
 from . import capi  # noqa: F401
 from .api import (Chain, SPARSEmaketreelistMCMC, SPARSEsumstatMCMC, makenodelist, maketreelistMCMC,  # noqa: F401
-                  maketreelistMCMC_bigtree, maketreelistMCMCbf, maketreelistMCMCks, maketreelistMCMCksmt,
-                  maketreelistMCMCmt, myreorder, pruningwiseedgeorder, sumstatMCMC, sumstatMCMC_bigtree,
-                  sumstatMCMCbf, sumstatMCMCks, sumstatMCMCksmt, sumstatMCMCmt)
+                  maketreelistMCMC2sDICt, maketreelistMCMC_bigtree, maketreelistMCMCbf, maketreelistMCMCks,
+                  maketreelistMCMCksDICt, maketreelistMCMCksmt, maketreelistMCMCmt, myreorder, pruningwiseedgeorder,
+                  sumstatMCMC, sumstatMCMC2sDICt, sumstatMCMC_bigtree, sumstatMCMCbf, sumstatMCMCks, sumstatMCMCksDICt,
+                  sumstatMCMCksmt, sumstatMCMCmt)
 from .tree import PhyloTree  # noqa: F401

@@ -8,6 +8,8 @@ calling the B200 library through its C ABI.
     R/sumstatMCMCks.R:21        sumstatMCMCks(z, Q, pid, Omega, N, prior)
     R/sumstatMCMCmt.R:21        sumstatMCMCmt(treelist, Q, pid, Omega, N, prior)
     R/sumstatMCMCksmt.R:21      sumstatMCMCksmt(treelist, Q, pid, Omega, N, prior)
+    R/sumstatMCMC2sDICt.R       sumstatMCMC2sDICt(z, Q, pid, Omega, N, prior)      -> bf columns + log p(y|Q)
+    R/sumstatMCMCksDICt.R       sumstatMCMCksDICt(z, Q, pid, Omega, N, prior)      -> ks columns + log p(y|Q)
     R/RcppExports.R:4-50        maketreelist*(x, Q, pid, B, Omega, nen, nodelist, root, N[, prior])
 
 Like the reference, the rate-updating samplers rewrite `Q` (and `B` in the maketreelist* forms) IN PLACE; pass
@@ -180,7 +182,8 @@ class Chain:
 _ENTRY = {capi.PM_V_PLAIN: "pm_maketreelistMCMC", capi.PM_V_SPARSE: "pm_SPARSEmaketreelistMCMC",
           capi.PM_V_BIGTREE: "pm_maketreelistMCMC_bigtree", capi.PM_V_BF: "pm_maketreelistMCMCbf",
           capi.PM_V_KS: "pm_maketreelistMCMCks", capi.PM_V_MT: "pm_maketreelistMCMCmt",
-          capi.PM_V_KSMT: "pm_maketreelistMCMCksmt"}
+          capi.PM_V_KSMT: "pm_maketreelistMCMCksmt", capi.PM_V_DIC2S: "pm_maketreelistMCMC2sDICt",
+          capi.PM_V_DICKS: "pm_maketreelistMCMCksDICt"}
 
 
 def _call(variant, x, Q, pid, B, Omega, order, N, prior=None, **opts):
@@ -205,7 +208,7 @@ def _call(variant, x, Q, pid, B, Omega, order, N, prior=None, **opts):
                 capi.ptr(out), err, 512)
     else:
         pr = np.ascontiguousarray(prior, dtype=np.float64)
-        if variant in (capi.PM_V_BF, capi.PM_V_KS):
+        if variant in (capi.PM_V_BF, capi.PM_V_KS, capi.PM_V_DIC2S, capi.PM_V_DICKS):
             rc = fn(C.byref(arr), n, capi.ptr(Qf), capi.ptr(pidc), capi.ptr(Bf), float(Omega), int(N), capi.ptr(pr),
                     len(pr), C.byref(opt), capi.ptr(out), err, 512)
         else:
@@ -234,6 +237,14 @@ def maketreelistMCMCbf(x, Q, pid, B, Omega, nen, nodelist, root, N, prior, **opt
 
 def maketreelistMCMCks(x, Q, pid, B, Omega, nen, nodelist, root, N, prior, **opts):
     return _call(capi.PM_V_KS, x, Q, pid, B, Omega, [(nen, nodelist, root)], N, prior, **opts)
+
+
+def maketreelistMCMC2sDICt(x, Q, pid, B, Omega, nen, nodelist, root, N, prior, **opts):
+    return _call(capi.PM_V_DIC2S, x, Q, pid, B, Omega, [(nen, nodelist, root)], N, prior, **opts)
+
+
+def maketreelistMCMCksDICt(x, Q, pid, B, Omega, nen, nodelist, root, N, prior, **opts):
+    return _call(capi.PM_V_DICKS, x, Q, pid, B, Omega, [(nen, nodelist, root)], N, prior, **opts)
 
 
 def maketreelistMCMCmt(x, Q, pid, B, Omega, nen, nodelist_m, roots, N, prior, **opts):
@@ -289,6 +300,16 @@ def sumstatMCMCbf(z, Q, pid, Omega, N, prior, **opts):
 
 def sumstatMCMCks(z, Q, pid, Omega, N, prior, **opts):
     return _single(maketreelistMCMCks, z, Q, pid, Omega, N, prior, **opts)
+
+
+def sumstatMCMC2sDICt(z, Q, pid, Omega, N, prior, **opts):
+    """R/sumstatMCMC2sDICt.R: the bf chain plus log p(y|Q) in the last column."""
+    return _single(maketreelistMCMC2sDICt, z, Q, pid, Omega, N, prior, **opts)
+
+
+def sumstatMCMCksDICt(z, Q, pid, Omega, N, prior, **opts):
+    """R/sumstatMCMCksDICt.R: the ks chain plus log p(y|Q) in the last column."""
+    return _single(maketreelistMCMCksDICt, z, Q, pid, Omega, N, prior, **opts)
 
 
 def _multi(fn, treelist, Q, pid, Omega, N, prior, **opts):

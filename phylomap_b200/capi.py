@@ -16,7 +16,7 @@ PM_OK, PM_ERR_ARG, PM_ERR_CUDA, PM_ERR_SAMPLE, PM_ERR_CAPACITY, PM_ERR_REPLAY = 
 PM_F64, PM_F32 = 0, 1
 PM_MODE_PRODUCTION, PM_MODE_DETERMINISTIC = 0, 1
 PM_RNG_PHILOX, PM_RNG_TABLE = 0, 1
-PM_V_PLAIN, PM_V_SPARSE, PM_V_BIGTREE, PM_V_BF, PM_V_KS, PM_V_MT, PM_V_KSMT = range(7)
+PM_V_PLAIN, PM_V_SPARSE, PM_V_BIGTREE, PM_V_BF, PM_V_KS, PM_V_MT, PM_V_KSMT, PM_V_DIC2S, PM_V_DICKS = range(9)
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int32)
 
@@ -25,7 +25,7 @@ class PmTree(C.Structure):
     _fields_ = [("n_tips", C.c_int32), ("n_edges", C.c_int32), ("edge", C.c_void_p), ("nen", C.c_void_p),
                 ("nodelist", C.c_void_p), ("root", C.c_int32), ("maps_off", C.c_void_p), ("maps_len", C.c_void_p),
                 ("maps_state", C.c_void_p), ("states", C.c_void_p), ("states_u8", C.c_void_p),
-                ("n_sites", C.c_int64)]
+                ("n_sites", C.c_int64), ("edge_length", C.c_void_p)]
 
 
 class PmOptions(C.Structure):
@@ -39,6 +39,7 @@ class PmOptions(C.Structure):
 
 EXPORTS = ["pm_default_options", "pm_maketreelistMCMC", "pm_SPARSEmaketreelistMCMC", "pm_maketreelistMCMC_bigtree",
            "pm_maketreelistMCMCbf", "pm_maketreelistMCMCks", "pm_maketreelistMCMCmt", "pm_maketreelistMCMCksmt",
+           "pm_maketreelistMCMC2sDICt", "pm_maketreelistMCMCksDICt",
            "pm_ncols", "pm_tree_order", "pm_chain_create", "pm_chain_run", "pm_chain_time_prune",
            "pm_chain_kernel_times", "pm_chain_enable_timing", "pm_chain_get_node_states", "pm_chain_get_piece_counts",
            "pm_chain_get_path", "pm_chain_get_partials", "pm_chain_device_bytes", "pm_chain_destroy",
@@ -69,7 +70,7 @@ def lib():
     for f in ("pm_maketreelistMCMC", "pm_SPARSEmaketreelistMCMC", "pm_maketreelistMCMC_bigtree"):
         getattr(L, f).argtypes = fixed
     rated = [vp, i32, vp, vp, vp, dbl, i32, vp, i32, vp, vp, C.c_char_p, C.c_size_t]
-    for f in ("pm_maketreelistMCMCbf", "pm_maketreelistMCMCks"):
+    for f in ("pm_maketreelistMCMCbf", "pm_maketreelistMCMCks", "pm_maketreelistMCMC2sDICt", "pm_maketreelistMCMCksDICt"):
         getattr(L, f).argtypes = rated
     multi = [vp, i32, i32, vp, vp, vp, dbl, i32, vp, i32, vp, vp, C.c_char_p, C.c_size_t]
     for f in ("pm_maketreelistMCMCmt", "pm_maketreelistMCMCksmt"):

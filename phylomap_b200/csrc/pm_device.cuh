@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #define PM_NMAX 32           // largest state count (generic path)
+#define PM_DIC_NMAX 8        // largest state count of the DIC log-likelihood kernels (2-state and k <= 3 hidden-rate models)
 #define PM_LOCAL_PATH_MAX 64 // largest merged-path capacity per (branch, site)
 #define PM_SMEM_POW 8        // powers of B kept in shared memory (fast mode, NS <= 4)
 // Production arithmetic: smallest value a stored (sum-normalised) partial may take.  Components whose relative weight

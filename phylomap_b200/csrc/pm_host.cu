@@ -25,6 +25,7 @@
 #include "../../include/phylomap_b200.h"
 #include "pm_launch.cuh"
 #include "pm_setup_kernels.cuh"
+#include "pm_loglik.cuh"
 #include "pm_rates.hpp"
 #include "pm_tree.hpp"
 
@@ -135,19 +136,22 @@ void upload(DevBuf& b, const std::vector<T>& v, cudaStream_t st) {
 
 struct Variant {
   int id;
-  bool sparse, normalize, full_counts, redraw_tips, parity_tips, rates, multi, hidden;
+  bool sparse, normalize, full_counts, redraw_tips, parity_tips, rates, multi, hidden, dic, two_state;
 };
 Variant variant_of(int v) {
   Variant r{};
   r.id = v;
+  const bool bf = v == PM_V_BF || v == PM_V_DIC2S, ks = v == PM_V_KS || v == PM_V_DICKS;
   r.sparse = v == PM_V_SPARSE;
-  r.normalize = v == PM_V_BIGTREE || v == PM_V_BF || v == PM_V_KS;
-  r.full_counts = v == PM_V_BF || v == PM_V_KS || v == PM_V_MT || v == PM_V_KSMT;
-  r.redraw_tips = v == PM_V_KS || v == PM_V_MT || v == PM_V_KSMT;
-  r.parity_tips = v == PM_V_KS || v == PM_V_KSMT;
+  r.normalize = v == PM_V_BIGTREE || bf || ks;
+  r.full_counts = bf || ks || v == PM_V_MT || v == PM_V_KSMT;
+  r.redraw_tips = ks || v == PM_V_MT || v == PM_V_KSMT;
+  r.parity_tips = ks || v == PM_V_KSMT;
   r.rates = r.full_counts;
   r.multi = v == PM_V_MT || v == PM_V_KSMT;
-  r.hidden = v == PM_V_KS || v == PM_V_KSMT;
+  r.hidden = ks || v == PM_V_KSMT;
+  r.dic = v == PM_V_DIC2S || v == PM_V_DICKS;
+  r.two_state = bf || v == PM_V_MT;
   return r;
 }
 
@@ -156,7 +160,9 @@ int ncols_of(int variant, int n) {
   switch (variant) {
     case PM_V_PLAIN: case PM_V_SPARSE: case PM_V_BIGTREE: return n + n * (n - 1);
     case PM_V_BF: case PM_V_MT: return n + n * n + 3;
+    case PM_V_DIC2S: return n + n * n + 4;
     case PM_V_KS: case PM_V_KSMT: return n + n * n + 2 + 3 * k + 1;
+    case PM_V_DICKS: return n + n * n + 2 + 3 * k + 2;
   }
   return -1;
 }
@@ -224,6 +230,7 @@ struct TreeDev {
   long long S = 0;
   DevBuf up_entries8, up_entries, up_off, down_entries, down_off, e_parent, e_child, e_len, maps_off, maps_len, cap_off;
   DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, slow_mask, pos1;
+  DevBuf e_len_d, TP, ll_partial;  // DIC samplers: branch lengths in FP64, exp(Q t_e) per branch, block partials of log p(y|Q)
   int mask_words = 0;
   std::vector<int> cap_off_h;
   pm::ChainParams<Real> P;
@@ -247,7 +254,8 @@ struct ChainT : pm_chain {
   bool own_stream = false;
   std::vector<std::unique_ptr<TreeDev<Real>>> trees;
   int jcap = 0;
-  DevBuf model, ppow, cnt, root_out, err_flag, rows, tab_off, tab_u;
+  DevBuf model, ppow, cnt, root_out, err_flag, rows, tab_off, tab_u, q_dev;
+  double* q_h = nullptr;  // pinned: Q row-major, for the DIC log-likelihood
   Real* model_h = nullptr;   // pinned staging: model then ppow
   double* rows_h = nullptr;  // pinned: ntrees * W
   unsigned* err_h = nullptr;
@@ -267,6 +275,7 @@ struct ChainT : pm_chain {
     if (model_h) cudaFreeHost(model_h);
     if (rows_h) cudaFreeHost(rows_h);
     if (err_h) cudaFreeHost(err_h);
+    if (q_h) cudaFreeHost(q_h);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 
@@ -339,6 +348,21 @@ struct ChainT : pm_chain {
     end_timed();
     launches += (exact || iter == 0) ? 4 : 5;
   }
+  // DIC samplers: log p(y | Q) of the current Q into row[n + n*n + 1] (after the sweep: PL is free again)
+  void launch_loglik(TreeDev<Real>& t, double* row) {
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) q_h[(size_t)i * n + j] = Q[i + (size_t)j * n];
+    CK(cudaMemcpyAsync(q_dev.p, q_h, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    const int E = t.sch.E;
+    pm::k_transprob<Real><<<(E + 127) / 128, 128, 0, stream>>>(q_dev.as<double>(), t.e_len_d.template as<double>(), E, n,
+                                                              t.TP.template as<Real>());
+    const int gx = (int)((t.S + 31) / 32);
+    if (NS == 2) pm::k_loglik<Real, 2><<<gx, 256, 0, stream>>>(t.P, t.TP.template as<Real>(), t.ll_partial.template as<double>());
+    else if (NS == 4) pm::k_loglik<Real, 4><<<gx, 256, 0, stream>>>(t.P, t.TP.template as<Real>(), t.ll_partial.template as<double>());
+    else pm::k_loglik<Real, 0><<<gx, 256, 0, stream>>>(t.P, t.TP.template as<Real>(), t.ll_partial.template as<double>());
+    pm::k_reduce_ll<<<1, 256, 0, stream>>>(t.ll_partial.template as<double>(), gx, row + n + n * n + 1);
+    launches += 3;
+  }
+
   template <int NSc, bool EX>
   void launch_prune_t(TreeDev<Real>& t) {
     pm::Sweep<Real, NSc, EX>::prune(t.P, prune_grid(t), prune_smem(t), stream, k1_variant);
@@ -406,8 +430,9 @@ struct ChainT : pm_chain {
     if (ntr < 1) fail(PM_ERR_ARG, "no trees");
     if (Ntot < 0) fail(PM_ERR_ARG, "N must be non-negative");
     if (V.hidden && (n < 4 || (n & 1))) fail(PM_ERR_ARG, "hidden-rate samplers need an even number of states >= 4");
-    if ((variant == PM_V_BF || variant == PM_V_MT) && n != 2) fail(PM_ERR_ARG, "this sampler is 2-state only");
-    const int need_prior = variant == PM_V_BF || variant == PM_V_MT ? 4 : variant == PM_V_KS ? 6 : variant == PM_V_KSMT ? 8 : 0;
+    if (V.two_state && n != 2) fail(PM_ERR_ARG, "this sampler is 2-state only");
+    if (V.dic && n > PM_DIC_NMAX) fail(PM_ERR_ARG, "the DIC samplers support at most %d states", PM_DIC_NMAX);
+    const int need_prior = V.two_state ? 4 : variant == PM_V_KSMT ? 8 : V.hidden ? 6 : 0;
     if (nprior < need_prior || (need_prior && !prior_)) fail(PM_ERR_ARG, "prior needs %d values", need_prior);
     if (need_prior) prior.assign(prior_, prior_ + nprior);
     pid.assign(pid_, pid_ + n);
@@ -417,7 +442,7 @@ struct ChainT : pm_chain {
     if (opt.rng == PM_RNG_TABLE && !exact) fail(PM_ERR_ARG, "the replay table feeds the deterministic mode only");
     if (opt.rng == PM_RNG_TABLE && (opt.site_offset != 0 || opt.allreduce)) fail(PM_ERR_ARG, "replay runs are single-process");
     NS = (n == 2) ? 2 : (n == 4) ? 4 : 0;
-    W = n + n * n + 1;
+    W = n + n * n + 1 + (V.dic ? 1 : 0);
     ncols = ncols_of(variant, n);
 
     // host-only validation of the trees first: malformed input is reported as PM_ERR_ARG even where no device exists
@@ -534,6 +559,14 @@ struct ChainT : pm_chain {
       upload(t->e_parent, t->sch.e_parent, stream);
       upload(t->e_child, t->sch.e_child, stream);
       upload(t->e_len, elen, stream);
+      if (V.dic) {
+        std::vector<double> eld(E);
+        for (int e = 0; e < E; e++) eld[e] = x.edge_length ? x.edge_length[e] : (double)elen[e];
+        if (x.edge_length) for (int e = 0; e < E; e++) if (!(eld[e] >= 0)) fail(PM_ERR_ARG, "tree %d: negative or NA edge.length", ti);
+        upload(t->e_len_d, eld, stream);
+        t->TP.alloc((size_t)E * n * n * sizeof(Real));
+        t->ll_partial.alloc((size_t)((S + 31) / 32) * sizeof(double));
+      }
       upload(t->maps_off, moff, stream);
       upload(t->maps_len, mlen, stream);
       upload(t->cap_off, t->cap_off_h, stream);
@@ -572,6 +605,7 @@ struct ChainT : pm_chain {
     CK(cudaMallocHost((void**)&model_h, (model_elems() + (size_t)jcap * n * n) * sizeof(Real)));
     CK(cudaMallocHost((void**)&rows_h, (size_t)ntrees * W * sizeof(double)));
     CK(cudaMallocHost((void**)&err_h, sizeof(unsigned)));
+    if (V.dic) { CK(cudaMallocHost((void**)&q_h, (size_t)n * n * sizeof(double))); q_dev.alloc((size_t)n * n * sizeof(double)); }
     cnt.alloc((size_t)n * n * sizeof(unsigned long long));
     root_out.alloc(sizeof(int));
     err_flag.alloc(sizeof(unsigned));
@@ -716,6 +750,7 @@ struct ChainT : pm_chain {
       const int it = iters_done;
       if (V.multi && it == 0) (void)g.next();  // the draw before the loop, :2332 / :2810
       for (int j = 0; j < ntrees; j++) launch_sweep(*trees[j], (uint32_t)it, rows.as<double>() + (size_t)j * W);
+      if (V.dic) launch_loglik(*trees[0], rows.as<double>());
       CK(cudaGetLastError());
       if (opt.allreduce) {
         if (opt.allreduce(opt.allreduce_ctx, rows.as<double>(), ntrees * W) != 0) fail(PM_ERR_CUDA, "allreduce callback failed");
@@ -727,7 +762,8 @@ struct ChainT : pm_chain {
         const double* r = rows_h + (size_t)j * W;
         for (int c = 0; c < n + n * n; c++) jodt[j][c] = r[c];
         if (V.hidden) rm.record_hidden(jodt[j].data()); else rm.record_two_state(jodt[j].data());
-        jodt[j][ncols - 1] = r[n + n * n];  // root state of global site 0 (overwritten by the tree index for mt)
+        if (V.dic) { jodt[j][ncols - 2] = r[n + n * n]; jodt[j][ncols - 1] = r[n + n * n + 1]; }
+        else jodt[j][ncols - 1] = r[n + n * n];  // root state of global site 0 (overwritten by the tree index for mt)
       }
       int pick = 0;
       if (V.multi) {  // sampleOnce with equal weights, :2347-2348
@@ -860,7 +896,7 @@ pm_chain* make_chain(int variant, const pm_tree* trees, int ntrees, int n, doubl
   pm_options def;
   if (!opt) { pm_default_options(&def); opt = &def; }
   if (!trees || !Q || !pid || !B) fail(PM_ERR_ARG, "null argument");
-  if (variant < PM_V_PLAIN || variant > PM_V_KSMT) fail(PM_ERR_ARG, "unknown variant");
+  if (variant < PM_V_PLAIN || variant > PM_V_DICKS) fail(PM_ERR_ARG, "unknown variant");
   if (opt->precision == PM_F32) {
     std::unique_ptr<ChainT<float>> c(new ChainT<float>());
     c->create(variant, trees, ntrees, n, Q, pid, B, Omega, prior, nprior, N_total, opt);
@@ -926,6 +962,17 @@ int pm_maketreelistMCMCksmt(const pm_tree* trees, int32_t ntrees, int32_t n, dou
                             double Omega, int32_t N, const double* prior, int32_t nprior, const pm_options* opt,
                             double* out, char* err, size_t errlen) {
   return one_call(PM_V_KSMT, trees, ntrees, n, Q, pid, B, Omega, N, prior, nprior, opt, out, err, errlen);
+}
+
+int pm_maketreelistMCMC2sDICt(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega, int32_t N,
+                              const double* prior, int32_t nprior, const pm_options* opt, double* out, char* err,
+                              size_t errlen) {
+  return one_call(PM_V_DIC2S, x, 1, n, Q, pid, B, Omega, N, prior, nprior, opt, out, err, errlen);
+}
+int pm_maketreelistMCMCksDICt(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega, int32_t N,
+                              const double* prior, int32_t nprior, const pm_options* opt, double* out, char* err,
+                              size_t errlen) {
+  return one_call(PM_V_DICKS, x, 1, n, Q, pid, B, Omega, N, prior, nprior, opt, out, err, errlen);
 }
 
 int pm_tree_order(const int32_t* edge, int32_t n_edges, int32_t n_tips, int32_t* nen, int32_t* nodelist, int32_t* root,

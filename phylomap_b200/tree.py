@@ -108,6 +108,9 @@ class PhyloTree:
         t.edge, t.nen, t.nodelist, t.root = capi.ptr(edge), capi.ptr(nen), capi.ptr(nodelist), int(root)
         t.maps_off, t.maps_len, t.maps_state = capi.ptr(off), capi.ptr(mlen), capi.ptr(mst)
         t.n_sites = st.shape[0]
+        el = np.ascontiguousarray(self.edge_length, dtype=np.float64)
+        keep.append(el)
+        t.edge_length = capi.ptr(el)
         return t, keep
 
     def oracle_dict(self, nen=None, nodelist=None, root=None):

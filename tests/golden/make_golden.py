@@ -73,6 +73,10 @@ def main():
     scales = [rng.uniform(0.7, 1.3, size=zk.E).tolist()]
     out.append(("ksmt_4state", {"variant": "KSMT", "Q": Q4.tolist(), "pid": [0.25] * 4, "Omega": 4.0, "N": 6, "seed": 17,
                                 "prior": cases.PRIOR_KSMT.tolist(), "tree": _tree_json(zk), "extra_tree_scales": scales}))
+    out.append(("dic2s_2state", {"variant": "DIC2S", "Q": cases.Q2.tolist(), "pid": [0.5, 0.5], "Omega": 0.5, "N": 8, "seed": 18,
+                                 "prior": cases.PRIOR_BF.tolist(), "tree": _tree_json(z)}))
+    out.append(("dicks_4state", {"variant": "DICKS", "Q": Q4.tolist(), "pid": [0.25] * 4, "Omega": 4.0, "N": 6, "seed": 19,
+                                 "prior": cases.PRIOR_KS.tolist(), "tree": _tree_json(zk)}))
     for name, case in out:
         rows = run_case(bridge, case)
         with open(os.path.join(HERE, name + ".json"), "w") as f:

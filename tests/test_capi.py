@@ -32,6 +32,8 @@ def test_ncols_layouts():
     assert L.pm_ncols(capi.PM_V_MT, 2) == 9
     assert L.pm_ncols(capi.PM_V_KS, 4) == 4 + 16 + 2 + 3 + 1
     assert L.pm_ncols(capi.PM_V_KSMT, 6) == 6 + 36 + 2 + 6 + 1
+    assert L.pm_ncols(capi.PM_V_DIC2S, 2) == 10        # src/phylomap.cpp:3233
+    assert L.pm_ncols(capi.PM_V_DICKS, 4) == 4 + 16 + 2 + 3 + 2
 
 
 @pytest.mark.parametrize("T,seed", [(2, 1), (3, 2), (17, 3), (200, 4), (3000, 5)])

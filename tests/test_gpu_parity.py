@@ -138,6 +138,64 @@ def test_ks_six_state(oracle):
     _compare_rows(ch.run(), ref, n, int_cols=set(range(n, n + n * n)) | {ref.shape[1] - 1}, tol=1e-7)
 
 
+def _loglik_scipy(z, Q, pid, parity=False):
+    """log p(y | Q) summed over sites: pruning with scipy's expm, independent of both the oracle and the library."""
+    from scipy.linalg import expm
+    T, n = z.T, Q.shape[0]
+    nen, _, root = z.order()
+    st = z.states if z.states.ndim == 2 else z.states[None, :]
+    P = [expm(Q * t) for t in z.edge_length]
+    tot = 0.0
+    for s in range(st.shape[0]):
+        PL = np.zeros((2 * T - 1, n))
+        for i in range(T):
+            if parity:
+                PL[i, (0 if st[s, i] % 2 == 1 else 1)::2] = 1
+            else:
+                PL[i, st[s, i] - 1] = 1
+        S = 0.0
+        for i in range(T - 1):
+            ea, eb = nen[2 * i] - 1, nen[2 * i + 1] - 1
+            v = (P[ea] @ PL[z.edge[ea, 1] - 1]) * (P[eb] @ PL[z.edge[eb, 1] - 1])
+            S += np.log(v.sum())
+            PL[z.edge[ea, 0] - 1] = v / v.sum()
+        tot += np.log(PL[root - 1] @ pid) + S
+    return tot
+
+
+def test_dic_two_state(oracle):
+    """maketreelistMCMC2sDICt: the bf chain + log p(y|Q) by matrix exponentiation (src/phylomap.cpp:3183-3264)."""
+    z = cases.tree2(T=30, S=4, seed=9)
+    N, Om = 25, 0.5
+    orc, ref = _oracle(oracle, oracle.DIC2S, [z], cases.Q2.copy(), cases.PID2, Om, N, prior=cases.PRIOR_BF)
+    got = pb.sumstatMCMC2sDICt(z, np.asfortranarray(cases.Q2.copy()), cases.PID2, Om, N, cases.PRIOR_BF, seed=7, **DET)
+    assert got.shape == (N, 10)
+    _compare_rows(got, ref, 2, int_cols={2, 3, 4, 5, 8}, tol=1e-8)
+    np.testing.assert_allclose(got[:, 9], ref[:, 9], rtol=1e-9)       # bar: 1e-6 relative in FP64
+    for i in (0, 7, N - 1):                                            # and against an independent scipy evaluation
+        Q = np.array([[-got[i, 6], got[i, 6]], [got[i, 7], -got[i, 7]]])
+        np.testing.assert_allclose(got[i, 9], _loglik_scipy(z, Q, cases.PID2), rtol=1e-9)
+    f32 = pb.sumstatMCMC2sDICt(z, np.asfortranarray(cases.Q2.copy()), cases.PID2, Om, 6, cases.PRIOR_BF, seed=7, precision="f32")
+    for i in range(6):                                                 # FP32 production mode: 1e-4 relative
+        Q = np.array([[-f32[i, 6], f32[i, 6]], [f32[i, 7], -f32[i, 7]]])
+        np.testing.assert_allclose(f32[i, 9], _loglik_scipy(z, Q, cases.PID2), rtol=1e-4)
+
+
+def test_dic_hidden_rates(oracle):
+    """maketreelistMCMCksDICt (src/phylomap.cpp:3300-3403): ks chain + log-likelihood with parity tip partials."""
+    Q = cases.q4()
+    z = cases.tree_hidden(Q, T=24, S=3, seed=4, mean_branch=0.5)
+    N, Om = 20, 4.0
+    pid = np.full(4, 0.25)
+    orc, ref = _oracle(oracle, oracle.DICKS, [z], Q.copy(), pid, Om, N, prior=cases.PRIOR_KS)
+    got = pb.sumstatMCMCksDICt(z, np.asfortranarray(Q.copy()), pid, Om, N, cases.PRIOR_KS, seed=7, **DET)
+    n = 4
+    assert got.shape == (N, n + n * n + 2 + 3 + 2)
+    _compare_rows(got[:, :-1], ref[:, :-1], n, int_cols=set(range(n, n + n * n)) | {ref.shape[1] - 2}, tol=1e-7)
+    np.testing.assert_allclose(got[:, -1], ref[:, -1], rtol=1e-8)
+    np.testing.assert_allclose(got[0, -1], _loglik_scipy(z, Q, pid, parity=True), rtol=1e-9)
+
+
 def _tree_set(maker, k, **kw):
     base = maker(seed=11, **kw)
     out = [base]
@@ -228,9 +286,10 @@ def test_golden_vectors():
     sys.path.insert(0, gold)
     import make_golden
     var = {"PLAIN": capi.PM_V_PLAIN, "SPARSE": capi.PM_V_SPARSE, "BIGTREE": capi.PM_V_BIGTREE, "BF": capi.PM_V_BF,
-           "KS": capi.PM_V_KS, "MT": capi.PM_V_MT, "KSMT": capi.PM_V_KSMT}
+           "KS": capi.PM_V_KS, "MT": capi.PM_V_MT, "KSMT": capi.PM_V_KSMT, "DIC2S": capi.PM_V_DIC2S,
+           "DICKS": capi.PM_V_DICKS}
     names = [f for f in sorted(os.listdir(gold)) if f.endswith(".json")]
-    assert len(names) >= 7
+    assert len(names) >= 9
     for name in names:
         g = json.load(open(os.path.join(gold, name)))
         case = g["case"]
@@ -245,7 +304,8 @@ def test_golden_vectors():
                       case["N"], prior=case.get("prior"), seed=case["seed"], **DET)
         got, ref = ch.run(), np.array(g["rows"])
         fixed = case["variant"] in ("PLAIN", "SPARSE", "BIGTREE")
-        ints = set(range(n, ref.shape[1])) if fixed else set(range(n, n + n * n)) | {ref.shape[1] - 1}
+        dic = case["variant"].startswith("DIC")
+        ints = set(range(n, ref.shape[1])) if fixed else set(range(n, n + n * n)) | {ref.shape[1] - (2 if dic else 1)}
         _compare_rows(got, ref, n, ints, tol=1e-7)
 
 

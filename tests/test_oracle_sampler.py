@@ -137,8 +137,33 @@ def test_golden_rows(oracle):
     sys.path.insert(0, GOLD)
     import make_golden
     names = [f for f in sorted(os.listdir(GOLD)) if f.endswith(".json")]
-    assert len(names) >= 7
+    assert len(names) >= 9
     for name in names:
         g = json.load(open(os.path.join(GOLD, name)))
         out = make_golden.run_case(oracle, g["case"])
         np.testing.assert_allclose(out, np.array(g["rows"]), rtol=1e-13, atol=0, err_msg=name)
+
+
+def test_dic_loglik_against_scipy(oracle):
+    """The DIC column (log p(y|Q) by matrix exponentiation, src/phylomap.cpp:3242-3250) against an independent
+    evaluation with scipy.linalg.expm; and it must not disturb the bf chain it rides on."""
+    from scipy.linalg import expm
+    z = cases.tree2(T=14, S=2, seed=5)
+    o, dic = _run(oracle, oracle.DIC2S, z, cases.Q2.copy(), cases.PID2, 0.5, 6, prior=cases.PRIOR_BF, seed=4)
+    _, bf = _run(oracle, oracle.BF, z, cases.Q2.copy(), cases.PID2, 0.5, 6, prior=cases.PRIOR_BF, seed=4)
+    assert np.array_equal(dic[:, :9], bf)
+    nen, _, root = z.order()
+    for i in (0, 5):
+        Q = np.array([[-dic[i, 6], dic[i, 6]], [dic[i, 7], -dic[i, 7]]])
+        tot = 0.0
+        for s in range(2):
+            PL = np.zeros((2 * z.T - 1, 2))
+            PL[np.arange(z.T), z.states[s] - 1] = 1
+            S = 0.0
+            for k in range(z.T - 1):
+                ea, eb = nen[2 * k] - 1, nen[2 * k + 1] - 1
+                v = (expm(Q * z.edge_length[ea]) @ PL[z.edge[ea, 1] - 1]) * (expm(Q * z.edge_length[eb]) @ PL[z.edge[eb, 1] - 1])
+                S += np.log(v.sum())
+                PL[z.edge[ea, 0] - 1] = v / v.sum()
+            tot += np.log(PL[root - 1] @ cases.PID2) + S
+        np.testing.assert_allclose(dic[i, 9], tot, rtol=1e-12)
