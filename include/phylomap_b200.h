@@ -14,6 +14,7 @@
  *   pm_maketreelistMCMCks       <- maketreelistMCMCks       src/phylomap.cpp:1802 (src/RcppExports.cpp:132)
  *   pm_maketreelistMCMCmt       <- maketreelistMCMCmt       src/phylomap.cpp:2267 (src/RcppExports.cpp:159)
  *   pm_maketreelistMCMCksmt     <- maketreelistMCMCksmt     src/phylomap.cpp:2722 (src/RcppExports.cpp:185)
+ *   pm_maketreelistEXP          <- maketreelistEXP          src/phylomap.cpp:3001 (src/RcppExports.cpp:80)
  *   pm_maketreelistMCMC2sDICt   <- maketreelistMCMC2sDICt   src/phylomap.cpp:3183 (src/RcppExports.cpp:211)
  *   pm_maketreelistMCMCksDICt   <- maketreelistMCMCksDICt   src/phylomap.cpp:3300 (src/RcppExports.cpp:237)
  *   pm_tree_order               <- pruningwiseedgeorder / makenodelist / myreorder, R/sumstatMCMC.R:1-18 (O(E) here)
@@ -137,6 +138,13 @@ int pm_maketreelistMCMCksDICt(const pm_tree* x, int32_t n, double* Q, const doub
                               const double* prior, int32_t nprior, const pm_options* opt, double* out, char* err,
                               size_t errlen);
 
+/* The direct sampler with matrix exponentiation, maketreelistEXP (src/phylomap.cpp:3001, src/RcppExports.cpp:80): N
+ * INDEPENDENT histories per site.  lefts / rights / d: eigenvectors, their inverse and diag(eigenvalues) of Q, column-major
+ * n x n as R/sumstatEXP.R:26-31 passes them.  Omega := -min diag(Q) (:3008).  out: [N x (n + n(n-1))] like the fixed-Q samplers.
+ * Production arithmetic only. */
+int pm_maketreelistEXP(const pm_tree* x, int32_t n, double* Q, const double* pid, int32_t N, const double* lefts,
+                       const double* rights, const double* d, const pm_options* opt, double* out, char* err, size_t errlen);
+
 /* Number of result columns of a variant (PM_V_*) for n states. */
 #define PM_V_PLAIN 0
 #define PM_V_SPARSE 1
@@ -147,6 +155,7 @@ int pm_maketreelistMCMCksDICt(const pm_tree* x, int32_t n, double* Q, const doub
 #define PM_V_KSMT 6
 #define PM_V_DIC2S 7
 #define PM_V_DICKS 8
+#define PM_V_EXP 9
 int32_t pm_ncols(int32_t variant, int32_t n);
 
 /* O(E) replacement of the R helpers pruningwiseedgeorder / makenodelist / myreorder (R/sumstatMCMC.R:1-18):

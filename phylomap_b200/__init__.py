@@ -4,9 +4,9 @@ Only the hot path lives here: the CUDA kernels and C ABI (csrc/, include/phyloma
 (capi), the host-side mirror of the reference's R functions (api), and synthetic-input generators (synth).
 """
 from . import capi  # noqa: F401
-from .api import (Chain, SPARSEmaketreelistMCMC, SPARSEsumstatMCMC, makenodelist, maketreelistMCMC,  # noqa: F401
+from .api import (Chain, SPARSEmaketreelistMCMC, SPARSEsumstatMCMC, makenodelist, maketreelistEXP, maketreelistMCMC,  # noqa: F401
                   maketreelistMCMC2sDICt, maketreelistMCMC_bigtree, maketreelistMCMCbf, maketreelistMCMCks,
                   maketreelistMCMCksDICt, maketreelistMCMCksmt, maketreelistMCMCmt, myreorder, pruningwiseedgeorder,
-                  sumstatMCMC, sumstatMCMC2sDICt, sumstatMCMC_bigtree, sumstatMCMCbf, sumstatMCMCks, sumstatMCMCksDICt,
+                  sumstatEXP, sumstatMCMC, sumstatMCMC2sDICt, sumstatMCMC_bigtree, sumstatMCMCbf, sumstatMCMCks, sumstatMCMCksDICt,
                   sumstatMCMCksmt, sumstatMCMCmt)
 from .tree import PhyloTree  # noqa: F401

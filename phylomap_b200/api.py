@@ -8,6 +8,7 @@ calling the B200 library through its C ABI.
     R/sumstatMCMCks.R:21        sumstatMCMCks(z, Q, pid, Omega, N, prior)
     R/sumstatMCMCmt.R:21        sumstatMCMCmt(treelist, Q, pid, Omega, N, prior)
     R/sumstatMCMCksmt.R:21      sumstatMCMCksmt(treelist, Q, pid, Omega, N, prior)
+    R/sumstatEXP.R:21           sumstatEXP(z, Q, pid, N)                           -> independent samples
     R/sumstatMCMC2sDICt.R       sumstatMCMC2sDICt(z, Q, pid, Omega, N, prior)      -> bf columns + log p(y|Q)
     R/sumstatMCMCksDICt.R       sumstatMCMCksDICt(z, Q, pid, Omega, N, prior)      -> ks columns + log p(y|Q)
     R/RcppExports.R:4-50        maketreelist*(x, Q, pid, B, Omega, nen, nodelist, root, N[, prior])
@@ -239,6 +240,26 @@ def maketreelistMCMCks(x, Q, pid, B, Omega, nen, nodelist, root, N, prior, **opt
     return _call(capi.PM_V_KS, x, Q, pid, B, Omega, [(nen, nodelist, root)], N, prior, **opts)
 
 
+def maketreelistEXP(x, Q, pid, nen, nodelist, root, N, lefts, rights, d, **opts):
+    """R/RcppExports.R: maketreelistEXP(x, Q, pid, nen, nodelist, root, N, lefts, rights, d) -> src/phylomap.cpp:3001."""
+    L = capi.lib()
+    t = PhyloTree.from_mapping(x)
+    n = np.asarray(Q).shape[0]
+    Qf = _inplace(Q, n)
+    pidc = np.ascontiguousarray(pid, dtype=np.float64)
+    lf, rf, df = [np.asfortranarray(np.array(m, dtype=np.float64)) for m in (lefts, rights, d)]
+    arr = (capi.PmTree * 1)()
+    arr[0], keep = t.flat(nen, nodelist, root)
+    opts.setdefault("precision", "f64")
+    opt, k2 = _options(**opts)
+    out = np.zeros((int(N), L.pm_ncols(capi.PM_V_EXP, n)), dtype=np.float64, order="F")
+    err = C.create_string_buffer(512)
+    rc = L.pm_maketreelistEXP(C.byref(arr), n, capi.ptr(Qf), capi.ptr(pidc), int(N), capi.ptr(lf), capi.ptr(rf), capi.ptr(df),
+                              C.byref(opt), capi.ptr(out), err, 512)
+    capi.check(rc, err)
+    return out
+
+
 def maketreelistMCMC2sDICt(x, Q, pid, B, Omega, nen, nodelist, root, N, prior, **opts):
     return _call(capi.PM_V_DIC2S, x, Q, pid, B, Omega, [(nen, nodelist, root)], N, prior, **opts)
 
@@ -300,6 +321,14 @@ def sumstatMCMCbf(z, Q, pid, Omega, N, prior, **opts):
 
 def sumstatMCMCks(z, Q, pid, Omega, N, prior, **opts):
     return _single(maketreelistMCMCks, z, Q, pid, Omega, N, prior, **opts)
+
+
+def sumstatEXP(z, Q, pid, N, **opts):
+    """R/sumstatEXP.R:21-33: eigendecompose Q (eigen / solve), then maketreelistEXP."""
+    z = PhyloTree.from_mapping(z)
+    nen, nodelist, root = z.order()
+    w, V = np.linalg.eig(np.asarray(Q, dtype=np.float64))
+    return maketreelistEXP(z, Q, pid, nen, nodelist, root, N, V.real, np.linalg.inv(V).real, np.diag(w.real), **opts)
 
 
 def sumstatMCMC2sDICt(z, Q, pid, Omega, N, prior, **opts):

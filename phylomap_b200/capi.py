@@ -16,7 +16,7 @@ PM_OK, PM_ERR_ARG, PM_ERR_CUDA, PM_ERR_SAMPLE, PM_ERR_CAPACITY, PM_ERR_REPLAY = 
 PM_F64, PM_F32 = 0, 1
 PM_MODE_PRODUCTION, PM_MODE_DETERMINISTIC = 0, 1
 PM_RNG_PHILOX, PM_RNG_TABLE = 0, 1
-PM_V_PLAIN, PM_V_SPARSE, PM_V_BIGTREE, PM_V_BF, PM_V_KS, PM_V_MT, PM_V_KSMT, PM_V_DIC2S, PM_V_DICKS = range(9)
+PM_V_PLAIN, PM_V_SPARSE, PM_V_BIGTREE, PM_V_BF, PM_V_KS, PM_V_MT, PM_V_KSMT, PM_V_DIC2S, PM_V_DICKS, PM_V_EXP = range(10)
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int32)
 
@@ -39,7 +39,7 @@ class PmOptions(C.Structure):
 
 EXPORTS = ["pm_default_options", "pm_maketreelistMCMC", "pm_SPARSEmaketreelistMCMC", "pm_maketreelistMCMC_bigtree",
            "pm_maketreelistMCMCbf", "pm_maketreelistMCMCks", "pm_maketreelistMCMCmt", "pm_maketreelistMCMCksmt",
-           "pm_maketreelistMCMC2sDICt", "pm_maketreelistMCMCksDICt",
+           "pm_maketreelistMCMC2sDICt", "pm_maketreelistMCMCksDICt", "pm_maketreelistEXP",
            "pm_ncols", "pm_tree_order", "pm_chain_create", "pm_chain_run", "pm_chain_time_prune",
            "pm_chain_kernel_times", "pm_chain_enable_timing", "pm_chain_get_node_states", "pm_chain_get_piece_counts",
            "pm_chain_get_path", "pm_chain_get_partials", "pm_chain_device_bytes", "pm_chain_destroy",
@@ -75,6 +75,7 @@ def lib():
     multi = [vp, i32, i32, vp, vp, vp, dbl, i32, vp, i32, vp, vp, C.c_char_p, C.c_size_t]
     for f in ("pm_maketreelistMCMCmt", "pm_maketreelistMCMCksmt"):
         getattr(L, f).argtypes = multi
+    L.pm_maketreelistEXP.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, C.c_char_p, C.c_size_t]
     L.pm_ncols.argtypes = [i32, i32]
     L.pm_tree_order.argtypes = [vp, i32, i32, vp, vp, vp, C.c_char_p, C.c_size_t]
     L.pm_chain_create.argtypes = [i32, vp, i32, i32, vp, vp, vp, dbl, vp, i32, i32, vp, vp, C.c_char_p, C.c_size_t]

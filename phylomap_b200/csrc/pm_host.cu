@@ -26,6 +26,7 @@
 #include "pm_launch.cuh"
 #include "pm_setup_kernels.cuh"
 #include "pm_loglik.cuh"
+#include "pm_exp.cuh"
 #include "pm_rates.hpp"
 #include "pm_tree.hpp"
 
@@ -136,7 +137,7 @@ void upload(DevBuf& b, const std::vector<T>& v, cudaStream_t st) {
 
 struct Variant {
   int id;
-  bool sparse, normalize, full_counts, redraw_tips, parity_tips, rates, multi, hidden, dic, two_state;
+  bool sparse, normalize, full_counts, redraw_tips, parity_tips, rates, multi, hidden, dic, two_state, exp;
 };
 Variant variant_of(int v) {
   Variant r{};
@@ -152,13 +153,14 @@ Variant variant_of(int v) {
   r.hidden = ks || v == PM_V_KSMT;
   r.dic = v == PM_V_DIC2S || v == PM_V_DICKS;
   r.two_state = bf || v == PM_V_MT;
+  r.exp = v == PM_V_EXP;
   return r;
 }
 
 int ncols_of(int variant, int n) {
   const int k = n / 2 - 1;
   switch (variant) {
-    case PM_V_PLAIN: case PM_V_SPARSE: case PM_V_BIGTREE: return n + n * (n - 1);
+    case PM_V_PLAIN: case PM_V_SPARSE: case PM_V_BIGTREE: case PM_V_EXP: return n + n * (n - 1);
     case PM_V_BF: case PM_V_MT: return n + n * n + 3;
     case PM_V_DIC2S: return n + n * n + 4;
     case PM_V_KS: case PM_V_KSMT: return n + n * n + 2 + 3 * k + 1;
@@ -256,6 +258,9 @@ struct ChainT : pm_chain {
   int jcap = 0;
   DevBuf model, ppow, cnt, root_out, err_flag, rows, tab_off, tab_u, q_dev;
   double* q_h = nullptr;  // pinned: Q row-major, for the DIC log-likelihood
+  std::vector<double> own_B;                    // EXP: B = I + Q / Omega is internal (the entry takes no B)
+  std::vector<double> eig_L, eig_R, eig_d;      // EXP: row-major eigenvectors, inverse, eigenvalues
+  DevBuf eig_dev;
   Real* model_h = nullptr;   // pinned staging: model then ppow
   double* rows_h = nullptr;  // pinned: ntrees * W
   unsigned* err_h = nullptr;
@@ -438,6 +443,7 @@ struct ChainT : pm_chain {
     pid.assign(pid_, pid_ + n);
     exact = opt.mode == PM_MODE_DETERMINISTIC;
     if (exact && opt.precision != PM_F64) fail(PM_ERR_ARG, "deterministic mode computes in FP64");
+    if (exact && V.exp) fail(PM_ERR_ARG, "the direct sampler (maketreelistEXP) runs in production arithmetic only");
     if (opt.rng == PM_RNG_TABLE && (!opt.tab_off || !opt.tab_u)) fail(PM_ERR_ARG, "replay table missing");
     if (opt.rng == PM_RNG_TABLE && !exact) fail(PM_ERR_ARG, "the replay table feeds the deterministic mode only");
     if (opt.rng == PM_RNG_TABLE && (opt.site_offset != 0 || opt.allreduce)) fail(PM_ERR_ARG, "replay runs are single-process");
@@ -559,7 +565,7 @@ struct ChainT : pm_chain {
       upload(t->e_parent, t->sch.e_parent, stream);
       upload(t->e_child, t->sch.e_child, stream);
       upload(t->e_len, elen, stream);
-      if (V.dic) {
+      if (V.dic || V.exp) {
         std::vector<double> eld(E);
         for (int e = 0; e < E; e++) eld[e] = x.edge_length ? x.edge_length[e] : (double)elen[e];
         if (x.edge_length) for (int e = 0; e < E; e++) if (!(eld[e] >= 0)) fail(PM_ERR_ARG, "tree %d: negative or NA edge.length", ti);
@@ -572,9 +578,9 @@ struct ChainT : pm_chain {
       upload(t->cap_off, t->cap_off_h, stream);
       t->tipcode.alloc((size_t)T * S);
       t->node_state.alloc((size_t)(2 * T - 1) * S);
-      t->meta.alloc((size_t)E * S * sizeof(uint32_t));
+      if (!V.exp) t->meta.alloc((size_t)E * S * sizeof(uint32_t));
       t->PL.alloc((size_t)(T - 1) * S * n * sizeof(Real));
-      for (int b = 0; b < 2; b++) {
+      for (int b = 0; b < 2 && !V.exp; b++) {
         t->rec_len[b].alloc((size_t)R * S * sizeof(Real));
         t->rec_st[b].alloc((size_t)R * S);
       }
@@ -583,7 +589,7 @@ struct ChainT : pm_chain {
       t->dw_partial.alloc((size_t)2 * t->nblocks * n * sizeof(double));
       CK(cudaMemsetAsync(t->dw_partial.p, 0, t->dw_partial.bytes, stream));
       t->mask_words = (t->chunk + 31) / 32;
-      if (!exact) {
+      if (!exact && !V.exp) {
         t->slow_mask.alloc((size_t)ny * t->mask_words * S * sizeof(uint32_t));
         t->pos1.alloc((size_t)E * S * sizeof(Real));
       }
@@ -594,7 +600,8 @@ struct ChainT : pm_chain {
 
     // table of powers
     jcap = opt.power_capacity > 0 ? opt.power_capacity : 64;
-    if (opt.power_capacity <= 0) {
+    if (V.exp) jcap = 302;  // newunifSample looks at up to 300 jumps (:120)
+    else if (opt.power_capacity <= 0) {
       const double lam = Omega * tmax;
       const double want = lam + 10 * std::sqrt(lam) + 24;
       jcap = (int)std::min(16384.0, std::max(64.0, want));
@@ -690,10 +697,22 @@ struct ChainT : pm_chain {
         CK(cudaStreamSynchronize(stream));
       }
       const long long tot = t.S * E;
-      pm::k_init_meta<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(P.maps_off, t.S, E, P.meta);
+      if (!V.exp) pm::k_init_meta<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(P.maps_off, t.S, E, P.meta);
       CK(cudaGetLastError());
     }
     stage_model(true);
+    if (V.exp) {
+      std::vector<double> eg;
+      eg.insert(eg.end(), eig_L.begin(), eig_L.end());
+      eg.insert(eg.end(), eig_R.begin(), eig_R.end());
+      eg.insert(eg.end(), eig_d.begin(), eig_d.end());
+      upload(eig_dev, eg, stream);
+      TreeDev<Real>& t = *trees[0];
+      const double* g = eig_dev.as<double>();
+      pm::k_transprob_eig<Real><<<(E + 127) / 128, 128, 0, stream>>>(g, g + (size_t)n * n, g + (size_t)2 * n * n,
+                                                                    t.e_len_d.template as<double>(), E, n, t.TP.template as<Real>());
+      CK(cudaGetLastError());
+    }
     check_device_errors();
   }
 
@@ -714,6 +733,35 @@ struct ChainT : pm_chain {
       }
   }
 
+  // ---- direct sampler (maketreelistEXP): independent histories, nothing carried between iterations ----
+  void launch_exp_iteration(TreeDev<Real>& t, uint32_t iter, double* row) {
+    const int gx = (int)((t.S + 31) / 32);
+    Real* TP = t.TP.template as<Real>();
+    double* llp = t.ll_partial.template as<double>();
+    const size_t smem_b = (size_t)4 * n * sizeof(double) + ((size_t)n * n + ((n * n) & 1)) * sizeof(unsigned) + (size_t)n * n * sizeof(Real);
+    begin_timed(0);
+    if (NS == 2) pm::k_loglik<Real, 2><<<gx, 256, 0, stream>>>(t.P, TP, llp);
+    else if (NS == 4) pm::k_loglik<Real, 4><<<gx, 256, 0, stream>>>(t.P, TP, llp);
+    else pm::k_loglik<Real, 0><<<gx, 256, 0, stream>>>(t.P, TP, llp);
+    end_timed();
+    begin_timed(1);
+    if (NS == 2) pm::k_exp_nodes<Real, 2><<<gx, 256, 0, stream>>>(t.P, TP, iter);
+    else if (NS == 4) pm::k_exp_nodes<Real, 4><<<gx, 256, 0, stream>>>(t.P, TP, iter);
+    else pm::k_exp_nodes<Real, 0><<<gx, 256, 0, stream>>>(t.P, TP, iter);
+    end_timed();
+    begin_timed(2);
+    const double* el = t.e_len_d.template as<double>();
+    if (NS == 2) pm::k_exp_branches<Real, 2><<<t.paths_grid, 128, smem_b, stream>>>(t.P, TP, el, (Real)Omega, iter, t.chunk);
+    else if (NS == 4) pm::k_exp_branches<Real, 4><<<t.paths_grid, 128, smem_b, stream>>>(t.P, TP, el, (Real)Omega, iter, t.chunk);
+    else pm::k_exp_branches<Real, 0><<<t.paths_grid, 128, smem_b, stream>>>(t.P, TP, el, (Real)Omega, iter, t.chunk);
+    end_timed();
+    begin_timed(3);
+    pm::k_reduce<<<1, 256, 0, stream>>>(t.dw_partial.template as<double>(), 2 * t.nblocks, n, cnt.as<unsigned long long>(),
+                                        root_out.as<int>(), row, 0);
+    end_timed();
+    launches += 4;
+  }
+
   void run(int count, double* out, int64_t ld) override {
     if (count < 0 || iters_done + count > N_total) fail(PM_ERR_ARG, "cannot run %d more iterations (%d of %d done)", count, iters_done, N_total);
     if (count == 0) return;
@@ -723,7 +771,8 @@ struct ChainT : pm_chain {
       ensure_rows(count);
       TreeDev<Real>& t = *trees[0];
       for (int i = 0; i < count; i++) {
-        launch_sweep(t, (uint32_t)(iters_done + i), rows.as<double>() + (size_t)i * W);
+        if (V.exp) launch_exp_iteration(t, (uint32_t)(iters_done + i), rows.as<double>() + (size_t)i * W);
+        else launch_sweep(t, (uint32_t)(iters_done + i), rows.as<double>() + (size_t)i * W);
         if (opt.progress) { printf("%i \r", iters_done + i); }
       }
       CK(cudaGetLastError());
@@ -891,18 +940,41 @@ template <> void ChainT<double>::launch_prune(TreeDev<double>& t) {
 }
 template <> void ChainT<float>::launch_prune(TreeDev<float>& t) { launch_prune_e<false>(t); }
 
+struct EigenIn { const double* lefts; const double* rights; const double* d; };
+
+template <typename Real>
+void prepare_exp(ChainT<Real>& c, int n, const double* Q, const EigenIn& eg, double*& B, double& Omega) {
+  // Omega := -min diag(Q) (:3008); B = I + Q / Omega is internal; eigen inputs arrive column-major from R
+  double mn = Q[0];
+  for (int i = 1; i < n; i++) mn = std::min(mn, Q[i + (size_t)i * n]);
+  Omega = -mn;
+  c.own_B.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) c.own_B[i + (size_t)j * n] = (i == j ? 1.0 : 0.0) + Q[i + (size_t)j * n] / Omega;
+  B = c.own_B.data();
+  c.eig_L.resize((size_t)n * n); c.eig_R.resize((size_t)n * n); c.eig_d.resize(n);
+  for (int i = 0; i < n; i++) {
+    c.eig_d[i] = eg.d[i + (size_t)i * n];
+    for (int j = 0; j < n; j++) { c.eig_L[(size_t)i * n + j] = eg.lefts[i + (size_t)j * n]; c.eig_R[(size_t)i * n + j] = eg.rights[i + (size_t)j * n]; }
+  }
+}
+
 pm_chain* make_chain(int variant, const pm_tree* trees, int ntrees, int n, double* Q, const double* pid, double* B,
-                     double Omega, const double* prior, int nprior, int N_total, const pm_options* opt) {
+                     double Omega, const double* prior, int nprior, int N_total, const pm_options* opt,
+                     const EigenIn* eg = nullptr) {
   pm_options def;
   if (!opt) { pm_default_options(&def); opt = &def; }
-  if (!trees || !Q || !pid || !B) fail(PM_ERR_ARG, "null argument");
-  if (variant < PM_V_PLAIN || variant > PM_V_DICKS) fail(PM_ERR_ARG, "unknown variant");
+  if (!trees || !Q || !pid || (!B && variant != PM_V_EXP)) fail(PM_ERR_ARG, "null argument");
+  if (variant == PM_V_EXP && (!eg || !eg->lefts || !eg->rights || !eg->d)) fail(PM_ERR_ARG, "the direct sampler needs the eigendecomposition of Q");
+  if (variant == PM_V_EXP && (n < 2 || n > PM_NMAX)) fail(PM_ERR_ARG, "number of states must be in 2..%d", PM_NMAX);
+  if (variant < PM_V_PLAIN || variant > PM_V_EXP) fail(PM_ERR_ARG, "unknown variant");
   if (opt->precision == PM_F32) {
     std::unique_ptr<ChainT<float>> c(new ChainT<float>());
+    if (variant == PM_V_EXP) prepare_exp(*c, n, Q, *eg, B, Omega);
     c->create(variant, trees, ntrees, n, Q, pid, B, Omega, prior, nprior, N_total, opt);
     return c.release();
   }
   std::unique_ptr<ChainT<double>> c(new ChainT<double>());
+  if (variant == PM_V_EXP) prepare_exp(*c, n, Q, *eg, B, Omega);
   c->create(variant, trees, ntrees, n, Q, pid, B, Omega, prior, nprior, N_total, opt);
   return c.release();
 }
@@ -962,6 +1034,16 @@ int pm_maketreelistMCMCksmt(const pm_tree* trees, int32_t ntrees, int32_t n, dou
                             double Omega, int32_t N, const double* prior, int32_t nprior, const pm_options* opt,
                             double* out, char* err, size_t errlen) {
   return one_call(PM_V_KSMT, trees, ntrees, n, Q, pid, B, Omega, N, prior, nprior, opt, out, err, errlen);
+}
+
+int pm_maketreelistEXP(const pm_tree* x, int32_t n, double* Q, const double* pid, int32_t N, const double* lefts,
+                       const double* rights, const double* d, const pm_options* opt, double* out, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!out && N > 0) fail(PM_ERR_ARG, "null output");
+    EigenIn eg{lefts, rights, d};
+    std::unique_ptr<pm_chain> c(make_chain(PM_V_EXP, x, 1, n, Q, pid, nullptr, 0.0, nullptr, 0, N, opt, &eg));
+    c->run(N, out, N);
+  });
 }
 
 int pm_maketreelistMCMC2sDICt(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega, int32_t N,

@@ -135,3 +135,38 @@ def test_ragged_site_counts_and_chunk_edges():
         out = pb.sumstatMCMC_bigtree(z, Q, pid, 2.4, 5, seed=3, precision="f32")
         np.testing.assert_allclose(out[:, :4].sum(1), S * tree.edge_length.sum(), rtol=2e-4)
         assert np.array_equal(out[:, 4:], np.round(out[:, 4:])) and np.all(out[:, 4:] >= 0)
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_direct_sampler_matches_oracle_exp(oracle, precision):
+    """maketreelistEXP on the GPU (independent samples) against the oracle's restatement of it: same distribution of
+    the per-iteration statistics (two-sample KS) and the same means."""
+    Q, pid = cases.jc(4, 0.1), np.full(4, 0.25)
+    z = cases.tree_n(Q, T=30, S=1, seed=3, mean_branch=2.0)
+    N = 4000
+    w, V = np.linalg.eig(Q)
+    eig = (V.real, np.linalg.inv(V).real, np.diag(w.real))
+    ref = oracle.OracleRun(oracle.EXP, [z.oracle_dict()], Q, pid, 0.3, N, rng_mode=oracle.SEQUENTIAL, seed=22, eig=eig).run()
+    got = pb.sumstatEXP(z, Q, pid, N, seed=5, precision=precision)
+    assert got.shape == ref.shape == (N, 16)
+    np.testing.assert_allclose(got[:, :4].sum(1), z.edge_length.sum(), rtol=1e-5)
+    assert np.array_equal(got[:, 4:], np.round(got[:, 4:]))
+    tg, tr = got[:, 4:].sum(1), ref[:, 4:].sum(1)
+    assert stats.ks_2samp(tg, tr).pvalue > 0.01
+    assert stats.ks_2samp(got[:, 0], ref[:, 0]).pvalue > 0.01
+    np.testing.assert_allclose(got[:, 4:].mean(0), ref[:, 4:].mean(0), rtol=0.12, atol=0.02)
+    np.testing.assert_allclose(got[:, :4].mean(0), ref[:, :4].mean(0), rtol=0.02)
+
+
+def test_direct_sampler_and_mcmc_agree_on_the_gpu():
+    """The reference's own cross-check (phylomap_tutorial.Rnw:119-135) at scale, entirely on the GPU: sumstatEXP vs
+    sumstatMCMC, many sites, expected counts within 1 %."""
+    Q, pid = cases.jc(4, 0.1), np.full(4, 0.25)
+    S = 2000
+    z = cases.tree_n(Q, T=100, S=S, seed=2, mean_branch=1.5)
+    ex = pb.sumstatEXP(z, Q, pid, 8, seed=3, precision="f32") / S
+    mc = pb.sumstatMCMC(z, Q, pid, 0.6, 60, seed=4, precision="f32")[20:] / S
+    te, tm = ex[:, 4:].sum(1), mc[:, 4:].sum(1)
+    se = np.sqrt(te.var() / len(te) + tm.var() / 4)
+    assert abs(te.mean() - tm.mean()) < 0.01 * te.mean() + 4 * se
+    np.testing.assert_allclose(ex[:, :4].mean(0), mc[:, :4].mean(0), rtol=0.02)
