@@ -83,8 +83,10 @@ typedef struct pm_options {
   int32_t rng;             /* PM_RNG_PHILOX | PM_RNG_TABLE */
   uint64_t seed;           /* Philox key; host-side rate-update draws use R's Mersenne-Twister set.seed((uint32)seed) */
   int64_t site_offset;     /* global index of local site 0 (site sharding); keys use global site indices */
-  int32_t path_capacity;   /* merged-path segments kept per (branch, site); 0 = default (8) */
-  int32_t power_capacity;  /* initial number of tabulated powers of B; 0 = default (64); grows on demand */
+  int32_t path_capacity;   /* stored path records per (site, branch) on average over a chunk of branches; 0 = sized from the
+                              Poisson tail of the real-jump counts and the initial maps (PM_ERR_CAPACITY asks to raise it) */
+  int32_t power_capacity;  /* number of tabulated powers of B; 0 = sized from Omega x the longest branch (>= 64); beyond
+                              the table the kernels fall back to repeated mat-vecs */
   const int64_t* tab_off;  /* PM_RNG_TABLE: CSR over slots ((tree*S+site)*N+iter)*(2T-1+2E) + slot */
   const double* tab_u;     /*               the uniforms */
   const double* host_tab;  /*               uniforms consumed by the host-side rate updates, in order */

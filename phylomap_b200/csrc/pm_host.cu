@@ -792,7 +792,6 @@ struct ChainT : pm_chain {
     ensure_rows(1);
     pm::host::RateModel rm{n, Q, B, Omega, prior.data()};
     pm::host::UniformSource& g = host_rng();
-    const int k = n / 2 - 1;
     std::vector<double> row(ncols);
     std::vector<std::vector<double>> jodt(ntrees, std::vector<double>(ncols, 0.0));
     for (int i = 0; i < count; i++) {
@@ -829,7 +828,6 @@ struct ChainT : pm_chain {
       iters_done++;
       stage_model(false);
       if (opt.progress) { printf("%i \r", it); }
-      (void)k;
     }
     CK(cudaStreamSynchronize(stream));
     collect_timed();

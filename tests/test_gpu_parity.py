@@ -327,3 +327,16 @@ def test_long_branches_many_pieces(oracle):
     _compare_rows(ch.run(), ref, 2, int_cols={2, 3})
     _compare_state(ch, orc, z, 3, z.E, n_paths=15)
     assert orc.piece_counts().max() > 40
+
+
+def test_medium_tree_many_chunks(oracle):
+    """300 tips x 70 sites, 4 states: several branch chunks per site tile, a partial last site block, record slices
+    shared by many branches — still identical to the oracle in deterministic mode."""
+    Q = cases.q4()
+    z = cases.tree_n(Q, T=300, S=70, seed=12, mean_branch=0.5, segments=3)
+    N, Om = 5, 2.4
+    pid = np.full(4, 0.25)
+    orc, ref = _oracle(oracle, oracle.BIGTREE, [z], Q, pid, Om, N)
+    ch = pb.Chain(capi.PM_V_BIGTREE, z, Q.copy(), pid, Om, N, seed=7, **DET)
+    _compare_rows(ch.run(), ref, 4, int_cols=set(range(4, 16)))
+    _compare_state(ch, orc, z, 70, z.E, n_paths=60)

@@ -170,3 +170,16 @@ def test_direct_sampler_and_mcmc_agree_on_the_gpu():
     se = np.sqrt(te.var() / len(te) + tm.var() / 4)
     assert abs(te.mean() - tm.mean()) < 0.01 * te.mean() + 4 * se
     np.testing.assert_allclose(ex[:, :4].mean(0), mc[:, :4].mean(0), rtol=0.02)
+
+
+def test_record_capacity_overflow_is_reported():
+    """A path with two or more real jumps keeps its runs as records in a per-(site, chunk) slice; when the caller
+    forces the slices too small the sweep must stop with PM_ERR_CAPACITY, not corrupt memory."""
+    Q = np.array([[-1.0, 1.0], [1.0, -1.0]])
+    z = cases.tree2(T=64, S=40, seed=3, mean_branch=6.0)     # ~6 real jumps per branch
+    with pytest.raises(capi.PhylomapError) as e:
+        pb.sumstatMCMC(z, Q, cases.PID2, 2.0, 10, seed=1, precision="f32", path_capacity=1)
+    assert e.value.code == capi.PM_ERR_CAPACITY
+    ok = pb.sumstatMCMC(z, Q, cases.PID2, 2.0, 10, seed=1, precision="f32")  # default sizing copes
+    np.testing.assert_allclose(ok[:, :2].sum(1), 40 * z.edge_length.sum(), rtol=2e-4)
+    assert ok[3:, 2:].mean() > 0.5 * 40 * z.edge_length.sum() * 0.9 / 2
