@@ -12,12 +12,6 @@
 #define PM_DIC_NMAX 8        // largest state count of the DIC log-likelihood kernels (2-state and k <= 3 hidden-rate models)
 #define PM_LOCAL_PATH_MAX 64 // largest merged-path capacity per (branch, site)
 #define PM_SMEM_POW 8        // powers of B kept in shared memory (fast mode, NS <= 4)
-// Production arithmetic: smallest value a stored (sum-normalised) partial may take.  Components whose relative weight
-// is below it can never be drawn in practice, but keeping them positive stops the product of two sibling partials
-// from underflowing to all-zero in FP32 (sibling clades that are each certain of different states, which happens
-// during burn-in from the reference's one-segment initial maps).  Structural zeros still surface through the exact
-// zeros of B^k in the draws.
-#define PM_PARTIAL_FLOOR 1e-18
 
 // device-side error bits (sticky, OR-ed into ChainParams::err_flag)
 #define PM_DE_SAMPLE_NA 1u

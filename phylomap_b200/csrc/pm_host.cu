@@ -269,6 +269,7 @@ struct ChainT : pm_chain {
   std::unique_ptr<pm::host::ReplaySource> replay;
   size_t smem_prune = 0, smem_nodes = 0, smem_paths = 0;
   int rows_cap = 0;
+  bool debug_sync = false; int debug_kernel = 0;
   int k3_variant = 4;   // minimum resident blocks the general path kernel is compiled for (PHYLOMAP_B200_K3H, for tuning)
   int k1_variant = 21;  // production pruning kernel variant (pm_launch_impl.cuh; PHYLOMAP_B200_K1_UNROLL overrides, for tuning)
   struct Timed { cudaEvent_t a, b; int k; };
@@ -389,6 +390,7 @@ struct ChainT : pm_chain {
   void launch_prune(TreeDev<Real>& t);
 
   void begin_timed(int k) {
+    debug_kernel = k;
     if (!timing) return;
     Timed t; t.k = k;
     CK(cudaEventCreate(&t.a)); CK(cudaEventCreate(&t.b));
@@ -396,8 +398,11 @@ struct ChainT : pm_chain {
     timed.push_back(t);
   }
   void end_timed() {
-    if (!timing) return;
-    CK(cudaEventRecord(timed.back().b, stream));
+    if (timing) CK(cudaEventRecord(timed.back().b, stream));
+    if (debug_sync) {  // PHYLOMAP_B200_DEBUG_SYNC=1: stop at the first kernel that raises a device error flag
+      try { check_device_errors(); }
+      catch (Fail& f) { f.msg += " [raised by sweep kernel #" + std::to_string(debug_kernel) + ": 0 prune, 1 nodes, 2 paths, 3 reduce]"; throw; }
+    }
   }
   void collect_timed() {
     for (auto& t : timed) {
@@ -417,7 +422,10 @@ struct ChainT : pm_chain {
     if (f & PM_DE_BAD_STATE) fail(PM_ERR_ARG, "tip states must lie in 1..n");
     if (f & PM_DE_SAMPLE_NA) fail(PM_ERR_SAMPLE, "NAs not allowed in probability");
     if (f & PM_DE_SAMPLE_NEG) fail(PM_ERR_SAMPLE, "Negative probabilities not allowed");
-    if (f & PM_DE_SAMPLE_ZERO) fail(PM_ERR_SAMPLE, "Not enough positive probabilities");
+    if (f & PM_DE_SAMPLE_ZERO)
+      fail(PM_ERR_SAMPLE, opt.precision == PM_F32 ? "Not enough positive probabilities (FP32 partial likelihoods span ~1e-45: on large trees with "
+                                                      "one-piece branches this can be an underflow; precision f64 has the reference's range)"
+                                                    : "Not enough positive probabilities");
     if (f & PM_DE_REPLAY) fail(PM_ERR_REPLAY, "replay table exhausted");
     if (f & PM_DE_PATH_CAP) fail(PM_ERR_CAPACITY, "a branch carries more real jumps than its path capacity; raise pm_options.path_capacity");
     if (f & PM_DE_M_OVERFLOW) fail(PM_ERR_CAPACITY, "more than 65535 pieces on one branch");
@@ -635,6 +643,7 @@ struct ChainT : pm_chain {
     mt.reseed((uint32_t)opt.seed);
     if (const char* v = getenv("PHYLOMAP_B200_K1_UNROLL")) k1_variant = atoi(v);
     if (const char* v = getenv("PHYLOMAP_B200_K3H")) k3_variant = atoi(v);
+    if (const char* v = getenv("PHYLOMAP_B200_DEBUG_SYNC")) debug_sync = v[0] == '1';
 
     // shared-memory sizes
     const int np_fast = exact ? 0 : ((NS == 2 || NS == 4) ? std::min(PM_SMEM_POW, jcap) : 0);
@@ -666,7 +675,7 @@ struct ChainT : pm_chain {
       for (int b = 0; b < 2; b++) { P.rec_len[b] = t.rec_len[b].template as<Real>(); P.rec_st[b] = t.rec_st[b].template as<uint8_t>(); }
       // per-node rescaling (makePLrcpp_bigtree :525) only rescales the weights of each draw: the production
       // arithmetic always applies it (FP32 partials underflow after ~40 tips otherwise); the deterministic mode
-      // follows the variant, underflow included
+      // follows the variant, underflow included.  No floor is applied: structural zeros stay exact.
       P.normalize = V.normalize || !exact; P.full_counts = V.full_counts; P.parity_tips = V.parity_tips;
       P.dw_partial = t.dw_partial.template as<double>(); P.cnt = cnt.as<unsigned long long>();
       P.root_out = root_out.as<int>(); P.err_flag = err_flag.as<unsigned>();

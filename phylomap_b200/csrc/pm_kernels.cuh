@@ -126,9 +126,11 @@ __global__ void __launch_bounds__(256) k_prune(ChainParams<Real> P) {
             Real s = 0;
 #pragma unroll
             for (int j = 0; j < n; j++) s += out[j];
-            const Real inv = (Real)1 / s;
+            // structural zeros must stay zeros (no floor); a product that underflowed altogether becomes the zero
+            // vector and surfaces in the draw as "Not enough positive probabilities", like a NaN would in the reference
+            const Real inv = s > (Real)0 ? (Real)1 / s : (Real)0;
 #pragma unroll
-            for (int j = 0; j < n; j++) out[j] = fmax(out[j] * inv, (Real)PM_PARTIAL_FLOOR);
+            for (int j = 0; j < n; j++) out[j] *= inv;
           }
         }
         VecIO<Real, NS>::store(P.PL + ((long long)(pn - P.T) * S + site) * n, n, out);
@@ -242,9 +244,11 @@ __global__ void __launch_bounds__(256, MINB) k_prune_pipe(ChainParams<Real> P) {
 #pragma unroll
         for (int j = 0; j < NS; j++) { out[j] = nd[u].vb[j] * nd[u].va[j]; s += out[j]; }
         if (normalize) {
-          const Real inv = fast_rcp<Real>(s);
+          // structural zeros must stay zeros (no floor); a product that underflowed altogether becomes the zero
+          // vector and surfaces in the draw as "Not enough positive probabilities", like a NaN would in the reference
+          const Real inv = s > (Real)0 ? fast_rcp<Real>(s) : (Real)0;
 #pragma unroll
-          for (int j = 0; j < NS; j++) out[j] = fmax(out[j] * inv, (Real)PM_PARTIAL_FLOOR);
+          for (int j = 0; j < NS; j++) out[j] *= inv;
         }
         if (active) VecIO<Real, NS>::store(PLs + (long long)(nd[u].pn - T) * rowPL, NS, out);
       }

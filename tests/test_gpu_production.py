@@ -102,7 +102,9 @@ def test_squamate_sized_sparse_run():
     tree = synth.yule_tree(3951, seed=3)
     tree = pb.PhyloTree(tree.edge, tree.edge_length * (87740.48 / tree.edge_length.sum()))
     S = 2048
-    z = synth.simulate_2_state_tree(5, tree, Q, cases.PID2, n_sites=S, device="cuda")
+    # initial maps: every branch in 8 equal pieces (the Squamate set-up script uses 100, R/Squamate_tree_setup.R:54-82);
+    # with the one-piece internal branches of simulate_2_state_tree a 3 951-tip tree underflows even FP64 partials
+    z = synth.simulate_2_state_tree(5, tree, Q, cases.PID2, n_sites=S, device="cuda", segments=8)
     out = pb.SPARSEsumstatMCMC(z, Q, cases.PID2, 0.012, 6, precision="f32", seed=3)
     np.testing.assert_allclose(out[:, :2].sum(1), S * tree.edge_length.sum(), rtol=2e-4)
     assert np.all(out[:, 2:] >= 0)
@@ -183,3 +185,39 @@ def test_record_capacity_overflow_is_reported():
     ok = pb.sumstatMCMC(z, Q, cases.PID2, 2.0, 10, seed=1, precision="f32")  # default sizing copes
     np.testing.assert_allclose(ok[:, :2].sum(1), 40 * z.edge_length.sum(), rtol=2e-4)
     assert ok[3:, 2:].mean() > 0.5 * 40 * z.edge_length.sum() * 0.9 / 2
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_partials_match_exact_pruning_on_peaked_data(precision):
+    """Hidden-rate model with parity tip partials on a large tree: sub-clades are certain of their state, sibling
+    partials multiply numbers like 1e-15 with structural zeros.  The stored partials must equal an exact (FP64, host)
+    pruning for the same jump counts — in particular impossible states must stay at exactly zero.  (Regression: a
+    floor on the stored partials once inflated them to 1e-18, i.e. to 1e-4 of a legitimate 1e-14 competitor.)"""
+    Q, pid = cases.q4(), np.full(4, 0.25)
+    T, S = 3000, 6
+    tree = synth.yule_tree(T, seed=4, mean_branch=0.1 / 1.2)
+    z = synth.simulate_4_state_tree(7, tree, Q, pid, n_sites=S, device="cuda", segments=2)
+    ch = pb.Chain(capi.PM_V_KS, z, np.asfortranarray(Q.copy()), pid, 4.0, 3, prior=cases.PRIOR_KS, precision=precision, seed=3)
+    ch.run(1)
+    m = ch.piece_counts()          # jump counts the next pruning pass will use
+    ch.time_prune(reps=1)          # K1 alone on the current state
+    nen, _, root = z.order()
+    par, chi = z.edge[:, 0] - 1, z.edge[:, 1] - 1
+    B = np.eye(4) + Q / 4.0        # ks proposals are all rejected or tiny in one sweep: rates as recorded in row 0
+    B = np.eye(4) + ch.Q / 4.0
+    pows = [np.linalg.matrix_power(B, k) for k in range(int(m.max()) + 1)]
+    for s in range(S):
+        got = ch.partials(s)
+        PL = np.zeros((2 * T - 1, 4))
+        for i in range(T):
+            PL[i, (0 if z.states[s, i] == 1 else 1)::2] = 1
+        for i in range(T - 1):
+            ea, eb = nen[2 * i] - 1, nen[2 * i + 1] - 1
+            v = (pows[m[s, ea] - 1] @ PL[chi[ea]]) * (pows[m[s, eb] - 1] @ PL[chi[eb]])
+            PL[par[ea]] = v / v.sum()
+        exact = PL[T:]
+        g = got[T:]
+        assert np.all(g[exact == 0] == 0), "structural zeros must stay exact zeros"
+        big = exact > 1e-6
+        np.testing.assert_allclose(g[big], exact[big], rtol=2e-3 if precision == "f32" else 1e-9)
+        assert np.all(g[exact < 1e-30] < 1e-20)
