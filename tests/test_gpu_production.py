@@ -203,8 +203,7 @@ def test_partials_match_exact_pruning_on_peaked_data(precision):
     ch.time_prune(reps=1)          # K1 alone on the current state
     nen, _, root = z.order()
     par, chi = z.edge[:, 0] - 1, z.edge[:, 1] - 1
-    B = np.eye(4) + Q / 4.0        # ks proposals are all rejected or tiny in one sweep: rates as recorded in row 0
-    B = np.eye(4) + ch.Q / 4.0
+    B = np.array(ch.B)             # rewritten in place by the rate update that ended the sweep
     pows = [np.linalg.matrix_power(B, k) for k in range(int(m.max()) + 1)]
     for s in range(S):
         got = ch.partials(s)
