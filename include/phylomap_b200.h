@@ -17,6 +17,7 @@
  *   pm_maketreelistEXP          <- maketreelistEXP          src/phylomap.cpp:3001 (src/RcppExports.cpp:80)
  *   pm_maketreelistMCMC2sDICt   <- maketreelistMCMC2sDICt   src/phylomap.cpp:3183 (src/RcppExports.cpp:211)
  *   pm_maketreelistMCMCksDICt   <- maketreelistMCMCksDICt   src/phylomap.cpp:3300 (src/RcppExports.cpp:237)
+ *   pm_loglik                   <- the pruning loop of make2stateDIC / make4stateDIC(big), R/sourceme.R:141-177, 248-284, 445-516
  *   pm_tree_order               <- pruningwiseedgeorder / makenodelist / myreorder, R/sumstatMCMC.R:1-18 (O(E) here)
  *
  * There is no CPU fallback: every entry fails with PM_ERR_CUDA when no sm_100 device is usable.
@@ -140,6 +141,14 @@ int pm_maketreelistMCMCksDICt(const pm_tree* x, int32_t n, double* Q, const doub
                               const double* prior, int32_t nprior, const pm_options* opt, double* out, char* err,
                               size_t errlen);
 
+/* log p(y | Q) alone, summed over sites (and over ranks when pm_options.allreduce is set): Felsenstein pruning with
+ * P(t_e) = exp(Q edge_length[e]) (maps sums when edge_length is NULL), every node rescaled.  This is the D(Q-hat) term the
+ * R helpers make2stateDIC / make4stateDIC / make{2,4}stateDICbig evaluate with expm() and an R loop over the nodes
+ * (R/sourceme.R:141-177, 248-284, 445-516).  parity_tips != 0: the hidden-rate tip partials (1,0,1,0,..) / (0,1,0,1,..)
+ * of make4stateDIC (:264-267); 0: one-hot tips.  Q column-major n x n, n <= 8; not modified. */
+int pm_loglik(const pm_tree* x, int32_t n, const double* Q, const double* pid, int32_t parity_tips, const pm_options* opt,
+              double* out, char* err, size_t errlen);
+
 /* The direct sampler with matrix exponentiation, maketreelistEXP (src/phylomap.cpp:3001, src/RcppExports.cpp:80): N
  * INDEPENDENT histories per site.  lefts / rights / d: eigenvectors, their inverse and diag(eigenvalues) of Q, column-major
  * n x n as R/sumstatEXP.R:26-31 passes them.  Omega := -min diag(Q) (:3008).  out: [N x (n + n(n-1))] like the fixed-Q samplers.
@@ -175,6 +184,14 @@ int pm_chain_create(int32_t variant, const pm_tree* trees, int32_t ntrees, int32
 /* Run `count` further iterations; rows [first .. first+count) of `out` (column-major, leading dimension ld)
  * are written.  first must equal the number of iterations already done. */
 int pm_chain_run(pm_chain* c, int32_t count, double* out, int64_t ld, char* err, size_t errlen);
+/* Checkpoint / resume (the reference has none: its chain state is lost when the call returns).  The
+ * exported blob holds what the next sweep reads and pm_chain_create does not rebuild: iteration counter, host generator,
+ * current Q and B, node states, jump counts, first positions and run records.  Import into a chain created with the SAME
+ * arguments (trees, sampler, precision, mode, seed, site block); Q and B are written back into the caller's arrays.  A
+ * resumed run continues bit for bit like the uninterrupted one (device uniforms are keyed by (seed, site, sweep, slot)). */
+int64_t pm_chain_state_bytes(pm_chain* c);
+int pm_chain_export_state(pm_chain* c, void* buf, int64_t bytes, char* err, size_t errlen);
+int pm_chain_import_state(pm_chain* c, const void* buf, int64_t bytes, char* err, size_t errlen);
 /* Launch `reps` pruning passes (kernel K1 only) on the current chain state; returns the mean milliseconds per pass
  * measured with CUDA events on the chain's stream.  Does not modify the chain. */
 int pm_chain_time_prune(pm_chain* c, int32_t tree, int32_t reps, float* ms_per_pass, char* err, size_t errlen);

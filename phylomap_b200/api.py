@@ -118,6 +118,21 @@ class Chain:
         self.done += count
         return out
 
+    def export_state(self):
+        """Checkpoint: the chain state as a byte array (pm_chain_export_state)."""
+        L = capi.lib()
+        buf = np.empty(int(L.pm_chain_state_bytes(self.h)), dtype=np.uint8)
+        err = C.create_string_buffer(512)
+        capi.check(L.pm_chain_export_state(self.h, capi.ptr(buf), buf.size, err, 512), err)
+        return buf
+
+    def import_state(self, buf):
+        """Resume from `export_state()` of a chain created with the same arguments; Q and B are restored in place."""
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        err = C.create_string_buffer(512)
+        capi.check(capi.lib().pm_chain_import_state(self.h, capi.ptr(buf), buf.size, err, 512), err)
+        self.done = int(np.frombuffer(buf[:64].tobytes(), dtype=np.int32)[9])  # StateHeader.iters_done
+
     def time_prune(self, reps=10, tree=0):
         ms = C.c_float(0)
         err = C.create_string_buffer(512)
@@ -339,6 +354,62 @@ def sumstatMCMC2sDICt(z, Q, pid, Omega, N, prior, **opts):
 def sumstatMCMCksDICt(z, Q, pid, Omega, N, prior, **opts):
     """R/sumstatMCMCksDICt.R: the ks chain plus log p(y|Q) in the last column."""
     return _single(maketreelistMCMCksDICt, z, Q, pid, Omega, N, prior, **opts)
+
+
+def loglik(z, Q, pid, parity_tips=False, order=None, **opts):
+    """log p(y | Q) summed over the sites of `z` (pm_loglik): pruning with exp(Q t_e) on the GPU."""
+    L = capi.lib()
+    z = PhyloTree.from_mapping(z)
+    n = np.asarray(Q).shape[0]
+    Qf = np.asfortranarray(np.asarray(Q, dtype=np.float64))
+    pidc = np.ascontiguousarray(pid, dtype=np.float64)
+    tree, keep = z.flat(*(order if order is not None else (None, None, None)))
+    opt, keep2 = _options(**opts)
+    out = C.c_double(0.0)
+    err = C.create_string_buffer(512)
+    rc = L.pm_loglik(C.byref(tree), n, capi.ptr(Qf), capi.ptr(pidc), int(bool(parity_tips)), C.byref(opt), C.byref(out), err, 512)
+    capi.check(rc, err)
+    return float(out.value)
+
+
+def _col(mat, name, pos):
+    """Column of a sampler output by the reference's name (a pandas frame) or by its position (a plain matrix)."""
+    if hasattr(mat, "columns"):
+        return np.asarray(mat[name], dtype=np.float64)
+    return np.asarray(mat, dtype=np.float64)[:, pos]
+
+
+def _dic(mat, D):
+    ll = _col(mat, "log(p(y|Q))", -1)
+    pD = np.mean(-2.0 * ll) - D            # R/sourceme.R:169-173
+    return D + 2.0 * pD
+
+
+def make2stateDIC(mat, atree, pid, **opts):
+    """R/sourceme.R:141-177: DIC of the 2-state model from a sumstatMCMC2sDICt trace: D(Q-hat) at the posterior-mean
+    rates (columns l01, l10 = 6, 7) plus 2 pD with pD = mean(-2 log p(y|Q)) - D(Q-hat)."""
+    l01, l10 = _col(mat, "l01", 6).mean(), _col(mat, "l10", 7).mean()
+    Q = np.array([[-l01, l01], [l10, -l10]])
+    return _dic(mat, -2.0 * loglik(atree, Q, pid, parity_tips=False, **opts))
+
+
+def make4stateDIC(mat, atree, pid, **opts):
+    """R/sourceme.R:248-284: the same for the hidden-rate model from a sumstatMCMCksDICt trace (columns l01, l10, k01,
+    k10, gamma = 20..24); tips enter as (1,0,1,0) / (0,1,0,1)."""
+    from .synth import make2sQ
+    r = [_col(mat, nm, 20 + i).mean() for i, nm in enumerate(("l01", "l10", "k01", "k10", "gamma"))]
+    return _dic(mat, -2.0 * loglik(atree, make2sQ(*r), pid, parity_tips=True, **opts))
+
+
+def make2stateDICbig(mat, atree, pid, ne=None, **opts):
+    """R/sourceme.R:445-474: the rescaled ("big tree") form; the GPU pruning always rescales, so this is make2stateDIC
+    with the caller's pruning-wise edge order."""
+    return make2stateDIC(mat, atree, pid, **opts)
+
+
+def make4stateDICbig(mat, atree, pid, ne=None, **opts):
+    """R/sourceme.R:476-516."""
+    return make4stateDIC(mat, atree, pid, **opts)
 
 
 def _multi(fn, treelist, Q, pid, Omega, N, prior, **opts):

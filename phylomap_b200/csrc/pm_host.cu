@@ -137,8 +137,10 @@ void upload(DevBuf& b, const std::vector<T>& v, cudaStream_t st) {
 
 struct Variant {
   int id;
-  bool sparse, normalize, full_counts, redraw_tips, parity_tips, rates, multi, hidden, dic, two_state, exp;
+  bool sparse, normalize, full_counts, redraw_tips, parity_tips, rates, multi, hidden, dic, two_state, exp, llonly;
 };
+// internal ids behind pm_loglik: a chain that only evaluates log p(y | Q) (no path state is allocated)
+enum { V_LOGLIK = 100, V_LOGLIK_PARITY = 101 };
 Variant variant_of(int v) {
   Variant r{};
   r.id = v;
@@ -154,6 +156,7 @@ Variant variant_of(int v) {
   r.dic = v == PM_V_DIC2S || v == PM_V_DICKS;
   r.two_state = bf || v == PM_V_MT;
   r.exp = v == PM_V_EXP;
+  if (v == V_LOGLIK || v == V_LOGLIK_PARITY) { r.llonly = true; r.dic = true; r.normalize = true; r.parity_tips = v == V_LOGLIK_PARITY; }
   return r;
 }
 
@@ -165,6 +168,7 @@ int ncols_of(int variant, int n) {
     case PM_V_DIC2S: return n + n * n + 4;
     case PM_V_KS: case PM_V_KSMT: return n + n * n + 2 + 3 * k + 1;
     case PM_V_DICKS: return n + n * n + 2 + 3 * k + 2;
+    case V_LOGLIK: case V_LOGLIK_PARITY: return 1;
   }
   return -1;
 }
@@ -218,6 +222,10 @@ struct pm_chain {
   virtual void piece_counts(int tree, int32_t* out) = 0;
   virtual int path(int tree, int64_t site, int e, double* len, int32_t* st, int cap) = 0;
   virtual void partials(int tree, int64_t site, double* out) = 0;
+  virtual double loglik() = 0;
+  virtual int64_t state_bytes() = 0;
+  virtual void export_state(void* buf, int64_t bytes) = 0;
+  virtual void import_state(const void* buf, int64_t bytes) = 0;
   double kernel_ms[4] = {0, 0, 0, 0};
   int64_t launches = 0;
   int64_t dev_bytes = 0;
@@ -540,7 +548,8 @@ struct ChainT : pm_chain {
           if (exact || m0 >= 2) init_records += m0;
         }
         long long cap;
-        if (opt.path_capacity > 0) cap = (long long)opt.path_capacity * (b1 - b0);
+        if (V.exp || V.llonly) cap = 4;  // no path state
+        else if (opt.path_capacity > 0) cap = (long long)opt.path_capacity * (b1 - b0);
         else if (exact) {
           const int jumps = poisson_cap(1.5 * Omega * len + 1.0, 1e-18);
           cap = std::max<long long>((long long)(b1 - b0) + jumps, init_records);
@@ -586,9 +595,9 @@ struct ChainT : pm_chain {
       upload(t->cap_off, t->cap_off_h, stream);
       t->tipcode.alloc((size_t)T * S);
       t->node_state.alloc((size_t)(2 * T - 1) * S);
-      if (!V.exp) t->meta.alloc((size_t)E * S * sizeof(uint32_t));
+      if (!V.exp && !V.llonly) t->meta.alloc((size_t)E * S * sizeof(uint32_t));
       t->PL.alloc((size_t)(T - 1) * S * n * sizeof(Real));
-      for (int b = 0; b < 2 && !V.exp; b++) {
+      for (int b = 0; b < 2 && !V.exp && !V.llonly; b++) {
         t->rec_len[b].alloc((size_t)R * S * sizeof(Real));
         t->rec_st[b].alloc((size_t)R * S);
       }
@@ -597,7 +606,7 @@ struct ChainT : pm_chain {
       t->dw_partial.alloc((size_t)2 * t->nblocks * n * sizeof(double));
       CK(cudaMemsetAsync(t->dw_partial.p, 0, t->dw_partial.bytes, stream));
       t->mask_words = (t->chunk + 31) / 32;
-      if (!exact && !V.exp) {
+      if (!exact && !V.exp && !V.llonly) {
         t->slow_mask.alloc((size_t)ny * t->mask_words * S * sizeof(uint32_t));
         t->pos1.alloc((size_t)E * S * sizeof(Real));
       }
@@ -706,7 +715,7 @@ struct ChainT : pm_chain {
         CK(cudaStreamSynchronize(stream));
       }
       const long long tot = t.S * E;
-      if (!V.exp) pm::k_init_meta<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(P.maps_off, t.S, E, P.meta);
+      if (!V.exp && !V.llonly) pm::k_init_meta<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(P.maps_off, t.S, E, P.meta);
       CK(cudaGetLastError());
     }
     stage_model(true);
@@ -925,6 +934,100 @@ struct ChainT : pm_chain {
     records(pos, nj + 1);
     return nj + 1;
   }
+  // ---- checkpoint / resume: everything a sweep reads that is not an input of pm_chain_create ----
+  struct StateHeader {
+    char magic[8];
+    int32_t variant, n, ntrees, precision, mode, T, E, iters_done, jcap, reserved;
+    int64_t S, site_offset, total_bytes;
+    uint64_t seed;
+  };
+  std::vector<DevBuf*> state_buffers() {
+    std::vector<DevBuf*> v{&model, &ppow};
+    for (auto& t : trees) {
+      v.push_back(&t->node_state); v.push_back(&t->meta); v.push_back(&t->pos1);
+      for (int b = 0; b < 2; b++) { v.push_back(&t->rec_len[b]); v.push_back(&t->rec_st[b]); }
+    }
+    return v;
+  }
+  size_t host_state_bytes() const { return sizeof(StateHeader) + 625 * sizeof(uint32_t) + ((size_t)2 * n * n + 2 * n) * sizeof(double); }
+  int64_t state_bytes() override {
+    size_t tot = host_state_bytes();
+    for (DevBuf* b : state_buffers()) tot += (b->bytes + 15) & ~(size_t)15;
+    return (int64_t)tot;
+  }
+  StateHeader make_header() {
+    StateHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "PMB200S", 8);
+    h.variant = V.id; h.n = n; h.ntrees = ntrees; h.precision = opt.precision; h.mode = opt.mode;
+    h.T = trees[0]->sch.T; h.E = trees[0]->sch.E; h.iters_done = iters_done; h.jcap = jcap;
+    h.S = trees[0]->S; h.site_offset = opt.site_offset; h.total_bytes = state_bytes(); h.seed = opt.seed;
+    return h;
+  }
+  void export_state(void* buf, int64_t bytes) override {
+    if (opt.rng == PM_RNG_TABLE) fail(PM_ERR_ARG, "replay-table runs cannot be checkpointed");
+    if (!buf || bytes < state_bytes()) fail(PM_ERR_ARG, "state buffer too small (%lld bytes needed)", (long long)state_bytes());
+    CK(cudaSetDevice(opt.device));
+    CK(cudaStreamSynchronize(stream));
+    unsigned char* p = (unsigned char*)buf;
+    const StateHeader h = make_header();
+    memcpy(p, &h, sizeof h); p += sizeof h;
+    uint32_t w[625]; mt.save(w);
+    memcpy(p, w, sizeof w); p += sizeof w;
+    memcpy(p, Q, (size_t)n * n * sizeof(double)); p += (size_t)n * n * sizeof(double);
+    memcpy(p, B, (size_t)n * n * sizeof(double)); p += (size_t)n * n * sizeof(double);
+    memcpy(p, scale_prev.data(), n * sizeof(double)); p += n * sizeof(double);
+    memcpy(p, rate_prev.data(), n * sizeof(double)); p += n * sizeof(double);
+    for (DevBuf* b : state_buffers()) {
+      if (b->bytes) CK(cudaMemcpyAsync(p, b->p, b->bytes, cudaMemcpyDeviceToHost, stream));
+      p += (b->bytes + 15) & ~(size_t)15;
+    }
+    CK(cudaStreamSynchronize(stream));
+  }
+  void import_state(const void* buf, int64_t bytes) override {
+    if (opt.rng == PM_RNG_TABLE) fail(PM_ERR_ARG, "replay-table runs cannot be checkpointed");
+    if (!buf || bytes < (int64_t)sizeof(StateHeader)) fail(PM_ERR_ARG, "not a chain state");
+    const unsigned char* p = (const unsigned char*)buf;
+    StateHeader h; memcpy(&h, p, sizeof h); p += sizeof h;
+    const StateHeader me = make_header();
+    if (memcmp(h.magic, me.magic, 8) != 0) fail(PM_ERR_ARG, "not a chain state");
+    if (h.variant != me.variant || h.n != me.n || h.ntrees != me.ntrees || h.precision != me.precision || h.mode != me.mode ||
+        h.T != me.T || h.E != me.E || h.S != me.S || h.site_offset != me.site_offset || h.jcap != me.jcap || h.seed != me.seed ||
+        h.total_bytes != me.total_bytes)
+      fail(PM_ERR_ARG, "the state was exported by a chain of a different shape, sampler, precision, seed or site block");
+    if (bytes < h.total_bytes) fail(PM_ERR_ARG, "truncated chain state");
+    if (h.iters_done < 0 || h.iters_done > N_total) fail(PM_ERR_ARG, "the state has %d iterations done, this chain was created for %d", h.iters_done, N_total);
+    CK(cudaSetDevice(opt.device));
+    CK(cudaStreamSynchronize(stream));
+    uint32_t w[625]; memcpy(w, p, sizeof w); p += sizeof w;
+    if (w[624] > 624u) fail(PM_ERR_ARG, "corrupt chain state");
+    mt.load(w);
+    memcpy(Q, p, (size_t)n * n * sizeof(double)); p += (size_t)n * n * sizeof(double);
+    memcpy(B, p, (size_t)n * n * sizeof(double)); p += (size_t)n * n * sizeof(double);
+    memcpy(scale_prev.data(), p, n * sizeof(double)); p += n * sizeof(double);
+    memcpy(rate_prev.data(), p, n * sizeof(double)); p += n * sizeof(double);
+    for (DevBuf* b : state_buffers()) {
+      if (b->bytes) CK(cudaMemcpyAsync(b->p, p, b->bytes, cudaMemcpyHostToDevice, stream));
+      p += (b->bytes + 15) & ~(size_t)15;
+    }
+    CK(cudaStreamSynchronize(stream));
+    iters_done = h.iters_done;
+  }
+
+  // log p(y | Q) of the chain's current Q, summed over the sites of all ranks (pm_loglik)
+  double loglik() override {
+    if (!V.dic) fail(PM_ERR_ARG, "this chain was not created with a log-likelihood column");
+    CK(cudaSetDevice(opt.device));
+    ensure_rows(1);
+    double* row = rows.as<double>();
+    launch_loglik(*trees[0], row);
+    CK(cudaGetLastError());
+    double* cell = row + n + n * n + 1;
+    if (opt.allreduce && opt.allreduce(opt.allreduce_ctx, cell, 1) != 0) fail(PM_ERR_CUDA, "allreduce callback failed");
+    CK(cudaMemcpyAsync(rows_h, cell, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    check_device_errors();
+    return rows_h[0];
+  }
   void partials(int tree, int64_t site, double* out) override {
     TreeDev<Real>& t = *trees.at(tree);
     const int T = t.sch.T;
@@ -967,13 +1070,13 @@ void prepare_exp(ChainT<Real>& c, int n, const double* Q, const EigenIn& eg, dou
 
 pm_chain* make_chain(int variant, const pm_tree* trees, int ntrees, int n, double* Q, const double* pid, double* B,
                      double Omega, const double* prior, int nprior, int N_total, const pm_options* opt,
-                     const EigenIn* eg = nullptr) {
+                     const EigenIn* eg = nullptr, bool internal = false) {
   pm_options def;
   if (!opt) { pm_default_options(&def); opt = &def; }
   if (!trees || !Q || !pid || (!B && variant != PM_V_EXP)) fail(PM_ERR_ARG, "null argument");
   if (variant == PM_V_EXP && (!eg || !eg->lefts || !eg->rights || !eg->d)) fail(PM_ERR_ARG, "the direct sampler needs the eigendecomposition of Q");
   if (variant == PM_V_EXP && (n < 2 || n > PM_NMAX)) fail(PM_ERR_ARG, "number of states must be in 2..%d", PM_NMAX);
-  if (variant < PM_V_PLAIN || variant > PM_V_EXP) fail(PM_ERR_ARG, "unknown variant");
+  if ((variant < PM_V_PLAIN || variant > PM_V_EXP) && !internal) fail(PM_ERR_ARG, "unknown variant");
   if (opt->precision == PM_F32) {
     std::unique_ptr<ChainT<float>> c(new ChainT<float>());
     if (variant == PM_V_EXP) prepare_exp(*c, n, Q, *eg, B, Omega);
@@ -1064,6 +1167,24 @@ int pm_maketreelistMCMCksDICt(const pm_tree* x, int32_t n, double* Q, const doub
   return one_call(PM_V_DICKS, x, 1, n, Q, pid, B, Omega, N, prior, nprior, opt, out, err, errlen);
 }
 
+int pm_loglik(const pm_tree* x, int32_t n, const double* Q, const double* pid, int32_t parity_tips, const pm_options* opt,
+              double* out, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!x || !Q || !pid || !out) fail(PM_ERR_ARG, "null argument");
+    if (n < 2 || n > PM_DIC_NMAX) fail(PM_ERR_ARG, "number of states must be in 2..%d", PM_DIC_NMAX);
+    if (parity_tips && (n & 1)) fail(PM_ERR_ARG, "parity tip partials need an even number of states");
+    // the chain machinery wants a uniformization pair (Omega, B) although the likelihood does not use it
+    std::vector<double> q(Q, Q + (size_t)n * n), b((size_t)n * n, 0.0);
+    double om = 0;
+    for (int i = 0; i < n; i++) om = std::max(om, 2 * std::fabs(q[i + (size_t)i * n]));
+    if (!(om > 0)) om = 1;
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) b[i + (size_t)j * n] = (i == j ? 1.0 : 0.0) + q[i + (size_t)j * n] / om;
+    std::unique_ptr<pm_chain> c(make_chain(parity_tips ? V_LOGLIK_PARITY : V_LOGLIK, x, 1, n, q.data(), pid, b.data(), om, nullptr, 0, 0,
+                                           opt, nullptr, true));
+    *out = c->loglik();
+  });
+}
+
 int pm_tree_order(const int32_t* edge, int32_t n_edges, int32_t n_tips, int32_t* nen, int32_t* nodelist, int32_t* root,
                   char* err, size_t errlen) {
   return guarded(err, errlen, [&] {
@@ -1084,6 +1205,19 @@ int pm_chain_run(pm_chain* c, int32_t count, double* out, int64_t ld, char* err,
   return guarded(err, errlen, [&] {
     if (!c || (!out && count > 0)) fail(PM_ERR_ARG, "null argument");
     c->run(count, out, ld);
+  });
+}
+int64_t pm_chain_state_bytes(pm_chain* c) { return c ? c->state_bytes() : 0; }
+int pm_chain_export_state(pm_chain* c, void* buf, int64_t bytes, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!c) fail(PM_ERR_ARG, "null argument");
+    c->export_state(buf, bytes);
+  });
+}
+int pm_chain_import_state(pm_chain* c, const void* buf, int64_t bytes, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!c) fail(PM_ERR_ARG, "null argument");
+    c->import_state(buf, bytes);
   });
 }
 int pm_chain_time_prune(pm_chain* c, int32_t tree, int32_t reps, float* ms_per_pass, char* err, size_t errlen) {

@@ -934,6 +934,9 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       else if (r < PM_LOCAL_PATH_MAX) { bufL[r] = L; bufS[r] = (uint8_t)s; }
       add_dwell(s, L);
       const Real rate = s_rate_new[s];
+      // the count word of run r is consumed whether or not the run uses it (gap mode, zero rate): the next sweep's
+      // open_run() takes one word per run when it regenerates this path
+      const uint32_t cw = r == 0 ? nA : r == 1 ? nB : cnt_new.next();
       int k = 0;
       if (rate_ok(rate)) {
         const Real lam = PN::mul(rate, L);
@@ -949,7 +952,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
           }
           if (r == 0) gaps0 = true;
         } else {
-          k = poisson_inv<Real>(lam, r == 0 ? nA : r == 1 ? nB : cnt_new.next());
+          k = poisson_inv<Real>(lam, cw);
         }
       }
       if (r == 0) k0 = k;

@@ -44,6 +44,9 @@ class MersenneR : public UniformSource {
     if (1.0 - v <= 0.0) return 1.0 - half_ulp;
     return v;
   }
+  // checkpointing (pm_chain_export_state): 624 state words + the read position
+  void save(uint32_t out[625]) const { for (int i = 0; i < 624; i++) out[i] = state_[i]; out[624] = (uint32_t)pos_; }
+  void load(const uint32_t in[625]) { for (int i = 0; i < 624; i++) state_[i] = in[i]; pos_ = (int)in[624]; }
 
  private:
   static uint32_t twist(uint32_t hi, uint32_t lo, uint32_t far) {

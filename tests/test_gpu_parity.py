@@ -9,7 +9,7 @@ import pytest
 
 import cases
 import phylomap_b200 as pb
-from phylomap_b200 import capi
+from phylomap_b200 import capi, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -194,6 +194,35 @@ def test_dic_hidden_rates(oracle):
     _compare_rows(got[:, :-1], ref[:, :-1], n, int_cols=set(range(n, n + n * n)) | {ref.shape[1] - 2}, tol=1e-7)
     np.testing.assert_allclose(got[:, -1], ref[:, -1], rtol=1e-8)
     np.testing.assert_allclose(got[0, -1], _loglik_scipy(z, Q, pid, parity=True), rtol=1e-9)
+
+
+def test_loglik_and_dic_helpers():
+    """pm_loglik and make{2,4}stateDIC(big) (R/sourceme.R:141-177, 248-284, 445-516): D(Q-hat) at the posterior-mean rates
+    against scipy, DIC = D + 2 pD from a DIC trace."""
+    z = cases.tree2(T=40, S=5, seed=3)
+    for prec, tol in (("f64", 1e-10), ("f32", 1e-4)):
+        np.testing.assert_allclose(pb.loglik(z, cases.Q2, cases.PID2, precision=prec), _loglik_scipy(z, cases.Q2, cases.PID2), rtol=tol)
+    mat = pb.sumstatMCMC2sDICt(z, np.asfortranarray(cases.Q2.copy()), cases.PID2, 0.5, 40, cases.PRIOR_BF, seed=7)
+    Qh = np.array([[-mat[:, 6].mean(), mat[:, 6].mean()], [mat[:, 7].mean(), -mat[:, 7].mean()]])
+    D = -2 * _loglik_scipy(z, Qh, cases.PID2)
+    want = D + 2 * (np.mean(-2 * mat[:, 9]) - D)
+    np.testing.assert_allclose(pb.make2stateDIC(mat, z, cases.PID2), want, rtol=1e-10)
+    np.testing.assert_allclose(pb.make2stateDICbig(mat, z, cases.PID2, z.order()[0]), want, rtol=1e-10)
+    import pandas as pd                      # the reference addresses the columns by name
+    frame = pd.DataFrame(mat, columns=["t0", "t1", "n00", "n01", "n10", "n11", "l01", "l10", "root_state", "log(p(y|Q))"])
+    np.testing.assert_allclose(pb.make2stateDIC(frame, z, cases.PID2), want, rtol=1e-10)
+
+    Q = cases.q4()
+    pid = np.full(4, 0.25)
+    zk = cases.tree_hidden(Q, T=24, S=3, seed=4, mean_branch=0.5)
+    np.testing.assert_allclose(pb.loglik(zk, Q, pid, parity_tips=True), _loglik_scipy(zk, Q, pid, parity=True), rtol=1e-10)
+    mk = pb.sumstatMCMCksDICt(zk, np.asfortranarray(Q.copy()), pid, 4.0, 30, cases.PRIOR_KS, seed=7)
+    Qk = synth.make2sQ(*[mk[:, 20 + i].mean() for i in range(5)])
+    Dk = -2 * _loglik_scipy(zk, Qk, pid, parity=True)
+    np.testing.assert_allclose(pb.make4stateDICbig(mk, zk, pid), Dk + 2 * (np.mean(-2 * mk[:, -1]) - Dk), rtol=1e-10)
+    with pytest.raises(capi.PhylomapError) as ei:
+        pb.loglik(zk, np.zeros((3, 3)), np.full(3, 1 / 3), parity_tips=True)
+    assert ei.value.code == capi.PM_ERR_ARG
 
 
 def _tree_set(maker, k, **kw):

@@ -220,3 +220,68 @@ def test_partials_match_exact_pruning_on_peaked_data(precision):
         big = exact > 1e-6
         np.testing.assert_allclose(g[big], exact[big], rtol=2e-3 if precision == "f32" else 1e-9)
         assert np.all(g[exact < 1e-30] < 1e-20)
+
+
+@pytest.mark.parametrize("what", ["bigtree_f32", "ks_f64", "ksmt_deterministic"])
+def test_checkpoint_resume_continues_bit_for_bit(what):
+    """pm_chain_export_state / import_state: a run cut in two (state exported, chain destroyed, a new chain created from
+    the original inputs and resumed) returns the rows of the uninterrupted run, rate traces included."""
+    N, cut = 14, 6
+    if what == "bigtree_f32":
+        Q = cases.q4()
+        z = cases.tree_n(Q, T=300, S=200, seed=5, mean_branch=1.5, segments=3)   # long branches: records in use
+        mk = lambda Qa: pb.Chain(capi.PM_V_BIGTREE, z, Qa, np.full(4, 0.25), 2.4, N, precision="f32", seed=11)
+    elif what == "ks_f64":
+        Q = cases.q4()
+        z = cases.tree_hidden(Q, T=60, S=40, seed=4, mean_branch=0.5)
+        mk = lambda Qa: pb.Chain(capi.PM_V_KS, z, Qa, np.full(4, 0.25), 4.0, N, prior=cases.PRIOR_KS, precision="f64", seed=11)
+    else:
+        Q = cases.q4()
+        base = cases.tree_hidden(Q, T=20, S=3, seed=4, mean_branch=0.5)
+        trees = [base, pb.PhyloTree(base.edge, base.edge_length * 1.2).with_states(base.states, segments=3)]
+        mk = lambda Qa: pb.Chain(capi.PM_V_KSMT, trees, Qa, np.full(4, 0.25), 4.0, N, prior=cases.PRIOR_KSMT, seed=11,
+                                 mode="deterministic")
+    full = mk(np.asfortranarray(Q.copy())).run(N)
+    Qa = np.asfortranarray(Q.copy())
+    a = mk(Qa)
+    head = a.run(cut)
+    blob = a.export_state()
+    Q_cut, B_cut = np.array(a.Q), np.array(a.B)
+    a.close()
+    Qb = np.asfortranarray(Q.copy())
+    b = mk(Qb)
+    b.import_state(blob)
+    assert b.done == cut
+    np.testing.assert_array_equal(np.array(b.Q), Q_cut)
+    np.testing.assert_array_equal(np.array(b.B), B_cut)
+    tail = b.run(N - cut)
+    np.testing.assert_array_equal(np.vstack([head, tail]), full)
+    # a state of another shape is refused
+    other = pb.Chain(capi.PM_V_BIGTREE, cases.tree_n(cases.q4(), T=10, S=2, seed=1), np.asfortranarray(cases.q4()), np.full(4, 0.25), 2.4, 3)
+    with pytest.raises(capi.PhylomapError) as ei:
+        other.import_state(blob)
+    assert ei.value.code == capi.PM_ERR_ARG
+    with pytest.raises(capi.PhylomapError):
+        other.import_state(np.zeros(16, dtype=np.uint8))
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_many_real_jumps_mixed_gap_and_count_runs(oracle, precision):
+    """Fast-regime 4-state model on long branches: paths with three and more real jumps whose runs mix both ways of
+    drawing virtual jumps (exponential gaps above lambda = 16, Poisson count below).  Regression: a gap-mode run used to
+    skip its count word while the next sweep's regeneration consumed one per run (PM_DE_INCONSISTENT at sweep 2).
+    Posterior of the sufficient statistics against the oracle chain, and a large-S run for the invariants."""
+    Q, pid = cases.q4(), np.full(4, 0.25)
+    z = cases.tree_n(Q, T=10, S=1, seed=5, mean_branch=5.0, segments=3)
+    N, thin, burn = 8000, 10, 500
+    ref = oracle.OracleRun(oracle.PLAIN, [z.oracle_dict()], Q, pid, 2.4, N, rng_mode=oracle.SEQUENTIAL, seed=11).run()[burn::thin]
+    got = pb.sumstatMCMC(z, Q, pid, 2.4, N, seed=5, precision=precision)[burn::thin]
+    np.testing.assert_allclose(got[:, :4].sum(1), z.edge_length.sum(), rtol=1e-5)
+    cols = {"R0": got[:, 0], "R2": got[:, 2], "Ntot": got[:, 4:].sum(1)}
+    refc = {"R0": ref[:, 0], "R2": ref[:, 2], "Ntot": ref[:, 4:].sum(1)}
+    for name in cols:
+        p = stats.ks_2samp(cols[name], refc[name]).pvalue
+        assert p > 0.005, "%s: KS p = %.4f" % (name, p)
+    zz = cases.tree_n(Q, T=300, S=200, seed=5, mean_branch=4.0, segments=2)
+    big = pb.sumstatMCMC_bigtree(zz, Q, pid, 2.4, 12, seed=3, precision=precision)
+    np.testing.assert_allclose(big[:, :4].sum(1), 200 * zz.edge_length.sum(), rtol=1e-4)
