@@ -343,6 +343,9 @@ def sumstatEXP(z, Q, pid, N, **opts):
     z = PhyloTree.from_mapping(z)
     nen, nodelist, root = z.order()
     w, V = np.linalg.eig(np.asarray(Q, dtype=np.float64))
+    if np.iscomplexobj(w) and np.abs(w.imag).max() > 1e-12 * max(1.0, np.abs(w).max()):
+        # R's eigen() would hand complex matrices to maketreelistEXP, whose NumericMatrix arguments reject them
+        raise ValueError("sumstatEXP needs a generator with real eigenvalues (the reference passes eigen(Q) as real matrices)")
     return maketreelistEXP(z, Q, pid, nen, nodelist, root, N, V.real, np.linalg.inv(V).real, np.diag(w.real), **opts)
 
 

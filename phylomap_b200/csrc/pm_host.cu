@@ -435,7 +435,10 @@ struct ChainT : pm_chain {
                                                       "one-piece branches this can be an underflow; precision f64 has the reference's range)"
                                                     : "Not enough positive probabilities");
     if (f & PM_DE_REPLAY) fail(PM_ERR_REPLAY, "replay table exhausted");
-    if (f & PM_DE_PATH_CAP) fail(PM_ERR_CAPACITY, "a branch carries more real jumps than its path capacity; raise pm_options.path_capacity");
+    if (f & PM_DE_JUMP_LIMIT)
+      fail(PM_ERR_CAPACITY, "a branch carries more than 63 state changes at one site (a path holds at most 64 runs); the branch is "
+                            "saturated: rescale the tree or the rates");
+    if (f & PM_DE_PATH_CAP) fail(PM_ERR_CAPACITY, "the run records of a branch chunk overflowed; raise pm_options.path_capacity");
     if (f & PM_DE_M_OVERFLOW) fail(PM_ERR_CAPACITY, "more than 65535 pieces on one branch");
     fail(PM_ERR_CUDA, "inconsistent chain state (device flag %u)", f);
   }

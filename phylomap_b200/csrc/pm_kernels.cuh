@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(128) k_paths(ChainParams<Real> P, uint32_t ite
       const bool skip = (!EXACT) && final_run && nout == 0;  // single-run path: length == t_e, state in meta
       if (!skip) {
         if (wr < cap_c && nout < PM_LOCAL_PATH_MAX) { wr_len[wr] = L; wr_st[wr] = (uint8_t)s; wr++; }
-        else errbits |= PM_DE_PATH_CAP;
+        else errbits |= (nout >= PM_LOCAL_PATH_MAX) ? PM_DE_JUMP_LIMIT : PM_DE_PATH_CAP;
       }
       if (NS > 0) {
 #pragma unroll
@@ -997,7 +997,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     // ... and the second run of a two-run path is what is left after the first (the form the next sweep rebuilds it in)
     emit(nout == 0 ? Le : nout == 1 ? PN::sub(Le, L0) : cur_len, cur_state);
     if (newm > 65535) { errbits |= PM_DE_M_OVERFLOW; newm = 65535; }
-    if (nout > 63) { errbits |= PM_DE_PATH_CAP; nout = 63; }
+    if (nout > 63) { errbits |= PM_DE_JUMP_LIMIT; nout = 63; }
     if (nout == 1) {
       if (k0 == 1) P.pos1[pe] = gaps0 ? gap0 : next_order_stat<Real>((Real)0, Le, 1, nB);
     } else if (nout == 2) P.pos1[pe] = L0;

@@ -1,0 +1,89 @@
+"""Randomised stress run of the production samplers: many small configurations (state count, sampler, tree size, site
+count, branch-length scale, initial segmentation, Omega, precision), a dozen sweeps each, checked through the
+invariants every row must satisfy.  Prints one line per failure and a summary; exit code 1 on any failure.
+
+    python scripts/stress.py [n_configs] [seed]
+"""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np
+import cases
+import phylomap_b200 as pb
+from phylomap_b200 import capi, synth
+
+ncfg = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+fails, done = [], 0
+
+
+def dense_q(n, r):
+    Q = r.uniform(0.02, 0.6, size=(n, n))
+    np.fill_diagonal(Q, 0)
+    np.fill_diagonal(Q, -Q.sum(1))
+    return Q
+
+
+for c in range(ncfg):
+    kind = rng.choice(["plain", "sparse", "bigtree", "bf", "ks", "mt", "ksmt", "dic2", "dicks"])
+    prec = rng.choice(["f32", "f64"])
+    T = int(rng.choice([3, 5, 17, 64, 200, 513]))
+    S = int(rng.choice([1, 7, 33, 129, 300]))
+    mb = float(rng.choice([0.05, 0.3, 1.5, 6.0]))
+    seg = int(rng.choice([2, 3, 5]))
+    N = 10
+    seed = int(rng.integers(1, 1 << 30))
+    desc = dict(kind=kind, prec=prec, T=T, S=S, mean_branch=mb, segments=seg, seed=seed)
+    try:
+        if kind in ("bf", "mt", "dic2"):
+            n, Q, pid = 2, cases.Q2 * float(rng.choice([1, 5])), cases.PID2
+            Om = 2.5 * np.abs(np.diag(Q)).max()
+            tree = synth.yule_tree(T, seed % 1000, mean_branch=mb / np.abs(np.diag(Q)).max() * 0.1)
+            z = synth.simulate_2_state_tree(seed, tree, Q, pid, n_sites=S, segments=seg)
+        elif kind in ("ks", "ksmt", "dicks"):
+            n = int(rng.choice([4, 6]))
+            Q, pid = (cases.q4() if n == 4 else cases.q6()), np.full(n, 1.0 / n)
+            Om = 1.2 * np.abs(np.diag(Q)).max() * float(rng.choice([1, 2]))
+            tree = synth.yule_tree(T, seed % 1000, mean_branch=mb)
+            z = synth.simulate_4_state_tree(seed, tree, Q, pid, n_sites=S, segments=max(seg, 3))
+        else:
+            n = int(rng.choice([2, 3, 4, 5, 8]))
+            Q, pid = dense_q(n, rng), np.full(n, 1.0 / n)
+            Om = np.abs(np.diag(Q)).max() * float(rng.choice([1.0, 1.5, 3.0]))
+            tree = synth.yule_tree(T, seed % 1000, mean_branch=mb)
+            st = synth.simulate_tip_states(tree, Q, pid, S, seed).numpy()
+            z = tree.with_states(st[0].astype(np.int32) if S == 1 else st, segments=seg)
+        Qf = np.asfortranarray(Q.copy())
+        tl = z.edge_length.sum()
+        if kind == "plain": out = pb.sumstatMCMC(z, Qf, pid, Om, N, precision=prec, seed=seed)
+        elif kind == "sparse": out = pb.SPARSEsumstatMCMC(z, Qf, pid, Om, N, precision=prec, seed=seed)
+        elif kind == "bigtree": out = pb.sumstatMCMC_bigtree(z, Qf, pid, Om, N, precision=prec, seed=seed)
+        elif kind == "bf": out = pb.sumstatMCMCbf(z, Qf, pid, Om, N, cases.PRIOR_BF, precision=prec, seed=seed)
+        elif kind == "dic2": out = pb.sumstatMCMC2sDICt(z, Qf, pid, Om, N, cases.PRIOR_BF, precision=prec, seed=seed)
+        elif kind == "ks": out = pb.sumstatMCMCks(z, Qf, pid, Om, N, cases.PRIOR_KS if n == 4 else np.array([1., 10, 2, 10, 20, 2]), precision=prec, seed=seed)
+        elif kind == "dicks": out = pb.sumstatMCMCksDICt(z, Qf, pid, Om, N, cases.PRIOR_KS, precision=prec, seed=seed)
+        else:
+            trees = [z, pb.PhyloTree(z.edge, z.edge_length * 1.3).with_states(z.states, segments=max(seg, 3))]
+            tl = None
+            if kind == "mt": out = pb.sumstatMCMCmt(trees, Qf, pid, Om, N, cases.PRIOR_BF, precision=prec, seed=seed)
+            else: out = pb.sumstatMCMCksmt(trees, Qf, pid, Om, N, cases.PRIOR_KSMT, precision=prec, seed=seed)
+        assert np.all(np.isfinite(out)), "non-finite output"
+        if tl is not None:
+            np.testing.assert_allclose(out[:, :n].sum(1), S * tl, rtol=3e-4 if prec == "f32" else 1e-9)
+        ncnt = n * (n - 1) if kind in ("plain", "sparse", "bigtree") else n * n
+        cnt = out[:, n:n + ncnt]
+        assert np.all(cnt >= 0) and np.all(cnt == np.round(cnt)), "counts"
+        done += 1
+    except capi.PhylomapError as e:
+        # the reference's own data-dependent failure (sparse generator + an impossible initial map) is not a defect
+        saturated = e.code == capi.PM_ERR_CAPACITY and "63 state changes" in e.msg and mb >= 6.0
+        if saturated or (e.code == capi.PM_ERR_SAMPLE and kind in ("ks", "ksmt", "dicks")):
+            done += 1
+            desc["note"] = "saturated branch" if saturated else "PM_ERR_SAMPLE"
+            print("note", json.dumps(desc), e.msg[:50], flush=True)
+        else:
+            fails.append(desc); print("FAIL", json.dumps(desc), e.msg[:100], flush=True)
+    except AssertionError as e:
+        fails.append(desc); print("FAIL", json.dumps(desc), str(e)[:200].replace("\n", " "), flush=True)
+print("configs", ncfg, "ok", done, "failed", len(fails))
+sys.exit(1 if fails else 0)

@@ -144,3 +144,13 @@ def test_malformed_inputs_are_reported_before_any_device_work():
     with pytest.raises(capi.PhylomapError) as e:                                         # prior too short
         pb.sumstatMCMCks(cases.tree_hidden(cases.q4(), T=6), cases.q4(), np.full(4, .25), 4.0, 2, [1.0, 2.0])
     assert e.value.code == capi.PM_ERR_ARG
+
+
+def test_sumstatEXP_rejects_complex_spectrum():
+    """R/sumstatEXP.R:26-29 passes eigen(Q) as real matrices; a generator with complex eigenvalues cannot be expressed."""
+    import phylomap_b200 as pb
+    from phylomap_b200 import synth
+    Q = np.array([[-1.0, 1.0, 0.0], [0.0, -1.0, 1.0], [1.0, 0.0, -1.0]])   # cyclic: eigenvalues -1.5 +- 0.87i
+    t = synth.yule_tree(4, 1).with_states(np.array([1, 2, 3, 1], dtype=np.int32))
+    with pytest.raises(ValueError):
+        pb.sumstatEXP(t, Q, np.full(3, 1 / 3), 2)

@@ -185,6 +185,12 @@ def test_record_capacity_overflow_is_reported():
     ok = pb.sumstatMCMC(z, Q, cases.PID2, 2.0, 10, seed=1, precision="f32")  # default sizing copes
     np.testing.assert_allclose(ok[:, :2].sum(1), 40 * z.edge_length.sum(), rtol=2e-4)
     assert ok[3:, 2:].mean() > 0.5 * 40 * z.edge_length.sum() * 0.9 / 2
+    # a saturated branch (more than 63 state changes at one site) is reported as such, in both arithmetic modes
+    zs = cases.tree2(T=6, S=8, seed=3, mean_branch=150.0)
+    for kw in (dict(precision="f32"), dict(mode="deterministic")):
+        with pytest.raises(capi.PhylomapError) as e:
+            pb.sumstatMCMC(zs, Q, cases.PID2, 2.0, 10, seed=1, **kw)
+        assert e.value.code == capi.PM_ERR_CAPACITY and "63" in e.value.msg
 
 
 @pytest.mark.parametrize("precision", ["f32", "f64"])
@@ -285,3 +291,32 @@ def test_many_real_jumps_mixed_gap_and_count_runs(oracle, precision):
     zz = cases.tree_n(Q, T=300, S=200, seed=5, mean_branch=4.0, segments=2)
     big = pb.sumstatMCMC_bigtree(zz, Q, pid, 2.4, 12, seed=3, precision=precision)
     np.testing.assert_allclose(big[:, :4].sum(1), 200 * zz.edge_length.sum(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_random_models_against_oracle_chain(oracle, case):
+    """Randomly drawn models (state count, dense generator, Omega, tree size, branch-length scale, sampler, precision):
+    the production chain and the oracle chain must sample the same posterior of dwell times and jump counts.  Fixed
+    seeds, so the outcome is deterministic."""
+    rng = np.random.default_rng(1000 + case)
+    n = int(rng.choice([2, 3, 5]))
+    Q = rng.uniform(0.05, 0.5, size=(n, n))
+    np.fill_diagonal(Q, 0)
+    np.fill_diagonal(Q, -Q.sum(1))
+    pid = np.full(n, 1.0 / n)
+    Om = np.abs(np.diag(Q)).max() * float(rng.choice([1.0, 1.7, 4.0]))
+    T = int(rng.choice([4, 9]))
+    mb = float(rng.choice([0.3, 2.0, 10.0])) / np.abs(np.diag(Q)).max()   # expected changes per branch: 0.3 .. 10
+    variant, fn = [(oracle.PLAIN, pb.sumstatMCMC), (oracle.SPARSE, pb.SPARSEsumstatMCMC), (oracle.BIGTREE, pb.sumstatMCMC_bigtree)][case % 3]
+    precision = ["f32", "f64"][case % 2]
+    z = cases.tree_n(Q, T=T, S=1, seed=40 + case, mean_branch=mb, segments=[None, 3][int(rng.integers(2))])  # None: the reference's initial maps
+    N, thin, burn = 9000, 9, 450
+    ref = oracle.OracleRun(variant, [z.oracle_dict()], Q, pid, Om, N, rng_mode=oracle.SEQUENTIAL, seed=7 + case).run()[burn::thin]
+    got = fn(z, Q, pid, Om, N, seed=70 + case, precision=precision)[burn::thin]
+    np.testing.assert_allclose(got[:, :n].sum(1), z.edge_length.sum(), rtol=1e-5)
+    checks = {"R0": (got[:, 0], ref[:, 0]), "R_last": (got[:, n - 1], ref[:, n - 1]),
+              "N_first": (got[:, n], ref[:, n]), "N_total": (got[:, n:].sum(1), ref[:, n:].sum(1))}
+    for name, (a, b) in checks.items():
+        # a dwell time has an atom at "no change anywhere": equal up to summation order, so compare on a 1e-7 grid
+        p = stats.ks_2samp(np.round(a, 7), np.round(b, 7)).pvalue
+        assert p > 0.002, "case %d (n=%d T=%d Omega=%.2f mean_branch=%.2f %s): %s KS p = %.5f" % (case, n, T, Om, mb, precision, name, p)
