@@ -238,6 +238,8 @@ template <typename Real>
 struct TreeDev {
   pm::host::Schedule sch;
   long long S = 0;
+  DevBuf cl_entries, cl_warp_off, cl_top_entries, cl_top_off;  // clade schedule of the production pruning kernel
+  int n_cl_top_levels = 0;
   DevBuf up_entries8, up_entries, up_off, down_entries, down_off, e_parent, e_child, e_len, maps_off, maps_len, cap_off;
   DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, slow_mask, pos1;
   DevBuf e_len_d, TP, ll_partial;  // DIC samplers: branch lengths in FP64, exp(Q t_e) per branch, block partials of log p(y|Q)
@@ -279,7 +281,7 @@ struct ChainT : pm_chain {
   int rows_cap = 0;
   bool debug_sync = false; int debug_kernel = 0;
   int k3_variant = 4;   // minimum resident blocks the general path kernel is compiled for (PHYLOMAP_B200_K3H, for tuning)
-  int k1_variant = 21;  // production pruning kernel variant (pm_launch_impl.cuh; PHYLOMAP_B200_K1_UNROLL overrides, for tuning)
+  int k1_variant = 42;  // production pruning kernel variant (pm_launch_impl.cuh; PHYLOMAP_B200_K1_UNROLL overrides, for tuning)
   struct Timed { cudaEvent_t a, b; int k; };
   std::vector<Timed> timed;
 
@@ -580,6 +582,41 @@ struct ChainT : pm_chain {
         upload(t->up_entries8, e8, stream);
       }
       upload(t->up_off, t->sch.up_off, stream);
+      if (!exact && (NS == 2 || NS == 4)) {
+        // clades of ~1/64 of the tree: ~8 per warp to balance, and only ~100 nodes left above them
+        int clade_max = std::max(8, std::min(512, (T - 1) / 64));
+        if (const char* v = getenv("PHYLOMAP_B200_CLADE")) clade_max = std::max(1, atoi(v));
+        pm::host::CladeSchedule cs;
+        pm::host::build_clade_schedule(t->sch, 8, clade_max, cs);
+        // phase-1 entries as byte offsets (PM_CLADE_ENTRY_INTS ints each): the kernel only adds them to per-lane bases
+        const int n1 = cs.warp_off.back();
+        std::vector<int> e16((size_t)PM_CLADE_ENTRY_INTS * std::max(n1, 1), 0);
+        auto put64 = [](int* dst, long long v) { dst[0] = (int)(unsigned)(v & 0xffffffffLL); dst[1] = (int)(v >> 32); };
+        const long long rowPL = (long long)S * n * (long long)sizeof(Real);
+        for (int i = 0; i < n1; i++) {
+          const int* en = &cs.entries[(size_t)8 * i];
+          int* o = &e16[(size_t)PM_CLADE_ENTRY_INTS * i];
+          const int pn = en[0], a = en[1], ea = en[2], b = en[3], eb = en[4];
+          int fl = en[5] & 3;
+          const int x = (en[5] & 4) ? a : (en[5] & 8) ? b : -1;
+          if (a < T) fl |= 16;
+          if (b < T) fl |= 32;
+          put64(o + 0, (long long)(pn - T) * rowPL);
+          put64(o + 2, x >= 0 ? (long long)(x - T) * rowPL : -1LL);
+          put64(o + 4, (long long)ea * S * 4);
+          put64(o + 6, (long long)eb * S * 4);
+          put64(o + 8, a < T ? (long long)a * S : -1LL);
+          put64(o + 10, b < T ? (long long)b * S : -1LL);
+          o[12] = fl;
+        }
+        std::vector<int> top(cs.entries.begin() + (size_t)8 * n1, cs.entries.end());
+        for (int& v : cs.top_off) v -= n1;
+        upload(t->cl_entries, e16, stream);
+        upload(t->cl_warp_off, cs.warp_off, stream);
+        upload(t->cl_top_entries, top, stream);
+        upload(t->cl_top_off, cs.top_off, stream);
+        t->n_cl_top_levels = (int)cs.top_off.size() - 1;
+      }
       upload(t->down_entries, t->sch.down_entries, stream);
       upload(t->down_off, t->sch.down_off, stream);
       upload(t->e_parent, t->sch.e_parent, stream);
@@ -676,6 +713,9 @@ struct ChainT : pm_chain {
       P.up_entries = t.up_entries.template as<int>(); P.up_off = t.up_off.template as<int>();
       P.up_entries8 = t.up_entries8.template as<int>();
       P.n_up_levels = (int)t.sch.up_off.size() - 1;
+      P.cl_entries = t.cl_entries.template as<int>(); P.cl_warp_off = t.cl_warp_off.template as<int>();
+      P.cl_top_entries = t.cl_top_entries.template as<int>();
+      P.cl_top_off = t.cl_top_off.template as<int>(); P.n_cl_top_levels = t.n_cl_top_levels;
       P.down_entries = t.down_entries.template as<int>(); P.down_off = t.down_off.template as<int>();
       P.n_down_levels = (int)t.sch.down_off.size() - 1;
       P.e_parent = t.e_parent.template as<int>(); P.e_child = t.e_child.template as<int>();

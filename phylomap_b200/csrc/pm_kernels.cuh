@@ -35,6 +35,8 @@ struct ChainParams {
   int jcap;
   const int* up_entries; const int* up_off; int n_up_levels;        // 5 ints per internal node: parent, a, ea, b, eb
   const int* up_entries8;  // the same entries padded to 8 ints (two 16-byte loads)
+  // clade schedule of k_prune_clade (pm_tree.hpp): 8 ints per node, per-warp sequences then the top levels
+  const int* cl_entries; const int* cl_warp_off; const int* cl_top_entries; const int* cl_top_off; int n_cl_top_levels;
   const int* down_entries; const int* down_off; int n_down_levels;  // 3 ints per drawn node: v, parent, edge
   const int* e_parent; const int* e_child; const Real* e_len;
   const long long* maps_off; const double* maps_len;
@@ -173,7 +175,9 @@ __device__ __forceinline__ void pow_times(const ChainParams<Real>& P, const Real
 // one-hot vector; schedule entries are two vector loads; the normalisation uses the hardware reciprocal.
 // ------------------------------------------------------------------------------------------------
 template <typename Real> __device__ __forceinline__ Real fast_rcp(Real x) { return (Real)1 / x; }
-template <> __device__ __forceinline__ float fast_rcp<float>(float x) { return __frcp_rn(x); }
+template <> __device__ __forceinline__ float fast_rcp<float>(float x) {  // one MUFU: the result only rescales a partial
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
 
 template <typename Real, int NS>
 struct PruneNode {  // one node of a round: what was loaded for it
@@ -269,6 +273,267 @@ __global__ void __launch_bounds__(256, MINB) k_prune_pipe(ChainParams<Real> P) {
       if (idx + step < end) load(A, idx + step, end);
       compute(B, idx, end);
       idx += step;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1, production arithmetic, clade order.  k_prune_pipe walks the tree level by level, so a partial written at one
+// level is read back from HBM a whole level later: 410 KB of traffic per site, 40 % of it re-reads of what the kernel
+// wrote itself.  Here every warp walks complete subtrees ("clades", pm_tree.hpp) alone, in post-order with the larger
+// child first:
+//   * a parent follows its last child immediately -> that child's partial is taken from registers;
+//   * its other internal child was finished a few nodes earlier by the same lane -> an L2 hit (same thread, same
+//     address: program order makes the store visible to the load);
+//   * jump counts and tip codes never depend on the kernel's own output, so they are fetched DEPTH nodes ahead;
+//   * no block-wide barrier until the clades are done; the few hundred nodes above them go level by level as before.
+// The schedule is uniform over the warp: lanes read 32 entries at once and hand them out with shuffles.
+// Results are bit-identical to k_prune_pipe (same operands, same operation order per node).
+// ------------------------------------------------------------------------------------------------
+// ---- shared-memory ring helpers (32-bit shared addresses, no generic-pointer arithmetic in the loop) ----
+__device__ __forceinline__ void cp_async4(unsigned dst, const void* gsrc, bool pred) {
+  const int sz = pred ? 4 : 0;  // src-size 0: the destination is zero-filled, nothing is read
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ int lds_u16(unsigned a) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return (int)v; }
+__device__ __forceinline__ int lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return (int)v; }
+__device__ __forceinline__ int4 lds_v4(unsigned a) {
+  int4 v; asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ int lds_s32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+
+// One slot of a warp's prefetch ring: what a node needs that does not depend on this kernel's output.
+//   [0,128) jump-count words of branch a per site   [128,256) of branch b   [256,288) tip codes of child a   [288,320) of b
+//   [320,336) byte offsets of the parent's and of the loaded child's partial (or -1)   [336,340) flags
+//   [352,384) schedule words 4..11 (branch and tip offsets) of the node that will take this slot next
+#define PM_CLADE_SLOT 384
+#define PM_CLADE_ENTRY_INTS 16  // host schedule entry (pm_host.cu): pn_off, x_off | ma_off, mb_off | ta_off, tb_off | flags (64 bytes)
+
+template <typename Real, int NS, int DEPTH, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Real* sPow = reinterpret_cast<Real*>(smem_raw + PM_CLADE_SLOT * 8 * DEPTH);  // [PM_SMEM_POW][NS*NS]  P_k, row-major
+  Real* sPowT = sPow + PM_SMEM_POW * NS * NS;                                  // [PM_SMEM_POW][NS*NS]  P_k transposed
+  const int npow_s = min(PM_SMEM_POW, P.jcap);
+  for (int i = threadIdx.x; i < npow_s * NS * NS; i += blockDim.x) {
+    const Real v = P.ppow[i];
+    sPow[i] = v;
+    const int k = i / (NS * NS), r = (i / NS) % NS, c = i % NS;
+    sPowT[k * NS * NS + c * NS + r] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long S = P.S;
+  const long long site0 = (long long)blockIdx.x * 32;
+  const long long site_raw = site0 + lane;
+  const bool active = site_raw < S;
+  const long long site = active ? site_raw : S - 1;
+  const bool parity = P.parity_tips != 0;
+  const int T = P.T;
+  const uint32_t* __restrict__ meta = P.meta + site;
+  const uint8_t* __restrict__ tip = P.tipcode + site;
+  Real* PLs = P.PL + site * NS;  // read and written by this thread: no __restrict__, no read-only loads
+  const long long rowPL = S * NS;
+
+  auto contribution = [&](int k, int code, Real* v) {
+    if (code >= 0 && !parity && k < npow_s) {
+      VecIO<Real, NS>::load(sPowT + k * NS * NS + code * NS, NS, v);
+    } else {
+      if (code >= 0) tip_partial<Real, NS>(code, NS, parity, v);
+      pow_times<Real, NS>(P, sPow, npow_s, k, v);
+    }
+  };
+  // out = normalised va * vb (production arithmetic always rescales; no floor: structural zeros stay zeros)
+  auto product = [&](const Real* va, const Real* vb, Real* out) {
+    Real sum = 0;
+#pragma unroll
+    for (int j = 0; j < NS; j++) { out[j] = vb[j] * va[j]; sum += out[j]; }
+    const Real inv = sum > (Real)0 ? fast_rcp<Real>(sum) : (Real)0;
+#pragma unroll
+    for (int j = 0; j < NS; j++) out[j] *= inv;
+  };
+
+  // ---- phase 1: this warp's clades ----
+  {
+    const int i0 = __ldg(P.cl_warp_off + warp), i1 = __ldg(P.cl_warp_off + warp + 1);
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(smem_raw) + warp * (DEPTH * PM_CLADE_SLOT);
+    char* const plb = reinterpret_cast<char*>(PLs);
+    const char* const mtb = reinterpret_cast<const char*>(meta);
+    const char* const tpb = reinterpret_cast<const char*>(P.tipcode) + site0 + 4 * (lane & 7);  // lanes 0..7: four tip codes each
+    const bool tip_in = site0 + 4 * (lane & 7) < S;
+    const int4* ep = reinterpret_cast<const int4*>(P.cl_entries) + 4 * (long long)i0;  // entry of the next node to issue
+    // keep the per-lane bases in registers: recomputing them from blockIdx / S every iteration costs more than they do
+    unsigned long long plb_u = reinterpret_cast<unsigned long long>(plb), mtb_u = reinterpret_cast<unsigned long long>(mtb),
+                       tpb_u = reinterpret_cast<unsigned long long>(tpb);
+    int act = active ? 1 : 0;
+    asm volatile("" : "+l"(plb_u), "+l"(mtb_u), "+l"(tpb_u), "+r"(act));
+    auto off64 = [](int lo, int hi) { return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); };
+    // start the asynchronous copies of the node with entry *e (q1, q2 = its second and third quarter) into the slot:
+    // two instructions for the jump-count words (every lane, one word per branch) and ONE for the rest, by lane role:
+    // lanes 0..7 four tip codes of child a each, 8..15 of child b, 16..20 the five header words, 21..28 the eight
+    // offset words of the node DEPTH further on (read back from the slot when that node is issued into it).  A child
+    // that is not a tip copies nothing (source size 0 zero-fills).
+    const bool role_b = (lane >> 3) == 1, role_hdr = lane >= 16 && lane < 21, role_nxt = lane >= 21;
+    const long long ent_delta = role_nxt ? (long long)DEPTH * 64 + 16 + 4 * (lane - 21)   // words 4..11 of entry e + DEPTH
+                                         : (lane == 20 ? 48 : 4 * (lane - 16));           // words 0..3 and 12 of entry e
+    const unsigned dst_off = role_nxt ? 352 + 4 * (lane - 21) : 256 + 4 * lane;
+    int tin = tip_in ? 1 : 0;
+    asm volatile("" : "+r"(tin));
+    auto issue = [&](unsigned slot, const int4* e, const int4& q1, const int4& q2, bool more) {
+      cp_async4(slot + 4 * lane, reinterpret_cast<const char*>(mtb_u) + off64(q1.x, q1.y));
+      cp_async4(slot + 128 + 4 * lane, reinterpret_cast<const char*>(mtb_u) + off64(q1.z, q1.w));
+      if (lane < 29) {
+        const int lo = role_b ? q2.z : q2.x, hi = role_b ? q2.w : q2.y;
+        const bool from_entry = role_hdr || role_nxt;
+        const bool on = role_hdr || (role_nxt && more) || (!from_entry && hi >= 0 && tin);
+        const char* src = from_entry ? reinterpret_cast<const char*>(e) + (role_nxt && !more ? 0 : ent_delta)
+                                     : reinterpret_cast<const char*>(tpb_u) + (hi >= 0 ? off64(lo, hi) : 0LL);
+        cp_async4(slot + dst_off, src, on);
+      }
+    };
+#pragma unroll 1
+    for (int u = 0; u < DEPTH; u++) {
+      if (i0 + u < i1) { issue(ring + u * PM_CLADE_SLOT, ep, __ldg(ep + 1), __ldg(ep + 2), i0 + u + DEPTH < i1); ep += 4; }
+      cp_async_commit();
+    }
+    Real prev[NS], xcur[NS], xnext[NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++) { prev[j] = 0; xcur[j] = 0; xnext[j] = 0; }
+    long long pn_off = 0;
+    int fl = 0;
+    if (i0 < i1) {
+      cp_async_wait<DEPTH - 1>();
+      __syncwarp();
+      const int4 h = lds_v4(ring + 320);
+      pn_off = off64(h.x, h.y);
+      fl = lds_s32(ring + 336);
+    }
+    unsigned slot = ring;
+    const unsigned ring_end = ring + DEPTH * PM_CLADE_SLOT;
+#pragma unroll 1
+    for (int idx = i0; idx < i1; idx++) {
+      const unsigned slot_n = (slot + PM_CLADE_SLOT == ring_end) ? ring : slot + PM_CLADE_SLOT;
+      // the group of node idx + 1 has landed as well (DEPTH - 2 younger ones may still be in flight): its header tells
+      // which internal child to fetch.  That child is not the node computed now, so it was stored at least one node ago.
+      cp_async_wait<DEPTH - 2>();
+      __syncwarp();
+      long long pn_off_n = 0;
+      int fl_n = 0;
+      if (idx + 1 < i1) {
+        const int4 h = lds_v4(slot_n + 320);
+        fl_n = lds_s32(slot_n + 336);
+        pn_off_n = off64(h.x, h.y);
+        if (h.w >= 0) VecIO<Real, NS>::load(reinterpret_cast<const Real*>(plb_u + (unsigned long long)off64(h.z, h.w)), NS, xnext);
+      }
+      const int ma = lds_u16(slot + 4 * lane), mb = lds_u16(slot + 128 + 4 * lane);
+      Real va[NS], vb[NS];
+      // fast path (warp-uniform): one-hot tips and every jump count inside the shared-memory table -> straight-line code,
+      // a tip child is one column of P_k, an internal child one 4 x 4 (2 x 2) product with P_k
+      const bool fast = !parity && __all_sync(0xffffffffu, ma <= npow_s && mb <= npow_s && ma > 0 && mb > 0);
+      if (fast) {
+        if (fl & 16) VecIO<Real, NS>::load(sPowT + ((ma - 1) * NS + lds_u8(slot + 256 + lane)) * NS, NS, va);
+        else {
+          const Real* Ma = sPow + (ma - 1) * NS * NS;
+          Real src[NS];
+#pragma unroll
+          for (int j = 0; j < NS; j++) src[j] = (fl & 1) ? prev[j] : xcur[j];
+#pragma unroll
+          for (int r = 0; r < NS; r++) {
+            Real row[NS];
+            VecIO<Real, NS>::load(Ma + r * NS, NS, row);
+            Real acc = 0;
+#pragma unroll
+            for (int c = 0; c < NS; c++) acc += row[c] * src[c];
+            va[r] = acc;
+          }
+        }
+        if (fl & 32) VecIO<Real, NS>::load(sPowT + ((mb - 1) * NS + lds_u8(slot + 288 + lane)) * NS, NS, vb);
+        else {
+          const Real* Mb = sPow + (mb - 1) * NS * NS;
+          Real src[NS];
+#pragma unroll
+          for (int j = 0; j < NS; j++) src[j] = (fl & 2) ? prev[j] : xcur[j];
+#pragma unroll
+          for (int r = 0; r < NS; r++) {
+            Real row[NS];
+            VecIO<Real, NS>::load(Mb + r * NS, NS, row);
+            Real acc = 0;
+#pragma unroll
+            for (int c = 0; c < NS; c++) acc += row[c] * src[c];
+            vb[r] = acc;
+          }
+        }
+      } else {
+        const int ca = (fl & 16) ? lds_u8(slot + 256 + lane) : -1, cb = (fl & 32) ? lds_u8(slot + 288 + lane) : -1;
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+          va[j] = (fl & 1) ? prev[j] : xcur[j];
+          vb[j] = (fl & 2) ? prev[j] : xcur[j];
+        }
+        contribution(mb - 1, cb, vb);
+        contribution(ma - 1, ca, va);
+      }
+      product(va, vb, prev);
+      if (act) VecIO<Real, NS>::store(reinterpret_cast<Real*>(plb_u + (unsigned long long)pn_off), NS, prev);
+#pragma unroll
+      for (int j = 0; j < NS; j++) xcur[j] = xnext[j];
+      pn_off = pn_off_n; fl = fl_n;
+      __syncwarp();  // every lane has read the slot before it is refilled
+      if (idx + DEPTH < i1) {  // the slot just consumed also carried this node's offset words
+        const int4 q1 = lds_v4(slot + 352), q2 = lds_v4(slot + 368);
+        __syncwarp();
+        issue(slot, ep, q1, q2, idx + 2 * DEPTH < i1);
+        ep += 4;
+      }
+      cp_async_commit();
+      slot = slot_n;
+    }
+    cp_async_wait<0>();
+  }
+  __syncthreads();
+
+  // ---- phase 2: the nodes above the clades, level by level (children come from memory) ----
+  const int4* __restrict__ ent = reinterpret_cast<const int4*>(P.cl_top_entries);  // 8 ints per node: pn a ea b | eb - - -
+  auto load = [&](PruneNode<Real, NS>& nd, int id) {
+    const int4 e0 = __ldg(ent + 2 * id), e1 = __ldg(ent + 2 * id + 1);
+    nd.pn = e0.x;
+    nd.ma = meta[(long long)e0.z * S];
+    nd.mb = meta[(long long)e1.x * S];
+    nd.ca = -1; nd.cb = -1;
+    if (e0.y < T) nd.ca = tip[(long long)e0.y * S];
+    else VecIO<Real, NS>::load(PLs + (long long)(e0.y - T) * rowPL, NS, nd.va);
+    if (e0.w < T) nd.cb = tip[(long long)e0.w * S];
+    else VecIO<Real, NS>::load(PLs + (long long)(e0.w - T) * rowPL, NS, nd.vb);
+  };
+  auto compute = [&](PruneNode<Real, NS>& nd) {
+    contribution((int)(nd.mb & 0xffffu) - 1, nd.cb, nd.vb);
+    contribution((int)(nd.ma & 0xffffu) - 1, nd.ca, nd.va);
+    Real out[NS];
+    product(nd.va, nd.vb, out);
+    if (active) VecIO<Real, NS>::store(PLs + (long long)(nd.pn - T) * rowPL, NS, out);
+  };
+  PruneNode<Real, NS> A, B;
+  for (int l = 0; l < P.n_cl_top_levels; l++) {
+    const int beg = __ldg(P.cl_top_off + l), end = __ldg(P.cl_top_off + l + 1);
+    int idx = beg + warp;
+    if (idx < end) load(A, idx);
+    while (idx < end) {
+      if (idx + nw < end) load(B, idx + nw);
+      compute(A);
+      idx += nw;
+      if (idx >= end) break;
+      if (idx + nw < end) load(A, idx + nw);
+      compute(B);
+      idx += nw;
     }
     __syncthreads();
   }

@@ -114,6 +114,106 @@ inline void build_schedule(int T, int E, const int32_t* edge, const int32_t* nen
   }
 }
 
+// Clade schedule of the production pruning kernel (k_prune_clade).  The tree is cut into clades (complete subtrees) of
+// at most `clade_max` internal nodes; each of the `nwarps` warps of a block owns a set of clades (balanced by size) and
+// walks them alone in post-order, larger child subtree first, so that a parent follows its last child immediately (the
+// child's partial is still in registers) and its other child shortly before (still in L2).  What lies above the clades
+// ("top", ~ Nn / clade_max nodes) is processed level by level by the whole block afterwards.
+//   entries: 8 ints per node: parent, a, ea, b | eb, flags, 0, 0
+//   flags:   1 = child a is the node processed just before by the same warp, 2 = child b is,
+//            4 = child a is internal and must be loaded, 8 = child b is
+struct CladeSchedule {
+  std::vector<int> entries;   // phase-1 sequences of warp 0, 1, .., then the top levels
+  std::vector<int> warp_off;  // [nwarps + 1] node offsets of the warps' sequences
+  std::vector<int> top_off;   // [n_top_levels + 1] node offsets of the top levels
+};
+
+inline void build_clade_schedule(const Schedule& s, int nwarps, int clade_max, CladeSchedule& c) {
+  const int T = s.T, NN = 2 * T - 1, Nn = T - 1;
+  std::vector<int> ka(NN, -1), kb(NN, -1), ea(NN, -1), eb(NN, -1), size(NN, 0), height(NN, 0);
+  std::vector<int> order(Nn);  // internal nodes, children before parents (the level order of `up_entries`)
+  for (int i = 0; i < Nn; i++) {
+    const int* en = &s.up_entries[(size_t)5 * i];
+    const int v = en[0];
+    ka[v] = en[1]; ea[v] = en[2]; kb[v] = en[3]; eb[v] = en[4];
+    order[i] = v;
+  }
+  for (int i = 0; i < Nn; i++) {
+    const int v = order[i];
+    size[v] = 1 + size[ka[v]] + size[kb[v]];
+  }
+  if (clade_max < 1) clade_max = 1;
+  // clade roots: size <= clade_max while the parent's is larger (or the node is the root)
+  std::vector<int> roots;
+  std::vector<char> is_top(NN, 0);
+  for (int i = 0; i < Nn; i++) {
+    const int v = order[i];
+    if (size[v] > clade_max) { is_top[v] = 1; continue; }
+    const bool at_root = v == s.root;
+    const int par = at_root ? -1 : s.e_parent[s.parent_edge[v]];
+    if (at_root || size[par] > clade_max) roots.push_back(v);
+  }
+  // longest-processing-time assignment of the clades to the warps
+  std::sort(roots.begin(), roots.end(), [&](int x, int y) { return size[x] != size[y] ? size[x] > size[y] : x < y; });
+  std::vector<std::vector<int>> mine(nwarps);
+  std::vector<long long> load(nwarps, 0);
+  for (int r : roots) {
+    int w = 0;
+    for (int k = 1; k < nwarps; k++) if (load[k] < load[w]) w = k;
+    mine[w].push_back(r);
+    load[w] += size[r];
+  }
+  c.entries.clear();
+  c.warp_off.assign(nwarps + 1, 0);
+  auto emit = [&](int v, int prev) {
+    int fl = 0;
+    if (ka[v] >= T) fl |= (ka[v] == prev) ? 1 : 4;
+    if (kb[v] >= T) fl |= (kb[v] == prev) ? 2 : 8;
+    const int en[8] = {v, ka[v], ea[v], kb[v], eb[v], fl, 0, 0};
+    c.entries.insert(c.entries.end(), en, en + 8);
+  };
+  std::vector<int> stack;
+  std::vector<char> expanded(NN, 0);
+  int count = 0;
+  for (int w = 0; w < nwarps; w++) {
+    c.warp_off[w] = count;
+    int prev = -1;
+    for (int r : mine[w]) {
+      stack.push_back(r);
+      while (!stack.empty()) {
+        const int v = stack.back();
+        if (v < T) { stack.pop_back(); continue; }
+        if (!expanded[v]) {
+          expanded[v] = 1;
+          // pushed last = processed first: the larger subtree
+          const int big = size[ka[v]] >= size[kb[v]] ? ka[v] : kb[v];
+          const int small = big == ka[v] ? kb[v] : ka[v];
+          stack.push_back(small);
+          stack.push_back(big);
+        } else { stack.pop_back(); emit(v, prev); prev = v; count++; }
+      }
+    }
+  }
+  c.warp_off[nwarps] = count;
+  // the top: levels by height above the clade roots; every internal child is loaded (flags 4 / 8)
+  int maxh = 0;
+  for (int i = 0; i < Nn; i++) {
+    const int v = order[i];
+    if (!is_top[v]) continue;
+    const int ha = is_top[ka[v]] ? height[ka[v]] : 0, hb = is_top[kb[v]] ? height[kb[v]] : 0;
+    height[v] = 1 + std::max(ha, hb);
+    maxh = std::max(maxh, height[v]);
+  }
+  std::vector<std::vector<int>> by_height(maxh + 1);
+  for (int i = 0; i < Nn; i++) if (is_top[order[i]]) by_height[height[order[i]]].push_back(order[i]);
+  c.top_off.assign(maxh + 1, 0);
+  for (int h = 1; h <= maxh; h++) {
+    c.top_off[h - 1] = count;
+    for (int v : by_height[h]) { emit(v, -1); count++; }
+  }
+  c.top_off[maxh] = count;
+}
+
 // A valid pruning-wise edge order (children before parents, the two edges of a node adjacent), the internal nodes
 // below the root top-down (reverse pruning order, like makenodelist), and the root.  O(E), iterative.
 inline void tree_order(const int32_t* edge, int E, int T, int32_t* nen, int32_t* nodelist, int32_t* root1) {
