@@ -590,7 +590,7 @@ struct ChainT : pm_chain {
         pm::host::build_clade_schedule(t->sch, 8, clade_max, cs);
         // phase-1 entries as byte offsets (PM_CLADE_ENTRY_INTS ints each): the kernel only adds them to per-lane bases
         const int n1 = cs.warp_off.back();
-        std::vector<int> e16((size_t)PM_CLADE_ENTRY_INTS * std::max(n1, 1), 0);
+        std::vector<int> e16((size_t)PM_CLADE_ENTRY_INTS * (n1 + 17), 0);  // padded: the kernel forms addresses up to 16 entries ahead
         auto put64 = [](int* dst, long long v) { dst[0] = (int)(unsigned)(v & 0xffffffffLL); dst[1] = (int)(v >> 32); };
         const long long rowPL = (long long)S * n * (long long)sizeof(Real);
         for (int i = 0; i < n1; i++) {

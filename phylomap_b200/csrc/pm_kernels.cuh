@@ -382,23 +382,28 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
     // lanes 0..7 four tip codes of child a each, 8..15 of child b, 16..20 the five header words, 21..28 the eight
     // offset words of the node DEPTH further on (read back from the slot when that node is issued into it).  A child
     // that is not a tip copies nothing (source size 0 zero-fills).
-    const bool role_b = (lane >> 3) == 1, role_hdr = lane >= 16 && lane < 21, role_nxt = lane >= 21;
-    const long long ent_delta = role_nxt ? (long long)DEPTH * 64 + 16 + 4 * (lane - 21)   // words 4..11 of entry e + DEPTH
-                                         : (lane == 20 ? 48 : 4 * (lane - 16));           // words 0..3 and 12 of entry e
-    const unsigned dst_off = role_nxt ? 352 + 4 * (lane - 21) : 256 + 4 * lane;
-    int tin = tip_in ? 1 : 0;
-    asm volatile("" : "+r"(tin));
+    // Branch-free by per-lane constants: source = cbase + X with X = the entry pointer (entry roles) or the tip-row
+    // offset of child a / b (tip roles; negative = not a tip -> nothing to copy).
+    const bool role_b = (lane >> 3) == 1, role_nxt = lane >= 21, role_ent = lane >= 16;
+    unsigned long long cbase = role_ent ? (unsigned long long)(role_nxt ? (long long)DEPTH * 64 + 16 + 4 * (lane - 21)  // words 4..11 of entry e + DEPTH
+                                                                        : (lane == 20 ? 48 : 4 * (lane - 16)))           // words 0..3 and 12 of entry e
+                                        : tpb_u;
+    // lanes 29..31 copy nothing: their zero-fill lands in the unused words [340, 352) of the slot
+    unsigned dst_off = lane >= 29 ? 340 + 4 * (lane - 29) : role_nxt ? 352 + 4 * (lane - 21) : 256 + 4 * lane;
+    // bit 0: this lane copies at all; 1: only while there is a node DEPTH further on; 2: role b; 3: entry role
+    int lrole = ((lane < 29 && (role_ent || tip_in)) ? 1 : 0) | (role_nxt ? 2 : 0) | (role_b ? 4 : 0) | (role_ent ? 8 : 0);
+    unsigned lane4 = 4 * lane;
+    // fast path only with the full shared-memory table (a power of two, so one OR tests both counts) and one-hot tips
+    unsigned fast_pow = (!parity && npow_s == PM_SMEM_POW) ? (unsigned)PM_SMEM_POW : 0u;
+    int lane_v = lane;
+    asm volatile("" : "+l"(cbase), "+r"(dst_off), "+r"(lrole), "+r"(lane4), "+r"(fast_pow), "+r"(lane_v));
     auto issue = [&](unsigned slot, const int4* e, const int4& q1, const int4& q2, bool more) {
-      cp_async4(slot + 4 * lane, reinterpret_cast<const char*>(mtb_u) + off64(q1.x, q1.y));
-      cp_async4(slot + 128 + 4 * lane, reinterpret_cast<const char*>(mtb_u) + off64(q1.z, q1.w));
-      if (lane < 29) {
-        const int lo = role_b ? q2.z : q2.x, hi = role_b ? q2.w : q2.y;
-        const bool from_entry = role_hdr || role_nxt;
-        const bool on = role_hdr || (role_nxt && more) || (!from_entry && hi >= 0 && tin);
-        const char* src = from_entry ? reinterpret_cast<const char*>(e) + (role_nxt && !more ? 0 : ent_delta)
-                                     : reinterpret_cast<const char*>(tpb_u) + (hi >= 0 ? off64(lo, hi) : 0LL);
-        cp_async4(slot + dst_off, src, on);
-      }
+      cp_async4(slot + lane4, reinterpret_cast<const char*>(mtb_u) + off64(q1.x, q1.y));
+      cp_async4(slot + 128 + lane4, reinterpret_cast<const char*>(mtb_u) + off64(q1.z, q1.w));
+      const long long tipoff = (lrole & 4) ? off64(q2.z, q2.w) : off64(q2.x, q2.y);
+      const long long X = (lrole & 8) ? reinterpret_cast<long long>(e) : tipoff;
+      const bool on = (lrole & 1) && X >= 0 && (more || !(lrole & 2));
+      cp_async4(slot + dst_off, reinterpret_cast<const char*>(cbase + (unsigned long long)(X >= 0 ? X : 0LL)), on);
     };
 #pragma unroll 1
     for (int u = 0; u < DEPTH; u++) {
@@ -434,13 +439,13 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
         pn_off_n = off64(h.x, h.y);
         if (h.w >= 0) VecIO<Real, NS>::load(reinterpret_cast<const Real*>(plb_u + (unsigned long long)off64(h.z, h.w)), NS, xnext);
       }
-      const int ma = lds_u16(slot + 4 * lane), mb = lds_u16(slot + 128 + 4 * lane);
+      const int ma = lds_u16(slot + lane4), mb = lds_u16(slot + 128 + lane4);
       Real va[NS], vb[NS];
       // fast path (warp-uniform): one-hot tips and every jump count inside the shared-memory table -> straight-line code,
       // a tip child is one column of P_k, an internal child one 4 x 4 (2 x 2) product with P_k
-      const bool fast = !parity && __all_sync(0xffffffffu, ma <= npow_s && mb <= npow_s && ma > 0 && mb > 0);
+      const bool fast = __all_sync(0xffffffffu, ((unsigned)(ma - 1) | (unsigned)(mb - 1)) < fast_pow);
       if (fast) {
-        if (fl & 16) VecIO<Real, NS>::load(sPowT + ((ma - 1) * NS + lds_u8(slot + 256 + lane)) * NS, NS, va);
+        if (fl & 16) VecIO<Real, NS>::load(sPowT + ((ma - 1) * NS + lds_u8(slot + 256 + lane_v)) * NS, NS, va);
         else {
           const Real* Ma = sPow + (ma - 1) * NS * NS;
           Real src[NS];
@@ -456,7 +461,7 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
             va[r] = acc;
           }
         }
-        if (fl & 32) VecIO<Real, NS>::load(sPowT + ((mb - 1) * NS + lds_u8(slot + 288 + lane)) * NS, NS, vb);
+        if (fl & 32) VecIO<Real, NS>::load(sPowT + ((mb - 1) * NS + lds_u8(slot + 288 + lane_v)) * NS, NS, vb);
         else {
           const Real* Mb = sPow + (mb - 1) * NS * NS;
           Real src[NS];
@@ -473,7 +478,7 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
           }
         }
       } else {
-        const int ca = (fl & 16) ? lds_u8(slot + 256 + lane) : -1, cb = (fl & 32) ? lds_u8(slot + 288 + lane) : -1;
+        const int ca = (fl & 16) ? lds_u8(slot + 256 + lane_v) : -1, cb = (fl & 32) ? lds_u8(slot + 288 + lane_v) : -1;
 #pragma unroll
         for (int j = 0; j < NS; j++) {
           va[j] = (fl & 1) ? prev[j] : xcur[j];
