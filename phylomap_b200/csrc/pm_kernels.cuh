@@ -410,29 +410,27 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
       if (i0 + u < i1) { issue(ring + u * PM_CLADE_SLOT, ep, __ldg(ep + 1), __ldg(ep + 2), i0 + u + DEPTH < i1); ep += 4; }
       cp_async_commit();
     }
-    Real prev[NS], xcur[NS], xnext[NS];
+    Real prev[NS], xA[NS], xB[NS];  // xA / xB: the loaded child of the current / next node, roles alternate
 #pragma unroll
-    for (int j = 0; j < NS; j++) { prev[j] = 0; xcur[j] = 0; xnext[j] = 0; }
-    long long pn_off = 0;
-    int fl = 0;
+    for (int j = 0; j < NS; j++) { prev[j] = 0; xA[j] = 0; xB[j] = 0; }
+    long long pnA = 0, pnB = 0;
+    int flA = 0, flB = 0;
     if (i0 < i1) {
       cp_async_wait<DEPTH - 1>();
       __syncwarp();
       const int4 h = lds_v4(ring + 320);
-      pn_off = off64(h.x, h.y);
-      fl = lds_s32(ring + 336);
+      pnA = off64(h.x, h.y);
+      flA = lds_s32(ring + 336);
     }
     unsigned slot = ring;
     const unsigned ring_end = ring + DEPTH * PM_CLADE_SLOT;
-#pragma unroll 1
-    for (int idx = i0; idx < i1; idx++) {
+    // one node: (pn_off, fl, xcur) describe it, (pn_off_n, fl_n, xnext) receive the next node's
+    auto step = [&](int idx, long long pn_off, int fl, const Real* xcur, long long& pn_off_n, int& fl_n, Real* xnext) {
       const unsigned slot_n = (slot + PM_CLADE_SLOT == ring_end) ? ring : slot + PM_CLADE_SLOT;
       // the group of node idx + 1 has landed as well (DEPTH - 2 younger ones may still be in flight): its header tells
       // which internal child to fetch.  That child is not the node computed now, so it was stored at least one node ago.
       cp_async_wait<DEPTH - 2>();
       __syncwarp();
-      long long pn_off_n = 0;
-      int fl_n = 0;
       if (idx + 1 < i1) {
         const int4 h = lds_v4(slot_n + 320);
         fl_n = lds_s32(slot_n + 336);
@@ -489,9 +487,6 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
       }
       product(va, vb, prev);
       if (act) VecIO<Real, NS>::store(reinterpret_cast<Real*>(plb_u + (unsigned long long)pn_off), NS, prev);
-#pragma unroll
-      for (int j = 0; j < NS; j++) xcur[j] = xnext[j];
-      pn_off = pn_off_n; fl = fl_n;
       __syncwarp();  // every lane has read the slot before it is refilled
       if (idx + DEPTH < i1) {  // the slot just consumed also carried this node's offset words
         const int4 q1 = lds_v4(slot + 352), q2 = lds_v4(slot + 368);
@@ -501,6 +496,11 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
       }
       cp_async_commit();
       slot = slot_n;
+    };
+#pragma unroll 1
+    for (int idx = i0; idx < i1; idx += 2) {
+      step(idx, pnA, flA, xA, pnB, flB, xB);
+      if (idx + 1 < i1) step(idx + 1, pnB, flB, xB, pnA, flA, xA);
     }
     cp_async_wait<0>();
   }
