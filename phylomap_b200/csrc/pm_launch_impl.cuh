@@ -22,7 +22,7 @@ void Sweep<Real, NS, EXACT>::prune(const ChainParams<Real>& P, int grid, size_t 
     else if (variant == 45) clade(k_prune_clade<Real, NS, 6, 3>, 6);
     else if (variant == 46) clade(k_prune_clade<Real, NS, 6, 5>, 6);
     else if (variant == 47) clade(k_prune_clade<Real, NS, 8, 4>, 8);
-    else clade(k_prune_clade<Real, NS, 8, 3>, 8);
+    else clade(k_prune_clade<Real, NS, 8, (sizeof(Real) == 8 ? 2 : 3)>, 8);  // FP64 needs the registers of 2 blocks / SM
   }
   else k_prune<Real, NS, EXACT><<<grid, 256, smem, st>>>(P);
 }

@@ -1,5 +1,5 @@
 """Times the production pruning kernel alone (pm_chain_time_prune) for its variants (PHYLOMAP_B200_K1_UNROLL:
-21 = one node per round [default], 20 = two) at the benchmark size, and checks that they give identical rows."""
+42 = clade order [default], 21 = level order, one node per round, 20 = two; see pm_launch_impl.cuh) at the benchmark size, and checks that they give identical rows."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
