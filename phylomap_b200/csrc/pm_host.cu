@@ -238,7 +238,8 @@ template <typename Real>
 struct TreeDev {
   pm::host::Schedule sch;
   long long S = 0;
-  DevBuf cl_entries, cl_warp_off, cl_top_entries, cl_top_off;  // clade schedule of the production pruning kernel
+  DevBuf cl_entries, cl_warp_off, cl_top_entries, cl_top_off, cd_top, cd_top_off, cd_entries, cd_warp_off, cd_tips;
+  int n_cd_top_levels = 0, n_cd_tips = 0;  // clade schedule of the production pruning kernel
   int n_cl_top_levels = 0;
   DevBuf up_entries8, up_entries, up_off, down_entries, down_off, e_parent, e_child, e_len, maps_off, maps_len, cap_off;
   DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, slow_mask, pos1;
@@ -616,6 +617,27 @@ struct ChainT : pm_chain {
         upload(t->cl_top_entries, top, stream);
         upload(t->cl_top_off, cs.top_off, stream);
         t->n_cl_top_levels = (int)cs.top_off.size() - 1;
+        // the same clades top-down for the node draws (k_nodes_clade): 16 ints per node, byte offsets
+        const int n2 = cs.down_warp_off.back();
+        std::vector<int> d16((size_t)16 * (n2 + 17), 0);
+        for (int i = 0; i < n2; i++) {
+          const int* en = &cs.down_seq[(size_t)4 * i];
+          int* o = &d16[(size_t)16 * i];
+          put64(o + 0, (long long)(en[0] - T) * rowPL);
+          put64(o + 2, (long long)en[2] * S * 4);
+          put64(o + 4, (long long)en[0] * S);
+          put64(o + 6, en[3] ? -1LL : (long long)en[1] * S);
+        }
+        upload(t->cd_entries, d16, stream);
+        upload(t->cd_warp_off, cs.down_warp_off, stream);
+        upload(t->cd_top, cs.down_top, stream);
+        upload(t->cd_top_off, cs.down_top_off, stream);
+        t->n_cd_top_levels = (int)cs.down_top_off.size() - 1;
+        std::vector<int> tips;
+        if (V.redraw_tips)
+          for (int v = 0; v < T; v++) { const int e = t->sch.parent_edge[v]; tips.push_back(v); tips.push_back(t->sch.e_parent[e]); tips.push_back(e); }
+        t->n_cd_tips = (int)tips.size() / 3;
+        upload(t->cd_tips, tips, stream);
       }
       upload(t->down_entries, t->sch.down_entries, stream);
       upload(t->down_off, t->sch.down_off, stream);
@@ -716,6 +738,9 @@ struct ChainT : pm_chain {
       P.cl_entries = t.cl_entries.template as<int>(); P.cl_warp_off = t.cl_warp_off.template as<int>();
       P.cl_top_entries = t.cl_top_entries.template as<int>();
       P.cl_top_off = t.cl_top_off.template as<int>(); P.n_cl_top_levels = t.n_cl_top_levels;
+      P.cd_top = t.cd_top.template as<int>(); P.cd_top_off = t.cd_top_off.template as<int>(); P.n_cd_top_levels = t.n_cd_top_levels;
+      P.cd_entries = t.cd_entries.template as<int>(); P.cd_warp_off = t.cd_warp_off.template as<int>();
+      P.cd_tips = t.cd_tips.template as<int>(); P.n_cd_tips = t.n_cd_tips;
       P.down_entries = t.down_entries.template as<int>(); P.down_off = t.down_off.template as<int>();
       P.n_down_levels = (int)t.sch.down_off.size() - 1;
       P.e_parent = t.e_parent.template as<int>(); P.e_child = t.e_child.template as<int>();

@@ -37,6 +37,9 @@ struct ChainParams {
   const int* up_entries8;  // the same entries padded to 8 ints (two 16-byte loads)
   // clade schedule of k_prune_clade (pm_tree.hpp): 8 ints per node, per-warp sequences then the top levels
   const int* cl_entries; const int* cl_warp_off; const int* cl_top_entries; const int* cl_top_off; int n_cl_top_levels;
+  // ... and of k_nodes_clade: top part by depth (4 ints per node: v, parent, edge, -), then per-warp pre-order sequences (16 ints)
+  const int* cd_top; const int* cd_top_off; int n_cd_top_levels; const int* cd_entries; const int* cd_warp_off;
+  const int* cd_tips; int n_cd_tips;  // tips to redraw (ks / mt samplers): 3 ints per tip: v, parent, edge
   const int* down_entries; const int* down_off; int n_down_levels;  // 3 ints per drawn node: v, parent, edge
   const int* e_parent; const int* e_child; const Real* e_len;
   const long long* maps_off; const double* maps_len;
@@ -308,6 +311,20 @@ __device__ __forceinline__ int lds_u16(unsigned a) { unsigned short v; asm volat
 __device__ __forceinline__ int lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return (int)v; }
 __device__ __forceinline__ int4 lds_v4(unsigned a) {
   int4 v; asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+template <typename Real, int NS> __device__ __forceinline__ void lds_vec(unsigned a, Real* v);
+template <> __device__ __forceinline__ void lds_vec<float, 4>(unsigned a, float* v) {
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+}
+template <> __device__ __forceinline__ void lds_vec<float, 2>(unsigned a, float* v) {
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(a));
+}
+template <> __device__ __forceinline__ void lds_vec<double, 2>(unsigned a, double* v) {
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a));
+}
+template <> __device__ __forceinline__ void lds_vec<double, 4>(unsigned a, double* v) {
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a));
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "r"(a + 16));
 }
 __device__ __forceinline__ int lds_s32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
@@ -620,86 +637,6 @@ template <typename Real> __device__ __forceinline__ Real u01_from_word(uint32_t 
 template <> __device__ __forceinline__ float u01_from_word<float>(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 template <> __device__ __forceinline__ double u01_from_word<double>(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
 
-template <typename Real, int NS>
-__global__ void __launch_bounds__(256) k_nodes_fast(ChainParams<Real> P, uint32_t iter) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Real* sBs = reinterpret_cast<Real*>(smem_raw);
-  Real* sVec = sBs + NS * NS;  // pid, scale_old, scale_new
-  Real* sPow = sVec + 3 * NS;
-  const int npow_s = min(PM_SMEM_POW, P.jcap);
-  load_model_smem<Real>(P, NS, nullptr, sBs, sVec, sPow, npow_s);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const long long S = P.S;
-  const long long site_raw = (long long)blockIdx.x * 32 + lane;
-  const bool active = site_raw < S;
-  const long long site = active ? site_raw : S - 1;
-  const bool parity = P.parity_tips != 0;
-  const int T = P.T;
-  const uint32_t gsite = P.rng.site0 + (uint32_t)site;
-  if (warp == 0) {  // root :618-627
-    Real w[NS], pl[NS];
-    VecIO<Real, NS>::load(P.PL + ((long long)(P.root - T) * S + site) * NS, NS, pl);
-#pragma unroll
-    for (int j = 0; j < NS; j++) w[j] = sVec[j] * pl[j];
-    uint32_t o[4];
-    philox4x32_10(0xffffffffu, make_slot(K_NODEGRP, 0u), iter, gsite, P.rng.k0, P.rng.k1, o);
-    const int s = categorical<Real, NS, false>(w, NS, u01_from_word<Real>(o[0]), P.err_flag);
-    if (active) {
-      P.node_state[(long long)P.root * S + site] = (uint8_t)s;
-      if (gsite == 0u) *P.root_out = s;
-    }
-  }
-  __syncthreads();
-  for (int l = 0; l < P.n_down_levels; l++) {
-    const int beg = __ldg(P.down_off + l), end = __ldg(P.down_off + l + 1);
-    for (int grp = (beg >> 2) + warp; grp <= ((end - 1) >> 2); grp += nw) {
-      uint32_t o[4];
-      philox4x32_10((uint32_t)grp, make_slot(K_NODEGRP, 0u), iter, gsite, P.rng.k0, P.rng.k1, o);
-      const int p0 = max(beg, grp << 2), p1 = min(end, (grp << 2) + 4);
-      // issue the loads of the whole group first
-      int vs[4], ks[4], pss[4];
-      Real pls[4][NS];
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int pos = min(p0 + q, p1 - 1);
-        const int* en = P.down_entries + 3 * pos;
-        const int v = __ldg(en), pn = __ldg(en + 1), e = __ldg(en + 2);
-        vs[q] = v;
-        pss[q] = P.node_state[(long long)pn * S + site];
-        ks[q] = (int)(P.meta[(long long)e * S + site] & 0xffffu) - 1;
-        if (v < T) tip_partial<Real, NS>(P.tipcode[(long long)v * S + site], NS, parity, pls[q]);
-        else VecIO<Real, NS>::load(P.PL + ((long long)(v - T) * S + site) * NS, NS, pls[q]);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int pos = p0 + q;
-        if (pos < p1) {  // warp-uniform
-          const int k = ks[q], ps = pss[q];
-          Real w[NS];
-          if (k < npow_s) {
-#pragma unroll
-            for (int j = 0; j < NS; j++) w[j] = sPow[k * NS * NS + ps * NS + j];
-          } else if (k < P.jcap) {
-#pragma unroll
-            for (int j = 0; j < NS; j++) w[j] = P.ppow[(size_t)k * NS * NS + ps * NS + j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < NS; j++) w[j] = (Real)(j == ps);
-            for (int r = 0; r < k; r++) matvec_t<Real, NS, false>(sBs, NS, w);
-          }
-#pragma unroll
-          for (int j = 0; j < NS; j++) w[j] *= pls[q][j];
-          const uint32_t word = (pos & 3) == 0 ? o[0] : (pos & 3) == 1 ? o[1] : (pos & 3) == 2 ? o[2] : o[3];
-          const int s = categorical<Real, NS, false>(w, NS, u01_from_word<Real>(word), P.err_flag);
-          if (active) P.node_state[(long long)vs[q] * S + site] = (uint8_t)s;
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // K3: branch paths.  Thread = one site x a chunk of branches; block = 128 consecutive sites.
 // ------------------------------------------------------------------------------------------------
@@ -872,6 +809,197 @@ __global__ void __launch_bounds__(128) k_paths(ChainParams<Real> P, uint32_t ite
     P.dw_partial[blk * n + threadIdx.x] = v;
   }
   for (int i = threadIdx.x; i < n * n; i += blockDim.x) if (s_cnt[i]) atomicAdd(&P.cnt[i], (unsigned long long)s_cnt[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2, production arithmetic, clade order (the top-down twin of k_prune_clade, same clades).  The root, then the nodes
+// above the clades by depth, then every warp walks its clades alone in pre-order: a node's parent is either the node
+// drawn just before (state in a register) or an ancestor drawn earlier by the same lane (one byte from L2, fetched one
+// node ahead); the node's partial and jump count come through a cp.async ring 8 nodes deep.  One Philox block serves
+// four consecutive nodes of a sequence.  Tips (ks / mt samplers) are redrawn at the end, four per Philox block.
+//   slot: [0, PLB) partial per site   [PLB, +128) jump-count words   [+128, +144) v_off, parent_off (or -1: previous node)
+//         [+144, +160) partial / jump-count offsets of the node that takes this slot next      (PLB = 32 * NS * sizeof(Real))
+//   entry (host, 16 ints): pl_off, meta_off | v_off, parent_off | pad
+// ------------------------------------------------------------------------------------------------
+template <typename Real, int NS>
+__device__ __forceinline__ int draw_node_state(const ChainParams<Real>& P, const Real* sBs, const Real* sPow, int npow_s, int k, int ps,
+                                               const Real* pl, uint32_t word) {
+  Real w[NS];
+  if (k < npow_s) VecIO<Real, NS>::load(sPow + (k * NS + ps) * NS, NS, w);
+  else if (k < P.jcap) {
+#pragma unroll
+    for (int j = 0; j < NS; j++) w[j] = P.ppow[(size_t)k * NS * NS + ps * NS + j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < NS; j++) w[j] = (Real)(j == ps);
+    for (int r = 0; r < k; r++) matvec_t<Real, NS, false>(sBs, NS, w);
+  }
+#pragma unroll
+  for (int j = 0; j < NS; j++) w[j] *= pl[j];
+  return categorical<Real, NS, false>(w, NS, u01_from_word<Real>(word), P.err_flag);
+}
+
+template <typename Real, int NS, int DEPTH, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, uint32_t iter) {
+  constexpr int PB = NS * (int)sizeof(Real);  // bytes of one partial
+  constexpr int PLB = 32 * PB;
+  constexpr int SLOT = PLB + 160;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Real* sBs = reinterpret_cast<Real*>(smem_raw + SLOT * 8 * DEPTH);
+  Real* sVec = sBs + NS * NS;  // pid, scale_old, scale_new
+  Real* sPow = sVec + 3 * NS;
+  const int npow_s = min(PM_SMEM_POW, P.jcap);
+  load_model_smem<Real>(P, NS, nullptr, sBs, sVec, sPow, npow_s);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long S = P.S;
+  const long long site_raw = (long long)blockIdx.x * 32 + lane;
+  const bool active = site_raw < S;
+  const long long site = active ? site_raw : S - 1;
+  const bool parity = P.parity_tips != 0;
+  const int T = P.T;
+  const uint32_t gsite = P.rng.site0 + (uint32_t)site;
+  const uint32_t kslot = make_slot(K_NODEGRP, 0u);
+  uint8_t* const nst = P.node_state + site;  // read and written by this thread
+  if (warp == 0) {  // root :618-627
+    Real w[NS], pl[NS];
+    VecIO<Real, NS>::load(P.PL + ((long long)(P.root - T) * S + site) * NS, NS, pl);
+#pragma unroll
+    for (int j = 0; j < NS; j++) w[j] = sVec[j] * pl[j];
+    uint32_t o[4];
+    philox4x32_10(0xffffffffu, kslot, iter, gsite, P.rng.k0, P.rng.k1, o);
+    const int s = categorical<Real, NS, false>(w, NS, u01_from_word<Real>(o[0]), P.err_flag);
+    if (active) {
+      nst[(long long)P.root * S] = (uint8_t)s;
+      if (gsite == 0u) *P.root_out = s;
+    }
+  }
+  __syncthreads();
+  // ---- the nodes above the clades, by depth (a few hundred): one node per warp at a time, Philox block 0x80000000 + index
+  for (int l = 0; l < P.n_cd_top_levels; l++) {
+    const int beg = __ldg(P.cd_top_off + l), end = __ldg(P.cd_top_off + l + 1);
+    for (int idx = beg + warp; idx < end; idx += nw) {
+      const int4 en = __ldg(reinterpret_cast<const int4*>(P.cd_top) + idx);
+      const int ps = nst[(long long)en.y * S];
+      const int k = (int)(P.meta[(long long)en.z * S + site] & 0xffffu) - 1;
+      Real pl[NS];
+      VecIO<Real, NS>::load(P.PL + ((long long)(en.x - T) * S + site) * NS, NS, pl);
+      uint32_t o[4];
+      philox4x32_10(0x80000000u + (uint32_t)idx, kslot, iter, gsite, P.rng.k0, P.rng.k1, o);
+      const int s = draw_node_state<Real, NS>(P, sBs, sPow, npow_s, k, ps, pl, o[0]);
+      if (active) nst[(long long)en.x * S] = (uint8_t)s;
+    }
+    __syncthreads();
+  }
+  // ---- this warp's clades, pre-order ----
+  {
+    const int i0 = __ldg(P.cd_warp_off + warp), i1 = __ldg(P.cd_warp_off + warp + 1);
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(smem_raw) + warp * (DEPTH * SLOT);
+    unsigned long long plb_u = reinterpret_cast<unsigned long long>(P.PL + site * NS),
+                       mtb_u = reinterpret_cast<unsigned long long>(P.meta + site),
+                       nsb_u = reinterpret_cast<unsigned long long>(nst);
+    int act = active ? 1 : 0;
+    unsigned lane4 = 4 * lane, lanePB = PB * lane;
+    // lanes 0..3 copy the header words (entry words 4..7), lanes 4..7 the offsets of the node DEPTH further on (words 0..3)
+    unsigned long long hsrc = lane < 4 ? 16 + 4 * lane : (unsigned long long)DEPTH * 64 + 4 * (lane - 4);
+    unsigned hdst = PLB + 128 + 4 * lane;
+    asm volatile("" : "+l"(plb_u), "+l"(mtb_u), "+l"(nsb_u), "+r"(act), "+r"(lane4), "+r"(lanePB), "+l"(hsrc), "+r"(hdst));
+    auto off64 = [](int lo, int hi) { return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); };
+    const int4* ep = reinterpret_cast<const int4*>(P.cd_entries) + 4 * (long long)i0;
+    auto issue = [&](unsigned slot, const int4* e, const int4& q0, bool more) {
+      const char* src = reinterpret_cast<const char*>(plb_u) + off64(q0.x, q0.y);
+      if (PB == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot + lanePB), "l"(src) : "memory");
+      else {
+        cp_async16(slot + lanePB, src);
+        if (PB == 32) cp_async16(slot + lanePB + 16, src + 16);
+      }
+      cp_async4(slot + PLB + lane4, reinterpret_cast<const char*>(mtb_u) + off64(q0.z, q0.w));
+      if (lane < 8) cp_async4(slot + hdst, reinterpret_cast<const char*>(e) + hsrc, lane < 4 || more);
+    };
+#pragma unroll 1
+    for (int u = 0; u < DEPTH; u++) {
+      if (i0 + u < i1) { issue(ring + u * SLOT, ep, __ldg(ep), i0 + u + DEPTH < i1); ep += 4; }
+      cp_async_commit();
+    }
+    long long vA = 0, vB = 0, pA = -1, pB = -1;  // node_state offsets of the node and of its parent (-1: previous node)
+    int psA = 0, psB = 0;                       // parent state fetched from memory
+    if (i0 < i1) {
+      cp_async_wait<DEPTH - 1>();
+      __syncwarp();
+      const int4 h = lds_v4(ring + PLB + 128);
+      vA = off64(h.x, h.y); pA = off64(h.z, h.w);
+      if (pA >= 0) psA = *reinterpret_cast<const uint8_t*>(nsb_u + (unsigned long long)pA);
+    }
+    unsigned slot = ring;
+    const unsigned ring_end = ring + DEPTH * SLOT;
+    int sprev = 0;
+    uint32_t o[4] = {0, 0, 0, 0};
+    auto step = [&](int idx, long long v_off, long long p_off, int ps_mem, long long& v_off_n, long long& p_off_n, int& ps_mem_n) {
+      const unsigned slot_n = (slot + SLOT == ring_end) ? ring : slot + SLOT;
+      cp_async_wait<DEPTH - 2>();
+      __syncwarp();
+      if (idx + 1 < i1) {
+        const int4 h = lds_v4(slot_n + PLB + 128);
+        v_off_n = off64(h.x, h.y); p_off_n = off64(h.z, h.w);
+        // the parent of the next node, unless it is the node drawn now: stored at least one node ago by this lane
+        if (h.w >= 0) ps_mem_n = *reinterpret_cast<const uint8_t*>(nsb_u + (unsigned long long)p_off_n);
+      }
+      if ((idx & 3) == 0 || idx == i0) philox4x32_10((uint32_t)idx >> 2, kslot, iter, gsite, P.rng.k0, P.rng.k1, o);
+      const uint32_t word = (idx & 3) == 0 ? o[0] : (idx & 3) == 1 ? o[1] : (idx & 3) == 2 ? o[2] : o[3];
+      Real pl[NS];
+      lds_vec<Real, NS>(slot + lanePB, pl);  // the partial of this node, copied by this lane
+      const int k = lds_u16(slot + PLB + lane4) - 1;
+      const int ps = p_off < 0 ? sprev : ps_mem;
+      const int sn = draw_node_state<Real, NS>(P, sBs, sPow, npow_s, k, ps, pl, word);
+      if (act) *reinterpret_cast<uint8_t*>(nsb_u + (unsigned long long)v_off) = (uint8_t)sn;
+      sprev = sn;
+      __syncwarp();
+      if (idx + DEPTH < i1) {
+        const int4 q0 = lds_v4(slot + PLB + 144);
+        __syncwarp();
+        issue(slot, ep, q0, idx + 2 * DEPTH < i1);
+        ep += 4;
+      }
+      cp_async_commit();
+      slot = slot_n;
+    };
+#pragma unroll 1
+    for (int idx = i0; idx < i1; idx += 2) {
+      step(idx, vA, pA, psA, vB, pB, psB);
+      if (idx + 1 < i1) step(idx + 1, vB, pB, psB, vA, pA, psA);
+    }
+    cp_async_wait<0>();
+  }
+  // ---- tips (samplers that redraw them): four consecutive list entries share a Philox block 0x40000000 + group ----
+  if (P.n_cd_tips > 0) {
+    __syncthreads();
+    for (int grp = warp; grp <= (P.n_cd_tips - 1) >> 2; grp += nw) {
+      uint32_t o[4];
+      philox4x32_10(0x40000000u + (uint32_t)grp, kslot, iter, gsite, P.rng.k0, P.rng.k1, o);
+      const int p0 = grp << 2, p1 = min(P.n_cd_tips, p0 + 4);
+      int vs[4], ks[4], pss[4], cds[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int pos = min(p0 + q, p1 - 1);
+        const int* en = P.cd_tips + 3 * pos;
+        const int v = __ldg(en), pn = __ldg(en + 1), e = __ldg(en + 2);
+        vs[q] = v;
+        pss[q] = nst[(long long)pn * S];
+        ks[q] = (int)(P.meta[(long long)e * S + site] & 0xffffu) - 1;
+        cds[q] = P.tipcode[(long long)v * S + site];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (p0 + q < p1) {  // warp-uniform
+          Real pl[NS];
+          tip_partial<Real, NS>(cds[q], NS, parity, pl);
+          const uint32_t word = q == 0 ? o[0] : q == 1 ? o[1] : q == 2 ? o[2] : o[3];
+          const int sn = draw_node_state<Real, NS>(P, sBs, sPow, npow_s, ks[q], pss[q], pl, word);
+          if (active) nst[(long long)vs[q] * S] = (uint8_t)sn;
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

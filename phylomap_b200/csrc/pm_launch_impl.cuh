@@ -28,7 +28,13 @@ void Sweep<Real, NS, EXACT>::prune(const ChainParams<Real>& P, int grid, size_t 
 }
 template <typename Real, int NS, bool EXACT>
 void Sweep<Real, NS, EXACT>::nodes(const ChainParams<Real>& P, int grid, size_t smem, cudaStream_t st, uint32_t iter) {
-  if constexpr (!EXACT && (NS == 2 || NS == 4)) k_nodes_fast<Real, NS><<<grid, 256, smem, st>>>(P, iter);
+  if constexpr (!EXACT && (NS == 2 || NS == 4)) {
+    constexpr int D = 8, MB = sizeof(Real) == 8 ? 2 : 3;
+    const size_t sm = smem + (size_t)(32 * NS * sizeof(Real) + 160) * 8 * D;
+    auto kern = k_nodes_clade<Real, NS, D, MB>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    kern<<<grid, 256, sm, st>>>(P, iter);
+  }
   else k_nodes<Real, NS, EXACT><<<grid, 256, smem, st>>>(P, iter);
 }
 template <typename Real, int NS, bool EXACT>

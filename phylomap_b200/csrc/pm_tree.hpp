@@ -126,6 +126,11 @@ struct CladeSchedule {
   std::vector<int> entries;   // phase-1 sequences of warp 0, 1, .., then the top levels
   std::vector<int> warp_off;  // [nwarps + 1] node offsets of the warps' sequences
   std::vector<int> top_off;   // [n_top_levels + 1] node offsets of the top levels
+  // the same clades top-down (k_nodes_clade): 4 ints per drawn internal node: v, parent, edge, 1 if the parent is the node
+  // drawn just before by the same warp.  First the nodes above the clades by depth (the root excluded), then the warps'
+  // pre-order sequences.
+  std::vector<int> down_top, down_top_off;  // levels of the top part
+  std::vector<int> down_seq, down_warp_off; // [nwarps + 1]
 };
 
 inline void build_clade_schedule(const Schedule& s, int nwarps, int clade_max, CladeSchedule& c) {
@@ -203,6 +208,56 @@ inline void build_clade_schedule(const Schedule& s, int nwarps, int clade_max, C
     const int ha = is_top[ka[v]] ? height[ka[v]] : 0, hb = is_top[kb[v]] ? height[kb[v]] : 0;
     height[v] = 1 + std::max(ha, hb);
     maxh = std::max(maxh, height[v]);
+  }
+  // ---- top-down (node draws) ----
+  {
+    std::vector<int> depth(NN, 0);
+    std::vector<std::vector<int>> by_depth;
+    for (int i = Nn - 1; i >= 0; i--) {  // parents before children
+      const int v = order[i];
+      if (!is_top[v]) continue;
+      if (v != s.root) depth[v] = depth[s.e_parent[s.parent_edge[v]]] + 1;
+      if (v == s.root) continue;
+      if ((int)by_depth.size() <= depth[v]) by_depth.resize(depth[v] + 1);
+      by_depth[depth[v]].push_back(v);
+    }
+    c.down_top.clear(); c.down_top_off.assign(1, 0);
+    for (size_t d = 1; d < by_depth.size(); d++) {
+      for (int v : by_depth[d]) {
+        const int e = s.parent_edge[v];
+        const int en[4] = {v, s.e_parent[e], e, 0};
+        c.down_top.insert(c.down_top.end(), en, en + 4);
+      }
+      c.down_top_off.push_back((int)c.down_top.size() / 4);
+    }
+    c.down_seq.clear(); c.down_warp_off.assign(nwarps + 1, 0);
+    int cnt2 = 0;
+    for (int w = 0; w < nwarps; w++) {
+      c.down_warp_off[w] = cnt2;
+      int prev = -1;
+      for (int r : mine[w]) {
+        if (r == s.root) { prev = -1; }  // the root is drawn separately; its clade starts with its children
+        stack.clear();
+        stack.push_back(r);
+        while (!stack.empty()) {
+          const int v = stack.back(); stack.pop_back();
+          if (v < T) continue;
+          if (v != s.root) {
+            const int e = s.parent_edge[v], par = s.e_parent[e];
+            const int en[4] = {v, par, e, par == prev ? 1 : 0};
+            c.down_seq.insert(c.down_seq.end(), en, en + 4);
+            cnt2++;
+            prev = v;
+          }
+          // pushed last = visited first: the larger subtree right after its parent
+          const int big = size[ka[v]] >= size[kb[v]] ? ka[v] : kb[v];
+          const int small = big == ka[v] ? kb[v] : ka[v];
+          stack.push_back(small);
+          stack.push_back(big);
+        }
+      }
+    }
+    c.down_warp_off[nwarps] = cnt2;
   }
   std::vector<std::vector<int>> by_height(maxh + 1);
   for (int i = 0; i < Nn; i++) if (is_top[order[i]]) by_height[height[order[i]]].push_back(order[i]);
