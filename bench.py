@@ -208,7 +208,7 @@ def run_ours(a, rank, local_rank, world):
         raise SystemExit("bench sanity check failed: dwell %r vs %r" % (tot[:3], expect))
 
     # roofline of the pruning pass
-    K1_NAME = "k_prune_clade<float,4,8,3>" if S % 4 == 0 else "k_prune_pipe<float,4,1,4>"
+    K1_NAME = "k_prune_clade<float,4,8,3>"
     k1_ms = chain.time_prune(reps=5)
     T = tree.T
     bytes_site = (T - 1) * 16 + (T - 2) * 16 + T * 1 + E * 4

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) k_exp_nodes(ChainParams<Real> P, const Re
       const int v = __ldg(en), pn = __ldg(en + 1), e = __ldg(en + 2);
       const int ps = P.node_state[(long long)pn * S + site];
       Real w[NC], pl[NC];
-      if (v < T) tip_partial<Real, NC>(P.tipcode[(long long)v * S + site], n, parity, pl);
+      if (v < T) tip_partial<Real, NC>(P.tipcode[(long long)v * P.TS + site], n, parity, pl);
       else VecIO<Real, NS>::load(P.PL + ((long long)(v - T) * S + site) * n, n, pl);
 #pragma unroll
       for (int j = 0; j < n; j++) w[j] = __ldg(TP + (size_t)e * n * n + ps * n + j) * pl[j];  // :2950

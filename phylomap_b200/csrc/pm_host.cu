@@ -237,7 +237,7 @@ namespace {
 template <typename Real>
 struct TreeDev {
   pm::host::Schedule sch;
-  long long S = 0;
+  long long S = 0, TS = 0;
   DevBuf cl_entries, cl_warp_off, cl_top_entries, cl_top_off, cd_top, cd_top_off, cd_entries, cd_warp_off, cd_tips;
   int n_cd_top_levels = 0, n_cd_tips = 0;  // clade schedule of the production pruning kernel
   int n_cl_top_levels = 0;
@@ -517,6 +517,7 @@ struct ChainT : pm_chain {
       std::unique_ptr<TreeDev<Real>> t(new TreeDev<Real>());
       t->sch = std::move(schedules[ti]);
       t->S = x.n_sites;
+      t->TS = (t->S + 15) / 16 * 16;  // tip-code rows are padded: every row starts 16-byte aligned whatever S is
       const int E = x.n_edges, T = x.n_tips;
       std::vector<long long> moff(E + 1);
       std::vector<Real> elen(E);
@@ -606,8 +607,8 @@ struct ChainT : pm_chain {
           put64(o + 2, x >= 0 ? (long long)(x - T) * rowPL : -1LL);
           put64(o + 4, (long long)ea * S * 4);
           put64(o + 6, (long long)eb * S * 4);
-          put64(o + 8, a < T ? (long long)a * S : -1LL);
-          put64(o + 10, b < T ? (long long)b * S : -1LL);
+          put64(o + 8, a < T ? (long long)a * t->TS : -1LL);
+          put64(o + 10, b < T ? (long long)b * t->TS : -1LL);
           o[12] = fl;
         }
         std::vector<int> top(cs.entries.begin() + (size_t)8 * n1, cs.entries.end());
@@ -655,7 +656,8 @@ struct ChainT : pm_chain {
       upload(t->maps_off, moff, stream);
       upload(t->maps_len, mlen, stream);
       upload(t->cap_off, t->cap_off_h, stream);
-      t->tipcode.alloc((size_t)T * S);
+      t->tipcode.alloc((size_t)T * t->TS);
+      CK(cudaMemsetAsync(t->tipcode.p, 0, t->tipcode.bytes, stream));
       t->node_state.alloc((size_t)(2 * T - 1) * S);
       if (!V.exp && !V.llonly) t->meta.alloc((size_t)E * S * sizeof(uint32_t));
       t->PL.alloc((size_t)(T - 1) * S * n * sizeof(Real));
@@ -747,7 +749,7 @@ struct ChainT : pm_chain {
       P.e_len = t.e_len.template as<Real>();
       P.maps_off = t.maps_off.template as<long long>(); P.maps_len = t.maps_len.template as<double>();
       P.root = t.sch.root;
-      P.tipcode = t.tipcode.template as<uint8_t>(); P.node_state = t.node_state.template as<uint8_t>();
+      P.tipcode = t.tipcode.template as<uint8_t>(); P.TS = t.TS; P.node_state = t.node_state.template as<uint8_t>();
       P.meta = t.meta.template as<uint32_t>(); P.PL = t.PL.template as<Real>();
       for (int b = 0; b < 2; b++) { P.rec_len[b] = t.rec_len[b].template as<Real>(); P.rec_st[b] = t.rec_st[b].template as<uint8_t>(); }
       // per-node rescaling (makePLrcpp_bigtree :525) only rescales the weights of each draw: the production
@@ -777,9 +779,9 @@ struct ChainT : pm_chain {
         CK(cudaMemcpyAsync(stage.p, src, (size_t)ns * T * esz, cudaMemcpyHostToDevice, stream));
         dim3 g((T + 31) / 32, (ns + 31) / 32), b(32, 8);
         if (x.states_u8)
-          pm::k_init_tips<uint8_t><<<g, b, 0, stream>>>(stage.as<uint8_t>(), ns, s0, t.S, T, n, V.parity_tips, t.tipcode.template as<uint8_t>(), P.node_state, P.err_flag);
+          pm::k_init_tips<uint8_t><<<g, b, 0, stream>>>(stage.as<uint8_t>(), ns, s0, t.S, t.TS, T, n, V.parity_tips, t.tipcode.template as<uint8_t>(), P.node_state, P.err_flag);
         else
-          pm::k_init_tips<int32_t><<<g, b, 0, stream>>>(stage.as<int32_t>(), ns, s0, t.S, T, n, V.parity_tips, t.tipcode.template as<uint8_t>(), P.node_state, P.err_flag);
+          pm::k_init_tips<int32_t><<<g, b, 0, stream>>>(stage.as<int32_t>(), ns, s0, t.S, t.TS, T, n, V.parity_tips, t.tipcode.template as<uint8_t>(), P.node_state, P.err_flag);
         CK(cudaStreamSynchronize(stream));
       }
       const long long tot = t.S * E;

@@ -44,7 +44,8 @@ struct ChainParams {
   const int* e_parent; const int* e_child; const Real* e_len;
   const long long* maps_off; const double* maps_len;
   int root;
-  const uint8_t* tipcode; uint8_t* node_state; uint32_t* meta; Real* PL;
+  const uint8_t* tipcode; long long TS;  // tip codes [T][TS]: rows padded to a multiple of 16 sites (4-byte aligned cp.async)
+  uint8_t* node_state; uint32_t* meta; Real* PL;
   uint32_t* slow_mask; int mask_words;  // production: per (chunk, word, site) bit mask of the branches left to k_paths_hard
   Real* pos1;  // production [E][S]: length of the first piece when m == 2 or the path has exactly one real jump
   Real* rec_len[2]; uint8_t* rec_st[2];  // double-buffered path records: written by sweep i into [i & 1], read by sweep i + 1
@@ -110,9 +111,9 @@ __global__ void __launch_bounds__(256) k_prune(ChainParams<Real> P) {
         const int ka = (int)(P.meta[(long long)ea * S + site] & 0xffffu) - 1;
         const int kb = (int)(P.meta[(long long)eb * S + site] & 0xffffu) - 1;
         Real va[NC], vb[NC];
-        if (a < P.T) tip_partial<Real, NC>(P.tipcode[(long long)a * S + site], n, parity, va);
+        if (a < P.T) tip_partial<Real, NC>(P.tipcode[(long long)a * P.TS + site], n, parity, va);
         else VecIO<Real, NS>::load(P.PL + ((long long)(a - P.T) * S + site) * n, n, va);
-        if (b < P.T) tip_partial<Real, NC>(P.tipcode[(long long)b * S + site], n, parity, vb);
+        if (b < P.T) tip_partial<Real, NC>(P.tipcode[(long long)b * P.TS + site], n, parity, vb);
         else VecIO<Real, NS>::load(P.PL + ((long long)(b - P.T) * S + site) * n, n, vb);
         apply_power<Real, NC, EXACT>(P, sBs, sPow, npow_s, n, kb, vb);
         apply_power<Real, NC, EXACT>(P, sBs, sPow, npow_s, n, ka, va);
@@ -225,9 +226,9 @@ __global__ void __launch_bounds__(256, MINB) k_prune_pipe(ChainParams<Real> P) {
       nd[u].ma = meta[(long long)e0.z * S];
       nd[u].mb = meta[(long long)e1.x * S];
       nd[u].ca = -1; nd[u].cb = -1;
-      if (e0.y < T) nd[u].ca = tip[(long long)e0.y * S];
+      if (e0.y < T) nd[u].ca = tip[(long long)e0.y * P.TS];
       else VecIO<Real, NS>::load(PLs + (long long)(e0.y - T) * rowPL, NS, nd[u].va);
-      if (e0.w < T) nd[u].cb = tip[(long long)e0.w * S];
+      if (e0.w < T) nd[u].cb = tip[(long long)e0.w * P.TS];
       else VecIO<Real, NS>::load(PLs + (long long)(e0.w - T) * rowPL, NS, nd[u].vb);
     }
   };
@@ -531,9 +532,9 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
     nd.ma = meta[(long long)e0.z * S];
     nd.mb = meta[(long long)e1.x * S];
     nd.ca = -1; nd.cb = -1;
-    if (e0.y < T) nd.ca = tip[(long long)e0.y * S];
+    if (e0.y < T) nd.ca = tip[(long long)e0.y * P.TS];
     else VecIO<Real, NS>::load(PLs + (long long)(e0.y - T) * rowPL, NS, nd.va);
-    if (e0.w < T) nd.cb = tip[(long long)e0.w * S];
+    if (e0.w < T) nd.cb = tip[(long long)e0.w * P.TS];
     else VecIO<Real, NS>::load(PLs + (long long)(e0.w - T) * rowPL, NS, nd.vb);
   };
   auto compute = [&](PruneNode<Real, NS>& nd) {
@@ -615,7 +616,7 @@ __global__ void __launch_bounds__(256) k_nodes(ChainParams<Real> P, uint32_t ite
           for (int j = 0; j < n; j++) w[j] = (Real)(j == ps);
           for (int r = 0; r < k; r++) matvec_t<Real, NC, EXACT>(sBs, n, w);
         }
-        if (v < P.T) tip_partial<Real, NC>(P.tipcode[(long long)v * S + site], n, parity, pl);
+        if (v < P.T) tip_partial<Real, NC>(P.tipcode[(long long)v * P.TS + site], n, parity, pl);
         else VecIO<Real, NS>::load(P.PL + ((long long)(v - P.T) * S + site) * n, n, pl);
 #pragma unroll
         for (int j = 0; j < n; j++) w[j] = Ar<Real, EXACT>::mul(w[j], pl[j]);
@@ -986,7 +987,7 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
         vs[q] = v;
         pss[q] = nst[(long long)pn * S];
         ks[q] = (int)(P.meta[(long long)e * S + site] & 0xffffu) - 1;
-        cds[q] = P.tipcode[(long long)v * S + site];
+        cds[q] = P.tipcode[(long long)v * P.TS + site];
       }
 #pragma unroll
       for (int q = 0; q < 4; q++) {

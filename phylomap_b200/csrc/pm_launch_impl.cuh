@@ -7,15 +7,14 @@ template <typename Real, int NS, bool EXACT>
 void Sweep<Real, NS, EXACT>::prune(const ChainParams<Real>& P, int grid, size_t smem, cudaStream_t st, int variant) {
   if constexpr (!EXACT && (NS == 2 || NS == 4)) {
     const size_t spipe = 2 * PM_SMEM_POW * NS * NS * sizeof(Real);
-    // 4x: clade order (needs 4-byte aligned tip rows: S % 4 == 0); 2x: level order (the kernel it replaced; also the
-    // fallback for other site counts)
+    // 4x: clade order (default); 2x: level order (the kernel it replaced, kept for comparison)
     auto clade = [&](auto kern, int depth) {
       const size_t sm = spipe + (size_t)PM_CLADE_SLOT * 8 * depth;
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
       kern<<<grid, 256, sm, st>>>(P);
     };
     if (variant == 20) k_prune_pipe<Real, NS, 2, 3><<<grid, 256, spipe, st>>>(P);  // two nodes per round
-    else if (variant == 21 || (P.S & 3) != 0) k_prune_pipe<Real, NS, 1, 4><<<grid, 256, spipe, st>>>(P);
+    else if (variant == 21) k_prune_pipe<Real, NS, 1, 4><<<grid, 256, spipe, st>>>(P);
     else if (variant == 41) clade(k_prune_clade<Real, NS, 4, 4>, 4);
     else if (variant == 43) clade(k_prune_clade<Real, NS, 8, 3>, 8);
     else if (variant == 44) clade(k_prune_clade<Real, NS, 16, 4>, 16);

@@ -63,9 +63,9 @@ __global__ void __launch_bounds__(256) k_loglik(ChainParams<Real> P, const Real*
       const int* en = P.up_entries + 5 * idx;
       const int pn = __ldg(en), a = __ldg(en + 1), ea = __ldg(en + 2), b = __ldg(en + 3), eb = __ldg(en + 4);
       Real ca[NC], cb[NC];
-      if (a < T) tip_partial<Real, NC>(P.tipcode[(long long)a * S + site], n, parity, ca);
+      if (a < T) tip_partial<Real, NC>(P.tipcode[(long long)a * P.TS + site], n, parity, ca);
       else VecIO<Real, NS>::load(P.PL + ((long long)(a - T) * S + site) * n, n, ca);
-      if (b < T) tip_partial<Real, NC>(P.tipcode[(long long)b * S + site], n, parity, cb);
+      if (b < T) tip_partial<Real, NC>(P.tipcode[(long long)b * P.TS + site], n, parity, cb);
       else VecIO<Real, NS>::load(P.PL + ((long long)(b - T) * S + site) * n, n, cb);
       const Real* __restrict__ Pa = TP + (size_t)ea * n * n;
       const Real* __restrict__ Pb = TP + (size_t)eb * n * n;

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ dw_pa
 // Tiled transpose through shared memory: reads coalesced along T, writes coalesced along S.  Validates the range.
 template <typename In>
 __global__ void __launch_bounds__(256) k_init_tips(const In* __restrict__ states, int ns, long long s_base, long long S,
-                                                   int T, int n, int parity, uint8_t* tipcode, uint8_t* node_state,
+                                                   long long TS, int T, int n, int parity, uint8_t* tipcode, uint8_t* node_state,
                                                    unsigned* err_flag) {
   __shared__ uint8_t tile[32][33];
   const int t0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
@@ -50,9 +50,8 @@ __global__ void __launch_bounds__(256) k_init_tips(const In* __restrict__ states
     const int t = t0 + r, s = s0 + threadIdx.x;
     if (s < ns && t < T) {
       const uint8_t code = tile[threadIdx.x][r];
-      const long long o = (long long)t * S + s_base + s;
-      tipcode[o] = code;
-      node_state[o] = parity ? (uint8_t)(code ? 0 : 1) : code;
+      tipcode[(long long)t * TS + s_base + s] = code;
+      node_state[(long long)t * S + s_base + s] = parity ? (uint8_t)(code ? 0 : 1) : code;
     }
   }
 }
