@@ -1,15 +1,15 @@
 // The four kernels of one MCMC sweep:
 //   K1 k_prune   Felsenstein pruning with P_e := B^(m_e - 1)        replaces makePLrcpp* (src/phylomap.cpp:490-529,
-//                                                                    1077-1088, 1938-1949) + mmmmvFORpl (:446-450)
+//      (production, n = 2 / 4: k_prune_clade)                        1077-1088, 1938-1949) + mmmmvFORpl (:446-450)
 //   K2 k_nodes   root draw + top-down node (and hidden-tip) draws    replaces sampleinternalnodes* (:535-738, 1091-1164,
-//                                                                    1314-1403, 1952-2046) + updatenodestates (:460-475)
+//      (production, n = 2 / 4: k_nodes_clade)                        1314-1403, 1952-2046) + updatenodestates (:460-475)
 //   K3 k_paths   per (site, branch): regenerate the virtual jumps of the previous sweep, redraw the segment states
 //                (resamplebranchstates :264-308), merge + count (shortener :44-73 / shortenerbf :997-1028), draw the
 //                new virtual jumps (:391-410), accumulate dwell times (:745-757), block-level reduction
 //   K4 k_reduce  deterministic reduction of the per-block partial sums into one row of sufficient statistics
 //
 // Data layout in HBM (site-minor everywhere, so a warp = 32 consecutive sites reads/writes contiguous bytes):
-//   tipcode    [T][S]      u8   observed tip state (0-based) or observed parity (hidden-rate models)
+//   tipcode    [T][TS]     u8   observed tip state (0-based) or observed parity (hidden-rate models); TS = S rounded up to 16
 //   node_state [2T-1][S]   u8   current state of every node
 //   meta       [E][S]      u32  m (pieces on the branch, bits 0-15) | real jumps nj (16-23) | first state (24-31)
 //   PL         [T-1][S][n] Real partial likelihoods of the internal nodes (one 16-byte vector per site for n=4 fp32)
@@ -629,11 +629,8 @@ __global__ void __launch_bounds__(256) k_nodes(ChainParams<Real> P, uint32_t ite
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K2, production arithmetic, 2 or 4 states.  One Philox block feeds FOUR consecutive entries of the top-down
-// list (the block is keyed by list position / 4, the word by position % 4), which cuts the dominant cost of the
-// draw — ten Philox rounds per node — by four.  A warp owns a group of four positions.
-// ------------------------------------------------------------------------------------------------
+// uniform in (0, 1) from one Philox word (production node draws: one block feeds four nodes, which cuts the dominant
+// cost of a draw -- ten Philox rounds -- by four)
 template <typename Real> __device__ __forceinline__ Real u01_from_word(uint32_t x);
 template <> __device__ __forceinline__ float u01_from_word<float>(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 template <> __device__ __forceinline__ double u01_from_word<double>(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
