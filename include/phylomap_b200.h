@@ -42,8 +42,8 @@ extern "C" {
 #define PM_ERR_ARG 1        /* malformed input (message in err) */
 #define PM_ERR_CUDA 2       /* CUDA runtime failure / no usable device */
 #define PM_ERR_SAMPLE 3     /* RcppArmadillo::sample would have thrown (NA / negative / all-zero weights) */
-#define PM_ERR_CAPACITY 4   /* a capacity was exceeded: the run records of a branch chunk (pm_options.path_capacity), 63 state
-                               changes on one branch at one site, or 65535 jump points on one branch */
+#define PM_ERR_CAPACITY 4   /* a capacity was exceeded: the run records of a branch chunk (pm_options.path_capacity), 65535 jump
+                               points on one branch, or (deterministic mode only) 63 state changes on one branch at one site */
 #define PM_ERR_REPLAY 5     /* replay table exhausted */
 
 /* precision of the device arithmetic */

@@ -22,7 +22,7 @@
 #define PM_DE_REPLAY 32u
 #define PM_DE_INCONSISTENT 64u
 #define PM_DE_BAD_STATE 128u
-#define PM_DE_JUMP_LIMIT 256u  // more real jumps on one branch than a path can hold (63)
+#define PM_DE_JUMP_LIMIT 256u  // deterministic mode: more real jumps on one branch than a path can hold (63)
 
 namespace pm {
 

@@ -439,8 +439,8 @@ struct ChainT : pm_chain {
                                                     : "Not enough positive probabilities");
     if (f & PM_DE_REPLAY) fail(PM_ERR_REPLAY, "replay table exhausted");
     if (f & PM_DE_JUMP_LIMIT)
-      fail(PM_ERR_CAPACITY, "a branch carries more than 63 state changes at one site (a path holds at most 64 runs); the branch is "
-                            "saturated: rescale the tree or the rates");
+      fail(PM_ERR_CAPACITY, "a branch carries more than 63 state changes at one site: the deterministic mode holds at most 64 runs "
+                            "per path (the production arithmetic has no such limit)");
     if (f & PM_DE_PATH_CAP) fail(PM_ERR_CAPACITY, "the run records of a branch chunk overflowed; raise pm_options.path_capacity");
     if (f & PM_DE_M_OVERFLOW) fail(PM_ERR_CAPACITY, "more than 65535 pieces on one branch");
     fail(PM_ERR_CUDA, "inconsistent chain state (device flag %u)", f);
@@ -570,7 +570,14 @@ struct ChainT : pm_chain {
             const long long m0 = moff[e + 1] - moff[e];
             if (m0 >= 3) init3 += m0;
           }
-          cap = std::max<long long>(chernoff_records_cap(lams, 1e-18), init3) + 4;
+          // ... or, simpler and valid for any rate: every path stores at most (jumps + 1) records (+ a header), and the
+          // jumps of the chunk together are dominated by one Poisson variable
+          double lam_sum = 0, lam_max = 0;
+          for (double l : lams) { lam_sum += l; lam_max = std::max(lam_max, l); }
+          const long long simple = (long long)poisson_cap(lam_sum, 1e-18) + 2LL * (b1 - b0);
+          long long stat = simple;
+          if (lam_max < 200.0) stat = std::min(stat, chernoff_records_cap(lams, 1e-18));  // (its series stops at 400 terms)
+          cap = std::max<long long>(stat, init3) + 4;
         }
         if (cap > (1 << 28)) fail(PM_ERR_CAPACITY, "path capacity of a branch chunk too large");
         cap = (cap + 3) & ~3;  // keep every slice 16-byte aligned
@@ -984,7 +991,8 @@ struct ChainT : pm_chain {
       return nj + 1;
     }
     // production: meta = m | nj << 16 (6 bits) | s0 << 22 | s1 << 27; pos1 for nj == 1; records for nj >= 2
-    const int nj = (m >> 16) & 0x3f, s0 = (m >> 22) & 0x1f, s1 = (m >> 27) & 0x1f;
+    int nj = (m >> 16) & 0x3f;
+    const int s0 = (m >> 22) & 0x1f, s1 = (m >> 27) & 0x1f;
     Real Le;
     CK(cudaMemcpy(&Le, t.e_len.template as<Real>() + e, sizeof(Real), cudaMemcpyDeviceToHost));
     if (nj == 0) {
@@ -1000,7 +1008,14 @@ struct ChainT : pm_chain {
     }
     Real off;  // paths with two or more real jumps: pos1 holds the offset of their records in the site's slice
     CK(cudaMemcpy(&off, t.pos1.template as<Real>() + (size_t)e * t.S + site, sizeof(Real), cudaMemcpyDeviceToHost));
-    const long long pos = (long long)off;
+    long long pos = (long long)off;
+    if (nj == 63) {  // 64 runs or more: a header record holds the count
+      Real cntv;
+      CK(cudaMemcpy(&cntv, t.rec_len[buf].template as<Real>() + (size_t)t.cap_off_h[c] * t.S + (size_t)site * cap_c + pos, sizeof(Real),
+                    cudaMemcpyDeviceToHost));
+      nj = (int)cntv - 1;
+      pos += 1;
+    }
     records(pos, nj + 1);
     return nj + 1;
   }

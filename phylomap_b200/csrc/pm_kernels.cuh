@@ -1278,7 +1278,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     const long long pe = (long long)eb * S + site;
     const uint32_t mt = P.meta[pe];
     const int m = (int)(mt & 0xffffu);
-    const int nj = first ? 0 : (int)((mt >> 16) & 0x3fu);
+    const int njf = first ? 0 : (int)((mt >> 16) & 0x3fu);  // real jumps; 63 = "63 or more, see the record header"
     const int ps = P.node_state[(long long)__ldg(P.e_parent + eb) * S + site];
     const int cs = P.node_state[(long long)__ldg(P.e_child + eb) * S + site];
     const Real Le = __ldg(P.e_len + eb);
@@ -1287,34 +1287,17 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     if (!first) pair_block(P.rng, (uint32_t)site, iter - 1u, (uint32_t)eb, po_old);
     const uint32_t oA = (eb & 1) ? po_old[2] : po_old[0], oB = (eb & 1) ? po_old[3] : po_old[1];
     const uint32_t nA = (eb & 1) ? po_new[2] : po_new[0], nB = (eb & 1) ? po_new[3] : po_new[1];
-    WordStream cnt_old; cnt_old.open(P.rng, (uint32_t)site, first ? iter : iter - 1u, K_BRCNT, (uint32_t)eb, 0u);
-    WordStream cnt_new; cnt_new.open(P.rng, (uint32_t)site, iter, K_BRCNT, (uint32_t)eb, 0u);
-    Stream gst; gst.open(P.rng, (uint32_t)site, iter, K_BRSTATE, (uint32_t)eb, P.err_flag);
-
-    // ---- the previous path, run by run ----
+    // nj == 1: pos1 = length of run 0; nj >= 2: pos1 = offset of the path's records in the site's slice.  A path with 64
+    // or more runs starts with a header record holding its run count.
+    const Real p1 = (!first && (njf >= 1)) ? P.pos1[pe] : (Real)0;
+    int rd0 = (njf >= 2) ? (int)p1 : 0;
+    int nj = njf;
+    if (njf == 63) {
+      const int q = min(rd0, cap_c - 1);
+      nj = max(63, (int)rd_len[sbase + q] - 1);
+      rd0 += 1;
+    }
     const int nrun = nj + 1;
-    int jrun = 0;
-    RunPieces<Real> rp;
-    long long cp = first ? P.maps_off[eb] : 0;
-    const Real p1 = (!first && (nj >= 1)) ? P.pos1[pe] : (Real)0;  // nj == 1: length of run 0; nj >= 2: record offset
-    const int rd0 = (nj >= 2) ? (int)p1 : 0;
-    auto open_run = [&](int r) {
-      Real len; int st;
-      if (nj == 0) { len = Le; st = (int)((mt >> 22) & 0x1fu); }
-      else if (nj == 1) { len = r == 0 ? p1 : PN::sub(Le, p1); st = (int)((mt >> (r == 0 ? 22 : 27)) & 0x1fu); }
-      else { const int q = min(rd0 + r, cap_c - 1); len = rd_len[sbase + q]; st = rd_st[sbase + q]; }
-      const uint32_t cw = r == 0 ? oA : r == 1 ? oB : cnt_old.next();
-      rp.begin(P.rng, (uint32_t)site, iter - 1u, (uint32_t)eb, r, len, s_rate_old[st], cw, nj == 0, oB);
-    };
-    if (!first) open_run(0);
-    auto next_piece = [&]() -> Real {
-      if (first) return (Real)P.maps_len[cp++];
-      if (jrun >= nrun) { errbits |= PM_DE_INCONSISTENT; return (Real)0; }
-      bool last;
-      const Real piece = rp.next(last);
-      if (last) { jrun++; if (jrun < nrun) open_run(jrun); }
-      return piece;
-    };
 
     // ---- the new path ----
     // Runs are emitted in order; the first two are held in registers until a third one shows up (a path with at most
@@ -1323,92 +1306,144 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     Real L0 = 0, L1 = 0, gap0 = 0;
     bool gaps0 = false;
     Real bufL[PM_LOCAL_PATH_MAX]; uint8_t bufS[PM_LOCAL_PATH_MAX];  // runs 2.. of a long path (local memory, rarely touched)
-    auto emit = [&](Real L, int s) {
-      const int r = nout;
-      if (r == 0) { L0 = L; S0 = s; }
-      else if (r == 1) { L1 = L; S1 = s; }
-      else if (r < PM_LOCAL_PATH_MAX) { bufL[r] = L; bufS[r] = (uint8_t)s; }
-      add_dwell(s, L);
-      const Real rate = s_rate_new[s];
-      // the count word of run r is consumed whether or not the run uses it (gap mode, zero rate): the next sweep's
-      // open_run() takes one word per run when it regenerates this path
-      const uint32_t cw = r == 0 ? nA : r == 1 ? nB : cnt_new.next();
-      int k = 0;
-      if (rate_ok(rate)) {
-        const Real lam = PN::mul(rate, L);
-        if (lam > (Real)PM_LAMBDA_INV) {
-          WordStream g; g.open(P.rng, (uint32_t)site, iter, K_BRGAP, (uint32_t)eb, (uint32_t)r);
-          Real x = 0;
-          for (;;) {
-            const Real gp = PN::div(PN::neglog(PN::u01(g.next())), rate);
-            const Real t2 = PN::add(x, gp);
-            if (!(t2 < L) || k > 70000) break;
-            x = t2; k++;
-            if (r == 0 && k == 1) gap0 = gp;
-          }
-          if (r == 0) gaps0 = true;
-        } else {
-          k = poisson_inv<Real>(lam, cw);
-        }
-      }
-      if (r == 0) k0 = k;
-      newm += k + 1;
-      nout++;
-    };
 
-    int cur_state = (m == 1) ? cs : ps;
-    Real cur_len = next_piece();
-    int prev = cur_state;
-    for (int p = 1; p < m; p++) {
-      int st;
-      if (p == m - 1) st = cs;
-      else {
-        const int jd = m - p - 1;  // beta_jd = Bs^jd e_cs
-        Real wv[NC];
-        const Real* M = (jd < npow_s) ? (sPow + jd * n * n) : (jd < P.jcap ? P.ppow + (size_t)jd * n * n : nullptr);
-        if (M) {
-#pragma unroll
-          for (int c = 0; c < n; c++) wv[c] = M[c * n + cs];
-        } else {
-#pragma unroll
-          for (int c = 0; c < n; c++) wv[c] = (Real)(c == cs);
-          for (int r = 0; r < jd; r++) matvec<Real, NC, false>(sBs, n, wv);
+    // One pass over the branch: regenerate the previous path piece by piece, redraw the interior states, merge, emit the
+    // runs.  All uniforms come from keyed streams opened here, so a second pass reproduces the first: a path with more
+    // runs than the local buffer holds (a saturated branch) is walked again with `replay` set, and this time its runs go
+    // straight to the records reserved at `wbase` -- nothing else is done twice (no counts, dwell times or draws of new
+    // virtual jumps).
+    bool replay = false;
+    int wbase = 0, total_runs = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {  // pass 1 only for a path longer than the local buffer (see below)
+      WordStream cnt_old; cnt_old.open(P.rng, (uint32_t)site, first ? iter : iter - 1u, K_BRCNT, (uint32_t)eb, 0u);
+      WordStream cnt_new; cnt_new.open(P.rng, (uint32_t)site, iter, K_BRCNT, (uint32_t)eb, 0u);
+      Stream gst; gst.open(P.rng, (uint32_t)site, iter, K_BRSTATE, (uint32_t)eb, P.err_flag);
+      int jrun = 0;
+      RunPieces<Real> rp;
+      long long cp = first ? P.maps_off[eb] : 0;
+      auto open_run = [&](int r) {
+        Real len; int st;
+        if (nj == 0) { len = Le; st = (int)((mt >> 22) & 0x1fu); }
+        else if (nj == 1) { len = r == 0 ? p1 : PN::sub(Le, p1); st = (int)((mt >> (r == 0 ? 22 : 27)) & 0x1fu); }
+        else { const int q = min(rd0 + r, cap_c - 1); len = rd_len[sbase + q]; st = rd_st[sbase + q]; }
+        const uint32_t cw = r == 0 ? oA : r == 1 ? oB : cnt_old.next();
+        rp.begin(P.rng, (uint32_t)site, iter - 1u, (uint32_t)eb, r, len, s_rate_old[st], cw, nj == 0, oB);
+      };
+      if (!first) open_run(0);
+      auto next_piece = [&]() -> Real {
+        if (first) return (Real)P.maps_len[cp++];
+        if (jrun >= nrun) { errbits |= PM_DE_INCONSISTENT; return (Real)0; }
+        bool last;
+        const Real piece = rp.next(last);
+        if (last) { jrun++; if (jrun < nrun) open_run(jrun); }
+        return piece;
+      };
+      nout = 0;
+      auto emit = [&](Real L, int s) {
+        const int r = nout;
+        if (replay) {  // records only; the header sits at wbase
+          wr_len[sbase + wbase + 1 + r] = L; wr_st[sbase + wbase + 1 + r] = (uint8_t)s;
+          nout++;
+          return;
         }
+        if (r == 0) { L0 = L; S0 = s; }
+        else if (r == 1) { L1 = L; S1 = s; }
+        else if (r < PM_LOCAL_PATH_MAX) { bufL[r] = L; bufS[r] = (uint8_t)s; }
+        add_dwell(s, L);
+        const Real rate = s_rate_new[s];
+        // the count word of run r is consumed whether or not the run uses it (gap mode, zero rate): the next sweep's
+        // open_run() takes one word per run when it regenerates this path
+        const uint32_t cw = r == 0 ? nA : r == 1 ? nB : cnt_new.next();
+        int k = 0;
+        if (rate_ok(rate)) {
+          const Real lam = PN::mul(rate, L);
+          if (lam > (Real)PM_LAMBDA_INV) {
+            WordStream g; g.open(P.rng, (uint32_t)site, iter, K_BRGAP, (uint32_t)eb, (uint32_t)r);
+            Real x = 0;
+            for (;;) {
+              const Real gp = PN::div(PN::neglog(PN::u01(g.next())), rate);
+              const Real t2 = PN::add(x, gp);
+              if (!(t2 < L) || k > 70000) break;
+              x = t2; k++;
+              if (r == 0 && k == 1) gap0 = gp;
+            }
+            if (r == 0) gaps0 = true;
+          } else {
+            k = poisson_inv<Real>(lam, cw);
+          }
+        }
+        if (r == 0) k0 = k;
+        newm += k + 1;
+        nout++;
+      };
+
+      int cur_state = (m == 1) ? cs : ps;
+      Real cur_len = next_piece();
+      int prev = cur_state;
+      for (int p = 1; p < m; p++) {
+        int st;
+        if (p == m - 1) st = cs;
+        else {
+          const int jd = m - p - 1;  // beta_jd = Bs^jd e_cs
+          Real wv[NC];
+          const Real* M = (jd < npow_s) ? (sPow + jd * n * n) : (jd < P.jcap ? P.ppow + (size_t)jd * n * n : nullptr);
+          if (M) {
 #pragma unroll
-        for (int c = 0; c < n; c++) wv[c] = sB[prev * n + c] * wv[c];
-        st = categorical<Real, NC, false>(wv, n, gst.next(), P.err_flag);
+            for (int c = 0; c < n; c++) wv[c] = M[c * n + cs];
+          } else {
+#pragma unroll
+            for (int c = 0; c < n; c++) wv[c] = (Real)(c == cs);
+            for (int r = 0; r < jd; r++) matvec<Real, NC, false>(sBs, n, wv);
+          }
+#pragma unroll
+          for (int c = 0; c < n; c++) wv[c] = sB[prev * n + c] * wv[c];
+          st = categorical<Real, NC, false>(wv, n, gst.next(), P.err_flag);
+        }
+        const Real len = next_piece();
+        if (full && !replay) atomicAdd(&s_cnt[prev * n + st], 1u);
+        if (st == cur_state) cur_len = cur_len + len;
+        else {
+          emit(cur_len, cur_state);
+          if (!full && !replay) atomicAdd(&s_cnt[cur_state * n + st], 1u);
+          cur_state = st; cur_len = len;
+        }
+        prev = st;
       }
-      const Real len = next_piece();
-      if (full) atomicAdd(&s_cnt[prev * n + st], 1u);
-      if (st == cur_state) cur_len = cur_len + len;
-      else {
-        emit(cur_len, cur_state);
-        if (!full) atomicAdd(&s_cnt[cur_state * n + st], 1u);
-        cur_state = st; cur_len = len;
+      if (!first && (jrun != nrun)) errbits |= PM_DE_INCONSISTENT;  // the regenerated pieces must add up to m
+      // a single-run path spans the whole branch: take its length from the tree, not from the sum of its pieces
+      // ... and the second run of a two-run path is what is left after the first (the form the next sweep rebuilds it in)
+      emit(nout == 0 ? Le : nout == 1 ? PN::sub(Le, L0) : cur_len, cur_state);
+      if (replay) {
+        if (nout != total_runs) errbits |= PM_DE_INCONSISTENT;
+        break;
       }
-      prev = st;
-    }
-    if (!first && (jrun != nrun)) errbits |= PM_DE_INCONSISTENT;  // the regenerated pieces must add up to m
-    // a single-run path spans the whole branch: take its length from the tree, not from the sum of its pieces
-    // ... and the second run of a two-run path is what is left after the first (the form the next sweep rebuilds it in)
-    emit(nout == 0 ? Le : nout == 1 ? PN::sub(Le, L0) : cur_len, cur_state);
-    if (newm > 65535) { errbits |= PM_DE_M_OVERFLOW; newm = 65535; }
-    if (nout > 63) { errbits |= PM_DE_JUMP_LIMIT; nout = 63; }
-    if (nout == 1) {
-      if (k0 == 1) P.pos1[pe] = gaps0 ? gap0 : next_order_stat<Real>((Real)0, Le, 1, nB);
-    } else if (nout == 2) P.pos1[pe] = L0;
-    else {
+      if (newm > 65535) { errbits |= PM_DE_M_OVERFLOW; newm = 65535; }
+      if (nout == 1) {
+        if (k0 == 1) P.pos1[pe] = gaps0 ? gap0 : next_order_stat<Real>((Real)0, Le, 1, nB);
+        break;
+      }
+      if (nout == 2) { P.pos1[pe] = L0; break; }
       // three or more runs: a contiguous block of records in the site's slice; its offset goes where a shorter path
-      // keeps the length of its first run
-      const int base = atomicAdd(&s_wr[tsite], nout);
-      if (base + nout <= cap_c) {
-        wr_len[sbase + base] = L0; wr_st[sbase + base] = (uint8_t)S0;
-        wr_len[sbase + base + 1] = L1; wr_st[sbase + base + 1] = (uint8_t)S1;
-        for (int r = 2; r < nout; r++) { wr_len[sbase + base + r] = bufL[r]; wr_st[sbase + base + r] = bufS[r]; }
-      } else errbits |= PM_DE_PATH_CAP;
+      // keeps the length of its first run.  64 runs or more: a header record with the count comes first.
+      const bool longp = nout >= 64;
+      const int need = nout + (longp ? 1 : 0);
+      const int base = atomicAdd(&s_wr[tsite], need);
       P.pos1[pe] = (Real)base;
+      if (base + need > cap_c) { errbits |= PM_DE_PATH_CAP; break; }
+      if (longp) { wr_len[sbase + base] = (Real)nout; wr_st[sbase + base] = 0; }
+      if (nout > PM_LOCAL_PATH_MAX) {  // not all runs were kept: walk the branch once more, writing them in place
+        replay = true; wbase = base; total_runs = nout;
+        continue;
+      }
+      const int o = base + (longp ? 1 : 0);
+      wr_len[sbase + o] = L0; wr_st[sbase + o] = (uint8_t)S0;
+      wr_len[sbase + o + 1] = L1; wr_st[sbase + o + 1] = (uint8_t)S1;
+      for (int r = 2; r < nout; r++) { wr_len[sbase + o + r] = bufL[r]; wr_st[sbase + o + r] = bufS[r]; }
+      break;
     }
-    P.meta[pe] = PM_META(newm, nout - 1, S0, S1);
+    if (replay) nout = total_runs;
+    P.meta[pe] = PM_META(newm, min(nout - 1, 63), S0, S1);
       }  // have
     }    // rounds
   }      // words

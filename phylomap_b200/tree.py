@@ -33,10 +33,34 @@ class PhyloTree:
 
     @classmethod
     def from_mapping(cls, z):
+        """From the R list itself: a dict with the R field names, e.g. what `rds.read_rds` returns for a tree saved with
+        saveRDS (inst/extdata/Squamate/phylomap_compatible_squamate_tree.RData)."""
         if isinstance(z, cls):
             return z
-        return cls(z["edge"], z.get("edge.length", [float(np.sum(m)) for m in z["maps"]]), z.get("states"),
-                   z.get("maps"), z.get("mapnames"))
+        from .rds import plain
+        z = plain(z)
+        states = z.get("states")
+        if states is not None:
+            states = np.asarray(states).astype(np.int32)  # R hands them over as doubles
+        return cls(z["edge"], z.get("edge.length", [float(np.sum(m)) for m in z["maps"]]), states,
+                   z.get("maps"), z.get("mapnames"), z.get("tip.label"))
+
+    @classmethod
+    def read_rds(cls, path):
+        """readRDS(path) of a phylomap-compatible tree."""
+        from .rds import read_rds
+        return cls.from_mapping(read_rds(path))
+
+    def to_mapping(self):
+        """The R list (for `rds.write_rds`): field names and 1-based conventions of the reference."""
+        out = {"edge": self.edge, "Nnode": np.array([self.Nnode], dtype=np.int32), "edge.length": self.edge_length,
+               "maps": [m for m in self.maps], "mapnames": [m for m in self.mapnames]}
+        if self.tip_label is not None:
+            out["tip.label"] = list(self.tip_label)
+        if self.states is not None:
+            out["states"] = np.asarray(self.states, dtype=np.float64)
+        from .rds import RObject
+        return RObject(out, {"class": ["phylo"], "order": ["cladewise"]})
 
     def with_states(self, states, halve_tip_branches=True, segments=None):
         """Attach tip data the way simulate_2_state_tree does (R/simulate_2_state_tree.R:16-30): every tip branch

@@ -1,6 +1,7 @@
 """Seeded inputs shared by the oracle tests (CPU) and the parity tests (GPU)."""
 import numpy as np
 
+import phylomap_b200 as pb
 from phylomap_b200 import synth
 
 Q2 = np.array([[-0.1, 0.1], [0.1, -0.1]])
@@ -41,3 +42,16 @@ def tree_hidden(Q, T=20, S=1, seed=1, mean_branch=1.0, segments=3):
     t = synth.yule_tree(T, seed, mean_branch=mean_branch)
     n = Q.shape[0]
     return synth.simulate_4_state_tree(500 + seed, t, Q, np.full(n, 1.0 / n), n_sites=S, segments=segments)
+
+
+def squamate_tree():
+    """The reference's Squamate tree (3 951 tips, 100 segments per branch) from the derived fixture
+    tests/golden/squamate_tree.npz (tests/golden/make_squamate_fixture.py).  Like the file it comes from it is a template:
+    its `states` hold the placeholder -10 for most tips (R/Squamate_tree_setup.R:60) and the vignette simulates tip data
+    onto it (`simulate_2_state_tree(seed = 101, atree, Q2, pid2)`, Squamate_DIC_model_selection.Rnw:93)."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "squamate_tree.npz"))
+    off, ml, ms = d["maps_off"], d["maps_len"], d["maps_state"].astype(np.int32)   # (each access decompresses: once)
+    maps = [ml[off[e]:off[e + 1]] for e in range(len(off) - 1)]
+    names = [ms[off[e]:off[e + 1]] for e in range(len(off) - 1)]
+    return pb.PhyloTree(d["edge"], d["edge_length"], d["states"].astype(np.int32), maps, names)

@@ -369,3 +369,25 @@ def test_medium_tree_many_chunks(oracle):
     ch = pb.Chain(capi.PM_V_BIGTREE, z, Q.copy(), pid, Om, N, seed=7, **DET)
     _compare_rows(ch.run(), ref, 4, int_cols=set(range(4, 16)))
     _compare_state(ch, orc, z, 70, z.E, n_paths=60)
+
+
+def test_squamate_vignette_configuration(oracle):
+    """The reference's own tree in the DIC vignette's setup (Squamate_DIC_model_selection.Rnw:78-104): 3 951 tips, every
+    branch cut into 100 segments, Q2, prior2r, Omega = 10 -- about 877 000 jump points per site and sweep, jump counts in
+    the thousands on the long branches.  Deterministic mode against the oracle, two sites."""
+    Q2 = np.array([[-0.001, 0.001], [0.006, -0.006]])
+    prior = np.array([0.55, 1.0, 0.55, 1.0])
+    z = synth.simulate_2_state_tree(101, cases.squamate_tree(), Q2, cases.PID2, n_sites=2, segments=100)
+    N, Om = 3, 10.0
+    orc, ref = _oracle(oracle, oracle.DIC2S, [z], Q2.copy(), cases.PID2, Om, N, prior=prior)
+    ch = pb.Chain(capi.PM_V_DIC2S, z, np.asfortranarray(Q2.copy()), cases.PID2, Om, N, prior=prior, seed=7, **DET)
+    got = ch.run(N)
+    _compare_rows(got, ref, 2, int_cols={2, 3, 4, 5, 8}, tol=1e-8)
+    np.testing.assert_allclose(got[:, 9], ref[:, 9], rtol=1e-9)
+    assert np.array_equal(ch.node_states(), orc.node_states(0))
+    assert np.array_equal(ch.piece_counts(), orc.piece_counts(0))
+    assert ch.piece_counts().max() > 1000
+    # production arithmetic on the same input: the invariants of a row
+    fast = pb.sumstatMCMC2sDICt(z, np.asfortranarray(Q2.copy()), cases.PID2, Om, 4, prior, seed=7, precision="f64")
+    np.testing.assert_allclose(fast[:, :2].sum(1), 2 * z.edge_length.sum(), rtol=1e-9)
+    assert np.all(np.abs(fast[1:, 2:6].sum(1) / (2 * Om * z.edge_length.sum()) - 1) < 0.01)

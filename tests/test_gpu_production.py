@@ -185,12 +185,34 @@ def test_record_capacity_overflow_is_reported():
     ok = pb.sumstatMCMC(z, Q, cases.PID2, 2.0, 10, seed=1, precision="f32")  # default sizing copes
     np.testing.assert_allclose(ok[:, :2].sum(1), 40 * z.edge_length.sum(), rtol=2e-4)
     assert ok[3:, 2:].mean() > 0.5 * 40 * z.edge_length.sum() * 0.9 / 2
-    # a saturated branch (more than 63 state changes at one site) is reported as such, in both arithmetic modes
+    # the deterministic mode holds at most 64 runs per path and says so on a saturated branch
     zs = cases.tree2(T=6, S=8, seed=3, mean_branch=150.0)
-    for kw in (dict(precision="f32"), dict(mode="deterministic")):
-        with pytest.raises(capi.PhylomapError) as e:
-            pb.sumstatMCMC(zs, Q, cases.PID2, 2.0, 10, seed=1, **kw)
-        assert e.value.code == capi.PM_ERR_CAPACITY and "63" in e.value.msg
+    with pytest.raises(capi.PhylomapError) as e:
+        pb.sumstatMCMC(zs, Q, cases.PID2, 2.0, 10, seed=1, mode="deterministic")
+    assert e.value.code == capi.PM_ERR_CAPACITY and "63" in e.value.msg
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_saturated_branches_long_paths(oracle, precision):
+    """Branches with hundreds of state changes (rate 1 on lengths ~150): paths of 64 runs and more keep their run count in
+    a header record and are written in a second, replayed pass.  Posterior of the jump counts against the oracle chain."""
+    Q = np.array([[-1.0, 1.0], [1.0, -1.0]])
+    z = cases.tree2(T=6, S=1, seed=3, mean_branch=150.0)
+    N, thin, burn = 3000, 6, 200
+    ref = oracle.OracleRun(oracle.PLAIN, [z.oracle_dict()], Q, cases.PID2, 2.0, N, rng_mode=oracle.SEQUENTIAL, seed=11).run()[burn::thin]
+    ch = pb.Chain(capi.PM_V_PLAIN, z, Q, cases.PID2, 2.0, N, seed=5, precision=precision)
+    got = ch.run(N)[burn::thin]
+    np.testing.assert_allclose(got[:, :2].sum(1), z.edge_length.sum(), rtol=1e-5)
+    assert got[:, 2:].sum(1).mean() > 0.8 * z.edge_length.sum()       # ~ one change per unit length
+    for col, name in [(2, "N01"), (3, "N10"), (0, "R0")]:
+        p = stats.ks_2samp(got[:, col], ref[:, col]).pvalue
+        assert p > 0.005, "%s: KS p = %.4f" % (name, p)
+    e_long = int(np.argmax(z.edge_length))                            # the stored path of the longest branch adds up
+    ln, st = ch.path(0, e_long, cap=4096)
+    assert len(ln) > 64 and np.all(st[1:] != st[:-1])
+    np.testing.assert_allclose(ln.sum(), z.edge_length[e_long], rtol=1e-4)
+    big = pb.sumstatMCMC(cases.tree2(T=6, S=300, seed=3, mean_branch=150.0), Q, cases.PID2, 2.0, 12, seed=2, precision=precision)
+    np.testing.assert_allclose(big[:, :2].sum(1), 300 * z.edge_length.sum(), rtol=1e-4)
 
 
 @pytest.mark.parametrize("precision", ["f32", "f64"])

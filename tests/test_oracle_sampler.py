@@ -167,3 +167,18 @@ def test_dic_loglik_against_scipy(oracle):
                 PL[z.edge[ea, 0] - 1] = v / v.sum()
             tot += np.log(PL[root - 1] @ cases.PID2) + S
         np.testing.assert_allclose(dic[i, 9], tot, rtol=1e-12)
+
+
+def test_squamate_tree_vignette_configuration(oracle):
+    """The DIC vignette's 2-state setup on the reference's own tree (Squamate_DIC_model_selection.Rnw:78-104: Q2, pid2,
+    prior2r, Omega = 10): a sweep adds ~Omega x tree length = 877 000 jump points; every row keeps the invariants."""
+    Q2 = np.array([[-0.001, 0.001], [0.006, -0.006]])
+    z = synth.simulate_2_state_tree(101, cases.squamate_tree(), Q2, cases.PID2, segments=100)
+    N = 3
+    run = oracle.OracleRun(oracle.DIC2S, [z.oracle_dict()], Q2, cases.PID2, 10.0, N, prior=np.array([0.55, 1, 0.55, 1.0]), seed=3)
+    rows = run.run()
+    assert rows.shape == (N, 10)
+    np.testing.assert_allclose(rows[:, :2].sum(1), z.edge_length.sum(), rtol=1e-9)
+    jumps = rows[:, 2:6].sum(1)                       # all jump points, virtual ones included
+    assert np.all(np.abs(jumps[1:] / (10.0 * z.edge_length.sum()) - 1) < 0.01)
+    assert np.all(rows[:, 6:8] > 0) and np.all(rows[:, 9] < 0) and np.all(np.isfinite(rows[:, 9]))
