@@ -17,6 +17,24 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 fails, done = [], 0
 
 
+def caterpillar(T, mean_branch, r):
+    """Ladder tree: the deepest possible schedule (T - 1 levels)."""
+    edge, node = [], T + 1
+    for t in range(T, 2, -1):          # internal nodes T+1 .. 2T-1 on the spine, tip t hangs off each
+        edge.append((node, t)); edge.append((node, node + 1)); node += 1
+    edge.append((node, 1)); edge.append((node, 2))
+    return pb.PhyloTree(np.array(edge, dtype=np.int32), r.exponential(mean_branch, size=len(edge)) + 1e-3)
+
+
+def make_tree(T, seed, mean_branch, r):
+    shape = r.choice(["yule", "yule", "caterpillar", "balanced"])
+    if shape == "caterpillar" and T > 2:
+        return caterpillar(T, mean_branch, r)
+    if shape == "balanced" and T >= 4:
+        return synth.balanced_tree(int(np.log2(T)), branch=mean_branch)
+    return synth.yule_tree(T, seed, mean_branch=mean_branch)
+
+
 def dense_q(n, r):
     Q = r.uniform(0.02, 0.6, size=(n, n))
     np.fill_diagonal(Q, 0)
@@ -27,7 +45,7 @@ def dense_q(n, r):
 for c in range(ncfg):
     kind = rng.choice(["plain", "sparse", "bigtree", "bf", "ks", "mt", "ksmt", "dic2", "dicks"])
     prec = rng.choice(["f32", "f64"])
-    T = int(rng.choice([3, 5, 17, 64, 200, 513]))
+    T = int(rng.choice([2, 3, 5, 17, 64, 200, 513]))
     S = int(rng.choice([1, 7, 33, 129, 300]))
     mb = float(rng.choice([0.05, 0.3, 1.5, 6.0]))
     seg = int(rng.choice([2, 3, 5]))
@@ -38,19 +56,19 @@ for c in range(ncfg):
         if kind in ("bf", "mt", "dic2"):
             n, Q, pid = 2, cases.Q2 * float(rng.choice([1, 5])), cases.PID2
             Om = 2.5 * np.abs(np.diag(Q)).max()
-            tree = synth.yule_tree(T, seed % 1000, mean_branch=mb / np.abs(np.diag(Q)).max() * 0.1)
+            tree = make_tree(T, seed % 1000, mb / np.abs(np.diag(Q)).max() * 0.1, rng)
             z = synth.simulate_2_state_tree(seed, tree, Q, pid, n_sites=S, segments=seg)
         elif kind in ("ks", "ksmt", "dicks"):
             n = int(rng.choice([4, 6]))
             Q, pid = (cases.q4() if n == 4 else cases.q6()), np.full(n, 1.0 / n)
             Om = 1.2 * np.abs(np.diag(Q)).max() * float(rng.choice([1, 2]))
-            tree = synth.yule_tree(T, seed % 1000, mean_branch=mb)
+            tree = make_tree(T, seed % 1000, mb, rng)
             z = synth.simulate_4_state_tree(seed, tree, Q, pid, n_sites=S, segments=max(seg, 3))
         else:
             n = int(rng.choice([2, 3, 4, 5, 8]))
             Q, pid = dense_q(n, rng), np.full(n, 1.0 / n)
             Om = np.abs(np.diag(Q)).max() * float(rng.choice([1.0, 1.5, 3.0]))
-            tree = synth.yule_tree(T, seed % 1000, mean_branch=mb)
+            tree = make_tree(T, seed % 1000, mb, rng)
             st = synth.simulate_tip_states(tree, Q, pid, S, seed).numpy()
             z = tree.with_states(st[0].astype(np.int32) if S == 1 else st, segments=seg)
         Qf = np.asfortranarray(Q.copy())

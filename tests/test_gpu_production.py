@@ -315,7 +315,16 @@ def test_many_real_jumps_mixed_gap_and_count_runs(oracle, precision):
     np.testing.assert_allclose(big[:, :4].sum(1), 200 * zz.edge_length.sum(), rtol=1e-4)
 
 
-@pytest.mark.parametrize("case", range(8))
+def _ladder_tree(T, mean_branch, rng):
+    """Caterpillar: the deepest schedule a tree of T tips can have."""
+    edge, node = [], T + 1
+    for t in range(T, 2, -1):
+        edge.append((node, t)); edge.append((node, node + 1)); node += 1
+    edge.append((node, 1)); edge.append((node, 2))
+    return pb.PhyloTree(np.array(edge, dtype=np.int32), rng.exponential(mean_branch, size=len(edge)) + 1e-3)
+
+
+@pytest.mark.parametrize("case", range(12))
 def test_random_models_against_oracle_chain(oracle, case):
     """Randomly drawn models (state count, dense generator, Omega, tree size, branch-length scale, sampler, precision):
     the production chain and the oracle chain must sample the same posterior of dwell times and jump counts.  Fixed
@@ -331,8 +340,17 @@ def test_random_models_against_oracle_chain(oracle, case):
     mb = float(rng.choice([0.3, 2.0, 10.0])) / np.abs(np.diag(Q)).max()   # expected changes per branch: 0.3 .. 10
     variant, fn = [(oracle.PLAIN, pb.sumstatMCMC), (oracle.SPARSE, pb.SPARSEsumstatMCMC), (oracle.BIGTREE, pb.sumstatMCMC_bigtree)][case % 3]
     precision = ["f32", "f64"][case % 2]
-    z = cases.tree_n(Q, T=T, S=1, seed=40 + case, mean_branch=mb, segments=[None, 3][int(rng.integers(2))])  # None: the reference's initial maps
-    N, thin, burn = 9000, 9, 450
+    seg = [None, 3][int(rng.integers(2))]  # None: the reference's initial maps
+    if case < 8:
+        z = cases.tree_n(Q, T=T, S=1, seed=40 + case, mean_branch=mb, segments=seg)
+    else:  # other shapes: ladder (cases 8, 9: 12 and 25 tips) and balanced (10, 11: 8 and 32 tips)
+        tree = _ladder_tree(12 if case == 8 else 25, mb, rng) if case < 10 else synth.balanced_tree(3 if case == 10 else 5, branch=mb)
+        st = synth.simulate_tip_states(tree, Q, pid, 1, 300 + case).numpy()
+        z = tree.with_states(st[0].astype(np.int32), segments=seg)
+        T = z.T
+    N, thin, burn = 12000, 12, 600
+    if case >= 8:   # the ladder mixes slowly (lag-12 autocorrelation of R0 ~ 0.6 in case 8): thin much harder
+        N, thin, burn = 40000, 100, 1000
     ref = oracle.OracleRun(variant, [z.oracle_dict()], Q, pid, Om, N, rng_mode=oracle.SEQUENTIAL, seed=7 + case).run()[burn::thin]
     got = fn(z, Q, pid, Om, N, seed=70 + case, precision=precision)[burn::thin]
     np.testing.assert_allclose(got[:, :n].sum(1), z.edge_length.sum(), rtol=1e-5)
@@ -341,4 +359,4 @@ def test_random_models_against_oracle_chain(oracle, case):
     for name, (a, b) in checks.items():
         # a dwell time has an atom at "no change anywhere": equal up to summation order, so compare on a 1e-7 grid
         p = stats.ks_2samp(np.round(a, 7), np.round(b, 7)).pvalue
-        assert p > 0.002, "case %d (n=%d T=%d Omega=%.2f mean_branch=%.2f %s): %s KS p = %.5f" % (case, n, T, Om, mb, precision, name, p)
+        assert p > 0.001, "case %d (n=%d T=%d Omega=%.2f mean_branch=%.2f %s): %s KS p = %.5f" % (case, n, T, Om, mb, precision, name, p)
