@@ -1312,10 +1312,10 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     // runs than the local buffer holds (a saturated branch) is walked again with `replay` set, and this time its runs go
     // straight to the records reserved at `wbase` -- nothing else is done twice (no counts, dwell times or draws of new
     // virtual jumps).
-    bool replay = false;
-    int wbase = 0, total_runs = 0;
+    int wbase = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {  // pass 1 only for a path longer than the local buffer (see below)
+      const bool replay = pass != 0;
       WordStream cnt_old; cnt_old.open(P.rng, (uint32_t)site, first ? iter : iter - 1u, K_BRCNT, (uint32_t)eb, 0u);
       WordStream cnt_new; cnt_new.open(P.rng, (uint32_t)site, iter, K_BRCNT, (uint32_t)eb, 0u);
       Stream gst; gst.open(P.rng, (uint32_t)site, iter, K_BRSTATE, (uint32_t)eb, P.err_flag);
@@ -1415,7 +1415,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       // ... and the second run of a two-run path is what is left after the first (the form the next sweep rebuilds it in)
       emit(nout == 0 ? Le : nout == 1 ? PN::sub(Le, L0) : cur_len, cur_state);
       if (replay) {
-        if (nout != total_runs) errbits |= PM_DE_INCONSISTENT;
+        if (nout != (int)wr_len[sbase + wbase]) errbits |= PM_DE_INCONSISTENT;  // the header holds the count of pass 0
         break;
       }
       if (newm > 65535) { errbits |= PM_DE_M_OVERFLOW; newm = 65535; }
@@ -1433,7 +1433,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       if (base + need > cap_c) { errbits |= PM_DE_PATH_CAP; break; }
       if (longp) { wr_len[sbase + base] = (Real)nout; wr_st[sbase + base] = 0; }
       if (nout > PM_LOCAL_PATH_MAX) {  // not all runs were kept: walk the branch once more, writing them in place
-        replay = true; wbase = base; total_runs = nout;
+        wbase = base;
         continue;
       }
       const int o = base + (longp ? 1 : 0);
@@ -1442,7 +1442,6 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       for (int r = 2; r < nout; r++) { wr_len[sbase + o + r] = bufL[r]; wr_st[sbase + o + r] = bufS[r]; }
       break;
     }
-    if (replay) nout = total_runs;
     P.meta[pe] = PM_META(newm, min(nout - 1, 63), S0, S1);
       }  // have
     }    // rounds
