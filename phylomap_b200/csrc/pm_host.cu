@@ -363,7 +363,7 @@ struct ChainT : pm_chain {
     pm::k_reduce<<<1, 256, 0, stream>>>(t.dw_partial.template as<double>(), 2 * t.nblocks, n, cnt.as<unsigned long long>(),
                                         root_out.as<int>(), row, 0);
     end_timed();
-    launches += (exact || iter == 0) ? 4 : 5;
+    launches += exact ? 4 : 5;
   }
   // DIC samplers: log p(y | Q) of the current Q into row[n + n*n + 1] (after the sweep: PL is free again)
   void launch_loglik(TreeDev<Real>& t, double* row) {
@@ -792,7 +792,8 @@ struct ChainT : pm_chain {
         CK(cudaStreamSynchronize(stream));
       }
       const long long tot = t.S * E;
-      if (!V.exp && !V.llonly) pm::k_init_meta<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(P.maps_off, t.S, E, P.meta);
+      if (!V.exp && !V.llonly)
+        pm::k_init_meta<Real><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(P.maps_off, P.maps_len, t.S, E, P.meta, exact ? nullptr : P.pos1);
       CK(cudaGetLastError());
     }
     stage_model(true);

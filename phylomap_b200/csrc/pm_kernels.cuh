@@ -1242,7 +1242,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       // append this word's items: exclusive scan of the popcounts over the block
       uint32_t bits = 0;
       if ((int)threadIdx.x < nsites) {
-        bits = first ? 0xffffffffu : mask[(long long)w * S];
+        bits = mask[(long long)w * S];  // (first sweep too: k_paths_easy has already dealt with the short maps)
         if (w == nwords - 1) bits &= lastmask;
       }
       const int c = __popc(bits);

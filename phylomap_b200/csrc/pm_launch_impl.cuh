@@ -41,11 +41,11 @@ void Sweep<Real, NS, EXACT>::paths(const ChainParams<Real>& P, dim3 grid, size_t
                                    int first, int chunk, int variant) {
   if constexpr (EXACT) k_paths<Real, NS, true><<<grid, 128, smem, st>>>(P, iter, first, chunk);
   else {
-    // first sweep: every branch takes its jump points from the caller's maps -> general path only.  The easy kernel
-    // must still define this sweep's partial sums, so it runs on an empty range instead (chunk = 0 branches).
+    // the easy kernel also serves the first sweep: a map of one or two pieces is a path like any other (pos1 was
+    // seeded from it), only longer maps are walked piece by piece by the general kernel
     const size_t smem_easy = (size_t)4 * P.n * sizeof(double) + (size_t)(P.n * P.n + ((P.n * P.n) & 1)) * sizeof(unsigned) +
                              (size_t)(P.n + (P.n & 1)) * sizeof(Real) + (size_t)chunk * (2 * sizeof(int) + sizeof(Real));
-    if (!first) k_paths_easy<Real, NS><<<grid, 128, smem_easy, st>>>(P, iter, chunk);
+    k_paths_easy<Real, NS><<<grid, 128, smem_easy, st>>>(P, iter, chunk);
     if (variant == 3) k_paths_hard<Real, NS, 3><<<grid, 128, smem, st>>>(P, iter, first, chunk);
     else k_paths_hard<Real, NS, 4><<<grid, 128, smem, st>>>(P, iter, first, chunk);
   }
