@@ -834,7 +834,24 @@ __device__ __forceinline__ int draw_node_state(const ChainParams<Real>& P, const
   }
 #pragma unroll
   for (int j = 0; j < NS; j++) w[j] *= pl[j];
-  return categorical<Real, NS, false>(w, NS, u01_from_word<Real>(word), P.err_flag);
+  // inverse-cdf draw, the same pick as categorical<.., false> for non-negative weights, without its per-state tests:
+  // the first state whose running sum exceeds t is the number of running sums t has reached (a state of weight zero
+  // repeats its predecessor's sum and cannot be the first)
+  Real c[NS];
+  c[0] = w[0];
+#pragma unroll
+  for (int j = 1; j < NS; j++) c[j] = c[j - 1] + w[j];
+  const Real tot = c[NS - 1];
+  if (!(tot > (Real)0) || !isfinite(tot)) { atomicOr(P.err_flag, tot > (Real)0 ? PM_DE_SAMPLE_NA : PM_DE_SAMPLE_ZERO); return 0; }
+  const Real t = u01_from_word<Real>(word) * tot;
+  int pick = 0;
+#pragma unroll
+  for (int j = 0; j < NS - 1; j++) pick += (t >= c[j]) ? 1 : 0;
+  if (!(t < tot)) {  // rounding put t on the total: the last state with positive weight, as categorical does
+#pragma unroll
+    for (int j = 0; j < NS; j++) if (w[j] > (Real)0) pick = j;
+  }
+  return pick;
 }
 
 template <typename Real, int NS, int DEPTH, int MINB>
