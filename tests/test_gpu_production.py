@@ -360,3 +360,18 @@ def test_random_models_against_oracle_chain(oracle, case):
         # a dwell time has an atom at "no change anywhere": equal up to summation order, so compare on a 1e-7 grid
         p = stats.ks_2samp(np.round(a, 7), np.round(b, 7)).pvalue
         assert p > 0.001, "case %d (n=%d T=%d Omega=%.2f mean_branch=%.2f %s): %s KS p = %.5f" % (case, n, T, Om, mb, precision, name, p)
+
+
+def test_hundred_thousand_tips():
+    """A tree ten times the benchmark's (100 000 tips, 199 998 branches): schedules, 64-bit offsets and capacities hold;
+    fixed-Q FP32 and the hidden-rate sampler in FP64."""
+    Q, pid = cases.q4(), np.full(4, 0.25)
+    T, S = 100000, 256
+    tree = synth.yule_tree(T, seed=4, mean_branch=0.1 / 1.2)
+    st = synth.simulate_tip_states(tree, Q, pid, S, seed=7, device="cuda").cpu().numpy()
+    a = pb.sumstatMCMC_bigtree(tree.with_states(st, segments=2), Q, pid, 2.4, 4, precision="f32", seed=11)
+    np.testing.assert_allclose(a[:, :4].sum(1), S * tree.edge_length.sum(), rtol=3e-4)
+    assert np.all(a[:, 4:] >= 0) and np.array_equal(a[:, 4:], np.round(a[:, 4:])) and a[:, 4:].sum() > 0
+    zk = synth.simulate_4_state_tree(7, tree, Q, pid, n_sites=S, device="cuda", segments=8)
+    ks = pb.sumstatMCMCks(zk, np.asfortranarray(Q.copy()), pid, 4.0, 3, cases.PRIOR_KS, precision="f64", seed=3)
+    np.testing.assert_allclose(ks[:, :4].sum(1), S * tree.edge_length.sum(), rtol=1e-9)
