@@ -57,6 +57,5 @@ print("sumstatMCMCksDICt  N = %d: %.1f s (%.2f ms per sweep)   posterior mean l0
 print("DIC_2_state = %.3f   DIC_4_state = %.3f   (%.2f s)   [the vignette's R run: 2538.272 and 2536.056, with R's tip data]" %
       (DIC_2_state, DIC_4_state, t3 - t2))
 if out:
-    rds.write_rds(out + "_2s.rds", SIMtstr, colnames=["t0", "t1", "n00", "n01", "n10", "n11", "l01", "l10", "root_state", "log(p(y|Q))"])
-    rds.write_rds(out + "_4s.rds", SIMfstr, colnames=["t1", "t2", "t3", "t4"] + ["n%d%d" % (a, b) for a in range(1, 5) for b in range(1, 5)] +
-                  ["l01", "l10", "k01", "k10", "gamma", "root_state", "log(p(y|Q))"])
+    rds.write_rds(out + "_2s.rds", SIMtstr, colnames=pb.colnames(pb.sumstatMCMC2sDICt))
+    rds.write_rds(out + "_4s.rds", SIMfstr, colnames=pb.colnames(pb.sumstatMCMCksDICt, 4))

@@ -359,6 +359,29 @@ def sumstatMCMCksDICt(z, Q, pid, Omega, N, prior, **opts):
     return _single(maketreelistMCMCksDICt, z, Q, pid, Omega, N, prior, **opts)
 
 
+def colnames(fn, n=None):
+    """Column names of a sampler's result, where the reference assigns any: `sumstatMCMCbf` (R/sumstatMCMCbf.R:33),
+    `sumstatMCMCmt` (R/sumstatMCMCmt.R:39) and the two DIC traces as make_12_chains labels them (R/sourceme.R:532, 547) --
+    the names `make2stateDIC` / `make4stateDIC` index by.  `fn` is the function or its name; n the number of states."""
+    name = fn if isinstance(fn, str) else fn.__name__
+    name = name.replace("maketreelist", "sumstat")
+    two = ["n00", "n01", "n10", "n11", "l01", "l10"]
+    if name == "sumstatMCMCbf":
+        return ["time 0", "time 1"] + two + ["root_state"]
+    if name == "sumstatMCMCmt":
+        return ["time_0", "time_1"] + two + ["tree_number"]
+    if name == "sumstatMCMC2sDICt":
+        return ["t0", "t1"] + two + ["root_state", "log(p(y|Q))"]
+    if name == "sumstatMCMCksDICt":
+        n = 4 if n is None else n
+        k = n // 2 - 1
+        rates = ["l01", "l10"] + (["k01", "k10", "gamma"] if k == 1 else ["k01_%d" % i for i in range(1, k + 1)] +
+                                  ["k10_%d" % i for i in range(1, k + 1)] + ["gamma_%d" % i for i in range(1, k + 1)])
+        return ["t%d" % i for i in range(1, n + 1)] + ["n%d%d" % (a, b) for a in range(1, n + 1) for b in range(1, n + 1)] + \
+            rates + ["root_state", "log(p(y|Q))"]
+    raise KeyError("the reference names no columns for %s" % name)
+
+
 def loglik(z, Q, pid, parity_tips=False, order=None, **opts):
     """log p(y | Q) summed over the sites of `z` (pm_loglik): pruning with exp(Q t_e) on the GPU."""
     L = capi.lib()

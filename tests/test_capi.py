@@ -154,3 +154,15 @@ def test_sumstatEXP_rejects_complex_spectrum():
     t = synth.yule_tree(4, 1).with_states(np.array([1, 2, 3, 1], dtype=np.int32))
     with pytest.raises(ValueError):
         pb.sumstatEXP(t, Q, np.full(3, 1 / 3), 2)
+
+
+def test_column_names_follow_the_reference():
+    import phylomap_b200 as pb
+    assert pb.colnames(pb.sumstatMCMCbf) == ["time 0", "time 1", "n00", "n01", "n10", "n11", "l01", "l10", "root_state"]
+    assert pb.colnames("maketreelistMCMCmt")[-1] == "tree_number"
+    two, four = pb.colnames(pb.sumstatMCMC2sDICt), pb.colnames(pb.sumstatMCMCksDICt, 4)
+    assert len(two) == capi.lib().pm_ncols(capi.PM_V_DIC2S, 2) and two[6:8] == ["l01", "l10"] and two[-1] == "log(p(y|Q))"
+    assert len(four) == capi.lib().pm_ncols(capi.PM_V_DICKS, 4) and four[20:25] == ["l01", "l10", "k01", "k10", "gamma"]
+    assert len(pb.colnames(pb.sumstatMCMCksDICt, 6)) == capi.lib().pm_ncols(capi.PM_V_DICKS, 6)
+    with pytest.raises(KeyError):
+        pb.colnames(pb.sumstatMCMC)
