@@ -402,6 +402,10 @@ def _col(mat, name, pos):
     """Column of a sampler output by the reference's name (a pandas frame) or by its position (a plain matrix)."""
     if hasattr(mat, "columns"):
         return np.asarray(mat[name], dtype=np.float64)
+    if hasattr(mat, "attributes") and hasattr(mat, "value"):  # rds.RObject: a matrix read back with its dimnames
+        names = (mat.attributes.get("dimnames") or [None, None])[1]
+        a = np.asarray(mat.value, dtype=np.float64)
+        return a[:, list(names).index(name)] if names else a[:, pos]
     return np.asarray(mat, dtype=np.float64)[:, pos]
 
 

@@ -80,3 +80,15 @@ def test_reads_the_reference_files():
     assert len(z.tip_label) == 3951 and z.tip_label[0] == "Sphenodon_punctatus"
     dic = rds.plain(rds.read_rds(REF_DIC))
     assert sorted(dic) == ["AIC", "diffuse", "restricted", "spike"] and dic["restricted"].tolist() == [2.0, 9.0]
+
+
+def test_dic_helpers_index_a_trace_read_back_by_name(tmp_path):
+    from phylomap_b200 import api
+    names = pb.colnames(pb.sumstatMCMC2sDICt)
+    mat = np.arange(40, dtype=np.float64).reshape(4, 10)
+    p = str(tmp_path / "t.rds")
+    rds.write_rds(p, mat[:, ::-1].copy(), colnames=names[::-1])      # columns stored in another order
+    back = rds.read_rds(p)
+    np.testing.assert_array_equal(api._col(back, "l01", 6), mat[:, 6])
+    np.testing.assert_array_equal(api._col(back, "log(p(y|Q))", -1), mat[:, 9])
+    np.testing.assert_array_equal(api._col(mat, "l01", 6), mat[:, 6])
