@@ -1082,27 +1082,31 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
     } else atomicAdd(&s_dw[s], (double)L);
   };
   // two-deep software pipeline: jump count and node states of branch i + 2, then pos1 of branch i + 1 if it has a
-  // jump point
+  // jump point.  Two branches per loop trip -- the pair (2j, 2j + 1) that shares a Philox block -- with the two register
+  // sets swapping roles, so nothing is copied around and the word selection is static.
   const int nb = e1 - e0;
-  uint32_t mtA = 0, mtB = 0; int psA = 0, csA = 0, psB = 0, csB = 0; Real p1A = 0;
-  const uint32_t* meta_f = meta_p;  // fetch cursor (two rows ahead of the store cursor)
-  auto fetch = [&](int i, uint32_t& mt, int& ps, int& cs) {
-    mt = *meta_f; meta_f += Su;
-    ps = nstate[(uint64_t)(uint32_t)s_par[i] * Su];
-    cs = nstate[(uint64_t)(uint32_t)s_chi[i] * Su];
+  struct Ahead { uint32_t mt; int ps, cs; Real p1; };
+  Ahead X = {0, 0, 0, 0}, Y = {0, 0, 0, 0};
+  const uint32_t* meta_f = meta_p;  // fetch cursor (runs ahead of the store cursor)
+  auto fetch = [&](int i, Ahead& a) {
+    a.mt = *meta_f; meta_f += Su;
+    a.ps = nstate[(uint64_t)(uint32_t)s_par[i] * Su];
+    a.cs = nstate[(uint64_t)(uint32_t)s_chi[i] * Su];
   };
-  if (nb > 0) { fetch(0, mtA, psA, csA); if ((mtA & 0xffffu) == 2u) p1A = pos1_p[0]; }
-  if (nb > 1) fetch(1, mtB, psB, csB);
   uint32_t po[4] = {0, 0, 0, 0};
   uint32_t bits = 0;
-  for (int i = 0; i < nb; i++) {
+  // one branch: `cur` holds what was fetched for it; with PIPE, `nxt` (branch i + 1) gets its pos1 and `cur` is refilled
+  // with branch i + 2.  ODD: second branch of its Philox pair (the block was drawn by the first, or here if it opens the chunk).
+  auto step = [&](int i, auto odd_c, auto pipe_c, Ahead& cur, Ahead& nxt) {
+    constexpr bool ODD = decltype(odd_c)::value, PIPE = decltype(pipe_c)::value;
     const int e = e0 + i;
-    const uint32_t mt = mtA; const int ps = psA, cs = csA; const Real p1 = p1A;
-    mtA = mtB; psA = psB; csA = csB;
-    if (i + 1 < nb && (mtA & 0xffffu) == 2u) p1A = pos1_p[Su];
-    if (i + 2 < nb) fetch(i + 2, mtB, psB, csB);
-    if (((e & 1) == 0) || i == 0) pair_block(P.rng, (uint32_t)site, iter, (uint32_t)e, po);
-    const uint32_t wA = (e & 1) ? po[2] : po[0], wB = (e & 1) ? po[3] : po[1];
+    const uint32_t mt = cur.mt; const int ps = cur.ps, cs = cur.cs; const Real p1 = cur.p1;
+    if (PIPE) {
+      if (i + 1 < nb && (nxt.mt & 0xffffu) == 2u) nxt.p1 = pos1_p[Su];
+      if (i + 2 < nb) fetch(i + 2, cur);
+    }
+    if (!ODD || !PIPE) pair_block(P.rng, (uint32_t)site, iter, (uint32_t)e, po);
+    const uint32_t wA = ODD ? po[2] : po[0], wB = ODD ? po[3] : po[1];
     const int m = (int)(mt & 0xffffu);
     const Real Le = s_len[i];
     // pieces: (Le) or (p1, Le - p1); states ps | cs (a one-piece branch carries the child state, :460-475)
@@ -1136,7 +1140,21 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
         for (int j = 0; j < NR; j++) { Rsum[j] += (double)Racc[j]; Racc[j] = 0; }
       }
     }
+  };
+  int i = 0;
+  if (nb > 0 && (e0 & 1)) {  // the chunk opens on the second branch of a pair: on its own, unpipelined
+    fetch(0, X);
+    if ((X.mt & 0xffffu) == 2u) X.p1 = pos1_p[0];
+    step(0, std::true_type(), std::false_type(), X, Y);
+    i = 1;
   }
+  if (i < nb) { fetch(i, X); if ((X.mt & 0xffffu) == 2u) X.p1 = pos1_p[0]; }
+  if (i + 1 < nb) fetch(i + 1, Y);
+  for (; i + 1 < nb; i += 2) {
+    step(i, std::false_type(), std::true_type(), X, Y);
+    step(i + 1, std::true_type(), std::true_type(), Y, X);
+  }
+  if (i < nb) step(i, std::false_type(), std::true_type(), X, Y);
   if (NS > 0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
