@@ -67,12 +67,27 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
+// The same with the ten round keys precomputed on the host (RngDesc::rk, kernel-parameter constants): the key schedule
+// costs no instructions.
+__device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk)[20],
+                                                 uint32_t o[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ rk[2 * r], n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
 enum SlotKind : uint32_t { K_NODE = 0, K_BRSTATE = 1, K_BREXP = 2, K_NODEGRP = 3, K_BRPAIR = 4, K_BRCNT = 5, K_BRPOS = 6, K_BRGAP = 7 };
 __device__ __forceinline__ uint32_t make_slot(uint32_t kind, uint32_t idx) { return (kind << 28) | idx; }
 
 // Description of where uniforms come from (per launch).
 struct RngDesc {
   uint32_t k0, k1;        // Philox key (per tree)
+  uint32_t rk[20];        // its ten round keys: k0 + r * 0x9E3779B9, k1 + r * 0xBB67AE85
   uint32_t site0;         // global index of local site 0
   const int64_t* tab_off; // replay table (device), or nullptr
   const double* tab_u;
@@ -287,7 +302,7 @@ struct WordStream {
 };
 
 __device__ __forceinline__ void pair_block(const RngDesc& d, uint32_t local_site, uint32_t it, uint32_t e, uint32_t o[4]) {
-  philox4x32_10(e >> 1, make_slot(K_BRPAIR, 0u), it, d.site0 + local_site, d.k0, d.k1, o);
+  philox4x32_10_rk(e >> 1, make_slot(K_BRPAIR, 0u), it, d.site0 + local_site, d.rk, o);
 }
 
 // ------------------------------------------------------------------------------------------------

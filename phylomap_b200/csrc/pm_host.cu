@@ -767,6 +767,7 @@ struct ChainT : pm_chain {
       P.root_out = root_out.as<int>(); P.err_flag = err_flag.as<unsigned>();
       const uint64_t key = opt.seed + (uint64_t)ti * 0x9E3779B97F4A7C15ull;
       P.rng.k0 = (uint32_t)key; P.rng.k1 = (uint32_t)(key >> 32);
+      for (int r = 0; r < 10; r++) { P.rng.rk[2 * r] = P.rng.k0 + (uint32_t)r * 0x9E3779B9u; P.rng.rk[2 * r + 1] = P.rng.k1 + (uint32_t)r * 0xBB67AE85u; }
       P.rng.site0 = (uint32_t)opt.site_offset;
       P.rng.tab_off = opt.rng == PM_RNG_TABLE ? (const int64_t*)tab_off.p : nullptr;
       P.rng.tab_u = opt.rng == PM_RNG_TABLE ? tab_u.as<double>() : nullptr;

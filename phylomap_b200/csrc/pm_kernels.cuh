@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
 #pragma unroll
     for (int j = 0; j < NS; j++) w[j] = sVec[j] * pl[j];
     uint32_t o[4];
-    philox4x32_10(0xffffffffu, kslot, iter, gsite, P.rng.k0, P.rng.k1, o);
+    philox4x32_10_rk(0xffffffffu, kslot, iter, gsite, P.rng.rk, o);
     const int s = categorical<Real, NS, false>(w, NS, u01_from_word<Real>(o[0]), P.err_flag);
     if (active) {
       nst[(long long)P.root * S] = (uint8_t)s;
@@ -900,7 +900,7 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
       Real pl[NS];
       VecIO<Real, NS>::load(P.PL + ((long long)(en.x - T) * S + site) * NS, NS, pl);
       uint32_t o[4];
-      philox4x32_10(0x80000000u + (uint32_t)idx, kslot, iter, gsite, P.rng.k0, P.rng.k1, o);
+      philox4x32_10_rk(0x80000000u + (uint32_t)idx, kslot, iter, gsite, P.rng.rk, o);
       const int s = draw_node_state<Real, NS>(P, sBs, sPow, npow_s, k, ps, pl, o[0]);
       if (active) nst[(long long)en.x * S] = (uint8_t)s;
     }
@@ -959,7 +959,7 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
         // the parent of the next node, unless it is the node drawn now: stored at least one node ago by this lane
         if (h.w >= 0) ps_mem_n = *reinterpret_cast<const uint8_t*>(nsb_u + (unsigned long long)p_off_n);
       }
-      if ((idx & 3) == 0 || idx == i0) philox4x32_10((uint32_t)idx >> 2, kslot, iter, gsite, P.rng.k0, P.rng.k1, o);
+      if ((idx & 3) == 0 || idx == i0) philox4x32_10_rk((uint32_t)idx >> 2, kslot, iter, gsite, P.rng.rk, o);
       const uint32_t word = (idx & 3) == 0 ? o[0] : (idx & 3) == 1 ? o[1] : (idx & 3) == 2 ? o[2] : o[3];
       Real pl[NS];
       lds_vec<Real, NS>(slot + lanePB, pl);  // the partial of this node, copied by this lane
@@ -990,7 +990,7 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
     __syncthreads();
     for (int grp = warp; grp <= (P.n_cd_tips - 1) >> 2; grp += nw) {
       uint32_t o[4];
-      philox4x32_10(0x40000000u + (uint32_t)grp, kslot, iter, gsite, P.rng.k0, P.rng.k1, o);
+      philox4x32_10_rk(0x40000000u + (uint32_t)grp, kslot, iter, gsite, P.rng.rk, o);
       const int p0 = grp << 2, p1 = min(P.n_cd_tips, p0 + 4);
       int vs[4], ks[4], pss[4], cds[4];
 #pragma unroll
