@@ -383,7 +383,8 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
   // ---- phase 1: this warp's clades ----
   {
     const int i0 = __ldg(P.cl_warp_off + warp), i1 = __ldg(P.cl_warp_off + warp + 1);
-    const unsigned ring = (unsigned)__cvta_generic_to_shared(smem_raw) + warp * (DEPTH * PM_CLADE_SLOT);
+    unsigned ring = (unsigned)__cvta_generic_to_shared(smem_raw) + warp * (DEPTH * PM_CLADE_SLOT);
+    asm volatile("" : "+r"(ring));  // kept in a register: the compiler would rebuild it from %tid and the window base per node
     char* const plb = reinterpret_cast<char*>(PLs);
     const char* const mtb = reinterpret_cast<const char*>(meta);
     const char* const tpb = reinterpret_cast<const char*>(P.tipcode) + site0 + 4 * (lane & 7);  // lanes 0..7: four tip codes each
@@ -441,7 +442,8 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
       flA = lds_s32(ring + 336);
     }
     unsigned slot = ring;
-    const unsigned ring_end = ring + DEPTH * PM_CLADE_SLOT;
+    unsigned ring_end = ring + DEPTH * PM_CLADE_SLOT;
+    asm volatile("" : "+r"(ring_end));
     // one node: (pn_off, fl, xcur) describe it, (pn_off_n, fl_n, xnext) receive the next node's
     auto step = [&](int idx, long long pn_off, int fl, const Real* xcur, long long& pn_off_n, int& fl_n, Real* xnext) {
       const unsigned slot_n = (slot + PM_CLADE_SLOT == ring_end) ? ring : slot + PM_CLADE_SLOT;
@@ -909,7 +911,8 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
   // ---- this warp's clades, pre-order ----
   {
     const int i0 = __ldg(P.cd_warp_off + warp), i1 = __ldg(P.cd_warp_off + warp + 1);
-    const unsigned ring = (unsigned)__cvta_generic_to_shared(smem_raw) + warp * (DEPTH * SLOT);
+    unsigned ring = (unsigned)__cvta_generic_to_shared(smem_raw) + warp * (DEPTH * SLOT);
+    asm volatile("" : "+r"(ring));  // kept in a register (see k_prune_clade)
     unsigned long long plb_u = reinterpret_cast<unsigned long long>(P.PL + site * NS),
                        mtb_u = reinterpret_cast<unsigned long long>(P.meta + site),
                        nsb_u = reinterpret_cast<unsigned long long>(nst);
@@ -946,7 +949,8 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
       if (pA >= 0) psA = *reinterpret_cast<const uint8_t*>(nsb_u + (unsigned long long)pA);
     }
     unsigned slot = ring;
-    const unsigned ring_end = ring + DEPTH * SLOT;
+    unsigned ring_end = ring + DEPTH * SLOT;
+    asm volatile("" : "+r"(ring_end));
     int sprev = 0;
     uint32_t o[4] = {0, 0, 0, 0};
     auto step = [&](int idx, long long v_off, long long p_off, int ps_mem, long long& v_off_n, long long& p_off_n, int& ps_mem_n) {
