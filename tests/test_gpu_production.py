@@ -375,3 +375,22 @@ def test_hundred_thousand_tips():
     zk = synth.simulate_4_state_tree(7, tree, Q, pid, n_sites=S, device="cuda", segments=8)
     ks = pb.sumstatMCMCks(zk, np.asfortranarray(Q.copy()), pid, 4.0, 3, cases.PRIOR_KS, precision="f64", seed=3)
     np.testing.assert_allclose(ks[:, :4].sum(1), S * tree.edge_length.sum(), rtol=1e-9)
+
+
+def test_production_rows_are_frozen():
+    """Regression fixture of the production arithmetic (tests/golden/make_production_golden.py): the same seeds give the
+    same rows as when the fixture was written -- integer columns exactly, sums to rounding.  Regenerate it only after a
+    deliberate change of the random-number mapping."""
+    import json
+    import os
+    sys_path_golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_production_golden", os.path.join(sys_path_golden, "make_production_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(sys_path_golden, "production_rows.json")))
+    got = mod.rows()
+    assert sorted(got) == sorted(want)
+    for k, ref in want.items():
+        ref = np.asarray(ref)
+        np.testing.assert_allclose(got[k], ref, rtol=1e-12, atol=0, err_msg=k)
