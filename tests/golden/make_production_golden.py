@@ -2,7 +2,7 @@
 draws cannot change them unnoticed.  These are not parity vectors (the production mode is checked against the oracle
 statistically): regenerate on a B200 after a deliberate change of the random-number mapping.
 
-    python tests/golden/make_production_golden.py        # writes tests/golden/production_rows.json (needs the GPU)
+    python tests/golden/make_production_golden.py        # writes tests/golden/production/rows.json (needs the GPU)
 """
 import json
 import os
@@ -32,6 +32,6 @@ def rows():
 
 
 if __name__ == "__main__":
-    dst = os.path.join(os.environ.get("PM_GOLDEN_OUT", HERE), "production_rows.json")
+    dst = os.path.join(os.environ.get("PM_GOLDEN_OUT", os.path.join(HERE, "production")), "rows.json")
     json.dump({k: v.tolist() for k, v in rows().items()}, open(dst, "w"))
     print("wrote", dst)

@@ -388,7 +388,7 @@ def test_production_rows_are_frozen():
     spec = importlib.util.spec_from_file_location("make_production_golden", os.path.join(sys_path_golden, "make_production_golden.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    want = json.load(open(os.path.join(sys_path_golden, "production_rows.json")))
+    want = json.load(open(os.path.join(sys_path_golden, "production", "rows.json")))
     got = mod.rows()
     assert sorted(got) == sorted(want)
     for k, ref in want.items():
