@@ -185,6 +185,14 @@ int pm_chain_create(int32_t variant, const pm_tree* trees, int32_t ntrees, int32
 /* Run `count` further iterations; rows [first .. first+count) of `out` (column-major, leading dimension ld)
  * are written.  first must equal the number of iterations already done. */
 int pm_chain_run(pm_chain* c, int32_t count, double* out, int64_t ld, char* err, size_t errlen);
+/* Test hook (host only, no device needed): builds the clade schedules the production pruning / node-draw kernels walk for
+ * this tree (pm_tree.hpp) and verifies them -- every internal node once, children before parents inside a warp's
+ * sequence, register / reload flags consistent, top-down order valid.  stats[8]: nodes in warp sequences, nodes above
+ * the clades, levels above, lightest and heaviest warp, children handed over in registers, top-down sequence nodes,
+ * top-down top nodes. */
+int pm_debug_clade_schedule(const int32_t* edge, int32_t n_edges, int32_t n_tips, const int32_t* nen, const int32_t* nodelist,
+                            int32_t root, int32_t nwarps, int32_t clade_max, int64_t* stats, char* err, size_t errlen);
+
 /* Checkpoint / resume (the reference has none: its chain state is lost when the call returns).  The
  * exported blob holds what the next sweep reads and pm_chain_create does not rebuild: iteration counter, host generator,
  * current Q and B, node states, jump counts, first positions and run records.  Import into a chain created with the SAME

@@ -40,7 +40,7 @@ class PmOptions(C.Structure):
 EXPORTS = ["pm_default_options", "pm_maketreelistMCMC", "pm_SPARSEmaketreelistMCMC", "pm_maketreelistMCMC_bigtree",
            "pm_maketreelistMCMCbf", "pm_maketreelistMCMCks", "pm_maketreelistMCMCmt", "pm_maketreelistMCMCksmt",
            "pm_maketreelistMCMC2sDICt", "pm_maketreelistMCMCksDICt", "pm_maketreelistEXP", "pm_loglik",
-           "pm_ncols", "pm_tree_order", "pm_chain_create", "pm_chain_run", "pm_chain_state_bytes",
+           "pm_ncols", "pm_tree_order", "pm_debug_clade_schedule", "pm_chain_create", "pm_chain_run", "pm_chain_state_bytes",
            "pm_chain_export_state", "pm_chain_import_state", "pm_chain_time_prune",
            "pm_chain_kernel_times", "pm_chain_enable_timing", "pm_chain_get_node_states", "pm_chain_get_piece_counts",
            "pm_chain_get_path", "pm_chain_get_partials", "pm_chain_device_bytes", "pm_chain_destroy",
@@ -80,6 +80,7 @@ def lib():
     L.pm_loglik.argtypes = [vp, i32, vp, vp, i32, vp, vp, C.c_char_p, C.c_size_t]
     L.pm_ncols.argtypes = [i32, i32]
     L.pm_tree_order.argtypes = [vp, i32, i32, vp, vp, vp, C.c_char_p, C.c_size_t]
+    L.pm_debug_clade_schedule.argtypes = [vp, i32, i32, vp, vp, i32, i32, i32, vp, C.c_char_p, C.c_size_t]
     L.pm_chain_create.argtypes = [i32, vp, i32, i32, vp, vp, vp, dbl, vp, i32, i32, vp, vp, C.c_char_p, C.c_size_t]
     L.pm_chain_run.argtypes = [vp, i32, vp, i64, C.c_char_p, C.c_size_t]
     L.pm_chain_state_bytes.argtypes = [vp]

@@ -1272,6 +1272,78 @@ int pm_loglik(const pm_tree* x, int32_t n, const double* Q, const double* pid, i
   });
 }
 
+int pm_debug_clade_schedule(const int32_t* edge, int32_t n_edges, int32_t n_tips, const int32_t* nen, const int32_t* nodelist,
+                            int32_t root, int32_t nwarps, int32_t clade_max, int64_t* stats, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!edge || !nen || !nodelist || !stats || nwarps < 1) fail(PM_ERR_ARG, "bad argument");
+    pm::host::Schedule sch;
+    try { pm::host::build_schedule(n_tips, n_edges, edge, nen, nodelist, root, false, sch); }
+    catch (const std::string& msg) { fail(PM_ERR_ARG, "%s", msg.c_str()); }
+    pm::host::CladeSchedule cs;
+    pm::host::build_clade_schedule(sch, nwarps, clade_max, cs);
+    const int T = n_tips, NN = 2 * T - 1;
+    // bottom-up: every internal node exactly once; inside a warp's sequence both children of a node are tips, the node
+    // just before (flag 1 / 2) or an earlier node of the SAME warp (flag 4 / 8); a top node's children are complete
+    std::vector<int> owner(NN, -2), posn(NN, -1);  // -2 unseen, -1 top, else warp
+    const int n1 = cs.warp_off[nwarps];
+    long long lo = 1LL << 60, hi = 0, nprev = 0;
+    for (int w = 0; w < nwarps; w++) {
+      lo = std::min<long long>(lo, cs.warp_off[w + 1] - cs.warp_off[w]);
+      hi = std::max<long long>(hi, cs.warp_off[w + 1] - cs.warp_off[w]);
+      int prev = -1;
+      for (int i = cs.warp_off[w]; i < cs.warp_off[w + 1]; i++) {
+        const int* en = &cs.entries[(size_t)8 * i];
+        const int v = en[0], fl = en[5];
+        if (v < T || v >= NN || owner[v] != -2) fail(PM_ERR_ARG, "node %d scheduled twice or out of range", v);
+        const int kids[2] = {en[1], en[3]};
+        for (int c = 0; c < 2; c++) {
+          const int k = kids[c], isprev = fl & (c ? 2 : 1), isload = fl & (c ? 8 : 4);
+          if (k < T) { if (isprev || isload) fail(PM_ERR_ARG, "tip child of %d flagged", v); continue; }
+          if (owner[k] != w) fail(PM_ERR_ARG, "child %d of %d is not an earlier node of the same warp", k, v);
+          if (isprev ? (k != prev) : (!isload || posn[k] >= i - 1)) fail(PM_ERR_ARG, "flags of node %d", v);
+          if (isprev) nprev++;
+        }
+        if ((fl & 4) && (fl & 8)) fail(PM_ERR_ARG, "node %d would load both children", v);
+        owner[v] = w; posn[v] = i; prev = v;
+      }
+    }
+    const int ntop = (int)cs.entries.size() / 8 - n1;
+    for (size_t l = 0; l + 1 < cs.top_off.size(); l++)
+      for (int i = cs.top_off[l]; i < cs.top_off[l + 1]; i++) {
+        const int* en = &cs.entries[(size_t)8 * i];
+        const int v = en[0];
+        if (v < T || v >= NN || owner[v] != -2) fail(PM_ERR_ARG, "top node %d scheduled twice", v);
+        const int kids[2] = {en[1], en[3]};
+        for (int k : kids) if (k >= T && (owner[k] == -2 || (owner[k] == -1 && posn[k] >= cs.top_off[l]))) fail(PM_ERR_ARG, "top node %d before its child %d", v, k);
+        owner[v] = -1; posn[v] = i;
+      }
+    for (int v = T; v < NN; v++) if (owner[v] == -2) fail(PM_ERR_ARG, "node %d never scheduled", v);
+    // top-down: every internal node but the root exactly once, after its parent
+    std::vector<int> seen(NN, 0);
+    seen[sch.root] = 1;
+    for (size_t l = 0; l + 1 < cs.down_top_off.size(); l++) {
+      for (int i = cs.down_top_off[l]; i < cs.down_top_off[l + 1]; i++) {
+        const int* en = &cs.down_top[(size_t)4 * i];
+        if (seen[en[0]] || !seen[en[1]] || seen[en[1]] > (int)l + 1) fail(PM_ERR_ARG, "top-down order of node %d", en[0]);
+      }
+      for (int i = cs.down_top_off[l]; i < cs.down_top_off[l + 1]; i++) seen[cs.down_top[(size_t)4 * i]] = (int)l + 2;
+    }
+    for (int w = 0; w < nwarps; w++) {
+      int prev = -1;
+      for (int i = cs.down_warp_off[w]; i < cs.down_warp_off[w + 1]; i++) {
+        const int* en = &cs.down_seq[(size_t)4 * i];
+        if (seen[en[0]] || !seen[en[1]]) fail(PM_ERR_ARG, "pre-order of node %d", en[0]);
+        if (en[3] && en[1] != prev) fail(PM_ERR_ARG, "parent-is-previous flag of node %d", en[0]);
+        if (sch.e_child[en[2]] != en[0] || sch.e_parent[en[2]] != en[1]) fail(PM_ERR_ARG, "edge of node %d", en[0]);
+        seen[en[0]] = 1 << 20; prev = en[0];
+      }
+    }
+    for (int v = T; v < NN; v++) if (!seen[v]) fail(PM_ERR_ARG, "node %d never drawn", v);
+    stats[0] = n1; stats[1] = ntop; stats[2] = (long long)cs.top_off.size() - 1; stats[3] = lo; stats[4] = hi; stats[5] = nprev;
+    stats[6] = cs.down_warp_off[nwarps]; stats[7] = (long long)cs.down_top.size() / 4;
+  });
+}
+
 int pm_tree_order(const int32_t* edge, int32_t n_edges, int32_t n_tips, int32_t* nen, int32_t* nodelist, int32_t* root,
                   char* err, size_t errlen) {
   return guarded(err, errlen, [&] {

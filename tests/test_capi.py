@@ -166,3 +166,34 @@ def test_column_names_follow_the_reference():
     assert len(pb.colnames(pb.sumstatMCMCksDICt, 6)) == capi.lib().pm_ncols(capi.PM_V_DICKS, 6)
     with pytest.raises(KeyError):
         pb.colnames(pb.sumstatMCMC)
+
+
+def _ladder(T):
+    edge, node = [], T + 1
+    for t in range(T, 2, -1):
+        edge.append((node, t)); edge.append((node, node + 1)); node += 1
+    edge.append((node, 1)); edge.append((node, 2))
+    return pb.PhyloTree(np.array(edge, dtype=np.int32), np.ones(len(edge)))
+
+
+@pytest.mark.parametrize("shape,T", [("yule", 2), ("yule", 3), ("yule", 9), ("yule", 500), ("yule", 10000), ("ladder", 40),
+                                     ("ladder", 700), ("balanced", 8), ("balanced", 1024)])
+def test_clade_schedules_are_valid(shape, T):
+    """Host logic behind k_prune_clade / k_nodes_clade (pm_tree.hpp::build_clade_schedule), checked by the library's own
+    verifier for several tree shapes and clade sizes: every internal node once, dependencies respected, flags consistent."""
+    from phylomap_b200 import synth
+    t = _ladder(T) if shape == "ladder" else synth.balanced_tree(int(np.log2(T))) if shape == "balanced" else synth.yule_tree(T, seed=T)
+    nen, nodelist, root = t.order()
+    edge = np.asfortranarray(t.edge)
+    for clade_max in (1, 8, max(8, (T - 1) // 64), 10 ** 6):
+        stats = np.zeros(8, dtype=np.int64)
+        err = C.create_string_buffer(512)
+        rc = capi.lib().pm_debug_clade_schedule(capi.ptr(edge), t.E, t.T, capi.ptr(nen), capi.ptr(nodelist), int(root), 8, clade_max,
+                                                capi.ptr(stats), err, 512)
+        assert rc == 0, err.value.decode()
+        n1, ntop, nlev, lo, hi, nprev, d1, dtop = stats.tolist()
+        assert n1 + ntop == T - 1 and d1 + dtop == T - 2
+        if clade_max >= T:                      # one clade: everything in one warp's sequence, nothing on top
+            assert ntop == 0 and hi == T - 1
+        if shape == "yule" and T == 10000 and clade_max == (T - 1) // 64:
+            assert ntop < 400 and hi - lo <= 0.02 * hi and nprev > 0.6 * (T - 1) * 0.66   # the benchmark's schedule: balanced, shallow top
