@@ -391,3 +391,18 @@ def test_squamate_vignette_configuration(oracle):
     fast = pb.sumstatMCMC2sDICt(z, np.asfortranarray(Q2.copy()), cases.PID2, Om, 4, prior, seed=7, precision="f64")
     np.testing.assert_allclose(fast[:, :2].sum(1), 2 * z.edge_length.sum(), rtol=1e-9)
     assert np.all(np.abs(fast[1:, 2:6].sum(1) / (2 * Om * z.edge_length.sum()) - 1) < 0.01)
+
+
+def test_config0_hundred_tips_thousand_sweeps(oracle):
+    """configs[0] of BASELINE.json, the reference's own CPU-runnable case: simulate_2_state_tree on a 100-tip tree,
+    sumstatMCMC for 1000 iterations, one site.  Deterministic mode against the oracle over the whole run."""
+    z = cases.tree2(T=100, S=1, seed=1, mean_branch=10.0)
+    N, Om = 1000, 0.2
+    orc, ref = _oracle(oracle, oracle.PLAIN, [z], cases.Q2, cases.PID2, Om, N)
+    got = pb.sumstatMCMC(z, cases.Q2, cases.PID2, Om, N, seed=7, **DET)
+    assert got.shape == (N, 4)
+    _compare_rows(got, ref, 2, int_cols={2, 3}, tol=1e-9)
+    fast = pb.sumstatMCMC(z, cases.Q2, cases.PID2, Om, N, seed=7)          # production arithmetic, same posterior
+    from scipy import stats
+    for col in (2, 3, 0):
+        assert stats.ks_2samp(fast[100::10, col], ref[100::10, col]).pvalue > 0.005

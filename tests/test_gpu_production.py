@@ -94,20 +94,20 @@ def test_full_tree_size_invariants():
     np.testing.assert_allclose(lo[:, :4] + hi[:, :4], a[:, :4], rtol=1e-5)
 
 
-def test_squamate_sized_sparse_run():
-    """configs[2] shape: 3 951 tips, 2-state SPARSE sampler with the vignette's Q (Squamate_DIC_model_selection.Rnw:83),
-    many synthetic sites.  (The Squamate newick itself lives under /root/reference, which does not exist on the GPU
-    box; a Yule tree of the same size and total length stands in.)"""
+def test_squamate_tree_sparse_run():
+    """configs[2]: the Squamate tree itself (3 951 tips, tree length 87 740; fixture derived from the package's .RData),
+    2-state SPARSE sampler with the vignette's Q (Squamate_DIC_model_selection.Rnw:83) and Omega = 0.012 (so that
+    Omega x tree length ~ 1 000 jump points per site), many synthetic sites."""
     Q = np.array([[-0.001, 0.001], [0.006, -0.006]])
-    tree = synth.yule_tree(3951, seed=3)
-    tree = pb.PhyloTree(tree.edge, tree.edge_length * (87740.48 / tree.edge_length.sum()))
+    tree = cases.squamate_tree()
     S = 2048
     # initial maps: every branch in 8 equal pieces (the Squamate set-up script uses 100, R/Squamate_tree_setup.R:54-82);
     # with the one-piece internal branches of simulate_2_state_tree a 3 951-tip tree underflows even FP64 partials
     z = synth.simulate_2_state_tree(5, tree, Q, cases.PID2, n_sites=S, device="cuda", segments=8)
-    out = pb.SPARSEsumstatMCMC(z, Q, cases.PID2, 0.012, 6, precision="f32", seed=3)
+    out = pb.SPARSEsumstatMCMC(z, Q, cases.PID2, 0.012, 8, precision="f32", seed=3)
     np.testing.assert_allclose(out[:, :2].sum(1), S * tree.edge_length.sum(), rtol=2e-4)
     assert np.all(out[:, 2:] >= 0)
+    assert out[4:, 2:].sum() > 0
 
 
 @pytest.mark.parametrize("precision", ["f32", "f64"])
