@@ -1247,6 +1247,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
   __shared__ uint32_t s_queue[128 * 32 + 128];  // item = branch-in-chunk << 8 | site-in-block
   __shared__ int s_wr[128];                     // records appended so far to the slice of each site
   __shared__ int s_scan[4];
+  __shared__ unsigned short s_bw[32][4];  // dense words: set bits of branch b in each warp
   const long long S = P.S;
   const long long site0 = (long long)blockIdx.x * blockDim.x;
   const int nsites = (int)min((long long)blockDim.x, S - site0);
@@ -1293,11 +1294,34 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       int base = qn;
       for (int ww = 0; ww < warp; ww++) base += s_scan[ww];
       const int total = s_scan[0] + s_scan[1] + s_scan[2] + s_scan[3];
-      int pos = base + inc - c;
-      while (bits) {
-        const int b = __ffs((int)bits) - 1;
-        bits &= bits - 1u;
-        s_queue[pos++] = ((uint32_t)((w << 5) + b) << 8) | threadIdx.x;
+      if (nsites == 128 && total >= 1024) {  // a full block and a quarter of the word's (site, branch) pairs or more
+        // Dense word (long paths everywhere: Omega x t >> 1): queue the items branch by branch, so that the 32 lanes of a
+        // warp get the SAME branch at 32 sites -- similar jump counts, similar trip counts -- instead of 32 different
+        // branches of one site, whose lengths differ by orders of magnitude.
+#pragma unroll 4
+        for (int b = 0; b < 32; b++) {
+          const unsigned bal = __ballot_sync(0xffffffffu, (bits >> b) & 1u);
+          if (lane == 0) s_bw[b][warp] = (unsigned short)__popc(bal);
+        }
+        __syncthreads();
+        int run = qn;
+#pragma unroll 4
+        for (int b = 0; b < 32; b++) {
+          const unsigned bal = __ballot_sync(0xffffffffu, (bits >> b) & 1u);
+          const int c0 = s_bw[b][0], c1 = s_bw[b][1], c2 = s_bw[b][2], c3 = s_bw[b][3];
+          if ((bits >> b) & 1u) {
+            const int before = (warp > 0 ? c0 : 0) + (warp > 1 ? c1 : 0) + (warp > 2 ? c2 : 0);
+            s_queue[run + before + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)((w << 5) + b) << 8) | threadIdx.x;
+          }
+          run += c0 + c1 + c2 + c3;
+        }
+      } else {
+        int pos = base + inc - c;
+        while (bits) {
+          const int b = __ffs((int)bits) - 1;
+          bits &= bits - 1u;
+          s_queue[pos++] = ((uint32_t)((w << 5) + b) << 8) | threadIdx.x;
+        }
       }
       qn += total;
       __syncthreads();
