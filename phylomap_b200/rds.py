@@ -258,18 +258,29 @@ class _Writer:
             self.attributes(attrs)
 
 
-def write_rds(path, obj, compress=True, colnames=None):
-    """saveRDS(obj, path) (version 2, XDR).  `colnames` adds dimnames(list(NULL, colnames)) to a matrix, the form the
+def write_rds(path, obj, compress=True, colnames=None, version=2):
+    """saveRDS(obj, path, version = 2 | 3, compress = TRUE | "gzip" | "bzip2" | "xz" | FALSE), XDR.  `colnames` adds dimnames(list(NULL, colnames)) to a matrix, the form the
     reference's DIC helpers index their traces by (R/sourceme.R:532)."""
     w = _Writer()
     w.out.append(b"X\n")
-    w.int(2)
+    w.int(version)
     w.int(0x00030500)  # written "by" R 3.5.0
-    w.int(0x00020300)  # readable from R 2.3.0
+    w.int(0x00020300 if version == 2 else 0x00030500)  # minimal R version that reads it
+    if version == 3:   # format 3 (R >= 3.5.0 default) adds the native encoding
+        w.int(5)
+        w.out.append(b"UTF-8")
+    elif version != 2:
+        raise ValueError("RDS version must be 2 or 3")
     extra = None
     if colnames is not None:
         extra = {"dimnames": [None, list(colnames)]}
     w.item(obj, extra)
     data = b"".join(w.out)
+    if compress in (True, "gzip"):
+        data = gzip.compress(data)
+    elif compress == "bzip2":
+        data = bz2.compress(data)
+    elif compress == "xz":
+        data = lzma.compress(data)
     with open(path, "wb") as f:
-        f.write(gzip.compress(data) if compress else data)
+        f.write(data)

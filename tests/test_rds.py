@@ -92,3 +92,26 @@ def test_dic_helpers_index_a_trace_read_back_by_name(tmp_path):
     np.testing.assert_array_equal(api._col(back, "l01", 6), mat[:, 6])
     np.testing.assert_array_equal(api._col(back, "log(p(y|Q))", -1), mat[:, 9])
     np.testing.assert_array_equal(api._col(mat, "l01", 6), mat[:, 6])
+
+
+@pytest.mark.parametrize("version", [2, 3])
+@pytest.mark.parametrize("compress", [True, "bzip2", "xz", False])
+def test_formats_and_compressions(tmp_path, version, compress):
+    obj = {"x": np.array([1.5, -2.0]), "names": ["a", "b"], "m": np.arange(6, dtype=np.int32).reshape(2, 3)}
+    p = str(tmp_path / "f.rds")
+    rds.write_rds(p, obj, compress=compress, version=version)
+    back = rds.read_rds(p)
+    np.testing.assert_array_equal(back["x"], obj["x"])
+    np.testing.assert_array_equal(back["m"], obj["m"])
+    assert back["names"] == ["a", "b"]
+
+
+def test_rejects_what_it_cannot_read(tmp_path):
+    p = str(tmp_path / "bad.rds")
+    open(p, "wb").write(b"RDX2\nnot an rds stream")
+    with pytest.raises(ValueError):
+        rds.read_rds(p)
+    import gzip
+    open(p, "wb").write(gzip.compress(b"X\n" + (2).to_bytes(4, "big") + bytes(8) + (238).to_bytes(4, "big")))   # an ALTREP item
+    with pytest.raises(ValueError):
+        rds.read_rds(p)
