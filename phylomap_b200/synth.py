@@ -120,9 +120,15 @@ def read_newick(text):
             children[par].append(v)
         return v
 
+    label = {}
+
     def set_len(v, tok):
         if ":" in tok:
-            blen[v] = float(tok.rsplit(":", 1)[1])
+            name, length = tok.rsplit(":", 1)
+            blen[v] = float(length)
+        else:
+            name = tok
+        label[v] = name.strip().strip("'")
 
     stack, i, root = [], 0, None
     while i < len(s):
@@ -152,7 +158,38 @@ def read_newick(text):
     for v in parent_of:
         blen.setdefault(v, 0.0)
     edge, el = _relabel_cladewise(parent_of, children, root, T, blen)
-    return PhyloTree(edge, el)
+    # tips are numbered in order of appearance (ape::read.tree): the same walk _relabel_cladewise does
+    tips, stack2 = [], [root]
+    while stack2:
+        v = stack2.pop()
+        if children[v]:
+            stack2.append(children[v][1])
+            stack2.append(children[v][0])
+        else:
+            tips.append(label.get(v, ""))
+    return PhyloTree(edge, el, tip_label=tips)
+
+
+def make_squamate_tree(newick_path, tipdata_csv, segments=100):
+    """R/Squamate_tree_setup.R:8-88 (`make_squamate_tree`): the Squamate phylogeny in the form the samplers take -- every
+    branch cut into 100 equal segments named 1, tip states from the trait table ("0" -> 1, "1" -> 2, anything else keeps the
+    script's placeholder -10), the last segment of a tip branch named after its tip state.  The tree file shipped in
+    inst/extdata already holds the 3 951 tips the script keeps."""
+    import csv
+    with open(newick_path) as f:
+        tree = read_newick(f.read())
+    with open(tipdata_csv, newline="") as f:
+        rows = list(csv.reader(f))[1:]
+    parity = {r[0]: r[1] for r in rows}
+    code = {"0": 1, "1": 2}
+    states = np.array([code.get(parity.get(name, ""), -10) for name in tree.tip_label], dtype=np.int32)
+    maps = [np.full(segments, t / segments) for t in tree.edge_length]
+    names = [np.ones(segments, dtype=np.int32) for _ in range(tree.E)]
+    for e in range(tree.E):
+        c = tree.edge[e, 1]
+        if c <= tree.T:
+            names[e][-1] = states[c - 1]
+    return PhyloTree(tree.edge, tree.edge_length, states, maps, names, tree.tip_label)
 
 
 def _expm(Qt):

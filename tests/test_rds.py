@@ -115,3 +115,21 @@ def test_rejects_what_it_cannot_read(tmp_path):
     open(p, "wb").write(gzip.compress(b"X\n" + (2).to_bytes(4, "big") + bytes(8) + (238).to_bytes(4, "big")))   # an ALTREP item
     with pytest.raises(ValueError):
         rds.read_rds(p)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TREE), reason="the reference's data files are only present in the build container")
+def test_make_squamate_tree_reproduces_the_shipped_fixture():
+    """R/Squamate_tree_setup.R restated (synth.make_squamate_tree) from the newick file and the trait table gives the
+    tree the package ships as .RData: ape's node numbering, tip labels, the 100-segment maps, the script's tip-state
+    coding (trait "1" -> 2; the trait table's "2" falls through to the placeholder -10, as in the shipped file)."""
+    from phylomap_b200 import synth
+    d = os.path.dirname(REF_TREE)
+    t = synth.make_squamate_tree(os.path.join(d, "squamate.phy"), os.path.join(d, "squamate_tipdata.csv"))
+    z = pb.PhyloTree.read_rds(REF_TREE)
+    np.testing.assert_array_equal(t.edge, z.edge)                       # read_newick numbers nodes like ape::read.tree
+    np.testing.assert_allclose(t.edge_length, z.edge_length, rtol=1e-14)
+    assert t.tip_label == list(z.tip_label)
+    np.testing.assert_array_equal(t.states, z.states)
+    for a, b in zip(t.mapnames, z.mapnames):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_allclose(np.concatenate(t.maps), np.concatenate(z.maps), rtol=1e-13)
