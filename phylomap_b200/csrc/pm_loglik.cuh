@@ -46,7 +46,7 @@ __global__ void k_transprob(const double* __restrict__ Qrow /* n*n row-major */,
 
 template <typename Real, int NS>
 __global__ void __launch_bounds__(256) k_loglik(ChainParams<Real> P, const Real* __restrict__ TP, double* __restrict__ ll_partial) {
-  constexpr int NC = NS > 0 ? NS : PM_DIC_NMAX;
+  constexpr int NC = NS > 0 ? NS : PM_NMAX;  // the direct sampler prunes with this kernel for any n <= PM_NMAX (the DIC chains stop at PM_DIC_NMAX)
   const int n = NS > 0 ? NS : P.n;
   __shared__ double s_S[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;

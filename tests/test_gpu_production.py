@@ -174,6 +174,31 @@ def test_direct_sampler_and_mcmc_agree_on_the_gpu():
     np.testing.assert_allclose(ex[:, :4].mean(0), mc[:, :4].mean(0), rtol=0.02)
 
 
+def test_tutorial_twenty_state_model_three_samplers(oracle):
+    """phylomap_tutorial.Rnw:67-135: 20-state tridiagonal Q, 50 tips, Omega = 0.2 -- sumstatEXP, sumstatMCMC and
+    SPARSEsumstatMCMC must give the same distribution of the number of jumps (the tutorial overlays their histograms).
+    Regression: the direct sampler's pruning kernel kept its partials in arrays of 8 states."""
+    Q = np.zeros((20, 20))
+    for j in range(19):
+        Q[j, j + 1] = Q[j + 1, j] = 0.003
+    np.fill_diagonal(Q, -Q.sum(1))
+    pid = np.full(20, 0.05)
+    phy = synth.yule_tree(50, seed=3, mean_branch=12.0)
+    tips = synth.simulate_tip_states(phy, Q, np.eye(20)[0], 1, seed=11).numpy()[0].astype(np.int32)
+    z = phy.with_states(tips)
+    N = 3000
+    ex = pb.sumstatEXP(z, Q, pid, N, seed=1)
+    mc = pb.sumstatMCMC(z, Q, pid, 0.2, N, seed=2)[200::4]
+    sp = pb.SPARSEsumstatMCMC(z, Q, pid, 0.2, N, seed=3)[200::4]
+    w, V = np.linalg.eig(Q)
+    ref = oracle.OracleRun(oracle.EXP, [z.oracle_dict()], Q, pid, 0.2, 1500, rng_mode=oracle.SEQUENTIAL, seed=22,
+                           eig=(V.real, np.linalg.inv(V).real, np.diag(w.real))).run()
+    je, jm, js, jr = (a[:, 20:].sum(1) for a in (ex, mc, sp, ref))
+    np.testing.assert_allclose(ex[:, :20].sum(1), z.edge_length.sum(), rtol=1e-5)
+    assert abs(je.mean() - jr.mean()) < 0.15 and abs(jm.mean() - jr.mean()) < 0.2 and abs(js.mean() - jr.mean()) < 0.2
+    assert stats.ks_2samp(je, jr).pvalue > 0.005 and stats.ks_2samp(je, jm).pvalue > 0.002 and stats.ks_2samp(jm, js).pvalue > 0.002
+
+
 def test_record_capacity_overflow_is_reported():
     """A path with two or more real jumps keeps its runs as records in a per-(site, chunk) slice; when the caller
     forces the slices too small the sweep must stop with PM_ERR_CAPACITY, not corrupt memory."""
