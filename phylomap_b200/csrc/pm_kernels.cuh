@@ -1026,16 +1026,21 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
 //
 // State a sweep leaves per (branch, site):  meta = m (bits 0-15) | real jumps nj (16-21) | state of run 0 (22-26) |
 // state of run 1 (27-31);  pos1 = length of the first piece when m == 2 or nj == 1 (the position of the only jump point,
-// respectively of the only real jump);  paths with nj >= 2 (a fraction of a percent) keep all their runs as records.
+// respectively of the only real jump);  paths with nj >= 2 (a fraction of a percent) keep all their runs as records and
+// pos1 holds their offset in the site's record slice; nj = 63 stands for "63 or more": such a path starts with a header
+// record holding its run count.  The first sweep finds m and (for two-piece maps) pos1 seeded from the caller's maps.
 //
 //   k_paths_easy  every branch whose previous path has at most one jump point (m <= 2: ~98 % here).  No
 //                 regeneration and no record is needed: the pieces are (pos1, t - pos1), the new states are the two
 //                 node states, the new virtual-jump counts take one uniform per run from a Philox block shared by two
 //                 branches.  Coalesced streaming over the chunk, straight-line code; everything else gets a bit in the
 //                 per-(site, chunk) mask.
-//   k_paths_hard  thread = (site, chunk) again, every lane walks the set bits of ITS mask: regenerates the virtual jumps
-//                 of the previous sweep run by run, redraws the interior states (resamplebranchstates :264-308),
-//                 merges and counts (shortener :44-73 / shortenerbf :997-1028), draws the new counts.
+//   k_paths_hard  block = 128 sites x one chunk again; the set bits of the block's masks are compacted into a shared-memory
+//                 work queue and handed out 128 at a time, one (site, branch) item per thread (dense mask words branch by
+//                 branch, so that a warp's lanes walk the same branch): regenerates the virtual jumps of the previous
+//                 sweep run by run, redraws the interior states (resamplebranchstates :264-308), merges and counts
+//                 (shortener :44-73 / shortenerbf :997-1028), draws the new counts; a path too long for the local
+//                 buffer is walked a second time to write its records in place.
 // ------------------------------------------------------------------------------------------------
 #define PM_META(m, nj, s0, s1) ((uint32_t)(m) | ((uint32_t)(nj) << 16) | ((uint32_t)(s0) << 22) | ((uint32_t)(s1) << 27))
 
