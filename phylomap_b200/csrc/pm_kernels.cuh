@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
     int lrole = ((lane < 29 && (role_ent || tip_in)) ? 1 : 0) | (role_nxt ? 2 : 0) | (role_b ? 4 : 0) | (role_ent ? 8 : 0);
     unsigned lane4 = 4 * lane;
     // fast path only with the full shared-memory table (a power of two, so one OR tests both counts) and one-hot tips
-    unsigned fast_pow = (!parity && npow_s == PM_SMEM_POW) ? (unsigned)PM_SMEM_POW : 0u;
+    unsigned fast_pow = ((!parity || NS == 4) && npow_s == PM_SMEM_POW) ? (unsigned)PM_SMEM_POW : 0u;
     int lane_v = lane;
     asm volatile("" : "+l"(cbase), "+r"(dst_off), "+r"(lrole), "+r"(lane4), "+r"(fast_pow), "+r"(lane_v));
     auto issue = [&](unsigned slot, const int4* e, const int4& q1, const int4& q2, bool more) {
@@ -445,6 +445,18 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
     unsigned ring_end = ring + DEPTH * PM_CLADE_SLOT;
     asm volatile("" : "+r"(ring_end));
     // one node: (pn_off, fl, xcur) describe it, (pn_off_n, fl_n, xnext) receive the next node's
+    // P_k times a tip's partial: one column of P_k for a one-hot tip; for the hidden-rate models' parity tips
+    // (1,0,1,0) / (0,1,0,1) the sum of the two columns whose state has the observed parity -- the same additions, in the
+    // same order, as the mat-vec with that 0/1 vector
+    auto tip_column = [&](int k, int code, Real* v) {
+      if (!parity) { VecIO<Real, NS>::load(sPowT + (k * NS + code) * NS, NS, v); return; }
+      Real c0[NS], c1[NS];
+      const int j0 = 1 - code;
+      VecIO<Real, NS>::load(sPowT + (k * NS + j0) * NS, NS, c0);
+      VecIO<Real, NS>::load(sPowT + (k * NS + (j0 + 2 < NS ? j0 + 2 : j0)) * NS, NS, c1);
+#pragma unroll
+      for (int j = 0; j < NS; j++) v[j] = c0[j] + c1[j];
+    };
     auto step = [&](int idx, long long pn_off, int fl, const Real* xcur, long long& pn_off_n, int& fl_n, Real* xnext) {
       const unsigned slot_n = (slot + PM_CLADE_SLOT == ring_end) ? ring : slot + PM_CLADE_SLOT;
       // the group of node idx + 1 has landed as well (DEPTH - 2 younger ones may still be in flight): its header tells
@@ -463,7 +475,7 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
       // a tip child is one column of P_k, an internal child one 4 x 4 (2 x 2) product with P_k
       const bool fast = __all_sync(0xffffffffu, ((unsigned)(ma - 1) | (unsigned)(mb - 1)) < fast_pow);
       if (fast) {
-        if (fl & 16) VecIO<Real, NS>::load(sPowT + ((ma - 1) * NS + lds_u8(slot + 256 + lane_v)) * NS, NS, va);
+        if (fl & 16) tip_column(ma - 1, lds_u8(slot + 256 + lane_v), va);
         else {
           const Real* Ma = sPow + (ma - 1) * NS * NS;
           Real src[NS];
@@ -479,7 +491,7 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
             va[r] = acc;
           }
         }
-        if (fl & 32) VecIO<Real, NS>::load(sPowT + ((mb - 1) * NS + lds_u8(slot + 288 + lane_v)) * NS, NS, vb);
+        if (fl & 32) tip_column(mb - 1, lds_u8(slot + 288 + lane_v), vb);
         else {
           const Real* Mb = sPow + (mb - 1) * NS * NS;
           Real src[NS];
