@@ -197,3 +197,17 @@ def test_clade_schedules_are_valid(shape, T):
             assert ntop == 0 and hi == T - 1
         if shape == "yule" and T == 10000 and clade_max == (T - 1) // 64:
             assert ntop < 400 and hi - lo <= 0.02 * hi and nprev > 0.6 * (T - 1) * 0.66   # the benchmark's schedule: balanced, shallow top
+
+
+def test_read_newick_numbers_nodes_like_ape():
+    """ape::read.tree numbering: tips 1..T in order of appearance, the root T + 1, internal nodes in preorder; edges in
+    preorder (checked against the package's 3 951-tip tree in tests/test_rds.py where the reference is present)."""
+    from phylomap_b200 import synth
+    t = synth.read_newick("((A:1,B:2):0.5,(C:3,('D d':4,E:5):1.5):2.5);")
+    assert t.tip_label == ["A", "B", "C", "D d", "E"]
+    assert t.edge.tolist() == [[6, 7], [7, 1], [7, 2], [6, 8], [8, 3], [8, 9], [9, 4], [9, 5]]
+    np.testing.assert_allclose(t.edge_length, [0.5, 1, 2, 2.5, 3, 1.5, 4, 5])
+    nen, nodelist, root = t.order()
+    assert root == 6 and sorted(nen.tolist()) == list(range(1, 9))
+    with pytest.raises(ValueError):
+        synth.read_newick("(A:1,B:1,C:1);")          # not binary
