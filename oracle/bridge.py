@@ -75,6 +75,87 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+_REF = None
+
+
+def ref_path():
+    return os.path.join(_HERE, "_ref", "libphylomap_ref.so")
+
+
+def ref_lib():
+    """oracle/_ref/libphylomap_ref.so: the UNMODIFIED reference sources (src/phylomap.cpp + RcppExports.cpp) compiled
+    against the stand-in headers of oracle/standin/ (oracle/Makefile, target `ref`).  Built here when /root/reference
+    exists; on the GPU box the prebuilt file travels with the repo.  Returns None when neither is available."""
+    global _REF
+    if _REF is None:
+        so = ref_path()
+        if os.path.exists("/root/reference/src/phylomap.cpp"):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        if not os.path.exists(so):
+            return None
+        L = C.CDLL(so)
+        L.ref_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        L.ref_ncols.argtypes = [C.c_int, C.c_int]
+        L.ref_rng_probe.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
+        _REF = L
+    return _REF
+
+
+def _pack_trees(trees, keep):
+    arr = (_Tree * len(trees))()
+    for i, t in enumerate(trees):
+        edge = np.asfortranarray(t["edge"], dtype=np.int32)
+        nen = np.ascontiguousarray(t["nen"], dtype=np.int32)
+        nodelist = np.ascontiguousarray(t["nodelist"], dtype=np.int32)
+        mo = np.ascontiguousarray(t["maps_off"], dtype=np.int64)
+        ml = np.ascontiguousarray(t["maps_len"], dtype=np.float64)
+        ms = np.ascontiguousarray(t["maps_state"], dtype=np.int32)
+        st = np.ascontiguousarray(t["states"], dtype=np.int32)
+        if st.ndim == 1:
+            st = st[None, :]
+        el = None if t.get("edge_length") is None else np.ascontiguousarray(t["edge_length"], dtype=np.float64)
+        keep += [edge, nen, nodelist, mo, ml, ms, st, el]
+        arr[i] = _Tree(st.shape[1], edge.shape[0], _p(edge), _p(nen), _p(nodelist), int(t["root"]), _p(mo), _p(ml), _p(ms),
+                       _p(st), st.shape[0], _p(el))
+    return arr
+
+
+def ref_run(variant, trees, Q, pid, Omega, N, prior=None, seed=1, B=None, eig=None):
+    """One call of the reference's own `.Call` entry point for `variant` (phylomap_maketreelistMCMC ... ksDICt) with R's
+    generator seeded like set.seed(seed).  One site per tree (the reference has no site axis).  Returns (rows, Q, B):
+    Q and B as the call left them (the rate-updating drivers rewrite them in place)."""
+    L = ref_lib()
+    if L is None:
+        raise OracleError("oracle/_ref is not built (no /root/reference here and no prebuilt library)")
+    keep = []
+    n = Q.shape[0]
+    Qf = np.asfortranarray(np.array(Q, dtype=np.float64))
+    Bf = np.asfortranarray(np.eye(n) + Qf / Omega) if B is None else np.asfortranarray(np.array(B, dtype=np.float64))
+    pidc = np.ascontiguousarray(pid, dtype=np.float64)
+    arr = _pack_trees(trees, keep)
+    pr = None if prior is None else np.ascontiguousarray(prior, dtype=np.float64)
+    cfg = _Config()
+    cfg.variant, cfg.n, cfg.N, cfg.ntrees, cfg.Omega = variant, n, N, len(trees), float(Omega)
+    cfg.prior, cfg.nprior = _p(pr), 0 if pr is None else len(pr)
+    cfg.rng_mode, cfg.seed = SEQUENTIAL, seed
+    if eig is not None:
+        lefts, rights, d = [np.asfortranarray(x, dtype=np.float64) for x in eig]
+        keep += [lefts, rights, d]
+        cfg.lefts, cfg.rights, cfg.d = _p(lefts), _p(rights), _p(d)
+    out = np.zeros((N, L.ref_ncols(variant, n)), dtype=np.float64, order="F")
+    err = C.create_string_buffer(512)
+    rc = L.ref_run(C.byref(arr), C.byref(cfg), _p(Qf), _p(pidc), _p(Bf), _p(out), err, 512)
+    if rc:
+        raise OracleError(err.value.decode())
+    return out, Qf, Bf
+
+
+def ref_rng_probe(seed, kind, n, a=0.0, b=0.0):
+    out = np.zeros(n)
+    ref_lib().ref_rng_probe(seed, {"unif": 0, "exp": 1, "norm": 2, "gamma": 3, "rexp": 4}[kind], n, a, b, _p(out))
+    return out
+
+
 class OracleError(RuntimeError):
     pass
 

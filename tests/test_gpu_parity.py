@@ -275,6 +275,64 @@ def test_replay_of_sequential_r_stream(oracle, variant, name, prior):
     _compare_state(ch, orc, z, 2, z.E, n_paths=20, exact_lengths=prior is None)
 
 
+def _reference_fixtures():
+    import glob
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    return sorted(p for p in glob.glob(os.path.join(here, "golden", "reference", "*.json")) if "/exp_" not in p)
+
+
+@pytest.mark.parametrize("path", _reference_fixtures(), ids=lambda p: p.split("/")[-1][:-5])
+def test_gpu_replays_the_reference(oracle, path):
+    """Tier 1 of BASELINE.json against THE REFERENCE ITSELF: tests/golden/reference/*.json are outputs of the unmodified
+    src/phylomap.cpp (oracle/_ref, made by tests/golden/make_reference_golden.py).  The kernels consume the uniform
+    stream of that R-order run (recorded by the oracle restatement, which reproduces the reference bit for bit:
+    tests/test_reference_pin.py) and must return the reference's rows: integer counts, root / tree columns identical,
+    dwell times 1e-9 (bar 1e-6), rates 1e-7, log-likelihood 1e-9; Q and B end where the reference left them."""
+    import json
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_reference_golden as mrg
+    with open(path) as f:
+        d = json.load(f)
+    case, want = d["case"], np.array(d["rows"])
+    trees = mrg.trees_of(case)
+    Q0, pid, n = np.array(case["Q"]), np.array(case["pid"]), len(case["pid"])
+    orc = oracle.OracleRun(getattr(oracle, case["variant"]), [t.oracle_dict() for t in trees], Q0.copy(), pid, case["Omega"],
+                           case["N"], prior=case.get("prior"), rng_mode=oracle.SEQUENTIAL, seed=case["seed"], want_log=True)
+    orc.run()
+    table, host = orc.export_log()
+    variant = {"PLAIN": capi.PM_V_PLAIN, "SPARSE": capi.PM_V_SPARSE, "BIGTREE": capi.PM_V_BIGTREE, "BF": capi.PM_V_BF,
+               "KS": capi.PM_V_KS, "MT": capi.PM_V_MT, "KSMT": capi.PM_V_KSMT, "DIC2S": capi.PM_V_DIC2S,
+               "DICKS": capi.PM_V_DICKS}[case["variant"]]
+    Qg = np.asfortranarray(Q0.copy())
+    ch = pb.Chain(variant, trees if len(trees) > 1 else trees[0], Qg, pid, case["Omega"], case["N"], prior=case.get("prior"),
+                  seed=case["seed"], table=table, host_table=host, **DET)
+    got = ch.run()
+    v = case["variant"]
+    if v in ("PLAIN", "SPARSE", "BIGTREE"):
+        ints, ll = set(range(n, n * n)), None
+    elif v in ("BF", "MT"):
+        ints, ll = {2, 3, 4, 5, 8}, None
+    elif v == "DIC2S":
+        ints, ll = {2, 3, 4, 5, 8}, 9
+    elif v in ("KS", "KSMT"):
+        ints, ll = set(range(n, n + n * n)) | {want.shape[1] - 1}, None
+    else:
+        ints, ll = set(range(n, n + n * n)) | {want.shape[1] - 2}, want.shape[1] - 1
+    assert got.shape == want.shape
+    for c in range(want.shape[1]):
+        if c in ints:
+            assert np.array_equal(got[:, c], want[:, c]), "integer column %d differs from the reference" % c
+        elif c == ll:
+            np.testing.assert_allclose(got[:, c], want[:, c], rtol=1e-9)
+        else:
+            np.testing.assert_allclose(got[:, c], want[:, c], rtol=1e-9 if c < n else 1e-7, atol=1e-12, err_msg="column %d" % c)
+    np.testing.assert_allclose(Qg, np.array(d["Q_after"]), rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(ch.B, np.array(d["B_after"]), rtol=1e-7, atol=1e-12)
+
+
 def test_one_call_entries_match_chain(oracle):
     """The seven drop-in entries (pm_maketreelist*) are the chain interface run in one go."""
     z = cases.tree2(T=20, S=3, seed=21)

@@ -25,6 +25,16 @@ def test_rgamma_moments(oracle):
         assert abs(x.var() / (shape * scale * scale) - 1) < 0.03
 
 
+def test_rgamma_distribution(oracle):
+    """Kolmogorov-Smirnov against the Gamma cdf in every regime of R's rgamma.c: GS (a < 1), and the three
+    (b, si, c) parameter ranges of GD (a <= 3.686, <= 13.022, above)."""
+    from scipy import stats
+    for shape, scale in [(0.3, 2.0), (0.9, 1.0), (1.0, 1.0), (2.5, 0.5), (3.686, 1.0), (7.0, 0.25), (20.0, 0.1), (400.0, 0.01)]:
+        x = oracle.rng_probe(11, "gamma", 100000, shape, scale)
+        p = stats.kstest(x, stats.gamma(shape, scale=scale).cdf).pvalue
+        assert p > 1e-3, (shape, scale, p)
+
+
 def test_philox_known_answers(oracle):
     # Random123 kat_vectors: philox4x32-10
     assert [hex(v) for v in oracle.philox([0, 0, 0, 0], [0, 0])] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
