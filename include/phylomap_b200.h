@@ -214,6 +214,11 @@ int pm_chain_get_piece_counts(pm_chain* c, int32_t tree, int32_t* out /* [S][E] 
 int pm_chain_get_path(pm_chain* c, int32_t tree, int64_t site, int32_t e, double* len, int32_t* st, int32_t cap);
 int pm_chain_get_partials(pm_chain* c, int32_t tree, int64_t site, double* out /* [2T-1][n], tip rows zero */);
 int64_t pm_chain_device_bytes(pm_chain* c);
+/* Rate-updating samplers: per rate parameter, in the order of the trace columns (l01, l10, then for the hidden-rate
+ * models kappa-> x k, kappa<- x k, gamma x k), how many Gamma proposals were drawn and how many were installed in Q
+ * (the reference has no such counter; its accept / reject logic is src/phylomap.cpp:1205-1219, 1466-1500, ...).
+ * Returns the number of parameters (0 for the fixed-Q samplers); at most `cap` entries are written. */
+int32_t pm_chain_acceptance(pm_chain* c, int64_t* proposed, int64_t* accepted, int32_t cap);
 void pm_chain_destroy(pm_chain* c);
 
 /* Host-side random numbers used by the rate updates (R's Mersenne-Twister after set.seed(seed), unif_rand, exp_rand,

@@ -151,6 +151,13 @@ class Chain:
     def device_bytes(self):
         return int(capi.lib().pm_chain_device_bytes(self.h))
 
+    def acceptance(self):
+        """(proposed, accepted) per rate parameter in trace-column order (l01, l10, kappa->, kappa<-, gamma)."""
+        prop = np.zeros(64, dtype=np.int64)
+        acc = np.zeros(64, dtype=np.int64)
+        k = capi.lib().pm_chain_acceptance(self.h, capi.ptr(prop), capi.ptr(acc), 64)
+        return prop[:k].copy(), acc[:k].copy()
+
     def node_states(self, tree=0):
         t = self.trees[tree]
         out = np.zeros((t.n_sites(), 2 * t.T - 1), dtype=np.int32)

@@ -43,7 +43,7 @@ EXPORTS = ["pm_default_options", "pm_maketreelistMCMC", "pm_SPARSEmaketreelistMC
            "pm_ncols", "pm_tree_order", "pm_debug_clade_schedule", "pm_chain_create", "pm_chain_run", "pm_chain_state_bytes",
            "pm_chain_export_state", "pm_chain_import_state", "pm_chain_time_prune",
            "pm_chain_kernel_times", "pm_chain_enable_timing", "pm_chain_get_node_states", "pm_chain_get_piece_counts",
-           "pm_chain_get_path", "pm_chain_get_partials", "pm_chain_device_bytes", "pm_chain_destroy",
+           "pm_chain_get_path", "pm_chain_get_partials", "pm_chain_device_bytes", "pm_chain_acceptance", "pm_chain_destroy",
            "pm_rng_probe", "pm_release_cached_memory", "pm_device_count", "pm_version"]
 
 _LIB = None
@@ -98,6 +98,8 @@ def lib():
     L.pm_chain_get_partials.argtypes = [vp, i32, i64, vp]
     L.pm_chain_device_bytes.argtypes = [vp]
     L.pm_chain_device_bytes.restype = i64
+    L.pm_chain_acceptance.argtypes = [vp, vp, vp, i32]
+    L.pm_chain_acceptance.restype = i32
     L.pm_chain_destroy.argtypes = [vp]
     L.pm_chain_destroy.restype = None
     L.pm_rng_probe.argtypes = [C.c_uint32, i32, i32, dbl, dbl, vp]

@@ -227,6 +227,7 @@ struct pm_chain {
   virtual void export_state(void* buf, int64_t bytes) = 0;
   virtual void import_state(const void* buf, int64_t bytes) = 0;
   double kernel_ms[4] = {0, 0, 0, 0};
+  std::vector<long long> rate_proposed, rate_accepted;  // per rate parameter, trace-column order (pm_rates.hpp)
   int64_t launches = 0;
   int64_t dev_bytes = 0;
   bool timing = false;
@@ -242,9 +243,10 @@ struct TreeDev {
   int n_cd_top_levels = 0, n_cd_tips = 0;  // clade schedule of the production pruning kernel
   int n_cl_top_levels = 0;
   DevBuf up_entries8, up_entries, up_off, down_entries, down_off, e_parent, e_child, e_len, maps_off, maps_len, cap_off;
-  DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, slow_mask, pos1;
+  DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, hard_ballot, wk_off, wk_g, rec_cursor, pos1;
+  long long wk_total = 0, dw_rows = 0;
+  int hard_blocks = 0;
   DevBuf e_len_d, TP, ll_partial;  // DIC samplers: branch lengths in FP64, exp(Q t_e) per branch, block partials of log p(y|Q)
-  int mask_words = 0;
   std::vector<int> cap_off_h;
   pm::ChainParams<Real> P;
   dim3 paths_grid;
@@ -281,7 +283,6 @@ struct ChainT : pm_chain {
   size_t smem_prune = 0, smem_nodes = 0, smem_paths = 0;
   int rows_cap = 0;
   bool debug_sync = false; int debug_kernel = 0;
-  int k3_variant = 4;   // minimum resident blocks the general path kernel is compiled for (PHYLOMAP_B200_K3H, for tuning)
   int k1_variant = 42;  // production pruning kernel variant (pm_launch_impl.cuh; PHYLOMAP_B200_K1_UNROLL overrides, for tuning)
   struct Timed { cudaEvent_t a, b; int k; };
   std::vector<Timed> timed;
@@ -357,10 +358,11 @@ struct ChainT : pm_chain {
     pm::Sweep<Real, NSc, EX>::nodes(t.P, gx, smem_nodes, stream, iter);
     end_timed();
     begin_timed(2);
-    pm::Sweep<Real, NSc, EX>::paths(t.P, t.paths_grid, smem_paths, stream, iter, iter == 0 ? 1 : 0, t.chunk, k3_variant);
+    if (!EX) CK(cudaMemsetAsync(t.rec_cursor.p, 0, t.rec_cursor.bytes, stream));  // (inside K3's timed region: it is part of the step)
+    pm::Sweep<Real, NSc, EX>::paths(t.P, t.paths_grid, smem_paths, stream, iter, iter == 0 ? 1 : 0, t.chunk, t.hard_blocks);
     end_timed();
     begin_timed(3);
-    pm::k_reduce<<<1, 256, 0, stream>>>(t.dw_partial.template as<double>(), 2 * t.nblocks, n, cnt.as<unsigned long long>(),
+    pm::k_reduce<<<1, 256, 0, stream>>>(t.dw_partial.template as<double>(), t.dw_rows, n, cnt.as<unsigned long long>(),
                                         root_out.as<int>(), row, 0);
     end_timed();
     launches += exact ? 4 : 5;
@@ -673,16 +675,35 @@ struct ChainT : pm_chain {
         t->rec_st[b].alloc((size_t)R * S);
       }
       CK(cudaMemsetAsync(t->node_state.p, 0, t->node_state.bytes, stream));
-      // two rows of partial dwell sums per block: [0, nblocks) easy / deterministic kernel, [nblocks, 2 nblocks) hard kernel
-      t->dw_partial.alloc((size_t)2 * t->nblocks * n * sizeof(double));
+      // partial dwell sums per block: [0, nblocks) easy / deterministic / direct-sampler kernel, then the general path kernel's
+      t->hard_blocks = (!exact && !V.exp && !V.llonly) ? prop.multiProcessorCount * 4 : 0;  // persistent: 4 blocks of 4 warps per SM
+      t->dw_rows = t->nblocks + t->hard_blocks;
+      t->dw_partial.alloc((size_t)t->dw_rows * n * sizeof(double));
       CK(cudaMemsetAsync(t->dw_partial.p, 0, t->dw_partial.bytes, stream));
-      t->mask_words = (t->chunk + 31) / 32;
       if (!exact && !V.exp && !V.llonly) {
-        t->slow_mask.alloc((size_t)ny * t->mask_words * S * sizeof(uint32_t));
+        // Branch-major ballot array and the general kernel's work items: branch e is cut into items of g_e ballot words
+        // (32 g_e sites), g_e chosen so that an item holds ~96 branch-sites with two or more jump points in equilibrium
+        // (their number on a branch of length t is Poisson(Omega t)).
+        const long long Wl = (S + 31) / 32;
+        t->hard_ballot.alloc((size_t)E * Wl * sizeof(uint32_t));
+        std::vector<long long> woff(E + 1, 0);
+        std::vector<int> wg(E);
+        for (int e = 0; e < E; e++) {
+          const double lam = Omega * (double)elen[e];
+          const double h = std::max(1e-6, 1.0 - std::exp(-lam) * (1.0 + lam));
+          long long g = (long long)std::ceil(96.0 / (32.0 * h));
+          g = std::max(1LL, std::min<long long>(std::min<long long>(g, 32), Wl));
+          wg[e] = (int)g;
+          woff[e + 1] = woff[e] + (Wl + g - 1) / g;
+        }
+        t->wk_total = woff[E];
+        upload(t->wk_off, woff, stream);
+        upload(t->wk_g, wg, stream);
+        t->rec_cursor.alloc((size_t)ny * S * sizeof(int));
         t->pos1.alloc((size_t)E * S * sizeof(Real));
       }
       dev_bytes += t->tipcode.bytes + t->node_state.bytes + t->meta.bytes + t->PL.bytes + 2 * (t->rec_len[0].bytes + t->rec_st[0].bytes) +
-                   t->dw_partial.bytes + t->slow_mask.bytes + t->pos1.bytes;
+                   t->dw_partial.bytes + t->hard_ballot.bytes + t->rec_cursor.bytes + t->pos1.bytes;
       trees.push_back(std::move(t));
     }
 
@@ -722,7 +743,6 @@ struct ChainT : pm_chain {
     }
     mt.reseed((uint32_t)opt.seed);
     if (const char* v = getenv("PHYLOMAP_B200_K1_UNROLL")) k1_variant = atoi(v);
-    if (const char* v = getenv("PHYLOMAP_B200_K3H")) k3_variant = atoi(v);
     if (const char* v = getenv("PHYLOMAP_B200_DEBUG_SYNC")) debug_sync = v[0] == '1';
 
     // shared-memory sizes
@@ -738,7 +758,9 @@ struct ChainT : pm_chain {
       pm::ChainParams<Real>& P = t.P;
       P.n = n; P.T = T; P.E = E; P.S = t.S;
       P.cap_off = t.cap_off.template as<int>();
-      P.slow_mask = t.slow_mask.template as<uint32_t>(); P.mask_words = t.mask_words;
+      P.hard_ballot = t.hard_ballot.template as<uint32_t>(); P.W = (int)((t.S + 31) / 32);
+      P.wk_off = t.wk_off.template as<long long>(); P.wk_g = t.wk_g.template as<int>(); P.wk_total = t.wk_total;
+      P.rec_cursor = t.rec_cursor.template as<int>(); P.chunk = t.chunk; P.easy_blocks = t.nblocks;
       P.pos1 = t.pos1.template as<Real>();
       P.model = model.as<Real>(); P.ppow = ppow.as<Real>(); P.jcap = jcap;
       P.up_entries = t.up_entries.template as<int>(); P.up_off = t.up_off.template as<int>();
@@ -853,7 +875,7 @@ struct ChainT : pm_chain {
     else pm::k_exp_branches<Real, 0><<<t.paths_grid, 128, smem_b, stream>>>(t.P, TP, el, (Real)Omega, iter, t.chunk);
     end_timed();
     begin_timed(3);
-    pm::k_reduce<<<1, 256, 0, stream>>>(t.dw_partial.template as<double>(), 2 * t.nblocks, n, cnt.as<unsigned long long>(),
+    pm::k_reduce<<<1, 256, 0, stream>>>(t.dw_partial.template as<double>(), t.dw_rows, n, cnt.as<unsigned long long>(),
                                         root_out.as<int>(), row, 0);
     end_timed();
     launches += 4;
@@ -888,6 +910,9 @@ struct ChainT : pm_chain {
     // rate-updating samplers: one host round trip per iteration
     ensure_rows(1);
     pm::host::RateModel rm{n, Q, B, Omega, prior.data()};
+    const size_t nparam = V.hidden ? (size_t)2 + 3 * (n / 2 - 1) : 2;
+    if (rate_proposed.size() != nparam) { rate_proposed.assign(nparam, 0); rate_accepted.assign(nparam, 0); }
+    rm.proposed = rate_proposed.data(); rm.accepted = rate_accepted.data();
     pm::host::UniformSource& g = host_rng();
     std::vector<double> row(ncols);
     std::vector<std::vector<double>> jodt(ntrees, std::vector<double>(ncols, 0.0));
@@ -1405,6 +1430,11 @@ int pm_chain_get_partials(pm_chain* c, int32_t tree, int64_t site, double* out) 
   return guarded(nullptr, 0, [&] { c->partials(tree, site, out); });
 }
 int64_t pm_chain_device_bytes(pm_chain* c) { return c->dev_bytes; }
+int32_t pm_chain_acceptance(pm_chain* c, int64_t* proposed, int64_t* accepted, int32_t cap) {
+  const int32_t np = (int32_t)c->rate_proposed.size();
+  for (int32_t i = 0; i < np && i < cap; i++) { proposed[i] = c->rate_proposed[i]; accepted[i] = c->rate_accepted[i]; }
+  return np;
+}
 void pm_chain_destroy(pm_chain* c) { delete c; }
 
 void pm_rng_probe(uint32_t seed, int32_t kind, int32_t n, double a, double b, double* out) {

@@ -46,7 +46,14 @@ struct ChainParams {
   int root;
   const uint8_t* tipcode; long long TS;  // tip codes [T][TS]: rows padded to a multiple of 16 sites (4-byte aligned cp.async)
   uint8_t* node_state; uint32_t* meta; Real* PL;
-  uint32_t* slow_mask; int mask_words;  // production: per (chunk, word, site) bit mask of the branches left to k_paths_hard
+  // production: branches left to k_paths_hard, one bit per site: hard_ballot[e * W + w] covers sites 32 w .. 32 w + 31.
+  // k_paths_hard walks them as work items of wk_g[e] consecutive words of one branch; branch e owns the items
+  // [wk_off[e], wk_off[e + 1]) (sized on the host so that an item holds ~100 set bits whatever the branch length).
+  uint32_t* hard_ballot; int W;
+  const long long* wk_off; const int* wk_g; long long wk_total;
+  int* rec_cursor;  // [n_chunks][S] records appended so far to the slice of (chunk, site) in this sweep
+  int chunk;        // branches per record chunk
+  long long easy_blocks;  // blocks of k_paths_easy: k_paths_hard's dwell partials follow theirs in dw_partial
   Real* pos1;  // production [E][S]: length of the first piece when m == 2 or the path has exactly one real jump
   Real* rec_len[2]; uint8_t* rec_st[2];  // double-buffered path records: written by sweep i into [i & 1], read by sweep i + 1
   int normalize, full_counts, parity_tips;
@@ -1046,13 +1053,15 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
 //                 regeneration and no record is needed: the pieces are (pos1, t - pos1), the new states are the two
 //                 node states, the new virtual-jump counts take one uniform per run from a Philox block shared by two
 //                 branches.  Coalesced streaming over the chunk, straight-line code; everything else gets a bit in the
-//                 per-(site, chunk) mask.
-//   k_paths_hard  block = 128 sites x one chunk again; the set bits of the block's masks are compacted into a shared-memory
-//                 work queue and handed out 128 at a time, one (site, branch) item per thread (dense mask words branch by
-//                 branch, so that a warp's lanes walk the same branch): regenerates the virtual jumps of the previous
-//                 sweep run by run, redraws the interior states (resamplebranchstates :264-308), merges and counts
-//                 (shortener :44-73 / shortenerbf :997-1028), draws the new counts; a path too long for the local
-//                 buffer is walked a second time to write its records in place.
+//                 branch-major ballot array (one warp vote and one 4-byte store per warp and branch).
+//   k_paths_hard  persistent warps over branch-major work items (a run of ballot words of ONE branch, sized on the host to
+//                 ~100 set bits).  A warp turns the set bits into (site, branch) items, reads their meta word and sorts
+//                 them into two per-warp shared-memory queues; whenever a queue holds 32 items they are processed, one per
+//                 lane: [short] three pieces with at most one real jump (~3/4 of the items here) by straight-line code,
+//                 [general] everything else: regenerate the virtual jumps of the previous sweep run by run, redraw the
+//                 interior states (resamplebranchstates :264-308), merge and count (shortener :44-73 / shortenerbf
+//                 :997-1028), draw the new counts; a path too long for the local buffer is walked a second time to write
+//                 its records in place.  No block barrier; lanes of a round run the same code on items of like shape.
 // ------------------------------------------------------------------------------------------------
 #define PM_META(m, nj, s0, s1) ((uint32_t)(m) | ((uint32_t)(nj) << 16) | ((uint32_t)(s0) << 22) | ((uint32_t)(s1) << 27))
 
@@ -1089,7 +1098,10 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
   const bool active = site_raw < S;
   const long long site = active ? site_raw : S - 1;
   const bool full = P.full_counts != 0;
-  uint32_t* __restrict__ mask = P.slow_mask + (long long)blockIdx.y * P.mask_words * S + site;
+  const long long wglob = site_raw >> 5;  // ballot word of this warp (the same for its 32 lanes)
+  uint32_t* __restrict__ bal_p = P.hard_ballot + (long long)e0 * P.W + wglob;
+  const bool bal_writer = (threadIdx.x & 31) == 0 && wglob < (long long)P.W;
+  const uint32_t Wu = (uint32_t)P.W;
   uint32_t* __restrict__ meta_p = P.meta + (long long)e0 * S + site;   // walks one row (S entries) per branch
   Real* __restrict__ pos1_p = P.pos1 + (long long)e0 * S + site;
   const uint8_t* __restrict__ nstate = P.node_state + site;
@@ -1115,7 +1127,6 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
     a.cs = nstate[(uint64_t)(uint32_t)s_chi[i] * Su];
   };
   uint32_t po[4] = {0, 0, 0, 0};
-  uint32_t bits = 0;
   // one branch: `cur` holds what was fetched for it; with PIPE, `nxt` (branch i + 1) gets its pos1 and `cur` is refilled
   // with branch i + 2.  ODD: second branch of its Philox pair (the block was drawn by the first, or here if it opens the chunk).
   auto step = [&](int i, auto odd_c, auto pipe_c, Ahead& cur, Ahead& nxt) {
@@ -1151,11 +1162,10 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
       *meta_p = PM_META(newm, two ? 1 : 0, s0, cs);
     }
     meta_p += Su; pos1_p += Su;
-    const int b = i & 31;
-    bits |= (hard ? 1u : 0u) << b;
-    if (b == 31 || i == nb - 1) {
-      if (active) mask[(uint64_t)(uint32_t)(i >> 5) * Su] = bits;
-      bits = 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, hard && active);
+    if (bal_writer) *bal_p = bal;
+    bal_p += Wu;
+    if ((i & 31) == 31 || i == nb - 1) {
       if (NS > 0) {
 #pragma unroll
         for (int j = 0; j < NR; j++) { Rsum[j] += (double)Racc[j]; Racc[j] = 0; }
@@ -1237,8 +1247,11 @@ struct RunPieces {
   }
 };
 
+// One (site, branch) item of the general path kernel, as queued per warp.
+struct HardItem { uint32_t site, e, meta; };
+
 template <typename Real, int NS, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, uint32_t iter, int first, int chunk) {
+__global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, uint32_t iter, int first) {
   constexpr int NC = NS > 0 ? NS : PM_NMAX;
   constexpr int NR = NS > 0 ? NS : 1;
   typedef typename StreamSel<Real, false>::type Stream;
@@ -1256,29 +1269,24 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
   for (int i = threadIdx.x; i < 5 * n; i += blockDim.x) sVec[i] = P.model[2 * n * n + i];
   for (int i = threadIdx.x; i < npow_s * n * n; i += blockDim.x) sPow[i] = P.ppow[i];
   for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_dw[i] = 0.0;
+  // per-warp queues of classified items: [0] the common short shape (processed by straight-line code), [1] everything else
+  __shared__ HardItem s_q[4][2][64];
   __syncthreads();
   const Real* s_rate_old = sVec + 3 * n;
   const Real* s_rate_new = sVec + 4 * n;
-  // block-wide work queue: the set bits of the 128 masks of this block, compacted, so that every round hands each
-  // thread one (site, branch) item whatever the distribution of the bits over the sites
-  __shared__ uint32_t s_queue[128 * 32 + 128];  // item = branch-in-chunk << 8 | site-in-block
-  __shared__ int s_wr[128];                     // records appended so far to the slice of each site
-  __shared__ int s_scan[4];
-  __shared__ unsigned short s_bw[32][4];  // dense words: set bits of branch b in each warp
+  Real rate_max = 0;  // largest virtual-jump rate of the previous and of this sweep: bounds every run's lambda by rate_max * t_e
+  for (int s = 0; s < n; s++) {
+    const Real a = s_rate_old[s], b = s_rate_new[s];
+    if (rate_ok(a)) rate_max = max(rate_max, a);
+    if (rate_ok(b)) rate_max = max(rate_max, b);
+  }
   const long long S = P.S;
-  const long long site0 = (long long)blockIdx.x * blockDim.x;
-  const int nsites = (int)min((long long)blockDim.x, S - site0);
-  const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
-  const int nwords = (e1 - e0 + 31) >> 5;
-  const uint32_t* __restrict__ mask = P.slow_mask + (long long)blockIdx.y * P.mask_words * S + site0 + min((int)threadIdx.x, nsites - 1);
-  const int cap0 = __ldg(P.cap_off + blockIdx.y), cap_c = __ldg(P.cap_off + blockIdx.y + 1) - cap0;
-  const long long abase0 = (long long)cap0 * S + site0 * (long long)cap_c;  // + site-in-block * cap_c + offset
-  const Real* __restrict__ rd_len = P.rec_len[(iter & 1u) ^ 1u] + abase0;
-  const uint8_t* __restrict__ rd_st = P.rec_st[(iter & 1u) ^ 1u] + abase0;
-  Real* __restrict__ wr_len = P.rec_len[iter & 1u] + abase0;
-  uint8_t* __restrict__ wr_st = P.rec_st[iter & 1u] + abase0;
-  s_wr[threadIdx.x] = 0;
+  const int W = P.W;
   const bool full = P.full_counts != 0;
+  const Real* __restrict__ rd_len = P.rec_len[(iter & 1u) ^ 1u];
+  const uint8_t* __restrict__ rd_st = P.rec_st[(iter & 1u) ^ 1u];
+  Real* __restrict__ wr_len = P.rec_len[iter & 1u];
+  uint8_t* __restrict__ wr_st = P.rec_st[iter & 1u];
   double Rsum[NR];
 #pragma unroll
   for (int j = 0; j < NR; j++) Rsum[j] = 0;
@@ -1290,73 +1298,127 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     } else atomicAdd(&s_dw[s], (double)L);
   };
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t lastmask = ((e1 - e0) & 31) ? ((1u << ((e1 - e0) & 31)) - 1u) : 0xffffffffu;
-  int qn = 0;  // items waiting in s_queue[0 .. qn)  (block-uniform)
-  __syncthreads();
+  const unsigned FULL = 0xffffffffu;
 
-  for (int w = 0; w <= nwords; w++) {
-    if (w < nwords) {
-      // append this word's items: exclusive scan of the popcounts over the block
-      uint32_t bits = 0;
-      if ((int)threadIdx.x < nsites) {
-        bits = mask[(long long)w * S];  // (first sweep too: k_paths_easy has already dealt with the short maps)
-        if (w == nwords - 1) bits &= lastmask;
-      }
-      const int c = __popc(bits);
-      int inc = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-      if (lane == 31) s_scan[warp] = inc;
-      __syncthreads();
-      int base = qn;
-      for (int ww = 0; ww < warp; ww++) base += s_scan[ww];
-      const int total = s_scan[0] + s_scan[1] + s_scan[2] + s_scan[3];
-      if (nsites == 128 && total >= 1024) {  // a full block and a quarter of the word's (site, branch) pairs or more
-        // Dense word (long paths everywhere: Omega x t >> 1): queue the items branch by branch, so that the 32 lanes of a
-        // warp get the SAME branch at 32 sites -- similar jump counts, similar trip counts -- instead of 32 different
-        // branches of one site, whose lengths differ by orders of magnitude.
-#pragma unroll 4
-        for (int b = 0; b < 32; b++) {
-          const unsigned bal = __ballot_sync(0xffffffffu, (bits >> b) & 1u);
-          if (lane == 0) s_bw[b][warp] = (unsigned short)__popc(bal);
-        }
-        __syncthreads();
-        int run = qn;
-#pragma unroll 4
-        for (int b = 0; b < 32; b++) {
-          const unsigned bal = __ballot_sync(0xffffffffu, (bits >> b) & 1u);
-          const int c0 = s_bw[b][0], c1 = s_bw[b][1], c2 = s_bw[b][2], c3 = s_bw[b][3];
-          if ((bits >> b) & 1u) {
-            const int before = (warp > 0 ? c0 : 0) + (warp > 1 ? c1 : 0) + (warp > 2 ? c2 : 0);
-            s_queue[run + before + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)((w << 5) + b) << 8) | threadIdx.x;
-          }
-          run += c0 + c1 + c2 + c3;
-        }
-      } else {
-        int pos = base + inc - c;
-        while (bits) {
-          const int b = __ffs((int)bits) - 1;
-          bits &= bits - 1u;
-          s_queue[pos++] = ((uint32_t)((w << 5) + b) << 8) | threadIdx.x;
-        }
-      }
-      qn += total;
-      __syncthreads();
+  // ---- the common short shape: three pieces (two jump points), at most one of them a real jump, every run in count mode.
+  // Straight-line restatement of what the general code below does for such an item: same streams, same words, same
+  // pinned arithmetic, so a path may be written by one and regenerated by the other.
+  auto short_item = [&](const HardItem it) {
+    const long long site = it.site;
+    const int eb = (int)it.e;
+    const uint32_t mt = it.meta;
+    const long long pe = (long long)eb * S + site;
+    const int nj = (int)((mt >> 16) & 0x3fu);
+    const int so0 = (int)((mt >> 22) & 0x1fu), so1 = (int)((mt >> 27) & 0x1fu);
+    const int ps = P.node_state[(long long)__ldg(P.e_parent + eb) * S + site];
+    const int cs = P.node_state[(long long)__ldg(P.e_child + eb) * S + site];
+    const Real Le = __ldg(P.e_len + eb);
+    uint32_t po_old[4], po_new[4];
+    pair_block(P.rng, (uint32_t)site, iter, (uint32_t)eb, po_new);
+    pair_block(P.rng, (uint32_t)site, iter - 1u, (uint32_t)eb, po_old);
+    const uint32_t oA = (eb & 1) ? po_old[2] : po_old[0], oB = (eb & 1) ? po_old[3] : po_old[1];
+    const uint32_t nA = (eb & 1) ? po_new[2] : po_new[0], nB = (eb & 1) ? po_new[3] : po_new[1];
+    // the three pieces of the previous path
+    Real a, b, c;
+    int run_with_jump = 0;
+    Real p1 = 0;
+    int kold0, kold1 = 0;
+    if (nj == 0) {
+      kold0 = poisson_inv<Real>(PN::mul(s_rate_old[so0], Le), oA);
+      if (kold0 != 2) errbits |= PM_DE_INCONSISTENT;
+    } else {
+      p1 = P.pos1[pe];
+      kold0 = poisson_inv<Real>(PN::mul(s_rate_old[so0], p1), oA);
+      kold1 = poisson_inv<Real>(PN::mul(s_rate_old[so1], PN::sub(Le, p1)), oB);
+      if (kold0 + kold1 != 1) errbits |= PM_DE_INCONSISTENT;
+      run_with_jump = kold1 == 1 ? 1 : 0;
     }
-    // full rounds of 128 items (and, after the last word, the remainder)
-    while (qn >= (int)blockDim.x || (w == nwords && qn > 0)) {
-      const int take = min(qn, (int)blockDim.x);
-      const bool have = (int)threadIdx.x < take;
-      const uint32_t item = have ? s_queue[qn - take + threadIdx.x] : 0u;
-      qn -= take;
-      if (have) {
-    const int tsite = (int)(item & 0xffu);
-    const long long site = site0 + tsite;
-    const int eb = e0 + (int)(item >> 8);
-    const long long sbase = (long long)tsite * cap_c;  // this site's slice inside the block's arena window
+    uint32_t pw[4];  // first position block of the run that needs one (K_BRPOS stream of that run, block 0)
+    philox4x32_10((uint32_t)run_with_jump << 20, make_slot(K_BRPOS, (uint32_t)eb), iter - 1u, P.rng.site0 + (uint32_t)site, P.rng.k0, P.rng.k1, pw);
+    if (nj == 0) {
+      const Real t2 = next_order_stat<Real>((Real)0, Le, 2, oB);   // (a single-run path takes its first position word from the pair block)
+      a = PN::sub(t2, (Real)0);
+      const Real t3 = next_order_stat<Real>(t2, Le, 1, pw[0]);
+      b = PN::sub(t3, t2);
+      c = PN::sub(Le, t3);
+    } else if (run_with_jump == 0) {
+      const Real t2 = next_order_stat<Real>((Real)0, p1, 1, pw[0]);
+      a = PN::sub(t2, (Real)0);
+      b = PN::sub(p1, t2);
+      c = PN::sub(PN::sub(Le, p1), (Real)0);
+    } else {
+      const Real L1r = PN::sub(Le, p1);
+      a = PN::sub(p1, (Real)0);
+      const Real t2 = next_order_stat<Real>((Real)0, L1r, 1, pw[0]);
+      b = PN::sub(t2, (Real)0);
+      c = PN::sub(L1r, t2);
+    }
+    // the interior state: B[ps, .] x (Bs e_cs)
+    int st;
+    {
+      Real wv[NC];
+      const Real* M = (1 < npow_s) ? (sPow + n * n) : (P.ppow + (size_t)n * n);
+#pragma unroll
+      for (int q = 0; q < n; q++) wv[q] = sB[ps * n + q] * M[q * n + cs];
+      Stream gst; gst.open(P.rng, (uint32_t)site, iter, K_BRSTATE, (uint32_t)eb, P.err_flag);
+      st = categorical<Real, NC, false>(wv, n, gst.next(), P.err_flag);
+    }
+    // merge, count, emit
+    if (full) { atomicAdd(&s_cnt[ps * n + st], 1u); atomicAdd(&s_cnt[st * n + cs], 1u); }
+    else {
+      if (st != ps) atomicAdd(&s_cnt[ps * n + st], 1u);
+      if (cs != st) atomicAdd(&s_cnt[st * n + cs], 1u);
+    }
+    int nout; Real L0, L1 = 0, L2 = 0; int S0, S1 = 0, S2 = 0;
+    if (st == ps) {
+      const Real ab = a + b;
+      if (cs == st) { nout = 1; L0 = Le; S0 = ps; }
+      else { nout = 2; L0 = ab; S0 = ps; L1 = PN::sub(Le, L0); S1 = cs; }
+    } else if (cs == st) { nout = 2; L0 = a; S0 = ps; L1 = PN::sub(Le, L0); S1 = cs; }
+    else { nout = 3; L0 = a; S0 = ps; L1 = b; S1 = st; L2 = c; S2 = cs; }
+    auto count_new = [&](int s, Real L, uint32_t cw) -> int {
+      const Real rate = s_rate_new[s];
+      return rate_ok(rate) ? poisson_inv<Real>(PN::mul(rate, L), cw) : 0;
+    };
+    add_dwell(S0, L0);
+    const int k0 = count_new(S0, L0, nA);
+    int newm = k0 + 1;
+    if (nout >= 2) { add_dwell(S1, L1); newm += count_new(S1, L1, nB) + 1; }
+    if (nout == 3) {
+      add_dwell(S2, L2);
+      uint32_t cwv[4];
+      philox4x32_10(0u, make_slot(K_BRCNT, (uint32_t)eb), iter, P.rng.site0 + (uint32_t)site, P.rng.k0, P.rng.k1, cwv);
+      newm += count_new(S2, L2, cwv[0]) + 1;
+    }
+    if (nout == 1) { if (k0 == 1) P.pos1[pe] = next_order_stat<Real>((Real)0, Le, 1, nB); }
+    else if (nout == 2) P.pos1[pe] = L0;
+    else {
+      const int ck = eb / P.chunk;
+      const int cap0 = __ldg(P.cap_off + ck), cap_c = __ldg(P.cap_off + ck + 1) - cap0;
+      const long long sl = (long long)cap0 * S + site * (long long)cap_c;
+      const int base = atomicAdd(P.rec_cursor + (long long)ck * S + site, 3);
+      P.pos1[pe] = (Real)base;
+      if (base + 3 > cap_c) errbits |= PM_DE_PATH_CAP;
+      else {
+        wr_len[sl + base] = L0; wr_st[sl + base] = (uint8_t)S0;
+        wr_len[sl + base + 1] = L1; wr_st[sl + base + 1] = (uint8_t)S1;
+        wr_len[sl + base + 2] = L2; wr_st[sl + base + 2] = (uint8_t)S2;
+      }
+    }
+    P.meta[pe] = PM_META(newm, nout - 1, S0, S1);
+  };
+
+  // ---- any item: regenerate the pieces run by run, redraw the interior states, merge, count, emit ----
+  auto general_item = [&](const HardItem it) {
+    const long long site = it.site;
+    const int eb = (int)it.e;
+    const uint32_t mt = it.meta;
+    const int ck = eb / P.chunk;
+    const int cap0 = __ldg(P.cap_off + ck), cap_c = __ldg(P.cap_off + ck + 1) - cap0;
+    const long long sbase = (long long)cap0 * S + site * (long long)cap_c;  // this site's record slice of the chunk
+    int* cursor = P.rec_cursor + (long long)ck * S + site;
 
     const long long pe = (long long)eb * S + site;
-    const uint32_t mt = P.meta[pe];
     const int m = (int)(mt & 0xffffu);
     const int njf = first ? 0 : (int)((mt >> 16) & 0x3fu);  // real jumps; 63 = "63 or more, see the record header"
     const int ps = P.node_state[(long long)__ldg(P.e_parent + eb) * S + site];
@@ -1508,7 +1570,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       // keeps the length of its first run.  64 runs or more: a header record with the count comes first.
       const bool longp = nout >= 64;
       const int need = nout + (longp ? 1 : 0);
-      const int base = atomicAdd(&s_wr[tsite], need);
+      const int base = atomicAdd(cursor, need);
       P.pos1[pe] = (Real)base;
       if (base + need > cap_c) { errbits |= PM_DE_PATH_CAP; break; }
       if (longp) { wr_len[sbase + base] = (Real)nout; wr_st[sbase + base] = 0; }
@@ -1523,9 +1585,70 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       break;
     }
     P.meta[pe] = PM_META(newm, min(nout - 1, 63), S0, S1);
-      }  // have
-    }    // rounds
-  }      // words
+  };
+
+  // ---- the warp walks its work items; items are classified, queued and processed 32 at a time ----
+  int nq0 = 0, nq1 = 0;  // queue fill (warp-uniform)
+  auto drain = [&](bool all) {
+    while (nq0 >= 32 || (all && nq0 > 0)) {
+      const int take = min(nq0, 32);
+      nq0 -= take;
+      if (lane < take) short_item(s_q[warp][0][nq0 + lane]);
+      __syncwarp();
+    }
+    while (nq1 >= 32 || (all && nq1 > 0)) {
+      const int take = min(nq1, 32);
+      nq1 -= take;
+      if (lane < take) general_item(s_q[warp][1][nq1 + lane]);
+      __syncwarp();
+    }
+  };
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp, NW = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long wi = gw; wi < P.wk_total; wi += NW) {
+    int lo = 0, hi = P.E;  // branch e with wk_off[e] <= wi < wk_off[e + 1]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(P.wk_off + mid) <= wi) lo = mid; else hi = mid; }
+    const int e = lo;
+    const int g = __ldg(P.wk_g + e);
+    const long long w0 = (wi - __ldg(P.wk_off + e)) * g;
+    const int nw = (int)min((long long)g, (long long)W - w0);
+    uint32_t bits = lane < nw ? P.hard_ballot[(long long)e * W + w0 + lane] : 0u;
+    const int c = __popc(bits);
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
+    const int total = __shfl_sync(FULL, inc, 31);
+    if (total == 0) continue;
+    const Real lam_max = PN::mul(rate_max, __ldg(P.e_len + e));
+    const bool short_ok = !first && lam_max <= (Real)PM_LAMBDA_INV;
+    for (int base = 0; base < total; base += 32) {
+      const int k = base + lane;
+      const bool have = k < total;
+      int j = 0;  // first lane whose inclusive count exceeds k
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_sync(FULL, inc, j + o - 1); if (v <= k) j += o; }
+      const int excl = __shfl_sync(FULL, inc - c, j);
+      const uint32_t wbits = __shfl_sync(FULL, bits, j);
+      HardItem it;
+      it.e = (uint32_t)e;
+      it.site = have ? (uint32_t)((w0 + j) * 32 + __fns(wbits, 0, k - excl + 1)) : 0u;
+      it.meta = have ? P.meta[(long long)e * S + it.site] : 0u;
+      bool is_short = false;
+      if (have && short_ok) {
+        const int m = (int)(it.meta & 0xffffu), njq = (int)((it.meta >> 16) & 0x3fu);
+        is_short = m == 3 && njq <= 1 && rate_ok(s_rate_old[(it.meta >> 22) & 0x1fu]) && (njq == 0 || rate_ok(s_rate_old[(it.meta >> 27) & 0x1fu]));
+      }
+      const unsigned b0 = __ballot_sync(FULL, have && is_short), b1 = __ballot_sync(FULL, have && !is_short);
+      const unsigned lt = (1u << lane) - 1u;
+      if (have) {
+        if (is_short) s_q[warp][0][nq0 + __popc(b0 & lt)] = it;
+        else s_q[warp][1][nq1 + __popc(b1 & lt)] = it;
+      }
+      nq0 += __popc(b0); nq1 += __popc(b1);
+      __syncwarp();
+      drain(false);
+    }
+  }
+  drain(true);
   if (errbits) atomicOr(P.err_flag, errbits);
 
   if (NS > 0) {
@@ -1538,12 +1661,11 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     }
   }
   __syncthreads();
-  const long long blk = (long long)gridDim.y * gridDim.x + (long long)blockIdx.y * gridDim.x + blockIdx.x;
   if ((int)threadIdx.x < n) {
     double v;
     if (NS > 0) { v = 0; for (int ww = 0; ww < (int)(blockDim.x >> 5); ww++) v += s_dw[ww * n + threadIdx.x]; }
     else v = s_dw[threadIdx.x];
-    P.dw_partial[blk * n + threadIdx.x] = v;
+    P.dw_partial[((long long)P.easy_blocks + blockIdx.x) * n + threadIdx.x] = v;
   }
   for (int i = threadIdx.x; i < n * n; i += blockDim.x) if (s_cnt[i]) atomicAdd(&P.cnt[i], (unsigned long long)s_cnt[i]);
 }

@@ -10,7 +10,7 @@ struct Sweep {
   static void prune(const ChainParams<Real>& P, int grid, size_t smem, cudaStream_t st, int variant);
   static void nodes(const ChainParams<Real>& P, int grid, size_t smem, cudaStream_t st, uint32_t iter);
   static void paths(const ChainParams<Real>& P, dim3 grid, size_t smem, cudaStream_t st, uint32_t iter, int first, int chunk,
-                    int variant);
+                    int hard_blocks);
 };
 
 }  // namespace pm

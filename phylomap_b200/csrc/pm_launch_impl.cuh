@@ -38,7 +38,7 @@ void Sweep<Real, NS, EXACT>::nodes(const ChainParams<Real>& P, int grid, size_t 
 }
 template <typename Real, int NS, bool EXACT>
 void Sweep<Real, NS, EXACT>::paths(const ChainParams<Real>& P, dim3 grid, size_t smem, cudaStream_t st, uint32_t iter,
-                                   int first, int chunk, int variant) {
+                                   int first, int chunk, int hard_blocks) {
   if constexpr (EXACT) k_paths<Real, NS, true><<<grid, 128, smem, st>>>(P, iter, first, chunk);
   else {
     // the easy kernel also serves the first sweep: a map of one or two pieces is a path like any other (pos1 was
@@ -46,8 +46,7 @@ void Sweep<Real, NS, EXACT>::paths(const ChainParams<Real>& P, dim3 grid, size_t
     const size_t smem_easy = (size_t)4 * P.n * sizeof(double) + (size_t)(P.n * P.n + ((P.n * P.n) & 1)) * sizeof(unsigned) +
                              (size_t)(P.n + (P.n & 1)) * sizeof(Real) + (size_t)chunk * (2 * sizeof(int) + sizeof(Real));
     k_paths_easy<Real, NS><<<grid, 128, smem_easy, st>>>(P, iter, chunk);
-    if (variant == 3) k_paths_hard<Real, NS, 3><<<grid, 128, smem, st>>>(P, iter, first, chunk);
-    else k_paths_hard<Real, NS, 4><<<grid, 128, smem, st>>>(P, iter, first, chunk);
+    k_paths_hard<Real, NS, 4><<<hard_blocks, 128, smem, st>>>(P, iter, first);
   }
 }
 

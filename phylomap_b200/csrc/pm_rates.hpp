@@ -24,6 +24,11 @@ struct RateModel {
   double* B;  // column-major n x n, caller's
   double Omega;
   const double* prior;
+  // tallies per rate parameter, in the order of the trace columns (l01, l10, kappa-> x k, kappa<- x k, gamma x k):
+  // proposals drawn and proposals installed (null: not kept)
+  long long* proposed = nullptr;
+  long long* accepted = nullptr;
+  void tally(int param, bool ok) { if (proposed) { proposed[param]++; if (ok) accepted[param]++; } }
 
   double& q(int r, int c) { return Q[r + (size_t)c * n]; }
   double& b(int r, int c) { return B[r + (size_t)c * n]; }
@@ -40,11 +45,12 @@ struct RateModel {
       const double dwell = st[dir];
       const double cur = dir == 0 ? q(0, 1) : q(1, 0);
       const double prop = r_rgamma(g, prior[2 * dir] + jumps, 1 / (prior[2 * dir + 1] + dwell));
-      if (prop > Omega) continue;  // no uniform is consumed on this exit (:1205)
+      if (prop > Omega) { tally(dir, false); continue; }  // no uniform is consumed on this exit (:1205)
       double ratio = std::pow((Omega - prop) / (Omega - cur), stays) * std::exp(dwell * (prop - cur));
       if (ratio > 1) ratio = 1;
       const double u = g.next();
-      if (metropolis_step && ratio < u) continue;
+      if (metropolis_step && ratio < u) { tally(dir, false); continue; }
+      tally(dir, true);
       if (dir == 0) {
         q(0, 0) = -prop; q(0, 1) = prop;
         b(0, 0) = 1 - prop / Omega; b(0, 1) = prop / Omega;
@@ -105,11 +111,13 @@ struct RateModel {
     la = la + Nc[state(k) * n + state(k)] *
                   std::log((Om - h.lk[k - 1] - h.ga[k] * prop) / (Om - h.lk[k - 1] - h.ga[k] * cur));
     const double u = g.next();
-    if (prop + h.rk[0] > Om) return;
-    for (int i = 1; i < k; i++) if (h.ga[i] * prop + h.rk[i] + h.lk[i - 1] > Om) return;
-    if (h.ga[k] * prop + h.lk[k - 1] > Om) return;
-    if (!multi_tree && prop < 1e-300) return;
-    if (la < std::log(u)) return;
+    bool ok = !(prop + h.rk[0] > Om);
+    for (int i = 1; i < k && ok; i++) if (h.ga[i] * prop + h.rk[i] + h.lk[i - 1] > Om) ok = false;
+    if (ok && h.ga[k] * prop + h.lk[k - 1] > Om) ok = false;
+    if (ok && !multi_tree && prop < 1e-300) ok = false;
+    if (ok && la < std::log(u)) ok = false;
+    tally(d, ok);
+    if (!ok) return;
     for (int i = 0; i <= k; i++) {
       double diag;
       if (i == 0) diag = -h.rk[0] - h.ga[0] * prop;
@@ -149,12 +157,15 @@ struct RateModel {
       la = la + Nc[s * n + s] * std::log(num / den);
     }
     const double u = g.next();
+    bool ok = true;
     for (int side = 0; side < 2; side++) {
       const double tr = h.ga[j] * h.lam[side];
-      if (has_opp ? (prop + tr + opp > Om) : (prop + tr > Om)) return;
+      if (has_opp ? (prop + tr + opp > Om) : (prop + tr > Om)) ok = false;
     }
-    if (!multi_tree && prop < 1e-300) return;
-    if (la < std::log(u)) return;
+    if (ok && !multi_tree && prop < 1e-300) ok = false;
+    if (ok && la < std::log(u)) ok = false;
+    tally(up ? 2 + j : 2 + k + (j - 1), ok);
+    if (!ok) return;
     q(e, e + step) = prop;
     q(o, o + step) = prop;
     for (int side = 0; side < 2; side++) {
@@ -185,12 +196,15 @@ struct RateModel {
       la = la + Nc[s * n + s] * std::log(num / den);
     }
     const double u = g.next();
+    bool ok = true;
     for (int side = 0; side < 2; side++) {
       const double l = h.lam[side];
-      if (last ? (h.lk[j - 1] + prop * l > Om) : (h.lk[j - 1] + prop * l + h.rk[j] > Om)) return;
+      if (last ? (h.lk[j - 1] + prop * l > Om) : (h.lk[j - 1] + prop * l + h.rk[j] > Om)) ok = false;
     }
-    if (!multi_tree && prop < 1e-300) return;
-    if (la < std::log(u)) return;
+    if (ok && !multi_tree && prop < 1e-300) ok = false;
+    if (ok && la < std::log(u)) ok = false;
+    tally(2 + 2 * k + (j - 1), ok);
+    if (!ok) return;
     q(e, o) = prop * h.lam[0];
     q(o, e) = prop * h.lam[1];
     for (int side = 0; side < 2; side++) {
