@@ -73,9 +73,13 @@ typedef struct pm_tree {
   const double* edge_length; /* x$edge.length [E]: read by the DIC samplers only (src/phylomap.cpp:3225); NULL = sum of maps */
 } pm_tree;
 
-/* Called once per iteration by the rate-updating samplers (bf/ks/mt/ksmt) when the sites are sharded over
- * several processes: must sum `count` doubles at DEVICE address `dev_buf` across all ranks, in stream order on
- * the stream given in pm_options.cuda_stream (e.g. ncclAllReduce / torch.distributed.all_reduce).  Return 0. */
+/* Site sharding over several processes (one per GPU).  Either give the library an NCCL clique (nccl_id / nccl_rank /
+ * nccl_world below: it then calls ncclAllReduce itself on the chain's stream), or a callback of this type, which must sum
+ * `count` doubles at DEVICE address `dev_buf` across all ranks in stream order on pm_options.cuda_stream (which is then
+ * mandatory: the library cannot order a foreign collective on its private stream) and return 0.  The reduced row carries
+ * one extra double, the sum of the ranks' device error flags, so every rank sees a failure in the same iteration and all
+ * of them leave together instead of hanging in the next collective.  Called once per iteration by the rate-updating
+ * samplers (bf/ks/mt/ksmt), once per pm_chain_run by the fixed-Q ones. */
 typedef int (*pm_allreduce_fn)(void* ctx, double* dev_buf, int32_t count);
 
 typedef struct pm_options {
@@ -97,10 +101,17 @@ typedef struct pm_options {
   void* allreduce_ctx;
   void* cuda_stream;       /* cudaStream_t to launch on; NULL = a private stream */
   int32_t progress;        /* non-zero: print "%i \r" per iteration like the reference (:930) */
+  int32_t nccl_world;      /* > 1: number of ranks of the NCCL clique the library joins at pm_chain_create (collective call) */
+  int32_t nccl_rank;       /* this process's rank in it */
   int32_t reserved;
+  const void* nccl_id;     /* the clique's 128-byte ncclUniqueId: pm_nccl_unique_id() on one rank, handed to the others by the
+                              caller (MPI, a file, torch.distributed.broadcast ...) */
 } pm_options;
 
 void pm_default_options(pm_options* o);
+/* Writes a fresh ncclUniqueId (128 bytes) for pm_options.nccl_id.  NCCL is loaded at run time (libnccl.so.2; override
+ * with PHYLOMAP_B200_NCCL=/path); PM_ERR_CUDA if it cannot be. */
+int pm_nccl_unique_id(void* out128, char* err, size_t errlen);
 
 /* Fixed-Q samplers.  out: caller-owned, column-major [N x (n + n(n-1))]:
  * [R_0..R_{n-1}, N_{0->1}, N_{0->2}, ... (diagonal skipped) ..., N_{n-1->n-2}]  (man/sumstatMCMC.Rd:18). */

@@ -70,7 +70,12 @@ SEXP tree_list(const ref_tree& t) {
   x.push_named("Nnode", wrap((int)(t.T - 1)));
   IntegerMatrix ns(t.E, 2);  // read at entry, overwritten by updatenodestates before any use (phylomap.cpp:460-475)
   x.push_named("node.states", ns);
-  x.push_named("states", int_vec(t.states, t.T));
+  if (t.S == 1) x.push_named("states", int_vec(t.states, t.T));
+  else {  // site axis (shim only): ntips x nsites matrix, one column per character = the [site][tip] block as it is
+    IntegerMatrix sm(t.T, (int)t.S);
+    for (long i = 0; i < (long)t.T * t.S; i++) sm[i] = t.states[i];
+    x.push_named("states", sm);
+  }
   if (t.edge_length) x.push_named("edge.length", real_vec(t.edge_length, t.E));
   return x;
 }
@@ -92,8 +97,10 @@ extern "C" int ref_run(const ref_tree* trees, const ref_config* cfg, double* Q, 
                        double* out /* N x ncols, column-major */, char* err, int errlen) {
   try {
     const int n = cfg->n, N = cfg->N, v = cfg->variant;
+#ifndef PM_SHIM_DRIVER
     for (int t = 0; t < cfg->ntrees; t++)
       if (trees[t].S != 1) throw std::runtime_error("the reference handles one character per call (S must be 1)");
+#endif
     if (cfg->rng_mode != 0) throw std::runtime_error("the reference consumes R's sequential stream only (rng_mode must be SEQUENTIAL)");
     standin::set_seed((unsigned)cfg->seed);
     standin::last_error().clear();
@@ -147,6 +154,23 @@ extern "C" int ref_run(const ref_tree* trees, const ref_config* cfg, double* Q, 
     return 1;
   }
 }
+
+#ifdef PM_SHIM_DRIVER
+// the two additions of the shim that are not `.Call` symbols of the reference
+Rcpp::List phylomap_tree_order(Rcpp::IntegerMatrix& edge, int ntips);
+extern "C" int shim_tree_order(const int32_t* edge, int E, int ntips, int32_t* nen, int32_t* nodelist, int32_t* root, char* err, int errlen) {
+  try {
+    IntegerMatrix em(E, 2);
+    for (long i = 0; i < 2L * E; i++) em[i] = edge[i];
+    List r = phylomap_tree_order(em, ntips);
+    IntegerVector a = r["nen"], b = r["nodelist"];
+    for (long i = 0; i < a.size(); i++) nen[i] = a[i];
+    for (long i = 0; i < b.size(); i++) nodelist[i] = b[i];
+    *root = as<int>(r["root"]);
+    return 0;
+  } catch (std::exception& e) { snprintf(err, errlen, "%s", e.what()); return 1; }
+}
+#endif
 
 // R-level probes of the stand-in generator (the same stream the reference consumes), for the RNG tests.
 extern "C" void ref_rng_probe(unsigned seed, int kind, int n, double a, double b, double* out) {

@@ -77,6 +77,11 @@ inline double Rf_dgamma(double x, double shape, double scale, int give_log) {
   return give_log ? l : std::exp(l);
 }
 
+inline bool Rf_isMatrix(const SEXP& s) { return s && s->nrow >= 0; }
+inline int Rf_nrows(const SEXP& s) { return s->nrow; }
+inline int Rf_ncols(const SEXP& s) { return s->ncol; }
+inline int Rf_length(const SEXP& s) { return s ? (int)s->length() : 0; }
+
 namespace Rcpp {
 
 template <int RTYPE> struct storage;
@@ -224,6 +229,10 @@ class List {
     return ListProxy(s, -1, name);
   }
   ListProxy operator[](const char* name) const { return (*this)[std::string(name)]; }
+  bool containsElementNamed(const char* name) const {
+    for (size_t i = 0; i < s->names.size(); i++) if (s->names[i] == name) return true;
+    return false;
+  }
   void push_named(const std::string& n, const SEXP& v) { s->list.push_back(v); s->names.resize(s->list.size()); s->names.back() = n; }
   static List create(const Named& a) { List l; l.push_named(a.name, a.value); return l; }
   static List create(const Named& a, const Named& b) { List l; l.push_named(a.name, a.value); l.push_named(b.name, b.value); return l; }
@@ -231,6 +240,13 @@ class List {
 };
 inline SEXP wrap(const List& l) { return l.s; }
 template <> struct as_impl<List> { static List get(const SEXP& s) { return List(s); } };
+
+// Rcpp::stop(): a C++ exception that END_RCPP turns into an R error
+class exception : public std::runtime_error {
+ public:
+  explicit exception(const std::string& m) : std::runtime_error(m) {}
+};
+inline void stop(const std::string& m) { throw exception(m); }
 
 // ---- random numbers ------------------------------------------------------------------------------------------
 struct RNGScope { RNGScope() {} ~RNGScope() {} };  // GetRNGstate / PutRNGstate: the stand-in generator is always live

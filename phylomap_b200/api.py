@@ -32,7 +32,7 @@ MT_COLNAMES = ["time_0", "time_1", "n00", "n01", "n10", "n11", "l01", "l10", "tr
 
 
 def _options(precision=None, mode=None, seed=None, device=None, rng=None, table=None, host_table=None,
-             site_offset=0, path_capacity=0, power_capacity=0, allreduce=None, stream=None, progress=False):
+             site_offset=0, path_capacity=0, power_capacity=0, allreduce=None, stream=None, progress=False, nccl=None):
     o = capi.default_options()
     env = os.environ
     precision = precision if precision is not None else env.get("PHYLOMAP_B200_PRECISION", "f64")
@@ -60,6 +60,12 @@ def _options(precision=None, mode=None, seed=None, device=None, rng=None, table=
         o.allreduce = cb
     if stream is not None:
         o.cuda_stream = int(stream)
+    if nccl is not None:   # (unique id bytes, rank, world): the library joins the clique and all-reduces itself
+        uid, rank, world = nccl
+        buf = np.frombuffer(bytes(uid), dtype=np.uint8).copy()
+        assert buf.size == 128
+        keep.append(buf)
+        o.nccl_id, o.nccl_rank, o.nccl_world = capi.ptr(buf), int(rank), int(world)
     return o, keep
 
 

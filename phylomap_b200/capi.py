@@ -34,10 +34,10 @@ class PmOptions(C.Structure):
                 ("power_capacity", C.c_int32), ("tab_off", C.c_void_p), ("tab_u", C.c_void_p),
                 ("host_tab", C.c_void_p), ("host_tab_n", C.c_int64), ("allreduce", ALLREDUCE_FN),
                 ("allreduce_ctx", C.c_void_p), ("cuda_stream", C.c_void_p), ("progress", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("nccl_world", C.c_int32), ("nccl_rank", C.c_int32), ("reserved", C.c_int32), ("nccl_id", C.c_void_p)]
 
 
-EXPORTS = ["pm_default_options", "pm_maketreelistMCMC", "pm_SPARSEmaketreelistMCMC", "pm_maketreelistMCMC_bigtree",
+EXPORTS = ["pm_default_options", "pm_nccl_unique_id", "pm_maketreelistMCMC", "pm_SPARSEmaketreelistMCMC", "pm_maketreelistMCMC_bigtree",
            "pm_maketreelistMCMCbf", "pm_maketreelistMCMCks", "pm_maketreelistMCMCmt", "pm_maketreelistMCMCksmt",
            "pm_maketreelistMCMC2sDICt", "pm_maketreelistMCMCksDICt", "pm_maketreelistEXP", "pm_loglik",
            "pm_ncols", "pm_tree_order", "pm_debug_clade_schedule", "pm_chain_create", "pm_chain_run", "pm_chain_state_bytes",

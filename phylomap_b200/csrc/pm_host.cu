@@ -27,6 +27,7 @@
 #include "pm_setup_kernels.cuh"
 #include "pm_loglik.cuh"
 #include "pm_exp.cuh"
+#include "pm_nccl.hpp"
 #include "pm_rates.hpp"
 #include "pm_tree.hpp"
 
@@ -243,7 +244,7 @@ struct TreeDev {
   int n_cd_top_levels = 0, n_cd_tips = 0;  // clade schedule of the production pruning kernel
   int n_cl_top_levels = 0;
   DevBuf up_entries8, up_entries, up_off, down_entries, down_off, e_parent, e_child, e_len, maps_off, maps_len, cap_off;
-  DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, hard_ballot, wk_off, wk_g, rec_cursor, pos1;
+  DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, hard_ballot, wk_off, wk_g, wk_hint, rec_cursor, pos1;
   long long wk_total = 0, dw_rows = 0;
   int hard_blocks = 0;
   DevBuf e_len_d, TP, ll_partial;  // DIC samplers: branch lengths in FP64, exp(Q t_e) per branch, block partials of log p(y|Q)
@@ -257,7 +258,8 @@ struct TreeDev {
 template <typename Real>
 struct ChainT : pm_chain {
   Variant V;
-  int n = 0, ntrees = 0, N_total = 0, iters_done = 0, W = 0, ncols = 0;
+  int n = 0, ntrees = 0, N_total = 0, iters_done = 0, W = 0, WR = 0, ncols = 0;  // W statistics per row; WR = W + 1: row stride (error slot last)
+  pm::host::NcclApi::Comm nccl = nullptr;
   int NS = 0;  // compile-time state count used for dispatch (2, 4 or 0)
   bool exact = false;
   double* Q = nullptr;  // caller's
@@ -288,7 +290,9 @@ struct ChainT : pm_chain {
   std::vector<Timed> timed;
 
   ~ChainT() override {
+    cudaSetDevice(opt.device);
     cudaDeviceSynchronize();
+    if (nccl) pm::host::NcclApi::get().CommDestroy(nccl);
     for (auto& t : timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (model_h) cudaFreeHost(model_h);
     if (rows_h) cudaFreeHost(rows_h);
@@ -363,7 +367,7 @@ struct ChainT : pm_chain {
     end_timed();
     begin_timed(3);
     pm::k_reduce<<<1, 256, 0, stream>>>(t.dw_partial.template as<double>(), t.dw_rows, n, cnt.as<unsigned long long>(),
-                                        root_out.as<int>(), row, 0);
+                                        root_out.as<int>(), row, 0, err_flag.as<unsigned>(), W);
     end_timed();
     launches += exact ? 4 : 5;
   }
@@ -470,9 +474,14 @@ struct ChainT : pm_chain {
     if (exact && V.exp) fail(PM_ERR_ARG, "the direct sampler (maketreelistEXP) runs in production arithmetic only");
     if (opt.rng == PM_RNG_TABLE && (!opt.tab_off || !opt.tab_u)) fail(PM_ERR_ARG, "replay table missing");
     if (opt.rng == PM_RNG_TABLE && !exact) fail(PM_ERR_ARG, "the replay table feeds the deterministic mode only");
-    if (opt.rng == PM_RNG_TABLE && (opt.site_offset != 0 || opt.allreduce)) fail(PM_ERR_ARG, "replay runs are single-process");
+    if (opt.rng == PM_RNG_TABLE && (opt.site_offset != 0 || opt.allreduce || opt.nccl_world > 1)) fail(PM_ERR_ARG, "replay runs are single-process");
+    if (opt.allreduce && !opt.cuda_stream)
+      fail(PM_ERR_ARG, "an allreduce callback needs pm_options.cuda_stream: the collective must be ordered on the stream the chain launches on");
+    if (opt.allreduce && opt.nccl_world > 1) fail(PM_ERR_ARG, "give either an allreduce callback or an NCCL clique, not both");
+    if (opt.nccl_world > 1 && (!opt.nccl_id || opt.nccl_rank < 0 || opt.nccl_rank >= opt.nccl_world)) fail(PM_ERR_ARG, "bad NCCL clique (nccl_id / nccl_rank / nccl_world)");
     NS = (n == 2) ? 2 : (n == 4) ? 4 : 0;
     W = n + n * n + 1 + (V.dic ? 1 : 0);
+    WR = W + 1;
     ncols = ncols_of(variant, n);
 
     // host-only validation of the trees first: malformed input is reported as PM_ERR_ARG even where no device exists
@@ -677,7 +686,7 @@ struct ChainT : pm_chain {
       CK(cudaMemsetAsync(t->node_state.p, 0, t->node_state.bytes, stream));
       // partial dwell sums per block: [0, nblocks) easy / deterministic / direct-sampler kernel, then the general path kernel's
       t->hard_blocks = (!exact && !V.exp && !V.llonly) ? prop.multiProcessorCount * 4 : 0;  // persistent: 4 blocks of 4 warps per SM
-      t->dw_rows = t->nblocks + t->hard_blocks;
+      t->dw_rows = t->nblocks + 3 * t->hard_blocks;  // general kernel: hard_blocks rows; short kernel: 2 hard_blocks (after them)
       t->dw_partial.alloc((size_t)t->dw_rows * n * sizeof(double));
       CK(cudaMemsetAsync(t->dw_partial.p, 0, t->dw_partial.bytes, stream));
       if (!exact && !V.exp && !V.llonly) {
@@ -697,6 +706,12 @@ struct ChainT : pm_chain {
           woff[e + 1] = woff[e] + (Wl + g - 1) / g;
         }
         t->wk_total = woff[E];
+        std::vector<int> hint((size_t)(t->wk_total >> 6) + 1);
+        for (long long i = 0, e = 0; i < (long long)hint.size(); i++) {
+          while (e + 1 < E && woff[e + 1] <= (i << 6)) e++;
+          hint[i] = (int)e;
+        }
+        upload(t->wk_hint, hint, stream);
         upload(t->wk_off, woff, stream);
         upload(t->wk_g, wg, stream);
         t->rec_cursor.alloc((size_t)ny * S * sizeof(int));
@@ -719,7 +734,15 @@ struct ChainT : pm_chain {
     model.alloc(model_elems() * sizeof(Real));
     ppow.alloc((size_t)jcap * n * n * sizeof(Real));
     CK(cudaMallocHost((void**)&model_h, (model_elems() + (size_t)jcap * n * n) * sizeof(Real)));
-    CK(cudaMallocHost((void**)&rows_h, (size_t)ntrees * W * sizeof(double)));
+    CK(cudaMallocHost((void**)&rows_h, (size_t)ntrees * WR * sizeof(double)));
+    if (opt.nccl_world > 1) {
+      auto& api = pm::host::NcclApi::get();
+      if (!api.ok()) fail(PM_ERR_CUDA, "NCCL could not be loaded: %s", api.why.c_str());
+      pm::host::NcclApi::UniqueId id;
+      memcpy(&id, opt.nccl_id, sizeof id);
+      const int rc = api.CommInitRank(&nccl, opt.nccl_world, id, opt.nccl_rank);
+      if (rc != 0) fail(PM_ERR_CUDA, "ncclCommInitRank failed: %s", api.error(rc).c_str());
+    }
     CK(cudaMallocHost((void**)&err_h, sizeof(unsigned)));
     if (V.dic) { CK(cudaMallocHost((void**)&q_h, (size_t)n * n * sizeof(double))); q_dev.alloc((size_t)n * n * sizeof(double)); }
     cnt.alloc((size_t)n * n * sizeof(unsigned long long));
@@ -760,6 +783,8 @@ struct ChainT : pm_chain {
       P.cap_off = t.cap_off.template as<int>();
       P.hard_ballot = t.hard_ballot.template as<uint32_t>(); P.W = (int)((t.S + 31) / 32);
       P.wk_off = t.wk_off.template as<long long>(); P.wk_g = t.wk_g.template as<int>(); P.wk_total = t.wk_total;
+      P.wk_hint = t.wk_hint.template as<int>();
+      P.tune = getenv("PHYLOMAP_B200_TUNE") ? atoi(getenv("PHYLOMAP_B200_TUNE")) : 0;
       P.rec_cursor = t.rec_cursor.template as<int>(); P.chunk = t.chunk; P.easy_blocks = t.nblocks;
       P.pos1 = t.pos1.template as<Real>();
       P.model = model.as<Real>(); P.ppow = ppow.as<Real>(); P.jcap = jcap;
@@ -835,10 +860,29 @@ struct ChainT : pm_chain {
     check_device_errors();
   }
 
+  // sum `count` doubles at device address `buf` over the ranks, in stream order (no-op for a single process)
+  void reduce_over_ranks(double* buf, int count) {
+    if (nccl) {
+      auto& api = pm::host::NcclApi::get();
+      const int rc = api.AllReduce(buf, buf, (size_t)count, pm::host::NcclApi::kDouble, pm::host::NcclApi::kSum, nccl, stream);
+      if (rc != 0) fail(PM_ERR_CUDA, "ncclAllReduce failed: %s", api.error(rc).c_str());
+    } else if (opt.allreduce) {
+      if (opt.allreduce(opt.allreduce_ctx, buf, count) != 0) fail(PM_ERR_CUDA, "allreduce callback failed");
+    }
+  }
+  // the error slot of a reduced row: non-zero when any rank raised a device flag in that sweep
+  void check_row_errors(const double* rows_host, int nrows) {
+    bool any = false;
+    for (int i = 0; i < nrows; i++) any = any || rows_host[(size_t)i * WR + W] != 0.0;
+    if (!any) return;
+    check_device_errors();  // throws with this rank's own reason if it has one
+    fail(PM_ERR_CUDA, "another rank reported a device error in this sweep; all ranks stop together");
+  }
+
   void ensure_rows(int count) {
     const int need = std::max(count, 1) * ntrees;
     if (need <= rows_cap) return;
-    rows.alloc((size_t)need * W * sizeof(double));
+    rows.alloc((size_t)need * WR * sizeof(double));
     rows_cap = need;
   }
 
@@ -876,7 +920,7 @@ struct ChainT : pm_chain {
     end_timed();
     begin_timed(3);
     pm::k_reduce<<<1, 256, 0, stream>>>(t.dw_partial.template as<double>(), t.dw_rows, n, cnt.as<unsigned long long>(),
-                                        root_out.as<int>(), row, 0);
+                                        root_out.as<int>(), row, 0, err_flag.as<unsigned>(), W);
     end_timed();
     launches += 4;
   }
@@ -890,19 +934,18 @@ struct ChainT : pm_chain {
       ensure_rows(count);
       TreeDev<Real>& t = *trees[0];
       for (int i = 0; i < count; i++) {
-        if (V.exp) launch_exp_iteration(t, (uint32_t)(iters_done + i), rows.as<double>() + (size_t)i * W);
-        else launch_sweep(t, (uint32_t)(iters_done + i), rows.as<double>() + (size_t)i * W);
+        if (V.exp) launch_exp_iteration(t, (uint32_t)(iters_done + i), rows.as<double>() + (size_t)i * WR);
+        else launch_sweep(t, (uint32_t)(iters_done + i), rows.as<double>() + (size_t)i * WR);
         if (opt.progress) { printf("%i \r", iters_done + i); }
       }
       CK(cudaGetLastError());
-      if (opt.allreduce) {
-        if (opt.allreduce(opt.allreduce_ctx, rows.as<double>(), count * W) != 0) fail(PM_ERR_CUDA, "allreduce callback failed");
-      }
-      std::vector<double> h((size_t)count * W);
+      reduce_over_ranks(rows.as<double>(), count * WR);
+      std::vector<double> h((size_t)count * WR);
       CK(cudaMemcpyAsync(h.data(), rows.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
-      check_device_errors();
+      CK(cudaStreamSynchronize(stream));
+      check_row_errors(h.data(), count);
       collect_timed();
-      for (int i = 0; i < count; i++) write_fixed_row(&h[(size_t)i * W], out, ld, i);
+      for (int i = 0; i < count; i++) write_fixed_row(&h[(size_t)i * WR], out, ld, i);
       iters_done += count;
       return;
     }
@@ -919,17 +962,18 @@ struct ChainT : pm_chain {
     for (int i = 0; i < count; i++) {
       const int it = iters_done;
       if (V.multi && it == 0) (void)g.next();  // the draw before the loop, :2332 / :2810
-      for (int j = 0; j < ntrees; j++) launch_sweep(*trees[j], (uint32_t)it, rows.as<double>() + (size_t)j * W);
+      for (int j = 0; j < ntrees; j++) launch_sweep(*trees[j], (uint32_t)it, rows.as<double>() + (size_t)j * WR);
       if (V.dic) launch_loglik(*trees[0], rows.as<double>());
       CK(cudaGetLastError());
-      if (opt.allreduce) {
-        if (opt.allreduce(opt.allreduce_ctx, rows.as<double>(), ntrees * W) != 0) fail(PM_ERR_CUDA, "allreduce callback failed");
-      }
-      CK(cudaMemcpyAsync(rows_h, rows.p, (size_t)ntrees * W * sizeof(double), cudaMemcpyDeviceToHost, stream));
-      check_device_errors();
+      // one small all-reduce per sweep (n + n^2 + 1 (+1) statistics + the error slot, per tree), then ONE synchronisation:
+      // the device error flag travels in the row instead of a second copy
+      reduce_over_ranks(rows.as<double>(), ntrees * WR);
+      CK(cudaMemcpyAsync(rows_h, rows.p, (size_t)ntrees * WR * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      check_row_errors(rows_h, ntrees);
       for (int j = 0; j < ntrees; j++) {
         std::fill(jodt[j].begin(), jodt[j].end(), 0.0);
-        const double* r = rows_h + (size_t)j * W;
+        const double* r = rows_h + (size_t)j * WR;
         for (int c = 0; c < n + n * n; c++) jodt[j][c] = r[c];
         if (V.hidden) rm.record_hidden(jodt[j].data()); else rm.record_two_state(jodt[j].data());
         if (V.dic) { jodt[j][ncols - 2] = r[n + n * n]; jodt[j][ncols - 1] = r[n + n * n + 1]; }
@@ -1135,7 +1179,7 @@ struct ChainT : pm_chain {
     launch_loglik(*trees[0], row);
     CK(cudaGetLastError());
     double* cell = row + n + n * n + 1;
-    if (opt.allreduce && opt.allreduce(opt.allreduce_ctx, cell, 1) != 0) fail(PM_ERR_CUDA, "allreduce callback failed");
+    reduce_over_ranks(cell, 1);
     CK(cudaMemcpyAsync(rows_h, cell, sizeof(double), cudaMemcpyDeviceToHost, stream));
     check_device_errors();
     return rows_h[0];
@@ -1430,6 +1474,17 @@ int pm_chain_get_partials(pm_chain* c, int32_t tree, int64_t site, double* out) 
   return guarded(nullptr, 0, [&] { c->partials(tree, site, out); });
 }
 int64_t pm_chain_device_bytes(pm_chain* c) { return c->dev_bytes; }
+int pm_nccl_unique_id(void* out128, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!out128) fail(PM_ERR_ARG, "null argument");
+    auto& api = pm::host::NcclApi::get();
+    if (!api.ok()) fail(PM_ERR_CUDA, "NCCL could not be loaded: %s", api.why.c_str());
+    pm::host::NcclApi::UniqueId id;
+    const int rc = api.GetUniqueId(&id);
+    if (rc != 0) fail(PM_ERR_CUDA, "ncclGetUniqueId failed: %s", api.error(rc).c_str());
+    memcpy(out128, &id, sizeof id);
+  });
+}
 int32_t pm_chain_acceptance(pm_chain* c, int64_t* proposed, int64_t* accepted, int32_t cap) {
   const int32_t np = (int32_t)c->rate_proposed.size();
   for (int32_t i = 0; i < np && i < cap; i++) { proposed[i] = c->rate_proposed[i]; accepted[i] = c->rate_accepted[i]; }

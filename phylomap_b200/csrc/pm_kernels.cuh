@@ -51,6 +51,8 @@ struct ChainParams {
   // [wk_off[e], wk_off[e + 1]) (sized on the host so that an item holds ~100 set bits whatever the branch length).
   uint32_t* hard_ballot; int W;
   const long long* wk_off; const int* wk_g; long long wk_total;
+  const int* wk_hint;  // [wk_total / 64 + 1] branch that owns work item 64 i
+  int tune;            // PHYLOMAP_B200_TUNE (experiments)
   int* rec_cursor;  // [n_chunks][S] records appended so far to the slice of (chunk, site) in this sweep
   int chunk;        // branches per record chunk
   long long easy_blocks;  // blocks of k_paths_easy: k_paths_hard's dwell partials follow theirs in dw_partial
@@ -1247,10 +1249,15 @@ struct RunPieces {
   }
 };
 
-// One (site, branch) item of the general path kernel, as queued per warp.
-struct HardItem { uint32_t site, e, meta; };
+// One (site, branch) item of the general path kernel, as queued per warp: everything the item reads from the sweep's
+// state is fetched when it is queued (four independent loads per lane in flight), so that processing it later waits
+// for no memory.
+template <typename Real>
+struct HardItem { uint32_t site, e, meta, ends; Real p1; };  // ends = parent state | child state << 8
 
-template <typename Real, int NS, int MINB>
+// WHICH = 0: the short items only (small code, half the registers: twice the resident warps), launched first: it clears
+// the ballot bits of the items it takes.  WHICH = 1: whatever is left.
+template <typename Real, int NS, int MINB, int WHICH>
 __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, uint32_t iter, int first) {
   constexpr int NC = NS > 0 ? NS : PM_NMAX;
   constexpr int NR = NS > 0 ? NS : 1;
@@ -1270,7 +1277,8 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
   for (int i = threadIdx.x; i < npow_s * n * n; i += blockDim.x) sPow[i] = P.ppow[i];
   for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_dw[i] = 0.0;
   // per-warp queues of classified items: [0] the common short shape (processed by straight-line code), [1] everything else
-  __shared__ HardItem s_q[4][2][64];
+  __shared__ HardItem<Real> s_q[4][64];
+  __shared__ unsigned short s_stage[4][1024];  // site offsets of the set bits of the warp's current work item (<= 32 words)
   __syncthreads();
   const Real* s_rate_old = sVec + 3 * n;
   const Real* s_rate_new = sVec + 4 * n;
@@ -1303,15 +1311,14 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
   // ---- the common short shape: three pieces (two jump points), at most one of them a real jump, every run in count mode.
   // Straight-line restatement of what the general code below does for such an item: same streams, same words, same
   // pinned arithmetic, so a path may be written by one and regenerated by the other.
-  auto short_item = [&](const HardItem it) {
+  auto short_item = [&](const HardItem<Real> it) {
     const long long site = it.site;
     const int eb = (int)it.e;
     const uint32_t mt = it.meta;
     const long long pe = (long long)eb * S + site;
     const int nj = (int)((mt >> 16) & 0x3fu);
     const int so0 = (int)((mt >> 22) & 0x1fu), so1 = (int)((mt >> 27) & 0x1fu);
-    const int ps = P.node_state[(long long)__ldg(P.e_parent + eb) * S + site];
-    const int cs = P.node_state[(long long)__ldg(P.e_child + eb) * S + site];
+    const int ps = (int)(it.ends & 0xffu), cs = (int)(it.ends >> 8);
     const Real Le = __ldg(P.e_len + eb);
     uint32_t po_old[4], po_new[4];
     pair_block(P.rng, (uint32_t)site, iter, (uint32_t)eb, po_new);
@@ -1327,7 +1334,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       kold0 = poisson_inv<Real>(PN::mul(s_rate_old[so0], Le), oA);
       if (kold0 != 2) errbits |= PM_DE_INCONSISTENT;
     } else {
-      p1 = P.pos1[pe];
+      p1 = it.p1;
       kold0 = poisson_inv<Real>(PN::mul(s_rate_old[so0], p1), oA);
       kold1 = poisson_inv<Real>(PN::mul(s_rate_old[so1], PN::sub(Le, p1)), oB);
       if (kold0 + kold1 != 1) errbits |= PM_DE_INCONSISTENT;
@@ -1409,7 +1416,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
   };
 
   // ---- any item: regenerate the pieces run by run, redraw the interior states, merge, count, emit ----
-  auto general_item = [&](const HardItem it) {
+  auto general_item = [&](const HardItem<Real> it) {
     const long long site = it.site;
     const int eb = (int)it.e;
     const uint32_t mt = it.meta;
@@ -1421,8 +1428,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     const long long pe = (long long)eb * S + site;
     const int m = (int)(mt & 0xffffu);
     const int njf = first ? 0 : (int)((mt >> 16) & 0x3fu);  // real jumps; 63 = "63 or more, see the record header"
-    const int ps = P.node_state[(long long)__ldg(P.e_parent + eb) * S + site];
-    const int cs = P.node_state[(long long)__ldg(P.e_child + eb) * S + site];
+    const int ps = (int)(it.ends & 0xffu), cs = (int)(it.ends >> 8);
     const Real Le = __ldg(P.e_len + eb);
     uint32_t po_old[4], po_new[4];
     pair_block(P.rng, (uint32_t)site, iter, (uint32_t)eb, po_new);
@@ -1431,7 +1437,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     const uint32_t nA = (eb & 1) ? po_new[2] : po_new[0], nB = (eb & 1) ? po_new[3] : po_new[1];
     // nj == 1: pos1 = length of run 0; nj >= 2: pos1 = offset of the path's records in the site's slice.  A path with 64
     // or more runs starts with a header record holding its run count.
-    const Real p1 = (!first && (njf >= 1)) ? P.pos1[pe] : (Real)0;
+    const Real p1 = (!first && (njf >= 1)) ? it.p1 : (Real)0;
     int rd0 = (njf >= 2) ? (int)p1 : 0;
     int nj = njf;
     if (njf == 63) {
@@ -1588,67 +1594,83 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
   };
 
   // ---- the warp walks its work items; items are classified, queued and processed 32 at a time ----
-  int nq0 = 0, nq1 = 0;  // queue fill (warp-uniform)
-  auto drain = [&](bool all) {
-    while (nq0 >= 32 || (all && nq0 > 0)) {
-      const int take = min(nq0, 32);
-      nq0 -= take;
-      if (lane < take) short_item(s_q[warp][0][nq0 + lane]);
-      __syncwarp();
-    }
-    while (nq1 >= 32 || (all && nq1 > 0)) {
-      const int take = min(nq1, 32);
-      nq1 -= take;
-      if (lane < take) general_item(s_q[warp][1][nq1 + lane]);
-      __syncwarp();
-    }
-  };
+  // One loop, one place where items are processed (the kernel stalls mostly on instruction fetch: branchy code, few
+  // resident warps -- every extra inlined copy of an item routine costs).
+  int nq = 0;  // queue fill (warp-uniform)
   const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp, NW = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long wi = gw; wi < P.wk_total; wi += NW) {
-    int lo = 0, hi = P.E;  // branch e with wk_off[e] <= wi < wk_off[e + 1]
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(P.wk_off + mid) <= wi) lo = mid; else hi = mid; }
-    const int e = lo;
-    const int g = __ldg(P.wk_g + e);
-    const long long w0 = (wi - __ldg(P.wk_off + e)) * g;
-    const int nw = (int)min((long long)g, (long long)W - w0);
-    uint32_t bits = lane < nw ? P.hard_ballot[(long long)e * W + w0 + lane] : 0u;
-    const int c = __popc(bits);
-    int inc = c;
+  long long wi = gw;
+  int e = 0, base = 0, total = 0, c = 0, inc = 0;
+  long long w0 = 0, prow = 0, crow = 0, erow = 0;
+  uint32_t bits = 0;
+  bool short_ok = false, finishing = false;
+  for (;;) {
+    const bool room = nq < 32;  // a round queues up to 32 items, the queue holds 64
+    if (room && base >= total && !finishing) {  // next work item
+      if (wi >= P.wk_total) finishing = true;
+      else {
+        e = __ldg(P.wk_hint + (wi >> 6));  // branch of work item (wi & ~63); the branch of wi is at most a few further
+        while (__ldg(P.wk_off + e + 1) <= wi) e++;
+        const int g = __ldg(P.wk_g + e);
+        w0 = (wi - __ldg(P.wk_off + e)) * g;
+        const int nw = (int)min((long long)g, (long long)W - w0);
+        wi += NW;
+        bits = lane < nw ? P.hard_ballot[(long long)e * W + w0 + lane] : 0u;
+        c = __popc(bits);
+        inc = c;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
-    const int total = __shfl_sync(FULL, inc, 31);
-    if (total == 0) continue;
-    const Real lam_max = PN::mul(rate_max, __ldg(P.e_len + e));
-    const bool short_ok = !first && lam_max <= (Real)PM_LAMBDA_INV;
-    for (int base = 0; base < total; base += 32) {
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
+        total = __shfl_sync(FULL, inc, 31);
+        base = 0;
+        if (total == 0) continue;
+        // every lane lists the set bits of its own word: site offsets inside the work item, in site order
+        __syncwarp();
+        {
+          int pos = inc - c;
+          uint32_t b2 = bits;
+          while (b2) { s_stage[warp][pos++] = (unsigned short)(lane * 32 + __ffs((int)b2) - 1); b2 &= b2 - 1u; }
+        }
+        __syncwarp();
+        short_ok = !first && !(P.tune & 1) && PN::mul(rate_max, __ldg(P.e_len + e)) <= (Real)PM_LAMBDA_INV;
+        prow = (long long)__ldg(P.e_parent + e) * S; crow = (long long)__ldg(P.e_child + e) * S; erow = (long long)e * S;
+      }
+    }
+    if (room && !finishing) {  // queue the next 32 items of the work item
       const int k = base + lane;
       const bool have = k < total;
-      int j = 0;  // first lane whose inclusive count exceeds k
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_sync(FULL, inc, j + o - 1); if (v <= k) j += o; }
-      const int excl = __shfl_sync(FULL, inc - c, j);
-      const uint32_t wbits = __shfl_sync(FULL, bits, j);
-      HardItem it;
+      HardItem<Real> it;
       it.e = (uint32_t)e;
-      it.site = have ? (uint32_t)((w0 + j) * 32 + __fns(wbits, 0, k - excl + 1)) : 0u;
-      it.meta = have ? P.meta[(long long)e * S + it.site] : 0u;
+      it.site = have ? (uint32_t)(w0 * 32 + s_stage[warp][k]) : 0u;
+      it.meta = 0u; it.ends = 0u; it.p1 = (Real)0;
+      if (have) {  // four independent loads
+        it.meta = P.meta[erow + it.site];
+        const uint32_t a = P.node_state[prow + it.site], b = P.node_state[crow + it.site];
+        if (!first) it.p1 = P.pos1[erow + it.site];
+        it.ends = a | (b << 8);
+      }
       bool is_short = false;
-      if (have && short_ok) {
+      if (WHICH == 0 && have && short_ok) {
         const int m = (int)(it.meta & 0xffffu), njq = (int)((it.meta >> 16) & 0x3fu);
         is_short = m == 3 && njq <= 1 && rate_ok(s_rate_old[(it.meta >> 22) & 0x1fu]) && (njq == 0 || rate_ok(s_rate_old[(it.meta >> 27) & 0x1fu]));
       }
-      const unsigned b0 = __ballot_sync(FULL, have && is_short), b1 = __ballot_sync(FULL, have && !is_short);
-      const unsigned lt = (1u << lane) - 1u;
-      if (have) {
-        if (is_short) s_q[warp][0][nq0 + __popc(b0 & lt)] = it;
-        else s_q[warp][1][nq1 + __popc(b1 & lt)] = it;
-      }
-      nq0 += __popc(b0); nq1 += __popc(b1);
+      // the short launch (first) takes its items out of the ballot array; the general launch takes whatever is left
+      const bool mine = have && (WHICH == 1 || is_short);
+      if (WHICH == 0 && mine) atomicAnd(P.hard_ballot + (long long)e * W + (it.site >> 5), ~(1u << (it.site & 31u)));
+      const unsigned bq = __ballot_sync(FULL, mine);
+      if (mine) s_q[warp][nq + __popc(bq & ((1u << lane) - 1u))] = it;
+      nq += __popc(bq);
+      base += 32;
       __syncwarp();
-      drain(false);
     }
+    if (nq >= 32 || (finishing && nq > 0)) {
+      const int take = min(nq, 32);
+      nq -= take;
+      if (lane < take) {
+        if (WHICH == 0) short_item(s_q[warp][nq + lane]);
+        else general_item(s_q[warp][nq + lane]);
+      }
+      __syncwarp();
+    } else if (finishing) break;
   }
-  drain(true);
   if (errbits) atomicOr(P.err_flag, errbits);
 
   if (NS > 0) {
@@ -1665,7 +1687,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     double v;
     if (NS > 0) { v = 0; for (int ww = 0; ww < (int)(blockDim.x >> 5); ww++) v += s_dw[ww * n + threadIdx.x]; }
     else v = s_dw[threadIdx.x];
-    P.dw_partial[((long long)P.easy_blocks + blockIdx.x) * n + threadIdx.x] = v;
+    P.dw_partial[((long long)P.easy_blocks + (WHICH ? 2LL * gridDim.x : 0LL) + blockIdx.x) * n + threadIdx.x] = v;
   }
   for (int i = threadIdx.x; i < n * n; i += blockDim.x) if (s_cnt[i]) atomicAdd(&P.cnt[i], (unsigned long long)s_cnt[i]);
 }

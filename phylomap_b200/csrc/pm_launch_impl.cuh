@@ -46,7 +46,9 @@ void Sweep<Real, NS, EXACT>::paths(const ChainParams<Real>& P, dim3 grid, size_t
     const size_t smem_easy = (size_t)4 * P.n * sizeof(double) + (size_t)(P.n * P.n + ((P.n * P.n) & 1)) * sizeof(unsigned) +
                              (size_t)(P.n + (P.n & 1)) * sizeof(Real) + (size_t)chunk * (2 * sizeof(int) + sizeof(Real));
     k_paths_easy<Real, NS><<<grid, 128, smem_easy, st>>>(P, iter, chunk);
-    k_paths_hard<Real, NS, 4><<<hard_blocks, 128, smem, st>>>(P, iter, first);
+    // (the short shape does not occur in the first sweep: the caller's maps are walked by the general routine)
+    if (!first) k_paths_hard<Real, NS, 8, 0><<<2 * hard_blocks, 128, smem, st>>>(P, iter, first);
+    k_paths_hard<Real, NS, 4, 1><<<hard_blocks, 128, smem, st>>>(P, iter, first);
   }
 }
 

@@ -7,8 +7,10 @@ namespace pm {
 // ------------------------------------------------------------------------------------------------
 // K4: one row of sufficient statistics [R(n) | N(n*n) | root].  One block, fixed summation order.
 // ------------------------------------------------------------------------------------------------
+// row[err_slot] receives this rank's device error flag (summed over ranks by the all-reduce that follows).
 __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ dw_partial, long long nblocks, int n,
-                                                unsigned long long* cnt, const int* root, double* row, int accumulate) {
+                                                unsigned long long* cnt, const int* root, double* row, int accumulate,
+                                                const unsigned* err_flag, int err_slot) {
   __shared__ double sh[256];
   for (int j = 0; j < n; j++) {
     double acc = 0;
@@ -21,6 +23,7 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ dw_pa
   }
   for (int i = threadIdx.x; i < n * n; i += 256) { row[n + i] = (accumulate ? row[n + i] : 0.0) + (double)cnt[i]; cnt[i] = 0ull; }
   if (threadIdx.x == 0 && !accumulate) row[n + n * n] = (double)(*root);
+  if (threadIdx.x == 0 && err_flag) row[err_slot] = (double)(*err_flag);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -9,6 +9,9 @@ everywhere without a broadcast.
 import numpy as np
 
 
+_STREAMS = []
+
+
 def shard(n_sites, rank, world):
     """Contiguous block [start, start + count) of the global site axis owned by `rank`."""
     base, extra = divmod(int(n_sites), int(world))
@@ -55,11 +58,44 @@ def allreduce_callback(stream_ptr=None, group=None):
     return cb
 
 
-def sharded_options(rank, world, start, stream_ptr=None):
-    """Keyword options for api.* that make a call one shard of a `world`-process run."""
+def nccl_clique(rank, world, group=None):
+    """(unique id, rank, world) for the `nccl=` option: rank 0 asks the library for an ncclUniqueId and torch.distributed
+    (any backend) hands it to the other ranks; from then on the library calls ncclAllReduce itself."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from . import capi
+    buf = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        raw = C.create_string_buffer(128)
+        err = C.create_string_buffer(512)
+        capi.check(capi.lib().pm_nccl_unique_id(raw, err, 512), err)
+        buf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+    if dist.get_backend(group) == "nccl":
+        dev = buf.cuda()
+        dist.broadcast(dev, src=0, group=group)
+        buf = dev.cpu()
+    else:
+        dist.broadcast(buf, src=0, group=group)
+    return bytes(buf.numpy().tobytes()), rank, world
+
+
+def sharded_options(rank, world, start, stream_ptr=None, native=True, group=None):
+    """Keyword options for api.* that make a call one shard of a `world`-process run.  native: the library's own NCCL
+    all-reduce (default); otherwise the torch.distributed callback, which needs the stream the chain launches on."""
     opts = {"site_offset": start, "device": rank}
     if world > 1:
-        opts["allreduce"] = allreduce_callback(stream_ptr)
+        if native:
+            opts["nccl"] = nccl_clique(rank, world, group)
+        else:
+            if not stream_ptr:
+                import torch
+                st = torch.cuda.Stream(device=rank)
+                _STREAMS.append(st)  # the chain launches on it: keep it alive
+                stream_ptr = st.cuda_stream
+            opts["allreduce"] = allreduce_callback(stream_ptr, group)
     if stream_ptr:
         opts["stream"] = stream_ptr
     return opts
