@@ -120,6 +120,50 @@ def _pack_trees(trees, keep):
     return arr
 
 
+_SHIM = None
+
+
+def shim_path():
+    return os.path.join(_HERE, "_ref", "libphylomap_shim.so")
+
+
+def shim_lib():
+    """oracle/_ref/libphylomap_shim.so: the reference's unmodified RcppExports.cpp + shim/phylomap_b200_shim.cpp (the
+    drop-in replacement of src/phylomap.cpp on the product's C ABI) + the same driver, against the stand-in headers
+    (oracle/Makefile, target `shim`).  The `.Call` symbols of the package, served by libphylomap_b200.so.  This is the one
+    place where test infrastructure loads the PRODUCT through the reference's boundary; nothing of the oracle restatement
+    is involved.  Returns None when it is not built."""
+    global _SHIM
+    if _SHIM is None:
+        if os.path.exists("/root/reference/src/RcppExports.cpp"):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "shim"])
+        so = shim_path()
+        if not os.path.exists(so):
+            return None
+        L = C.CDLL(so)
+        L.ref_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        L.ref_ncols.argtypes = [C.c_int, C.c_int]
+        L.ref_rng_probe.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
+        L.shim_tree_order.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        _SHIM = L
+    return _SHIM
+
+
+def shim_run(variant, trees, Q, pid, Omega, N, prior=None, seed=1, B=None, eig=None):
+    """The same call as ref_run, answered by the product through the shim (any number of sites: states become an
+    ntips x nsites matrix).  Precision / mode / device come from the PHYLOMAP_B200_* environment like in an R session."""
+    L = shim_lib()
+    if L is None:
+        raise OracleError("oracle/_ref/libphylomap_shim.so is not built")
+    return _lib_run(L, variant, trees, Q, pid, Omega, N, prior, seed, B, eig)
+
+
+def shim_seed(seed):
+    """The 64-bit seed the shim derives from R's stream after set.seed(seed): two unif_rand() draws (shim/phylomap_b200_shim.cpp)."""
+    u = ref_rng_probe(seed, "unif", 2, lib_=shim_lib())
+    return (int(u[0] * 4294967296.0) << 32) | int(u[1] * 4294967296.0)
+
+
 def ref_run(variant, trees, Q, pid, Omega, N, prior=None, seed=1, B=None, eig=None):
     """One call of the reference's own `.Call` entry point for `variant` (phylomap_maketreelistMCMC ... ksDICt) with R's
     generator seeded like set.seed(seed).  One site per tree (the reference has no site axis).  Returns (rows, Q, B):
@@ -127,6 +171,10 @@ def ref_run(variant, trees, Q, pid, Omega, N, prior=None, seed=1, B=None, eig=No
     L = ref_lib()
     if L is None:
         raise OracleError("oracle/_ref is not built (no /root/reference here and no prebuilt library)")
+    return _lib_run(L, variant, trees, Q, pid, Omega, N, prior, seed, B, eig)
+
+
+def _lib_run(L, variant, trees, Q, pid, Omega, N, prior, seed, B, eig):
     keep = []
     n = Q.shape[0]
     Qf = np.asfortranarray(np.array(Q, dtype=np.float64))
@@ -150,9 +198,9 @@ def ref_run(variant, trees, Q, pid, Omega, N, prior=None, seed=1, B=None, eig=No
     return out, Qf, Bf
 
 
-def ref_rng_probe(seed, kind, n, a=0.0, b=0.0):
+def ref_rng_probe(seed, kind, n, a=0.0, b=0.0, lib_=None):
     out = np.zeros(n)
-    ref_lib().ref_rng_probe(seed, {"unif": 0, "exp": 1, "norm": 2, "gamma": 3, "rexp": 4}[kind], n, a, b, _p(out))
+    (lib_ or ref_lib()).ref_rng_probe(seed, {"unif": 0, "exp": 1, "norm": 2, "gamma": 3, "rexp": 4}[kind], n, a, b, _p(out))
     return out
 
 

@@ -64,7 +64,7 @@ def test_config1_thousand_tips_ten_thousand_sites(oracle):
 
 def test_config2_squamate_hundred_thousand_sites():
     """The Squamate tree itself (3 951 tips, tree length 87 740; fixture derived from the package's .RData), the
-    vignette's Q (Squamate_DIC_model_selection.Rnw:83), Omega = 0.012, SPARSE sampler, 100 000 synthetic sites.
+    vignette's Q (Squamate_DIC_model_selection.Rnw:83), SPARSE sampler, 100 000 synthetic sites.
     FP64 production arithmetic: with rates this slow on a tree this large a few sites in 1e5 have sister clades that each
     settle their state beyond 1e-45, the range of an FP32 partial, and FP32 reports "Not enough positive probabilities"
     (PM_ERR_SAMPLE) for them instead of drawing from a zero vector; FP64 has the reference's range."""
@@ -72,9 +72,12 @@ def test_config2_squamate_hundred_thousand_sites():
     tree = cases.squamate_tree()
     S = 100000
     z = synth.simulate_2_state_tree(5, tree, Q, cases.PID2, n_sites=S, device="cuda", segments=8)
-    # the initial maps of simulate_2_state_tree (every internal branch in state 1) are far from equilibrium and this chain
-    # forgets them slowly (the dwell-time gap halves every ~40 sweeps): 400 sweeps of burn-in
-    mc = pb.SPARSEsumstatMCMC(z, Q, cases.PID2, 0.012, 520, precision="f64", seed=3)[400:]
+    # The initial maps of simulate_2_state_tree (every internal branch in state 1) are far from equilibrium, and a branch
+    # without a jump point pins its two end states together, so the chain forgets them at a speed set by Omega x t: with
+    # Omega = 0.012 (0.13 jump points per branch) the gap to the direct sampler still shrinks by a third per 120 sweeps
+    # after 400 sweeps.  Omega = 0.06 (0.66 per branch, ~5 300 jump points per site and sweep) mixes five times faster.
+    Om = 0.06
+    mc = pb.SPARSEsumstatMCMC(z, Q, cases.PID2, Om, 300, precision="f64", seed=3)[230:]
     np.testing.assert_allclose(mc[:, :2].sum(1), S * tree.edge_length.sum(), rtol=2e-4)
     assert np.all(mc[:, 2:] >= 0) and np.array_equal(mc[:, 2:], np.round(mc[:, 2:]))
     ex = pb.sumstatEXP(z, Q, cases.PID2, 8, seed=9, precision="f64")
