@@ -12,8 +12,13 @@ reduction) over all local sites = E x S_local branch-site histories.  Production
 `e2e`     : the same sweeps through the drop-in entry pm_maketreelistMCMC_bigtree with HOST buffers: tip states
             uploaded from pinned host memory, chain built, K sweeps, result matrix copied back — all inside the timer.
 `roofline`: pruning pass K1 (k_prune) timed alone with CUDA events; algorithmic bytes per site from SURVEY.md §8(d).
-`cpu_baseline` / `--impl reference`: the CPU oracle (line-for-line restatement of src/phylomap.cpp; the R package
-            itself cannot be built without R) on a bounded site sample, one process per host core.
+`rate_sampler`: sumstatMCMCks (hidden-rate model, Q updated every sweep) on the same tree and sites: ms per sweep, and
+            per sweep the device time of the one small NCCL all-reduce and the host time of the replicated rate update --
+            the part of the design that has a collective in it (the fixed-Q headline all-reduces once per run).
+`cpu_baseline` / `--impl reference`: the reference's own code -- oracle/_ref = the unmodified src/phylomap.cpp compiled
+            against stand-in Rcpp / Armadillo headers (R is absent) -- on a bounded site sample, one process per host
+            core; beside it the in-repo port in "faithful" mode (keeps the reference's O(E) edge search per node, :643) and in
+            "optimised" mode (parent-edge table): the honest CPU context for the GPU number.
 """
 import argparse
 import json
@@ -106,37 +111,88 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def _oracle_worker(args):
-    """One process: the oracle on a slice of sites.  Returns (histories, seconds)."""
-    tree_d, Q, pid, N, seed = args
+# CPU legs.  Nothing here touches the product library: the tree order is computed in numpy so that the reference arm's
+# process maps no libphylomap_b200.so (the driver checks which native libraries a process loaded).
+def tree_order_numpy(edge, T):
+    """A valid (nen, nodelist, root) for the reference's samplers (R/sumstatMCMC.R:1-18): nen lists the two child edges of
+    every internal node, children before parents; nodelist lists the internal nodes below the root, parents first."""
+    E = edge.shape[0]
+    kids = {}
+    for r in range(E):
+        kids.setdefault(int(edge[r, 0]), []).append(r)
+    root = (set(kids) - set(int(c) for c in edge[:, 1])).pop()
+    nen, nodelist, stack = [], [], [(root, 0)]
+    while stack:
+        v, k = stack.pop()
+        rows = kids[v]
+        if k == 0 and v != root:
+            nodelist.append(v)
+        if k < len(rows):
+            stack.append((v, k + 1))
+            c = int(edge[rows[k], 1])
+            if c > T:
+                stack.append((c, 0))
+        else:
+            nen += [r + 1 for r in rows]
+    return np.array(nen, dtype=np.int32), np.array(nodelist, dtype=np.int32), root
+
+
+def _cpu_worker(args):
+    """One process: `kind` on a slice of sites.  Returns (histories, seconds)."""
+    kind, tree_d, Q, pid, N, seed = args
     from oracle import bridge
-    run = bridge.OracleRun(bridge.BIGTREE, [tree_d], Q, pid, OMEGA, N, rng_mode=bridge.KEYED, seed=seed)
+    E, S = tree_d["edge"].shape[0], tree_d["states"].shape[0]
     t0 = time.perf_counter()
-    run.run()
-    dt = time.perf_counter() - t0
-    return tree_d["edge"].shape[0] * tree_d["states"].shape[0] * N, dt
+    if kind == "reference":   # the reference handles one character per call: one call per site
+        for s in range(S):
+            d = dict(tree_d)
+            d["states"] = tree_d["states"][s:s + 1]
+            bridge.ref_run(bridge.BIGTREE, [d], Q, pid, OMEGA, N, seed=seed + s)
+    else:
+        run = bridge.OracleRun(bridge.BIGTREE, [tree_d], Q, pid, OMEGA, N, rng_mode=bridge.SEQUENTIAL, seed=seed)
+        run.set_fast_lookup(kind == "port_optimised")
+        run.run()
+    return E * S * N, time.perf_counter() - t0
 
 
-def cpu_reference(tree, Q, pid, steps, sites_per_core=None, cores=None):
-    """The reference algorithm (oracle) on all host cores: sites are independent for fixed Q, so each core gets its
-    own slice — the most favourable way to run the single-threaded reference on this host."""
+CPU_SITES = {"reference": 3, "port_faithful": 6, "port_optimised": 80}   # sites per core: a few seconds of work each
+
+
+def cpu_leg(kind, tree, Q, pid, steps, order, sites_per_core=None, cores=None):
+    """`kind` on all host cores: sites are independent for fixed Q, so each core gets its own slice -- the most favourable
+    way to run the single-threaded reference on this host."""
     import multiprocessing as mp
     from phylomap_b200 import synth
     cores = cores or os.cpu_count() or 1
-    sites_per_core = sites_per_core or int(os.environ.get("PM_BENCH_CPU_SITES", 12))
-    st = synth.simulate_tip_states(tree, Q, pid, cores * sites_per_core, seed=99).numpy()
+    spc = sites_per_core or int(os.environ.get("PM_BENCH_CPU_SITES", CPU_SITES[kind]))
+    st = synth.simulate_tip_states(tree, Q, pid, cores * spc, seed=99).numpy()
     jobs = []
     for c in range(cores):
-        z = tree.with_states(st[c * sites_per_core:(c + 1) * sites_per_core], segments=2)
-        jobs.append((z.oracle_dict(), Q.copy(), pid, steps, 1000 + c))
+        z = tree.with_states(st[c * spc:(c + 1) * spc], segments=2)
+        jobs.append((kind, z.oracle_dict(*order), Q.copy(), pid, steps, 1000 + 97 * c))
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_oracle_worker, jobs)
+        res = pool.map(_cpu_worker, jobs)
     wall = time.perf_counter() - t0
-    hist = sum(r[0] for r in res)
-    return {"value": hist / wall, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d sites x %d cores x %d sweeps of the same tree/model, one oracle process per core, wall %.1f s"
-                      % (sites_per_core, cores, steps, wall)}, wall
+    what = {"reference": "oracle/_ref: the unmodified src/phylomap.cpp (maketreelistMCMC_bigtree) compiled against stand-in Rcpp / Armadillo headers",
+            "port_faithful": "in-repo port, keeps the reference's O(E) edge search per node (:643)",
+            "port_optimised": "in-repo port with a parent-edge table"}[kind]
+    return {"value": sum(r[0] for r in res) / wall, "unit": UNIT, "cores": cores, "kind": "reference" if kind == "reference" else "port",
+            "sample": "%s; %d sites x %d cores x %d sweeps of the same tree/model, one process per core, wall %.1f s"
+                      % (what, spc, cores, steps, wall)}, wall
+
+
+def cpu_baseline(tree, Q, pid, steps=6):
+    """The reported CPU context: the reference's own code where oracle/_ref exists, and the port in both modes."""
+    from oracle import bridge
+    bridge.build()
+    order = tree_order_numpy(tree.edge, tree.T)
+    have_ref = bridge.ref_lib() is not None
+    main, _ = cpu_leg("reference" if have_ref else "port_faithful", tree, Q, pid, steps, order)
+    for k in ("port_faithful", "port_optimised"):
+        leg, _ = cpu_leg(k, tree, Q, pid, steps, order)
+        main[k] = {"value": leg["value"], "sample": leg["sample"]}
+    return main
 
 
 def run_reference(a, rank, world):
@@ -145,18 +201,22 @@ def run_reference(a, rank, world):
     from oracle import bridge
     bridge.build()
     tree, Q, pid = workload_tree()
-    # warm-up: a tiny run so that page-in / fork costs stay out of the measurement
-    for _ in range(min(a.warmup, 1)):
-        cpu_reference(tree, Q, pid, 1, sites_per_core=1)
+    order = tree_order_numpy(tree.edge, tree.T)
+    kind = "reference" if bridge.ref_lib() is not None else "port_faithful"
+    for _ in range(min(a.warmup, 1)):   # a tiny run so that page-in / fork costs stay out of the measurement
+        cpu_leg(kind, tree, Q, pid, 1, order, sites_per_core=1)
     steps = max(1, min(a.steps, int(os.environ.get("PM_BENCH_CPU_STEPS", 6))))
-    cb, wall = cpu_reference(tree, Q, pid, steps)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(a.gpus, SITES_PER_GPU),
+    cb, wall = cpu_leg(kind, tree, Q, pid, steps, order)
+    cfg = config(a.gpus, SITES_PER_GPU)
+    cfg["precision"] = "f64"
+    cfg["rng"] = "R Mersenne-Twister (sequential)"
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+            "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference = CPU oracle restating src/phylomap.cpp (R/Rcpp/RcppArmadillo absent, the package cannot be built); "
-                    "each step is a bounded site sample of the workload"}
+            "note": "each step is one sweep over a bounded site sample of the workload (%s); steps = sweeps actually run "
+                    "(requested %d)" % (cb["sample"], a.steps)}
     print(json.dumps(line))
 
 
@@ -188,9 +248,9 @@ def run_ours(a, rank, local_rank, world):
     stream = torch.cuda.Stream()
     opts = dict(precision="f32", mode="production", seed=2026, device=local_rank, site_offset=rank * S,
                 stream=stream.cuda_stream)
-    if world > 1:  # the one collective of the path: sum of the statistics rows (here once per pm_chain_run, fixed Q)
+    if world > 1:  # the one collective of the path: the library's own ncclAllReduce of the statistics rows
         from phylomap_b200 import dist as pdist
-        opts["allreduce"] = pdist.allreduce_callback(stream.cuda_stream)
+        opts["nccl"] = pdist.nccl_clique(rank, world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -261,29 +321,73 @@ def run_ours(a, rank, local_rank, world):
     del chain
     torch.cuda.empty_cache()
 
-    # end to end through the drop-in entry with host buffers
-    barrier()
-    out = np.zeros((a.steps, 16), order="F")
-    t0 = time.perf_counter()
-    e2e_opts = dict(opts)  # same stream: the all-reduce callback must be ordered after the sweeps
-    res = pb.maketreelistMCMC_bigtree(z, Q.copy(), pid, np.asfortranarray(np.eye(4) + Q / OMEGA), OMEGA, *order[0], a.steps,
-                                      **e2e_opts)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    del out
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    # end to end through the drop-in entry with host buffers: once with the library's device-buffer cache emptied (what a
+    # single call in a fresh R session pays: cudaMalloc of the whole state), once more with the cache warm (a session that
+    # calls the sampler repeatedly on the same tree)
+    def e2e_call():
+        barrier()
+        t0 = time.perf_counter()
+        res = pb.maketreelistMCMC_bigtree(z, Q.copy(), pid, np.asfortranarray(np.eye(4) + Q / OMEGA), OMEGA, *order[0], a.steps,
+                                          **opts)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), res
+    capi.lib().pm_release_cached_memory()
+    first_s, res = e2e_call()
+    e2e_s, res = e2e_call()
     e2e = {"value": E * S * world * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(S * tree.T / a.steps),
-           "d2h_bytes_per_step": int(res.nbytes / a.steps), "seconds": e2e_s,
-           "what": "pm_maketreelistMCMC_bigtree(host tree + pinned u8 tip states): upload, chain build, %d sweeps, read-back; second call in the process, so device buffers come from the library's cache instead of cudaMalloc" % a.steps}
+           "d2h_bytes_per_step": int(res.nbytes / a.steps), "seconds": e2e_s, "first_call_seconds": first_s,
+           "first_call_value": E * S * world * a.steps / first_s,
+           "what": "pm_maketreelistMCMC_bigtree(host tree + pinned u8 tip states): upload, chain build, %d sweeps, read-back. "
+                   "`value` / `seconds`: a repeated call (device buffers come from the library's cache); `first_call_*`: the same "
+                   "call with the cache emptied first (cudaMalloc of the whole state included)" % a.steps}
+
+    # the rate-updating sampler on the same tree and site count: one small all-reduce + replicated host update per sweep
+    rate = None
+    if not a.no_rate:
+        capi.lib().pm_release_cached_memory()
+        zk = z  # same tips read as observed parity (1 / 2) of the hidden-rate model
+        par = torch.from_numpy(z.states)
+        par = ((par - 1) % 2 + 1).to(torch.uint8).numpy()     # observed trait of the 4 hidden states: 1,3 -> 1; 2,4 -> 2
+        zk = tree.with_states(par, segments=2)
+        Qk = np.asfortranarray(Q.copy())
+        n_ks = max(4, min(a.steps, 12))
+        prior_ks = np.array([1.0, 10.0, 2.0, 10.0, 20.0, 2.0])  # phylomap_tutorial.Rnw:261
+        ks_opts = {k: v for k, v in opts.items() if k != "nccl"}
+        if world > 1:
+            ks_opts["nccl"] = pdist.nccl_clique(rank, world)
+        ch = pb.Chain(capi.PM_V_KS, zk, Qk, pid, 4.0, n_ks + 3, prior=prior_ks, order=order, **ks_opts)
+        ch.run(3)
+        barrier()
+        ch.enable_timing(True)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        t0 = time.perf_counter()
+        ch.run(n_ks)
+        k1.record(stream)
+        torch.cuda.synchronize()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+        comm_ms, host_ms = ch.overheads()
+        kt, _ = ch.kernel_times()
+        t = torch.tensor([wall_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rate = {"sampler": "sumstatMCMCks (4-state hidden-rate model, Omega = 4, prior c(1,10,2,10,20,2)), %d sites per GPU" % S,
+                "sweeps": n_ks, "ms_per_sweep": float(t.item()) / n_ks, "value": E * S * world * n_ks / (float(t.item()) * 1e-3),
+                "unit": UNIT, "allreduce_us_per_sweep": 1e3 * comm_ms / n_ks, "host_update_us_per_sweep": 1e3 * host_ms / n_ks,
+                "allreduce_doubles": 4 + 16 + 1 + 1, "collective": "ncclAllReduce issued by the library on the chain's stream" if world > 1 else "none (1 rank)",
+                "in_sweep_ms": {k: v / n_ks for k, v in kt.items()},
+                "limits": "kernel time; the collective + D2H + host update + model upload are serialised with the sweep "
+                          "(the next sweep's kernels need the new Q)"}
+        ch.close()
+        del ch
 
     cb = None
     if rank == 0 and world == 1 and not a.no_cpu:
-        from oracle import bridge
-        bridge.build()
-        cb, _ = cpu_reference(tree, Q, pid, 6)
+        cb = cpu_baseline(tree, Q, pid)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -291,7 +395,8 @@ def run_ours(a, rank, local_rank, world):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config(world, S), "clocks": clk.summary(), "e2e": e2e,
-                "gpu_launches": int(launches - launches0), "roofline": roof, "cpu_baseline": cb, "device_bytes": dev_bytes}
+                "gpu_launches": int(launches - launches0), "roofline": roof, "cpu_baseline": cb, "rate_sampler": rate,
+                "device_bytes": dev_bytes, "device_bytes_per_branch_site": dev_bytes / (E * S)}
         print(json.dumps(line))
 
 
@@ -302,6 +407,7 @@ def main():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    p.add_argument("--no-rate", action="store_true", help="skip the rate_sampler block")
     a = p.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

@@ -219,6 +219,9 @@ int pm_chain_time_prune(pm_chain* c, int32_t tree, int32_t reps, float* ms_per_p
  * the number of kernel launches issued. */
 void pm_chain_kernel_times(pm_chain* c, double ms[4], int64_t* launches);
 void pm_chain_enable_timing(pm_chain* c, int32_t on);
+/* Rate-updating samplers, with timing enabled: ms[0] = device time of the per-sweep all-reduces (CUDA events around the
+ * collective), ms[1] = host time of the replicated rate updates + model upload, both accumulated since creation. */
+void pm_chain_overheads(pm_chain* c, double ms[2]);
 /* State after the last sweep, copied to host (for parity tests). */
 int pm_chain_get_node_states(pm_chain* c, int32_t tree, int32_t* out /* [S][2T-1] 0-based */);
 int pm_chain_get_piece_counts(pm_chain* c, int32_t tree, int32_t* out /* [S][E] */);

@@ -52,6 +52,7 @@ def lib():
         L.orc_run.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
         L.orc_ncols.argtypes = [C.c_void_p]
         L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_set_fast_lookup.argtypes = [C.c_void_p, C.c_int]
         L.orc_get_node_states.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_get_piece_counts.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_get_path.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
@@ -268,6 +269,10 @@ class OracleRun:
         if not self.h:
             raise OracleError(err.value.decode())
         self.ncols = L.orc_ncols(self.h)
+
+    def set_fast_lookup(self, on=True):
+        """bench.py's "optimised CPU" leg: parent-edge table instead of the reference's O(E) search per node (:643)."""
+        lib().orc_set_fast_lookup(self.h, int(on))
 
     def run(self):
         out = np.zeros((self.N, self.ncols), dtype=np.float64, order="F")

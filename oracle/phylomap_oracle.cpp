@@ -202,6 +202,9 @@ struct TreeIn {
   const int* states = nullptr;      // [S*T] 1-based, site-major
   int64_t S = 1;
   const double* edge_length = nullptr;
+  // "optimised CPU" baseline only (orc_set_fast_lookup): edge row of every non-root node, so that the node draws cost
+  // O(1) per node instead of the reference's linear search (:643); empty = faithful.  Same draws, same results.
+  std::vector<int> parent_edge;
   int parent(int e) const { return edge[e]; }
   int child(int e) const { return edge[E + e]; }
 };
@@ -281,7 +284,8 @@ struct Chain {
     for (int i = 0; i < t.T - 2; i++) {
       int node = t.nodelist[i];
       int j = 0;
-      while (t.child(j) != node) j++;  // the reference's O(E) search, :643
+      if (!t.parent_edge.empty()) j = t.parent_edge[node - 1];
+      else while (t.child(j) != node) j++;  // the reference's O(E) search, :643
       int ps = rm[t.parent(j) - 1];
       std::fill(w.begin(), w.end(), 0.0);
       w[ps] = 1;
@@ -964,6 +968,17 @@ void* orc_create(const orc_tree* trees, const orc_config* cfg, double* Q, const 
 }
 
 int orc_ncols(void* h) { return ((orc::Run*)h)->ncols(); }
+
+// bench.py's "optimised CPU" leg: replace the reference's O(E) edge search per node by a lookup table
+void orc_set_fast_lookup(void* h, int on) {
+  auto* r = (orc::Run*)h;
+  for (auto& t : r->trees) {
+    t.parent_edge.clear();
+    if (!on) continue;
+    t.parent_edge.assign(2 * t.T - 1, 0);
+    for (int e = t.E - 1; e >= 0; e--) t.parent_edge[t.child(e) - 1] = e;  // first matching row wins, like the search
+  }
+}
 
 int orc_run(void* h, double* out, char* err, int errlen) {
   auto* r = (orc::Run*)h;

@@ -154,6 +154,12 @@ class Chain:
         capi.lib().pm_chain_kernel_times(self.h, ms, C.byref(n))
         return {"prune": ms[0], "sample_nodes": ms[1], "resample_paths": ms[2], "reduce": ms[3]}, int(n.value)
 
+    def overheads(self):
+        """(all-reduce device ms, host rate-update ms) accumulated while timing was enabled (rate-updating samplers)."""
+        ms = (C.c_double * 2)()
+        capi.lib().pm_chain_overheads(self.h, ms)
+        return float(ms[0]), float(ms[1])
+
     def device_bytes(self):
         return int(capi.lib().pm_chain_device_bytes(self.h))
 

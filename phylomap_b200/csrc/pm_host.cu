@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -229,6 +230,7 @@ struct pm_chain {
   virtual void import_state(const void* buf, int64_t bytes) = 0;
   double kernel_ms[4] = {0, 0, 0, 0};
   std::vector<long long> rate_proposed, rate_accepted;  // per rate parameter, trace-column order (pm_rates.hpp)
+  double comm_ms = 0, host_update_ms = 0;  // with timing on: device time of the per-sweep all-reduces, host time of the rate updates
   int64_t launches = 0;
   int64_t dev_bytes = 0;
   bool timing = false;
@@ -967,9 +969,14 @@ struct ChainT : pm_chain {
       CK(cudaGetLastError());
       // one small all-reduce per sweep (n + n^2 + 1 (+1) statistics + the error slot, per tree), then ONE synchronisation:
       // the device error flag travels in the row instead of a second copy
+      cudaEvent_t ca = nullptr, cb = nullptr;
+      if (timing) { CK(cudaEventCreate(&ca)); CK(cudaEventCreate(&cb)); CK(cudaEventRecord(ca, stream)); }
       reduce_over_ranks(rows.as<double>(), ntrees * WR);
+      if (timing) CK(cudaEventRecord(cb, stream));
       CK(cudaMemcpyAsync(rows_h, rows.p, (size_t)ntrees * WR * sizeof(double), cudaMemcpyDeviceToHost, stream));
       CK(cudaStreamSynchronize(stream));
+      if (timing) { float ms = 0; cudaEventElapsedTime(&ms, ca, cb); comm_ms += ms; cudaEventDestroy(ca); cudaEventDestroy(cb); }
+      const auto host_t0 = std::chrono::steady_clock::now();
       check_row_errors(rows_h, ntrees);
       for (int j = 0; j < ntrees; j++) {
         std::fill(jodt[j].begin(), jodt[j].end(), 0.0);
@@ -993,6 +1000,7 @@ struct ChainT : pm_chain {
       if (g.exhausted()) fail(PM_ERR_REPLAY, "host replay table exhausted");
       iters_done++;
       stage_model(false);
+      if (timing) host_update_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
       if (opt.progress) { printf("%i \r", it); }
     }
     CK(cudaStreamSynchronize(stream));
@@ -1459,6 +1467,7 @@ void pm_chain_kernel_times(pm_chain* c, double ms[4], int64_t* launches) {
   if (launches) *launches = c->launches;
 }
 void pm_chain_enable_timing(pm_chain* c, int32_t on) { c->timing = on != 0; }
+void pm_chain_overheads(pm_chain* c, double ms[2]) { ms[0] = c->comm_ms; ms[1] = c->host_update_ms; }
 int pm_chain_get_node_states(pm_chain* c, int32_t tree, int32_t* out) {
   return guarded(nullptr, 0, [&] { c->node_states(tree, out); });
 }
