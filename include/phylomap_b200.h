@@ -101,7 +101,9 @@ typedef struct pm_options {
   void* allreduce_ctx;
   void* cuda_stream;       /* cudaStream_t to launch on; NULL = a private stream */
   int32_t progress;        /* non-zero: print "%i \r" per iteration like the reference (:930) */
-  int32_t nccl_world;      /* > 1: number of ranks of the NCCL clique the library joins at pm_chain_create (collective call) */
+  int32_t nccl_world;      /* > 1: number of ranks of the NCCL clique the library joins at pm_chain_create (a collective call
+                              the first time an id is seen; the communicator is then kept for the life of the process and
+                              reused by every later call that passes the same id) */
   int32_t nccl_rank;       /* this process's rank in it */
   int32_t reserved;
   const void* nccl_id;     /* the clique's 128-byte ncclUniqueId: pm_nccl_unique_id() on one rank, handed to the others by the

@@ -215,6 +215,26 @@ long long chernoff_records_cap(const std::vector<double>& lams, double eps) {
 
 }  // namespace
 
+// NCCL communicators live as long as the process: a unique id can initialise a clique only once, and a session calls the
+// samplers many times with the same id (ncclCommInitRank costs tenths of a second).  Keyed by the id's 128 bytes.
+static pm::host::NcclApi::Comm clique(const void* id128, int world, int rank) {
+  static std::mutex mu;
+  static std::map<std::string, pm::host::NcclApi::Comm> comms;
+  auto& api = pm::host::NcclApi::get();
+  if (!api.ok()) fail(PM_ERR_CUDA, "NCCL could not be loaded: %s", api.why.c_str());
+  const std::string key((const char*)id128, 128);
+  std::lock_guard<std::mutex> g(mu);
+  auto it = comms.find(key);
+  if (it != comms.end()) return it->second;
+  pm::host::NcclApi::UniqueId id;
+  memcpy(&id, id128, sizeof id);
+  pm::host::NcclApi::Comm c = nullptr;
+  const int rc = api.CommInitRank(&c, world, id, rank);
+  if (rc != 0) fail(PM_ERR_CUDA, "ncclCommInitRank failed: %s", api.error(rc).c_str());
+  comms[key] = c;
+  return c;
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 struct pm_chain {
   virtual ~pm_chain() {}
@@ -294,7 +314,6 @@ struct ChainT : pm_chain {
   ~ChainT() override {
     cudaSetDevice(opt.device);
     cudaDeviceSynchronize();
-    if (nccl) pm::host::NcclApi::get().CommDestroy(nccl);
     for (auto& t : timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (model_h) cudaFreeHost(model_h);
     if (rows_h) cudaFreeHost(rows_h);
@@ -737,14 +756,7 @@ struct ChainT : pm_chain {
     ppow.alloc((size_t)jcap * n * n * sizeof(Real));
     CK(cudaMallocHost((void**)&model_h, (model_elems() + (size_t)jcap * n * n) * sizeof(Real)));
     CK(cudaMallocHost((void**)&rows_h, (size_t)ntrees * WR * sizeof(double)));
-    if (opt.nccl_world > 1) {
-      auto& api = pm::host::NcclApi::get();
-      if (!api.ok()) fail(PM_ERR_CUDA, "NCCL could not be loaded: %s", api.why.c_str());
-      pm::host::NcclApi::UniqueId id;
-      memcpy(&id, opt.nccl_id, sizeof id);
-      const int rc = api.CommInitRank(&nccl, opt.nccl_world, id, opt.nccl_rank);
-      if (rc != 0) fail(PM_ERR_CUDA, "ncclCommInitRank failed: %s", api.error(rc).c_str());
-    }
+    if (opt.nccl_world > 1) nccl = clique(opt.nccl_id, opt.nccl_world, opt.nccl_rank);
     CK(cudaMallocHost((void**)&err_h, sizeof(unsigned)));
     if (V.dic) { CK(cudaMallocHost((void**)&q_h, (size_t)n * n * sizeof(double))); q_dev.alloc((size_t)n * n * sizeof(double)); }
     cnt.alloc((size_t)n * n * sizeof(unsigned long long));
