@@ -1265,12 +1265,61 @@ pm_chain* make_chain(int variant, const pm_tree* trees, int ntrees, int n, doubl
   return c.release();
 }
 
+// Fixed-Q samplers over a block of sites [s0, s0 + count) of `x`: a chain of its own (sites are independent given Q).
+void run_site_block(int variant, const pm_tree* x, int n, double* Q, const double* pid, double* B, double Omega, int N,
+                    const pm_options* opt, const EigenIn* eg, long long s0, long long count, double* out) {
+  pm_tree t = *x;
+  t.n_sites = count;
+  if (x->states_u8) t.states_u8 = x->states_u8 + s0 * (long long)x->n_tips;
+  if (x->states) t.states = x->states + s0 * (long long)x->n_tips;
+  pm_options o = *opt;
+  o.site_offset = opt->site_offset + s0;
+  std::unique_ptr<pm_chain> c(make_chain(variant, &t, 1, n, Q, pid, B, Omega, nullptr, 0, N, &o, eg));
+  c->run(N, out, N);
+}
+
 int one_call(int variant, const pm_tree* trees, int ntrees, int n, double* Q, const double* pid, double* B, double Omega,
-             int N, const double* prior, int nprior, const pm_options* opt, double* out, char* err, size_t errlen) {
+             int N, const double* prior, int nprior, const pm_options* opt, double* out, char* err, size_t errlen,
+             const EigenIn* eg = nullptr) {
   return guarded(err, errlen, [&] {
     if (!out && N > 0) fail(PM_ERR_ARG, "null output");
-    std::unique_ptr<pm_chain> c(make_chain(variant, trees, ntrees, n, Q, pid, B, Omega, prior, nprior, N, opt));
-    c->run(N, out, N);
+    pm_options def;
+    if (!opt) { pm_default_options(&def); opt = &def; }
+    const bool fixed_q = variant == PM_V_PLAIN || variant == PM_V_SPARSE || variant == PM_V_BIGTREE || variant == PM_V_EXP;
+    const bool single_process = !opt->allreduce && opt->nccl_world <= 1;
+    long long tile = 0;  // sites per chain; 0 = all at once
+    if (const char* v = getenv("PHYLOMAP_B200_SITE_TILE")) tile = atoll(v);
+    if (!fixed_q || !trees || ntrees != 1 || opt->rng == PM_RNG_TABLE || trees[0].n_sites < 2) tile = 0;
+    const long long S = trees ? trees[0].n_sites : 0;
+    // A call whose state does not fit in device memory is cut into site tiles, run one after the other (each an
+    // independent chain of N sweeps: the fixed-Q samplers couple the sites through nothing but the final sum).  The tile
+    // is halved until a chain can be allocated.  The rate-updating samplers need all sites resident in every sweep (Q
+    // depends on their sum): they are left to fail with the allocator's message.  With several ranks the tile size must
+    // be the same everywhere (one all-reduce per tile), so it is only taken from PHYLOMAP_B200_SITE_TILE there.
+    for (;;) {
+      const long long ts = (tile > 0 && tile < S) ? tile : S;
+      try {
+        if (ts >= S) {
+          std::unique_ptr<pm_chain> c(make_chain(variant, trees, ntrees, n, Q, pid, B, Omega, prior, nprior, N, opt, eg));
+          c->run(N, out, N);
+        } else {
+          const int nc = ncols_of(variant, n);
+          std::vector<double> part((size_t)N * nc), acc((size_t)N * nc, 0.0);
+          for (long long s0 = 0; s0 < S; s0 += ts) {
+            run_site_block(variant, trees, n, Q, pid, B, Omega, N, opt, eg, s0, std::min(ts, S - s0), part.data());
+            for (size_t i = 0; i < acc.size(); i++) acc[i] += part[i];
+          }
+          std::copy(acc.begin(), acc.end(), out);
+        }
+        return;
+      } catch (const Fail& f) {
+        const bool oom = f.code == PM_ERR_CUDA && f.msg.find("cudaMalloc") != std::string::npos;
+        if (!oom || !fixed_q || !single_process || ts < 64 || ntrees != 1 || opt->rng == PM_RNG_TABLE) throw;
+        cudaGetLastError();
+        pool().release();
+        tile = (ts + 1) / 2;
+      }
+    }
   });
 }
 
@@ -1324,12 +1373,8 @@ int pm_maketreelistMCMCksmt(const pm_tree* trees, int32_t ntrees, int32_t n, dou
 
 int pm_maketreelistEXP(const pm_tree* x, int32_t n, double* Q, const double* pid, int32_t N, const double* lefts,
                        const double* rights, const double* d, const pm_options* opt, double* out, char* err, size_t errlen) {
-  return guarded(err, errlen, [&] {
-    if (!out && N > 0) fail(PM_ERR_ARG, "null output");
-    EigenIn eg{lefts, rights, d};
-    std::unique_ptr<pm_chain> c(make_chain(PM_V_EXP, x, 1, n, Q, pid, nullptr, 0.0, nullptr, 0, N, opt, &eg));
-    c->run(N, out, N);
-  });
+  EigenIn eg{lefts, rights, d};
+  return one_call(PM_V_EXP, x, 1, n, Q, pid, nullptr, 0.0, N, nullptr, 0, opt, out, err, errlen, &eg);
 }
 
 int pm_maketreelistMCMC2sDICt(const pm_tree* x, int32_t n, double* Q, const double* pid, double* B, double Omega, int32_t N,

@@ -1,0 +1,38 @@
+"""The reference's literal usage, one character per call: seconds per sweep of the GPU library
+against the CPU port on ONE core, for BASELINE configs[0] (100 tips, 1 000 sweeps) and the Squamate vignette tree."""
+import os, sys, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np, torch
+import cases
+import phylomap_b200 as pb
+from phylomap_b200 import synth
+from oracle import bridge
+out = {}
+def gpu(fn, *a, **k):
+    fn(*a, **k)  # warm
+    torch.cuda.synchronize(); t = time.perf_counter(); r = fn(*a, **k); torch.cuda.synchronize()
+    return time.perf_counter() - t, r
+def cpu(variant, z, Q, pid, Om, N, fast):
+    o = bridge.OracleRun(variant, [z.oracle_dict()], Q, pid, Om, N, rng_mode=bridge.SEQUENTIAL, seed=3)
+    o.set_fast_lookup(fast)
+    t = time.perf_counter(); o.run(); return time.perf_counter() - t
+# configs[0]
+z = synth.simulate_2_state_tree(101, synth.yule_tree(100, seed=1, mean_branch=5.0), cases.Q2, cases.PID2)
+N = 1000
+for prec in ("f32", "f64"):
+    dt, _ = gpu(pb.sumstatMCMC, z, cases.Q2, cases.PID2, 0.2, N, seed=5, precision=prec)
+    out["cfg0_gpu_%s_us_per_sweep" % prec] = 1e6 * dt / N
+out["cfg0_cpu_port_faithful_us_per_sweep"] = 1e6 * cpu(bridge.PLAIN, z, cases.Q2, cases.PID2, 0.2, N, False) / N
+out["cfg0_cpu_port_optimised_us_per_sweep"] = 1e6 * cpu(bridge.PLAIN, z, cases.Q2, cases.PID2, 0.2, N, True) / N
+t = time.perf_counter(); bridge.ref_run(bridge.PLAIN, [z.oracle_dict()], cases.Q2, cases.PID2, 0.2, N, seed=3)
+out["cfg0_cpu_reference_us_per_sweep"] = 1e6 * (time.perf_counter() - t) / N
+# the Squamate vignette: 3 951 tips x 100 segments, Omega = 10, one character
+Q = np.array([[-0.001, 0.001], [0.006, -0.006]])
+zs = synth.simulate_2_state_tree(101, cases.squamate_tree(), Q, cases.PID2)
+N2 = 40
+dt, _ = gpu(pb.sumstatMCMC_bigtree, zs, Q, cases.PID2, 10.0, N2, seed=5, precision="f64")
+out["squamate_gpu_f64_ms_per_sweep"] = 1e3 * dt / N2
+out["squamate_cpu_port_faithful_ms_per_sweep"] = 1e3 * cpu(bridge.BIGTREE, zs, Q, cases.PID2, 10.0, 4, False) / 4
+out["squamate_cpu_port_optimised_ms_per_sweep"] = 1e3 * cpu(bridge.BIGTREE, zs, Q, cases.PID2, 10.0, 4, True) / 4
+print(json.dumps(out))

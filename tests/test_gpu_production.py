@@ -419,3 +419,19 @@ def test_production_rows_are_frozen():
     for k, ref in want.items():
         ref = np.asarray(ref)
         np.testing.assert_allclose(got[k], ref, rtol=1e-12, atol=0, err_msg=k)
+
+
+def test_site_tiles_equal_one_call(monkeypatch):
+    """A fixed-Q call that does not fit in device memory is cut into site tiles run one after the other (pm_host.cu,
+    one_call).  Forced here with PHYLOMAP_B200_SITE_TILE: the tiles are keyed by global site index, so the summed
+    rows equal the untiled call -- integer counts exactly, dwell times to FP32 summation order."""
+    Q, pid = cases.q4(), np.full(4, 0.25)
+    z = cases.tree_n(Q, T=120, S=333, seed=12, mean_branch=0.4, segments=2)
+    whole = pb.sumstatMCMC_bigtree(z, Q, pid, 2.4, 6, seed=21, precision="f32")
+    ex_whole = pb.sumstatEXP(z, Q, pid, 4, seed=22, precision="f32")
+    monkeypatch.setenv("PHYLOMAP_B200_SITE_TILE", "100")
+    tiled = pb.sumstatMCMC_bigtree(z, Q, pid, 2.4, 6, seed=21, precision="f32")
+    assert np.array_equal(tiled[:, 4:], whole[:, 4:])
+    np.testing.assert_allclose(tiled[:, :4], whole[:, :4], rtol=1e-5)
+    ex_tiled = pb.sumstatEXP(z, Q, pid, 4, seed=22, precision="f32")
+    assert np.array_equal(ex_tiled[:, 4:], ex_whole[:, 4:])
