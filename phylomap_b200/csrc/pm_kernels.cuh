@@ -1308,108 +1308,138 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned FULL = 0xffffffffu;
 
-  // ---- the common short shape: three pieces (two jump points), at most one of them a real jump, every run in count mode.
-  // Straight-line restatement of what the general code below does for such an item: same streams, same words, same
-  // pinned arithmetic, so a path may be written by one and regenerated by the other.
+  // ---- the common short shapes: three or four pieces (two or three jump points), at most one of them a real jump, every
+  // run in count mode.  Unrolled, register-only restatement of what the general code below does for such an item: same
+  // streams, same words, same pinned arithmetic, so a path may be written by one and regenerated by the other.
   auto short_item = [&](const HardItem<Real> it) {
     const long long site = it.site;
     const int eb = (int)it.e;
     const uint32_t mt = it.meta;
     const long long pe = (long long)eb * S + site;
+    const int m = (int)(mt & 0xffffu);  // 3 or 4
     const int nj = (int)((mt >> 16) & 0x3fu);
     const int so0 = (int)((mt >> 22) & 0x1fu), so1 = (int)((mt >> 27) & 0x1fu);
     const int ps = (int)(it.ends & 0xffu), cs = (int)(it.ends >> 8);
     const Real Le = __ldg(P.e_len + eb);
+    const uint32_t gsite = P.rng.site0 + (uint32_t)site;
     uint32_t po_old[4], po_new[4];
     pair_block(P.rng, (uint32_t)site, iter, (uint32_t)eb, po_new);
     pair_block(P.rng, (uint32_t)site, iter - 1u, (uint32_t)eb, po_old);
     const uint32_t oA = (eb & 1) ? po_old[2] : po_old[0], oB = (eb & 1) ? po_old[3] : po_old[1];
     const uint32_t nA = (eb & 1) ? po_new[2] : po_new[0], nB = (eb & 1) ? po_new[3] : po_new[1];
-    // the three pieces of the previous path
-    Real a, b, c;
-    int run_with_jump = 0;
-    Real p1 = 0;
-    int kold0, kold1 = 0;
-    if (nj == 0) {
-      kold0 = poisson_inv<Real>(PN::mul(s_rate_old[so0], Le), oA);
-      if (kold0 != 2) errbits |= PM_DE_INCONSISTENT;
-    } else {
-      p1 = it.p1;
-      kold0 = poisson_inv<Real>(PN::mul(s_rate_old[so0], p1), oA);
-      kold1 = poisson_inv<Real>(PN::mul(s_rate_old[so1], PN::sub(Le, p1)), oB);
-      if (kold0 + kold1 != 1) errbits |= PM_DE_INCONSISTENT;
-      run_with_jump = kold1 == 1 ? 1 : 0;
-    }
-    uint32_t pw[4];  // first position block of the run that needs one (K_BRPOS stream of that run, block 0)
-    philox4x32_10((uint32_t)run_with_jump << 20, make_slot(K_BRPOS, (uint32_t)eb), iter - 1u, P.rng.site0 + (uint32_t)site, P.rng.k0, P.rng.k1, pw);
-    if (nj == 0) {
-      const Real t2 = next_order_stat<Real>((Real)0, Le, 2, oB);   // (a single-run path takes its first position word from the pair block)
-      a = PN::sub(t2, (Real)0);
-      const Real t3 = next_order_stat<Real>(t2, Le, 1, pw[0]);
-      b = PN::sub(t3, t2);
-      c = PN::sub(Le, t3);
-    } else if (run_with_jump == 0) {
-      const Real t2 = next_order_stat<Real>((Real)0, p1, 1, pw[0]);
-      a = PN::sub(t2, (Real)0);
-      b = PN::sub(p1, t2);
-      c = PN::sub(PN::sub(Le, p1), (Real)0);
-    } else {
-      const Real L1r = PN::sub(Le, p1);
-      a = PN::sub(p1, (Real)0);
-      const Real t2 = next_order_stat<Real>((Real)0, L1r, 1, pw[0]);
-      b = PN::sub(t2, (Real)0);
-      c = PN::sub(L1r, t2);
-    }
-    // the interior state: B[ps, .] x (Bs e_cs)
-    int st;
+    // ---- the m pieces of the previous path: up to three on each of its (one or two) runs
+    Real r0[3] = {0, 0, 0}, r1[3] = {0, 0, 0};
+    int k0o, k1o = 0;
+    const Real p1 = nj == 0 ? Le : it.p1;          // length of run 0
+    const Real L1r = PN::sub(Le, p1);              // length of run 1 (nj == 1)
+    k0o = poisson_inv<Real>(PN::mul(s_rate_old[so0], p1), oA);
+    if (nj == 1) k1o = poisson_inv<Real>(PN::mul(s_rate_old[so1], L1r), oB);
+    if (k0o + k1o != m - 1 - nj || k0o > 3 || k1o > 2) { errbits |= PM_DE_INCONSISTENT; k0o = min(k0o, 3); k1o = min(k1o, 2); }
     {
-      Real wv[NC];
-      const Real* M = (1 < npow_s) ? (sPow + n * n) : (P.ppow + (size_t)n * n);
+      // run 0: a single-run path takes its first position word from the pair block, the others from the K_BRPOS stream
+      const bool firstB = nj == 0;
+      uint32_t pw[4] = {0, 0, 0, 0};
+      if (k0o > (firstB ? 1 : 0)) philox4x32_10(0u, make_slot(K_BRPOS, (uint32_t)eb), iter - 1u, gsite, P.rng.k0, P.rng.k1, pw);
+      Real x = 0;
 #pragma unroll
-      for (int q = 0; q < n; q++) wv[q] = sB[ps * n + q] * M[q * n + cs];
-      Stream gst; gst.open(P.rng, (uint32_t)site, iter, K_BRSTATE, (uint32_t)eb, P.err_flag);
-      st = categorical<Real, NC, false>(wv, n, gst.next(), P.err_flag);
+      for (int q = 0; q < 3; q++) {
+        if (q < k0o) {
+          const uint32_t w = firstB ? (q == 0 ? oB : pw[q - 1 < 0 ? 0 : q - 1]) : pw[q];
+          const Real t2 = next_order_stat<Real>(x, p1, k0o - q, w);
+          const Real piece = PN::sub(t2, x);
+          x = t2;
+          if (q == 0) r0[0] = piece; else if (q == 1) r0[1] = piece; else r0[2] = piece;
+        }
+      }
+      const Real lastp = PN::sub(p1, x);
+      if (k0o == 0) r0[0] = lastp; else if (k0o == 1) r0[1] = lastp; else if (k0o == 2) r0[2] = lastp;
+      // (k0o == 3: m == 4, nj == 0 -- the fourth piece is kept in r1[0])
+      if (k0o == 3) r1[0] = lastp;
     }
-    // merge, count, emit
-    if (full) { atomicAdd(&s_cnt[ps * n + st], 1u); atomicAdd(&s_cnt[st * n + cs], 1u); }
-    else {
-      if (st != ps) atomicAdd(&s_cnt[ps * n + st], 1u);
-      if (cs != st) atomicAdd(&s_cnt[st * n + cs], 1u);
+    if (nj == 1) {
+      uint32_t pw[4] = {0, 0, 0, 0};
+      if (k1o > 0) philox4x32_10(1u << 20, make_slot(K_BRPOS, (uint32_t)eb), iter - 1u, gsite, P.rng.k0, P.rng.k1, pw);
+      Real x = 0;
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        if (q < k1o) {
+          const Real t2 = next_order_stat<Real>(x, L1r, k1o - q, pw[q]);
+          const Real piece = PN::sub(t2, x);
+          x = t2;
+          if (q == 0) r1[0] = piece; else r1[1] = piece;
+        }
+      }
+      const Real lastp = PN::sub(L1r, x);
+      if (k1o == 0) r1[0] = lastp; else if (k1o == 1) r1[1] = lastp; else r1[2] = lastp;
     }
-    int nout; Real L0, L1 = 0, L2 = 0; int S0, S1 = 0, S2 = 0;
-    if (st == ps) {
-      const Real ab = a + b;
-      if (cs == st) { nout = 1; L0 = Le; S0 = ps; }
-      else { nout = 2; L0 = ab; S0 = ps; L1 = PN::sub(Le, L0); S1 = cs; }
-    } else if (cs == st) { nout = 2; L0 = a; S0 = ps; L1 = PN::sub(Le, L0); S1 = cs; }
-    else { nout = 3; L0 = a; S0 = ps; L1 = b; S1 = st; L2 = c; S2 = cs; }
-    auto count_new = [&](int s, Real L, uint32_t cw) -> int {
-      const Real rate = s_rate_new[s];
-      return rate_ok(rate) ? poisson_inv<Real>(PN::mul(rate, L), cw) : 0;
+    // piece j of the path: the pieces of run 0 (k0o + 1 of them, at most three kept in r0), then those of run 1
+    const int n0 = min(k0o + 1, 3);
+    auto piece_len = [&](int jx) -> Real {
+      const int t = jx - n0;
+      return jx < n0 ? (jx == 0 ? r0[0] : jx == 1 ? r0[1] : r0[2]) : (t == 0 ? r1[0] : t == 1 ? r1[1] : r1[2]);
     };
-    add_dwell(S0, L0);
-    const int k0 = count_new(S0, L0, nA);
-    int newm = k0 + 1;
-    if (nout >= 2) { add_dwell(S1, L1); newm += count_new(S1, L1, nB) + 1; }
-    if (nout == 3) {
-      add_dwell(S2, L2);
-      uint32_t cwv[4];
-      philox4x32_10(0u, make_slot(K_BRCNT, (uint32_t)eb), iter, P.rng.site0 + (uint32_t)site, P.rng.k0, P.rng.k1, cwv);
-      newm += count_new(S2, L2, cwv[0]) + 1;
+    // ---- the new path ----
+    int nout = 0, newm = 0, S0 = 0, S1 = 0, S2 = 0, S3 = 0, k0n = 0;
+    Real L0 = 0, L1 = 0, L2 = 0, L3 = 0;
+    uint32_t cw[4] = {0, 0, 0, 0};
+    bool have_cw = false;
+    auto emit = [&](Real L, int sst) {
+      const int r = nout;
+      if (r == 0) { L0 = L; S0 = sst; } else if (r == 1) { L1 = L; S1 = sst; } else if (r == 2) { L2 = L; S2 = sst; } else { L3 = L; S3 = sst; }
+      add_dwell(sst, L);
+      if (r >= 2 && !have_cw) {
+        philox4x32_10(0u, make_slot(K_BRCNT, (uint32_t)eb), iter, gsite, P.rng.k0, P.rng.k1, cw);
+        have_cw = true;
+      }
+      const uint32_t w = r == 0 ? nA : r == 1 ? nB : r == 2 ? cw[0] : cw[1];
+      const Real rate = s_rate_new[sst];
+      const int k = rate_ok(rate) ? poisson_inv<Real>(PN::mul(rate, L), w) : 0;
+      if (r == 0) k0n = k;
+      newm += k + 1;
+      nout++;
+    };
+    Stream gst; gst.open(P.rng, (uint32_t)site, iter, K_BRSTATE, (uint32_t)eb, P.err_flag);
+    int cur_state = ps, prev = ps;
+    Real cur_len = piece_len(0);
+#pragma unroll
+    for (int pp = 1; pp < 4; pp++) {
+      if (pp < m) {
+        int st;
+        if (pp == m - 1) st = cs;
+        else {
+          const int jd = m - pp - 1;  // 1 or 2
+          Real wv[NC];
+          const Real* M = (jd < npow_s) ? (sPow + jd * n * n) : (P.ppow + (size_t)jd * n * n);
+#pragma unroll
+          for (int q = 0; q < n; q++) wv[q] = sB[prev * n + q] * M[q * n + cs];
+          st = categorical<Real, NC, false>(wv, n, gst.next(), P.err_flag);
+        }
+        const Real len = piece_len(pp);
+        if (full) atomicAdd(&s_cnt[prev * n + st], 1u);
+        if (st == cur_state) cur_len = cur_len + len;
+        else {
+          emit(cur_len, cur_state);
+          if (!full) atomicAdd(&s_cnt[cur_state * n + st], 1u);
+          cur_state = st; cur_len = len;
+        }
+        prev = st;
+      }
     }
-    if (nout == 1) { if (k0 == 1) P.pos1[pe] = next_order_stat<Real>((Real)0, Le, 1, nB); }
+    emit(nout == 0 ? Le : nout == 1 ? PN::sub(Le, L0) : cur_len, cur_state);
+    if (nout == 1) { if (k0n == 1) P.pos1[pe] = next_order_stat<Real>((Real)0, Le, 1, nB); }
     else if (nout == 2) P.pos1[pe] = L0;
     else {
       const int ck = eb / P.chunk;
       const int cap0 = __ldg(P.cap_off + ck), cap_c = __ldg(P.cap_off + ck + 1) - cap0;
       const long long sl = (long long)cap0 * S + site * (long long)cap_c;
-      const int base = atomicAdd(P.rec_cursor + (long long)ck * S + site, 3);
+      const int base = atomicAdd(P.rec_cursor + (long long)ck * S + site, nout);
       P.pos1[pe] = (Real)base;
-      if (base + 3 > cap_c) errbits |= PM_DE_PATH_CAP;
+      if (base + nout > cap_c) errbits |= PM_DE_PATH_CAP;
       else {
         wr_len[sl + base] = L0; wr_st[sl + base] = (uint8_t)S0;
         wr_len[sl + base + 1] = L1; wr_st[sl + base + 1] = (uint8_t)S1;
         wr_len[sl + base + 2] = L2; wr_st[sl + base + 2] = (uint8_t)S2;
+        if (nout == 4) { wr_len[sl + base + 3] = L3; wr_st[sl + base + 3] = (uint8_t)S3; }
       }
     }
     P.meta[pe] = PM_META(newm, nout - 1, S0, S1);
@@ -1650,7 +1680,8 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       bool is_short = false;
       if (WHICH == 0 && have && short_ok) {
         const int m = (int)(it.meta & 0xffffu), njq = (int)((it.meta >> 16) & 0x3fu);
-        is_short = m == 3 && njq <= 1 && rate_ok(s_rate_old[(it.meta >> 22) & 0x1fu]) && (njq == 0 || rate_ok(s_rate_old[(it.meta >> 27) & 0x1fu]));
+        is_short = (m == 3 || m == 4) && njq <= 1 && rate_ok(s_rate_old[(it.meta >> 22) & 0x1fu]) &&
+                   (njq == 0 || rate_ok(s_rate_old[(it.meta >> 27) & 0x1fu]));
       }
       // the short launch (first) takes its items out of the ballot array; the general launch takes whatever is left
       const bool mine = have && (WHICH == 1 || is_short);
