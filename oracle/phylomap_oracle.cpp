@@ -3,11 +3,20 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
 // library.  The product (phylomap_b200/) never links, imports or executes it.
 //
-// PARITY UNPINNED: the reference ships no golden vectors for this path and cannot be built here (needs R,
-// Rcpp, RcppArmadillo).  This file restates /root/reference/src/phylomap.cpp on flat arrays,
-// keeping its order of floating-point operations and of random draws; third-party arithmetic (R nmath RNG,
-// RcppArmadillo::sample, Armadillo tiny mat-vec / accu) is restated in r_rng.hpp and below from the published
-// algorithms.  The RNG layer alone is pinned, against well-known R outputs (tests/test_oracle_rng.py).
+// PINNED AGAINST THE REFERENCE ITSELF (round 2): the reference ships no golden vectors for this path, but its two source
+// files compile unmodified against the stand-in Rcpp / RcppArmadillo / Armadillo headers of oracle/standin/
+// (oracle/Makefile, target `ref` -> oracle/_ref/libphylomap_ref.so).  In R-sequential mode this restatement reproduces the
+// rows of all ten `.Call` entry points bit for bit (tests/test_reference_pin.py, fixtures tests/golden/reference/*.json
+// made by tests/golden/make_reference_golden.py); the DIC log-likelihood column agrees to 1e-12 (arma::expmat is a Pade
+// scheme restated twice).  One known divergence: above 16 states RcppArmadillo::sample's std::sort is no longer an
+// insertion sort and EXACT ties between weights may be ordered differently (a Jukes-Cantor-like 20-state model).
+// What remains unpinned is the layer BELOW both: R's nmath RNG (restated in r_rng.hpp from the published algorithms,
+// checked against widely published R outputs, tests/test_oracle_rng.py) and real Armadillo's summation order for n > 4
+// (BLAS: implementation-defined).
+//
+// This file restates /root/reference/src/phylomap.cpp on flat arrays, keeping its order of floating-point operations
+// and of random draws; third-party arithmetic (R nmath RNG, RcppArmadillo::sample, Armadillo tiny mat-vec / accu) is
+// restated in r_rng.hpp and below from the published algorithms.
 //
 // Reference map (file = src/phylomap.cpp):
 //   Branch / makeabranch ............ :18-34      -> struct Seg, Chain::init_from_maps

@@ -263,9 +263,18 @@ __global__ void __launch_bounds__(256, MINB) k_prune_pipe(ChainParams<Real> P) {
         if (normalize) {
           // structural zeros must stay zeros (no floor); a product that underflowed altogether becomes the zero
           // vector and surfaces in the draw as "Not enough positive probabilities", like a NaN would in the reference
-          const Real inv = s > (Real)0 ? fast_rcp<Real>(s) : (Real)0;
+          if (sizeof(Real) == 4 && !(s > (Real)1e-30)) {  // FP32: redo an underflowed product in double (see k_prune_clade)
+            double d[NS], ds = 0;
 #pragma unroll
-          for (int j = 0; j < NS; j++) out[j] *= inv;
+            for (int j = 0; j < NS; j++) { d[j] = (double)nd[u].vb[j] * (double)nd[u].va[j]; ds += d[j]; }
+            const double di = ds > 0 ? 1.0 / ds : 0.0;
+#pragma unroll
+            for (int j = 0; j < NS; j++) out[j] = (Real)(d[j] * di);
+          } else {
+            const Real inv = s > (Real)0 ? fast_rcp<Real>(s) : (Real)0;
+#pragma unroll
+            for (int j = 0; j < NS; j++) out[j] *= inv;
+          }
         }
         if (active) VecIO<Real, NS>::store(PLs + (long long)(nd[u].pn - T) * rowPL, NS, out);
       }
@@ -384,6 +393,17 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
     Real sum = 0;
 #pragma unroll
     for (int j = 0; j < NS; j++) { out[j] = vb[j] * va[j]; sum += out[j]; }
+    if (sizeof(Real) == 4 && !(sum > (Real)1e-30) && !(P.tune & 2)) {
+      // FP32 only, rare: two clades that each all but settle a DIFFERENT state (1e-20 x 1e-20): the products underflow
+      // although both factors are representable.  Redo this node in double, where they cannot.
+      double d[NS], ds = 0;
+#pragma unroll
+      for (int j = 0; j < NS; j++) { d[j] = (double)vb[j] * (double)va[j]; ds += d[j]; }
+      const double di = ds > 0 ? 1.0 / ds : 0.0;
+#pragma unroll
+      for (int j = 0; j < NS; j++) out[j] = (Real)(d[j] * di);
+      return;
+    }
     const Real inv = sum > (Real)0 ? fast_rcp<Real>(sum) : (Real)0;
 #pragma unroll
     for (int j = 0; j < NS; j++) out[j] *= inv;

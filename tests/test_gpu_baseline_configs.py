@@ -62,12 +62,13 @@ def test_config1_thousand_tips_ten_thousand_sites(oracle):
             assert abs(a.mean() - b.mean()) <= 0.01 * abs(b.mean()) + 4 * se, (what, name, a.mean(), b.mean(), se)
 
 
-def test_config2_squamate_hundred_thousand_sites():
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_config2_squamate_hundred_thousand_sites(precision):
     """The Squamate tree itself (3 951 tips, tree length 87 740; fixture derived from the package's .RData), the
     vignette's Q (Squamate_DIC_model_selection.Rnw:83), SPARSE sampler, 100 000 synthetic sites.
-    FP64 production arithmetic: with rates this slow on a tree this large a few sites in 1e5 have sister clades that each
-    settle their state beyond 1e-45, the range of an FP32 partial, and FP32 reports "Not enough positive probabilities"
-    (PM_ERR_SAMPLE) for them instead of drawing from a zero vector; FP64 has the reference's range."""
+    FP32 and FP64 production arithmetic.  With rates this slow on a tree this large a few sites in 1e5 have sister clades
+    that each all but settle a DIFFERENT state (1e-20 x 1e-20): the FP32 product underflows although both factors are
+    representable; the pruning kernel redoes such a node in double (round 1 reported PM_ERR_SAMPLE for them)."""
     Q = np.array([[-0.001, 0.001], [0.006, -0.006]])
     tree = cases.squamate_tree()
     S = 100000
@@ -77,7 +78,7 @@ def test_config2_squamate_hundred_thousand_sites():
     # Omega = 0.012 (0.13 jump points per branch) the gap to the direct sampler still shrinks by a third per 120 sweeps
     # after 400 sweeps.  Omega = 0.06 (0.66 per branch, ~5 300 jump points per site and sweep) mixes five times faster.
     Om = 0.06
-    mc = pb.SPARSEsumstatMCMC(z, Q, cases.PID2, Om, 300, precision="f64", seed=3)[230:]
+    mc = pb.SPARSEsumstatMCMC(z, Q, cases.PID2, Om, 300, precision=precision, seed=3)[230:]
     np.testing.assert_allclose(mc[:, :2].sum(1), S * tree.edge_length.sum(), rtol=2e-4)
     assert np.all(mc[:, 2:] >= 0) and np.array_equal(mc[:, 2:], np.round(mc[:, 2:]))
     ex = pb.sumstatEXP(z, Q, cases.PID2, 8, seed=9, precision="f64")
