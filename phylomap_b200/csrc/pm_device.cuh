@@ -226,9 +226,22 @@ template <> struct Pin<float> {
   static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
   // (w >> 9 + 1/2) 2^-23: exact in FP32 (24 significant bits), strictly inside (0, 1), one fused multiply-add
   static __device__ __forceinline__ float u01(uint32_t w) { return __fmaf_rn((float)(w >> 9), 1.0f / 8388608.0f, 1.0f / 16777216.0f); }
-  static __device__ __forceinline__ float expm(float x) { return __expf(-x); }  // ex2.approx: same bits everywhere
+  // exp(-x) for 0 <= x <= PM_LAMBDA_INV: ex2.approx of x * -log2(e), the two instructions __expf(-x) boils down to once
+  // its fix-up for results below 2^-126 is dropped (never needed here: the argument is >= -24); same bits everywhere
+  static __device__ __forceinline__ float expm(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(x, -1.4426950216293334961f)));
+    return r;
+  }
   static __device__ __forceinline__ float root(float u, int k) { return exp2f(__fdiv_rn(log2f(u), (float)k)); }
   static __device__ __forceinline__ float neglog(float u) { return -logf(u); }
+  static __device__ __forceinline__ int above3(float u, float a, float b, float c) {  // three set-on-compare, one 3-input add
+    unsigned x, y, z;
+    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(x) : "f"(u), "f"(a));
+    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(y) : "f"(u), "f"(b));
+    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(z) : "f"(u), "f"(c));
+    return -(int)(x + y + z);
+  }
 };
 template <> struct Pin<double> {
   static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
@@ -239,6 +252,7 @@ template <> struct Pin<double> {
   static __device__ __forceinline__ double expm(double x) { return exp(-x); }
   static __device__ __forceinline__ double root(double u, int k) { return exp2(__ddiv_rn(log2(u), (double)k)); }
   static __device__ __forceinline__ double neglog(double u) { return -log(u); }
+  static __device__ __forceinline__ int above3(double u, double a, double b, double c) { return (u > a ? 1 : 0) + (u > b ? 1 : 0) + (u > c ? 1 : 0); }
 };
 
 // number of Poisson(lam) events by inversion of the cdf.  p_k = p_{k-1} * lam * (1/k) with the reciprocal from a
@@ -260,7 +274,7 @@ __device__ __forceinline__ int poisson_inv(Real lam, uint32_t word) {
   const Real p1 = PN::mul(p0, lam);
   const Real p2 = PN::mul(PN::mul(p1, lam), (Real)0.5);
   const Real c1 = PN::add(p0, p1), c2 = PN::add(c1, p2);
-  int k = (u > p0 ? 1 : 0) + (u > c1 ? 1 : 0) + (u > c2 ? 1 : 0);
+  int k = Pin<Real>::above3(u, p0, c1, c2);  // (u > p0) + (u > c1) + (u > c2)
   if (k == 3) {  // ... then the general recurrence p_k = p_{k-1} * lam * (1/k)
     Real p = p2, c = c2;
     k = 2;

@@ -1111,6 +1111,7 @@ struct ChainT : pm_chain {
     return nj + 1;
   }
   // ---- checkpoint / resume: everything a sweep reads that is not an input of pm_chain_create ----
+  static constexpr uint32_t PM_STATE_FORMAT = 2;  // 1: round 1 (per-site masks); 2: branch-major ballots, global record cursors
   struct StateHeader {
     char magic[8];
     int32_t variant, n, ntrees, precision, mode, T, E, iters_done, jcap, reserved;
@@ -1138,6 +1139,14 @@ struct ChainT : pm_chain {
     h.variant = V.id; h.n = n; h.ntrees = ntrees; h.precision = opt.precision; h.mode = opt.mode;
     h.T = trees[0]->sch.T; h.E = trees[0]->sch.E; h.iters_done = iters_done; h.jcap = jcap;
     h.S = trees[0]->S; h.site_offset = opt.site_offset; h.total_bytes = state_bytes(); h.seed = opt.seed;
+    // format version and a hash of what fixes the interpretation of the buffers (the packing of `meta`, the record slices
+    // of every chunk, the count-mode threshold, the local path buffer): a blob written under another layout is refused
+    // instead of being read under this one
+    uint32_t hsh = 2166136261u;
+    auto mix = [&](uint32_t v) { hsh = (hsh ^ v) * 16777619u; };
+    mix(PM_STATE_FORMAT); mix(PM_META(1, 2, 3, 4)); mix(PM_LAMBDA_INV); mix(PM_LOCAL_PATH_MAX); mix(PM_SMEM_POW);
+    for (auto& t : trees) { mix((uint32_t)t->chunk); for (int c : t->cap_off_h) mix((uint32_t)c); }
+    h.reserved = (int32_t)((PM_STATE_FORMAT << 24) | (hsh & 0xffffffu));
     return h;
   }
   void export_state(void* buf, int64_t bytes) override {
@@ -1171,6 +1180,9 @@ struct ChainT : pm_chain {
         h.T != me.T || h.E != me.E || h.S != me.S || h.site_offset != me.site_offset || h.jcap != me.jcap || h.seed != me.seed ||
         h.total_bytes != me.total_bytes)
       fail(PM_ERR_ARG, "the state was exported by a chain of a different shape, sampler, precision, seed or site block");
+    if (h.reserved != me.reserved)
+      fail(PM_ERR_ARG, "the state was exported under another state format or buffer layout (format %d here, %d in the blob)",
+           (int)PM_STATE_FORMAT, (int)((uint32_t)h.reserved >> 24));
     if (bytes < h.total_bytes) fail(PM_ERR_ARG, "truncated chain state");
     if (h.iters_done < 0 || h.iters_done > N_total) fail(PM_ERR_ARG, "the state has %d iterations done, this chain was created for %d", h.iters_done, N_total);
     CK(cudaSetDevice(opt.device));

@@ -1130,11 +1130,24 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
   Real Racc[NR]; double Rsum[NR];
 #pragma unroll
   for (int j = 0; j < NR; j++) { Racc[j] = 0; Rsum[j] = 0; }
+  // dwell of state s: Racc += e_s * L with the unit vector e_s read from shared memory (one vector load + NS fused
+  // multiply-adds; fma(1, L, acc) = acc + L and fma(0, L, acc) = acc exactly) instead of NS compare / select / add triples
+  __shared__ __align__(16) Real s_unit[NR][NR];
+  if (NS > 0 && (int)threadIdx.x < NR * NR) s_unit[threadIdx.x / NR][threadIdx.x % NR] = (threadIdx.x / NR == threadIdx.x % NR) ? (Real)1 : (Real)0;
+  __syncthreads();
   auto add_dwell = [&](int s, Real L) {
     if (NS > 0) {
+      Real u[NR];
+      VecIO<Real, NS>::load(&s_unit[s][0], NS, u);
 #pragma unroll
-      for (int j = 0; j < NR; j++) Racc[j] += (s == j) ? L : (Real)0;
+      for (int j = 0; j < NR; j++) Racc[j] = fma(u[j], L, Racc[j]);
     } else atomicAdd(&s_dw[s], (double)L);
+  };
+  auto flush_dwell = [&]() {
+    if (NS > 0) {
+#pragma unroll
+      for (int j = 0; j < NR; j++) { Rsum[j] += (double)Racc[j]; Racc[j] = 0; }
+    }
   };
   // two-deep software pipeline: jump count and node states of branch i + 2, then pos1 of branch i + 1 if it has a
   // jump point.  Two branches per loop trip -- the pair (2j, 2j + 1) that shares a Philox block -- with the two register
@@ -1187,12 +1200,6 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
     const unsigned bal = __ballot_sync(0xffffffffu, hard && active);
     if (bal_writer) *bal_p = bal;
     bal_p += Wu;
-    if ((i & 31) == 31 || i == nb - 1) {
-      if (NS > 0) {
-#pragma unroll
-        for (int j = 0; j < NR; j++) { Rsum[j] += (double)Racc[j]; Racc[j] = 0; }
-      }
-    }
   };
   int i = 0;
   if (nb > 0 && (e0 & 1)) {  // the chunk opens on the second branch of a pair: on its own, unpipelined
@@ -1203,11 +1210,16 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
   }
   if (i < nb) { fetch(i, X); if ((X.mt & 0xffffu) == 2u) X.p1 = pos1_p[0]; }
   if (i + 1 < nb) fetch(i + 1, Y);
-  for (; i + 1 < nb; i += 2) {
-    step(i, std::false_type(), std::true_type(), X, Y);
-    step(i + 1, std::true_type(), std::true_type(), Y, X);
+  while (i + 1 < nb) {  // 32 pairs, then the FP32 dwell sums of the stretch go to the double accumulators
+    const int stop = min(nb - 1, i + 64);
+    for (; i + 1 <= stop; i += 2) {
+      step(i, std::false_type(), std::true_type(), X, Y);
+      step(i + 1, std::true_type(), std::true_type(), Y, X);
+    }
+    flush_dwell();
   }
   if (i < nb) step(i, std::false_type(), std::true_type(), X, Y);
+  flush_dwell();
   if (NS > 0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll

@@ -309,6 +309,13 @@ def test_checkpoint_resume_continues_bit_for_bit(what):
     np.testing.assert_array_equal(np.array(b.B), B_cut)
     tail = b.run(N - cut)
     np.testing.assert_array_equal(np.vstack([head, tail]), full)
+    # a blob written under another state format / buffer layout is refused, not reinterpreted (header word 10)
+    other = blob.copy()
+    other[8 + 4 * 9: 8 + 4 * 10] = np.frombuffer(np.int32(0x01abcdef).tobytes(), dtype=np.uint8)
+    c = mk(np.asfortranarray(Q.copy()))
+    with pytest.raises(capi.PhylomapError) as ei:
+        c.import_state(other)
+    assert ei.value.code == capi.PM_ERR_ARG and "format" in str(ei.value)
     # a state of another shape is refused
     other = pb.Chain(capi.PM_V_BIGTREE, cases.tree_n(cases.q4(), T=10, S=2, seed=1), np.asfortranarray(cases.q4()), np.full(4, 0.25), 2.4, 3)
     with pytest.raises(capi.PhylomapError) as ei:
