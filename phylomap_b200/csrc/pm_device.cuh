@@ -233,7 +233,13 @@ template <> struct Pin<float> {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(x, -1.4426950216293334961f)));
     return r;
   }
-  static __device__ __forceinline__ float root(float u, int k) { return exp2f(__fdiv_rn(log2f(u), (float)k)); }
+  // u^(1/k), 0 < u < 1: lg2.approx / ex2.approx (relative error ~1e-6: it places a jump on its run, nothing compares it)
+  static __device__ __forceinline__ float root(float u, int k) {
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fdiv_rn(l, (float)k)));
+    return r;
+  }
   static __device__ __forceinline__ float neglog(float u) { return -logf(u); }
   static __device__ __forceinline__ int above3(float u, float a, float b, float c) {  // three set-on-compare, one 3-input add
     unsigned x, y, z;

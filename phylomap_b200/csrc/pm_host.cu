@@ -1111,7 +1111,7 @@ struct ChainT : pm_chain {
     return nj + 1;
   }
   // ---- checkpoint / resume: everything a sweep reads that is not an input of pm_chain_create ----
-  static constexpr uint32_t PM_STATE_FORMAT = 2;  // 1: round 1 (per-site masks); 2: branch-major ballots, global record cursors
+  static constexpr uint32_t PM_STATE_FORMAT = 3;  // 1: round 1 (per-site masks); 2: branch-major ballots, global record cursors; 3: two-run paths count their virtual jumps together
   struct StateHeader {
     char magic[8];
     int32_t variant, n, ntrees, precision, mode, T, E, iters_done, jcap, reserved;

@@ -1090,8 +1090,12 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
 template <typename Real>
 __device__ __forceinline__ bool rate_ok(Real r) { return isfinite(r) && r > (Real)0; }
 
+__device__ __forceinline__ float lds_real(unsigned a, float) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double lds_real(unsigned a, double) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 template <typename Real, int NS>
-__global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_t iter, int chunk) {
+__global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy(ChainParams<Real> P, uint32_t iter, int chunk) {
   constexpr int NR = NS > 0 ? NS : 1;
   typedef Pin<Real> PN;
   const int n = NS > 0 ? NS : P.n;
@@ -1103,6 +1107,9 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
   int* s_par = reinterpret_cast<int*>(s_rate + n + (n & 1));
   int* s_chi = s_par + chunk;
   Real* s_len = reinterpret_cast<Real*>(s_chi + chunk);
+  // dwell of state s: Racc += e_s * L with the unit vector e_s read from shared memory (one vector load + NS fused
+  // multiply-adds; fma(1, L, acc) = acc + L and fma(0, L, acc) = acc exactly) instead of NS compare / select / add triples
+  __shared__ __align__(16) Real s_unit[NR][NR];
   const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
   for (int i = threadIdx.x; i < n * n; i += blockDim.x) s_cnt[i] = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {  // a state without a valid rate draws no virtual jumps
@@ -1113,12 +1120,15 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
   for (int i = threadIdx.x; i < e1 - e0; i += blockDim.x) {
     s_par[i] = P.e_parent[e0 + i]; s_chi[i] = P.e_child[e0 + i]; s_len[i] = P.e_len[e0 + i];
   }
+  if (NS > 0 && (int)threadIdx.x < NR * NR) s_unit[threadIdx.x / NR][threadIdx.x % NR] = (threadIdx.x / NR == threadIdx.x % NR) ? (Real)1 : (Real)0;
   __syncthreads();
+  // 32-bit shared-memory addresses, formed once (generic pointers would be converted again at every access)
+  const unsigned a_par = smem_addr(s_par), a_chi = smem_addr(s_chi), a_len = smem_addr(s_len), a_rate = smem_addr(s_rate),
+                 a_unit = smem_addr(&s_unit[0][0]);
   const long long S = P.S;
   const uint32_t Su = (uint32_t)S;  // S < 2^31 (checked by the host): 32 x 32 -> 64-bit offsets are one instruction
   const long long site_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = site_raw < S;
-  const long long site = active ? site_raw : S - 1;
+  const long long site = site_raw < S ? site_raw : S - 1;
   const bool full = P.full_counts != 0;
   const long long wglob = site_raw >> 5;  // ballot word of this warp (the same for its 32 lanes)
   uint32_t* __restrict__ bal_p = P.hard_ballot + (long long)e0 * P.W + wglob;
@@ -1130,18 +1140,13 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
   Real Racc[NR]; double Rsum[NR];
 #pragma unroll
   for (int j = 0; j < NR; j++) { Racc[j] = 0; Rsum[j] = 0; }
-  // dwell of state s: Racc += e_s * L with the unit vector e_s read from shared memory (one vector load + NS fused
-  // multiply-adds; fma(1, L, acc) = acc + L and fma(0, L, acc) = acc exactly) instead of NS compare / select / add triples
-  __shared__ __align__(16) Real s_unit[NR][NR];
-  if (NS > 0 && (int)threadIdx.x < NR * NR) s_unit[threadIdx.x / NR][threadIdx.x % NR] = (threadIdx.x / NR == threadIdx.x % NR) ? (Real)1 : (Real)0;
-  __syncthreads();
   auto add_dwell = [&](int s, Real L) {
     if (NS > 0) {
       Real u[NR];
-      VecIO<Real, NS>::load(&s_unit[s][0], NS, u);
+      lds_vec<Real, NS>(a_unit + (unsigned)s * (unsigned)(NR * sizeof(Real)), u);
 #pragma unroll
       for (int j = 0; j < NR; j++) Racc[j] = fma(u[j], L, Racc[j]);
-    } else atomicAdd(&s_dw[s], (double)L);
+    } else if (L != (Real)0) atomicAdd(&s_dw[s], (double)L);
   };
   auto flush_dwell = [&]() {
     if (NS > 0) {
@@ -1158,68 +1163,80 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
   const uint32_t* meta_f = meta_p;  // fetch cursor (runs ahead of the store cursor)
   auto fetch = [&](int i, Ahead& a) {
     a.mt = *meta_f; meta_f += Su;
-    a.ps = nstate[(uint64_t)(uint32_t)s_par[i] * Su];
-    a.cs = nstate[(uint64_t)(uint32_t)s_chi[i] * Su];
+    a.ps = nstate[(uint64_t)(uint32_t)lds_s32(a_par + 4u * (unsigned)i) * Su];
+    a.cs = nstate[(uint64_t)(uint32_t)lds_s32(a_chi + 4u * (unsigned)i) * Su];
   };
   uint32_t po[4] = {0, 0, 0, 0};
   // one branch: `cur` holds what was fetched for it; with PIPE, `nxt` (branch i + 1) gets its pos1 and `cur` is refilled
-  // with branch i + 2.  ODD: second branch of its Philox pair (the block was drawn by the first, or here if it opens the chunk).
-  auto step = [&](int i, auto odd_c, auto pipe_c, Ahead& cur, Ahead& nxt) {
-    constexpr bool ODD = decltype(odd_c)::value, PIPE = decltype(pipe_c)::value;
+  // with branch i + 2 (GUARD: only if those branches exist -- the steady-state loop knows they do).  ODD: second branch
+  // of its Philox pair (the block was drawn by the first, or here if it opens the chunk).  TAIL: the block may hold
+  // sites past the end.  Straight-line code: lanes that leave their branch to the general kernels compute along and
+  // contribute zeros; only the stores are predicated.
+  auto step = [&](int i, auto odd_c, auto pipe_c, auto guard_c, auto tail_c, Ahead& cur, Ahead& nxt) {
+    constexpr bool ODD = decltype(odd_c)::value, PIPE = decltype(pipe_c)::value, GUARD = decltype(guard_c)::value,
+                   TAIL = decltype(tail_c)::value;
     const int e = e0 + i;
     const uint32_t mt = cur.mt; const int ps = cur.ps, cs = cur.cs; const Real p1 = cur.p1;
     if (PIPE) {
-      if (i + 1 < nb && (nxt.mt & 0xffffu) == 2u) nxt.p1 = pos1_p[Su];
-      if (i + 2 < nb) fetch(i + 2, cur);
+      if ((!GUARD || i + 1 < nb) && (nxt.mt & 0xffffu) == 2u) nxt.p1 = pos1_p[Su];
+      if (!GUARD || i + 2 < nb) fetch(i + 2, cur);
     }
     if (!ODD || !PIPE) pair_block(P.rng, (uint32_t)site, iter, (uint32_t)e, po);
     const uint32_t wA = ODD ? po[2] : po[0], wB = ODD ? po[3] : po[1];
     const int m = (int)(mt & 0xffffu);
-    const Real Le = s_len[i];
-    // pieces: (Le) or (p1, Le - p1); states ps | cs (a one-piece branch carries the child state, :460-475)
+    const Real Le = lds_real(a_len + (unsigned)sizeof(Real) * (unsigned)i, (Real)0);
+    // pieces: (Le) or (p1, Le - p1); states ps | cs (a one-piece branch carries the child state, :460-475).  The
+    // virtual jumps of a two-run path are counted together: K ~ Poisson(lam0 + lam1) from the A word (their positions,
+    // if a later sweep needs them, are regenerated by the general kernels, see RunPieces)
     const bool two = (m == 2) && (ps != cs);
     const Real L0 = two ? p1 : Le;
     const int s0 = two ? ps : cs;
-    const Real lam0 = PN::mul(s_rate[s0], L0);                       // rates are clamped to >= 0 when staged
-    const Real L1 = PN::sub(Le, p1);
-    const Real lam1 = two ? PN::mul(s_rate[cs], L1) : (Real)0;
-    const bool hard = (m > 2) || lam0 > (Real)PM_LAMBDA_INV || lam1 > (Real)PM_LAMBDA_INV;
-    const int k0 = poisson_inv<Real>(lam0, wA);
-    const int k1 = two ? poisson_inv<Real>(lam1, wB) : 0;
-    if (!hard && active) {
-      if (m == 2 && (full || two)) atomicAdd(&s_cnt[ps * n + cs], 1u);
-      add_dwell(s0, L0);
-      if (two) add_dwell(cs, L1);
-      const int newm = (two ? 2 : 1) + k0 + k1;
-      // a path that ends up with a single jump point keeps that point in pos1: the real jump stays where it was;
-      // a lone new virtual jump gets its position now
-      if (!two && k0 == 1) *pos1_p = next_order_stat<Real>((Real)0, Le, 1, wB);
-      *meta_p = PM_META(newm, two ? 1 : 0, s0, cs);
-    }
+    const Real L1 = two ? PN::sub(Le, p1) : (Real)0;
+    // rates are clamped to >= 0 when staged; x + 0 = x: a single run has lam = rate * t_e exactly
+    const Real lam = PN::add(PN::mul(lds_real(a_rate + (unsigned)sizeof(Real) * (unsigned)s0, (Real)0), L0),
+                             PN::mul(lds_real(a_rate + (unsigned)sizeof(Real) * (unsigned)cs, (Real)0), L1));
+    const bool hard = (m > 2) || lam > (Real)PM_LAMBDA_INV;
+    const bool ok = TAIL ? (!hard && site_raw < S) : !hard;
+    const int k = poisson_inv<Real>(lam, wA);
+    if (ok && m == 2 && (full || two)) atomicAdd(&s_cnt[ps * n + cs], 1u);
+    add_dwell(s0, ok ? L0 : (Real)0);
+    add_dwell(cs, ok ? L1 : (Real)0);
+    // a path that ends up with a single jump point keeps that point in pos1: the real jump stays where it was;
+    // a lone new virtual jump gets its position now
+    if (ok && !two && k == 1) *pos1_p = next_order_stat<Real>((Real)0, Le, 1, wB);
+    if (ok) *meta_p = PM_META((two ? 2 : 1) + k, two ? 1 : 0, s0, cs);
     meta_p += Su; pos1_p += Su;
-    const unsigned bal = __ballot_sync(0xffffffffu, hard && active);
+    const unsigned bal = __ballot_sync(0xffffffffu, TAIL ? (hard && site_raw < S) : hard);
     if (bal_writer) *bal_p = bal;
     bal_p += Wu;
   };
-  int i = 0;
-  if (nb > 0 && (e0 & 1)) {  // the chunk opens on the second branch of a pair: on its own, unpipelined
-    fetch(0, X);
-    if ((X.mt & 0xffffu) == 2u) X.p1 = pos1_p[0];
-    step(0, std::true_type(), std::false_type(), X, Y);
-    i = 1;
-  }
-  if (i < nb) { fetch(i, X); if ((X.mt & 0xffffu) == 2u) X.p1 = pos1_p[0]; }
-  if (i + 1 < nb) fetch(i + 1, Y);
-  while (i + 1 < nb) {  // 32 pairs, then the FP32 dwell sums of the stretch go to the double accumulators
-    const int stop = min(nb - 1, i + 64);
-    for (; i + 1 <= stop; i += 2) {
-      step(i, std::false_type(), std::true_type(), X, Y);
-      step(i + 1, std::true_type(), std::true_type(), Y, X);
+  auto run = [&](auto tail_c) {
+    const std::true_type T{}; const std::false_type F{};
+    int i = 0;
+    if (nb > 0 && (e0 & 1)) {  // the chunk opens on the second branch of a pair: on its own, unpipelined
+      fetch(0, X);
+      if ((X.mt & 0xffffu) == 2u) X.p1 = pos1_p[0];
+      step(0, T, F, T, tail_c, X, Y);
+      i = 1;
     }
+    if (i < nb) { fetch(i, X); if ((X.mt & 0xffffu) == 2u) X.p1 = pos1_p[0]; }
+    if (i + 1 < nb) fetch(i + 1, Y);
+    while (i + 3 < nb) {  // 32 pairs, then the FP32 dwell sums of the stretch go to the double accumulators
+      const int stop = min(nb - 4, i + 62);
+      for (; i <= stop; i += 2) {
+        step(i, F, T, F, tail_c, X, Y);
+        step(i + 1, T, T, F, tail_c, Y, X);
+      }
+      flush_dwell();
+    }
+    for (; i + 1 < nb; i += 2) {  // the last pair(s): nothing, or not everything, left to prefetch
+      step(i, F, T, T, tail_c, X, Y);
+      step(i + 1, T, T, T, tail_c, Y, X);
+    }
+    if (i < nb) step(i, F, T, T, tail_c, X, Y);
     flush_dwell();
-  }
-  if (i < nb) step(i, std::false_type(), std::true_type(), X, Y);
-  flush_dwell();
+  };
+  if ((long long)(blockIdx.x + 1) * blockDim.x <= S) run(std::false_type()); else run(std::true_type());
   if (NS > 0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -1241,26 +1258,62 @@ __global__ void __launch_bounds__(128) k_paths_easy(ChainParams<Real> P, uint32_
   for (int i = threadIdx.x; i < n * n; i += blockDim.x) if (s_cnt[i]) atomicAdd(&P.cnt[i], (unsigned long long)s_cnt[i]);
 }
 
+// rate of the virtual jumps in a state, 0 where the model has none (a state without a valid rate draws no virtual jumps)
+template <typename Real>
+__device__ __forceinline__ Real rate_or_zero(Real r) { return rate_ok(r) ? r : (Real)0; }
+
 // The pieces of one run of the previous path, in order (regenerated, never stored).
+// Joint mode: a two-run path (one real jump, at p1) whose virtual jumps were COUNTED TOGETHER -- K ~ Poisson(lam0 + lam1)
+// from one uniform (pm_device.cuh).  Their positions are K independent draws from the piecewise-constant intensity,
+// generated in increasing order: order statistics v_1 < ... < v_K of uniforms on (0, 1), v < q = lam0 / (lam0 + lam1)
+// falls on run 0 at v * (lamT / r0), the rest on run 1 at (v - q) * (lamT / r1) past the real jump.  By the splitting
+// property of the Poisson process this is the law of two independent Poisson(lam_i) sets of uniform positions.
 template <typename Real>
 struct RunPieces {
-  Real L, x, rate;
+  Real L, x, rate;  // joint mode: `rate` holds q, the share of run 0 in the branch's intensity
   int left;       // count mode: jumps not yet emitted
   bool gaps;      // lambda > PM_LAMBDA_INV
-  bool firstB;    // the first position uniform is the pair block's B word (single-run path)
+  bool firstB;    // the first position uniform is the pair block's B word (single-run path, joint two-run path)
   uint32_t wB;
   WordStream ws;  // positions (count mode) or gaps
+  bool joint, pend, run0;
+  Real v, sc;     // joint mode: last order statistic drawn on (0, 1); branch length per unit of v on the current run
   __device__ __forceinline__ void begin(const RngDesc& d, uint32_t site, uint32_t it, uint32_t e, int run, Real len, Real r,
                                        uint32_t cnt_word, bool single_run, uint32_t wordB) {
-    L = len; x = 0; rate = r; left = 0; gaps = false; firstB = single_run; wB = wordB;
+    L = len; x = 0; rate = r; left = 0; gaps = false; firstB = single_run; wB = wordB; joint = false;
     if (!rate_ok(r)) return;
     const Real lam = Pin<Real>::mul(r, len);
     if (lam > (Real)PM_LAMBDA_INV) { gaps = true; ws.open(d, site, it, K_BRGAP, e, (uint32_t)run); }
     else { left = poisson_inv<Real>(lam, cnt_word); ws.open(d, site, it, K_BRPOS, e, (uint32_t)run); }
   }
+  // joint mode, run 0 of length len0 and (clamped) rate r0; K virtual jumps on the whole branch
+  __device__ __forceinline__ void begin_joint(const RngDesc& d, uint32_t site, uint32_t it, uint32_t e, Real len0, int K, Real lam0,
+                                             Real lamT, Real r0, uint32_t wordB) {
+    typedef Pin<Real> PN;
+    L = len0; x = 0; left = K; gaps = false; firstB = true; wB = wordB; joint = true; pend = false; run0 = true;
+    v = 0; rate = PN::div(lam0, lamT); sc = PN::div(lamT, r0);
+    ws.open(d, site, it, K_BRPOS, e, 0u);
+  }
+  __device__ __forceinline__ void second_run(Real len1, Real lamT, Real r1) { L = len1; x = 0; run0 = false; sc = Pin<Real>::div(lamT, r1); }
   // returns the next piece; `last` tells whether it closes the run
   __device__ __forceinline__ Real next(bool& last) {
     typedef Pin<Real> PN;
+    if (joint) {
+      if (!pend && left > 0) {
+        uint32_t w;
+        if (firstB) { w = wB; firstB = false; } else w = ws.next();
+        v = next_order_stat<Real>(v, (Real)1, left, w);
+        left--; pend = true;
+      }
+      if (pend && (!run0 || v < rate)) {
+        const Real t2 = min(PN::mul(run0 ? v : PN::sub(v, rate), sc), L);
+        const Real piece = max(PN::sub(t2, x), (Real)0);
+        x = max(t2, x); pend = false; last = false;
+        return piece;
+      }
+      last = true;
+      return PN::sub(L, x);
+    }
     if (gaps) {
       const Real g = PN::div(PN::neglog(PN::u01(ws.next())), rate);
       const Real t2 = PN::add(x, g);
@@ -1280,6 +1333,23 @@ struct RunPieces {
     return PN::sub(L, x);
   }
 };
+
+// number of exponential gaps of the given rate that fit into a run of length L (a run too long for the count mode);
+// *first = the first gap.  Rare: kept out of line.
+template <typename Real>
+__device__ __noinline__ int count_gaps(RngDesc d, uint32_t site, uint32_t it, uint32_t e, uint32_t run, Real L, Real rate, Real* first) {
+  typedef Pin<Real> PN;
+  WordStream g; g.open(d, site, it, K_BRGAP, e, run);
+  Real x = 0; int k = 0;
+  for (;;) {
+    const Real gp = PN::div(PN::neglog(PN::u01(g.next())), rate);
+    const Real t2 = PN::add(x, gp);
+    if (!(t2 < L) || k > 70000) break;
+    x = t2; k++;
+    if (k == 1) *first = gp;
+  }
+  return k;
+}
 
 // One (site, branch) item of the general path kernel, as queued per warp: everything the item reads from the sweep's
 // state is fetched when it is queued (four independent loads per lane in flight), so that processing it later waits
@@ -1356,78 +1426,71 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     const uint32_t gsite = P.rng.site0 + (uint32_t)site;
     uint32_t po_old[4], po_new[4];
     pair_block(P.rng, (uint32_t)site, iter, (uint32_t)eb, po_new);
-    pair_block(P.rng, (uint32_t)site, iter - 1u, (uint32_t)eb, po_old);
-    const uint32_t oA = (eb & 1) ? po_old[2] : po_old[0], oB = (eb & 1) ? po_old[3] : po_old[1];
+    if (nj < 2) pair_block(P.rng, (uint32_t)site, iter - 1u, (uint32_t)eb, po_old);
     const uint32_t nA = (eb & 1) ? po_new[2] : po_new[0], nB = (eb & 1) ? po_new[3] : po_new[1];
-    // ---- the m pieces of the previous path: up to three on each of its (one or two) runs
-    Real r0[3] = {0, 0, 0}, r1[3] = {0, 0, 0};
-    int k0o, k1o = 0;
-    const Real p1 = nj == 0 ? Le : it.p1;          // length of run 0
-    const Real L1r = PN::sub(Le, p1);              // length of run 1 (nj == 1)
-    k0o = poisson_inv<Real>(PN::mul(s_rate_old[so0], p1), oA);
-    if (nj == 1) k1o = poisson_inv<Real>(PN::mul(s_rate_old[so1], L1r), oB);
-    if (k0o + k1o != m - 1 - nj || k0o > 3 || k1o > 2) { errbits |= PM_DE_INCONSISTENT; k0o = min(k0o, 3); k1o = min(k1o, 2); }
-    {
-      // run 0: a single-run path takes its first position word from the pair block, the others from the K_BRPOS stream
-      const bool firstB = nj == 0;
+    // ---- the m - 1 jump points of the previous path, in order.  nj <= 1: K = m - 1 - nj virtual ones (one to three) and,
+    // if nj == 1, the real one at p1.  The virtual ones are order statistics of K uniforms on (0, 1) -- words: the pair
+    // block's B, then the (K_BRPOS, e; run 0) block -- mapped through the inverse of the normalised intensity: all of
+    // (0, 1) onto the single run, or (0, q) onto run 0 and (q, 1) onto run 1 (joint count, see RunPieces).
+    // nj == m - 1 (two or three real jumps, no virtual one): the path's records.
+    Real J0, J1, J2;
+    if (nj >= 2) {
+      const int ck = eb / P.chunk;
+      const int cap0 = __ldg(P.cap_off + ck), cap_c = __ldg(P.cap_off + ck + 1) - cap0;
+      const long long sl = (long long)cap0 * S + site * (long long)cap_c;
+      const int rd0 = (int)it.p1;
+      J0 = rd_len[sl + min(rd0, cap_c - 1)];
+      J1 = PN::add(J0, rd_len[sl + min(rd0 + 1, cap_c - 1)]);
+      J2 = m == 4 ? PN::add(J1, rd_len[sl + min(rd0 + 2, cap_c - 1)]) : J1;
+    } else {
+      const int K = m - 1 - nj;
+      const Real p1 = nj == 0 ? Le : it.p1;          // length of run 0
+      const Real L1r = PN::sub(Le, p1);              // length of run 1 (nj == 1)
+      Real qq = (Real)2, sc0 = Le, sc1 = 0;
+      if (nj == 1) {
+        const Real ro0 = rate_or_zero(s_rate_old[so0]), ro1 = rate_or_zero(s_rate_old[so1]);
+        const Real lam0 = PN::mul(ro0, p1), lamT = PN::add(lam0, PN::mul(ro1, L1r));
+        qq = PN::div(lam0, lamT); sc0 = PN::div(lamT, ro0); sc1 = PN::div(lamT, ro1);
+      }
+      const uint32_t oB = (eb & 1) ? po_old[3] : po_old[1];
       uint32_t pw[4] = {0, 0, 0, 0};
-      if (k0o > (firstB ? 1 : 0)) philox4x32_10(0u, make_slot(K_BRPOS, (uint32_t)eb), iter - 1u, gsite, P.rng.k0, P.rng.k1, pw);
-      Real x = 0;
+      if (K > 1) philox4x32_10(0u, make_slot(K_BRPOS, (uint32_t)eb), iter - 1u, gsite, P.rng.k0, P.rng.k1, pw);
+      Real vt0 = 0, vt1 = 0, vt2 = 0;
+      int k0o = 0;  // virtual jumps on run 0
+      {
+        Real v = 0;
 #pragma unroll
-      for (int q = 0; q < 3; q++) {
-        if (q < k0o) {
-          const uint32_t w = firstB ? (q == 0 ? oB : pw[q - 1 < 0 ? 0 : q - 1]) : pw[q];
-          const Real t2 = next_order_stat<Real>(x, p1, k0o - q, w);
-          const Real piece = PN::sub(t2, x);
-          x = t2;
-          if (q == 0) r0[0] = piece; else if (q == 1) r0[1] = piece; else r0[2] = piece;
+        for (int j = 0; j < 3; j++) {
+          if (j < K) {
+            v = next_order_stat<Real>(v, (Real)1, K - j, j == 0 ? oB : pw[j - 1 < 0 ? 0 : j - 1]);
+            const bool on0 = v < qq;
+            const Real t = on0 ? min(PN::mul(v, sc0), p1) : PN::add(p1, min(PN::mul(PN::sub(v, qq), sc1), L1r));
+            k0o += on0 ? 1 : 0;
+            if (j == 0) vt0 = t; else if (j == 1) vt1 = t; else vt2 = t;
+          }
         }
       }
-      const Real lastp = PN::sub(p1, x);
-      if (k0o == 0) r0[0] = lastp; else if (k0o == 1) r0[1] = lastp; else if (k0o == 2) r0[2] = lastp;
-      // (k0o == 3: m == 4, nj == 0 -- the fourth piece is kept in r1[0])
-      if (k0o == 3) r1[0] = lastp;
-    }
-    if (nj == 1) {
-      uint32_t pw[4] = {0, 0, 0, 0};
-      if (k1o > 0) philox4x32_10(1u << 20, make_slot(K_BRPOS, (uint32_t)eb), iter - 1u, gsite, P.rng.k0, P.rng.k1, pw);
-      Real x = 0;
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        if (q < k1o) {
-          const Real t2 = next_order_stat<Real>(x, L1r, k1o - q, pw[q]);
-          const Real piece = PN::sub(t2, x);
-          x = t2;
-          if (q == 0) r1[0] = piece; else r1[1] = piece;
-        }
+      // the jump points with the real one in its place (after the k0o virtual jumps of run 0)
+      J0 = vt0; J1 = vt1; J2 = vt2;
+      if (nj == 1) {
+        J2 = k0o == 2 ? p1 : vt1;
+        J1 = k0o == 0 ? vt0 : k0o == 1 ? p1 : vt1;
+        J0 = k0o == 0 ? p1 : vt0;
       }
-      const Real lastp = PN::sub(L1r, x);
-      if (k1o == 0) r1[0] = lastp; else if (k1o == 1) r1[1] = lastp; else r1[2] = lastp;
     }
-    // piece j of the path: the pieces of run 0 (k0o + 1 of them, at most three kept in r0), then those of run 1
-    const int n0 = min(k0o + 1, 3);
+    // piece j of the path lies between jump points j - 1 and j (0 and Le at the ends); m = 3 or 4
     auto piece_len = [&](int jx) -> Real {
-      const int t = jx - n0;
-      return jx < n0 ? (jx == 0 ? r0[0] : jx == 1 ? r0[1] : r0[2]) : (t == 0 ? r1[0] : t == 1 ? r1[1] : r1[2]);
+      const Real hi = jx == 0 ? J0 : jx == 1 ? J1 : (jx == 2 && m == 4) ? J2 : Le;
+      const Real lo = jx == 0 ? (Real)0 : jx == 1 ? J0 : jx == 2 ? J1 : J2;
+      return PN::sub(hi, lo);
     };
     // ---- the new path ----
-    int nout = 0, newm = 0, S0 = 0, S1 = 0, S2 = 0, S3 = 0, k0n = 0;
+    int nout = 0, S0 = 0, S1 = 0, S2 = 0, S3 = 0;
     Real L0 = 0, L1 = 0, L2 = 0, L3 = 0;
-    uint32_t cw[4] = {0, 0, 0, 0};
-    bool have_cw = false;
     auto emit = [&](Real L, int sst) {
       const int r = nout;
       if (r == 0) { L0 = L; S0 = sst; } else if (r == 1) { L1 = L; S1 = sst; } else if (r == 2) { L2 = L; S2 = sst; } else { L3 = L; S3 = sst; }
       add_dwell(sst, L);
-      if (r >= 2 && !have_cw) {
-        philox4x32_10(0u, make_slot(K_BRCNT, (uint32_t)eb), iter, gsite, P.rng.k0, P.rng.k1, cw);
-        have_cw = true;
-      }
-      const uint32_t w = r == 0 ? nA : r == 1 ? nB : r == 2 ? cw[0] : cw[1];
-      const Real rate = s_rate_new[sst];
-      const int k = rate_ok(rate) ? poisson_inv<Real>(PN::mul(rate, L), w) : 0;
-      if (r == 0) k0n = k;
-      newm += k + 1;
       nout++;
     };
     Stream gst; gst.open(P.rng, (uint32_t)site, iter, K_BRSTATE, (uint32_t)eb, P.err_flag);
@@ -1458,20 +1521,38 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       }
     }
     emit(nout == 0 ? Le : nout == 1 ? PN::sub(Le, L0) : cur_len, cur_state);
-    if (nout == 1) { if (k0n == 1) P.pos1[pe] = next_order_stat<Real>((Real)0, Le, 1, nB); }
-    else if (nout == 2) P.pos1[pe] = L0;
-    else {
-      const int ck = eb / P.chunk;
-      const int cap0 = __ldg(P.cap_off + ck), cap_c = __ldg(P.cap_off + ck + 1) - cap0;
-      const long long sl = (long long)cap0 * S + site * (long long)cap_c;
-      const int base = atomicAdd(P.rec_cursor + (long long)ck * S + site, nout);
-      P.pos1[pe] = (Real)base;
-      if (base + nout > cap_c) errbits |= PM_DE_PATH_CAP;
-      else {
-        wr_len[sl + base] = L0; wr_st[sl + base] = (uint8_t)S0;
-        wr_len[sl + base + 1] = L1; wr_st[sl + base + 1] = (uint8_t)S1;
-        wr_len[sl + base + 2] = L2; wr_st[sl + base + 2] = (uint8_t)S2;
-        if (nout == 4) { wr_len[sl + base + 3] = L3; wr_st[sl + base + 3] = (uint8_t)S3; }
+    // ---- the new virtual jumps: one run, or two runs counted together, from the pair block's A word; three or four
+    // runs one by one (A, B, then the K_BRCNT block).  lam <= rate_max t_e < PM_LAMBDA_INV here: always count mode
+    int newm = nout;
+    const Real rn0 = rate_or_zero(s_rate_new[S0]);
+    if (nout == 1) {
+      const int k0n = poisson_inv<Real>(PN::mul(rn0, L0), nA);
+      newm += k0n;
+      if (k0n == 1) P.pos1[pe] = next_order_stat<Real>((Real)0, Le, 1, nB);
+    } else {
+      const Real rn1 = rate_or_zero(s_rate_new[S1]);
+      const Real lam0 = PN::mul(rn0, L0), lam1 = PN::mul(rn1, L1);
+      if (nout == 2) {
+        newm += poisson_inv<Real>(PN::add(lam0, lam1), nA);
+        P.pos1[pe] = L0;
+      } else {
+        uint32_t cw[4];
+        philox4x32_10(0u, make_slot(K_BRCNT, (uint32_t)eb), iter, gsite, P.rng.k0, P.rng.k1, cw);
+        newm += poisson_inv<Real>(lam0, nA) + poisson_inv<Real>(lam1, nB) +
+                poisson_inv<Real>(PN::mul(rate_or_zero(s_rate_new[S2]), L2), cw[0]);
+        if (nout == 4) newm += poisson_inv<Real>(PN::mul(rate_or_zero(s_rate_new[S3]), L3), cw[1]);
+        const int ck = eb / P.chunk;
+        const int cap0 = __ldg(P.cap_off + ck), cap_c = __ldg(P.cap_off + ck + 1) - cap0;
+        const long long sl = (long long)cap0 * S + site * (long long)cap_c;
+        const int base = atomicAdd(P.rec_cursor + (long long)ck * S + site, nout);
+        P.pos1[pe] = (Real)base;
+        if (base + nout > cap_c) errbits |= PM_DE_PATH_CAP;
+        else {
+          wr_len[sl + base] = L0; wr_st[sl + base] = (uint8_t)S0;
+          wr_len[sl + base + 1] = L1; wr_st[sl + base + 1] = (uint8_t)S1;
+          wr_len[sl + base + 2] = L2; wr_st[sl + base + 2] = (uint8_t)S2;
+          if (nout == 4) { wr_len[sl + base + 3] = L3; wr_st[sl + base + 3] = (uint8_t)S3; }
+        }
       }
     }
     P.meta[pe] = PM_META(newm, nout - 1, S0, S1);
@@ -1508,6 +1589,12 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       rd0 += 1;
     }
     const int nrun = nj + 1;
+    // a two-run path in joint count mode (the rule of the sweep that wrote it, evaluated with that sweep's rates)
+    bool joint_old = false;
+    if (!first && nj == 1) {
+      const Real jr0 = rate_or_zero(s_rate_old[(mt >> 22) & 0x1fu]), jr1 = rate_or_zero(s_rate_old[(mt >> 27) & 0x1fu]);
+      joint_old = !(PN::add(PN::mul(jr0, p1), PN::mul(jr1, PN::sub(Le, p1))) > (Real)PM_LAMBDA_INV);
+    }
 
     // ---- the new path ----
     // Runs are emitted in order; the first two are held in registers until a third one shows up (a path with at most
@@ -1534,6 +1621,14 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       long long cp = first ? P.maps_off[eb] : 0;
       auto open_run = [&](int r) {
         Real len; int st;
+        if (joint_old) {  // two runs whose virtual jumps were counted together (A word); positions: B, then (K_BRPOS; run 0)
+          const Real jr0 = rate_or_zero(s_rate_old[(mt >> 22) & 0x1fu]), jr1 = rate_or_zero(s_rate_old[(mt >> 27) & 0x1fu]);
+          const Real L1o = PN::sub(Le, p1);
+          const Real jlam0 = PN::mul(jr0, p1), jlamT = PN::add(jlam0, PN::mul(jr1, L1o));
+          if (r == 0) rp.begin_joint(P.rng, (uint32_t)site, iter - 1u, (uint32_t)eb, p1, poisson_inv<Real>(jlamT, oA), jlam0, jlamT, jr0, oB);
+          else rp.second_run(L1o, jlamT, jr1);
+          return;
+        }
         if (nj == 0) { len = Le; st = (int)((mt >> 22) & 0x1fu); }
         else if (nj == 1) { len = r == 0 ? p1 : PN::sub(Le, p1); st = (int)((mt >> (r == 0 ? 22 : 27)) & 0x1fu); }
         else { const int q = min(rd0 + r, cap_c - 1); len = rd_len[sbase + q]; st = rd_st[sbase + q]; }
@@ -1550,6 +1645,16 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
         return piece;
       };
       nout = 0;
+      // new virtual jumps of run r (length L, clamped rate): their count, by inversion or, above PM_LAMBDA_INV, by gaps
+      auto draw_run = [&](int r, Real L, Real rate, uint32_t cw) -> int {
+        if (!(rate > (Real)0)) return 0;
+        const Real lam = PN::mul(rate, L);
+        if (!(lam > (Real)PM_LAMBDA_INV)) return poisson_inv<Real>(lam, cw);
+        Real g1 = 0;
+        const int k = count_gaps<Real>(P.rng, (uint32_t)site, iter, (uint32_t)eb, (uint32_t)r, L, rate, &g1);
+        if (r == 0) { gaps0 = true; gap0 = g1; }
+        return k;
+      };
       auto emit = [&](Real L, int s) {
         const int r = nout;
         if (replay) {  // records only; the header sits at wbase
@@ -1561,30 +1666,11 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
         else if (r == 1) { L1 = L; S1 = s; }
         else if (r < PM_LOCAL_PATH_MAX) { bufL[r] = L; bufS[r] = (uint8_t)s; }
         add_dwell(s, L);
-        const Real rate = s_rate_new[s];
-        // the count word of run r is consumed whether or not the run uses it (gap mode, zero rate): the next sweep's
-        // open_run() takes one word per run when it regenerates this path
-        const uint32_t cw = r == 0 ? nA : r == 1 ? nB : cnt_new.next();
-        int k = 0;
-        if (rate_ok(rate)) {
-          const Real lam = PN::mul(rate, L);
-          if (lam > (Real)PM_LAMBDA_INV) {
-            WordStream g; g.open(P.rng, (uint32_t)site, iter, K_BRGAP, (uint32_t)eb, (uint32_t)r);
-            Real x = 0;
-            for (;;) {
-              const Real gp = PN::div(PN::neglog(PN::u01(g.next())), rate);
-              const Real t2 = PN::add(x, gp);
-              if (!(t2 < L) || k > 70000) break;
-              x = t2; k++;
-              if (r == 0 && k == 1) gap0 = gp;
-            }
-            if (r == 0) gaps0 = true;
-          } else {
-            k = poisson_inv<Real>(lam, cw);
-          }
-        }
-        if (r == 0) k0 = k;
-        newm += k + 1;
+        // the count word of run r >= 2 is consumed whether or not the run uses it (gap mode, zero rate): the next sweep's
+        // open_run() takes one word per run when it regenerates this path.  Runs 0 and 1 draw when the path is complete
+        // (a path of two runs counts its virtual jumps together)
+        newm += 1;
+        if (r >= 2) newm += draw_run(r, L, rate_or_zero(s_rate_new[s]), cnt_new.next());
         nout++;
       };
 
@@ -1627,6 +1713,19 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       if (replay) {
         if (nout != (int)wr_len[sbase + wbase]) errbits |= PM_DE_INCONSISTENT;  // the header holds the count of pass 0
         break;
+      }
+      {  // runs 0 and 1
+        const Real rn0 = rate_or_zero(s_rate_new[S0]), rn1 = nout >= 2 ? rate_or_zero(s_rate_new[S1]) : (Real)0;
+        const bool together = nout == 2 && !(PN::add(PN::mul(rn0, L0), PN::mul(rn1, L1)) > (Real)PM_LAMBDA_INV);
+        if (together) newm += poisson_inv<Real>(PN::add(PN::mul(rn0, L0), PN::mul(rn1, L1)), nA);
+        else {
+#pragma unroll 1
+          for (int r = 0; r < min(nout, 2); r++) {
+            const int k = draw_run(r, r == 0 ? L0 : L1, r == 0 ? rn0 : rn1, r == 0 ? nA : nB);
+            if (r == 0) k0 = k;
+            newm += k;
+          }
+        }
       }
       if (newm > 65535) { errbits |= PM_DE_M_OVERFLOW; newm = 65535; }
       if (nout == 1) {
@@ -1692,7 +1791,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
           while (b2) { s_stage[warp][pos++] = (unsigned short)(lane * 32 + __ffs((int)b2) - 1); b2 &= b2 - 1u; }
         }
         __syncwarp();
-        short_ok = !first && !(P.tune & 1) && PN::mul(rate_max, __ldg(P.e_len + e)) <= (Real)PM_LAMBDA_INV;
+        short_ok = !first && !(P.tune & 1) && PN::mul(rate_max, __ldg(P.e_len + e)) <= (Real)(PM_LAMBDA_INV - 0.5);  // (sums of two products stay below PM_LAMBDA_INV)
         prow = (long long)__ldg(P.e_parent + e) * S; crow = (long long)__ldg(P.e_child + e) * S; erow = (long long)e * S;
       }
     }
@@ -1712,8 +1811,8 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       bool is_short = false;
       if (WHICH == 0 && have && short_ok) {
         const int m = (int)(it.meta & 0xffffu), njq = (int)((it.meta >> 16) & 0x3fu);
-        is_short = (m == 3 || m == 4) && njq <= 1 && rate_ok(s_rate_old[(it.meta >> 22) & 0x1fu]) &&
-                   (njq == 0 || rate_ok(s_rate_old[(it.meta >> 27) & 0x1fu]));
+        // three or four pieces; at most one real jump (the virtual ones are regenerated) or nothing but real jumps (records)
+        is_short = (m == 3 || m == 4) && (njq <= 1 || njq == m - 1);
       }
       // the short launch (first) takes its items out of the ballot array; the general launch takes whatever is left
       const bool mine = have && (WHICH == 1 || is_short);
