@@ -302,6 +302,23 @@ __device__ __forceinline__ Real next_order_stat(Real x, Real L, int remaining, u
   return Pin<Real>::add(x, Pin<Real>::mul(Pin<Real>::sub(L, x), frac));
 }
 
+// A position on a branch of length t_e is stored as a 16-bit fraction of t_e (upper half of the `meta` word):
+// q t_e / 65536, q rounded to nearest -- dyadic fractions (the midpoint of a caller's two-piece map) are exact, and
+// encoding a decoded value gives q back, so a jump that survives a sweep does not drift.  Every kernel computes with the
+// decoded value only -- lengths, rates, the count-mode decision -- so writer and reader of a path agree to the bit.
+// A uniformly distributed position is pos_rand(word): 17 random bits rounded to 16, symmetric about the midpoint.
+template <typename Real>
+__device__ __forceinline__ Real pos_dec(uint32_t q, Real Le) { return Pin<Real>::mul((Real)q, Pin<Real>::mul(Le, (Real)(1.0 / 65536.0))); }
+template <typename Real>
+__device__ __forceinline__ uint32_t pos_enc(Real p, Real Le) {
+  const Real f = Pin<Real>::add(Pin<Real>::mul(p, Pin<Real>::div((Real)65536, Le)), (Real)0.5);  // NaN (t_e = 0) converts to 0
+  return (uint32_t)min(max((int)f, 0), 65535);
+}
+__device__ __forceinline__ uint32_t pos_rand(uint32_t word) { return min(((word >> 15) + 1u) >> 1, 65535u); }
+// shape word of a stored path (16 bits): real jumps nj (0-5; 63 = "63 or more, see the record header") | state of the
+// first run (6-10) | state of the second run (11-15)
+#define PM_SHAPE(nj, s0, s1) ((uint16_t)((uint32_t)(nj) | ((uint32_t)(s0) << 6) | ((uint32_t)(s1) << 11)))
+
 // lazily evaluated sequence of Philox words: (kind, idx) stream, sub-stream `hi` (run index), word j
 struct WordStream {
   uint32_t k0, k1, site, iter, slot, hi, j;

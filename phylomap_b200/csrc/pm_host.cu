@@ -266,7 +266,7 @@ struct TreeDev {
   int n_cd_top_levels = 0, n_cd_tips = 0;  // clade schedule of the production pruning kernel
   int n_cl_top_levels = 0;
   DevBuf up_entries8, up_entries, up_off, down_entries, down_off, e_parent, e_child, e_len, maps_off, maps_len, cap_off;
-  DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, hard_ballot, wk_off, wk_g, wk_hint, rec_cursor, pos1;
+  DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, hard_ballot, wk_off, wk_g, wk_hint, rec_cursor, shape;
   long long wk_total = 0, dw_rows = 0;
   int hard_blocks = 0;
   DevBuf e_len_d, TP, ll_partial;  // DIC samplers: branch lengths in FP64, exp(Q t_e) per branch, block partials of log p(y|Q)
@@ -568,10 +568,14 @@ struct ChainT : pm_chain {
       ny = std::max(1LL, std::min<long long>(ny, (E + 15) / 16));
       ny = std::min<long long>(ny, 65535);
       ny = std::max<long long>(ny, (E + 2047) / 2048);  // the easy path kernel stages a chunk's topology in shared memory
+      // (production: the offset of a path's records inside its (site, chunk) slice is a 16-bit field of the state word,
+      // so a chunk whose slice would be longer is split)
+      for (;;) {
       t->chunk = (int)((E + ny - 1) / ny);
       ny = (E + t->chunk - 1) / t->chunk;
       t->paths_grid = dim3((unsigned)gx, (unsigned)ny, 1);
       t->nblocks = gx * ny;
+      long long cap_max = 0;
       // record capacity of every chunk.  Real jumps sit on uniformization points, and in equilibrium the points of a
       // chunk are Poisson(Omega x total length), so the Poisson tail bounds them; a path with j real jumps stores
       // j + 1 runs (<= 2j).  The first sweep instead finds its points in the caller's maps (m_e - 1 per branch), so
@@ -613,7 +617,12 @@ struct ChainT : pm_chain {
         }
         if (cap > (1 << 28)) fail(PM_ERR_CAPACITY, "path capacity of a branch chunk too large");
         cap = (cap + 3) & ~3;  // keep every slice 16-byte aligned
+        cap_max = std::max(cap_max, cap);
         t->cap_off_h[c + 1] = t->cap_off_h[c] + (int)cap;
+      }
+      if (exact || V.exp || V.llonly || cap_max <= 65535) break;
+      if (t->chunk <= 1 || ny >= 65535) fail(PM_ERR_CAPACITY, "a branch needs more than 65 535 path records per site");
+      ny = std::min<long long>(std::min<long long>(2 * ny, E), 65535);
       }
       const long long R = t->cap_off_h[ny];
       upload(t->up_entries, t->sch.up_entries, stream);
@@ -736,10 +745,10 @@ struct ChainT : pm_chain {
         upload(t->wk_off, woff, stream);
         upload(t->wk_g, wg, stream);
         t->rec_cursor.alloc((size_t)ny * S * sizeof(int));
-        t->pos1.alloc((size_t)E * S * sizeof(Real));
+        t->shape.alloc((size_t)E * S * sizeof(uint16_t));
       }
       dev_bytes += t->tipcode.bytes + t->node_state.bytes + t->meta.bytes + t->PL.bytes + 2 * (t->rec_len[0].bytes + t->rec_st[0].bytes) +
-                   t->dw_partial.bytes + t->hard_ballot.bytes + t->rec_cursor.bytes + t->pos1.bytes;
+                   t->dw_partial.bytes + t->hard_ballot.bytes + t->rec_cursor.bytes + t->shape.bytes;
       trees.push_back(std::move(t));
     }
 
@@ -800,7 +809,7 @@ struct ChainT : pm_chain {
       P.wk_hint = t.wk_hint.template as<int>();
       P.tune = getenv("PHYLOMAP_B200_TUNE") ? atoi(getenv("PHYLOMAP_B200_TUNE")) : 0;
       P.rec_cursor = t.rec_cursor.template as<int>(); P.chunk = t.chunk; P.easy_blocks = t.nblocks;
-      P.pos1 = t.pos1.template as<Real>();
+      P.shape = t.shape.template as<uint16_t>();
       P.model = model.as<Real>(); P.ppow = ppow.as<Real>(); P.jcap = jcap;
       P.up_entries = t.up_entries.template as<int>(); P.up_off = t.up_off.template as<int>();
       P.up_entries8 = t.up_entries8.template as<int>();
@@ -855,7 +864,7 @@ struct ChainT : pm_chain {
       }
       const long long tot = t.S * E;
       if (!V.exp && !V.llonly)
-        pm::k_init_meta<Real><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(P.maps_off, P.maps_len, t.S, E, P.meta, exact ? nullptr : P.pos1);
+        pm::k_init_meta<Real><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(P.maps_off, P.maps_len, t.S, E, P.meta, P.e_len, exact ? nullptr : P.shape);
       CK(cudaGetLastError());
     }
     stage_model(true);
@@ -1081,9 +1090,13 @@ struct ChainT : pm_chain {
       records(pos, nj + 1);
       return nj + 1;
     }
-    // production: meta = m | nj << 16 (6 bits) | s0 << 22 | s1 << 27; pos1 for nj == 1; records for nj >= 2
-    int nj = (m >> 16) & 0x3f;
-    const int s0 = (m >> 22) & 0x1f, s1 = (m >> 27) & 0x1f;
+    // production: meta = m | q << 16 (q: 16-bit position of the jump point of a two-run path, or the offset of the path's
+    // records in the site's slice); shape = nj (6 bits) | s0 << 6 | s1 << 11
+    uint16_t shp = 0;
+    CK(cudaMemcpy(&shp, t.shape.template as<uint16_t>() + (size_t)e * t.S + site, 2, cudaMemcpyDeviceToHost));
+    int nj = shp & 0x3f;
+    const int s0 = (shp >> 6) & 0x1f, s1 = (shp >> 11) & 0x1f;
+    const uint32_t q = m >> 16;
     Real Le;
     CK(cudaMemcpy(&Le, t.e_len.template as<Real>() + e, sizeof(Real), cudaMemcpyDeviceToHost));
     if (nj == 0) {
@@ -1091,15 +1104,12 @@ struct ChainT : pm_chain {
       return 1;
     }
     if (nj == 1) {
-      Real p1;
-      CK(cudaMemcpy(&p1, t.pos1.template as<Real>() + (size_t)e * t.S + site, sizeof(Real), cudaMemcpyDeviceToHost));
+      const Real p1 = (Real)q * (Le * (Real)(1.0 / 65536.0));
       if (cap > 0) { len[0] = (double)p1; st[0] = s0; }
       if (cap > 1) { len[1] = (double)(Le - p1); st[1] = s1; }
       return 2;
     }
-    Real off;  // paths with two or more real jumps: pos1 holds the offset of their records in the site's slice
-    CK(cudaMemcpy(&off, t.pos1.template as<Real>() + (size_t)e * t.S + site, sizeof(Real), cudaMemcpyDeviceToHost));
-    long long pos = (long long)off;
+    long long pos = (long long)q;  // paths with two or more real jumps: the offset of their records in the site's slice
     if (nj == 63) {  // 64 runs or more: a header record holds the count
       Real cntv;
       CK(cudaMemcpy(&cntv, t.rec_len[buf].template as<Real>() + (size_t)t.cap_off_h[c] * t.S + (size_t)site * cap_c + pos, sizeof(Real),
@@ -1111,7 +1121,7 @@ struct ChainT : pm_chain {
     return nj + 1;
   }
   // ---- checkpoint / resume: everything a sweep reads that is not an input of pm_chain_create ----
-  static constexpr uint32_t PM_STATE_FORMAT = 3;  // 1: round 1 (per-site masks); 2: branch-major ballots, global record cursors; 3: two-run paths count their virtual jumps together
+  static constexpr uint32_t PM_STATE_FORMAT = 4;  // 1: round 1 (per-site masks); 2: branch-major ballots, global record cursors; 3: two-run paths count their virtual jumps together; 4: 16-bit positions inside meta, shape words
   struct StateHeader {
     char magic[8];
     int32_t variant, n, ntrees, precision, mode, T, E, iters_done, jcap, reserved;
@@ -1121,7 +1131,7 @@ struct ChainT : pm_chain {
   std::vector<DevBuf*> state_buffers() {
     std::vector<DevBuf*> v{&model, &ppow};
     for (auto& t : trees) {
-      v.push_back(&t->node_state); v.push_back(&t->meta); v.push_back(&t->pos1);
+      v.push_back(&t->node_state); v.push_back(&t->meta); v.push_back(&t->shape);
       for (int b = 0; b < 2; b++) { v.push_back(&t->rec_len[b]); v.push_back(&t->rec_st[b]); }
     }
     return v;
@@ -1144,7 +1154,7 @@ struct ChainT : pm_chain {
     // instead of being read under this one
     uint32_t hsh = 2166136261u;
     auto mix = [&](uint32_t v) { hsh = (hsh ^ v) * 16777619u; };
-    mix(PM_STATE_FORMAT); mix(PM_META(1, 2, 3, 4)); mix(PM_LAMBDA_INV); mix(PM_LOCAL_PATH_MAX); mix(PM_SMEM_POW);
+    mix(PM_STATE_FORMAT); mix(PM_META(1, 2)); mix((uint32_t)PM_SHAPE(1, 2, 3)); mix(PM_LAMBDA_INV); mix(PM_LOCAL_PATH_MAX); mix(PM_SMEM_POW);
     for (auto& t : trees) { mix((uint32_t)t->chunk); for (int c : t->cap_off_h) mix((uint32_t)c); }
     h.reserved = (int32_t)((PM_STATE_FORMAT << 24) | (hsh & 0xffffffu));
     return h;

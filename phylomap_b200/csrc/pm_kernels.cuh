@@ -56,7 +56,9 @@ struct ChainParams {
   int* rec_cursor;  // [n_chunks][S] records appended so far to the slice of (chunk, site) in this sweep
   int chunk;        // branches per record chunk
   long long easy_blocks;  // blocks of k_paths_easy: k_paths_hard's dwell partials follow theirs in dw_partial
-  Real* pos1;  // production [E][S]: length of the first piece when m == 2 or the path has exactly one real jump
+  // production: meta[e][s] = m | q << 16, q = 16-bit position (pos_dec) of the jump point of a path with one jump point
+  // or one real jump, or the offset of the records of a path with two or more real jumps; shape[e][s] = PM_SHAPE(nj, s0, s1)
+  uint16_t* shape;
   Real* rec_len[2]; uint8_t* rec_st[2];  // double-buffered path records: written by sweep i into [i & 1], read by sweep i + 1
   int normalize, full_counts, parity_tips;
   double* dw_partial; unsigned long long* cnt; int* root_out;
@@ -1085,7 +1087,7 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
 //                 :997-1028), draw the new counts; a path too long for the local buffer is walked a second time to write
 //                 its records in place.  No block barrier; lanes of a round run the same code on items of like shape.
 // ------------------------------------------------------------------------------------------------
-#define PM_META(m, nj, s0, s1) ((uint32_t)(m) | ((uint32_t)(nj) << 16) | ((uint32_t)(s0) << 22) | ((uint32_t)(s1) << 27))
+#define PM_META(m, q) ((uint32_t)(m) | ((uint32_t)(q) << 16))
 
 template <typename Real>
 __device__ __forceinline__ bool rate_ok(Real r) { return isfinite(r) && r > (Real)0; }
@@ -1135,7 +1137,7 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
   const bool bal_writer = (threadIdx.x & 31) == 0 && wglob < (long long)P.W;
   const uint32_t Wu = (uint32_t)P.W;
   uint32_t* __restrict__ meta_p = P.meta + (long long)e0 * S + site;   // walks one row (S entries) per branch
-  Real* __restrict__ pos1_p = P.pos1 + (long long)e0 * S + site;
+  uint16_t* __restrict__ shape_p = P.shape + (long long)e0 * S + site;
   const uint8_t* __restrict__ nstate = P.node_state + site;
   Real Racc[NR]; double Rsum[NR];
 #pragma unroll
@@ -1154,12 +1156,12 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
       for (int j = 0; j < NR; j++) { Rsum[j] += (double)Racc[j]; Racc[j] = 0; }
     }
   };
-  // two-deep software pipeline: jump count and node states of branch i + 2, then pos1 of branch i + 1 if it has a
-  // jump point.  Two branches per loop trip -- the pair (2j, 2j + 1) that shares a Philox block -- with the two register
-  // sets swapping roles, so nothing is copied around and the word selection is static.
+  // Software pipeline over pairs of branches (2j, 2j + 1: they share a Philox block): at the top of a trip the state
+  // words and node states of the NEXT pair are requested (three independent loads per branch: the position of a lone
+  // jump point travels inside the state word), so no load is waited for inside a trip.
   const int nb = e1 - e0;
-  struct Ahead { uint32_t mt; int ps, cs; Real p1; };
-  Ahead X = {0, 0, 0, 0}, Y = {0, 0, 0, 0};
+  struct Ahead { uint32_t mt; int ps, cs; };
+  Ahead X = {0, 0, 0}, Y = {0, 0, 0};
   const uint32_t* meta_f = meta_p;  // fetch cursor (runs ahead of the store cursor)
   auto fetch = [&](int i, Ahead& a) {
     a.mt = *meta_f; meta_f += Su;
@@ -1167,28 +1169,23 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
     a.cs = nstate[(uint64_t)(uint32_t)lds_s32(a_chi + 4u * (unsigned)i) * Su];
   };
   uint32_t po[4] = {0, 0, 0, 0};
-  // one branch: `cur` holds what was fetched for it; with PIPE, `nxt` (branch i + 1) gets its pos1 and `cur` is refilled
-  // with branch i + 2 (GUARD: only if those branches exist -- the steady-state loop knows they do).  ODD: second branch
-  // of its Philox pair (the block was drawn by the first, or here if it opens the chunk).  TAIL: the block may hold
-  // sites past the end.  Straight-line code: lanes that leave their branch to the general kernels compute along and
-  // contribute zeros; only the stores are predicated.
-  auto step = [&](int i, auto odd_c, auto pipe_c, auto guard_c, auto tail_c, Ahead& cur, Ahead& nxt) {
-    constexpr bool ODD = decltype(odd_c)::value, PIPE = decltype(pipe_c)::value, GUARD = decltype(guard_c)::value,
-                   TAIL = decltype(tail_c)::value;
+  // one branch, from what was fetched for it.  ODD: second branch of its Philox pair (the block was drawn by the first,
+  // unless NEWBLK: it opens the chunk).  TAIL: the block may hold sites past the end.  Straight-line code: lanes that
+  // leave their branch to the general kernels compute along and contribute zeros; only the stores are predicated.
+  auto body = [&](int i, auto odd_c, auto newblk_c, auto tail_c, const Ahead cur) {
+    constexpr bool ODD = decltype(odd_c)::value, NEWBLK = decltype(newblk_c)::value, TAIL = decltype(tail_c)::value;
     const int e = e0 + i;
-    const uint32_t mt = cur.mt; const int ps = cur.ps, cs = cur.cs; const Real p1 = cur.p1;
-    if (PIPE) {
-      if ((!GUARD || i + 1 < nb) && (nxt.mt & 0xffffu) == 2u) nxt.p1 = pos1_p[Su];
-      if (!GUARD || i + 2 < nb) fetch(i + 2, cur);
-    }
-    if (!ODD || !PIPE) pair_block(P.rng, (uint32_t)site, iter, (uint32_t)e, po);
+    const uint32_t mt = cur.mt; const int ps = cur.ps, cs = cur.cs;
+    if (NEWBLK) pair_block(P.rng, (uint32_t)site, iter, (uint32_t)e, po);
     const uint32_t wA = ODD ? po[2] : po[0], wB = ODD ? po[3] : po[1];
     const int m = (int)(mt & 0xffffu);
+    const uint32_t q = mt >> 16;
     const Real Le = lds_real(a_len + (unsigned)sizeof(Real) * (unsigned)i, (Real)0);
     // pieces: (Le) or (p1, Le - p1); states ps | cs (a one-piece branch carries the child state, :460-475).  The
     // virtual jumps of a two-run path are counted together: K ~ Poisson(lam0 + lam1) from the A word (their positions,
     // if a later sweep needs them, are regenerated by the general kernels, see RunPieces)
     const bool two = (m == 2) && (ps != cs);
+    const Real p1 = pos_dec<Real>(q, Le);
     const Real L0 = two ? p1 : Le;
     const int s0 = two ? ps : cs;
     const Real L1 = two ? PN::sub(Le, p1) : (Real)0;
@@ -1201,11 +1198,11 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
     if (ok && m == 2 && (full || two)) atomicAdd(&s_cnt[ps * n + cs], 1u);
     add_dwell(s0, ok ? L0 : (Real)0);
     add_dwell(cs, ok ? L1 : (Real)0);
-    // a path that ends up with a single jump point keeps that point in pos1: the real jump stays where it was;
-    // a lone new virtual jump gets its position now
-    if (ok && !two && k == 1) *pos1_p = next_order_stat<Real>((Real)0, Le, 1, wB);
-    if (ok) *meta_p = PM_META((two ? 2 : 1) + k, two ? 1 : 0, s0, cs);
-    meta_p += Su; pos1_p += Su;
+    // a path that ends up with a single jump point keeps that point in the state word: the real jump stays where it
+    // was; a lone new virtual jump is uniform on the branch -- its 16-bit position comes from the B word
+    const uint32_t newq = (!two && k == 1) ? pos_rand(wB) : q;
+    if (ok) { *meta_p = PM_META((two ? 2 : 1) + k, newq); *shape_p = PM_SHAPE(two ? 1 : 0, s0, cs); }
+    meta_p += Su; shape_p += Su;
     const unsigned bal = __ballot_sync(0xffffffffu, TAIL ? (hard && site_raw < S) : hard);
     if (bal_writer) *bal_p = bal;
     bal_p += Wu;
@@ -1215,25 +1212,29 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
     int i = 0;
     if (nb > 0 && (e0 & 1)) {  // the chunk opens on the second branch of a pair: on its own, unpipelined
       fetch(0, X);
-      if ((X.mt & 0xffffu) == 2u) X.p1 = pos1_p[0];
-      step(0, T, F, T, tail_c, X, Y);
+      body(0, T, T, tail_c, X);
       i = 1;
     }
-    if (i < nb) { fetch(i, X); if ((X.mt & 0xffffu) == 2u) X.p1 = pos1_p[0]; }
+    if (i < nb) fetch(i, X);
     if (i + 1 < nb) fetch(i + 1, Y);
     while (i + 3 < nb) {  // 32 pairs, then the FP32 dwell sums of the stretch go to the double accumulators
       const int stop = min(nb - 4, i + 62);
       for (; i <= stop; i += 2) {
-        step(i, F, T, F, tail_c, X, Y);
-        step(i + 1, T, T, F, tail_c, Y, X);
+        const Ahead cx = X, cy = Y;
+        fetch(i + 2, X); fetch(i + 3, Y);
+        body(i, F, T, tail_c, cx);
+        body(i + 1, T, F, tail_c, cy);
       }
       flush_dwell();
     }
     for (; i + 1 < nb; i += 2) {  // the last pair(s): nothing, or not everything, left to prefetch
-      step(i, F, T, T, tail_c, X, Y);
-      step(i + 1, T, T, T, tail_c, Y, X);
+      const Ahead cx = X, cy = Y;
+      if (i + 2 < nb) fetch(i + 2, X);
+      if (i + 3 < nb) fetch(i + 3, Y);
+      body(i, F, T, tail_c, cx);
+      body(i + 1, T, F, tail_c, cy);
     }
-    if (i < nb) step(i, F, T, T, tail_c, X, Y);
+    if (i < nb) body(i, F, T, tail_c, X);
     flush_dwell();
   };
   if ((long long)(blockIdx.x + 1) * blockDim.x <= S) run(std::false_type()); else run(std::true_type());
@@ -1355,7 +1356,7 @@ __device__ __noinline__ int count_gaps(RngDesc d, uint32_t site, uint32_t it, ui
 // state is fetched when it is queued (four independent loads per lane in flight), so that processing it later waits
 // for no memory.
 template <typename Real>
-struct HardItem { uint32_t site, e, meta, ends; Real p1; };  // ends = parent state | child state << 8
+struct HardItem { uint32_t site, e, meta, ends, shape; };  // ends = parent state | child state << 8
 
 // WHICH = 0: the short items only (small code, half the registers: twice the resident warps), launched first: it clears
 // the ballot bits of the items it takes.  WHICH = 1: whatever is left.
@@ -1419,8 +1420,8 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     const uint32_t mt = it.meta;
     const long long pe = (long long)eb * S + site;
     const int m = (int)(mt & 0xffffu);  // 3 or 4
-    const int nj = (int)((mt >> 16) & 0x3fu);
-    const int so0 = (int)((mt >> 22) & 0x1fu), so1 = (int)((mt >> 27) & 0x1fu);
+    const int nj = (int)(it.shape & 0x3fu);
+    const int so0 = (int)((it.shape >> 6) & 0x1fu), so1 = (int)((it.shape >> 11) & 0x1fu);
     const int ps = (int)(it.ends & 0xffu), cs = (int)(it.ends >> 8);
     const Real Le = __ldg(P.e_len + eb);
     const uint32_t gsite = P.rng.site0 + (uint32_t)site;
@@ -1438,13 +1439,13 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       const int ck = eb / P.chunk;
       const int cap0 = __ldg(P.cap_off + ck), cap_c = __ldg(P.cap_off + ck + 1) - cap0;
       const long long sl = (long long)cap0 * S + site * (long long)cap_c;
-      const int rd0 = (int)it.p1;
+      const int rd0 = (int)(mt >> 16);
       J0 = rd_len[sl + min(rd0, cap_c - 1)];
       J1 = PN::add(J0, rd_len[sl + min(rd0 + 1, cap_c - 1)]);
       J2 = m == 4 ? PN::add(J1, rd_len[sl + min(rd0 + 2, cap_c - 1)]) : J1;
     } else {
       const int K = m - 1 - nj;
-      const Real p1 = nj == 0 ? Le : it.p1;          // length of run 0
+      const Real p1 = nj == 0 ? Le : pos_dec<Real>(mt >> 16, Le);          // length of run 0
       const Real L1r = PN::sub(Le, p1);              // length of run 1 (nj == 1)
       Real qq = (Real)2, sc0 = Le, sc1 = 0;
       if (nj == 1) {
@@ -1490,7 +1491,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     auto emit = [&](Real L, int sst) {
       const int r = nout;
       if (r == 0) { L0 = L; S0 = sst; } else if (r == 1) { L1 = L; S1 = sst; } else if (r == 2) { L2 = L; S2 = sst; } else { L3 = L; S3 = sst; }
-      add_dwell(sst, L);
+      if (r >= 2) add_dwell(sst, L);  // (runs 0 and 1: when the path is complete -- a two-run path is quantised first)
       nout++;
     };
     Stream gst; gst.open(P.rng, (uint32_t)site, iter, K_BRSTATE, (uint32_t)eb, P.err_flag);
@@ -1524,18 +1525,23 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     // ---- the new virtual jumps: one run, or two runs counted together, from the pair block's A word; three or four
     // runs one by one (A, B, then the K_BRCNT block).  lam <= rate_max t_e < PM_LAMBDA_INV here: always count mode
     int newm = nout;
+    uint32_t newq = 0;
     const Real rn0 = rate_or_zero(s_rate_new[S0]);
     if (nout == 1) {
+      add_dwell(S0, L0);
       const int k0n = poisson_inv<Real>(PN::mul(rn0, L0), nA);
       newm += k0n;
-      if (k0n == 1) P.pos1[pe] = next_order_stat<Real>((Real)0, Le, 1, nB);
+      newq = pos_rand(nB);  // position of a lone virtual jump (used if k0n == 1): uniform on the branch
     } else {
       const Real rn1 = rate_or_zero(s_rate_new[S1]);
+      if (nout == 2) {  // the jump point moves to its 16-bit lattice: everything below sees the stored path
+        newq = pos_enc<Real>(L0, Le);
+        L0 = pos_dec<Real>(newq, Le); L1 = PN::sub(Le, L0);
+      }
+      add_dwell(S0, L0); add_dwell(S1, L1);
       const Real lam0 = PN::mul(rn0, L0), lam1 = PN::mul(rn1, L1);
-      if (nout == 2) {
-        newm += poisson_inv<Real>(PN::add(lam0, lam1), nA);
-        P.pos1[pe] = L0;
-      } else {
+      if (nout == 2) newm += poisson_inv<Real>(PN::add(lam0, lam1), nA);
+      else {
         uint32_t cw[4];
         philox4x32_10(0u, make_slot(K_BRCNT, (uint32_t)eb), iter, gsite, P.rng.k0, P.rng.k1, cw);
         newm += poisson_inv<Real>(lam0, nA) + poisson_inv<Real>(lam1, nB) +
@@ -1545,7 +1551,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
         const int cap0 = __ldg(P.cap_off + ck), cap_c = __ldg(P.cap_off + ck + 1) - cap0;
         const long long sl = (long long)cap0 * S + site * (long long)cap_c;
         const int base = atomicAdd(P.rec_cursor + (long long)ck * S + site, nout);
-        P.pos1[pe] = (Real)base;
+        newq = (uint32_t)base;
         if (base + nout > cap_c) errbits |= PM_DE_PATH_CAP;
         else {
           wr_len[sl + base] = L0; wr_st[sl + base] = (uint8_t)S0;
@@ -1555,7 +1561,8 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
         }
       }
     }
-    P.meta[pe] = PM_META(newm, nout - 1, S0, S1);
+    P.meta[pe] = PM_META(newm, newq);
+    P.shape[pe] = PM_SHAPE(nout - 1, S0, S1);
   };
 
   // ---- any item: regenerate the pieces run by run, redraw the interior states, merge, count, emit ----
@@ -1570,7 +1577,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
 
     const long long pe = (long long)eb * S + site;
     const int m = (int)(mt & 0xffffu);
-    const int njf = first ? 0 : (int)((mt >> 16) & 0x3fu);  // real jumps; 63 = "63 or more, see the record header"
+    const int njf = first ? 0 : (int)(it.shape & 0x3fu);  // real jumps; 63 = "63 or more, see the record header"
     const int ps = (int)(it.ends & 0xffu), cs = (int)(it.ends >> 8);
     const Real Le = __ldg(P.e_len + eb);
     uint32_t po_old[4], po_new[4];
@@ -1580,8 +1587,8 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     const uint32_t nA = (eb & 1) ? po_new[2] : po_new[0], nB = (eb & 1) ? po_new[3] : po_new[1];
     // nj == 1: pos1 = length of run 0; nj >= 2: pos1 = offset of the path's records in the site's slice.  A path with 64
     // or more runs starts with a header record holding its run count.
-    const Real p1 = (!first && (njf >= 1)) ? it.p1 : (Real)0;
-    int rd0 = (njf >= 2) ? (int)p1 : 0;
+    const Real p1 = (!first && njf == 1) ? pos_dec<Real>(mt >> 16, Le) : (Real)0;
+    int rd0 = (njf >= 2) ? (int)(mt >> 16) : 0;
     int nj = njf;
     if (njf == 63) {
       const int q = min(rd0, cap_c - 1);
@@ -1592,7 +1599,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     // a two-run path in joint count mode (the rule of the sweep that wrote it, evaluated with that sweep's rates)
     bool joint_old = false;
     if (!first && nj == 1) {
-      const Real jr0 = rate_or_zero(s_rate_old[(mt >> 22) & 0x1fu]), jr1 = rate_or_zero(s_rate_old[(mt >> 27) & 0x1fu]);
+      const Real jr0 = rate_or_zero(s_rate_old[(it.shape >> 6) & 0x1fu]), jr1 = rate_or_zero(s_rate_old[(it.shape >> 11) & 0x1fu]);
       joint_old = !(PN::add(PN::mul(jr0, p1), PN::mul(jr1, PN::sub(Le, p1))) > (Real)PM_LAMBDA_INV);
     }
 
@@ -1610,6 +1617,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     // straight to the records reserved at `wbase` -- nothing else is done twice (no counts, dwell times or draws of new
     // virtual jumps).
     int wbase = 0;
+    uint32_t newq = 0;  // position field of the new state word
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {  // pass 1 only for a path longer than the local buffer (see below)
       const bool replay = pass != 0;
@@ -1622,15 +1630,15 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       auto open_run = [&](int r) {
         Real len; int st;
         if (joint_old) {  // two runs whose virtual jumps were counted together (A word); positions: B, then (K_BRPOS; run 0)
-          const Real jr0 = rate_or_zero(s_rate_old[(mt >> 22) & 0x1fu]), jr1 = rate_or_zero(s_rate_old[(mt >> 27) & 0x1fu]);
+          const Real jr0 = rate_or_zero(s_rate_old[(it.shape >> 6) & 0x1fu]), jr1 = rate_or_zero(s_rate_old[(it.shape >> 11) & 0x1fu]);
           const Real L1o = PN::sub(Le, p1);
           const Real jlam0 = PN::mul(jr0, p1), jlamT = PN::add(jlam0, PN::mul(jr1, L1o));
           if (r == 0) rp.begin_joint(P.rng, (uint32_t)site, iter - 1u, (uint32_t)eb, p1, poisson_inv<Real>(jlamT, oA), jlam0, jlamT, jr0, oB);
           else rp.second_run(L1o, jlamT, jr1);
           return;
         }
-        if (nj == 0) { len = Le; st = (int)((mt >> 22) & 0x1fu); }
-        else if (nj == 1) { len = r == 0 ? p1 : PN::sub(Le, p1); st = (int)((mt >> (r == 0 ? 22 : 27)) & 0x1fu); }
+        if (nj == 0) { len = Le; st = (int)((it.shape >> 6) & 0x1fu); }
+        else if (nj == 1) { len = r == 0 ? p1 : PN::sub(Le, p1); st = (int)((it.shape >> (r == 0 ? 6 : 11)) & 0x1fu); }
         else { const int q = min(rd0 + r, cap_c - 1); len = rd_len[sbase + q]; st = rd_st[sbase + q]; }
         const uint32_t cw = r == 0 ? oA : r == 1 ? oB : cnt_old.next();
         rp.begin(P.rng, (uint32_t)site, iter - 1u, (uint32_t)eb, r, len, s_rate_old[st], cw, nj == 0, oB);
@@ -1665,7 +1673,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
         if (r == 0) { L0 = L; S0 = s; }
         else if (r == 1) { L1 = L; S1 = s; }
         else if (r < PM_LOCAL_PATH_MAX) { bufL[r] = L; bufS[r] = (uint8_t)s; }
-        add_dwell(s, L);
+        if (r >= 2) add_dwell(s, L);
         // the count word of run r >= 2 is consumed whether or not the run uses it (gap mode, zero rate): the next sweep's
         // open_run() takes one word per run when it regenerates this path.  Runs 0 and 1 draw when the path is complete
         // (a path of two runs counts its virtual jumps together)
@@ -1714,7 +1722,13 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
         if (nout != (int)wr_len[sbase + wbase]) errbits |= PM_DE_INCONSISTENT;  // the header holds the count of pass 0
         break;
       }
-      {  // runs 0 and 1
+      {  // runs 0 and 1: dwell times and new virtual jumps, now that the path is complete
+        if (nout == 2) {  // the jump point moves to its 16-bit lattice: everything below sees the stored path
+          newq = pos_enc<Real>(L0, Le);
+          L0 = pos_dec<Real>(newq, Le); L1 = PN::sub(Le, L0);
+        }
+        add_dwell(S0, L0);
+        if (nout >= 2) add_dwell(S1, L1);
         const Real rn0 = rate_or_zero(s_rate_new[S0]), rn1 = nout >= 2 ? rate_or_zero(s_rate_new[S1]) : (Real)0;
         const bool together = nout == 2 && !(PN::add(PN::mul(rn0, L0), PN::mul(rn1, L1)) > (Real)PM_LAMBDA_INV);
         if (together) newm += poisson_inv<Real>(PN::add(PN::mul(rn0, L0), PN::mul(rn1, L1)), nA);
@@ -1728,18 +1742,18 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
         }
       }
       if (newm > 65535) { errbits |= PM_DE_M_OVERFLOW; newm = 65535; }
-      if (nout == 1) {
-        if (k0 == 1) P.pos1[pe] = gaps0 ? gap0 : next_order_stat<Real>((Real)0, Le, 1, nB);
+      if (nout == 1) {  // a lone virtual jump: uniform on the branch (count mode), or where the first gap put it
+        newq = (k0 == 1 && gaps0) ? pos_enc<Real>(gap0, Le) : pos_rand(nB);
         break;
       }
-      if (nout == 2) { P.pos1[pe] = L0; break; }
+      if (nout == 2) break;
       // three or more runs: a contiguous block of records in the site's slice; its offset goes where a shorter path
-      // keeps the length of its first run.  64 runs or more: a header record with the count comes first.
+      // keeps the position of its jump point.  64 runs or more: a header record with the count comes first.
       const bool longp = nout >= 64;
       const int need = nout + (longp ? 1 : 0);
       const int base = atomicAdd(cursor, need);
-      P.pos1[pe] = (Real)base;
-      if (base + need > cap_c) { errbits |= PM_DE_PATH_CAP; break; }
+      newq = (uint32_t)min(base, 65535);
+      if (base + need > cap_c || base > 65535) { errbits |= PM_DE_PATH_CAP; break; }
       if (longp) { wr_len[sbase + base] = (Real)nout; wr_st[sbase + base] = 0; }
       if (nout > PM_LOCAL_PATH_MAX) {  // not all runs were kept: walk the branch once more, writing them in place
         wbase = base;
@@ -1751,7 +1765,8 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       for (int r = 2; r < nout; r++) { wr_len[sbase + o + r] = bufL[r]; wr_st[sbase + o + r] = bufS[r]; }
       break;
     }
-    P.meta[pe] = PM_META(newm, min(nout - 1, 63), S0, S1);
+    P.meta[pe] = PM_META(newm, newq);
+    P.shape[pe] = PM_SHAPE(min(nout - 1, 63), S0, S1);
   };
 
   // ---- the warp walks its work items; items are classified, queued and processed 32 at a time ----
@@ -1801,16 +1816,16 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       HardItem<Real> it;
       it.e = (uint32_t)e;
       it.site = have ? (uint32_t)(w0 * 32 + s_stage[warp][k]) : 0u;
-      it.meta = 0u; it.ends = 0u; it.p1 = (Real)0;
+      it.meta = 0u; it.ends = 0u; it.shape = 0u;
       if (have) {  // four independent loads
         it.meta = P.meta[erow + it.site];
         const uint32_t a = P.node_state[prow + it.site], b = P.node_state[crow + it.site];
-        if (!first) it.p1 = P.pos1[erow + it.site];
+        if (!first) it.shape = P.shape[erow + it.site];
         it.ends = a | (b << 8);
       }
       bool is_short = false;
       if (WHICH == 0 && have && short_ok) {
-        const int m = (int)(it.meta & 0xffffu), njq = (int)((it.meta >> 16) & 0x3fu);
+        const int m = (int)(it.meta & 0xffffu), njq = (int)(it.shape & 0x3fu);
         // three or four pieces; at most one real jump (the virtual ones are regenerated) or nothing but real jumps (records)
         is_short = (m == 3 || m == 4) && (njq <= 1 || njq == m - 1);
       }

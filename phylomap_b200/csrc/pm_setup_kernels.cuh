@@ -59,18 +59,22 @@ __global__ void __launch_bounds__(256) k_init_tips(const In* __restrict__ states
   }
 }
 
-// meta <- number of pieces of the caller's map of every branch; production arithmetic also seeds pos1 with the position
-// of the only jump point of a two-piece map, so that the first sweep can treat such a branch like any later one
-// (k_paths_easy) instead of walking the map in the general kernel.
+// meta <- number of pieces of the caller's map of every branch; production arithmetic also seeds the position field
+// (upper 16 bits) with the only jump point of a two-piece map, so that the first sweep can treat such a branch like any
+// later one (k_paths_easy) instead of walking the map in the general kernel.
 template <typename Real>
 __global__ void k_init_meta(const long long* __restrict__ maps_off, const double* __restrict__ maps_len, long long S, int E,
-                            uint32_t* meta, Real* pos1) {
+                            uint32_t* meta, const Real* __restrict__ e_len, uint16_t* shape) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S * E) return;
   const long long e = i / S;
   const long long a = maps_off[e], m = maps_off[e + 1] - a;
-  meta[i] = (uint32_t)m;
-  if (pos1 && m == 2) pos1[i] = (Real)maps_len[a];
+  uint32_t w = (uint32_t)m;
+  if (shape) {
+    if (m == 2) w |= pos_enc<Real>((Real)maps_len[a], e_len[e]) << 16;
+    shape[i] = 0;
+  }
+  meta[i] = w;
 }
 
 }  // namespace pm
