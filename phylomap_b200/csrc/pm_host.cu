@@ -189,26 +189,33 @@ int poisson_cap(double lam, double eps) {
 
 // c such that P( sum_e X_e >= c ) < eps for independent X_e = (N_e + 1) 1[N_e >= 2], N_e ~ Poisson(lam_e):
 // min over theta of (log(1/eps) + sum_e log E exp(theta X_e)) / theta
-long long chernoff_records_cap(const std::vector<double>& lams, double eps) {
-  double best = 1e300;
-  for (double theta : {0.25, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0}) {
-    double acc = std::log(1.0 / eps);
-    bool ok = true;
-    for (double lam : lams) {
-      // E exp(theta X) = P(N < 2) + sum_{j >= 2} exp(theta (j + 1)) P(N = j)
-      double pj = std::exp(-lam), mgf = pj;  // j = 0
-      pj *= lam; mgf += pj;                  // j = 1
+long long chernoff_records_cap(const std::vector<double>& lams, double eps, double copies = 1.0) {  // `copies` independent sites share the slice
+  // (the small thetas serve slices shared by many sites: the bound tends to copies x mean + log(1 / eps) / theta)
+  constexpr int NT = 11;
+  const double thetas[NT] = {0.02, 0.04, 0.07, 0.12, 0.25, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0};
+  double acc[NT], eth[NT];
+  bool ok[NT];
+  for (int t = 0; t < NT; t++) { acc[t] = 0; eth[t] = std::exp(thetas[t]); ok[t] = true; }
+  for (double lam : lams) {
+    const double p0 = std::exp(-lam);
+    for (int t = 0; t < NT; t++) {
+      if (!ok[t]) continue;
+      // E exp(theta X) = P(N < 2) + sum_{j >= 2} exp(theta (j + 1)) P(N = j); consecutive terms differ by the factor
+      // exp(theta) lam / j (no exponential inside the loop: this runs for every branch at every chain creation)
+      double mgf = p0 + p0 * lam;
+      double term = eth[t] * eth[t] * p0 * lam;  // the j = 1 term of the series (not part of the sum)
       for (int j = 2; j < 400; j++) {
-        pj *= lam / j;
-        const double term = std::exp(theta * (j + 1)) * pj;
+        term *= eth[t] * lam / j;
         mgf += term;
-        if (j > lam * std::exp(theta) + 5 && term < 1e-30 * mgf) break;
+        if (j > lam * eth[t] + 5 && term < 1e-30 * mgf) break;
       }
-      if (!std::isfinite(mgf)) { ok = false; break; }
-      acc += std::log(mgf);
+      if (!std::isfinite(mgf)) { ok[t] = false; continue; }
+      acc[t] += std::log(mgf);
     }
-    if (ok) best = std::min(best, acc / theta);
   }
+  double best = 1e300;
+  for (int t = 0; t < NT; t++)
+    if (ok[t]) best = std::min(best, (std::log(1.0 / eps) + copies * acc[t]) / thetas[t]);
   if (!(best < 1e15)) return 1LL << 40;
   return (long long)std::ceil(best);
 }
@@ -269,6 +276,9 @@ struct TreeDev {
   DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, hard_ballot, wk_off, wk_g, wk_hint, rec_cursor, shape;
   long long wk_total = 0, dw_rows = 0;
   int hard_blocks = 0;
+  long long pl_tile = 0;     // sites per pruning / node-draw launch (= sites the partials buffer holds); S when not tiled
+  int rec_shift = 0;         // production path records: 2^rec_shift consecutive sites share a slice
+  long long rec_groups = 0;
   DevBuf e_len_d, TP, ll_partial;  // DIC samplers: branch lengths in FP64, exp(Q t_e) per branch, block partials of log p(y|Q)
   std::vector<int> cap_off_h;
   pm::ChainParams<Real> P;
@@ -310,6 +320,16 @@ struct ChainT : pm_chain {
   int k1_variant = 42;  // production pruning kernel variant (pm_launch_impl.cuh; PHYLOMAP_B200_K1_UNROLL overrides, for tuning)
   struct Timed { cudaEvent_t a, b; int k; };
   std::vector<Timed> timed;
+  // CUDA-graph replay of one sweep (fixed-Q samplers on small problems: a sweep of a 100-tip tree is seven launches of a
+  // few microseconds each, and the host cannot issue them as fast as the GPU retires them).  The sweep index and the
+  // output row live in device memory (ChainParams::ctl), so one instantiated graph serves every sweep of the chain.
+  DevBuf ctl;
+  uint32_t* ctl_h = nullptr;          // pinned
+  cudaGraphExec_t sweep_graph = nullptr;
+  void* graph_rows = nullptr;         // the rows buffer the graph writes to (re-captured if it moves)
+  bool capturing = false;
+  int graph_mode = -1;                // PHYLOMAP_B200_GRAPH: 0 never, 1 always, otherwise by problem size
+  int launches_per_sweep = 0;
 
   ~ChainT() override {
     cudaSetDevice(opt.device);
@@ -319,6 +339,8 @@ struct ChainT : pm_chain {
     if (rows_h) cudaFreeHost(rows_h);
     if (err_h) cudaFreeHost(err_h);
     if (q_h) cudaFreeHost(q_h);
+    if (ctl_h) cudaFreeHost(ctl_h);
+    if (sweep_graph) cudaGraphExecDestroy(sweep_graph);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 
@@ -375,22 +397,36 @@ struct ChainT : pm_chain {
 
   template <int NSc, bool EX>
   void launch_sweep_t(TreeDev<Real>& t, uint32_t iter, double* row) {
-    const int gx = (int)((t.S + 31) / 32);
-    begin_timed(0);
-    pm::Sweep<Real, NSc, EX>::prune(t.P, prune_grid(t), prune_smem(t), stream, k1_variant);
-    end_timed();
-    begin_timed(1);
-    pm::Sweep<Real, NSc, EX>::nodes(t.P, gx, smem_nodes, stream, iter);
-    end_timed();
+    int ntiles = 0;
+    const uint32_t* ctl_d = capturing ? ctl.as<uint32_t>() : nullptr;
+    for (long long b = 0; b < t.S; b += t.pl_tile, ntiles++) {  // K1 -> K2 per site tile (one tile unless the partials are tiled)
+      pm::ChainParams<Real> P = t.P;
+      P.tile_base = b;
+      P.ctl = ctl_d;
+      const int gx = (int)((std::min(t.pl_tile, t.S - b) + 31) / 32);
+      begin_timed(0);
+      pm::Sweep<Real, NSc, EX>::prune(P, gx, prune_smem(t), stream, k1_variant);
+      end_timed();
+      begin_timed(1);
+      pm::Sweep<Real, NSc, EX>::nodes(P, gx, smem_nodes, stream, iter);
+      end_timed();
+    }
     begin_timed(2);
     if (!EX) CK(cudaMemsetAsync(t.rec_cursor.p, 0, t.rec_cursor.bytes, stream));  // (inside K3's timed region: it is part of the step)
-    pm::Sweep<Real, NSc, EX>::paths(t.P, t.paths_grid, smem_paths, stream, iter, iter == 0 ? 1 : 0, t.chunk, t.hard_blocks);
+    {
+      pm::ChainParams<Real> P = t.P;
+      P.ctl = ctl_d;
+      // (a captured sweep serves every index: its kernels take `first` from the index they read, and the short-shape
+      // kernel, which has nothing to do in a first sweep, is always part of it)
+      pm::Sweep<Real, NSc, EX>::paths(P, t.paths_grid, smem_paths, stream, iter, (iter == 0 && !capturing) ? 1 : 0, t.chunk, t.hard_blocks);
+    }
     end_timed();
     begin_timed(3);
     pm::k_reduce<<<1, 256, 0, stream>>>(t.dw_partial.template as<double>(), t.dw_rows, n, cnt.as<unsigned long long>(),
-                                        root_out.as<int>(), row, 0, err_flag.as<unsigned>(), W);
+                                        root_out.as<int>(), row, 0, err_flag.as<unsigned>(), W, capturing ? ctl.as<uint32_t>() : nullptr, WR);
     end_timed();
-    launches += exact ? 4 : 5;
+    launches_per_sweep = 2 * ntiles + (exact ? 2 : (iter == 0 && !capturing) ? 3 : 4);
+    if (!capturing) launches += launches_per_sweep;
   }
   // DIC samplers: log p(y | Q) of the current Q into row[n + n*n + 1] (after the sweep: PL is free again)
   void launch_loglik(TreeDev<Real>& t, double* row) {
@@ -407,9 +443,16 @@ struct ChainT : pm_chain {
     launches += 3;
   }
 
+  // the pruning pass alone: over all site tiles, or over the one tile that holds `only_site`
   template <int NSc, bool EX>
-  void launch_prune_t(TreeDev<Real>& t) {
-    pm::Sweep<Real, NSc, EX>::prune(t.P, prune_grid(t), prune_smem(t), stream, k1_variant);
+  void launch_prune_t(TreeDev<Real>& t, long long only_site) {
+    for (long long b = 0; b < t.S; b += t.pl_tile) {
+      if (only_site >= 0 && (only_site < b || only_site >= b + t.pl_tile)) continue;
+      pm::ChainParams<Real> P = t.P;
+      P.tile_base = b;
+      pm::Sweep<Real, NSc, EX>::prune(P, (int)((std::min(t.pl_tile, t.S - b) + 31) / 32), prune_smem(t), stream, k1_variant);
+      launches++;
+    }
   }
 
   template <bool EX>
@@ -419,13 +462,13 @@ struct ChainT : pm_chain {
     else launch_sweep_t<0, EX>(t, iter, row);
   }
   template <bool EX>
-  void launch_prune_e(TreeDev<Real>& t) {
-    if (NS == 2) launch_prune_t<2, EX>(t);
-    else if (NS == 4) launch_prune_t<4, EX>(t);
-    else launch_prune_t<0, EX>(t);
+  void launch_prune_e(TreeDev<Real>& t, long long only_site) {
+    if (NS == 2) launch_prune_t<2, EX>(t, only_site);
+    else if (NS == 4) launch_prune_t<4, EX>(t, only_site);
+    else launch_prune_t<0, EX>(t, only_site);
   }
   void launch_sweep(TreeDev<Real>& t, uint32_t iter, double* row);
-  void launch_prune(TreeDev<Real>& t);
+  void launch_prune(TreeDev<Real>& t, long long only_site = -1);
 
   void begin_timed(int k) {
     debug_kernel = k;
@@ -479,6 +522,15 @@ struct ChainT : pm_chain {
     V = variant_of(variant);
     n = n_; ntrees = ntr; N_total = Ntot; Q = Q_; B = B_; Omega = Om;
     opt = *o;
+    // PHYLOMAP_B200_TRACE=1: host wall time of the phases of a chain's construction, on stderr
+    const bool trace = getenv("PHYLOMAP_B200_TRACE") && getenv("PHYLOMAP_B200_TRACE")[0] == '1';
+    auto trace_t0 = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+      if (!trace) return;
+      const auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[phylomap_b200] create: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - trace_t0).count());
+      trace_t0 = now;
+    };
     if (n < 2 || n > PM_NMAX) fail(PM_ERR_ARG, "number of states must be in 2..%d", PM_NMAX);
     if (!V.multi && ntr != 1) fail(PM_ERR_ARG, "this sampler takes exactly one tree");
     if (ntr < 1) fail(PM_ERR_ARG, "no trees");
@@ -530,6 +582,7 @@ struct ChainT : pm_chain {
       }
     }
 
+    mark("validation + schedules");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) fail(PM_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
     if (opt.device < 0 || opt.device >= ndev) fail(PM_ERR_CUDA, "device %d not present", opt.device);
@@ -568,8 +621,19 @@ struct ChainT : pm_chain {
       ny = std::max(1LL, std::min<long long>(ny, (E + 15) / 16));
       ny = std::min<long long>(ny, 65535);
       ny = std::max<long long>(ny, (E + 2047) / 2048);  // the easy path kernel stages a chunk's topology in shared memory
-      // (production: the offset of a path's records inside its (site, chunk) slice is a 16-bit field of the state word,
-      // so a chunk whose slice would be longer is split)
+      // (production: the offset of a path's records inside its slice is a 16-bit field of the state word, so a chunk
+      // whose slice would be longer is split).  Production slices are shared by groups of 32 consecutive sites: the
+      // bound on the records of 32 independent sites together is far tighter, relative to its mean, than 32 bounds on
+      // one site each (3.8 -> 0.3 bytes per branch-site at the benchmark's size).  Where such a slice would not fit the
+      // 16-bit offset (long paths: the Squamate vignette) every site keeps its own.
+      const bool pooled_ok = !exact && !V.exp && !V.llonly && !(getenv("PHYLOMAP_B200_REC_POOL") && getenv("PHYLOMAP_B200_REC_POOL")[0] == '0');
+      const long long ny_first = ny;
+      for (int attempt = pooled_ok ? 0 : 1; attempt < 2; attempt++) {
+      t->rec_shift = attempt == 0 ? 5 : 0;
+      const double G = (double)(1 << t->rec_shift);
+      t->rec_groups = (S + (1LL << t->rec_shift) - 1) >> t->rec_shift;
+      ny = ny_first;
+      bool fits = true;
       for (;;) {
       t->chunk = (int)((E + ny - 1) / ny);
       ny = (E + t->chunk - 1) / t->chunk;
@@ -592,7 +656,7 @@ struct ChainT : pm_chain {
         }
         long long cap;
         if (V.exp || V.llonly) cap = 4;  // no path state
-        else if (opt.path_capacity > 0) cap = (long long)opt.path_capacity * (b1 - b0);
+        else if (opt.path_capacity > 0) cap = (long long)opt.path_capacity * (b1 - b0) * (long long)G;
         else if (exact) {
           const int jumps = poisson_cap(1.5 * Omega * len + 1.0, 1e-18);
           cap = std::max<long long>((long long)(b1 - b0) + jumps, init_records);
@@ -610,21 +674,36 @@ struct ChainT : pm_chain {
           // jumps of the chunk together are dominated by one Poisson variable
           double lam_sum = 0, lam_max = 0;
           for (double l : lams) { lam_sum += l; lam_max = std::max(lam_max, l); }
-          const long long simple = (long long)poisson_cap(lam_sum, 1e-18) + 2LL * (b1 - b0);
+          const long long simple = (long long)poisson_cap(G * lam_sum, 1e-18) + 2LL * (b1 - b0) * (long long)G;
           long long stat = simple;
-          if (lam_max < 200.0) stat = std::min(stat, chernoff_records_cap(lams, 1e-18));  // (its series stops at 400 terms)
-          cap = std::max<long long>(stat, init3) + 4;
+          if (lam_max < 200.0) stat = std::min(stat, chernoff_records_cap(lams, 1e-18, G));  // (its series stops at 400 terms)
+          cap = std::max<long long>(stat, init3 * (long long)G) + 4;
         }
-        if (cap > (1 << 28)) fail(PM_ERR_CAPACITY, "path capacity of a branch chunk too large");
+        if (cap > (1 << 28)) { if (t->rec_shift) cap = 1 << 28; else fail(PM_ERR_CAPACITY, "path capacity of a branch chunk too large"); }
         cap = (cap + 3) & ~3;  // keep every slice 16-byte aligned
         cap_max = std::max(cap_max, cap);
         t->cap_off_h[c + 1] = t->cap_off_h[c] + (int)cap;
       }
       if (exact || V.exp || V.llonly || cap_max <= 65535) break;
+      if (t->rec_shift) { fits = false; break; }  // shared slices too long for the offset field: per-site slices instead
       if (t->chunk <= 1 || ny >= 65535) fail(PM_ERR_CAPACITY, "a branch needs more than 65 535 path records per site");
       ny = std::min<long long>(std::min<long long>(2 * ny, E), 65535);
       }
+      if (fits) break;
+      }
       const long long R = t->cap_off_h[ny];
+      mark("record capacities");
+      // Partials are scratch between the pruning pass and the node draws of one sweep: the production kernels (n = 2, 4)
+      // run K1 -> K2 site tile by site tile, so the buffer holds one tile.  A tile is two full waves of the pruning
+      // kernel's grid (3 blocks of 32 sites per SM in FP32, 2 in FP64): every launch but the last fills the GPU evenly.
+      // The DIC chains evaluate log p(y | Q) over all sites after the sweep and keep the whole array, like the generic and
+      // the deterministic kernels.
+      t->pl_tile = S;
+      if (!exact && (NS == 2 || NS == 4) && !V.dic && !V.exp && !V.llonly) {
+        long long tile = 32LL * prop.multiProcessorCount * (sizeof(Real) == 8 ? 2 : 3) * 2;
+        if (const char* v = getenv("PHYLOMAP_B200_PL_TILE")) tile = atoll(v) <= 0 ? S : (atoll(v) + 31) / 32 * 32;
+        t->pl_tile = std::min(S, tile);
+      }
       upload(t->up_entries, t->sch.up_entries, stream);
       {
         std::vector<int> e8((size_t)8 * (T - 1), 0);
@@ -642,7 +721,7 @@ struct ChainT : pm_chain {
         const int n1 = cs.warp_off.back();
         std::vector<int> e16((size_t)PM_CLADE_ENTRY_INTS * (n1 + 17), 0);  // padded: the kernel forms addresses up to 16 entries ahead
         auto put64 = [](int* dst, long long v) { dst[0] = (int)(unsigned)(v & 0xffffffffLL); dst[1] = (int)(v >> 32); };
-        const long long rowPL = (long long)S * n * (long long)sizeof(Real);
+        const long long rowPL = (long long)t->pl_tile * n * (long long)sizeof(Real);
         for (int i = 0; i < n1; i++) {
           const int* en = &cs.entries[(size_t)8 * i];
           int* o = &e16[(size_t)PM_CLADE_ENTRY_INTS * i];
@@ -701,6 +780,7 @@ struct ChainT : pm_chain {
         t->TP.alloc((size_t)E * n * n * sizeof(Real));
         t->ll_partial.alloc((size_t)((S + 31) / 32) * sizeof(double));
       }
+      mark("clade schedules + uploads");
       upload(t->maps_off, moff, stream);
       upload(t->maps_len, mlen, stream);
       upload(t->cap_off, t->cap_off_h, stream);
@@ -708,17 +788,12 @@ struct ChainT : pm_chain {
       CK(cudaMemsetAsync(t->tipcode.p, 0, t->tipcode.bytes, stream));
       t->node_state.alloc((size_t)(2 * T - 1) * S);
       if (!V.exp && !V.llonly) t->meta.alloc((size_t)E * S * sizeof(uint32_t));
-      t->PL.alloc((size_t)(T - 1) * S * n * sizeof(Real));
+      t->PL.alloc((size_t)(T - 1) * t->pl_tile * n * sizeof(Real));
       for (int b = 0; b < 2 && !V.exp && !V.llonly; b++) {
-        t->rec_len[b].alloc((size_t)R * S * sizeof(Real));
-        t->rec_st[b].alloc((size_t)R * S);
+        t->rec_len[b].alloc((size_t)R * t->rec_groups * sizeof(Real));
+        t->rec_st[b].alloc((size_t)R * t->rec_groups);
       }
       CK(cudaMemsetAsync(t->node_state.p, 0, t->node_state.bytes, stream));
-      // partial dwell sums per block: [0, nblocks) easy / deterministic / direct-sampler kernel, then the general path kernel's
-      t->hard_blocks = (!exact && !V.exp && !V.llonly) ? prop.multiProcessorCount * 4 : 0;  // persistent: 4 blocks of 4 warps per SM
-      t->dw_rows = t->nblocks + 3 * t->hard_blocks;  // general kernel: hard_blocks rows; short kernel: 2 hard_blocks (after them)
-      t->dw_partial.alloc((size_t)t->dw_rows * n * sizeof(double));
-      CK(cudaMemsetAsync(t->dw_partial.p, 0, t->dw_partial.bytes, stream));
       if (!exact && !V.exp && !V.llonly) {
         // Branch-major ballot array and the general kernel's work items: branch e is cut into items of g_e ballot words
         // (32 g_e sites), g_e chosen so that an item holds ~96 branch-sites with two or more jump points in equilibrium
@@ -744,12 +819,19 @@ struct ChainT : pm_chain {
         upload(t->wk_hint, hint, stream);
         upload(t->wk_off, woff, stream);
         upload(t->wk_g, wg, stream);
-        t->rec_cursor.alloc((size_t)ny * S * sizeof(int));
+        t->rec_cursor.alloc((size_t)ny * t->rec_groups * sizeof(int));
         t->shape.alloc((size_t)E * S * sizeof(uint16_t));
+        // persistent: 4 blocks of 4 warps per SM, fewer when there are not that many work items (a handful of sites)
+        t->hard_blocks = (int)std::max<long long>(1, std::min<long long>(prop.multiProcessorCount * 4LL, (t->wk_total + 3) / 4));
       }
+      // partial dwell sums per block: [0, nblocks) easy / deterministic / direct-sampler kernel, then the general path kernel's
+      t->dw_rows = t->nblocks + 3 * t->hard_blocks;  // general kernel: hard_blocks rows; short kernel: 2 hard_blocks (after them)
+      t->dw_partial.alloc((size_t)t->dw_rows * n * sizeof(double));
+      CK(cudaMemsetAsync(t->dw_partial.p, 0, t->dw_partial.bytes, stream));
       dev_bytes += t->tipcode.bytes + t->node_state.bytes + t->meta.bytes + t->PL.bytes + 2 * (t->rec_len[0].bytes + t->rec_st[0].bytes) +
                    t->dw_partial.bytes + t->hard_ballot.bytes + t->rec_cursor.bytes + t->shape.bytes;
       trees.push_back(std::move(t));
+      mark("device buffers");
     }
 
     // table of powers
@@ -767,6 +849,9 @@ struct ChainT : pm_chain {
     CK(cudaMallocHost((void**)&rows_h, (size_t)ntrees * WR * sizeof(double)));
     if (opt.nccl_world > 1) nccl = clique(opt.nccl_id, opt.nccl_world, opt.nccl_rank);
     CK(cudaMallocHost((void**)&err_h, sizeof(unsigned)));
+    CK(cudaMallocHost((void**)&ctl_h, 2 * sizeof(uint32_t)));
+    ctl.alloc(2 * sizeof(uint32_t));
+    if (const char* v = getenv("PHYLOMAP_B200_GRAPH")) graph_mode = atoi(v);
     if (V.dic) { CK(cudaMallocHost((void**)&q_h, (size_t)n * n * sizeof(double))); q_dev.alloc((size_t)n * n * sizeof(double)); }
     cnt.alloc((size_t)n * n * sizeof(unsigned long long));
     root_out.alloc(sizeof(int));
@@ -791,6 +876,7 @@ struct ChainT : pm_chain {
     if (const char* v = getenv("PHYLOMAP_B200_K1_UNROLL")) k1_variant = atoi(v);
     if (const char* v = getenv("PHYLOMAP_B200_DEBUG_SYNC")) debug_sync = v[0] == '1';
 
+    mark("pinned buffers, replay table");
     // shared-memory sizes
     const int np_fast = exact ? 0 : ((NS == 2 || NS == 4) ? std::min(PM_SMEM_POW, jcap) : 0);
     smem_prune = ((size_t)n * n + (size_t)np_fast * n * n) * sizeof(Real);
@@ -828,6 +914,7 @@ struct ChainT : pm_chain {
       P.root = t.sch.root;
       P.tipcode = t.tipcode.template as<uint8_t>(); P.TS = t.TS; P.node_state = t.node_state.template as<uint8_t>();
       P.meta = t.meta.template as<uint32_t>(); P.PL = t.PL.template as<Real>();
+      P.tile_base = 0; P.pl_S = t.pl_tile; P.rec_shift = t.rec_shift; P.rec_groups = t.rec_groups; P.ctl = nullptr;
       for (int b = 0; b < 2; b++) { P.rec_len[b] = t.rec_len[b].template as<Real>(); P.rec_st[b] = t.rec_st[b].template as<uint8_t>(); }
       // per-node rescaling (makePLrcpp_bigtree :525) only rescales the weights of each draw: the production
       // arithmetic always applies it (FP32 partials underflow after ~40 tips otherwise); the deterministic mode
@@ -862,6 +949,7 @@ struct ChainT : pm_chain {
           pm::k_init_tips<int32_t><<<g, b, 0, stream>>>(stage.as<int32_t>(), ns, s0, t.S, t.TS, T, n, V.parity_tips, t.tipcode.template as<uint8_t>(), P.node_state, P.err_flag);
         CK(cudaStreamSynchronize(stream));
       }
+      mark("tip states: H2D + transpose");
       const long long tot = t.S * E;
       if (!V.exp && !V.llonly)
         pm::k_init_meta<Real><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(P.maps_off, P.maps_len, t.S, E, P.meta, P.e_len, exact ? nullptr : P.shape);
@@ -881,6 +969,7 @@ struct ChainT : pm_chain {
       CK(cudaGetLastError());
     }
     check_device_errors();
+    mark("init kernels + sync");
   }
 
   // sum `count` doubles at device address `buf` over the ranks, in stream order (no-op for a single process)
@@ -956,8 +1045,33 @@ struct ChainT : pm_chain {
     if (!V.rates) {
       ensure_rows(count);
       TreeDev<Real>& t = *trees[0];
+      // small problems: the first sweep of the call goes out launch by launch (it also sets the kernels' attributes), the
+      // others replay a captured sweep
+      const bool small = (double)t.S * t.sch.E <= (double)(1 << 22);
+      const bool use_graph = !V.exp && !timing && !debug_sync && count > 1 && (graph_mode == 1 || (graph_mode != 0 && small));
       for (int i = 0; i < count; i++) {
         if (V.exp) launch_exp_iteration(t, (uint32_t)(iters_done + i), rows.as<double>() + (size_t)i * WR);
+        else if (use_graph && i > 0) {
+          if (i == 1) {
+            if (sweep_graph && graph_rows != rows.p) { cudaGraphExecDestroy(sweep_graph); sweep_graph = nullptr; }
+            if (!sweep_graph) {
+              cudaGraph_t g = nullptr;
+              CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
+              capturing = true;
+              try { launch_sweep(t, 1u, rows.as<double>()); } catch (...) { capturing = false; cudaStreamEndCapture(stream, &g); if (g) cudaGraphDestroy(g); throw; }
+              capturing = false;
+              CK(cudaStreamEndCapture(stream, &g));
+              const cudaError_t ge = cudaGraphInstantiate(&sweep_graph, g, 0);
+              cudaGraphDestroy(g);
+              if (ge != cudaSuccess) fail(PM_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ge));
+              graph_rows = rows.p;
+            }
+            ctl_h[0] = (uint32_t)(iters_done + 1); ctl_h[1] = 1u;
+            CK(cudaMemcpyAsync(ctl.p, ctl_h, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+          }
+          CK(cudaGraphLaunch(sweep_graph, stream));
+          launches += launches_per_sweep;
+        }
         else launch_sweep(t, (uint32_t)(iters_done + i), rows.as<double>() + (size_t)i * WR);
         if (opt.progress) { printf("%i \r", iters_done + i); }
       }
@@ -1042,7 +1156,6 @@ struct ChainT : pm_chain {
     CK(cudaEventElapsedTime(&ms, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
     CK(cudaGetLastError());
-    launches += reps + 1;
     return ms / reps;
   }
 
@@ -1071,7 +1184,7 @@ struct ChainT : pm_chain {
     const int cap_c = t.cap_off_h[c + 1] - t.cap_off_h[c];
     const int buf = (iters_done - 1) & 1;
     auto records = [&](long long pos, int count) {
-      const size_t base = (size_t)t.cap_off_h[c] * t.S + (size_t)site * cap_c + pos;
+      const size_t base = (size_t)t.cap_off_h[c] * t.rec_groups + (size_t)(site >> t.rec_shift) * cap_c + pos;
       for (int k = 0; k < count && k < cap; k++) {
         Real L; uint8_t s;
         CK(cudaMemcpy(&L, t.rec_len[buf].template as<Real>() + base + k, sizeof(Real), cudaMemcpyDeviceToHost));
@@ -1112,7 +1225,7 @@ struct ChainT : pm_chain {
     long long pos = (long long)q;  // paths with two or more real jumps: the offset of their records in the site's slice
     if (nj == 63) {  // 64 runs or more: a header record holds the count
       Real cntv;
-      CK(cudaMemcpy(&cntv, t.rec_len[buf].template as<Real>() + (size_t)t.cap_off_h[c] * t.S + (size_t)site * cap_c + pos, sizeof(Real),
+      CK(cudaMemcpy(&cntv, t.rec_len[buf].template as<Real>() + (size_t)t.cap_off_h[c] * t.rec_groups + (size_t)(site >> t.rec_shift) * cap_c + pos, sizeof(Real),
                     cudaMemcpyDeviceToHost));
       nj = (int)cntv - 1;
       pos += 1;
@@ -1121,7 +1234,7 @@ struct ChainT : pm_chain {
     return nj + 1;
   }
   // ---- checkpoint / resume: everything a sweep reads that is not an input of pm_chain_create ----
-  static constexpr uint32_t PM_STATE_FORMAT = 4;  // 1: round 1 (per-site masks); 2: branch-major ballots, global record cursors; 3: two-run paths count their virtual jumps together; 4: 16-bit positions inside meta, shape words
+  static constexpr uint32_t PM_STATE_FORMAT = 5;  // 5: production record slices shared by groups of 32 sites; 1: round 1 (per-site masks); 2: branch-major ballots, global record cursors; 3: two-run paths count their virtual jumps together; 4: 16-bit positions inside meta, shape words
   struct StateHeader {
     char magic[8];
     int32_t variant, n, ntrees, precision, mode, T, E, iters_done, jcap, reserved;
@@ -1155,7 +1268,7 @@ struct ChainT : pm_chain {
     uint32_t hsh = 2166136261u;
     auto mix = [&](uint32_t v) { hsh = (hsh ^ v) * 16777619u; };
     mix(PM_STATE_FORMAT); mix(PM_META(1, 2)); mix((uint32_t)PM_SHAPE(1, 2, 3)); mix(PM_LAMBDA_INV); mix(PM_LOCAL_PATH_MAX); mix(PM_SMEM_POW);
-    for (auto& t : trees) { mix((uint32_t)t->chunk); for (int c : t->cap_off_h) mix((uint32_t)c); }
+    for (auto& t : trees) { mix((uint32_t)t->chunk); mix((uint32_t)t->rec_shift); for (int c : t->cap_off_h) mix((uint32_t)c); }
     h.reserved = (int32_t)((PM_STATE_FORMAT << 24) | (hsh & 0xffffffu));
     return h;
   }
@@ -1232,8 +1345,15 @@ struct ChainT : pm_chain {
     if (site < 0 || site >= t.S) fail(PM_ERR_ARG, "bad site");
     std::fill(out, out + (size_t)(2 * T - 1) * n, 0.0);
     std::vector<Real> v(n);
+    long long lsite = site;
+    if (t.pl_tile < t.S) {  // tiled partials: the buffer holds the last tile of the last pass; prune the tile of `site` on the current state
+      CK(cudaSetDevice(opt.device));
+      launch_prune(t, site);
+      CK(cudaStreamSynchronize(stream));
+      lsite = site % t.pl_tile;
+    }
     for (int i = 0; i < T - 1; i++) {
-      CK(cudaMemcpy(v.data(), t.PL.template as<Real>() + ((size_t)i * t.S + site) * n, n * sizeof(Real), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(v.data(), t.PL.template as<Real>() + ((size_t)i * t.pl_tile + lsite) * n, n * sizeof(Real), cudaMemcpyDeviceToHost));
       for (int j = 0; j < n; j++) out[(size_t)(T + i) * n + j] = (double)v[j];
     }
   }
@@ -1243,10 +1363,10 @@ template <> void ChainT<double>::launch_sweep(TreeDev<double>& t, uint32_t iter,
   if (exact) launch_sweep_e<true>(t, iter, row); else launch_sweep_e<false>(t, iter, row);
 }
 template <> void ChainT<float>::launch_sweep(TreeDev<float>& t, uint32_t iter, double* row) { launch_sweep_e<false>(t, iter, row); }
-template <> void ChainT<double>::launch_prune(TreeDev<double>& t) {
-  if (exact) launch_prune_e<true>(t); else launch_prune_e<false>(t);
+template <> void ChainT<double>::launch_prune(TreeDev<double>& t, long long only_site) {
+  if (exact) launch_prune_e<true>(t, only_site); else launch_prune_e<false>(t, only_site);
 }
-template <> void ChainT<float>::launch_prune(TreeDev<float>& t) { launch_prune_e<false>(t); }
+template <> void ChainT<float>::launch_prune(TreeDev<float>& t, long long only_site) { launch_prune_e<false>(t, only_site); }
 
 struct EigenIn { const double* lefts; const double* rights; const double* d; };
 

@@ -46,6 +46,18 @@ struct ChainParams {
   int root;
   const uint8_t* tipcode; long long TS;  // tip codes [T][TS]: rows padded to a multiple of 16 sites (4-byte aligned cp.async)
   uint8_t* node_state; uint32_t* meta; Real* PL;
+  // production pruning / node kernels (n = 2, 4) work on one SITE TILE at a time: a launch covers the sites
+  // [tile_base, tile_base + 32 gridDim.x) and PL holds pl_S sites per node row, indexed by site - tile_base (the partials
+  // are per-sweep scratch between K1 and K2, so one tile's worth is all that is ever resident).  Everywhere else
+  // tile_base = 0 and pl_S = S.
+  long long tile_base, pl_S;
+  // production path records: the slice of a branch chunk is shared by the 2^rec_shift consecutive sites of a group
+  // (rec_groups groups per chunk): layout [chunk][group][cap], cursor [chunk][group]
+  int rec_shift; long long rec_groups;
+  // CUDA-graph replay of a sweep (small problems, where launch overhead dominates): the sweep index is read from device
+  // memory instead of the kernel argument, so one instantiated graph serves every sweep.  ctl[0] = index of the sweep to
+  // run, ctl[1] = row of the statistics block it fills; k_reduce advances both.  nullptr: the arguments hold.
+  const uint32_t* ctl;
   // production: branches left to k_paths_hard, one bit per site: hard_ballot[e * W + w] covers sites 32 w .. 32 w + 31.
   // k_paths_hard walks them as work items of wk_g[e] consecutive words of one branch; branch e owns the items
   // [wk_off[e], wk_off[e + 1]) (sized on the host so that an item holds ~100 set bits whatever the branch length).
@@ -53,7 +65,7 @@ struct ChainParams {
   const long long* wk_off; const int* wk_g; long long wk_total;
   const int* wk_hint;  // [wk_total / 64 + 1] branch that owns work item 64 i
   int tune;            // PHYLOMAP_B200_TUNE (experiments)
-  int* rec_cursor;  // [n_chunks][S] records appended so far to the slice of (chunk, site) in this sweep
+  int* rec_cursor;  // [n_chunks][rec_groups] records appended so far to the slice of (chunk, site group) in this sweep
   int chunk;        // branches per record chunk
   long long easy_blocks;  // blocks of k_paths_easy: k_paths_hard's dwell partials follow theirs in dw_partial
   // production: meta[e][s] = m | q << 16, q = 16-bit position (pos_dec) of the jump point of a path with one jump point
@@ -216,7 +228,7 @@ __global__ void __launch_bounds__(256, MINB) k_prune_pipe(ChainParams<Real> P) {
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long S = P.S;
-  const long long site_raw = (long long)blockIdx.x * 32 + lane;
+  const long long site_raw = P.tile_base + (long long)blockIdx.x * 32 + lane;
   const bool active = site_raw < S;
   const long long site = active ? site_raw : S - 1;
   const bool parity = P.parity_tips != 0;
@@ -224,8 +236,8 @@ __global__ void __launch_bounds__(256, MINB) k_prune_pipe(ChainParams<Real> P) {
   const int T = P.T;
   const uint32_t* __restrict__ meta = P.meta + site;
   const uint8_t* __restrict__ tip = P.tipcode + site;
-  Real* PLs = P.PL + site * NS;
-  const long long rowPL = S * NS;
+  Real* PLs = P.PL + (site - P.tile_base) * NS;
+  const long long rowPL = P.pl_S * NS;
   const int4* __restrict__ ent = reinterpret_cast<const int4*>(P.up_entries8);  // (pn, a, ea, b) (eb, -, -, -)
 
   auto load = [&](PruneNode<Real, NS>* nd, int idx, int end) {
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long S = P.S;
-  const long long site0 = (long long)blockIdx.x * 32;
+  const long long site0 = P.tile_base + (long long)blockIdx.x * 32;
   const long long site_raw = site0 + lane;
   const bool active = site_raw < S;
   const long long site = active ? site_raw : S - 1;
@@ -379,8 +391,8 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
   const int T = P.T;
   const uint32_t* __restrict__ meta = P.meta + site;
   const uint8_t* __restrict__ tip = P.tipcode + site;
-  Real* PLs = P.PL + site * NS;  // read and written by this thread: no __restrict__, no read-only loads
-  const long long rowPL = S * NS;
+  Real* PLs = P.PL + (site - P.tile_base) * NS;  // read and written by this thread: no __restrict__, no read-only loads
+  const long long rowPL = P.pl_S * NS;
 
   auto contribution = [&](int k, int code, Real* v) {
     if (code >= 0 && !parity && k < npow_s) {
@@ -612,6 +624,7 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
 // ------------------------------------------------------------------------------------------------
 template <typename Real, int NS, bool EXACT>
 __global__ void __launch_bounds__(256) k_nodes(ChainParams<Real> P, uint32_t iter) {
+  if (P.ctl) iter = P.ctl[0];
   constexpr int NC = NS > 0 ? NS : PM_NMAX;
   typedef typename StreamSel<Real, EXACT>::type Stream;
   const int n = NS > 0 ? NS : P.n;
@@ -685,6 +698,7 @@ template <> __device__ __forceinline__ double u01_from_word<double>(uint32_t x) 
 // ------------------------------------------------------------------------------------------------
 template <typename Real, int NS, bool EXACT>
 __global__ void __launch_bounds__(128) k_paths(ChainParams<Real> P, uint32_t iter, int first, int chunk) {
+  if (P.ctl) { iter = P.ctl[0]; first = iter == 0u; }
   constexpr int NC = NS > 0 ? NS : PM_NMAX;
   typedef typename StreamSel<Real, EXACT>::type Stream;
   typedef ExpDev<Real, EXACT> Exp;
@@ -901,6 +915,7 @@ __device__ __forceinline__ int draw_node_state(const ChainParams<Real>& P, const
 
 template <typename Real, int NS, int DEPTH, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, uint32_t iter) {
+  if (P.ctl) iter = P.ctl[0];
   constexpr int PB = NS * (int)sizeof(Real);  // bytes of one partial
   constexpr int PLB = 32 * PB;
   constexpr int SLOT = PLB + 160;
@@ -913,9 +928,10 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long S = P.S;
-  const long long site_raw = (long long)blockIdx.x * 32 + lane;
+  const long long site_raw = P.tile_base + (long long)blockIdx.x * 32 + lane;
   const bool active = site_raw < S;
   const long long site = active ? site_raw : S - 1;
+  const long long lsite = site - P.tile_base;  // index of the site in the partials of this tile
   const bool parity = P.parity_tips != 0;
   const int T = P.T;
   const uint32_t gsite = P.rng.site0 + (uint32_t)site;
@@ -923,7 +939,7 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
   uint8_t* const nst = P.node_state + site;  // read and written by this thread
   if (warp == 0) {  // root :618-627
     Real w[NS], pl[NS];
-    VecIO<Real, NS>::load(P.PL + ((long long)(P.root - T) * S + site) * NS, NS, pl);
+    VecIO<Real, NS>::load(P.PL + ((long long)(P.root - T) * P.pl_S + lsite) * NS, NS, pl);
 #pragma unroll
     for (int j = 0; j < NS; j++) w[j] = sVec[j] * pl[j];
     uint32_t o[4];
@@ -943,7 +959,7 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
       const int ps = nst[(long long)en.y * S];
       const int k = (int)(P.meta[(long long)en.z * S + site] & 0xffffu) - 1;
       Real pl[NS];
-      VecIO<Real, NS>::load(P.PL + ((long long)(en.x - T) * S + site) * NS, NS, pl);
+      VecIO<Real, NS>::load(P.PL + ((long long)(en.x - T) * P.pl_S + lsite) * NS, NS, pl);
       uint32_t o[4];
       philox4x32_10_rk(0x80000000u + (uint32_t)idx, kslot, iter, gsite, P.rng.rk, o);
       const int s = draw_node_state<Real, NS>(P, sBs, sPow, npow_s, k, ps, pl, o[0]);
@@ -956,7 +972,7 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
     const int i0 = __ldg(P.cd_warp_off + warp), i1 = __ldg(P.cd_warp_off + warp + 1);
     unsigned ring = (unsigned)__cvta_generic_to_shared(smem_raw) + warp * (DEPTH * SLOT);
     asm volatile("" : "+r"(ring));  // kept in a register (see k_prune_clade)
-    unsigned long long plb_u = reinterpret_cast<unsigned long long>(P.PL + site * NS),
+    unsigned long long plb_u = reinterpret_cast<unsigned long long>(P.PL + lsite * NS),
                        mtb_u = reinterpret_cast<unsigned long long>(P.meta + site),
                        nsb_u = reinterpret_cast<unsigned long long>(nst);
     int act = active ? 1 : 0;
@@ -1098,6 +1114,7 @@ __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)
 
 template <typename Real, int NS>
 __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy(ChainParams<Real> P, uint32_t iter, int chunk) {
+  if (P.ctl) iter = P.ctl[0];
   constexpr int NR = NS > 0 ? NS : 1;
   typedef Pin<Real> PN;
   const int n = NS > 0 ? NS : P.n;
@@ -1362,6 +1379,7 @@ struct HardItem { uint32_t site, e, meta, ends, shape; };  // ends = parent stat
 // the ballot bits of the items it takes.  WHICH = 1: whatever is left.
 template <typename Real, int NS, int MINB, int WHICH>
 __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, uint32_t iter, int first) {
+  if (P.ctl) { iter = P.ctl[0]; first = iter == 0u; }
   constexpr int NC = NS > 0 ? NS : PM_NMAX;
   constexpr int NR = NS > 0 ? NS : 1;
   typedef typename StreamSel<Real, false>::type Stream;
@@ -1438,7 +1456,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     if (nj >= 2) {
       const int ck = eb / P.chunk;
       const int cap0 = __ldg(P.cap_off + ck), cap_c = __ldg(P.cap_off + ck + 1) - cap0;
-      const long long sl = (long long)cap0 * S + site * (long long)cap_c;
+      const long long sl = ((long long)cap0 * P.rec_groups) + (site >> P.rec_shift) * (long long)cap_c;
       const int rd0 = (int)(mt >> 16);
       J0 = rd_len[sl + min(rd0, cap_c - 1)];
       J1 = PN::add(J0, rd_len[sl + min(rd0 + 1, cap_c - 1)]);
@@ -1549,8 +1567,8 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
         if (nout == 4) newm += poisson_inv<Real>(PN::mul(rate_or_zero(s_rate_new[S3]), L3), cw[1]);
         const int ck = eb / P.chunk;
         const int cap0 = __ldg(P.cap_off + ck), cap_c = __ldg(P.cap_off + ck + 1) - cap0;
-        const long long sl = (long long)cap0 * S + site * (long long)cap_c;
-        const int base = atomicAdd(P.rec_cursor + (long long)ck * S + site, nout);
+        const long long sl = ((long long)cap0 * P.rec_groups) + (site >> P.rec_shift) * (long long)cap_c;
+        const int base = atomicAdd(P.rec_cursor + (long long)ck * P.rec_groups + (site >> P.rec_shift), nout);
         newq = (uint32_t)base;
         if (base + nout > cap_c) errbits |= PM_DE_PATH_CAP;
         else {
@@ -1572,8 +1590,8 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     const uint32_t mt = it.meta;
     const int ck = eb / P.chunk;
     const int cap0 = __ldg(P.cap_off + ck), cap_c = __ldg(P.cap_off + ck + 1) - cap0;
-    const long long sbase = (long long)cap0 * S + site * (long long)cap_c;  // this site's record slice of the chunk
-    int* cursor = P.rec_cursor + (long long)ck * S + site;
+    const long long sbase = ((long long)cap0 * P.rec_groups) + (site >> P.rec_shift) * (long long)cap_c;  // record slice of the site's group
+    int* cursor = P.rec_cursor + (long long)ck * P.rec_groups + (site >> P.rec_shift);
 
     const long long pe = (long long)eb * S + site;
     const int m = (int)(mt & 0xffffu);

@@ -10,8 +10,10 @@ namespace pm {
 // row[err_slot] receives this rank's device error flag (summed over ranks by the all-reduce that follows).
 __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ dw_partial, long long nblocks, int n,
                                                 unsigned long long* cnt, const int* root, double* row, int accumulate,
-                                                const unsigned* err_flag, int err_slot) {
+                                                const unsigned* err_flag, int err_slot, uint32_t* ctl = nullptr,
+                                                int row_stride = 0) {
   __shared__ double sh[256];
+  if (ctl) row += (size_t)ctl[1] * row_stride;  // graph replay: the row index lives in device memory (ChainParams::ctl)
   for (int j = 0; j < n; j++) {
     double acc = 0;
     for (long long b = threadIdx.x; b < nblocks; b += 256) acc += dw_partial[b * n + j];
@@ -24,6 +26,10 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ dw_pa
   for (int i = threadIdx.x; i < n * n; i += 256) { row[n + i] = (accumulate ? row[n + i] : 0.0) + (double)cnt[i]; cnt[i] = 0ull; }
   if (threadIdx.x == 0 && !accumulate) row[n + n * n] = (double)(*root);
   if (threadIdx.x == 0 && err_flag) row[err_slot] = (double)(*err_flag);
+  if (ctl) {  // this sweep is complete: the next replay of the graph runs the next sweep into the next row
+    __syncthreads();
+    if (threadIdx.x == 0) { ctl[0] += 1u; ctl[1] += 1u; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -21,8 +21,15 @@ def cpu(variant, z, Q, pid, Om, N, fast):
 z = synth.simulate_2_state_tree(101, synth.yule_tree(100, seed=1, mean_branch=5.0), cases.Q2, cases.PID2)
 N = 1000
 for prec in ("f32", "f64"):
-    dt, _ = gpu(pb.sumstatMCMC, z, cases.Q2, cases.PID2, 0.2, N, seed=5, precision=prec)
-    out["cfg0_gpu_%s_us_per_sweep" % prec] = 1e6 * dt / N
+    for graph in ("1", "0"):   # replay of a captured sweep (the default at this size) against launch-by-launch
+        os.environ["PHYLOMAP_B200_GRAPH"] = graph
+        dt, _ = gpu(pb.sumstatMCMC, z, cases.Q2, cases.PID2, 0.2, N, seed=5, precision=prec)
+        out["cfg0_gpu_%s_%s_us_per_sweep" % (prec, "graph" if graph == "1" else "launches")] = 1e6 * dt / N
+del os.environ["PHYLOMAP_B200_GRAPH"]
+for S in (8, 32):   # a few characters at once on the same tree
+    zS = synth.simulate_2_state_tree(101, synth.yule_tree(100, seed=1, mean_branch=5.0), cases.Q2, cases.PID2, n_sites=S)
+    dt, _ = gpu(pb.sumstatMCMC, zS, cases.Q2, cases.PID2, 0.2, N, seed=5, precision="f32")
+    out["cfg0_gpu_f32_%d_sites_us_per_sweep" % S] = 1e6 * dt / N
 out["cfg0_cpu_port_faithful_us_per_sweep"] = 1e6 * cpu(bridge.PLAIN, z, cases.Q2, cases.PID2, 0.2, N, False) / N
 out["cfg0_cpu_port_optimised_us_per_sweep"] = 1e6 * cpu(bridge.PLAIN, z, cases.Q2, cases.PID2, 0.2, N, True) / N
 t = time.perf_counter(); bridge.ref_run(bridge.PLAIN, [z.oracle_dict()], cases.Q2, cases.PID2, 0.2, N, seed=3)

@@ -442,3 +442,84 @@ def test_site_tiles_equal_one_call(monkeypatch):
     np.testing.assert_allclose(tiled[:, :4], whole[:, :4], rtol=1e-5)
     ex_tiled = pb.sumstatEXP(z, Q, pid, 4, seed=22, precision="f32")
     assert np.array_equal(ex_tiled[:, 4:], ex_whole[:, 4:])
+
+
+@pytest.mark.parametrize("what", ["bigtree_f32", "ks_f32", "ksmt_f64"])
+def test_rows_do_not_depend_on_the_memory_layout(what, monkeypatch):
+    """Site-tiled partials (K1 -> K2 tile by tile, PHYLOMAP_B200_PL_TILE) and record slices shared by groups of 32 sites
+    (PHYLOMAP_B200_REC_POOL) only change where scratch and records live: every site draws from its own Philox keys, so the
+    rows -- counts, dwell times, rate traces -- must be identical bit for bit to the untiled / per-site layout, also when
+    the last tile is ragged, and a stored path must read back the same from either layout."""
+    N = 10
+    if what == "bigtree_f32":
+        Q = cases.q4()
+        z = cases.tree_n(Q, T=300, S=203, seed=5, mean_branch=1.5, segments=3)   # long branches: records in use
+        mk = lambda: pb.Chain(capi.PM_V_BIGTREE, z, Q.copy(), np.full(4, 0.25), 2.4, N, precision="f32", seed=11)
+    elif what == "ks_f32":
+        Q = cases.q4()
+        z = cases.tree_hidden(Q, T=90, S=150, seed=4, mean_branch=0.8)
+        mk = lambda: pb.Chain(capi.PM_V_KS, z, np.asfortranarray(Q.copy()), np.full(4, 0.25), 4.0, N, prior=cases.PRIOR_KS,
+                              precision="f32", seed=11)
+    else:
+        Q = cases.q4()
+        base = cases.tree_hidden(Q, T=40, S=70, seed=4, mean_branch=0.5)
+        trees = [base, pb.PhyloTree(base.edge, base.edge_length * 1.2).with_states(base.states, segments=3)]
+        mk = lambda: pb.Chain(capi.PM_V_KSMT, trees, np.asfortranarray(Q.copy()), np.full(4, 0.25), 4.0, N,
+                              prior=cases.PRIOR_KSMT, precision="f64", seed=11)
+
+    def run(tile, pool):
+        monkeypatch.setenv("PHYLOMAP_B200_PL_TILE", str(tile))
+        monkeypatch.setenv("PHYLOMAP_B200_REC_POOL", str(pool))
+        ch = mk()
+        rows = ch.run(N)
+        E = (z if what != "ksmt_f64" else trees[0]).E
+        paths = [ch.path(s, e, cap=256) for s in (0, 33, 69) for e in range(0, E, max(1, E // 12))]
+        pc = ch.piece_counts()
+        ch.time_prune(reps=1)                     # K1 alone on the final state: what partials() reports in either layout
+        pls = [ch.partials(s) for s in (0, 33, 69)]
+        ch.close()
+        return rows, paths, pc, pls
+
+    ref_rows, ref_paths, ref_pc, ref_pls = run(0, 0)   # untiled partials, one record slice per (site, chunk)
+    for tile, pool in [(64, 0), (0, 1), (32, 1), (96, 1)]:
+        rows, paths, pc, pls = run(tile, pool)
+        for a, b in zip(ref_pls, pls):
+            assert np.array_equal(a, b)
+        assert np.array_equal(rows, ref_rows), "rows differ with PL tile %d, pooled records %d" % (tile, pool)
+        assert np.array_equal(pc, ref_pc)
+        for (l0, s0), (l1, s1) in zip(ref_paths, paths):
+            assert np.array_equal(l0, l1) and np.array_equal(s0, s1)
+
+
+@pytest.mark.parametrize("what", ["plain_f32_one_site", "bigtree_f64", "plain_deterministic", "sparse_f32_generic_n"])
+def test_graph_replay_gives_the_rows_of_plain_launches(what, monkeypatch):
+    """Small problems replay one captured sweep (CUDA graph, sweep index and output row in device memory) instead of
+    launching every kernel from the host: the rows must be those of the launch-by-launch run, bit for bit, across several
+    pm_chain_run calls of different lengths (the statistics buffer moves: the graph is captured again)."""
+    if what == "plain_f32_one_site":
+        z = cases.tree2(T=100, S=1, seed=1, mean_branch=5.0)
+        mk = lambda: pb.Chain(capi.PM_V_PLAIN, z, cases.Q2, cases.PID2, 0.2, 64, precision="f32", seed=5)
+    elif what == "bigtree_f64":
+        Q = cases.q4()
+        z = cases.tree_n(Q, T=60, S=45, seed=5, mean_branch=1.5, segments=3)
+        mk = lambda: pb.Chain(capi.PM_V_BIGTREE, z, Q.copy(), np.full(4, 0.25), 2.4, 64, precision="f64", seed=11)
+    elif what == "plain_deterministic":
+        z = cases.tree2(T=30, S=3, seed=2, mean_branch=3.0)
+        mk = lambda: pb.Chain(capi.PM_V_PLAIN, z, cases.Q2, cases.PID2, 0.2, 64, precision="f64", mode="deterministic", seed=5)
+    else:
+        Q = cases.jc(5, 0.1)
+        z = cases.tree_n(Q, T=40, S=9, seed=3, mean_branch=1.0, segments=2)
+        mk = lambda: pb.Chain(capi.PM_V_SPARSE, z, Q.copy(), np.full(5, 0.2), 1.0, 64, precision="f32", seed=7)
+
+    def run(graph):
+        monkeypatch.setenv("PHYLOMAP_B200_GRAPH", str(graph))
+        ch = mk()
+        rows = np.vstack([ch.run(5), ch.run(1), ch.run(30), ch.run(28)])
+        ns = ch.node_states()
+        ch.close()
+        return rows, ns
+
+    ref, ns0 = run(0)
+    got, ns1 = run(1)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(ns0, ns1)
