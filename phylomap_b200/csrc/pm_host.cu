@@ -276,7 +276,10 @@ struct TreeDev {
   DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, hard_ballot, wk_off, wk_g, wk_hint, rec_cursor, shape;
   long long wk_total = 0, dw_rows = 0;
   int hard_blocks = 0;
-  long long pl_tile = 0;     // sites per pruning / node-draw launch (= sites the partials buffer holds); S when not tiled
+  int pl_slots = 0;          // 32-site slots of the partials buffer (fused prune + node-draw kernel: SMs x resident blocks per SM); 0: separate kernels, partials of all sites
+  int slots_per_sm = 0;
+  DevBuf slot_busy;          // one flag per slot
+  long long pl_sites = 0;    // sites per node row of the partials buffer: 32 pl_slots, or S
   int rec_shift = 0;         // production path records: 2^rec_shift consecutive sites share a slice
   long long rec_groups = 0;
   DevBuf e_len_d, TP, ll_partial;  // DIC samplers: branch lengths in FP64, exp(Q t_e) per branch, block partials of log p(y|Q)
@@ -323,7 +326,7 @@ struct ChainT : pm_chain {
   // CUDA-graph replay of one sweep (fixed-Q samplers on small problems: a sweep of a 100-tip tree is seven launches of a
   // few microseconds each, and the host cannot issue them as fast as the GPU retires them).  The sweep index and the
   // output row live in device memory (ChainParams::ctl), so one instantiated graph serves every sweep of the chain.
-  DevBuf ctl;
+  DevBuf ctl, phase_ns;               // phase_ns: block-nanoseconds the fused kernel spent pruning / drawing nodes (timing on)
   uint32_t* ctl_h = nullptr;          // pinned
   cudaGraphExec_t sweep_graph = nullptr;
   void* graph_rows = nullptr;         // the rows buffer the graph writes to (re-captured if it moves)
@@ -397,19 +400,24 @@ struct ChainT : pm_chain {
 
   template <int NSc, bool EX>
   void launch_sweep_t(TreeDev<Real>& t, uint32_t iter, double* row) {
-    int ntiles = 0;
     const uint32_t* ctl_d = capturing ? ctl.as<uint32_t>() : nullptr;
-    for (long long b = 0; b < t.S; b += t.pl_tile, ntiles++) {  // K1 -> K2 per site tile (one tile unless the partials are tiled)
+    {
       pm::ChainParams<Real> P = t.P;
-      P.tile_base = b;
       P.ctl = ctl_d;
-      const int gx = (int)((std::min(t.pl_tile, t.S - b) + 31) / 32);
-      begin_timed(0);
-      pm::Sweep<Real, NSc, EX>::prune(P, gx, prune_smem(t), stream, k1_variant);
-      end_timed();
-      begin_timed(1);
-      pm::Sweep<Real, NSc, EX>::nodes(P, gx, smem_nodes, stream, iter);
-      end_timed();
+      const int gx = (int)((t.S + 31) / 32);
+      if (t.pl_slots) {  // K1 + K2 in one launch; with timing on, the blocks report the time they spend in each pass
+        begin_timed(4);
+        pm::Sweep<Real, NSc, EX>::prune_nodes(P, gx, smem_nodes, stream, iter, 0, 3, t.slots_per_sm ? t.slot_busy.template as<int>() : nullptr,
+                                              t.slots_per_sm, timing ? phase_ns.as<unsigned long long>() : nullptr);
+        end_timed();
+      } else {
+        begin_timed(0);
+        pm::Sweep<Real, NSc, EX>::prune(P, gx, prune_smem(t), stream, k1_variant);
+        end_timed();
+        begin_timed(1);
+        pm::Sweep<Real, NSc, EX>::nodes(P, gx, smem_nodes, stream, iter);
+        end_timed();
+      }
     }
     begin_timed(2);
     if (!EX) CK(cudaMemsetAsync(t.rec_cursor.p, 0, t.rec_cursor.bytes, stream));  // (inside K3's timed region: it is part of the step)
@@ -425,7 +433,7 @@ struct ChainT : pm_chain {
     pm::k_reduce<<<1, 256, 0, stream>>>(t.dw_partial.template as<double>(), t.dw_rows, n, cnt.as<unsigned long long>(),
                                         root_out.as<int>(), row, 0, err_flag.as<unsigned>(), W, capturing ? ctl.as<uint32_t>() : nullptr, WR);
     end_timed();
-    launches_per_sweep = 2 * ntiles + (exact ? 2 : (iter == 0 && !capturing) ? 3 : 4);
+    launches_per_sweep = (t.pl_slots ? 1 : 2) + (exact ? 2 : (iter == 0 && !capturing) ? 3 : 4);
     if (!capturing) launches += launches_per_sweep;
   }
   // DIC samplers: log p(y | Q) of the current Q into row[n + n*n + 1] (after the sweep: PL is free again)
@@ -446,13 +454,13 @@ struct ChainT : pm_chain {
   // the pruning pass alone: over all site tiles, or over the one tile that holds `only_site`
   template <int NSc, bool EX>
   void launch_prune_t(TreeDev<Real>& t, long long only_site) {
-    for (long long b = 0; b < t.S; b += t.pl_tile) {
-      if (only_site >= 0 && (only_site < b || only_site >= b + t.pl_tile)) continue;
-      pm::ChainParams<Real> P = t.P;
-      P.tile_base = b;
-      pm::Sweep<Real, NSc, EX>::prune(P, (int)((std::min(t.pl_tile, t.S - b) + 31) / 32), prune_smem(t), stream, k1_variant);
-      launches++;
-    }
+    const long long nb = (t.S + 31) / 32;
+    if (t.pl_slots) {  // the pruning pass of the fused kernel: all site blocks, or the one that holds `only_site` (it lands in slot 0)
+      if (only_site >= 0) pm::Sweep<Real, NSc, EX>::prune_nodes(t.P, 1, smem_nodes, stream, 0u, only_site / 32, 1, nullptr, 0, nullptr);
+      else pm::Sweep<Real, NSc, EX>::prune_nodes(t.P, (int)nb, smem_nodes, stream, 0u, 0, 1, t.slots_per_sm ? t.slot_busy.template as<int>() : nullptr,
+                                                 t.slots_per_sm, nullptr);
+    } else pm::Sweep<Real, NSc, EX>::prune(t.P, (int)nb, prune_smem(t), stream, k1_variant);
+    launches++;
   }
 
   template <bool EX>
@@ -486,13 +494,23 @@ struct ChainT : pm_chain {
     }
   }
   void collect_timed() {
+    double fused = 0;
     for (auto& t : timed) {
       float ms = 0;
       cudaEventElapsedTime(&ms, t.a, t.b);
-      kernel_ms[t.k] += ms;
+      if (t.k == 4) fused += ms; else kernel_ms[t.k] += ms;
       cudaEventDestroy(t.a); cudaEventDestroy(t.b);
     }
     timed.clear();
+    if (fused > 0) {  // the fused kernel's time goes to the two passes in proportion to the block-time spent in each
+      unsigned long long ns[2] = {0, 0};
+      cudaMemcpy(ns, phase_ns.p, sizeof ns, cudaMemcpyDeviceToHost);
+      cudaMemset(phase_ns.p, 0, sizeof ns);
+      const double tot = (double)ns[0] + (double)ns[1];
+      const double share = tot > 0 ? (double)ns[0] / tot : 0.5;
+      kernel_ms[0] += fused * share;
+      kernel_ms[1] += fused * (1.0 - share);
+    }
   }
 
   void check_device_errors() {
@@ -693,16 +711,28 @@ struct ChainT : pm_chain {
       }
       const long long R = t->cap_off_h[ny];
       mark("record capacities");
-      // Partials are scratch between the pruning pass and the node draws of one sweep: the production kernels (n = 2, 4)
-      // run K1 -> K2 site tile by site tile, so the buffer holds one tile.  A tile is two full waves of the pruning
-      // kernel's grid (3 blocks of 32 sites per SM in FP32, 2 in FP64): every launch but the last fills the GPU evenly.
-      // The DIC chains evaluate log p(y | Q) over all sites after the sweep and keep the whole array, like the generic and
-      // the deterministic kernels.
-      t->pl_tile = S;
-      if (!exact && (NS == 2 || NS == 4) && !V.dic && !V.exp && !V.llonly) {
-        long long tile = 32LL * prop.multiProcessorCount * (sizeof(Real) == 8 ? 2 : 3) * 2;
-        if (const char* v = getenv("PHYLOMAP_B200_PL_TILE")) tile = atoll(v) <= 0 ? S : (atoll(v) + 31) / 32 * 32;
-        t->pl_tile = std::min(S, tile);
+      // Partials are scratch between the pruning pass and the node draws of one sweep, and a block's partials are read by
+      // nobody but the same block's node draws: the production kernels (n = 2, 4) run both passes in ONE kernel whose
+      // blocks keep their partials in a slot of 32 sites, claimed for the life of the block (k_prune_nodes_clade): as many
+      // slots per SM as blocks can be resident there (3 in FP32, 2 in FP64: the occupancy the runtime reports for the
+      // smallest shared-memory configuration, an upper bound).  The DIC chains evaluate log p(y | Q) over all sites after
+      // the sweep and keep the whole array, like the generic and the deterministic kernels.
+      // PHYLOMAP_B200_FUSED=0: the two separate kernels and the full array (for comparison).
+      t->pl_slots = 0;
+      t->pl_sites = S;
+      if (!exact && (NS == 2 || NS == 4) && !V.dic && !V.exp && !V.llonly && !(getenv("PHYLOMAP_B200_FUSED") && getenv("PHYLOMAP_B200_FUSED")[0] == '0')) {
+        const size_t smem_lo = ((size_t)n * n + 3 * n) * sizeof(Real);
+        const int per_sm = NS == 2 ? pm::Sweep<Real, 2, false>::fused_blocks_per_sm(smem_lo) : pm::Sweep<Real, 4, false>::fused_blocks_per_sm(smem_lo);
+        if (per_sm < 1) fail(PM_ERR_CUDA, "cudaOccupancyMaxActiveBlocksPerMultiprocessor failed for the fused prune + node-draw kernel");
+        t->slots_per_sm = per_sm;
+        t->pl_slots = prop.multiProcessorCount * per_sm;
+        t->pl_sites = 32LL * t->pl_slots;
+        if (t->pl_sites >= ((S + 31) / 32) * 32) {  // fewer site blocks than slots: block i uses slot i
+          t->pl_slots = (int)((S + 31) / 32); t->pl_sites = 32LL * t->pl_slots; t->slots_per_sm = 0;
+        } else {
+          t->slot_busy.alloc((size_t)t->pl_slots * sizeof(int));
+          CK(cudaMemsetAsync(t->slot_busy.p, 0, t->slot_busy.bytes, stream));
+        }
       }
       upload(t->up_entries, t->sch.up_entries, stream);
       {
@@ -712,8 +742,11 @@ struct ChainT : pm_chain {
       }
       upload(t->up_off, t->sch.up_off, stream);
       if (!exact && (NS == 2 || NS == 4)) {
-        // clades of ~1/64 of the tree: ~8 per warp to balance, and only ~100 nodes left above them
-        int clade_max = std::max(8, std::min(512, (T - 1) / 64));
+        // clades of ~1/64 of the tree: ~8 per warp to balance, and only ~100 nodes left above them.  Small trees (where a
+        // sweep is a matter of latency, not throughput): ~1/8 of the tree, so that almost every node is walked inside a
+        // warp's prefetched sequence and only a few levels with block barriers are left above.  (A function of the tree
+        // alone: the node draws are keyed by schedule position, and a site must not depend on how many others run.)
+        int clade_max = (T - 1 < 512) ? std::max(8, (T - 1) / 8) : std::max(8, std::min(512, (T - 1) / 64));
         if (const char* v = getenv("PHYLOMAP_B200_CLADE")) clade_max = std::max(1, atoi(v));
         pm::host::CladeSchedule cs;
         pm::host::build_clade_schedule(t->sch, 8, clade_max, cs);
@@ -721,7 +754,7 @@ struct ChainT : pm_chain {
         const int n1 = cs.warp_off.back();
         std::vector<int> e16((size_t)PM_CLADE_ENTRY_INTS * (n1 + 17), 0);  // padded: the kernel forms addresses up to 16 entries ahead
         auto put64 = [](int* dst, long long v) { dst[0] = (int)(unsigned)(v & 0xffffffffLL); dst[1] = (int)(v >> 32); };
-        const long long rowPL = (long long)t->pl_tile * n * (long long)sizeof(Real);
+        const long long rowPL = (long long)t->pl_sites * n * (long long)sizeof(Real);
         for (int i = 0; i < n1; i++) {
           const int* en = &cs.entries[(size_t)8 * i];
           int* o = &e16[(size_t)PM_CLADE_ENTRY_INTS * i];
@@ -788,7 +821,7 @@ struct ChainT : pm_chain {
       CK(cudaMemsetAsync(t->tipcode.p, 0, t->tipcode.bytes, stream));
       t->node_state.alloc((size_t)(2 * T - 1) * S);
       if (!V.exp && !V.llonly) t->meta.alloc((size_t)E * S * sizeof(uint32_t));
-      t->PL.alloc((size_t)(T - 1) * t->pl_tile * n * sizeof(Real));
+      t->PL.alloc((size_t)(T - 1) * t->pl_sites * n * sizeof(Real));
       for (int b = 0; b < 2 && !V.exp && !V.llonly; b++) {
         t->rec_len[b].alloc((size_t)R * t->rec_groups * sizeof(Real));
         t->rec_st[b].alloc((size_t)R * t->rec_groups);
@@ -851,6 +884,8 @@ struct ChainT : pm_chain {
     CK(cudaMallocHost((void**)&err_h, sizeof(unsigned)));
     CK(cudaMallocHost((void**)&ctl_h, 2 * sizeof(uint32_t)));
     ctl.alloc(2 * sizeof(uint32_t));
+    phase_ns.alloc(2 * sizeof(unsigned long long));
+    CK(cudaMemsetAsync(phase_ns.p, 0, phase_ns.bytes, stream));
     if (const char* v = getenv("PHYLOMAP_B200_GRAPH")) graph_mode = atoi(v);
     if (V.dic) { CK(cudaMallocHost((void**)&q_h, (size_t)n * n * sizeof(double))); q_dev.alloc((size_t)n * n * sizeof(double)); }
     cnt.alloc((size_t)n * n * sizeof(unsigned long long));
@@ -914,7 +949,7 @@ struct ChainT : pm_chain {
       P.root = t.sch.root;
       P.tipcode = t.tipcode.template as<uint8_t>(); P.TS = t.TS; P.node_state = t.node_state.template as<uint8_t>();
       P.meta = t.meta.template as<uint32_t>(); P.PL = t.PL.template as<Real>();
-      P.tile_base = 0; P.pl_S = t.pl_tile; P.rec_shift = t.rec_shift; P.rec_groups = t.rec_groups; P.ctl = nullptr;
+      P.tile_base = 0; P.pl_S = t.pl_sites; P.rec_shift = t.rec_shift; P.rec_groups = t.rec_groups; P.ctl = nullptr;
       for (int b = 0; b < 2; b++) { P.rec_len[b] = t.rec_len[b].template as<Real>(); P.rec_st[b] = t.rec_st[b].template as<uint8_t>(); }
       // per-node rescaling (makePLrcpp_bigtree :525) only rescales the weights of each draw: the production
       // arithmetic always applies it (FP32 partials underflow after ~40 tips otherwise); the deterministic mode
@@ -1346,14 +1381,14 @@ struct ChainT : pm_chain {
     std::fill(out, out + (size_t)(2 * T - 1) * n, 0.0);
     std::vector<Real> v(n);
     long long lsite = site;
-    if (t.pl_tile < t.S) {  // tiled partials: the buffer holds the last tile of the last pass; prune the tile of `site` on the current state
+    if (t.pl_slots && t.slots_per_sm) {  // the slots hold whatever site blocks came last: prune the block of `site` on the current state (into slot 0)
       CK(cudaSetDevice(opt.device));
       launch_prune(t, site);
       CK(cudaStreamSynchronize(stream));
-      lsite = site % t.pl_tile;
-    }
+      lsite = site % 32;
+    }  // (fewer site blocks than slots: block i uses slot i, column = site)
     for (int i = 0; i < T - 1; i++) {
-      CK(cudaMemcpy(v.data(), t.PL.template as<Real>() + ((size_t)i * t.pl_tile + lsite) * n, n * sizeof(Real), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(v.data(), t.PL.template as<Real>() + ((size_t)i * t.pl_sites + lsite) * n, n * sizeof(Real), cudaMemcpyDeviceToHost));
       for (int j = 0; j < n; j++) out[(size_t)(T + i) * n + j] = (double)v[j];
     }
   }

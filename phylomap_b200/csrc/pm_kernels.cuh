@@ -46,10 +46,9 @@ struct ChainParams {
   int root;
   const uint8_t* tipcode; long long TS;  // tip codes [T][TS]: rows padded to a multiple of 16 sites (4-byte aligned cp.async)
   uint8_t* node_state; uint32_t* meta; Real* PL;
-  // production pruning / node kernels (n = 2, 4) work on one SITE TILE at a time: a launch covers the sites
-  // [tile_base, tile_base + 32 gridDim.x) and PL holds pl_S sites per node row, indexed by site - tile_base (the partials
-  // are per-sweep scratch between K1 and K2, so one tile's worth is all that is ever resident).  Everywhere else
-  // tile_base = 0 and pl_S = S.
+  // PL holds pl_S sites per node row.  Production (n = 2, 4): the fused prune + node-draw kernel keeps the partials of
+  // the 32 sites of a block in the slot the block claimed (pl_S = 32 x slots: the partials are per-sweep scratch between
+  // K1 and K2); everywhere else pl_S = S and column = site (tile_base = 0: first site of a stand-alone launch).
   long long tile_base, pl_S;
   // production path records: the slice of a branch chunk is shared by the 2^rec_shift consecutive sites of a group
   // (rec_groups groups per chunk): layout [chunk][group][cap], cursor [chunk][group]
@@ -368,8 +367,10 @@ __device__ __forceinline__ int lds_s32(unsigned a) { int v; asm volatile("ld.sha
 #define PM_CLADE_SLOT 384
 #define PM_CLADE_ENTRY_INTS 16  // host schedule entry (pm_host.cu): pn_off, x_off | ma_off, mb_off | ta_off, tb_off | flags (64 bytes)
 
-template <typename Real, int NS, int DEPTH, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) {
+// (the work of one block on the 32 sites [site0, site0 + 32), whose partials live at columns [pl0, pl0 + 32) of the
+// partials buffer: called by the stand-alone kernel and by the fused prune + node-draw kernel below)
+template <typename Real, int NS, int DEPTH>
+__device__ __forceinline__ void prune_clade_block(const ChainParams<Real>& P, const long long site0, const long long pl0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Real* sPow = reinterpret_cast<Real*>(smem_raw + PM_CLADE_SLOT * 8 * DEPTH);  // [PM_SMEM_POW][NS*NS]  P_k, row-major
   Real* sPowT = sPow + PM_SMEM_POW * NS * NS;                                  // [PM_SMEM_POW][NS*NS]  P_k transposed
@@ -383,7 +384,6 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long S = P.S;
-  const long long site0 = P.tile_base + (long long)blockIdx.x * 32;
   const long long site_raw = site0 + lane;
   const bool active = site_raw < S;
   const long long site = active ? site_raw : S - 1;
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
   const int T = P.T;
   const uint32_t* __restrict__ meta = P.meta + site;
   const uint8_t* __restrict__ tip = P.tipcode + site;
-  Real* PLs = P.PL + (site - P.tile_base) * NS;  // read and written by this thread: no __restrict__, no read-only loads
+  Real* PLs = P.PL + (pl0 + (site - site0)) * NS;  // read and written by this thread: no __restrict__, no read-only loads
   const long long rowPL = P.pl_S * NS;
 
   auto contribution = [&](int k, int code, Real* v) {
@@ -617,6 +617,11 @@ __global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) 
     }
     __syncthreads();
   }
+}
+
+template <typename Real, int NS, int DEPTH, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_prune_clade(ChainParams<Real> P) {
+  prune_clade_block<Real, NS, DEPTH>(P, P.tile_base + (long long)blockIdx.x * 32, (long long)blockIdx.x * 32);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -913,9 +918,8 @@ __device__ __forceinline__ int draw_node_state(const ChainParams<Real>& P, const
   return pick;
 }
 
-template <typename Real, int NS, int DEPTH, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, uint32_t iter) {
-  if (P.ctl) iter = P.ctl[0];
+template <typename Real, int NS, int DEPTH>
+__device__ __forceinline__ void nodes_clade_block(const ChainParams<Real>& P, const uint32_t iter, const long long site0, const long long pl0) {
   constexpr int PB = NS * (int)sizeof(Real);  // bytes of one partial
   constexpr int PLB = 32 * PB;
   constexpr int SLOT = PLB + 160;
@@ -928,10 +932,10 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long S = P.S;
-  const long long site_raw = P.tile_base + (long long)blockIdx.x * 32 + lane;
+  const long long site_raw = site0 + lane;
   const bool active = site_raw < S;
   const long long site = active ? site_raw : S - 1;
-  const long long lsite = site - P.tile_base;  // index of the site in the partials of this tile
+  const long long lsite = pl0 + (site - site0);  // column of the site in the partials buffer
   const bool parity = P.parity_tips != 0;
   const int T = P.T;
   const uint32_t gsite = P.rng.site0 + (uint32_t)site;
@@ -1078,6 +1082,62 @@ __global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, 
       }
     }
   }
+}
+
+template <typename Real, int NS, int DEPTH, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_nodes_clade(ChainParams<Real> P, uint32_t iter) {
+  if (P.ctl) iter = P.ctl[0];
+  nodes_clade_block<Real, NS, DEPTH>(P, iter, P.tile_base + (long long)blockIdx.x * 32, (long long)blockIdx.x * 32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K2 fused (production, n = 2 / 4).  A block's partials are read by nobody but the same block's node draws, so a
+// block prunes its 32 sites and draws their node states straight away.  The partials of the whole sweep then live in one
+// SLOT of 32 sites per block that is RESIDENT at a time -- slots_per_sm per SM, claimed at block start and released at
+// block end (a block keeps its SM) -- (T - 1) x 32 x n reals per slot: 2.3 GB at 10 000 tips instead of 20 GB for
+// 125 000 sites, and the two passes share one launch with no tail between them.  The schedules' byte offsets are built
+// for a row of 32 x slots sites (ChainParams::pl_S).
+//   phases: 1 = prune only (timing, partials read-back), 3 = both.   phase_ns (optional): block-time spent in each pass.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned sm_id() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+
+template <typename Real, int NS, int DEPTH, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_prune_nodes_clade(ChainParams<Real> P, uint32_t iter, long long b0, int phases, int* slot_busy,
+                                                                 int slots_per_sm, unsigned long long* phase_ns) {
+  if (P.ctl) iter = P.ctl[0];
+  __shared__ unsigned long long s_t[2];
+  __shared__ int s_slot;
+  if (threadIdx.x == 0) {
+    // claim a slot of this SM: at most slots_per_sm blocks are resident on it (occupancy), and a block that leaves has
+    // released its slot before the next one can start here
+    // (slot_busy == nullptr: slot = block index, for a launch of at most as many blocks as there are slots)
+    int slot = (int)blockIdx.x;
+    if (slot_busy) {
+      const int base = (int)sm_id() * slots_per_sm;
+      int k = 0;
+      while (atomicCAS(slot_busy + base + k, 0, 1) != 0) k = (k + 1 == slots_per_sm) ? 0 : k + 1;
+      slot = base + k;
+    }
+    s_slot = slot;
+    if (phase_ns) s_t[0] = global_ns();
+  }
+  __syncthreads();
+  const int slot = s_slot;
+  const long long site0 = (b0 + blockIdx.x) * 32, pl0 = (long long)slot * 32;
+  prune_clade_block<Real, NS, DEPTH>(P, site0, pl0);
+  __syncthreads();  // every partial of these sites is written (and visible to the block) before the draws read them
+  if (phases & 2) {
+    if (phase_ns && threadIdx.x == 0) s_t[1] = global_ns();
+    nodes_clade_block<Real, NS, DEPTH>(P, iter, site0, pl0);
+    __syncthreads();
+    if (phase_ns && threadIdx.x == 0) {
+      const unsigned long long t2 = global_ns();
+      atomicAdd(phase_ns, s_t[1] - s_t[0]);
+      atomicAdd(phase_ns + 1, t2 - s_t[1]);
+    }
+  }
+  if (threadIdx.x == 0 && slot_busy) atomicExch(slot_busy + slot, 0);  // (after a barrier: nobody reads the slot any more)
 }
 
 // ------------------------------------------------------------------------------------------------

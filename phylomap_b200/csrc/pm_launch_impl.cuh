@@ -37,6 +37,39 @@ void Sweep<Real, NS, EXACT>::nodes(const ChainParams<Real>& P, int grid, size_t 
   else k_nodes<Real, NS, EXACT><<<grid, 256, smem, st>>>(P, iter);
 }
 template <typename Real, int NS, bool EXACT>
+struct FusedCfg {
+  static constexpr int D = 8, MB = sizeof(Real) == 8 ? 2 : 3;  // FP64 needs the registers of 2 blocks / SM
+  static size_t smem(size_t smem_nodes) {
+    const size_t sm_prune = 2 * PM_SMEM_POW * (NS > 0 ? NS : 1) * (NS > 0 ? NS : 1) * sizeof(Real) + (size_t)PM_CLADE_SLOT * 8 * D;
+    const size_t sm_nodes = smem_nodes + (size_t)(32 * (NS > 0 ? NS : 1) * sizeof(Real) + 160) * 8 * D;
+    return sm_prune > sm_nodes ? sm_prune : sm_nodes;
+  }
+};
+template <typename Real, int NS, bool EXACT>
+int Sweep<Real, NS, EXACT>::fused_blocks_per_sm(size_t smem_nodes) {
+  if constexpr (!EXACT && (NS == 2 || NS == 4)) {
+    typedef FusedCfg<Real, NS, EXACT> C;
+    auto kern = k_prune_nodes_clade<Real, NS, C::D, C::MB>;
+    const size_t sm = C::smem(smem_nodes);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, sm) != cudaSuccess) return 0;
+    return nb;
+  }
+  return 0;
+}
+template <typename Real, int NS, bool EXACT>
+void Sweep<Real, NS, EXACT>::prune_nodes(const ChainParams<Real>& P, int grid, size_t smem_nodes, cudaStream_t st, uint32_t iter,
+                                         long long b0, int phases, int* slot_busy, int slots_per_sm, unsigned long long* phase_ns) {
+  if constexpr (!EXACT && (NS == 2 || NS == 4)) {
+    typedef FusedCfg<Real, NS, EXACT> C;
+    auto kern = k_prune_nodes_clade<Real, NS, C::D, C::MB>;
+    const size_t sm = C::smem(smem_nodes);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    kern<<<grid, 256, sm, st>>>(P, iter, b0, phases, slot_busy, slots_per_sm, phase_ns);
+  }
+}
+template <typename Real, int NS, bool EXACT>
 void Sweep<Real, NS, EXACT>::paths(const ChainParams<Real>& P, dim3 grid, size_t smem, cudaStream_t st, uint32_t iter,
                                    int first, int chunk, int hard_blocks) {
   if constexpr (EXACT) k_paths<Real, NS, true><<<grid, 128, smem, st>>>(P, iter, first, chunk);

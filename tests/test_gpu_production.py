@@ -444,16 +444,18 @@ def test_site_tiles_equal_one_call(monkeypatch):
     assert np.array_equal(ex_tiled[:, 4:], ex_whole[:, 4:])
 
 
-@pytest.mark.parametrize("what", ["bigtree_f32", "ks_f32", "ksmt_f64"])
+@pytest.mark.parametrize("what", ["bigtree_f32", "bigtree_f32_many_sites", "ks_f32", "ksmt_f64"])
 def test_rows_do_not_depend_on_the_memory_layout(what, monkeypatch):
-    """Site-tiled partials (K1 -> K2 tile by tile, PHYLOMAP_B200_PL_TILE) and record slices shared by groups of 32 sites
-    (PHYLOMAP_B200_REC_POOL) only change where scratch and records live: every site draws from its own Philox keys, so the
-    rows -- counts, dwell times, rate traces -- must be identical bit for bit to the untiled / per-site layout, also when
-    the last tile is ragged, and a stored path must read back the same from either layout."""
+    """The fused prune + node-draw kernel (partials in per-block slots claimed per SM, PHYLOMAP_B200_FUSED) and record
+    slices shared by groups of 32 sites (PHYLOMAP_B200_REC_POOL) only change where scratch and records live: every site
+    draws from its own Philox keys, so the rows -- counts, dwell times, rate traces -- must be identical bit for bit to the
+    two separate kernels with the full partials array / per-site slices, also with a ragged last block and with more site
+    blocks than slots (slots are claimed and handed on), and a stored path must read back the same from either layout."""
     N = 10
-    if what == "bigtree_f32":
+    if what.startswith("bigtree_f32"):
         Q = cases.q4()
-        z = cases.tree_n(Q, T=300, S=203, seed=5, mean_branch=1.5, segments=3)   # long branches: records in use
+        many = what.endswith("many_sites")     # 470 site blocks > 444 slots on a B200
+        z = cases.tree_n(Q, T=40 if many else 300, S=15013 if many else 203, seed=5, mean_branch=1.5, segments=3)   # long branches: records in use
         mk = lambda: pb.Chain(capi.PM_V_BIGTREE, z, Q.copy(), np.full(4, 0.25), 2.4, N, precision="f32", seed=11)
     elif what == "ks_f32":
         Q = cases.q4()
@@ -467,25 +469,26 @@ def test_rows_do_not_depend_on_the_memory_layout(what, monkeypatch):
         mk = lambda: pb.Chain(capi.PM_V_KSMT, trees, np.asfortranarray(Q.copy()), np.full(4, 0.25), 4.0, N,
                               prior=cases.PRIOR_KSMT, precision="f64", seed=11)
 
-    def run(tile, pool):
-        monkeypatch.setenv("PHYLOMAP_B200_PL_TILE", str(tile))
+    def run(fused, pool):
+        monkeypatch.setenv("PHYLOMAP_B200_FUSED", str(fused))
         monkeypatch.setenv("PHYLOMAP_B200_REC_POOL", str(pool))
         ch = mk()
         rows = ch.run(N)
-        E = (z if what != "ksmt_f64" else trees[0]).E
-        paths = [ch.path(s, e, cap=256) for s in (0, 33, 69) for e in range(0, E, max(1, E // 12))]
+        t0 = z if what != "ksmt_f64" else trees[0]
+        sites = (0, 33, 69) if t0.n_sites() < 1000 else (0, 7000, 15012)
+        paths = [ch.path(s, e, cap=256) for s in sites for e in range(0, t0.E, max(1, t0.E // 12))]
         pc = ch.piece_counts()
         ch.time_prune(reps=1)                     # K1 alone on the final state: what partials() reports in either layout
-        pls = [ch.partials(s) for s in (0, 33, 69)]
+        pls = [ch.partials(s) for s in sites]
         ch.close()
         return rows, paths, pc, pls
 
-    ref_rows, ref_paths, ref_pc, ref_pls = run(0, 0)   # untiled partials, one record slice per (site, chunk)
-    for tile, pool in [(64, 0), (0, 1), (32, 1), (96, 1)]:
-        rows, paths, pc, pls = run(tile, pool)
+    ref_rows, ref_paths, ref_pc, ref_pls = run(0, 0)   # separate kernels + full partials array, one record slice per (site, chunk)
+    for fused, pool in [(1, 0), (0, 1), (1, 1)]:
+        rows, paths, pc, pls = run(fused, pool)
         for a, b in zip(ref_pls, pls):
             assert np.array_equal(a, b)
-        assert np.array_equal(rows, ref_rows), "rows differ with PL tile %d, pooled records %d" % (tile, pool)
+        assert np.array_equal(rows, ref_rows), "rows differ with fused %d, pooled records %d" % (fused, pool)
         assert np.array_equal(pc, ref_pc)
         for (l0, s0), (l1, s1) in zip(ref_paths, paths):
             assert np.array_equal(l0, l1) and np.array_equal(s0, s1)
