@@ -286,35 +286,49 @@ def run_ours(a, rank, local_rank, world):
     if not np.allclose(tot, expect, rtol=1e-3):
         raise SystemExit("bench sanity check failed: dwell %r vs %r" % (tot[:3], expect))
 
-    # roofline of the pruning pass
-    K1_NAME = "k_prune_clade<float,4,8,3>"
+    # roofline of the pruning pass (K1).  In the step it is the first pass of the fused launch
+    # k_prune_nodes_clade (prune the block's 32 sites, then draw their node states): the launch is timed with CUDA events
+    # and split between the two passes by the block-nanoseconds (%globaltimer) the blocks report for each; the same pass
+    # launched alone (phases = 1), five times back to back, is the cross-check `ms_per_launch_isolated`.
+    K1_NAME = "k_prune_nodes_clade<float,4,8,3>"
     k1_ms = chain.time_prune(reps=5)
     T = tree.T
     bytes_site = (T - 1) * 16 + (T - 2) * 16 + T * 1 + E * 4
+    bytes_site_k2 = (T - 2) * 16 + E * 4 + (2 * T - 1) * 2      # partials and jump counts once, node states r/w
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch, from the committed ncu capture
+    traffic = traffic_fused = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu captures
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        k1 = tj[K1_NAME]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if S == 125000 and TIPS == 10000:
+            k1 = tj[K1_NAME + " (pruning pass alone)"]
             traffic = k1["dram_bytes_read"] + k1["dram_bytes_write"]
+            kf = tj[K1_NAME]
+            traffic_fused = kf["dram_bytes_read"] + kf["dram_bytes_write"]
     except Exception:
         pass
-    k1_iso_ms = k1_ms                                  # K1 launched alone, five times back to back
-    k1_ms = ktimes["prune"] / a.steps                  # K1 inside the timed region (CUDA events around every launch)
+    k1_iso_ms = k1_ms                                  # the pruning pass launched alone, five times back to back
+    k1_ms = ktimes["prune"] / a.steps                  # the pruning pass inside the timed region (share of the fused launch)
+    fused_ms = (ktimes["prune"] + ktimes["sample_nodes"]) / a.steps   # the fused launch itself (CUDA events)
     ach = bytes_site * S / (k1_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": K1_NAME, "achieved": ach, "peak": peak, "unit": "GB/s",
-            "frac": ach / peak, "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu capture of this workload)" if traffic else None,
+    ach_fused = (bytes_site + bytes_site_k2) * S / (fused_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": K1_NAME + ", pruning pass (K1)", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": traffic, "traffic_source": "profiles/r2_traffic.json (ncu capture of this workload)" if traffic else None,
             "algorithmic_bytes_per_launch": bytes_site * S, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650",
-            "ms_per_launch": k1_ms, "ms_per_launch_isolated": k1_iso_ms, "algorithmic_bytes_per_site": bytes_site,
+            "ms_per_launch": k1_ms, "ms_per_launch_isolated": k1_iso_ms, "frac_isolated": bytes_site * S / (k1_iso_ms * 1e-3) / 1e9 / peak,
+            "algorithmic_bytes_per_site": bytes_site,
             "dram_gbs_actual": (traffic / (k1_ms * 1e-3) / 1e9) if traffic else None,
-            "note": "the clade-order kernel hands a child's partial to its parent through registers / L2, so its DRAM traffic is "
-                    "below the algorithmic bytes (which count every partial once written and once read)",
+            "note": "K1 is the first pass of the fused prune + node-draw launch: ms_per_launch = the launch's CUDA-event time x the "
+                    "share of block-nanoseconds its blocks spent pruning; ms_per_launch_isolated = the same pass launched alone.  The "
+                    "clade-order walk hands a child's partial to its parent through registers / L2, so its DRAM traffic is below the "
+                    "algorithmic bytes (which count every partial once written and once read)",
+            "fused_launch": {"kernel": K1_NAME, "ms_per_launch": fused_ms, "algorithmic_bytes_per_site": bytes_site + bytes_site_k2,
+                             "achieved": ach_fused, "frac": ach_fused / peak, "traffic": traffic_fused,
+                             "dram_gbs_actual": (traffic_fused / (fused_ms * 1e-3) / 1e9) if traffic_fused else None},
             "in_step_ms": {k: v / a.steps for k, v in ktimes.items()}}
     dev_bytes = chain.device_bytes()
     chain.close()
