@@ -222,6 +222,25 @@ long long chernoff_records_cap(const std::vector<double>& lams, double eps, doub
 
 }  // namespace
 
+// Range of %smid on a device (asked once per device with a one-thread kernel, see k_nsmid).
+static int sm_id_range(int device, int reported_sms) {
+  static std::mutex mu;
+  static std::map<int, int> known;
+  std::lock_guard<std::mutex> g(mu);
+  auto it = known.find(device);
+  if (it != known.end()) return it->second;
+  int* d = nullptr;
+  int v = 0;
+  if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) fail(PM_ERR_CUDA, "cudaMalloc failed");
+  pm::k_nsmid<<<1, 1>>>(d);
+  const cudaError_t e = cudaMemcpy(&v, d, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) fail(PM_ERR_CUDA, "reading %%nsmid failed: %s", cudaGetErrorString(e));
+  v = std::max(v, reported_sms);
+  known[device] = v;
+  return v;
+}
+
 // NCCL communicators live as long as the process: a unique id can initialise a clique only once, and a session calls the
 // samplers many times with the same id (ncclCommInitRank costs tenths of a second).  Keyed by the id's 128 bytes.
 static pm::host::NcclApi::Comm clique(const void* id128, int world, int rank) {
@@ -725,7 +744,7 @@ struct ChainT : pm_chain {
         const int per_sm = NS == 2 ? pm::Sweep<Real, 2, false>::fused_blocks_per_sm(smem_lo) : pm::Sweep<Real, 4, false>::fused_blocks_per_sm(smem_lo);
         if (per_sm < 1) fail(PM_ERR_CUDA, "cudaOccupancyMaxActiveBlocksPerMultiprocessor failed for the fused prune + node-draw kernel");
         t->slots_per_sm = per_sm;
-        t->pl_slots = prop.multiProcessorCount * per_sm;
+        t->pl_slots = sm_id_range(opt.device, prop.multiProcessorCount) * per_sm;  // slots are indexed by %smid
         t->pl_sites = 32LL * t->pl_slots;
         if (t->pl_sites >= ((S + 31) / 32) * 32) {  // fewer site blocks than slots: block i uses slot i
           t->pl_slots = (int)((S + 31) / 32); t->pl_sites = 32LL * t->pl_slots; t->slots_per_sm = 0;

@@ -35,6 +35,14 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ dw_pa
 // ------------------------------------------------------------------------------------------------
 // Set-up kernels.
 // ------------------------------------------------------------------------------------------------
+// %nsmid: the range of the SM identifiers a block can read from %smid (PTX: it may exceed the number of SMs the runtime
+// reports, and the numbering need not be contiguous).  The fused prune + node-draw kernel indexes its slots by %smid.
+__global__ void k_nsmid(int* out) {
+  unsigned v;
+  asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v));
+  *out = (int)v;
+}
+
 // states [ns][T] (a staged block of site rows; int32 1-based, or u8) -> tipcode / node_state [T][S] at site s_base.
 // Tiled transpose through shared memory: reads coalesced along T, writes coalesced along S.  Validates the range.
 template <typename In>

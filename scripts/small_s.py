@@ -11,8 +11,11 @@ from oracle import bridge
 out = {}
 def gpu(fn, *a, **k):
     fn(*a, **k)  # warm
-    torch.cuda.synchronize(); t = time.perf_counter(); r = fn(*a, **k); torch.cuda.synchronize()
-    return time.perf_counter() - t, r
+    best = 1e30
+    for _ in range(3):   # best of three calls (a call of 1 000 sweeps of a 100-tip tree lasts 0.1 s: host jitter shows)
+        torch.cuda.synchronize(); t = time.perf_counter(); r = fn(*a, **k); torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t)
+    return best, r
 def cpu(variant, z, Q, pid, Om, N, fast):
     o = bridge.OracleRun(variant, [z.oracle_dict()], Q, pid, Om, N, rng_mode=bridge.SEQUENTIAL, seed=3)
     o.set_fast_lookup(fast)
