@@ -620,16 +620,22 @@ struct ChainT : pm_chain {
     }
 
     mark("validation + schedules");
+    const auto mark_dev = [&] { mark("device queries + stream"); };
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) fail(PM_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
     if (opt.device < 0 || opt.device >= ndev) fail(PM_ERR_CUDA, "device %d not present", opt.device);
     CK(cudaSetDevice(opt.device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, opt.device));
+    // (three attributes, not cudaGetDeviceProperties: that call reads every property of the device and takes 10-150 ms,
+    // a quarter of a short call)
+    struct { int major = 0, minor = 0, multiProcessorCount = 0; } prop;
+    CK(cudaDeviceGetAttribute(&prop.major, cudaDevAttrComputeCapabilityMajor, opt.device));
+    CK(cudaDeviceGetAttribute(&prop.minor, cudaDevAttrComputeCapabilityMinor, opt.device));
+    CK(cudaDeviceGetAttribute(&prop.multiProcessorCount, cudaDevAttrMultiProcessorCount, opt.device));
     if (prop.major != 10) fail(PM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", opt.device, prop.major, prop.minor);
     if (opt.cuda_stream) stream = (cudaStream_t)opt.cuda_stream;
     else { CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
 
+    mark_dev();
     const int T0 = tr[0].n_tips, E0 = tr[0].n_edges;
     double tmax = 0, qmax = 0;
     for (int s = 0; s < n; s++) qmax = std::max(qmax, -Q[s + (size_t)s * n]);
@@ -813,10 +819,13 @@ struct ChainT : pm_chain {
         upload(t->cd_top, cs.down_top, stream);
         upload(t->cd_top_off, cs.down_top_off, stream);
         t->n_cd_top_levels = (int)cs.down_top_off.size() - 1;
-        std::vector<int> tips;
+        std::vector<long long> tips;  // entry v = tip v: the parent's node-state row, the jump-count row of its branch (bytes)
         if (V.redraw_tips)
-          for (int v = 0; v < T; v++) { const int e = t->sch.parent_edge[v]; tips.push_back(v); tips.push_back(t->sch.e_parent[e]); tips.push_back(e); }
-        t->n_cd_tips = (int)tips.size() / 3;
+          for (int v = 0; v < T; v++) {
+            const int e = t->sch.parent_edge[v];
+            tips.push_back((long long)t->sch.e_parent[e] * S); tips.push_back((long long)e * S * 4);
+          }
+        t->n_cd_tips = (int)tips.size() / 2;
         upload(t->cd_tips, tips, stream);
       }
       upload(t->down_entries, t->sch.down_entries, stream);
@@ -959,7 +968,7 @@ struct ChainT : pm_chain {
       P.cl_top_off = t.cl_top_off.template as<int>(); P.n_cl_top_levels = t.n_cl_top_levels;
       P.cd_top = t.cd_top.template as<int>(); P.cd_top_off = t.cd_top_off.template as<int>(); P.n_cd_top_levels = t.n_cd_top_levels;
       P.cd_entries = t.cd_entries.template as<int>(); P.cd_warp_off = t.cd_warp_off.template as<int>();
-      P.cd_tips = t.cd_tips.template as<int>(); P.n_cd_tips = t.n_cd_tips;
+      P.cd_tips = t.cd_tips.template as<long long>(); P.n_cd_tips = t.n_cd_tips;
       P.down_entries = t.down_entries.template as<int>(); P.down_off = t.down_off.template as<int>();
       P.n_down_levels = (int)t.sch.down_off.size() - 1;
       P.e_parent = t.e_parent.template as<int>(); P.e_child = t.e_child.template as<int>();
@@ -1004,9 +1013,9 @@ struct ChainT : pm_chain {
         CK(cudaStreamSynchronize(stream));
       }
       mark("tip states: H2D + transpose");
-      const long long tot = t.S * E;
       if (!V.exp && !V.llonly)
-        pm::k_init_meta<Real><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(P.maps_off, P.maps_len, t.S, E, P.meta, P.e_len, exact ? nullptr : P.shape);
+        pm::k_init_meta<Real><<<dim3((unsigned)((t.S + 255) / 256), (unsigned)std::min(E, 65535)), 256, 0, stream>>>(P.maps_off, P.maps_len, t.S, E, P.meta, P.e_len,
+                                                                                                                       exact ? nullptr : P.shape);
       CK(cudaGetLastError());
     }
     stage_model(true);

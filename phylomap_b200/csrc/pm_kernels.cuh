@@ -39,7 +39,9 @@ struct ChainParams {
   const int* cl_entries; const int* cl_warp_off; const int* cl_top_entries; const int* cl_top_off; int n_cl_top_levels;
   // ... and of k_nodes_clade: top part by depth (4 ints per node: v, parent, edge, -), then per-warp pre-order sequences (16 ints)
   const int* cd_top; const int* cd_top_off; int n_cd_top_levels; const int* cd_entries; const int* cd_warp_off;
-  const int* cd_tips; int n_cd_tips;  // tips to redraw (ks / mt samplers): 3 ints per tip: v, parent, edge
+  // tips to redraw (ks / mt samplers: all of them, entry v = tip v), 2 offsets per tip: the parent's node-state row
+  // (parent x S) and the jump-count row of the tip's branch in bytes (edge x S x 4)
+  const long long* cd_tips; int n_cd_tips;
   const int* down_entries; const int* down_off; int n_down_levels;  // 3 ints per drawn node: v, parent, edge
   const int* e_parent; const int* e_child; const Real* e_len;
   const long long* maps_off; const double* maps_len;
@@ -1052,34 +1054,49 @@ __device__ __forceinline__ void nodes_clade_block(const ChainParams<Real>& P, co
     }
     cp_async_wait<0>();
   }
-  // ---- tips (samplers that redraw them): four consecutive list entries share a Philox block 0x40000000 + group ----
+  // ---- tips (samplers that redraw them): four consecutive list entries share a Philox block 0x40000000 + group.  Software
+  // pipeline: the twelve loads of a warp's NEXT group are in flight while it draws the current one.
   if (P.n_cd_tips > 0) {
     __syncthreads();
-    for (int grp = warp; grp <= (P.n_cd_tips - 1) >> 2; grp += nw) {
+    const int ntip = P.n_cd_tips, ngrp = (ntip + 3) >> 2;
+    const uint8_t* const tipb = P.tipcode + site;
+    const char* const mtb = reinterpret_cast<const char*>(P.meta + site);
+    struct TipLoad { int ps, k, cd; };
+    auto load = [&](int grp, TipLoad (&L)[4]) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int v = min(4 * grp + q, ntip - 1);
+        const longlong2 en = __ldg(reinterpret_cast<const longlong2*>(P.cd_tips) + v);
+        L[q].ps = nst[en.x];
+        L[q].k = (int)(*reinterpret_cast<const uint32_t*>(mtb + en.y) & 0xffffu) - 1;
+        L[q].cd = tipb[(long long)v * P.TS];
+      }
+    };
+    auto draw = [&](int grp, const TipLoad (&L)[4]) {
       uint32_t o[4];
       philox4x32_10_rk(0x40000000u + (uint32_t)grp, kslot, iter, gsite, P.rng.rk, o);
-      const int p0 = grp << 2, p1 = min(P.n_cd_tips, p0 + 4);
-      int vs[4], ks[4], pss[4], cds[4];
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        const int pos = min(p0 + q, p1 - 1);
-        const int* en = P.cd_tips + 3 * pos;
-        const int v = __ldg(en), pn = __ldg(en + 1), e = __ldg(en + 2);
-        vs[q] = v;
-        pss[q] = nst[(long long)pn * S];
-        ks[q] = (int)(P.meta[(long long)e * S + site] & 0xffffu) - 1;
-        cds[q] = P.tipcode[(long long)v * P.TS + site];
-      }
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        if (p0 + q < p1) {  // warp-uniform
+        if (4 * grp + q < ntip) {  // warp-uniform
           Real pl[NS];
-          tip_partial<Real, NS>(cds[q], NS, parity, pl);
+          tip_partial<Real, NS>(L[q].cd, NS, parity, pl);
           const uint32_t word = q == 0 ? o[0] : q == 1 ? o[1] : q == 2 ? o[2] : o[3];
-          const int sn = draw_node_state<Real, NS>(P, sBs, sPow, npow_s, ks[q], pss[q], pl, word);
-          if (active) nst[(long long)vs[q] * S] = (uint8_t)sn;
+          const int sn = draw_node_state<Real, NS>(P, sBs, sPow, npow_s, L[q].k, L[q].ps, pl, word);
+          if (active) nst[(long long)(4 * grp + q) * S] = (uint8_t)sn;
         }
       }
+    };
+    TipLoad A[4], B[4];
+    int grp = warp;
+    if (grp < ngrp) load(grp, A);
+    while (grp < ngrp) {
+      if (grp + nw < ngrp) load(grp + nw, B);
+      draw(grp, A);
+      grp += nw;
+      if (grp >= ngrp) break;
+      if (grp + nw < ngrp) load(grp + nw, A);
+      draw(grp, B);
+      grp += nw;
     }
   }
 }

@@ -77,18 +77,19 @@ __global__ void __launch_bounds__(256) k_init_tips(const In* __restrict__ states
 // (upper 16 bits) with the only jump point of a two-piece map, so that the first sweep can treat such a branch like any
 // later one (k_paths_easy) instead of walking the map in the general kernel.
 template <typename Real>
-__global__ void k_init_meta(const long long* __restrict__ maps_off, const double* __restrict__ maps_len, long long S, int E,
-                            uint32_t* meta, const Real* __restrict__ e_len, uint16_t* shape) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S * E) return;
-  const long long e = i / S;
-  const long long a = maps_off[e], m = maps_off[e + 1] - a;
-  uint32_t w = (uint32_t)m;
-  if (shape) {
-    if (m == 2) w |= pos_enc<Real>((Real)maps_len[a], e_len[e]) << 16;
-    shape[i] = 0;
+__global__ void __launch_bounds__(256) k_init_meta(const long long* __restrict__ maps_off, const double* __restrict__ maps_len, long long S, int E,
+                                                   uint32_t* meta, const Real* __restrict__ e_len, uint16_t* shape) {
+  // grid: x over sites, y over branches (strided): the word of a branch is the same for all its sites
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int e = blockIdx.y; e < E; e += gridDim.y) {
+    const long long a = maps_off[e], m = maps_off[e + 1] - a;
+    uint32_t w = (uint32_t)m;
+    if (shape && m == 2) w |= pos_enc<Real>((Real)maps_len[a], e_len[e]) << 16;
+    if (s < S) {
+      meta[(long long)e * S + s] = w;
+      if (shape) shape[(long long)e * S + s] = 0;
+    }
   }
-  meta[i] = w;
 }
 
 }  // namespace pm
