@@ -195,7 +195,9 @@ long long chernoff_records_cap(const std::vector<double>& lams, double eps, doub
   const double thetas[NT] = {0.02, 0.04, 0.07, 0.12, 0.25, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0};
   double acc[NT], eth[NT];
   bool ok[NT];
-  for (int t = 0; t < NT; t++) { acc[t] = 0; eth[t] = std::exp(thetas[t]); ok[t] = true; }
+  // a slice of one site is bounded best by a large theta, a slice shared by many sites by a small one: half the grid each
+  for (int t = 0; t < NT; t++) { acc[t] = 0; eth[t] = std::exp(thetas[t]); ok[t] = copies > 1.0 ? t < 7 : t >= 4; }
+  static const std::vector<double> inv_j = [] { std::vector<double> v(400, 0.0); for (int j = 1; j < 400; j++) v[j] = 1.0 / j; return v; }();
   for (double lam : lams) {
     const double p0 = std::exp(-lam);
     for (int t = 0; t < NT; t++) {
@@ -205,7 +207,7 @@ long long chernoff_records_cap(const std::vector<double>& lams, double eps, doub
       double mgf = p0 + p0 * lam;
       double term = eth[t] * eth[t] * p0 * lam;  // the j = 1 term of the series (not part of the sum)
       for (int j = 2; j < 400; j++) {
-        term *= eth[t] * lam / j;
+        term *= eth[t] * lam * inv_j[j];
         mgf += term;
         if (j > lam * eth[t] + 5 && term < 1e-30 * mgf) break;
       }
