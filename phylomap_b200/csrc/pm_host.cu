@@ -294,7 +294,7 @@ struct TreeDev {
   int n_cd_top_levels = 0, n_cd_tips = 0;  // clade schedule of the production pruning kernel
   int n_cl_top_levels = 0;
   DevBuf up_entries8, up_entries, up_off, down_entries, down_off, e_parent, e_child, e_len, maps_off, maps_len, cap_off;
-  DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, hard_ballot, wk_off, wk_g, wk_hint, rec_cursor, shape;
+  DevBuf tipcode, node_state, meta, PL, rec_len[2], rec_st[2], dw_partial, hard_ballot, wk_off, wk_g, wk_hint, wk_item, rec_cursor, shape;
   long long wk_total = 0, dw_rows = 0;
   int hard_blocks = 0;
   int pl_slots = 0;          // 32-site slots of the partials buffer (fused prune + node-draw kernel: SMs x resident blocks per SM); 0: separate kernels, partials of all sites
@@ -882,6 +882,9 @@ struct ChainT : pm_chain {
         upload(t->wk_hint, hint, stream);
         upload(t->wk_off, woff, stream);
         upload(t->wk_g, wg, stream);
+        t->wk_item.alloc((size_t)std::max<long long>(t->wk_total, 1) * sizeof(unsigned long long));
+        pm::k_build_items<<<(unsigned)((t->wk_total + 255) / 256), 256, 0, stream>>>(t->wk_off.template as<long long>(), t->wk_g.template as<int>(), E, Wl,
+                                                                                    t->wk_total, t->wk_item.template as<unsigned long long>());
         t->rec_cursor.alloc((size_t)ny * t->rec_groups * sizeof(int));
         t->shape.alloc((size_t)E * S * sizeof(uint16_t));
         // persistent: 4 blocks of 4 warps per SM, fewer when there are not that many work items (a handful of sites)
@@ -892,7 +895,7 @@ struct ChainT : pm_chain {
       t->dw_partial.alloc((size_t)t->dw_rows * n * sizeof(double));
       CK(cudaMemsetAsync(t->dw_partial.p, 0, t->dw_partial.bytes, stream));
       dev_bytes += t->tipcode.bytes + t->node_state.bytes + t->meta.bytes + t->PL.bytes + 2 * (t->rec_len[0].bytes + t->rec_st[0].bytes) +
-                   t->dw_partial.bytes + t->hard_ballot.bytes + t->rec_cursor.bytes + t->shape.bytes;
+                   t->dw_partial.bytes + t->hard_ballot.bytes + t->rec_cursor.bytes + t->shape.bytes + t->wk_item.bytes;
       trees.push_back(std::move(t));
       mark("device buffers");
     }
@@ -957,7 +960,7 @@ struct ChainT : pm_chain {
       P.cap_off = t.cap_off.template as<int>();
       P.hard_ballot = t.hard_ballot.template as<uint32_t>(); P.W = (int)((t.S + 31) / 32);
       P.wk_off = t.wk_off.template as<long long>(); P.wk_g = t.wk_g.template as<int>(); P.wk_total = t.wk_total;
-      P.wk_hint = t.wk_hint.template as<int>();
+      P.wk_hint = t.wk_hint.template as<int>(); P.wk_item = t.wk_item.template as<unsigned long long>();
       P.tune = getenv("PHYLOMAP_B200_TUNE") ? atoi(getenv("PHYLOMAP_B200_TUNE")) : 0;
       P.rec_cursor = t.rec_cursor.template as<int>(); P.chunk = t.chunk; P.easy_blocks = t.nblocks;
       P.shape = t.shape.template as<uint16_t>();

@@ -65,6 +65,9 @@ struct ChainParams {
   uint32_t* hard_ballot; int W;
   const long long* wk_off; const int* wk_g; long long wk_total;
   const int* wk_hint;  // [wk_total / 64 + 1] branch that owns work item 64 i
+  // ... flattened (k_build_items): item i = branch (bits 32-63) | first ballot word (5-31) | words - 1 (0-4), so that a warp
+  // finds its next item with ONE load, issued an item ahead, instead of a chain of four dependent ones
+  const unsigned long long* wk_item;
   int tune;            // PHYLOMAP_B200_TUNE (experiments)
   int* rec_cursor;  // [n_chunks][rec_groups] records appended so far to the slice of (chunk, site group) in this sweep
   int chunk;        // branches per record chunk
@@ -1197,8 +1200,9 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
   const int n = NS > 0 ? NS : P.n;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_dw = reinterpret_cast<double*>(smem_raw);              // [4 warps][n] (NS>0) or [n] atomics (NS==0)
-  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_dw + 4 * n);    // [n*n]
-  Real* s_rate = reinterpret_cast<Real*>(s_cnt + n * n + ((n * n) & 1));  // [n] Omega + Q_ss of this sweep
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_dw + 4 * n);    // [4 warps][n*n]: a copy per warp, so that the atomics of a warp
+                                                                  // (one per branch in nine warps out of ten) never wait for another warp's
+  Real* s_rate = reinterpret_cast<Real*>(s_cnt + 4 * (n * n + ((n * n) & 1)));  // [n] Omega + Q_ss of this sweep
   // topology of the chunk (the same for every thread of the block): parent / child node and branch length
   int* s_par = reinterpret_cast<int*>(s_rate + n + (n & 1));
   int* s_chi = s_par + chunk;
@@ -1207,7 +1211,9 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
   // multiply-adds; fma(1, L, acc) = acc + L and fma(0, L, acc) = acc exactly) instead of NS compare / select / add triples
   __shared__ __align__(16) Real s_unit[NR][NR];
   const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
-  for (int i = threadIdx.x; i < n * n; i += blockDim.x) s_cnt[i] = 0;
+  const int cnt_stride = n * n + ((n * n) & 1);
+  for (int i = threadIdx.x; i < 4 * cnt_stride; i += blockDim.x) s_cnt[i] = 0;
+  unsigned* const w_cnt = s_cnt + (threadIdx.x >> 5) * cnt_stride;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {  // a state without a valid rate draws no virtual jumps
     const Real r = P.model[2 * n * n + 4 * n + i];
     s_rate[i] = rate_ok(r) ? r : (Real)0;
@@ -1289,7 +1295,7 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
     const bool hard = (m > 2) || lam > (Real)PM_LAMBDA_INV;
     const bool ok = TAIL ? (!hard && site_raw < S) : !hard;
     const int k = poisson_inv<Real>(lam, wA);
-    if (ok && m == 2 && (full || two)) atomicAdd(&s_cnt[ps * n + cs], 1u);
+    if (ok && m == 2 && (full || two)) atomicAdd(&w_cnt[ps * n + cs], 1u);
     add_dwell(s0, ok ? L0 : (Real)0);
     add_dwell(cs, ok ? L1 : (Real)0);
     // a path that ends up with a single jump point keeps that point in the state word: the real jump stays where it
@@ -1350,7 +1356,10 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
     else v = s_dw[threadIdx.x];
     P.dw_partial[blk * n + threadIdx.x] = v;
   }
-  for (int i = threadIdx.x; i < n * n; i += blockDim.x) if (s_cnt[i]) atomicAdd(&P.cnt[i], (unsigned long long)s_cnt[i]);
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+    const unsigned v = s_cnt[i] + s_cnt[cnt_stride + i] + s_cnt[2 * cnt_stride + i] + s_cnt[3 * cnt_stride + i];
+    if (v) atomicAdd(&P.cnt[i], (unsigned long long)v);
+  }
 }
 
 // rate of the virtual jumps in a state, 0 where the model has none (a state without a valid rate draws no virtual jumps)
@@ -1870,6 +1879,7 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
   int nq = 0;  // queue fill (warp-uniform)
   const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp, NW = (long long)gridDim.x * (blockDim.x >> 5);
   long long wi = gw;
+  unsigned long long en_next = wi < P.wk_total ? __ldg(P.wk_item + wi) : 0ull;  // the entry of the NEXT work item, in flight
   int e = 0, base = 0, total = 0, c = 0, inc = 0;
   long long w0 = 0, prow = 0, crow = 0, erow = 0;
   uint32_t bits = 0;
@@ -1879,12 +1889,12 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     if (room && base >= total && !finishing) {  // next work item
       if (wi >= P.wk_total) finishing = true;
       else {
-        e = __ldg(P.wk_hint + (wi >> 6));  // branch of work item (wi & ~63); the branch of wi is at most a few further
-        while (__ldg(P.wk_off + e + 1) <= wi) e++;
-        const int g = __ldg(P.wk_g + e);
-        w0 = (wi - __ldg(P.wk_off + e)) * g;
-        const int nw = (int)min((long long)g, (long long)W - w0);
+        const unsigned long long en = en_next;
+        e = (int)(en >> 32);
+        w0 = (long long)((en >> 5) & 0x7ffffffull);
+        const int nw = (int)(en & 31ull) + 1;
         wi += NW;
+        en_next = wi < P.wk_total ? __ldg(P.wk_item + wi) : 0ull;
         bits = lane < nw ? P.hard_ballot[(long long)e * W + w0 + lane] : 0u;
         c = __popc(bits);
         inc = c;

@@ -35,6 +35,23 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ dw_pa
 // ------------------------------------------------------------------------------------------------
 // Set-up kernels.
 // ------------------------------------------------------------------------------------------------
+// Work items of the persistent path kernels, flattened: item i = branch | first ballot word | words - 1 (ChainParams::wk_item).
+// Branch e owns the items [wk_off[e], wk_off[e + 1]), g_e = wk_g[e] words each (the last one what is left of the W words).
+__global__ void k_build_items(const long long* __restrict__ wk_off, const int* __restrict__ wk_g, int E, long long W, long long total,
+                              unsigned long long* items) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int lo = 0, hi = E - 1;  // the last branch with wk_off[e] <= i
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (wk_off[mid] <= i) lo = mid; else hi = mid - 1;
+  }
+  const long long g = wk_g[lo];
+  const long long w0 = (i - wk_off[lo]) * g;
+  const long long nw = min(g, W - w0);
+  items[i] = ((unsigned long long)(unsigned)lo << 32) | ((unsigned long long)w0 << 5) | (unsigned long long)(nw - 1);
+}
+
 // %nsmid: the range of the SM identifiers a block can read from %smid (PTX: it may exceed the number of SMs the runtime
 // reports, and the numbering need not be contiguous).  The fused prune + node-draw kernel indexes its slots by %smid.
 __global__ void k_nsmid(int* out) {
