@@ -1200,9 +1200,8 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
   const int n = NS > 0 ? NS : P.n;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_dw = reinterpret_cast<double*>(smem_raw);              // [4 warps][n] (NS>0) or [n] atomics (NS==0)
-  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_dw + 4 * n);    // [4 warps][n*n]: a copy per warp, so that the atomics of a warp
-                                                                  // (one per branch in nine warps out of ten) never wait for another warp's
-  Real* s_rate = reinterpret_cast<Real*>(s_cnt + 4 * (n * n + ((n * n) & 1)));  // [n] Omega + Q_ss of this sweep
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_dw + 4 * n);    // [n*n] (a copy per warp was tried: +2 % time, the address arithmetic costs more than the conflicts)
+  Real* s_rate = reinterpret_cast<Real*>(s_cnt + n * n + ((n * n) & 1));  // [n] Omega + Q_ss of this sweep
   // topology of the chunk (the same for every thread of the block): parent / child node and branch length
   int* s_par = reinterpret_cast<int*>(s_rate + n + (n & 1));
   int* s_chi = s_par + chunk;
@@ -1211,9 +1210,7 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
   // multiply-adds; fma(1, L, acc) = acc + L and fma(0, L, acc) = acc exactly) instead of NS compare / select / add triples
   __shared__ __align__(16) Real s_unit[NR][NR];
   const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
-  const int cnt_stride = n * n + ((n * n) & 1);
-  for (int i = threadIdx.x; i < 4 * cnt_stride; i += blockDim.x) s_cnt[i] = 0;
-  unsigned* const w_cnt = s_cnt + (threadIdx.x >> 5) * cnt_stride;
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) s_cnt[i] = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {  // a state without a valid rate draws no virtual jumps
     const Real r = P.model[2 * n * n + 4 * n + i];
     s_rate[i] = rate_ok(r) ? r : (Real)0;
@@ -1295,7 +1292,7 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
     const bool hard = (m > 2) || lam > (Real)PM_LAMBDA_INV;
     const bool ok = TAIL ? (!hard && site_raw < S) : !hard;
     const int k = poisson_inv<Real>(lam, wA);
-    if (ok && m == 2 && (full || two)) atomicAdd(&w_cnt[ps * n + cs], 1u);
+    if (ok && m == 2 && (full || two)) atomicAdd(&s_cnt[ps * n + cs], 1u);
     add_dwell(s0, ok ? L0 : (Real)0);
     add_dwell(cs, ok ? L1 : (Real)0);
     // a path that ends up with a single jump point keeps that point in the state word: the real jump stays where it
@@ -1356,10 +1353,7 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
     else v = s_dw[threadIdx.x];
     P.dw_partial[blk * n + threadIdx.x] = v;
   }
-  for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
-    const unsigned v = s_cnt[i] + s_cnt[cnt_stride + i] + s_cnt[2 * cnt_stride + i] + s_cnt[3 * cnt_stride + i];
-    if (v) atomicAdd(&P.cnt[i], (unsigned long long)v);
-  }
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) if (s_cnt[i]) atomicAdd(&P.cnt[i], (unsigned long long)s_cnt[i]);
 }
 
 // rate of the virtual jumps in a state, 0 where the model has none (a state without a valid rate draws no virtual jumps)
