@@ -666,6 +666,7 @@ struct ChainT : pm_chain {
       ny = std::max(1LL, std::min<long long>(ny, (E + 15) / 16));
       ny = std::min<long long>(ny, 65535);
       ny = std::max<long long>(ny, (E + 2047) / 2048);  // the easy path kernel stages a chunk's topology in shared memory
+      ny = std::max<long long>(ny, (E + ((1LL << 32) - 1) / S - 1) / std::max<long long>(1, ((1LL << 32) - 1) / S));  // ... and indexes the rows of a chunk with 32 bits: chunk x S < 2^32
       // (production: the offset of a path's records inside its slice is a 16-bit field of the state word, so a chunk
       // whose slice would be longer is split).  Production slices are shared by groups of 32 consecutive sites: the
       // bound on the records of 32 independent sites together is far tighter, relative to its mean, than 32 bounds on

@@ -1230,11 +1230,14 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
   const long long site = site_raw < S ? site_raw : S - 1;
   const bool full = P.full_counts != 0;
   const long long wglob = site_raw >> 5;  // ballot word of this warp (the same for its 32 lanes)
-  uint32_t* __restrict__ bal_p = P.hard_ballot + (long long)e0 * P.W + wglob;
+  // Rows of the chunk are addressed as base + 32-bit element index (the host keeps chunk x S below 2^32): one wide
+  // multiply-add per access and one add per branch, instead of a 64-bit pointer bump per array
+  uint32_t* __restrict__ const bal_b = P.hard_ballot + (long long)e0 * P.W + wglob;
   const bool bal_writer = (threadIdx.x & 31) == 0 && wglob < (long long)P.W;
   const uint32_t Wu = (uint32_t)P.W;
-  uint32_t* __restrict__ meta_p = P.meta + (long long)e0 * S + site;   // walks one row (S entries) per branch
-  uint16_t* __restrict__ shape_p = P.shape + (long long)e0 * S + site;
+  uint32_t* __restrict__ const meta_b = P.meta + (long long)e0 * S + site;   // row i of the chunk: meta_b[i * S]
+  uint16_t* __restrict__ const shape_b = P.shape + (long long)e0 * S + site;
+  uint32_t row = 0, rowf = 0, rowb = 0;  // i * S of the store cursor and of the fetch cursor, i * W of the ballot cursor
   const uint8_t* __restrict__ nstate = P.node_state + site;
   Real Racc[NR]; double Rsum[NR];
 #pragma unroll
@@ -1259,9 +1262,8 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
   const int nb = e1 - e0;
   struct Ahead { uint32_t mt; int ps, cs; };
   Ahead X = {0, 0, 0}, Y = {0, 0, 0};
-  const uint32_t* meta_f = meta_p;  // fetch cursor (runs ahead of the store cursor)
   auto fetch = [&](int i, Ahead& a) {
-    a.mt = *meta_f; meta_f += Su;
+    a.mt = meta_b[rowf]; rowf += Su;
     a.ps = nstate[(uint64_t)(uint32_t)lds_s32(a_par + 4u * (unsigned)i) * Su];
     a.cs = nstate[(uint64_t)(uint32_t)lds_s32(a_chi + 4u * (unsigned)i) * Su];
   };
@@ -1298,11 +1300,11 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
     // a path that ends up with a single jump point keeps that point in the state word: the real jump stays where it
     // was; a lone new virtual jump is uniform on the branch -- its 16-bit position comes from the B word
     const uint32_t newq = (!two && k == 1) ? pos_rand(wB) : q;
-    if (ok) { *meta_p = PM_META((two ? 2 : 1) + k, newq); *shape_p = PM_SHAPE(two ? 1 : 0, s0, cs); }
-    meta_p += Su; shape_p += Su;
+    if (ok) { meta_b[row] = PM_META((two ? 2 : 1) + k, newq); shape_b[row] = PM_SHAPE(two ? 1 : 0, s0, cs); }
+    row += Su;
     const unsigned bal = __ballot_sync(0xffffffffu, TAIL ? (hard && site_raw < S) : hard);
-    if (bal_writer) *bal_p = bal;
-    bal_p += Wu;
+    if (bal_writer) bal_b[rowb] = bal;
+    rowb += Wu;
   };
   auto run = [&](auto tail_c) {
     const std::true_type T{}; const std::false_type F{};
