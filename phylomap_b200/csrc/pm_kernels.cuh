@@ -1192,6 +1192,27 @@ __device__ __forceinline__ float lds_real(unsigned a, float) { float v; asm vola
 __device__ __forceinline__ double lds_real(unsigned a, double) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// Shared-memory layout of k_paths_easy, in bytes from the start of the dynamic window (all offsets multiples of 16):
+//   [0, dw) dwell partials [4 warps][n] f64 | cnt: transition counters [n*n] u32 | rate [n] | unit: identity matrix [n][n]
+//   | topo: one 16-byte entry per branch of the chunk: parent node, child node (int), branch length (Real)
+// With a compile-time state count every offset but the entry index is an immediate, so the kernel keeps ONE base address
+// in a register (formed from several pointers, the compiler rebuilds the shared window base at every use: ~10 % of the
+// loop's instructions).
+template <typename Real>
+struct EasySmem {
+  int cnt, rate, unit, topo;
+  __host__ __device__ static int up16(int x) { return (x + 15) & ~15; }
+  __host__ __device__ explicit EasySmem(int n) {
+    cnt = up16(4 * n * (int)sizeof(double));
+    rate = up16(cnt + n * n * (int)sizeof(unsigned));
+    unit = up16(rate + n * (int)sizeof(Real));
+    topo = up16(unit + n * n * (int)sizeof(Real));
+  }
+  __host__ __device__ size_t bytes(int chunk) const { return (size_t)topo + (size_t)chunk * 16; }
+};
+__device__ __forceinline__ void lds_v2s32(unsigned a, int& x, int& y) { asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(x), "=r"(y) : "r"(a)); }
+__device__ __forceinline__ void red_shared_inc(unsigned a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
+
 template <typename Real, int NS>
 __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy(ChainParams<Real> P, uint32_t iter, int chunk) {
   if (P.ctl) iter = P.ctl[0];
@@ -1199,31 +1220,33 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
   typedef Pin<Real> PN;
   const int n = NS > 0 ? NS : P.n;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_dw = reinterpret_cast<double*>(smem_raw);              // [4 warps][n] (NS>0) or [n] atomics (NS==0)
-  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_dw + 4 * n);    // [n*n] (a copy per warp was tried: +2 % time, the address arithmetic costs more than the conflicts)
-  Real* s_rate = reinterpret_cast<Real*>(s_cnt + n * n + ((n * n) & 1));  // [n] Omega + Q_ss of this sweep
-  // topology of the chunk (the same for every thread of the block): parent / child node and branch length
-  int* s_par = reinterpret_cast<int*>(s_rate + n + (n & 1));
-  int* s_chi = s_par + chunk;
-  Real* s_len = reinterpret_cast<Real*>(s_chi + chunk);
+  const EasySmem<Real> lay(n);
+  double* s_dw = reinterpret_cast<double*>(smem_raw);                       // [4 warps][n] (NS>0) or [n] atomics (NS==0)
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(smem_raw + lay.cnt);       // [n*n] (a copy per warp was tried: +2 % time)
+  Real* s_rate = reinterpret_cast<Real*>(smem_raw + lay.rate);             // [n] Omega + Q_ss of this sweep
   // dwell of state s: Racc += e_s * L with the unit vector e_s read from shared memory (one vector load + NS fused
   // multiply-adds; fma(1, L, acc) = acc + L and fma(0, L, acc) = acc exactly) instead of NS compare / select / add triples
-  __shared__ __align__(16) Real s_unit[NR][NR];
+  Real* s_unit = reinterpret_cast<Real*>(smem_raw + lay.unit);             // [n][n]
+  // topology of the chunk (the same for every thread of the block): parent / child node and branch length per branch
+  unsigned char* s_topo = smem_raw + lay.topo;
   const int e0 = blockIdx.y * chunk, e1 = min(P.E, e0 + chunk);
-  for (int i = threadIdx.x; i < n * n; i += blockDim.x) s_cnt[i] = 0;
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) { s_cnt[i] = 0; s_unit[i] = (i / n == i % n) ? (Real)1 : (Real)0; }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {  // a state without a valid rate draws no virtual jumps
     const Real r = P.model[2 * n * n + 4 * n + i];
     s_rate[i] = rate_ok(r) ? r : (Real)0;
   }
   for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_dw[i] = 0.0;
   for (int i = threadIdx.x; i < e1 - e0; i += blockDim.x) {
-    s_par[i] = P.e_parent[e0 + i]; s_chi[i] = P.e_child[e0 + i]; s_len[i] = P.e_len[e0 + i];
+    int* en = reinterpret_cast<int*>(s_topo + 16 * (size_t)i);
+    en[0] = P.e_parent[e0 + i]; en[1] = P.e_child[e0 + i];
+    *reinterpret_cast<Real*>(en + 2) = P.e_len[e0 + i];
   }
-  if (NS > 0 && (int)threadIdx.x < NR * NR) s_unit[threadIdx.x / NR][threadIdx.x % NR] = (threadIdx.x / NR == threadIdx.x % NR) ? (Real)1 : (Real)0;
   __syncthreads();
-  // 32-bit shared-memory addresses, formed once (generic pointers would be converted again at every access)
-  const unsigned a_par = smem_addr(s_par), a_chi = smem_addr(s_chi), a_len = smem_addr(s_len), a_rate = smem_addr(s_rate),
-                 a_unit = smem_addr(&s_unit[0][0]);
+  // ONE 32-bit shared-memory base, kept in a register; everything else is base + immediate (+ scaled index)
+  unsigned a_base = smem_addr(smem_raw);
+  asm volatile("" : "+r"(a_base));
+  const unsigned a_cnt = a_base + (unsigned)lay.cnt, a_rate = a_base + (unsigned)lay.rate, a_unit = a_base + (unsigned)lay.unit,
+                 a_topo = a_base + (unsigned)lay.topo;
   const long long S = P.S;
   const uint32_t Su = (uint32_t)S;  // S < 2^31 (checked by the host): 32 x 32 -> 64-bit offsets are one instruction
   const long long site_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1264,8 +1287,10 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
   Ahead X = {0, 0, 0}, Y = {0, 0, 0};
   auto fetch = [&](int i, Ahead& a) {
     a.mt = meta_b[rowf]; rowf += Su;
-    a.ps = nstate[(uint64_t)(uint32_t)lds_s32(a_par + 4u * (unsigned)i) * Su];
-    a.cs = nstate[(uint64_t)(uint32_t)lds_s32(a_chi + 4u * (unsigned)i) * Su];
+    int par, chi;
+    lds_v2s32(a_topo + 16u * (unsigned)i, par, chi);
+    a.ps = nstate[(uint64_t)(uint32_t)par * Su];
+    a.cs = nstate[(uint64_t)(uint32_t)chi * Su];
   };
   uint32_t po[4] = {0, 0, 0, 0};
   // one branch, from what was fetched for it.  ODD: second branch of its Philox pair (the block was drawn by the first,
@@ -1279,7 +1304,7 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
     const uint32_t wA = ODD ? po[2] : po[0], wB = ODD ? po[3] : po[1];
     const int m = (int)(mt & 0xffffu);
     const uint32_t q = mt >> 16;
-    const Real Le = lds_real(a_len + (unsigned)sizeof(Real) * (unsigned)i, (Real)0);
+    const Real Le = lds_real(a_topo + 16u * (unsigned)i + 8u, (Real)0);
     // pieces: (Le) or (p1, Le - p1); states ps | cs (a one-piece branch carries the child state, :460-475).  The
     // virtual jumps of a two-run path are counted together: K ~ Poisson(lam0 + lam1) from the A word (their positions,
     // if a later sweep needs them, are regenerated by the general kernels, see RunPieces)
@@ -1294,7 +1319,7 @@ __global__ void __launch_bounds__(128, (sizeof(Real) == 8 ? 6 : 8)) k_paths_easy
     const bool hard = (m > 2) || lam > (Real)PM_LAMBDA_INV;
     const bool ok = TAIL ? (!hard && site_raw < S) : !hard;
     const int k = poisson_inv<Real>(lam, wA);
-    if (ok && m == 2 && (full || two)) atomicAdd(&s_cnt[ps * n + cs], 1u);
+    if (ok && m == 2 && (full || two)) red_shared_inc(a_cnt + 4u * (unsigned)(ps * n + cs));
     add_dwell(s0, ok ? L0 : (Real)0);
     add_dwell(cs, ok ? L1 : (Real)0);
     // a path that ends up with a single jump point keeps that point in the state word: the real jump stays where it
