@@ -302,6 +302,12 @@ struct TreeDev {
   DevBuf slot_busy;          // one flag per slot
   long long pl_sites = 0;    // sites per node row of the partials buffer: 32 pl_slots, or S
   int rec_shift = 0;         // production path records: 2^rec_shift consecutive sites share a slice
+  // few sites on a tree whose per-site state fits shared memory (pm_small.cuh): a block per site runs the whole sweep, and
+  // for the fixed-Q samplers all the sweeps of a call, in one launch
+  bool small_ok = false;
+  int small_chunks = 0;      // record chunks (rows of rec_cursor)
+  DevBuf small_down, small_part, small_cnt, small_root;
+  int small_cap = 0;         // sweeps the output buffers hold
   long long rec_groups = 0;
   DevBuf e_len_d, TP, ll_partial;  // DIC samplers: branch lengths in FP64, exp(Q t_e) per branch, block partials of log p(y|Q)
   std::vector<int> cap_off_h;
@@ -421,6 +427,7 @@ struct ChainT : pm_chain {
 
   template <int NSc, bool EX>
   void launch_sweep_t(TreeDev<Real>& t, uint32_t iter, double* row) {
+    if (!EX && use_small(t)) { launch_small(t, iter, 1, row); launches_per_sweep = 2; return; }
     const uint32_t* ctl_d = capturing ? ctl.as<uint32_t>() : nullptr;
     {
       pm::ChainParams<Real> P = t.P;
@@ -456,6 +463,32 @@ struct ChainT : pm_chain {
     end_timed();
     launches_per_sweep = (t.pl_slots ? 1 : 2) + (exact ? 2 : (iter == 0 && !capturing) ? 3 : 4);
     if (!capturing) launches += launches_per_sweep;
+  }
+  // Few sites on a small tree: sweeps [iter0, iter0 + nsweeps) of every site in one launch, a block per site, the state in
+  // shared memory (pm_small.cuh); a second launch sums the sites and assembles the rows (WR doubles per sweep, from rows_d).
+  bool use_small(const TreeDev<Real>& t) const { return t.small_ok && !timing && !debug_sync && !capturing; }
+  void launch_small(TreeDev<Real>& t, uint32_t iter0, int nsweeps, double* rows_d) {
+    const long long S = t.S;
+    const int batch = (int)std::max<long long>(1, std::min<long long>(nsweeps, (64LL << 20) / (S * n * (long long)sizeof(double))));
+    if (t.small_cap < batch) {
+      t.small_part.alloc((size_t)batch * S * n * sizeof(double));
+      t.small_cnt.alloc((size_t)batch * n * n * sizeof(unsigned long long));
+      t.small_root.alloc((size_t)batch * sizeof(int));
+      t.small_cap = batch;
+    }
+    for (int b0 = 0; b0 < nsweeps; b0 += batch) {
+      const int nb = std::min(batch, nsweeps - b0);
+      CK(cudaMemsetAsync(t.small_cnt.p, 0, (size_t)nb * n * n * sizeof(unsigned long long), stream));
+      CK(cudaMemsetAsync(t.small_root.p, 0, (size_t)nb * sizeof(int), stream));
+      pm::SmallOut o;
+      o.part = t.small_part.template as<double>(); o.cnt = t.small_cnt.template as<unsigned long long>(); o.root = t.small_root.template as<int>();
+      o.down = reinterpret_cast<const int4*>(t.small_down.p); o.down_off = t.down_off.template as<int>();
+      o.n_down_levels = (int)t.sch.down_off.size() - 1; o.n_chunks = t.small_chunks;
+      if (NS == 2) pm::Sweep<Real, 2, false>::small_chain(t.P, (int)S, stream, iter0 + (uint32_t)b0, nb, o);
+      else pm::Sweep<Real, 4, false>::small_chain(t.P, (int)S, stream, iter0 + (uint32_t)b0, nb, o);
+      pm::k_small_reduce<<<nb, 128, 0, stream>>>(o.part, o.cnt, o.root, S, n, rows_d + (size_t)b0 * WR, WR, err_flag.as<unsigned>(), W);
+      launches += 2;
+    }
   }
   // DIC samplers: log p(y | Q) of the current Q into row[n + n*n + 1] (after the sweep: PL is free again)
   void launch_loglik(TreeDev<Real>& t, double* row) {
@@ -672,7 +705,18 @@ struct ChainT : pm_chain {
       // bound on the records of 32 independent sites together is far tighter, relative to its mean, than 32 bounds on
       // one site each (3.8 -> 0.3 bytes per branch-site at the benchmark's size).  Where such a slice would not fit the
       // 16-bit offset (long paths: the Squamate vignette) every site keeps its own.
-      const bool pooled_ok = !exact && !V.exp && !V.llonly && !(getenv("PHYLOMAP_B200_REC_POOL") && getenv("PHYLOMAP_B200_REC_POOL")[0] == '0');
+      // One block per site, state in shared memory (pm_small.cuh), when the sites are few and the tree fits: production
+      // arithmetic, 2 / 4 states.  PHYLOMAP_B200_SMALL=0 keeps the 32-sites-per-warp kernels (same rows: the tests compare),
+      // PHYLOMAP_B200_SMALL_SITES moves the site limit (default: four blocks per SM).
+      {
+        long long small_sites = 4LL * prop.multiProcessorCount;
+        if (const char* v = getenv("PHYLOMAP_B200_SMALL_SITES")) small_sites = atoll(v);
+        const bool off = getenv("PHYLOMAP_B200_SMALL") && getenv("PHYLOMAP_B200_SMALL")[0] == '0';
+        const size_t need = NS == 2 ? pm::Sweep<Real, 2, false>::small_smem(T) : NS == 4 ? pm::Sweep<Real, 4, false>::small_smem(T) : (size_t)-1;
+        t->small_ok = !off && !exact && (NS == 2 || NS == 4) && !V.exp && !V.llonly && opt.rng != PM_RNG_TABLE && S <= small_sites &&
+                      need <= (size_t)200 * 1024;
+      }
+      const bool pooled_ok = !t->small_ok && !exact && !V.exp && !V.llonly && !(getenv("PHYLOMAP_B200_REC_POOL") && getenv("PHYLOMAP_B200_REC_POOL")[0] == '0');
       const long long ny_first = ny;
       for (int attempt = pooled_ok ? 0 : 1; attempt < 2; attempt++) {
       t->rec_shift = attempt == 0 ? 5 : 0;
@@ -738,6 +782,7 @@ struct ChainT : pm_chain {
       if (fits) break;
       }
       const long long R = t->cap_off_h[ny];
+      t->small_chunks = (int)ny;
       mark("record capacities");
       // Partials are scratch between the pruning pass and the node draws of one sweep, and a block's partials are read by
       // nobody but the same block's node draws: the production kernels (n = 2, 4) run both passes in ONE kernel whose
@@ -830,6 +875,21 @@ struct ChainT : pm_chain {
           }
         t->n_cd_tips = (int)tips.size() / 2;
         upload(t->cd_tips, tips, stream);
+        if (t->small_ok) {
+          // the same draws node by node: every drawn node with the Philox block and word the clade kernel gives it
+          // (k_small_chain decodes the key), grouped by depth like the generic schedule
+          std::vector<uint32_t> key(2 * (size_t)T - 1, 0u);
+          for (int i = 0; i < (int)cs.down_top.size() / 4; i++) key[cs.down_top[(size_t)4 * i]] = 0x80000000u | (uint32_t)i;
+          for (int i = 0; i < n2; i++) key[cs.down_seq[(size_t)4 * i]] = (uint32_t)i;
+          for (int v = 0; v < T; v++) key[v] = 0x40000000u | (uint32_t)v;
+          const int nd = (int)t->sch.down_entries.size() / 3;
+          std::vector<int> d4((size_t)4 * std::max(nd, 1), 0);
+          for (int i = 0; i < nd; i++) {
+            const int* en = &t->sch.down_entries[(size_t)3 * i];
+            d4[(size_t)4 * i] = en[0]; d4[(size_t)4 * i + 1] = en[1]; d4[(size_t)4 * i + 2] = en[2]; d4[(size_t)4 * i + 3] = (int)key[en[0]];
+          }
+          upload(t->small_down, d4, stream);
+        }
       }
       upload(t->down_entries, t->sch.down_entries, stream);
       upload(t->down_off, t->sch.down_off, stream);
@@ -1117,8 +1177,10 @@ struct ChainT : pm_chain {
       // small problems: the first sweep of the call goes out launch by launch (it also sets the kernels' attributes), the
       // others replay a captured sweep
       const bool small = (double)t.S * t.sch.E <= (double)(1 << 22);
-      const bool use_graph = !V.exp && !timing && !debug_sync && count > 1 && (graph_mode == 1 || (graph_mode != 0 && small));
-      for (int i = 0; i < count; i++) {
+      const bool one_launch = !V.exp && !exact && use_small(t);  // every sweep of the call inside one launch
+      const bool use_graph = !one_launch && !V.exp && !timing && !debug_sync && count > 1 && (graph_mode == 1 || (graph_mode != 0 && small));
+      if (one_launch) launch_small(t, (uint32_t)iters_done, count, rows.as<double>());
+      for (int i = 0; i < count && !one_launch; i++) {
         if (V.exp) launch_exp_iteration(t, (uint32_t)(iters_done + i), rows.as<double>() + (size_t)i * WR);
         else if (use_graph && i > 0) {
           if (i == 1) {

@@ -1482,68 +1482,47 @@ __device__ __noinline__ int count_gaps(RngDesc d, uint32_t site, uint32_t it, ui
 template <typename Real>
 struct HardItem { uint32_t site, e, meta, ends, shape; };  // ends = parent state | child state << 8
 
-// WHICH = 0: the short items only (small code, half the registers: twice the resident warps), launched first: it clears
-// the ballot bits of the items it takes.  WHICH = 1: whatever is left.
-template <typename Real, int NS, int MINB, int WHICH>
-__global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, uint32_t iter, int first) {
-  if (P.ctl) { iter = P.ctl[0]; first = iter == 0u; }
-  constexpr int NC = NS > 0 ? NS : PM_NMAX;
-  constexpr int NR = NS > 0 ? NS : 1;
+// The two item routines of the general path kernels, as methods of a per-thread context (so that the persistent kernels
+// below and the one-block-per-site chain kernel of small trees, pm_small.cuh, run the SAME code on an item).  They return
+// the item's new state word and shape word; the caller stores them.
+template <typename Real, int NS>
+struct PathWorker {
+  static constexpr int NC = NS > 0 ? NS : PM_NMAX;
+  static constexpr int NR = NS > 0 ? NS : 1;
   typedef typename StreamSel<Real, false>::type Stream;
   typedef Pin<Real> PN;
-  const int n = NS > 0 ? NS : P.n;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_dw = reinterpret_cast<double*>(smem_raw);                 // [4 warps][n] (NS>0) or [n] atomics (NS==0)
-  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_dw + 4 * n);       // [n*n]
-  Real* sB = reinterpret_cast<Real*>(s_cnt + n * n + ((n * n) & 1));  // dense B (forward row)
-  Real* sBs = sB + n * n;
-  Real* sVec = sBs + n * n;  // pid | scale_old | scale_new | rate_old | rate_new
-  Real* sPow = sVec + 5 * n;
-  const int npow_s = min(smem_pow_count<NS, false>(), P.jcap);
-  for (int i = threadIdx.x; i < n * n; i += blockDim.x) { sB[i] = P.model[i]; sBs[i] = P.model[n * n + i]; s_cnt[i] = 0; }
-  for (int i = threadIdx.x; i < 5 * n; i += blockDim.x) sVec[i] = P.model[2 * n * n + i];
-  for (int i = threadIdx.x; i < npow_s * n * n; i += blockDim.x) sPow[i] = P.ppow[i];
-  for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_dw[i] = 0.0;
-  // per-warp queues of classified items: [0] the common short shape (processed by straight-line code), [1] everything else
-  __shared__ HardItem<Real> s_q[4][64];
-  __shared__ unsigned short s_stage[4][1024];  // site offsets of the set bits of the warp's current work item (<= 32 words)
-  __syncthreads();
-  const Real* s_rate_old = sVec + 3 * n;
-  const Real* s_rate_new = sVec + 4 * n;
-  Real rate_max = 0;  // largest virtual-jump rate of the previous and of this sweep: bounds every run's lambda by rate_max * t_e
-  for (int s = 0; s < n; s++) {
-    const Real a = s_rate_old[s], b = s_rate_new[s];
-    if (rate_ok(a)) rate_max = max(rate_max, a);
-    if (rate_ok(b)) rate_max = max(rate_max, b);
-  }
-  const long long S = P.S;
-  const int W = P.W;
-  const bool full = P.full_counts != 0;
-  const Real* __restrict__ rd_len = P.rec_len[(iter & 1u) ^ 1u];
-  const uint8_t* __restrict__ rd_st = P.rec_st[(iter & 1u) ^ 1u];
-  Real* __restrict__ wr_len = P.rec_len[iter & 1u];
-  uint8_t* __restrict__ wr_st = P.rec_st[iter & 1u];
+  const ChainParams<Real>& P;
+  const uint32_t iter; const int first; const int n; const bool full;
+  const Real* const sB; const Real* const sBs; const Real* const sPow; const int npow_s;
+  unsigned* const s_cnt; double* const s_dw;
+  const Real* const s_rate_old; const Real* const s_rate_new;
+  const Real* __restrict__ rd_len; const uint8_t* __restrict__ rd_st;
+  Real* __restrict__ wr_len; uint8_t* __restrict__ wr_st;
   double Rsum[NR];
+  unsigned errbits;
+  __device__ __forceinline__ PathWorker(const ChainParams<Real>& P_, uint32_t iter_, int first_, int n_, const Real* sB_, const Real* sBs_,
+                                        const Real* sPow_, int npow_s_, unsigned* s_cnt_, double* s_dw_, const Real* rate_old_,
+                                        const Real* rate_new_)
+      : P(P_), iter(iter_), first(first_), n(n_), full(P_.full_counts != 0), sB(sB_), sBs(sBs_), sPow(sPow_), npow_s(npow_s_),
+        s_cnt(s_cnt_), s_dw(s_dw_), s_rate_old(rate_old_), s_rate_new(rate_new_), rd_len(P_.rec_len[(iter_ & 1u) ^ 1u]),
+        rd_st(P_.rec_st[(iter_ & 1u) ^ 1u]), wr_len(P_.rec_len[iter_ & 1u]), wr_st(P_.rec_st[iter_ & 1u]), errbits(0) {
 #pragma unroll
-  for (int j = 0; j < NR; j++) Rsum[j] = 0;
-  unsigned errbits = 0;
-  auto add_dwell = [&](int s, Real L) {
+    for (int j = 0; j < NR; j++) Rsum[j] = 0;
+  }
+  __device__ __forceinline__ void add_dwell(int s, Real L) {
     if (NS > 0) {
 #pragma unroll
       for (int j = 0; j < NR; j++) Rsum[j] += (s == j) ? (double)L : 0.0;
     } else atomicAdd(&s_dw[s], (double)L);
-  };
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned FULL = 0xffffffffu;
+  }
 
   // ---- the common short shapes: three or four pieces (two or three jump points), at most one of them a real jump, every
   // run in count mode.  Unrolled, register-only restatement of what the general code below does for such an item: same
   // streams, same words, same pinned arithmetic, so a path may be written by one and regenerated by the other.
-  auto short_item = [&](const HardItem<Real> it) {
+  __device__ __forceinline__ void short_item(const HardItem<Real> it, uint32_t& meta_out, uint16_t& shape_out) {
     const long long site = it.site;
     const int eb = (int)it.e;
     const uint32_t mt = it.meta;
-    const long long pe = (long long)eb * S + site;
     const int m = (int)(mt & 0xffffu);  // 3 or 4
     const int nj = (int)(it.shape & 0x3fu);
     const int so0 = (int)((it.shape >> 6) & 0x1fu), so1 = (int)((it.shape >> 11) & 0x1fu);
@@ -1686,12 +1665,12 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
         }
       }
     }
-    P.meta[pe] = PM_META(newm, newq);
-    P.shape[pe] = PM_SHAPE(nout - 1, S0, S1);
-  };
+    meta_out = PM_META(newm, newq);
+    shape_out = PM_SHAPE(nout - 1, S0, S1);
+  }
 
   // ---- any item: regenerate the pieces run by run, redraw the interior states, merge, count, emit ----
-  auto general_item = [&](const HardItem<Real> it) {
+  __device__ __forceinline__ void general_item(const HardItem<Real> it, uint32_t& meta_out, uint16_t& shape_out) {
     const long long site = it.site;
     const int eb = (int)it.e;
     const uint32_t mt = it.meta;
@@ -1700,7 +1679,6 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
     const long long sbase = ((long long)cap0 * P.rec_groups) + (site >> P.rec_shift) * (long long)cap_c;  // record slice of the site's group
     int* cursor = P.rec_cursor + (long long)ck * P.rec_groups + (site >> P.rec_shift);
 
-    const long long pe = (long long)eb * S + site;
     const int m = (int)(mt & 0xffffu);
     const int njf = first ? 0 : (int)(it.shape & 0x3fu);  // real jumps; 63 = "63 or more, see the record header"
     const int ps = (int)(it.ends & 0xffu), cs = (int)(it.ends >> 8);
@@ -1890,9 +1868,50 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       for (int r = 2; r < nout; r++) { wr_len[sbase + o + r] = bufL[r]; wr_st[sbase + o + r] = bufS[r]; }
       break;
     }
-    P.meta[pe] = PM_META(newm, newq);
-    P.shape[pe] = PM_SHAPE(min(nout - 1, 63), S0, S1);
-  };
+    meta_out = PM_META(newm, newq);
+    shape_out = PM_SHAPE(min(nout - 1, 63), S0, S1);
+  }
+};
+
+// WHICH = 0: the short items only (small code, half the registers: twice the resident warps), launched first: it clears
+// the ballot bits of the items it takes.  WHICH = 1: whatever is left.
+template <typename Real, int NS, int MINB, int WHICH>
+__global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, uint32_t iter, int first) {
+  if (P.ctl) { iter = P.ctl[0]; first = iter == 0u; }
+  constexpr int NC = NS > 0 ? NS : PM_NMAX;
+  constexpr int NR = NS > 0 ? NS : 1;
+  typedef typename StreamSel<Real, false>::type Stream;
+  typedef Pin<Real> PN;
+  const int n = NS > 0 ? NS : P.n;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_dw = reinterpret_cast<double*>(smem_raw);                 // [4 warps][n] (NS>0) or [n] atomics (NS==0)
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_dw + 4 * n);       // [n*n]
+  Real* sB = reinterpret_cast<Real*>(s_cnt + n * n + ((n * n) & 1));  // dense B (forward row)
+  Real* sBs = sB + n * n;
+  Real* sVec = sBs + n * n;  // pid | scale_old | scale_new | rate_old | rate_new
+  Real* sPow = sVec + 5 * n;
+  const int npow_s = min(smem_pow_count<NS, false>(), P.jcap);
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) { sB[i] = P.model[i]; sBs[i] = P.model[n * n + i]; s_cnt[i] = 0; }
+  for (int i = threadIdx.x; i < 5 * n; i += blockDim.x) sVec[i] = P.model[2 * n * n + i];
+  for (int i = threadIdx.x; i < npow_s * n * n; i += blockDim.x) sPow[i] = P.ppow[i];
+  for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_dw[i] = 0.0;
+  // per-warp queues of classified items: [0] the common short shape (processed by straight-line code), [1] everything else
+  __shared__ HardItem<Real> s_q[4][64];
+  __shared__ unsigned short s_stage[4][1024];  // site offsets of the set bits of the warp's current work item (<= 32 words)
+  __syncthreads();
+  const Real* s_rate_old = sVec + 3 * n;
+  const Real* s_rate_new = sVec + 4 * n;
+  Real rate_max = 0;  // largest virtual-jump rate of the previous and of this sweep: bounds every run's lambda by rate_max * t_e
+  for (int s = 0; s < n; s++) {
+    const Real a = s_rate_old[s], b = s_rate_new[s];
+    if (rate_ok(a)) rate_max = max(rate_max, a);
+    if (rate_ok(b)) rate_max = max(rate_max, b);
+  }
+  const long long S = P.S;
+  const int W = P.W;
+  PathWorker<Real, NS> pw(P, iter, first, n, sB, sBs, sPow, npow_s, s_cnt, s_dw, s_rate_old, s_rate_new);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned FULL = 0xffffffffu;
 
   // ---- the warp walks its work items; items are classified, queued and processed 32 at a time ----
   // One loop, one place where items are processed (the kernel stalls mostly on instruction fetch: branchy code, few
@@ -1968,18 +1987,23 @@ __global__ void __launch_bounds__(128, MINB) k_paths_hard(ChainParams<Real> P, u
       const int take = min(nq, 32);
       nq -= take;
       if (lane < take) {
-        if (WHICH == 0) short_item(s_q[warp][nq + lane]);
-        else general_item(s_q[warp][nq + lane]);
+        const HardItem<Real> it = s_q[warp][nq + lane];
+        uint32_t mo; uint16_t so;
+        if (WHICH == 0) pw.short_item(it, mo, so);
+        else pw.general_item(it, mo, so);
+        const long long pe = (long long)it.e * S + it.site;
+        P.meta[pe] = mo;
+        P.shape[pe] = so;
       }
       __syncwarp();
     } else if (finishing) break;
   }
-  if (errbits) atomicOr(P.err_flag, errbits);
+  if (pw.errbits) atomicOr(P.err_flag, pw.errbits);
 
   if (NS > 0) {
 #pragma unroll
     for (int j = 0; j < NR; j++) {
-      double v = Rsum[j];
+      double v = pw.Rsum[j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
       if (lane == 0) s_dw[warp * n + j] = v;

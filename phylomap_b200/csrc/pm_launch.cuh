@@ -2,6 +2,7 @@
 // translation units (pm_sweep_*.cu) so that they compile in parallel.
 #pragma once
 #include "pm_kernels.cuh"
+#include "pm_small.cuh"
 
 namespace pm {
 
@@ -17,6 +18,10 @@ struct Sweep {
                           int phases, int* slot_busy, int slots_per_sm, unsigned long long* phase_ns);
   static void paths(const ChainParams<Real>& P, dim3 grid, size_t smem, cudaStream_t st, uint32_t iter, int first, int chunk,
                     int hard_blocks);
+  // production, n = 2 / 4, few sites on a tree whose per-site state fits shared memory: `nsweeps` sweeps of every site in
+  // ONE launch, a block per site (pm_small.cuh).  small_smem: the dynamic shared memory it needs for T tips.
+  static size_t small_smem(int T);
+  static void small_chain(const ChainParams<Real>& P, int sites, cudaStream_t st, uint32_t iter0, int nsweeps, const SmallOut& out);
 };
 
 }  // namespace pm

@@ -83,5 +83,20 @@ void Sweep<Real, NS, EXACT>::paths(const ChainParams<Real>& P, dim3 grid, size_t
     k_paths_hard<Real, NS, 4, 1><<<hard_blocks, 128, smem, st>>>(P, iter, first);
   }
 }
+template <typename Real, int NS, bool EXACT>
+size_t Sweep<Real, NS, EXACT>::small_smem(int T) {
+  if constexpr (!EXACT && (NS == 2 || NS == 4)) return (size_t)SmallSmem<Real, NS>(T).total;
+  return (size_t)1 << 40;  // no such kernel
+}
+template <typename Real, int NS, bool EXACT>
+void Sweep<Real, NS, EXACT>::small_chain(const ChainParams<Real>& P, int sites, cudaStream_t st, uint32_t iter0, int nsweeps,
+                                         const SmallOut& out) {
+  if constexpr (!EXACT && (NS == 2 || NS == 4)) {
+    auto kern = k_small_chain<Real, NS>;
+    const size_t sm = (size_t)SmallSmem<Real, NS>(P.T).total;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    kern<<<sites, 256, sm, st>>>(P, iter0, nsweeps, out);
+  }
+}
 
 }  // namespace pm

@@ -23,16 +23,39 @@ def cpu(variant, z, Q, pid, Om, N, fast):
 # configs[0]
 z = synth.simulate_2_state_tree(101, synth.yule_tree(100, seed=1, mean_branch=5.0), cases.Q2, cases.PID2)
 N = 1000
+def resident(zz, Q, pid, Om, n_sweeps, prec, variant=None):
+    """us per sweep of a chain that already exists (creation, upload and the first call excluded): best of three calls"""
+    from phylomap_b200 import capi
+    ch = pb.Chain(capi.PM_V_PLAIN if variant is None else variant, zz, Q, pid, Om, 5 * n_sweeps, precision=prec, seed=5)
+    ch.run(n_sweeps)
+    best = 1e30
+    for _ in range(3):
+        torch.cuda.synchronize(); t = time.perf_counter(); ch.run(n_sweeps); torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t)
+    ch.close()
+    return 1e6 * best / n_sweeps
+# the one-block-per-site chain kernel (pm_small.cuh, the default at this size) ...
 for prec in ("f32", "f64"):
-    for graph in ("1", "0"):   # replay of a captured sweep (the default at this size) against launch-by-launch
+    dt, _ = gpu(pb.sumstatMCMC, z, cases.Q2, cases.PID2, 0.2, N, seed=5, precision=prec)
+    out["cfg0_gpu_%s_one_block_per_site_us_per_sweep_whole_call" % prec] = 1e6 * dt / N
+    out["cfg0_gpu_%s_one_block_per_site_us_per_sweep_resident" % prec] = resident(z, cases.Q2, cases.PID2, 0.2, N, prec)
+# ... against the 32-sites-per-warp kernels
+os.environ["PHYLOMAP_B200_SMALL"] = "0"
+for prec in ("f32", "f64"):
+    for graph in ("1", "0"):   # replay of a captured sweep (their default at this size) against launch-by-launch
         os.environ["PHYLOMAP_B200_GRAPH"] = graph
         dt, _ = gpu(pb.sumstatMCMC, z, cases.Q2, cases.PID2, 0.2, N, seed=5, precision=prec)
-        out["cfg0_gpu_%s_%s_us_per_sweep" % (prec, "graph" if graph == "1" else "launches")] = 1e6 * dt / N
+        out["cfg0_gpu_%s_wide_%s_us_per_sweep_whole_call" % (prec, "graph" if graph == "1" else "launches")] = 1e6 * dt / N
 del os.environ["PHYLOMAP_B200_GRAPH"]
-for S in (8, 32):   # a few characters at once on the same tree
+out["cfg0_gpu_f32_wide_us_per_sweep_resident"] = resident(z, cases.Q2, cases.PID2, 0.2, N, "f32")
+for S in (8, 32, 148, 592, 2048):   # a few characters at once on the same tree, either set of kernels
     zS = synth.simulate_2_state_tree(101, synth.yule_tree(100, seed=1, mean_branch=5.0), cases.Q2, cases.PID2, n_sites=S)
-    dt, _ = gpu(pb.sumstatMCMC, zS, cases.Q2, cases.PID2, 0.2, N, seed=5, precision="f32")
-    out["cfg0_gpu_f32_%d_sites_us_per_sweep" % S] = 1e6 * dt / N
+    for small in ("1", "0"):
+        os.environ["PHYLOMAP_B200_SMALL"] = small
+        os.environ["PHYLOMAP_B200_SMALL_SITES"] = "1000000"
+        out["cfg0_gpu_f32_%d_sites_%s_us_per_sweep_resident" % (S, "one_block_per_site" if small == "1" else "wide")] = \
+            resident(zS, cases.Q2, cases.PID2, 0.2, 200, "f32")
+del os.environ["PHYLOMAP_B200_SMALL"], os.environ["PHYLOMAP_B200_SMALL_SITES"]
 out["cfg0_cpu_port_faithful_us_per_sweep"] = 1e6 * cpu(bridge.PLAIN, z, cases.Q2, cases.PID2, 0.2, N, False) / N
 out["cfg0_cpu_port_optimised_us_per_sweep"] = 1e6 * cpu(bridge.PLAIN, z, cases.Q2, cases.PID2, 0.2, N, True) / N
 t = time.perf_counter(); bridge.ref_run(bridge.PLAIN, [z.oracle_dict()], cases.Q2, cases.PID2, 0.2, N, seed=3)
@@ -42,7 +65,11 @@ Q = np.array([[-0.001, 0.001], [0.006, -0.006]])
 zs = synth.simulate_2_state_tree(101, cases.squamate_tree(), Q, cases.PID2)
 N2 = 40
 dt, _ = gpu(pb.sumstatMCMC_bigtree, zs, Q, cases.PID2, 10.0, N2, seed=5, precision="f64")
-out["squamate_gpu_f64_ms_per_sweep"] = 1e3 * dt / N2
+out["squamate_gpu_f64_one_block_per_site_ms_per_sweep"] = 1e3 * dt / N2
+os.environ["PHYLOMAP_B200_SMALL"] = "0"
+dt, _ = gpu(pb.sumstatMCMC_bigtree, zs, Q, cases.PID2, 10.0, N2, seed=5, precision="f64")
+out["squamate_gpu_f64_wide_ms_per_sweep"] = 1e3 * dt / N2
+del os.environ["PHYLOMAP_B200_SMALL"]
 out["squamate_cpu_port_faithful_ms_per_sweep"] = 1e3 * cpu(bridge.BIGTREE, zs, Q, cases.PID2, 10.0, 4, False) / 4
 out["squamate_cpu_port_optimised_ms_per_sweep"] = 1e3 * cpu(bridge.BIGTREE, zs, Q, cases.PID2, 10.0, 4, True) / 4
 print(json.dumps(out))

@@ -469,6 +469,8 @@ def test_rows_do_not_depend_on_the_memory_layout(what, monkeypatch):
         mk = lambda: pb.Chain(capi.PM_V_KSMT, trees, np.asfortranarray(Q.copy()), np.full(4, 0.25), 4.0, N,
                               prior=cases.PRIOR_KSMT, precision="f64", seed=11)
 
+    monkeypatch.setenv("PHYLOMAP_B200_SMALL", "0")   # the layouts of the 32-sites-per-warp kernels (test_gpu_small.py covers the other)
+
     def run(fused, pool):
         monkeypatch.setenv("PHYLOMAP_B200_FUSED", str(fused))
         monkeypatch.setenv("PHYLOMAP_B200_REC_POOL", str(pool))
@@ -513,6 +515,8 @@ def test_graph_replay_gives_the_rows_of_plain_launches(what, monkeypatch):
         Q = cases.jc(5, 0.1)
         z = cases.tree_n(Q, T=40, S=9, seed=3, mean_branch=1.0, segments=2)
         mk = lambda: pb.Chain(capi.PM_V_SPARSE, z, Q.copy(), np.full(5, 0.2), 1.0, 64, precision="f32", seed=7)
+
+    monkeypatch.setenv("PHYLOMAP_B200_SMALL", "0")   # (the one-block-per-site kernel has no per-sweep launches to replay)
 
     def run(graph):
         monkeypatch.setenv("PHYLOMAP_B200_GRAPH", str(graph))
