@@ -15,6 +15,8 @@ reduction) over all local sites = E x S_local branch-site histories.  Production
 `rate_sampler`: sumstatMCMCks (hidden-rate model, Q updated every sweep) on the same tree and sites: ms per sweep, and
             per sweep the device time of the one small NCCL all-reduce and the host time of the replicated rate update --
             the part of the design that has a collective in it (the fixed-Q headline all-reduces once per run).
+`one_character`: BASELINE configs[0] (one binary trait, 100 tips, 1 000 sweeps: the reference's literal usage) -- microseconds
+            per sweep on the GPU (whole call / resident chain) beside the reference's code and the optimised port on one core.
 `cpu_baseline` / `--impl reference`: the reference's own code -- oracle/_ref = the unmodified src/phylomap.cpp compiled
             against stand-in Rcpp / Armadillo headers (R is absent) -- on a bounded site sample, one process per host
             core; beside it the in-repo port in "faithful" mode (keeps the reference's O(E) edge search per node, :643) and in
@@ -193,6 +195,45 @@ def cpu_baseline(tree, Q, pid, steps=6):
         leg, _ = cpu_leg(k, tree, Q, pid, steps, order)
         main[k] = {"value": leg["value"], "sample": leg["sample"]}
     return main
+
+
+def one_character(opts):
+    """BASELINE configs[0], the reference's literal usage: ONE binary character on a 100-tip tree, sumstatMCMC, 1 000 sweeps
+    (tutorial sec. 2).  GPU: the whole drop-in call with host buffers (chain built, sweeps, result matrix back) and the
+    sweeps alone on a chain that already exists -- at this size the library runs a block per site with the site's state in
+    shared memory and every sweep of the call inside one launch (pm_small.cuh).  CPU, one core: the reference's own code
+    (oracle/_ref) and the in-repo port with a parent-edge table."""
+    import torch
+    import phylomap_b200 as pb
+    from phylomap_b200 import capi, synth
+    from oracle import bridge
+    Q2, pid2, Om, N = np.array([[-0.1, 0.1], [0.1, -0.1]]), np.array([0.5, 0.5]), 0.2, 1000
+    z = synth.simulate_2_state_tree(101, synth.yule_tree(100, seed=1, mean_branch=5.0), Q2, pid2)
+    kw = {k: v for k, v in opts.items() if k in ("precision", "device")}
+
+    def best(fn, reps=3):
+        fn()
+        b = 1e30
+        for _ in range(reps):
+            torch.cuda.synchronize(); t = time.perf_counter(); fn(); torch.cuda.synchronize()
+            b = min(b, time.perf_counter() - t)
+        return b
+    call = best(lambda: pb.sumstatMCMC(z, Q2, pid2, Om, N, seed=5, **kw))
+    ch = pb.Chain(capi.PM_V_PLAIN, z, Q2, pid2, Om, 5 * N, seed=5, **kw)
+    res = best(lambda: ch.run(N))
+    _, launches = ch.kernel_times()
+    ch.close()
+    out = {"workload": "BASELINE configs[0]: sumstatMCMC, 100-tip tree, one binary character, Omega = 0.2, 1 000 sweeps",
+           "gpu_us_per_sweep_whole_call": 1e6 * call / N, "gpu_us_per_sweep_resident_chain": 1e6 * res / N,
+           "gpu_launches_per_call": int(launches // 5), "cpu_cores": 1}
+    run = bridge.OracleRun(bridge.PLAIN, [z.oracle_dict()], Q2, pid2, Om, N, rng_mode=bridge.SEQUENTIAL, seed=3)
+    run.set_fast_lookup(True)
+    t = time.perf_counter(); run.run()
+    out["cpu_port_optimised_us_per_sweep"] = 1e6 * (time.perf_counter() - t) / N
+    if bridge.ref_lib() is not None:
+        t = time.perf_counter(); bridge.ref_run(bridge.PLAIN, [z.oracle_dict()], Q2, pid2, Om, N, seed=3)
+        out["cpu_reference_us_per_sweep"] = 1e6 * (time.perf_counter() - t) / N
+    return out
 
 
 def run_reference(a, rank, world):
@@ -399,9 +440,10 @@ def run_ours(a, rank, local_rank, world):
         ch.close()
         del ch
 
-    cb = None
+    cb = one = None
     if rank == 0 and world == 1 and not a.no_cpu:
         cb = cpu_baseline(tree, Q, pid)
+        one = one_character(opts)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -409,7 +451,7 @@ def run_ours(a, rank, local_rank, world):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config(world, S), "clocks": clk.summary(), "e2e": e2e,
-                "gpu_launches": int(launches - launches0), "roofline": roof, "cpu_baseline": cb, "rate_sampler": rate,
+                "gpu_launches": int(launches - launches0), "roofline": roof, "cpu_baseline": cb, "rate_sampler": rate, "one_character": one,
                 "device_bytes": dev_bytes, "device_bytes_per_branch_site": dev_bytes / (E * S)}
         print(json.dumps(line))
 

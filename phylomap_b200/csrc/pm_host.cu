@@ -305,6 +305,7 @@ struct TreeDev {
   // few sites on a tree whose per-site state fits shared memory (pm_small.cuh): a block per site runs the whole sweep, and
   // for the fixed-Q samplers all the sweeps of a call, in one launch
   bool small_ok = false;
+  bool small_two = false;    // more sites than SMs: two blocks per SM (128 registers) instead of one
   int small_chunks = 0;      // record chunks (rows of rec_cursor)
   DevBuf small_down, small_part, small_cnt, small_root;
   int small_cap = 0;         // sweeps the output buffers hold
@@ -484,8 +485,8 @@ struct ChainT : pm_chain {
       o.part = t.small_part.template as<double>(); o.cnt = t.small_cnt.template as<unsigned long long>(); o.root = t.small_root.template as<int>();
       o.down = reinterpret_cast<const int4*>(t.small_down.p); o.down_off = t.down_off.template as<int>();
       o.n_down_levels = (int)t.sch.down_off.size() - 1; o.n_chunks = t.small_chunks;
-      if (NS == 2) pm::Sweep<Real, 2, false>::small_chain(t.P, (int)S, stream, iter0 + (uint32_t)b0, nb, o);
-      else pm::Sweep<Real, 4, false>::small_chain(t.P, (int)S, stream, iter0 + (uint32_t)b0, nb, o);
+      if (NS == 2) pm::Sweep<Real, 2, false>::small_chain(t.P, (int)S, stream, iter0 + (uint32_t)b0, nb, o, t.small_two);
+      else pm::Sweep<Real, 4, false>::small_chain(t.P, (int)S, stream, iter0 + (uint32_t)b0, nb, o, t.small_two);
       pm::k_small_reduce<<<nb, 128, 0, stream>>>(o.part, o.cnt, o.root, S, n, rows_d + (size_t)b0 * WR, WR, err_flag.as<unsigned>(), W);
       launches += 2;
     }
@@ -713,8 +714,23 @@ struct ChainT : pm_chain {
         if (const char* v = getenv("PHYLOMAP_B200_SMALL_SITES")) small_sites = atoll(v);
         const bool off = getenv("PHYLOMAP_B200_SMALL") && getenv("PHYLOMAP_B200_SMALL")[0] == '0';
         const size_t need = NS == 2 ? pm::Sweep<Real, 2, false>::small_smem(T) : NS == 4 ? pm::Sweep<Real, 4, false>::small_smem(T) : (size_t)-1;
+        // ... and the paths of one site are short: a block walks its site's branches with 256 threads, one branch per thread
+        // at a time, while the wide kernels spread the branch-sites of a long-path problem (the Squamate vignette: 877 000
+        // jump points per site and sweep) over the whole device.  What costs is the general item routine: hard = the sum
+        // over the branches of P(two or more jump points) x (2 + expected jump points), jump points ~ Poisson(Omega t).
+        // Measured (scripts/small_calib.py, us per sweep, one character): this kernel ~ 20 + 0.05 hard + 0.03 T, the wide
+        // ones ~ 65 + 0.13 T: it pays up to hard ~ 1500 + 0.7 T.  PHYLOMAP_B200_SMALL_WORK scales that limit.
+        double hard = 0;
+        for (int e = 0; e < E; e++) {
+          const double lam = Omega * (double)elen[e];
+          hard += (1.0 - std::exp(-lam) * (1.0 + lam)) * (2.0 + lam);
+        }
+        double small_work = 1.0;
+        if (const char* v = getenv("PHYLOMAP_B200_SMALL_WORK")) small_work = atof(v);
+        const double work = hard, work_limit = small_work * (1500.0 + 0.7 * T);
+        t->small_two = S > prop.multiProcessorCount;
         t->small_ok = !off && !exact && (NS == 2 || NS == 4) && !V.exp && !V.llonly && opt.rng != PM_RNG_TABLE && S <= small_sites &&
-                      need <= (size_t)200 * 1024;
+                      need <= (size_t)200 * 1024 && work <= work_limit;
       }
       const bool pooled_ok = !t->small_ok && !exact && !V.exp && !V.llonly && !(getenv("PHYLOMAP_B200_REC_POOL") && getenv("PHYLOMAP_B200_REC_POOL")[0] == '0');
       const long long ny_first = ny;

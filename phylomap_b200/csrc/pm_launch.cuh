@@ -21,7 +21,8 @@ struct Sweep {
   // production, n = 2 / 4, few sites on a tree whose per-site state fits shared memory: `nsweeps` sweeps of every site in
   // ONE launch, a block per site (pm_small.cuh).  small_smem: the dynamic shared memory it needs for T tips.
   static size_t small_smem(int T);
-  static void small_chain(const ChainParams<Real>& P, int sites, cudaStream_t st, uint32_t iter0, int nsweeps, const SmallOut& out);
+  static void small_chain(const ChainParams<Real>& P, int sites, cudaStream_t st, uint32_t iter0, int nsweeps, const SmallOut& out,
+                          bool two_per_sm);
 };
 
 }  // namespace pm

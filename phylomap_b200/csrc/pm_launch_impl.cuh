@@ -90,10 +90,11 @@ size_t Sweep<Real, NS, EXACT>::small_smem(int T) {
 }
 template <typename Real, int NS, bool EXACT>
 void Sweep<Real, NS, EXACT>::small_chain(const ChainParams<Real>& P, int sites, cudaStream_t st, uint32_t iter0, int nsweeps,
-                                         const SmallOut& out) {
+                                         const SmallOut& out, bool two_per_sm) {
   if constexpr (!EXACT && (NS == 2 || NS == 4)) {
-    auto kern = k_small_chain<Real, NS>;
     const size_t sm = (size_t)SmallSmem<Real, NS>(P.T).total;
+    const bool two = (P.tune & 8) ? false : (P.tune & 16) ? true : two_per_sm;  // (PHYLOMAP_B200_TUNE 8 / 16 force either)
+    auto kern = two ? k_small_chain<Real, NS, 2> : k_small_chain<Real, NS, 1>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     kern<<<sites, 256, sm, st>>>(P, iter0, nsweeps, out);
   }

@@ -47,8 +47,10 @@ struct SmallSmem {
   }
 };
 
-template <typename Real, int NS>
-__global__ void __launch_bounds__(256) k_small_chain(ChainParams<Real> P, uint32_t iter0, int nsweeps, SmallOut out) {
+// MINB = 1: all the registers the item routine wants (one site: latency); MINB = 2: 128 registers, two blocks per SM (more
+// sites than SMs: throughput)
+template <typename Real, int NS, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_small_chain(ChainParams<Real> P, uint32_t iter0, int nsweeps, SmallOut out) {
   typedef Pin<Real> PN;
   constexpr int n = NS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
