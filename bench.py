@@ -225,7 +225,7 @@ def one_character(opts):
     ch.close()
     out = {"workload": "BASELINE configs[0]: sumstatMCMC, 100-tip tree, one binary character, Omega = 0.2, 1 000 sweeps",
            "gpu_us_per_sweep_whole_call": 1e6 * call / N, "gpu_us_per_sweep_resident_chain": 1e6 * res / N,
-           "gpu_launches_per_call": int(launches // 5), "cpu_cores": 1}
+           "gpu_launches_per_call": int(launches // 4), "cpu_cores": 1}
     run = bridge.OracleRun(bridge.PLAIN, [z.oracle_dict()], Q2, pid2, Om, N, rng_mode=bridge.SEQUENTIAL, seed=3)
     run.set_fast_lookup(True)
     t = time.perf_counter(); run.run()
