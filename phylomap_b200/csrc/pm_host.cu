@@ -334,13 +334,14 @@ struct ChainT : pm_chain {
   bool own_stream = false;
   std::vector<std::unique_ptr<TreeDev<Real>>> trees;
   int jcap = 0;
-  DevBuf model, ppow, cnt, root_out, err_flag, rows, tab_off, tab_u, q_dev;
+  DevBuf model, cnt, root_out, err_flag, rows, tab_off, tab_u, q_dev;
   double* q_h = nullptr;  // pinned: Q row-major, for the DIC log-likelihood
   std::vector<double> own_B;                    // EXP: B = I + Q / Omega is internal (the entry takes no B)
   std::vector<double> eig_L, eig_R, eig_d;      // EXP: row-major eigenvectors, inverse, eigenvalues
   DevBuf eig_dev;
   Real* model_h = nullptr;   // pinned staging: model then ppow
   double* rows_h = nullptr;  // pinned: ntrees * W
+  double* rows_h_dev = nullptr;  // the same buffer as the device sees it (mapped pinned memory)
   unsigned* err_h = nullptr;
   std::vector<double> scale_prev, rate_prev;
   pm::host::MersenneR mt{0};
@@ -378,6 +379,8 @@ struct ChainT : pm_chain {
   pm::host::UniformSource& host_rng() { return replay ? static_cast<pm::host::UniformSource&>(*replay) : mt; }
 
   size_t model_elems() const { return (size_t)2 * n * n + 5 * n; }
+  // the table of powers follows the model in ONE device buffer (one upload per sweep of a rate-updating sampler), 16-byte aligned
+  size_t model_stride() const { return (model_elems() + 3) & ~(size_t)3; }
 
   // ---- model upload: B, thresholded B, pid, scales, table of powers ----
   void stage_model(bool first) {
@@ -403,7 +406,7 @@ struct ChainT : pm_chain {
     scale_prev = scale_new; rate_prev = rate_new;
     // P_0 = I, P_j = Bs P_{j-1}: left-to-right dot products in double (column c of P_j is the reference's
     // backward vector B^j e_c bit for bit, src/phylomap.cpp:283-287)
-    Real* pw = m + model_elems();
+    Real* pw = m + model_stride();
     std::vector<double> cur((size_t)n * n, 0.0), nxt((size_t)n * n);
     for (int i = 0; i < n; i++) cur[(size_t)i * n + i] = 1.0;
     for (int j = 0; j < jcap; j++) {
@@ -418,8 +421,7 @@ struct ChainT : pm_chain {
         cur.swap(nxt);
       }
     }
-    CK(cudaMemcpyAsync(model.p, m, model_elems() * sizeof(Real), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(ppow.p, pw, (size_t)jcap * n * n * sizeof(Real), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(model.p, m, (model_stride() + (size_t)jcap * n * n) * sizeof(Real), cudaMemcpyHostToDevice, stream));
   }
 
   // ---- kernel dispatch ----
@@ -428,7 +430,7 @@ struct ChainT : pm_chain {
 
   template <int NSc, bool EX>
   void launch_sweep_t(TreeDev<Real>& t, uint32_t iter, double* row) {
-    if (!EX && use_small(t)) { launch_small(t, iter, 1, row); launches_per_sweep = 2; return; }
+    if (!EX && use_small(t)) { launch_small(t, iter, 1, row); launches_per_sweep = t.S == 1 ? 1 : 2; return; }
     const uint32_t* ctl_d = capturing ? ctl.as<uint32_t>() : nullptr;
     {
       pm::ChainParams<Real> P = t.P;
@@ -470,23 +472,33 @@ struct ChainT : pm_chain {
   bool use_small(const TreeDev<Real>& t) const { return t.small_ok && !timing && !debug_sync && !capturing; }
   void launch_small(TreeDev<Real>& t, uint32_t iter0, int nsweeps, double* rows_d) {
     const long long S = t.S;
+    pm::SmallOut o;
+    o.down = reinterpret_cast<const int4*>(t.small_down.p); o.down_off = t.down_off.template as<int>();
+    o.n_down_levels = (int)t.sch.down_off.size() - 1; o.n_chunks = t.small_chunks;
+    o.part = nullptr; o.cnt = nullptr; o.root = nullptr; o.rows = nullptr; o.row_stride = WR; o.err_slot = W;
+    auto launch = [&](uint32_t it0, int nb) {
+      if (NS == 2) pm::Sweep<Real, 2, false>::small_chain(t.P, (int)S, stream, it0, nb, o, t.small_two);
+      else pm::Sweep<Real, 4, false>::small_chain(t.P, (int)S, stream, it0, nb, o, t.small_two);
+    };
+    if (S == 1) {  // the one block writes the rows itself: one launch, whatever the number of sweeps
+      o.rows = rows_d;
+      launch(iter0, nsweeps);
+      launches += 1;
+      return;
+    }
     const int batch = (int)std::max<long long>(1, std::min<long long>(nsweeps, (64LL << 20) / (S * n * (long long)sizeof(double))));
     if (t.small_cap < batch) {
       t.small_part.alloc((size_t)batch * S * n * sizeof(double));
       t.small_cnt.alloc((size_t)batch * n * n * sizeof(unsigned long long));
       t.small_root.alloc((size_t)batch * sizeof(int));
       t.small_cap = batch;
+      CK(cudaMemsetAsync(t.small_cnt.p, 0, t.small_cnt.bytes, stream));   // (k_small_reduce hands them back zeroed)
+      CK(cudaMemsetAsync(t.small_root.p, 0, t.small_root.bytes, stream));
     }
+    o.part = t.small_part.template as<double>(); o.cnt = t.small_cnt.template as<unsigned long long>(); o.root = t.small_root.template as<int>();
     for (int b0 = 0; b0 < nsweeps; b0 += batch) {
       const int nb = std::min(batch, nsweeps - b0);
-      CK(cudaMemsetAsync(t.small_cnt.p, 0, (size_t)nb * n * n * sizeof(unsigned long long), stream));
-      CK(cudaMemsetAsync(t.small_root.p, 0, (size_t)nb * sizeof(int), stream));
-      pm::SmallOut o;
-      o.part = t.small_part.template as<double>(); o.cnt = t.small_cnt.template as<unsigned long long>(); o.root = t.small_root.template as<int>();
-      o.down = reinterpret_cast<const int4*>(t.small_down.p); o.down_off = t.down_off.template as<int>();
-      o.n_down_levels = (int)t.sch.down_off.size() - 1; o.n_chunks = t.small_chunks;
-      if (NS == 2) pm::Sweep<Real, 2, false>::small_chain(t.P, (int)S, stream, iter0 + (uint32_t)b0, nb, o, t.small_two);
-      else pm::Sweep<Real, 4, false>::small_chain(t.P, (int)S, stream, iter0 + (uint32_t)b0, nb, o, t.small_two);
+      launch(iter0 + (uint32_t)b0, nb);
       pm::k_small_reduce<<<nb, 128, 0, stream>>>(o.part, o.cnt, o.root, S, n, rows_d + (size_t)b0 * WR, WR, err_flag.as<unsigned>(), W);
       launches += 2;
     }
@@ -986,10 +998,11 @@ struct ChainT : pm_chain {
       jcap = (int)std::min(16384.0, std::max(64.0, want));
     }
     if (jcap < 2) jcap = 2;
-    model.alloc(model_elems() * sizeof(Real));
-    ppow.alloc((size_t)jcap * n * n * sizeof(Real));
-    CK(cudaMallocHost((void**)&model_h, (model_elems() + (size_t)jcap * n * n) * sizeof(Real)));
+    model.alloc((model_stride() + (size_t)jcap * n * n) * sizeof(Real));
+    CK(cudaMallocHost((void**)&model_h, (model_stride() + (size_t)jcap * n * n) * sizeof(Real)));
+    memset(model_h, 0, (model_stride() + (size_t)jcap * n * n) * sizeof(Real));
     CK(cudaMallocHost((void**)&rows_h, (size_t)ntrees * WR * sizeof(double)));
+    if (cudaHostGetDevicePointer((void**)&rows_h_dev, rows_h, 0) != cudaSuccess) { rows_h_dev = nullptr; (void)cudaGetLastError(); }
     if (opt.nccl_world > 1) nccl = clique(opt.nccl_id, opt.nccl_world, opt.nccl_rank);
     CK(cudaMallocHost((void**)&err_h, sizeof(unsigned)));
     CK(cudaMallocHost((void**)&ctl_h, 2 * sizeof(uint32_t)));
@@ -1041,7 +1054,7 @@ struct ChainT : pm_chain {
       P.tune = getenv("PHYLOMAP_B200_TUNE") ? atoi(getenv("PHYLOMAP_B200_TUNE")) : 0;
       P.rec_cursor = t.rec_cursor.template as<int>(); P.chunk = t.chunk; P.easy_blocks = t.nblocks;
       P.shape = t.shape.template as<uint16_t>();
-      P.model = model.as<Real>(); P.ppow = ppow.as<Real>(); P.jcap = jcap;
+      P.model = model.as<Real>(); P.ppow = model.as<Real>() + model_stride(); P.jcap = jcap;
       P.up_entries = t.up_entries.template as<int>(); P.up_off = t.up_off.template as<int>();
       P.up_entries8 = t.up_entries8.template as<int>();
       P.n_up_levels = (int)t.sch.up_off.size() - 1;
@@ -1246,7 +1259,12 @@ struct ChainT : pm_chain {
     for (int i = 0; i < count; i++) {
       const int it = iters_done;
       if (V.multi && it == 0) (void)g.next();  // the draw before the loop, :2332 / :2810
-      for (int j = 0; j < ntrees; j++) launch_sweep(*trees[j], (uint32_t)it, rows.as<double>() + (size_t)j * WR);
+      // the one-block-per-site kernels of a single process write their rows straight into the pinned host buffer (mapped:
+      // no copy to wait for after the launch); otherwise rows land in device memory, where the collective finds them
+      bool host_rows = rows_h_dev != nullptr && !nccl && !opt.allreduce && !V.dic;
+      for (int j = 0; j < ntrees; j++) host_rows = host_rows && use_small(*trees[j]);
+      double* const row0 = host_rows ? rows_h_dev : rows.as<double>();
+      for (int j = 0; j < ntrees; j++) launch_sweep(*trees[j], (uint32_t)it, row0 + (size_t)j * WR);
       if (V.dic) launch_loglik(*trees[0], rows.as<double>());
       CK(cudaGetLastError());
       // one small all-reduce per sweep (n + n^2 + 1 (+1) statistics + the error slot, per tree), then ONE synchronisation:
@@ -1255,7 +1273,7 @@ struct ChainT : pm_chain {
       if (timing) { CK(cudaEventCreate(&ca)); CK(cudaEventCreate(&cb)); CK(cudaEventRecord(ca, stream)); }
       reduce_over_ranks(rows.as<double>(), ntrees * WR);
       if (timing) CK(cudaEventRecord(cb, stream));
-      CK(cudaMemcpyAsync(rows_h, rows.p, (size_t)ntrees * WR * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      if (!host_rows) CK(cudaMemcpyAsync(rows_h, rows.p, (size_t)ntrees * WR * sizeof(double), cudaMemcpyDeviceToHost, stream));
       CK(cudaStreamSynchronize(stream));
       if (timing) { float ms = 0; cudaEventElapsedTime(&ms, ca, cb); comm_ms += ms; cudaEventDestroy(ca); cudaEventDestroy(cb); }
       const auto host_t0 = std::chrono::steady_clock::now();
@@ -1381,7 +1399,7 @@ struct ChainT : pm_chain {
     return nj + 1;
   }
   // ---- checkpoint / resume: everything a sweep reads that is not an input of pm_chain_create ----
-  static constexpr uint32_t PM_STATE_FORMAT = 5;  // 5: production record slices shared by groups of 32 sites; 1: round 1 (per-site masks); 2: branch-major ballots, global record cursors; 3: two-run paths count their virtual jumps together; 4: 16-bit positions inside meta, shape words
+  static constexpr uint32_t PM_STATE_FORMAT = 6;  // 6: model and table of powers in one buffer; 5: production record slices shared by groups of 32 sites; 1: round 1 (per-site masks); 2: branch-major ballots, global record cursors; 3: two-run paths count their virtual jumps together; 4: 16-bit positions inside meta, shape words
   struct StateHeader {
     char magic[8];
     int32_t variant, n, ntrees, precision, mode, T, E, iters_done, jcap, reserved;
@@ -1389,7 +1407,7 @@ struct ChainT : pm_chain {
     uint64_t seed;
   };
   std::vector<DevBuf*> state_buffers() {
-    std::vector<DevBuf*> v{&model, &ppow};
+    std::vector<DevBuf*> v{&model};
     for (auto& t : trees) {
       v.push_back(&t->node_state); v.push_back(&t->meta); v.push_back(&t->shape);
       for (int b = 0; b < 2; b++) { v.push_back(&t->rec_len[b]); v.push_back(&t->rec_st[b]); }

@@ -34,9 +34,9 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ dw_pa
 
 // The rows of a k_small_chain launch (pm_small.cuh): block i sums the per-site dwell times of sweep i in a fixed order and
 // assembles row i in k_reduce's layout [R(n) | N(n*n) | root | .. | error flag].
-__global__ void __launch_bounds__(128) k_small_reduce(const double* __restrict__ part, const unsigned long long* __restrict__ cnt,
-                                                      const int* __restrict__ root, long long S, int n, double* rows, int row_stride,
-                                                      const unsigned* err_flag, int err_slot) {
+// (the counters and the root slot are handed back zeroed, like k_reduce does: the next launch adds to them atomically)
+__global__ void __launch_bounds__(128) k_small_reduce(const double* __restrict__ part, unsigned long long* cnt, int* root, long long S,
+                                                      int n, double* rows, int row_stride, const unsigned* err_flag, int err_slot) {
   __shared__ double sh[128];
   const long long i = blockIdx.x;
   double* row = rows + (size_t)i * row_stride;
@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(128) k_small_reduce(const double* __restrict__
     if (threadIdx.x == 0) row[j] = sh[0];
     __syncthreads();
   }
-  for (int k = threadIdx.x; k < n * n; k += 128) row[n + k] = (double)cnt[i * n * n + k];
-  if (threadIdx.x == 0) { row[n + n * n] = (double)root[i]; row[err_slot] = (double)(*err_flag); }
+  for (int k = threadIdx.x; k < n * n; k += 128) { row[n + k] = (double)cnt[i * n * n + k]; cnt[i * n * n + k] = 0ull; }
+  if (threadIdx.x == 0) { row[n + n * n] = (double)root[i]; root[i] = 0; row[err_slot] = (double)(*err_flag); }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -25,6 +25,9 @@ struct SmallOut {
   const int4* down;          // top-down draw list: v, parent, edge, key -- grouped by depth (down_off), tips last at their depth
   const int* down_off; int n_down_levels;
   int n_chunks;              // record chunks (rec_cursor rows)
+  // ONE site: the block writes the rows itself, in k_reduce's layout [R(n) | N(n*n) | root | .. | error flag] (device
+  // memory or mapped host memory: a rate-updating sampler reads the row right after the launch); nullptr: part / cnt / root
+  double* rows; int row_stride, err_slot;
 };
 
 // shared-memory layout (bytes, every section 16-byte aligned)
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(256, MINB) k_small_chain(ChainParams<Real> P, 
       philox4x32_10_rk(0xffffffffu, kslot, iter, gsite, P.rng.rk, o);
       const int s = categorical<Real, NS, false>(w, NS, u01_from_word<Real>(o[0]), P.err_flag);
       sState[P.root] = (uint8_t)s;
-      if (gsite == 0u) out.root[sw] = s;
+      if (gsite == 0u && !out.rows) out.root[sw] = s;
     }
     __syncthreads();
     for (int l = 0; l < out.n_down_levels; l++) {
@@ -231,12 +234,26 @@ __global__ void __launch_bounds__(256, MINB) k_small_chain(ChainParams<Real> P, 
       if (lane == 0) s_dw[warp * n + j] = v;
     }
     __syncthreads();
-    if (tid < n) {
-      double v = 0;
-      for (int w = 0; w < (nthr >> 5); w++) v += s_dw[w * n + tid];
-      out.part[((long long)sw * S + site) * n + tid] = v;
+    if (out.rows) {  // one site: the row of this sweep is complete here
+      double* const row = out.rows + (size_t)sw * out.row_stride;
+      if (tid < n) {
+        double v = 0;
+        for (int w = 0; w < (nthr >> 5); w++) v += s_dw[w * n + tid];
+        row[tid] = v;
+      }
+      for (int i = tid; i < n * n; i += nthr) row[n + i] = (double)s_cnt[i];
+      if (tid == 0) {
+        row[n + n * n] = gsite == 0u ? (double)sState[P.root] : 0.0;
+        row[out.err_slot] = (double)atomicOr(P.err_flag, 0u);  // (every thread's flags were raised before the barrier above)
+      }
+    } else {
+      if (tid < n) {
+        double v = 0;
+        for (int w = 0; w < (nthr >> 5); w++) v += s_dw[w * n + tid];
+        out.part[((long long)sw * S + site) * n + tid] = v;
+      }
+      for (int i = tid; i < n * n; i += nthr) if (s_cnt[i]) atomicAdd(&out.cnt[(long long)sw * n * n + i], (unsigned long long)s_cnt[i]);
     }
-    for (int i = tid; i < n * n; i += nthr) if (s_cnt[i]) atomicAdd(&out.cnt[(long long)sw * n * n + i], (unsigned long long)s_cnt[i]);
     __syncthreads();
   }
 

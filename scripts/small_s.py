@@ -60,6 +60,28 @@ out["cfg0_cpu_port_faithful_us_per_sweep"] = 1e6 * cpu(bridge.PLAIN, z, cases.Q2
 out["cfg0_cpu_port_optimised_us_per_sweep"] = 1e6 * cpu(bridge.PLAIN, z, cases.Q2, cases.PID2, 0.2, N, True) / N
 t = time.perf_counter(); bridge.ref_run(bridge.PLAIN, [z.oracle_dict()], cases.Q2, cases.PID2, 0.2, N, seed=3)
 out["cfg0_cpu_reference_us_per_sweep"] = 1e6 * (time.perf_counter() - t) / N
+# the rate-updating samplers with one character (the tutorial's usage): one launch per sweep, the host update in between
+from phylomap_b200 import capi
+zb = synth.simulate_2_state_tree(101, synth.yule_tree(100, seed=1, mean_branch=5.0), cases.Q2, cases.PID2)
+zk = cases.tree_hidden(cases.q4(), T=100, S=1, seed=4, mean_branch=1.0)
+for name, var, ovar, zz, Qm, pidm, Om, prior in (("bf", capi.PM_V_BF, bridge.BF, zb, cases.Q2, cases.PID2, 0.4, cases.PRIOR_BF),
+                                                  ("ks", capi.PM_V_KS, bridge.KS, zk, cases.q4(), np.full(4, 0.25), 4.0, cases.PRIOR_KS)):
+    for small in ("1", "0"):
+        os.environ["PHYLOMAP_B200_SMALL"] = small
+        ch = pb.Chain(var, zz, np.asfortranarray(Qm.copy()), pidm, Om, 4 * N, prior=prior, precision="f32", seed=5)
+        ch.run(N)
+        b = 1e30
+        for _ in range(3):
+            torch.cuda.synchronize(); t = time.perf_counter(); ch.run(N); torch.cuda.synchronize()
+            b = min(b, time.perf_counter() - t)
+        ch.close()
+        out["%s_gpu_f32_%s_us_per_sweep_resident" % (name, "one_block_per_site" if small == "1" else "wide")] = 1e6 * b / N
+    del os.environ["PHYLOMAP_B200_SMALL"]
+    o = bridge.OracleRun(ovar, [zz.oracle_dict()], np.asfortranarray(Qm.copy()), pidm, Om, N, prior=prior, rng_mode=bridge.SEQUENTIAL, seed=3)
+    o.set_fast_lookup(True)
+    t = time.perf_counter(); o.run(); out["%s_cpu_port_optimised_us_per_sweep" % name] = 1e6 * (time.perf_counter() - t) / N
+    t = time.perf_counter(); bridge.ref_run(ovar, [zz.oracle_dict()], np.asfortranarray(Qm.copy()), pidm, Om, N, prior=prior, seed=3)
+    out["%s_cpu_reference_us_per_sweep" % name] = 1e6 * (time.perf_counter() - t) / N
 # the Squamate vignette: 3 951 tips x 100 segments, Omega = 10, one character
 Q = np.array([[-0.001, 0.001], [0.006, -0.006]])
 zs = synth.simulate_2_state_tree(101, cases.squamate_tree(), Q, cases.PID2)
