@@ -307,7 +307,8 @@ struct TreeDev {
   bool small_ok = false;
   bool small_two = false;    // more sites than SMs: two blocks per SM (128 registers) instead of one
   int small_chunks = 0;      // record chunks (rows of rec_cursor)
-  DevBuf small_down, small_part, small_cnt, small_root;
+  DevBuf small_down, small_part, small_cnt, small_root, small_prof;
+  DevBuf tip_stage;          // staging of the tip-state upload (create() only)
   int small_cap = 0;         // sweeps the output buffers hold
   long long rec_groups = 0;
   DevBuf e_len_d, TP, ll_partial;  // DIC samplers: branch lengths in FP64, exp(Q t_e) per branch, block partials of log p(y|Q)
@@ -372,6 +373,12 @@ struct ChainT : pm_chain {
     if (err_h) cudaFreeHost(err_h);
     if (q_h) cudaFreeHost(q_h);
     if (ctl_h) cudaFreeHost(ctl_h);
+    for (auto& t : trees) if (t && t->small_prof.p) {
+      long long h[12];
+      if (cudaMemcpy(h, t->small_prof.p, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess)
+        fprintf(stderr, "[phylomap_b200] k_small_chain block 0 (%d + %d levels), cycles over %d sweeps: prune %lld, node draws %lld, paths %lld, row %lld; paths per warp:"
+                        " %lld %lld %lld %lld %lld %lld %lld %lld\n", (int)t->sch.up_off.size() - 1, (int)t->sch.down_off.size() - 1, iters_done, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11]);
+    }
     if (sweep_graph) cudaGraphExecDestroy(sweep_graph);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
@@ -476,6 +483,11 @@ struct ChainT : pm_chain {
     o.down = reinterpret_cast<const int4*>(t.small_down.p); o.down_off = t.down_off.template as<int>();
     o.n_down_levels = (int)t.sch.down_off.size() - 1; o.n_chunks = t.small_chunks;
     o.part = nullptr; o.cnt = nullptr; o.root = nullptr; o.rows = nullptr; o.row_stride = WR; o.err_slot = W;
+    o.prof = nullptr;
+    if (getenv("PHYLOMAP_B200_SMALL_PROF")) {
+      if (!t.small_prof.p) { t.small_prof.alloc(12 * sizeof(long long)); CK(cudaMemsetAsync(t.small_prof.p, 0, t.small_prof.bytes, stream)); }
+      o.prof = t.small_prof.template as<long long>();
+    }
     auto launch = [&](uint32_t it0, int nb) {
       if (NS == 2) pm::Sweep<Real, 2, false>::small_chain(t.P, (int)S, stream, it0, nb, o, t.small_two);
       else pm::Sweep<Real, 4, false>::small_chain(t.P, (int)S, stream, it0, nb, o, t.small_two);
@@ -684,6 +696,21 @@ struct ChainT : pm_chain {
     else { CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
 
     mark_dev();
+    err_flag.alloc(sizeof(unsigned));
+    CK(cudaMemsetAsync(err_flag.p, 0, err_flag.bytes, stream));
+    // a second stream for the upload of the tip states (the largest transfer of create()): everything else -- schedule
+    // uploads, the set-up kernels -- goes on `stream` meanwhile; the two are joined before create() returns
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    struct AuxGuard {
+      cudaStream_t& s; cudaEvent_t& a; cudaEvent_t& b;
+      ~AuxGuard() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } aux_guard{aux, ev_a, ev_b};
+    CK(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev_a, stream));   // (the error flag is zeroed on `stream`)
+    CK(cudaStreamWaitEvent(aux, ev_a, 0));
     const int T0 = tr[0].n_tips, E0 = tr[0].n_edges;
     double tmax = 0, qmax = 0;
     for (int s = 0; s < n; s++) qmax = std::max(qmax, -Q[s + (size_t)s * n]);
@@ -695,6 +722,32 @@ struct ChainT : pm_chain {
       t->S = x.n_sites;
       t->TS = (t->S + 15) / 16 * 16;  // tip-code rows are padded: every row starts 16-byte aligned whatever S is
       const int E = x.n_edges, T = x.n_tips;
+      // The tip states start their way over PCIe FIRST: [S][T] rows staged in blocks and transposed to [T][S] on the
+      // device, all asynchronous on the second stream, so that the host work below (record capacities, schedules) and the set-up kernels run
+      // while they travel.  (The staging buffer is kept until the end of create(): the pool must not hand it out again.)
+      {
+        t->tipcode.alloc((size_t)T * t->TS);
+        CK(cudaMemsetAsync(t->tipcode.p, 0, t->tipcode.bytes, aux));
+        t->node_state.alloc((size_t)(2 * T - 1) * t->S);
+        CK(cudaMemsetAsync(t->node_state.p, 0, t->node_state.bytes, aux));
+        const size_t esz = x.states_u8 ? 1 : 4;
+        long long rows_per = std::max<long long>(32, (256LL << 20) / ((long long)T * (long long)esz));
+        rows_per = std::min<long long>(rows_per, std::min<long long>(t->S, 32LL * 65535));
+        t->tip_stage.alloc((size_t)rows_per * T * esz);
+        for (long long s0 = 0; s0 < t->S; s0 += rows_per) {
+          const int ns = (int)std::min<long long>(rows_per, t->S - s0);
+          const void* src = x.states_u8 ? (const void*)(x.states_u8 + s0 * T) : (const void*)(x.states + s0 * T);
+          CK(cudaMemcpyAsync(t->tip_stage.p, src, (size_t)ns * T * esz, cudaMemcpyHostToDevice, aux));
+          dim3 g((T + 31) / 32, (ns + 31) / 32), b(32, 8);
+          if (x.states_u8)
+            pm::k_init_tips<uint8_t><<<g, b, 0, aux>>>(t->tip_stage.template as<uint8_t>(), ns, s0, t->S, t->TS, T, n, V.parity_tips,
+                                                          t->tipcode.template as<uint8_t>(), t->node_state.template as<uint8_t>(), err_flag.as<unsigned>());
+          else
+            pm::k_init_tips<int32_t><<<g, b, 0, aux>>>(t->tip_stage.template as<int32_t>(), ns, s0, t->S, t->TS, T, n, V.parity_tips,
+                                                          t->tipcode.template as<uint8_t>(), t->node_state.template as<uint8_t>(), err_flag.as<unsigned>());
+        }
+        CK(cudaGetLastError());
+      }
       std::vector<long long> moff(E + 1);
       std::vector<Real> elen(E);
       for (int e = 0; e <= E; e++) moff[e] = x.maps_off[e];
@@ -709,6 +762,7 @@ struct ChainT : pm_chain {
       // launch geometry of the path kernel: a thread owns one site x one chunk of consecutive branches
       const long long gx = (S + 127) / 128;
       long long ny = (148LL * 16 * 6 + gx - 1) / gx;
+      if (const char* v = getenv("PHYLOMAP_B200_PATH_CHUNKS")) ny = std::max(1, atoi(v));  // (experiments: wave quantisation of the streaming path kernel)
       ny = std::max(1LL, std::min<long long>(ny, (E + 15) / 16));
       ny = std::min<long long>(ny, 65535);
       ny = std::max<long long>(ny, (E + 2047) / 2048);  // the easy path kernel stages a chunk's topology in shared memory
@@ -936,16 +990,12 @@ struct ChainT : pm_chain {
       upload(t->maps_off, moff, stream);
       upload(t->maps_len, mlen, stream);
       upload(t->cap_off, t->cap_off_h, stream);
-      t->tipcode.alloc((size_t)T * t->TS);
-      CK(cudaMemsetAsync(t->tipcode.p, 0, t->tipcode.bytes, stream));
-      t->node_state.alloc((size_t)(2 * T - 1) * S);
       if (!V.exp && !V.llonly) t->meta.alloc((size_t)E * S * sizeof(uint32_t));
       t->PL.alloc((size_t)(T - 1) * t->pl_sites * n * sizeof(Real));
       for (int b = 0; b < 2 && !V.exp && !V.llonly; b++) {
         t->rec_len[b].alloc((size_t)R * t->rec_groups * sizeof(Real));
         t->rec_st[b].alloc((size_t)R * t->rec_groups);
       }
-      CK(cudaMemsetAsync(t->node_state.p, 0, t->node_state.bytes, stream));
       if (!exact && !V.exp && !V.llonly) {
         // Branch-major ballot array and the general kernel's work items: branch e is cut into items of g_e ballot words
         // (32 g_e sites), g_e chosen so that an item holds ~96 branch-sites with two or more jump points in equilibrium
@@ -1013,10 +1063,8 @@ struct ChainT : pm_chain {
     if (V.dic) { CK(cudaMallocHost((void**)&q_h, (size_t)n * n * sizeof(double))); q_dev.alloc((size_t)n * n * sizeof(double)); }
     cnt.alloc((size_t)n * n * sizeof(unsigned long long));
     root_out.alloc(sizeof(int));
-    err_flag.alloc(sizeof(unsigned));
     CK(cudaMemsetAsync(cnt.p, 0, cnt.bytes, stream));
     CK(cudaMemsetAsync(root_out.p, 0, root_out.bytes, stream));
-    CK(cudaMemsetAsync(err_flag.p, 0, err_flag.bytes, stream));
 
     // replay table
     const int T = T0, E = E0;
@@ -1090,29 +1138,16 @@ struct ChainT : pm_chain {
       P.rng.tab_base = (int64_t)ti * t.S * N_total * spi;
       P.rng.slots_per_iter = spi; P.rng.n_nodes = 2 * T - 1;
 
-      // tip states -> [T][S], staged in blocks of site rows
-      const size_t esz = x.states_u8 ? 1 : 4;
-      long long rows_per = std::max<long long>(32, (256LL << 20) / ((long long)T * (long long)esz));
-      rows_per = std::min<long long>(rows_per, std::min<long long>(t.S, 32LL * 65535));
-      DevBuf stage;
-      stage.alloc((size_t)rows_per * T * esz);
-      for (long long s0 = 0; s0 < t.S; s0 += rows_per) {
-        const int ns = (int)std::min<long long>(rows_per, t.S - s0);
-        const void* src = x.states_u8 ? (const void*)(x.states_u8 + s0 * T) : (const void*)(x.states + s0 * T);
-        CK(cudaMemcpyAsync(stage.p, src, (size_t)ns * T * esz, cudaMemcpyHostToDevice, stream));
-        dim3 g((T + 31) / 32, (ns + 31) / 32), b(32, 8);
-        if (x.states_u8)
-          pm::k_init_tips<uint8_t><<<g, b, 0, stream>>>(stage.as<uint8_t>(), ns, s0, t.S, t.TS, T, n, V.parity_tips, t.tipcode.template as<uint8_t>(), P.node_state, P.err_flag);
-        else
-          pm::k_init_tips<int32_t><<<g, b, 0, stream>>>(stage.as<int32_t>(), ns, s0, t.S, t.TS, T, n, V.parity_tips, t.tipcode.template as<uint8_t>(), P.node_state, P.err_flag);
-        CK(cudaStreamSynchronize(stream));
-      }
-      mark("tip states: H2D + transpose");
+      // (the jump-count / shape words of every branch-site -- 15 GB of writes at the benchmark size -- do not depend on the
+      // tip states, which are still on their way on the second stream)
       if (!V.exp && !V.llonly)
         pm::k_init_meta<Real><<<dim3((unsigned)((t.S + 255) / 256), (unsigned)std::min(E, 65535)), 256, 0, stream>>>(P.maps_off, P.maps_len, t.S, E, P.meta, P.e_len,
                                                                                                                        exact ? nullptr : P.shape);
+      mark("set-up kernels issued");
       CK(cudaGetLastError());
     }
+    CK(cudaEventRecord(ev_b, aux));          // join: the tip states of every tree are in place
+    CK(cudaStreamWaitEvent(stream, ev_b, 0));
     stage_model(true);
     if (V.exp) {
       std::vector<double> eg;
@@ -1127,7 +1162,8 @@ struct ChainT : pm_chain {
       CK(cudaGetLastError());
     }
     check_device_errors();
-    mark("init kernels + sync");
+    for (auto& t : trees) t->tip_stage.alloc(0);   // (everything is on the device now)
+    mark("tip states: H2D + transpose, init kernels, sync");
   }
 
   // sum `count` doubles at device address `buf` over the ranks, in stream order (no-op for a single process)
