@@ -776,8 +776,9 @@ struct ChainT : pm_chain {
       // arithmetic, 2 / 4 states.  PHYLOMAP_B200_SMALL=0 keeps the 32-sites-per-warp kernels (same rows: the tests compare),
       // PHYLOMAP_B200_SMALL_SITES moves the site limit (default: four blocks per SM).
       {
-        long long small_sites = 4LL * prop.multiProcessorCount;
-        if (const char* v = getenv("PHYLOMAP_B200_SMALL_SITES")) small_sites = atoll(v);
+        long long small_sites = 16LL * prop.multiProcessorCount;   // (hard cap; the cost rule below decides before it)
+        const bool sites_forced = getenv("PHYLOMAP_B200_SMALL_SITES") != nullptr;
+        if (sites_forced) small_sites = atoll(getenv("PHYLOMAP_B200_SMALL_SITES"));
         const bool off = getenv("PHYLOMAP_B200_SMALL") && getenv("PHYLOMAP_B200_SMALL")[0] == '0';
         const size_t need = NS == 2 ? pm::Sweep<Real, 2, false>::small_smem(T) : NS == 4 ? pm::Sweep<Real, 4, false>::small_smem(T) : (size_t)-1;
         // ... and the paths of one site are short: a block walks its site's branches with 256 threads, one branch per thread
@@ -795,7 +796,14 @@ struct ChainT : pm_chain {
         if (const char* v = getenv("PHYLOMAP_B200_SMALL_WORK")) small_work = atof(v);
         const double work = hard, work_limit = small_work * (1500.0 + 0.7 * T);
         t->small_two = S > prop.multiProcessorCount;
-        t->small_ok = !off && !exact && (NS == 2 || NS == 4) && !V.exp && !V.llonly && opt.rng != PM_RNG_TABLE && S <= small_sites &&
+        // More sites than SMs: two blocks per SM, waves of 2 x SMs sites; measured (profiles/r2_warp_per_site_attempt.log,
+        // 100-800 tips, 296-2368 sites) a wave takes ~ 10 + 0.28 T + 0.05 hard us and the wide kernels ~ 160 + 0.09 T + 0.01 S.
+        bool sites_ok = S <= small_sites;
+        if (t->small_two && !sites_forced) {
+          const double waves = std::ceil((double)S / (2.0 * prop.multiProcessorCount));
+          sites_ok = sites_ok && waves * (10.0 + 0.28 * T + 0.05 * hard) < 160.0 + 0.09 * T + 0.01 * (double)S;
+        }
+        t->small_ok = !off && !exact && (NS == 2 || NS == 4) && !V.exp && !V.llonly && opt.rng != PM_RNG_TABLE && sites_ok &&
                       need <= (size_t)200 * 1024 && work <= work_limit;
       }
       const bool pooled_ok = !t->small_ok && !exact && !V.exp && !V.llonly && !(getenv("PHYLOMAP_B200_REC_POOL") && getenv("PHYLOMAP_B200_REC_POOL")[0] == '0');
