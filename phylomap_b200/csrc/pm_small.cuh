@@ -9,7 +9,7 @@
 // and nothing is launched, read back or synchronised per sweep.  The read-only topology comes through the L1 cache.
 //
 // Every draw takes the Philox key, and every item runs the arithmetic, of the 32-sites-per-warp kernels (the node draws
-// are keyed by the position of the node in the clade schedule: `SmallDown::key`; the paths run the same item routines,
+// are keyed by the position of the node in the clade schedule: the `key` word of `SmallOut::down`; the paths run the same item routines,
 // PathWorker), so a chain gives the same rows whichever set of kernels runs it -- tests/test_gpu_small.py compares node
 // states, piece counts and transition counts bit for bit; dwell-time sums differ in their rounding (summation order).
 #pragma once
