@@ -40,6 +40,16 @@ def _case(what):
         trees = [base, pb.PhyloTree(base.edge, base.edge_length * 1.2).with_states(base.states, segments=3)]
         return (lambda: pb.Chain(capi.PM_V_KSMT, trees, np.asfortranarray(Q.copy()), np.full(4, 0.25), 4.0, 16,
                                  prior=cases.PRIOR_KSMT, precision="f64", seed=11)), base, (16,), 4
+    if what == "bf_f64_one_character":              # one site + rate updates: the block writes its row straight into mapped host memory
+        z = cases.tree2(T=60, S=1, seed=3, mean_branch=3.0)
+        return (lambda: pb.Chain(capi.PM_V_BF, z, np.asfortranarray(cases.Q2.copy()), cases.PID2, 0.4, 40, prior=cases.PRIOR_BF,
+                                 precision="f64", seed=9)), z, (25, 15), 2
+    if what == "ksmt_f64_one_character":
+        Q = cases.q4()
+        base = cases.tree_hidden(Q, T=40, S=1, seed=4, mean_branch=0.5)
+        trees = [base, pb.PhyloTree(base.edge, base.edge_length * 1.2).with_states(base.states, segments=3)]
+        return (lambda: pb.Chain(capi.PM_V_KSMT, trees, np.asfortranarray(Q.copy()), np.full(4, 0.25), 4.0, 30,
+                                 prior=cases.PRIOR_KSMT, precision="f64", seed=11)), base, (30,), 4
     if what == "dic_ks_f64":
         Q = cases.q4()
         z = cases.tree_hidden(Q, T=50, S=5, seed=6, mean_branch=0.6)
@@ -49,7 +59,7 @@ def _case(what):
 
 
 @pytest.mark.parametrize("what", ["plain_f32_one_character", "bigtree_f32_records", "sparse_f64_gap_mode", "bf_f64", "ks_f64",
-                                  "ksmt_f64", "dic_ks_f64"])
+                                  "ksmt_f64", "dic_ks_f64", "bf_f64_one_character", "ksmt_f64_one_character"])
 def test_one_block_per_site_gives_the_rows_of_the_wide_kernels(what, monkeypatch):
     mk, z, runs, nd = _case(what)
 
