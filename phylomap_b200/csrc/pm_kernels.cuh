@@ -923,6 +923,43 @@ __device__ __forceinline__ int draw_node_state(const ChainParams<Real>& P, const
   return pick;
 }
 
+// The redraw of a tip of the hidden-rate samplers (ks / ksmt: the observed trait is the PARITY of the state, `code`): only
+// the two states a = 1 - code and b = a + 2 carry weight, so the draw is between two entries of the row of P_k.  The same
+// pick, bit for bit, as draw_node_state() with the 0/1 partial of tip_partial(): there the zero entries add nothing to
+// the running sums (c = ra, ra, ra + rb, ra + rb for code 1; 0, ra, ra, ra + rb for code 0), t = u (ra + rb) falls below ra
+// or not, and a t that rounding put on the total takes the last state with positive weight.
+template <typename Real>
+__device__ __forceinline__ int draw_parity_tip4(const ChainParams<Real>& P, const Real* sBs, const Real* sPow, int npow_s, int k, int ps,
+                                                int code, uint32_t word) {
+  Real w[4];
+  if (k < npow_s) VecIO<Real, 4>::load(sPow + (k * 4 + ps) * 4, 4, w);
+  else if (k < P.jcap) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) w[j] = P.ppow[(size_t)k * 16 + ps * 4 + j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) w[j] = (Real)(j == ps);
+    for (int r = 0; r < k; r++) matvec_t<Real, 4, false>(sBs, 4, w);
+  }
+  const Real ra = code ? w[0] : w[1], rb = code ? w[2] : w[3];
+  const Real tot = ra + rb;
+  if (!(tot > (Real)0) || !isfinite(tot)) { atomicOr(P.err_flag, tot > (Real)0 ? PM_DE_SAMPLE_NA : PM_DE_SAMPLE_ZERO); return 0; }
+  const Real t = u01_from_word<Real>(word) * tot;
+  const int a = 1 - code;
+  int pick = (t < ra) ? a : a + 2;
+  if (!(t < tot)) pick = (rb > (Real)0) ? a + 2 : a;
+  return pick;
+}
+// a redrawn tip: the two-state draw above for parity tips of a 4-state model, the general draw otherwise
+template <typename Real, int NS>
+__device__ __forceinline__ int draw_tip_state(const ChainParams<Real>& P, const Real* sBs, const Real* sPow, int npow_s, int k, int ps, int code,
+                                              bool parity, uint32_t word) {
+  if (NS == 4 && parity) return draw_parity_tip4<Real>(P, sBs, sPow, npow_s, k, ps, code, word);
+  Real pl[NS];
+  tip_partial<Real, NS>(code, NS, parity, pl);
+  return draw_node_state<Real, NS>(P, sBs, sPow, npow_s, k, ps, pl, word);
+}
+
 template <typename Real, int NS, int DEPTH>
 __device__ __forceinline__ void nodes_clade_block(const ChainParams<Real>& P, const uint32_t iter, const long long site0, const long long pl0) {
   constexpr int PB = NS * (int)sizeof(Real);  // bytes of one partial
@@ -1081,10 +1118,8 @@ __device__ __forceinline__ void nodes_clade_block(const ChainParams<Real>& P, co
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         if (4 * grp + q < ntip) {  // warp-uniform
-          Real pl[NS];
-          tip_partial<Real, NS>(L[q].cd, NS, parity, pl);
           const uint32_t word = q == 0 ? o[0] : q == 1 ? o[1] : q == 2 ? o[2] : o[3];
-          const int sn = draw_node_state<Real, NS>(P, sBs, sPow, npow_s, L[q].k, L[q].ps, pl, word);
+          const int sn = draw_tip_state<Real, NS>(P, sBs, sPow, npow_s, L[q].k, L[q].ps, L[q].cd, parity, word);
           if (active) nst[(long long)(4 * grp + q) * S] = (uint8_t)sn;
         }
       }

@@ -178,8 +178,7 @@ __global__ void __launch_bounds__(256, MINB) k_small_chain(ChainParams<Real> P, 
         const int ps = sState[en.y];
         const int k = (int)(sMeta[en.z] & 0xffffu) - 1;
         Real pl[NS];
-        if (en.x < T) tip_partial<Real, NS>(sTip[en.x], NS, parity, pl);
-        else VecIO<Real, NS>::load(sPL + (en.x - T) * NS, NS, pl);
+        if (en.x >= T) VecIO<Real, NS>::load(sPL + (en.x - T) * NS, NS, pl);
         // key: class (bits 30-31) | payload.  0: position i in the clade sequences -> block i >> 2, word i & 3;
         // 2: position i in the top list -> block 0x80000000 + i, word 0;  1: tip v -> block 0x40000000 + (v >> 2), word v & 3
         const uint32_t key = (uint32_t)en.w, cls = key >> 30, pay = key & 0x3fffffffu;
@@ -188,7 +187,8 @@ __global__ void __launch_bounds__(256, MINB) k_small_chain(ChainParams<Real> P, 
         uint32_t o[4];
         philox4x32_10_rk(ctr, kslot, iter, gsite, P.rng.rk, o);
         const uint32_t word = wsel == 0u ? o[0] : wsel == 1u ? o[1] : wsel == 2u ? o[2] : o[3];
-        const int sn = draw_node_state<Real, NS>(P, sBs, sPow, npow_s, k, ps, pl, word);
+        const int sn = en.x < T ? draw_tip_state<Real, NS>(P, sBs, sPow, npow_s, k, ps, sTip[en.x], parity, word)
+                                : draw_node_state<Real, NS>(P, sBs, sPow, npow_s, k, ps, pl, word);
         sState[en.x] = (uint8_t)sn;
       }
       __syncthreads();
