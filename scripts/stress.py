@@ -15,6 +15,7 @@ from phylomap_b200 import capi, synth
 ncfg = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 fails, done = [], 0
+nequiv = 0
 
 
 def caterpillar(T, mean_branch, r):
@@ -71,20 +72,38 @@ for c in range(ncfg):
             tree = make_tree(T, seed % 1000, mb, rng)
             st = synth.simulate_tip_states(tree, Q, pid, S, seed).numpy()
             z = tree.with_states(st[0].astype(np.int32) if S == 1 else st, segments=seg)
-        Qf = np.asfortranarray(Q.copy())
         tl = z.edge_length.sum()
-        if kind == "plain": out = pb.sumstatMCMC(z, Qf, pid, Om, N, precision=prec, seed=seed)
-        elif kind == "sparse": out = pb.SPARSEsumstatMCMC(z, Qf, pid, Om, N, precision=prec, seed=seed)
-        elif kind == "bigtree": out = pb.sumstatMCMC_bigtree(z, Qf, pid, Om, N, precision=prec, seed=seed)
-        elif kind == "bf": out = pb.sumstatMCMCbf(z, Qf, pid, Om, N, cases.PRIOR_BF, precision=prec, seed=seed)
-        elif kind == "dic2": out = pb.sumstatMCMC2sDICt(z, Qf, pid, Om, N, cases.PRIOR_BF, precision=prec, seed=seed)
-        elif kind == "ks": out = pb.sumstatMCMCks(z, Qf, pid, Om, N, cases.PRIOR_KS if n == 4 else np.array([1., 10, 2, 10, 20, 2]), precision=prec, seed=seed)
-        elif kind == "dicks": out = pb.sumstatMCMCksDICt(z, Qf, pid, Om, N, cases.PRIOR_KS, precision=prec, seed=seed)
-        else:
+        def call():
+          Qf = np.asfortranarray(Q.copy())
+          tl = z.edge_length.sum()
+          if kind == "plain": out = pb.sumstatMCMC(z, Qf, pid, Om, N, precision=prec, seed=seed)
+          elif kind == "sparse": out = pb.SPARSEsumstatMCMC(z, Qf, pid, Om, N, precision=prec, seed=seed)
+          elif kind == "bigtree": out = pb.sumstatMCMC_bigtree(z, Qf, pid, Om, N, precision=prec, seed=seed)
+          elif kind == "bf": out = pb.sumstatMCMCbf(z, Qf, pid, Om, N, cases.PRIOR_BF, precision=prec, seed=seed)
+          elif kind == "dic2": out = pb.sumstatMCMC2sDICt(z, Qf, pid, Om, N, cases.PRIOR_BF, precision=prec, seed=seed)
+          elif kind == "ks": out = pb.sumstatMCMCks(z, Qf, pid, Om, N, cases.PRIOR_KS if n == 4 else np.array([1., 10, 2, 10, 20, 2]), precision=prec, seed=seed)
+          elif kind == "dicks": out = pb.sumstatMCMCksDICt(z, Qf, pid, Om, N, cases.PRIOR_KS, precision=prec, seed=seed)
+          else:
             trees = [z, pb.PhyloTree(z.edge, z.edge_length * 1.3).with_states(z.states, segments=max(seg, 3))]
-            tl = None
             if kind == "mt": out = pb.sumstatMCMCmt(trees, Qf, pid, Om, N, cases.PRIOR_BF, precision=prec, seed=seed)
             else: out = pb.sumstatMCMCksmt(trees, Qf, pid, Om, N, cases.PRIOR_KSMT, precision=prec, seed=seed)
+          return out
+        if kind in ("mt", "ksmt"): tl = None
+        out = call()
+        # PM_STRESS_EQUIV=1: the one-block-per-site kernel (forced for any path length) against the 32-sites-per-warp kernels on
+        # the same configuration -- the same histories: counts identical, sums to the rounding of their summation order
+        if os.environ.get("PM_STRESS_EQUIV") and n in (2, 4) and (kind in ("plain", "sparse", "bigtree") or prec == "f64"):
+            os.environ["PHYLOMAP_B200_SMALL"] = "1"; os.environ["PHYLOMAP_B200_SMALL_WORK"] = "1e15"
+            a = call()
+            os.environ["PHYLOMAP_B200_SMALL"] = "0"
+            b = call()
+            del os.environ["PHYLOMAP_B200_SMALL"], os.environ["PHYLOMAP_B200_SMALL_WORK"]
+            if kind in ("plain", "sparse", "bigtree"):
+                assert np.array_equal(a[:, n:], b[:, n:]), "one-block-per-site kernel: counts differ from the wide kernels"
+                np.testing.assert_allclose(a[:, :n], b[:, :n], rtol=5e-6 if prec == "f32" else 1e-12)
+            else:
+                np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
+            nequiv += 1
         assert np.all(np.isfinite(out)), "non-finite output"
         if tl is not None:
             np.testing.assert_allclose(out[:, :n].sum(1), S * tl, rtol=3e-4 if prec == "f32" else 1e-9)
@@ -103,5 +122,5 @@ for c in range(ncfg):
             fails.append(desc); print("FAIL", json.dumps(desc), e.msg[:100], flush=True)
     except AssertionError as e:
         fails.append(desc); print("FAIL", json.dumps(desc), str(e)[:200].replace("\n", " "), flush=True)
-print("configs", ncfg, "ok", done, "failed", len(fails))
+print("configs", ncfg, "ok", done, "failed", len(fails), "compared with the other kernel set", nequiv)
 sys.exit(1 if fails else 0)
