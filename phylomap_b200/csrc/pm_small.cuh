@@ -126,6 +126,29 @@ __global__ void __launch_bounds__(256, MINB) k_small_chain(ChainParams<Real> P, 
     for (int j = 0; j < NS; j++) o[j] *= inv;
   };
 
+  // A tree with at most as many internal nodes / drawn nodes / branches as the block has threads (the reference's
+  // configs[0]: 99 / 98 / 198): every node and branch has a thread of its own, and its schedule entry stays in that
+  // thread's registers for the whole launch -- a level then costs a compare and a barrier besides the node's arithmetic,
+  // where the general loop reads the level's bounds and the entry again in every sweep (two thirds of a level's time).
+  const int n_up = T - 1, n_down = __ldg(out.down_off + out.n_down_levels);
+  // (only in the one-block-per-SM build: at the 128 registers of the two-per-SM build the entries would be spilled)
+  const bool own_up = MINB == 1 && n_up <= nthr, own_down = MINB == 1 && n_down <= nthr, own_br = MINB == 1 && E <= nthr;
+  int u_lv = -1, u_pn = 0, u_a = 0, u_ea = 0, u_b = 0, u_eb = 0;
+  if (own_up && tid < n_up) {
+    const int* en = P.up_entries + 5 * tid;
+    u_pn = __ldg(en); u_a = __ldg(en + 1); u_ea = __ldg(en + 2); u_b = __ldg(en + 3); u_eb = __ldg(en + 4);
+    for (int l = 0; l < P.n_up_levels; l++) if (tid >= __ldg(P.up_off + l)) u_lv = l;
+  }
+  int d_lv = -1;
+  int4 d_en = make_int4(0, 0, 0, 0);
+  if (own_down && tid < n_down) {
+    d_en = __ldg(out.down + tid);
+    for (int l = 0; l < out.n_down_levels; l++) if (tid >= __ldg(out.down_off + l)) d_lv = l;
+  }
+  int b_par = 0, b_chi = 0;
+  Real b_len = 0;
+  if (own_br && tid < E) { b_par = __ldg(P.e_parent + tid); b_chi = __ldg(P.e_child + tid); b_len = __ldg(P.e_len + tid); }
+
   for (int sw = 0; sw < nsweeps; sw++) {
     const uint32_t iter = iter0 + (uint32_t)sw;
     const int first = iter == 0u ? 1 : 0;
@@ -139,22 +162,31 @@ __global__ void __launch_bounds__(256, MINB) k_small_chain(ChainParams<Real> P, 
       if (out.prof && blockIdx.x == 0) { const long long t2 = clock64(); if (tid == 0) out.prof[slot] += t2 - tk; tk = t2; }
     };
     // ---- K1: pruning, level by level, one node per thread (makePLrcpp_bigtree :503-529) ----
-    for (int l = 0; l < P.n_up_levels; l++) {
-      const int beg = __ldg(P.up_off + l), end = __ldg(P.up_off + l + 1);
-      for (int idx = beg + tid; idx < end; idx += nthr) {
-        const int* en = P.up_entries + 5 * idx;
-        const int pn = __ldg(en), a = __ldg(en + 1), ea = __ldg(en + 2), b = __ldg(en + 3), eb = __ldg(en + 4);
-        const int ka = (int)(sMeta[ea] & 0xffffu) - 1, kb = (int)(sMeta[eb] & 0xffffu) - 1;
-        Real va[NS], vb[NS], o[NS];
-        int ca = -1, cb = -1;
-        if (a < T) ca = sTip[a]; else VecIO<Real, NS>::load(sPL + (a - T) * NS, NS, va);
-        if (b < T) cb = sTip[b]; else VecIO<Real, NS>::load(sPL + (b - T) * NS, NS, vb);
-        contribution(kb, cb, vb);
-        contribution(ka, ca, va);
-        product(va, vb, o);
-        VecIO<Real, NS>::store(sPL + (pn - T) * NS, NS, o);
+    auto prune_node = [&](int pn, int a, int ea, int b, int eb) {
+      const int ka = (int)(sMeta[ea] & 0xffffu) - 1, kb = (int)(sMeta[eb] & 0xffffu) - 1;
+      Real va[NS], vb[NS], o[NS];
+      int ca = -1, cb = -1;
+      if (a < T) ca = sTip[a]; else VecIO<Real, NS>::load(sPL + (a - T) * NS, NS, va);
+      if (b < T) cb = sTip[b]; else VecIO<Real, NS>::load(sPL + (b - T) * NS, NS, vb);
+      contribution(kb, cb, vb);
+      contribution(ka, ca, va);
+      product(va, vb, o);
+      VecIO<Real, NS>::store(sPL + (pn - T) * NS, NS, o);
+    };
+    if (own_up) {
+      for (int l = 0; l < P.n_up_levels; l++) {
+        if (u_lv == l) prune_node(u_pn, u_a, u_ea, u_b, u_eb);
+        __syncthreads();
       }
-      __syncthreads();
+    } else {
+      for (int l = 0; l < P.n_up_levels; l++) {
+        const int beg = __ldg(P.up_off + l), end = __ldg(P.up_off + l + 1);
+        for (int idx = beg + tid; idx < end; idx += nthr) {
+          const int* en = P.up_entries + 5 * idx;
+          prune_node(__ldg(en), __ldg(en + 1), __ldg(en + 2), __ldg(en + 3), __ldg(en + 4));
+        }
+        __syncthreads();
+      }
     }
 
     lap(0);
@@ -171,27 +203,34 @@ __global__ void __launch_bounds__(256, MINB) k_small_chain(ChainParams<Real> P, 
       if (gsite == 0u && !out.rows) out.root[sw] = s;
     }
     __syncthreads();
-    for (int l = 0; l < out.n_down_levels; l++) {
-      const int beg = __ldg(out.down_off + l), end = __ldg(out.down_off + l + 1);
-      for (int idx = beg + tid; idx < end; idx += nthr) {
-        const int4 en = __ldg(out.down + idx);  // v, parent, edge, key
-        const int ps = sState[en.y];
-        const int k = (int)(sMeta[en.z] & 0xffffu) - 1;
-        Real pl[NS];
-        if (en.x >= T) VecIO<Real, NS>::load(sPL + (en.x - T) * NS, NS, pl);
-        // key: class (bits 30-31) | payload.  0: position i in the clade sequences -> block i >> 2, word i & 3;
-        // 2: position i in the top list -> block 0x80000000 + i, word 0;  1: tip v -> block 0x40000000 + (v >> 2), word v & 3
-        const uint32_t key = (uint32_t)en.w, cls = key >> 30, pay = key & 0x3fffffffu;
-        const uint32_t ctr = cls == 2u ? key : (cls << 30) + (pay >> 2);
-        const uint32_t wsel = cls == 2u ? 0u : (pay & 3u);
-        uint32_t o[4];
-        philox4x32_10_rk(ctr, kslot, iter, gsite, P.rng.rk, o);
-        const uint32_t word = wsel == 0u ? o[0] : wsel == 1u ? o[1] : wsel == 2u ? o[2] : o[3];
-        const int sn = en.x < T ? draw_tip_state<Real, NS>(P, sBs, sPow, npow_s, k, ps, sTip[en.x], parity, word)
-                                : draw_node_state<Real, NS>(P, sBs, sPow, npow_s, k, ps, pl, word);
-        sState[en.x] = (uint8_t)sn;
+    auto draw_node = [&](const int4 en) {  // v, parent, edge, key
+      const int ps = sState[en.y];
+      const int k = (int)(sMeta[en.z] & 0xffffu) - 1;
+      Real pl[NS];
+      if (en.x >= T) VecIO<Real, NS>::load(sPL + (en.x - T) * NS, NS, pl);
+      // key: class (bits 30-31) | payload.  0: position i in the clade sequences -> block i >> 2, word i & 3;
+      // 2: position i in the top list -> block 0x80000000 + i, word 0;  1: tip v -> block 0x40000000 + (v >> 2), word v & 3
+      const uint32_t key = (uint32_t)en.w, cls = key >> 30, pay = key & 0x3fffffffu;
+      const uint32_t ctr = cls == 2u ? key : (cls << 30) + (pay >> 2);
+      const uint32_t wsel = cls == 2u ? 0u : (pay & 3u);
+      uint32_t o[4];
+      philox4x32_10_rk(ctr, kslot, iter, gsite, P.rng.rk, o);
+      const uint32_t word = wsel == 0u ? o[0] : wsel == 1u ? o[1] : wsel == 2u ? o[2] : o[3];
+      const int sn = en.x < T ? draw_tip_state<Real, NS>(P, sBs, sPow, npow_s, k, ps, sTip[en.x], parity, word)
+                              : draw_node_state<Real, NS>(P, sBs, sPow, npow_s, k, ps, pl, word);
+      sState[en.x] = (uint8_t)sn;
+    };
+    if (own_down) {
+      for (int l = 0; l < out.n_down_levels; l++) {
+        if (d_lv == l) draw_node(d_en);
+        __syncthreads();
       }
-      __syncthreads();
+    } else {
+      for (int l = 0; l < out.n_down_levels; l++) {
+        const int beg = __ldg(out.down_off + l), end = __ldg(out.down_off + l + 1);
+        for (int idx = beg + tid; idx < end; idx += nthr) draw_node(__ldg(out.down + idx));
+        __syncthreads();
+      }
     }
 
     lap(1);
@@ -200,8 +239,8 @@ __global__ void __launch_bounds__(256, MINB) k_small_chain(ChainParams<Real> P, 
     PathWorker<Real, NS> pw(P, iter, first, n, sB, sBs, sPow, npow_s, s_cnt, s_dw, s_rate_old, s_rate_new);
     for (int e = tid; e < E; e += nthr) {
       const uint32_t mt = sMeta[e];
-      const int ps = sState[__ldg(P.e_parent + e)], cs = sState[__ldg(P.e_child + e)];
-      const Real Le = __ldg(P.e_len + e);
+      const int ps = sState[own_br ? b_par : __ldg(P.e_parent + e)], cs = sState[own_br ? b_chi : __ldg(P.e_child + e)];
+      const Real Le = own_br ? b_len : __ldg(P.e_len + e);
       const int m = (int)(mt & 0xffffu);
       const uint32_t q = mt >> 16;
       const bool two = (m == 2) && (ps != cs);
