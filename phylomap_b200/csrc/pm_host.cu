@@ -307,9 +307,10 @@ struct TreeDev {
   bool small_ok = false;
   bool small_two = false;    // more sites than SMs: two blocks per SM (128 registers) instead of one
   int small_chunks = 0;      // record chunks (rows of rec_cursor)
-  DevBuf small_down, small_part, small_cnt, small_root, small_prof;
+  DevBuf small_down, small_part, small_cnt, small_root, small_prof, small_border;
   DevBuf tip_stage;          // staging of the tip-state upload (create() only)
   int small_cap = 0;         // sweeps the output buffers hold
+  int small_order_n = 0;     // entries of small_border
   long long rec_groups = 0;
   DevBuf e_len_d, TP, ll_partial;  // DIC samplers: branch lengths in FP64, exp(Q t_e) per branch, block partials of log p(y|Q)
   std::vector<int> cap_off_h;
@@ -482,6 +483,7 @@ struct ChainT : pm_chain {
     pm::SmallOut o;
     o.down = reinterpret_cast<const int4*>(t.small_down.p); o.down_off = t.down_off.template as<int>();
     o.n_down_levels = (int)t.sch.down_off.size() - 1; o.n_chunks = t.small_chunks;
+    o.br_order = t.small_border.template as<int>(); o.n_order = t.small_order_n;
     o.part = nullptr; o.cnt = nullptr; o.root = nullptr; o.rows = nullptr; o.row_stride = WR; o.err_slot = W;
     o.prof = nullptr;
     if (getenv("PHYLOMAP_B200_SMALL_PROF")) {
@@ -979,6 +981,21 @@ struct ChainT : pm_chain {
             d4[(size_t)4 * i] = en[0]; d4[(size_t)4 * i + 1] = en[1]; d4[(size_t)4 * i + 2] = en[2]; d4[(size_t)4 * i + 3] = (int)key[en[0]];
           }
           upload(t->small_down, d4, stream);
+          // Which thread takes which branch.  A warp runs the general item routine in lockstep: it takes as long as its
+          // longest path, plus a share for every other shape among its items.  Up to 256 branches (one per thread): the
+          // branches sorted by decreasing length are DEALT over the 8 warps, so that every warp gets one of the longest,
+          // one of the next eight, ... (measured on configs[0]: all long branches in one warp 30 300 cycles for the path
+          // phase, edge order 26 000).  Larger trees: decreasing length (warps of similar paths: throughput).
+          std::vector<int> sorted(E);
+          for (int e = 0; e < E; e++) sorted[e] = e;
+          std::stable_sort(sorted.begin(), sorted.end(), [&](int x, int y) { return elen[x] > elen[y]; });
+          std::vector<int> border;
+          if (E <= 256) {
+            border.assign(256, -1);
+            for (int k = 0; k < E; k++) border[(size_t)(k % 8) * 32 + k / 8] = sorted[k];   // warp k % 8, lane k / 8
+          } else border = sorted;
+          t->small_order_n = (int)border.size();
+          upload(t->small_border, border, stream);
         }
       }
       upload(t->down_entries, t->sch.down_entries, stream);

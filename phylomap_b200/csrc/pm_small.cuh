@@ -25,6 +25,7 @@ struct SmallOut {
   const int4* down;          // top-down draw list: v, parent, edge, key -- grouped by depth (down_off), tips last at their depth
   const int* down_off; int n_down_levels;
   int n_chunks;              // record chunks (rec_cursor rows)
+  const int* br_order; int n_order;  // thread i takes branch br_order[i] (-1: none), i < n_order: see pm_host.cu (long branches dealt over the warps)
   // ONE site: the block writes the rows itself, in k_reduce's layout [R(n) | N(n*n) | root | .. | error flag] (device
   // memory or mapped host memory: a rate-updating sampler reads the row right after the launch); nullptr: part / cnt / root
   double* rows; int row_stride, err_slot;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256, MINB) k_small_chain(ChainParams<Real> P, 
   // where the general loop reads the level's bounds and the entry again in every sweep (two thirds of a level's time).
   const int n_up = T - 1, n_down = __ldg(out.down_off + out.n_down_levels);
   // (only in the one-block-per-SM build: at the 128 registers of the two-per-SM build the entries would be spilled)
-  const bool own_up = MINB == 1 && n_up <= nthr, own_down = MINB == 1 && n_down <= nthr, own_br = MINB == 1 && E <= nthr;
+  const bool own_up = MINB == 1 && n_up <= nthr, own_down = MINB == 1 && n_down <= nthr, own_br = MINB == 1 && out.n_order <= nthr;
   int u_lv = -1, u_pn = 0, u_a = 0, u_ea = 0, u_b = 0, u_eb = 0;
   if (own_up && tid < n_up) {
     const int* en = P.up_entries + 5 * tid;
@@ -147,7 +148,11 @@ __global__ void __launch_bounds__(256, MINB) k_small_chain(ChainParams<Real> P, 
   }
   int b_par = 0, b_chi = 0;
   Real b_len = 0;
-  if (own_br && tid < E) { b_par = __ldg(P.e_parent + tid); b_chi = __ldg(P.e_child + tid); b_len = __ldg(P.e_len + tid); }
+  int b_e = -1;
+  if (own_br && tid < out.n_order) {
+    b_e = __ldg(out.br_order + tid);
+    if (b_e >= 0) { b_par = __ldg(P.e_parent + b_e); b_chi = __ldg(P.e_child + b_e); b_len = __ldg(P.e_len + b_e); }
+  }
 
   for (int sw = 0; sw < nsweeps; sw++) {
     const uint32_t iter = iter0 + (uint32_t)sw;
@@ -237,7 +242,9 @@ __global__ void __launch_bounds__(256, MINB) k_small_chain(ChainParams<Real> P, 
     // ---- K3: one branch per thread.  At most one jump point and count mode: the body of k_paths_easy; everything else:
     // the general item routine of k_paths_hard (which also reproduces what its short routine computes) ----
     PathWorker<Real, NS> pw(P, iter, first, n, sB, sBs, sPow, npow_s, s_cnt, s_dw, s_rate_old, s_rate_new);
-    for (int e = tid; e < E; e += nthr) {
+    for (int i = tid; i < out.n_order; i += nthr) {
+      const int e = own_br ? b_e : __ldg(out.br_order + i);
+      if (e < 0) continue;
       const uint32_t mt = sMeta[e];
       const int ps = sState[own_br ? b_par : __ldg(P.e_parent + e)], cs = sState[own_br ? b_chi : __ldg(P.e_child + e)];
       const Real Le = own_br ? b_len : __ldg(P.e_len + e);
